@@ -1,0 +1,369 @@
+"""ctypes binding of include/ctopprm_b200.h.  No compute happens here."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+LAYOUT_PLAIN, LAYOUT_CELL8, LAYOUT_TEX, LAYOUT_BRICK = 1, 2, 4, 8
+EDGE_NODES, EDGE_GUARDS = 0, 1
+ERR_NEED_CANDIDATES = -4
+
+_lib = None
+
+
+class CtpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ctopprm_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "lib", "libctopprm_b200.so")
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_D = C.c_double
+_I = C.c_int
+
+# name -> argtypes (every function returns int except ctp_last_error)
+_SIGS = {
+    "ctp_version": [],
+    "ctp_device_count": [_P],
+    "ctp_map_create": [_P, _I, _P, _P, _I, _I, _P],
+    "ctp_map_create_f64": [_P, _I, _P, _P, _I, _I, _P],
+    "ctp_map_destroy": [_P],
+    "ctp_map_set_layout": [_P, _I],
+    "ctp_map_info": [_P, _P],
+    "ctp_reserve": [_P, _I64, _I64, _I64, _I],
+    "ctp_lookup_counter_read": [_P, _P, _P, _I],
+    "ctp_clearance": [_P, _P, _I64, _P],
+    "ctp_clearance_dev": [_P, _P, _I64, _P, _P],
+    "ctp_in_collision": [_P, _P, _I64, _D, _P],
+    "ctp_in_collision_dev": [_P, _P, _I64, _D, _P, _P],
+    "ctp_gradient": [_P, _P, _I64, _P, _P],
+    "ctp_gradient_dev": [_P, _P, _I64, _P, _P, _P],
+    "ctp_edge_check": [_P, _P, _P, _I64, _D, _D, _I, _I, _P, _P, _P, _P],
+    "ctp_edge_check_dev": [_P, _P, _P, _I64, _D, _D, _I, _I, _P, _P, _P, _P, _P],
+    "ctp_edge_check_indexed": [_P, _P, _I64, _P, _P, _I64, _D, _D, _I, _P, _P, _P],
+    "ctp_edge_check_indexed_dev": [_P, _P, _I64, _P, _P, _I64, _D, _D, _I, _P, _P, _P, _P],
+    "ctp_sample_reject": [_P, _P, _P, _P, _I64, _I64, _D, _I64, _P, _P, _P, _P],
+    "ctp_sample_reject_dev": [_P, _P, _P, _P, _I64, _I64, _D, _I64, _P, _P, _P, _P, _P],
+    "ctp_sample_ellipsoid": [_P, _P, _P, _I64, _I64, _D, _I, C.c_uint64, _P],
+    "ctp_sample_ellipsoid_dev": [_P, _P, _P, _I64, _I64, _D, _I, C.c_uint64, _P, _P],
+    "ctp_knn": [_P, _P, _I64, _I64, _I, _P, _P],
+    "ctp_knn_dev": [_P, _P, _I64, _I64, _I, _P, _P, _P],
+    "ctp_build_prm": [_P, _P, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
+    "ctp_build_prm_dev": [_P, _P, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P, _P],
+    "ctp_sample_multiple": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
+    "ctp_sample_path": [_P, _P, _P, _P, _P, _I64, _P, _P, _P],
+    "ctp_deformable": [_P, _P, _P, _P, _I64, _P, _P, _P, _I64, _D, _D, _P],
+    "ctp_shorten_path": [_P, _P, _P, _P, _I64, _I, _D, _D, C.c_int32, _P, _P, _P, _P, _P],
+}
+
+
+def lib():
+    """Load libctopprm_b200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "-- there is no CPU fallback for the CTopPRM hot path")
+        L = C.CDLL(path)
+        L.ctp_last_error.restype = C.c_char_p
+        L.ctp_last_error.argtypes = []
+        for name, args in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = C.c_int
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return ["ctp_last_error"] + list(_SIGS)
+
+
+def _check(rc, allow=()):
+    if rc != 0 and rc not in allow:
+        raise CtpError(rc, lib().ctp_last_error().decode())
+    return rc
+
+
+def _np(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+def _ptr(a):
+    """numpy array / torch tensor / int / None -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return None
+    if isinstance(stream, int):
+        return C.c_void_p(stream)
+    return C.c_void_p(stream.cuda_stream)
+
+
+class DeviceMap:
+    """ESDF resident on one GPU.  Mirrors ESDFMap/BaseMap's batchable queries
+    (src/esdf_map.cpp, src/base_map.cpp); numpy in / numpy out uses the host-pointer ABI,
+    the ``*_dev`` methods take torch CUDA tensors and a stream."""
+
+    def __init__(self, vox, centroid, extents, device=0, layouts=LAYOUT_PLAIN):
+        L = lib()
+        vox = np.asarray(vox)
+        if vox.ndim != 3 or not (vox.shape[0] == vox.shape[1] == vox.shape[2]):
+            raise ValueError("voxels must be a cubic (N,N,N) array (src/esdf_map.cpp:24)")
+        self.n = int(vox.shape[0])
+        self.centroid = _np(centroid, np.float64)
+        self.extents = _np(extents, np.float64)
+        h = C.c_void_p()
+        if vox.dtype == np.float64:
+            v = np.ascontiguousarray(vox)
+            _check(L.ctp_map_create_f64(_ptr(v), self.n, _ptr(self.centroid), _ptr(self.extents), device, layouts, C.byref(h)))
+        else:
+            v = _np(vox, np.float32)
+            _check(L.ctp_map_create(_ptr(v), self.n, _ptr(self.centroid), _ptr(self.extents), device, layouts, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    @classmethod
+    def load(cls, filename, device=0, layouts=LAYOUT_PLAIN):
+        """ESDFMap::load (src/esdf_map.cpp:6-72): four concatenated NPY records."""
+        from .synth import read_map
+        if not os.path.exists(filename):
+            raise RuntimeError("npy_load: Unable to open file " + filename)  # src/esdf_map.cpp:11-12
+        vox, c, e, _ = read_map(filename)
+        return cls(vox, c, e, device=device, layouts=layouts)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ctp_map_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- bookkeeping ---------------------------------------------------------------------
+    def info(self):
+        a = np.zeros(10)
+        _check(lib().ctp_map_info(self._h, _ptr(a)))
+        return a
+
+    def get_min_pos(self):
+        return self.info()[0:3]
+
+    def get_max_pos(self):
+        return self.info()[3:6]
+
+    def set_layout(self, layout):
+        _check(lib().ctp_map_set_layout(self._h, layout))
+
+    def reserve(self, q, n, m, k=13):
+        _check(lib().ctp_reserve(self._h, q, n, m, k))
+
+    def read_lookups(self, stream=None, reset=True):
+        v = C.c_uint64(0)
+        _check(lib().ctp_lookup_counter_read(self._h, _stream_ptr(stream), C.byref(v), int(reset)))
+        return v.value
+
+    # -- host-pointer API ----------------------------------------------------------------
+    def clearance(self, xyz):
+        xyz = _np(xyz, np.float64).reshape(-1, 3)
+        out = np.empty(len(xyz))
+        _check(lib().ctp_clearance(self._h, _ptr(xyz), len(xyz), _ptr(out)))
+        return out
+
+    def in_collision(self, xyz, clr):
+        xyz = _np(xyz, np.float64).reshape(-1, 3)
+        out = np.empty(len(xyz), dtype=np.uint8)
+        _check(lib().ctp_in_collision(self._h, _ptr(xyz), len(xyz), clr, _ptr(out)))
+        return out.astype(bool)
+
+    def gradient(self, xyz):
+        xyz = _np(xyz, np.float64).reshape(-1, 3)
+        g = np.empty_like(xyz)
+        c = np.empty_like(xyz)
+        _check(lib().ctp_gradient(self._h, _ptr(xyz), len(xyz), _ptr(g), _ptr(c)))
+        return g, c
+
+    def edge_check(self, a, b, clr, cdc, mode=EDGE_NODES, group=0):
+        a = _np(a, np.float64).reshape(-1, 3)
+        b = _np(b, np.float64).reshape(-1, 3)
+        m = len(a)
+        free = np.empty(m, dtype=np.uint8)
+        hit = np.empty((m, 3))
+        hit_idx = np.empty(m, dtype=np.int32)
+        lookups = np.empty(m, dtype=np.int32)
+        _check(lib().ctp_edge_check(self._h, _ptr(a), _ptr(b), m, clr, cdc, mode, group, _ptr(free), _ptr(hit),
+                                    _ptr(hit_idx), _ptr(lookups)))
+        return free.astype(bool), hit, hit_idx, lookups
+
+    def edge_check_indexed(self, nodes, frm, to, clr, cdc, group=0):
+        nodes = _np(nodes, np.float64).reshape(-1, 3)
+        frm = _np(frm, np.int32)
+        to = _np(to, np.int32)
+        m = len(frm)
+        free = np.empty(m, dtype=np.uint8)
+        hit_idx = np.empty(m, dtype=np.int32)
+        lookups = np.empty(m, dtype=np.int32)
+        _check(lib().ctp_edge_check_indexed(self._h, _ptr(nodes), len(nodes), _ptr(frm), _ptr(to), m, clr, cdc, group,
+                                            _ptr(free), _ptr(hit_idx), _ptr(lookups)))
+        return free.astype(bool), hit_idx, lookups
+
+    def sample_reject(self, start, goal, cand, clr, n, allow_short=False):
+        start = _np(start, np.float64).reshape(-1, 3)
+        goal = _np(goal, np.float64).reshape(-1, 3)
+        q = len(start)
+        cand = _np(cand, np.float64).reshape(q, -1, 3)
+        m = cand.shape[1]
+        nodes = np.empty((q, n, 3))
+        n_filled = np.empty(q, dtype=np.int32)
+        n_used = np.empty(q, dtype=np.int32)
+        accept = np.empty((q, m), dtype=np.uint8)
+        _check(lib().ctp_sample_reject(self._h, _ptr(start), _ptr(goal), _ptr(cand), q, m, clr, n, _ptr(nodes),
+                                       _ptr(n_filled), _ptr(n_used), _ptr(accept)),
+               allow=(ERR_NEED_CANDIDATES,) if allow_short else ())
+        return nodes, n_filled, n_used, accept.astype(bool)
+
+    def sample_ellipsoid(self, start, goal, m, ratio, planar, seed):
+        start = _np(start, np.float64).reshape(-1, 3)
+        goal = _np(goal, np.float64).reshape(-1, 3)
+        q = len(start)
+        cand = np.empty((q, m, 3))
+        _check(lib().ctp_sample_ellipsoid(self._h, _ptr(start), _ptr(goal), q, m, ratio, int(planar), seed, _ptr(cand)))
+        return cand
+
+    def knn(self, nodes, k=13):
+        nodes = _np(nodes, np.float64)
+        if nodes.ndim == 2:
+            nodes = nodes[None]
+        q, n, _ = nodes.shape
+        idx = np.empty((q, n, k), dtype=np.int32)
+        d2 = np.empty((q, n, k), dtype=np.float32)
+        _check(lib().ctp_knn(self._h, _ptr(nodes), q, n, k, _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    def build_prm(self, nodes, clr, cdc, k=13):
+        nodes = _np(nodes, np.float64)
+        if nodes.ndim == 2:
+            nodes = nodes[None]
+        q, n, _ = nodes.shape
+        cap = 2 * q * n * k
+        nbr = np.empty((q, n, k), dtype=np.int32)
+        dfree = np.empty((q, n, k), dtype=np.uint8)
+        row_ptr = np.empty((q, n + 1), dtype=np.int32)
+        col = np.empty(cap, dtype=np.int32)
+        w = np.empty(cap)
+        off = np.empty(q + 1, dtype=np.int64)
+        _check(lib().ctp_build_prm(self._h, _ptr(nodes), q, n, k, clr, cdc, _ptr(nbr), _ptr(dfree), _ptr(row_ptr),
+                                   _ptr(col), _ptr(w), cap, _ptr(off)))
+        nnz = int(off[q])
+        return dict(nbr=nbr, directed_free=dfree.astype(bool), row_ptr=row_ptr, col=col[:nnz], w=w[:nnz], nnz_off=off)
+
+    def sample_multiple(self, start, goal, cand, n, clr, cdc, k=13, out=None):
+        """TopologicalPRMClustering::sampleMultiple from host candidates to host CSR."""
+        start = _np(start, np.float64).reshape(-1, 3)
+        goal = _np(goal, np.float64).reshape(-1, 3)
+        q = len(start)
+        cand = _np(cand, np.float64).reshape(q, -1, 3)
+        m = cand.shape[1]
+        cap = 2 * q * n * k
+        if out is None:
+            out = dict(nodes=np.empty((q, n, 3)), n_filled=np.empty(q, dtype=np.int32),
+                       row_ptr=np.empty((q, n + 1), dtype=np.int32), col=np.empty(cap, dtype=np.int32),
+                       w=np.empty(cap), nnz_off=np.empty(q + 1, dtype=np.int64))
+        _check(lib().ctp_sample_multiple(self._h, _ptr(start), _ptr(goal), _ptr(cand), q, m, n, k, clr, cdc,
+                                         _ptr(out["nodes"]), _ptr(out["n_filled"]), _ptr(out["row_ptr"]),
+                                         _ptr(out["col"]), _ptr(out["w"]), cap, _ptr(out["nnz_off"])))
+        return out
+
+    @staticmethod
+    def _pack_polylines(paths):
+        off = np.zeros(len(paths) + 1, dtype=np.int32)
+        for i, p in enumerate(paths):
+            off[i + 1] = off[i] + len(p)
+        pts = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in paths]))
+        return pts, off
+
+    def sample_path(self, paths, lengths, num_samples):
+        pts, off = self._pack_polylines(paths)
+        lengths = _np(lengths, np.float64)
+        ns = _np(num_samples, np.float64)
+        cnt = len(paths)
+        oo = np.zeros(cnt + 1, dtype=np.int64)
+        oo[1:] = np.cumsum(ns.astype(np.int64))
+        out = np.empty((int(oo[-1]), 3))
+        st = np.empty(cnt, dtype=np.int32)
+        _check(lib().ctp_sample_path(self._h, _ptr(pts), _ptr(off), _ptr(lengths), _ptr(ns), cnt, _ptr(out), _ptr(oo), _ptr(st)))
+        return [out[oo[i]:oo[i + 1]] for i in range(cnt)], st
+
+    def deformable(self, paths, lengths, ia, ib, num_check, clr, cdc):
+        pts, off = self._pack_polylines(paths)
+        lengths = _np(lengths, np.float64)
+        ia = _np(ia, np.int32)
+        ib = _np(ib, np.int32)
+        nc = _np(num_check, np.float64)
+        out = np.empty(len(ia), dtype=np.uint8)
+        _check(lib().ctp_deformable(self._h, _ptr(pts), _ptr(off), _ptr(lengths), len(paths), _ptr(ia), _ptr(ib),
+                                    _ptr(nc), len(ia), clr, cdc, _ptr(out)))
+        return out
+
+    def shorten_path(self, paths, lengths, forward, clr, cdc, cap=None):
+        pts, off = self._pack_polylines(paths)
+        lengths = _np(lengths, np.float64)
+        cnt = len(paths)
+        if cap is None:
+            cap = int(max(len(p) for p in paths) + 64)
+        out = np.empty((cnt, cap, 3))
+        origin = np.empty((cnt, cap), dtype=np.int32)
+        out_n = np.empty(cnt, dtype=np.int32)
+        out_len = np.empty(cnt)
+        st = np.empty(cnt, dtype=np.int32)
+        _check(lib().ctp_shorten_path(self._h, _ptr(pts), _ptr(off), _ptr(lengths), cnt, int(forward), clr, cdc, cap,
+                                      _ptr(out), _ptr(origin), _ptr(out_n), _ptr(out_len), _ptr(st)))
+        return [out[i, :out_n[i]] for i in range(cnt)], [origin[i, :out_n[i]] for i in range(cnt)], out_len, st
+
+    # -- device-pointer API (torch CUDA tensors) -----------------------------------------
+    def clearance_dev(self, xyz, out, stream=None):
+        _check(lib().ctp_clearance_dev(self._h, _ptr(xyz), xyz.numel() // 3, _ptr(out), _stream_ptr(stream)))
+
+    def edge_check_dev(self, a, b, clr, cdc, free, mode=EDGE_NODES, group=0, hit=None, hit_idx=None, lookups=None,
+                       stream=None):
+        _check(lib().ctp_edge_check_dev(self._h, _ptr(a), _ptr(b), a.numel() // 3, clr, cdc, mode, group, _ptr(free),
+                                        _ptr(hit), _ptr(hit_idx), _ptr(lookups), _stream_ptr(stream)))
+
+    def sample_reject_dev(self, start, goal, cand, q, m, clr, n, nodes, n_filled, n_used, accept=None, stream=None):
+        _check(lib().ctp_sample_reject_dev(self._h, _ptr(start), _ptr(goal), _ptr(cand), q, m, clr, n, _ptr(nodes),
+                                           _ptr(n_filled), _ptr(n_used), _ptr(accept), _stream_ptr(stream)))
+
+    def sample_ellipsoid_dev(self, start, goal, q, m, ratio, planar, seed, cand, stream=None):
+        _check(lib().ctp_sample_ellipsoid_dev(self._h, _ptr(start), _ptr(goal), q, m, ratio, int(planar), seed,
+                                              _ptr(cand), _stream_ptr(stream)))
+
+    def knn_dev(self, nodes, q, n, k, idx, d2=None, stream=None):
+        _check(lib().ctp_knn_dev(self._h, _ptr(nodes), q, n, k, _ptr(idx), _ptr(d2), _stream_ptr(stream)))
+
+    def build_prm_dev(self, nodes, q, n, k, clr, cdc, row_ptr, col, w, cap, nnz_off, nbr=None, directed_free=None,
+                      stream=None):
+        _check(lib().ctp_build_prm_dev(self._h, _ptr(nodes), q, n, k, clr, cdc, _ptr(nbr), _ptr(directed_free),
+                                       _ptr(row_ptr), _ptr(col), _ptr(w), cap, _ptr(nnz_off), _stream_ptr(stream)))

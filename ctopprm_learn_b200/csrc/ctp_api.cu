@@ -1,0 +1,811 @@
+// ctp_api.cu -- C ABI of libctopprm_b200.so (see include/ctopprm_b200.h).
+// Host-side plumbing only: handle, device layouts, scratch arenas, kernel dispatch.
+#include "../../include/ctopprm_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "ctp_device.cuh"
+#include "ctp_paths.cuh"
+#include "ctp_prm.cuh"
+
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(e_ == cudaErrorMemoryAllocation ? CTP_ERR_NOMEM : CTP_ERR_CUDA,         \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKR(call)               \
+  do {                          \
+    int r_ = (call);            \
+    if (r_ != CTP_OK) return r_; \
+  } while (0)
+#define REQUIRE(cond, msg) \
+  do {                     \
+    if (!(cond)) return fail(CTP_ERR_INVALID, "%s: %s", __func__, msg); \
+  } while (0)
+
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, used = 0;
+};
+
+struct ctp_map {
+  int device = 0;
+  int n = 0;
+  int layouts = 0, active = CTP_L_PLAIN;
+  MapDev dev{};
+  float *d_plain = nullptr, *d_cell8 = nullptr, *d_brick = nullptr;
+  cudaArray_t arr = nullptr;
+  cudaTextureObject_t tex = 0;
+  Arena ws;  // scratch of the _dev entry points
+  Arena io;  // device staging of the host-pointer entry points
+  unsigned long long *d_lookups = nullptr;
+  int sm_count = 148;
+  size_t map_bytes = 0;
+};
+
+static int arena_reserve(Arena &a, size_t bytes) {
+  if (bytes <= a.cap) return CTP_OK;
+  CK(cudaDeviceSynchronize());  // nothing may still be using the old block
+  if (a.base) CK(cudaFree(a.base));
+  a.base = nullptr;
+  a.cap = 0;
+  size_t want = bytes + bytes / 4 + (1 << 20);
+  CK(cudaMalloc(&a.base, want));
+  a.cap = want;
+  return CTP_OK;
+}
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+template <typename T> static T *arena_take(Arena &a, size_t count) {
+  T *p = reinterpret_cast<T *>(a.base + a.used);
+  a.used += align_up(count * sizeof(T));
+  return p;
+}
+
+extern "C" const char *ctp_last_error(void) { return g_err; }
+extern "C" int ctp_version(void) { return 100; }
+extern "C" int ctp_device_count(int *count) {
+  REQUIRE(count, "null");
+  CK(cudaGetDeviceCount(count));
+  return CTP_OK;
+}
+
+// ---------------------------------- map handle --------------------------------------------
+static int map_build_layouts(ctp_map *m) {
+  const int n = m->n;
+  if (m->layouts & CTP_L_CELL8) {
+    const size_t n1 = (size_t)n - 1, bytes = n1 * n1 * n1 * 32;
+    CK(cudaMalloc(&m->d_cell8, bytes));
+    m->map_bytes += bytes;
+    k_build_cell8<<<m->sm_count * 8, 256>>>(m->d_plain, n, m->d_cell8);
+    CK(cudaGetLastError());
+  }
+  if (m->layouts & CTP_L_BRICK) {
+    const int nb = (n + 3) / 4;
+    const size_t bytes = (size_t)nb * nb * nb * 256;
+    CK(cudaMalloc(&m->d_brick, bytes));
+    m->map_bytes += bytes;
+    k_build_brick<<<m->sm_count * 8, 256>>>(m->d_plain, n, nb, m->d_brick);
+    CK(cudaGetLastError());
+  }
+  if (m->layouts & CTP_L_TEX) {
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+    cudaExtent ext = make_cudaExtent((size_t)n, (size_t)n, (size_t)n);  // width=z, height=y, layers=x
+    CK(cudaMalloc3DArray(&m->arr, &fd, ext, cudaArrayLayered | cudaArrayTextureGather));
+    m->map_bytes += (size_t)n * n * n * 4;
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof cp);
+    cp.srcPtr = make_cudaPitchedPtr(m->d_plain, (size_t)n * sizeof(float), (size_t)n, (size_t)n);
+    cp.dstArray = m->arr;
+    cp.extent = ext;
+    cp.kind = cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpy3D(&cp));
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof rd);
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = m->arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    CK(cudaCreateTextureObject(&m->tex, &rd, &td, nullptr));
+  }
+  CK(cudaDeviceSynchronize());
+  return CTP_OK;
+}
+
+static void map_fill_params(ctp_map *m, const double c[3], const double e[3]) {
+  MapDev &d = m->dev;
+  const double N = (double)m->n;                       // src/esdf_map.cpp:24
+  const double max_e = fmax(fmax(e[0], e[1]), e[2]);   // src/esdf_map.cpp:27
+  d.cx = c[0]; d.cy = c[1]; d.cz = c[2];
+  d.lox = c[0] - e[0] / 2; d.loy = c[1] - e[1] / 2; d.loz = c[2] - e[2] / 2;  // :75
+  d.hix = c[0] + e[0] / 2; d.hiy = c[1] + e[1] / 2; d.hiz = c[2] + e[2] / 2;  // :76
+  d.s1 = 2.0 / max_e;
+  d.s2 = N / 2.0;
+  d.nm1 = N - 1.0;
+  d.nd = N;
+  d.dp = max_e / (N - 1.0);                            // :124
+  d.mex = c[0] - 1.0 * max_e / 2.0;                    // :125
+  d.mey = c[1] - 1.0 * max_e / 2.0;
+  d.mez = c[2] - 1.0 * max_e / 2.0;
+  d.n = m->n;
+  d.nb = (m->n + 3) / 4;
+  d.plain = m->d_plain;
+  d.cell8 = m->d_cell8;
+  d.brick = m->d_brick;
+  d.tex = m->tex;
+}
+
+static int pick_active(int layouts) {
+  if (layouts & CTP_L_TEX) return CTP_L_TEX;
+  if (layouts & CTP_L_CELL8) return CTP_L_CELL8;
+  if (layouts & CTP_L_BRICK) return CTP_L_BRICK;
+  return CTP_L_PLAIN;
+}
+
+static int map_create_common(const void *vox, bool is_f64, int n, const double c[3], const double e[3],
+                             int device, int layouts, ctp_map **out) {
+  REQUIRE(vox && c && e && out, "null argument");
+  REQUIRE(n >= 2 && n <= 2048, "voxels per axis must be in [2, 2048]");
+  REQUIRE((layouts & ~15) == 0, "unknown layout bits");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+  CK(cudaSetDevice(device));
+  ctp_map *m = new (std::nothrow) ctp_map();
+  if (!m) return fail(CTP_ERR_NOMEM, "host allocation failed");
+  m->device = device;
+  m->n = n;
+  m->layouts = layouts | CTP_L_PLAIN;
+  cudaDeviceProp prop;
+  cudaError_t pe = cudaGetDeviceProperties(&prop, device);
+  if (pe == cudaSuccess) m->sm_count = prop.multiProcessorCount;
+  const size_t cnt = (size_t)n * n * n;
+  int rc = CTP_OK;
+  auto body = [&]() -> int {
+    CK(cudaMalloc(&m->d_plain, cnt * sizeof(float)));
+    m->map_bytes += cnt * sizeof(float);
+    if (!is_f64) {
+      CK(cudaMemcpy(m->d_plain, vox, cnt * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+      // chunked narrow f64 -> f32 on the device
+      const size_t chunk = (size_t)1 << 24;
+      double *tmp = nullptr;
+      CK(cudaMalloc(&tmp, std::min(chunk, cnt) * sizeof(double)));
+      for (size_t o = 0; o < cnt; o += chunk) {
+        const size_t c2 = std::min(chunk, cnt - o);
+        cudaError_t e1 = cudaMemcpy(tmp, (const double *)vox + o, c2 * sizeof(double), cudaMemcpyHostToDevice);
+        if (e1 != cudaSuccess) { cudaFree(tmp); CK(e1); }
+        k_narrow_f64<<<m->sm_count * 4, 256>>>(tmp, c2, m->d_plain + o);
+      }
+      cudaError_t e2 = cudaDeviceSynchronize();
+      cudaFree(tmp);
+      CK(e2);
+    }
+    CK(cudaMalloc(&m->d_lookups, sizeof(unsigned long long)));
+    CK(cudaMemset(m->d_lookups, 0, sizeof(unsigned long long)));
+    CKR(map_build_layouts(m));
+    return CTP_OK;
+  };
+  rc = body();
+  if (rc != CTP_OK) {
+    ctp_map_destroy(m);
+    return rc;
+  }
+  m->active = pick_active(m->layouts);
+  map_fill_params(m, c, e);
+  *out = m;
+  return CTP_OK;
+}
+
+extern "C" int ctp_map_create(const float *vox, int n, const double c[3], const double e[3], int device,
+                              int layouts, ctp_map **out) {
+  return map_create_common(vox, false, n, c, e, device, layouts, out);
+}
+extern "C" int ctp_map_create_f64(const double *vox, int n, const double c[3], const double e[3], int device,
+                                  int layouts, ctp_map **out) {
+  return map_create_common(vox, true, n, c, e, device, layouts, out);
+}
+
+extern "C" int ctp_map_destroy(ctp_map *m) {
+  if (!m) return CTP_OK;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  if (m->tex) cudaDestroyTextureObject(m->tex);
+  if (m->arr) cudaFreeArray(m->arr);
+  cudaFree(m->d_plain);
+  cudaFree(m->d_cell8);
+  cudaFree(m->d_brick);
+  cudaFree(m->d_lookups);
+  cudaFree(m->ws.base);
+  cudaFree(m->io.base);
+  delete m;
+  return CTP_OK;
+}
+
+extern "C" int ctp_map_set_layout(ctp_map *m, int layout) {
+  REQUIRE(m, "null map");
+  REQUIRE(layout == CTP_L_PLAIN || layout == CTP_L_CELL8 || layout == CTP_L_TEX || layout == CTP_L_BRICK,
+          "layout must be a single CTP_LAYOUT_* value");
+  REQUIRE(m->layouts & layout, "layout was not materialised at ctp_map_create");
+  m->active = layout;
+  return CTP_OK;
+}
+
+extern "C" int ctp_map_info(const ctp_map *m, double info[10]) {
+  REQUIRE(m && info, "null");
+  info[0] = m->dev.lox; info[1] = m->dev.loy; info[2] = m->dev.loz;
+  info[3] = m->dev.hix; info[4] = m->dev.hiy; info[5] = m->dev.hiz;
+  info[6] = m->n;
+  info[7] = m->active;
+  info[8] = m->device;
+  info[9] = (double)(m->map_bytes + m->ws.cap + m->io.cap);
+  return CTP_OK;
+}
+
+extern "C" int ctp_lookup_counter_read(ctp_map *m, void *stream, uint64_t *lookups, int reset) {
+  REQUIRE(m && lookups, "null");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long v = 0;
+  CK(cudaMemcpyAsync(&v, m->d_lookups, sizeof v, cudaMemcpyDeviceToHost, st));
+  if (reset) CK(cudaMemsetAsync(m->d_lookups, 0, sizeof v, st));
+  CK(cudaStreamSynchronize(st));
+  *lookups = v;
+  return CTP_OK;
+}
+
+#define DISPATCH_L(m, ...)                                                     \
+  switch ((m)->active) {                                                       \
+    case CTP_L_PLAIN: { constexpr int L = CTP_L_PLAIN; __VA_ARGS__; } break;   \
+    case CTP_L_CELL8: { constexpr int L = CTP_L_CELL8; __VA_ARGS__; } break;   \
+    case CTP_L_TEX:   { constexpr int L = CTP_L_TEX;   __VA_ARGS__; } break;   \
+    default:          { constexpr int L = CTP_L_BRICK; __VA_ARGS__; } break;   \
+  }
+
+static inline int grid_for(int64_t items, int block, int cap_blocks) {
+  int64_t g = (items + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap_blocks) g = cap_blocks;
+  return (int)g;
+}
+
+// ------------------------------ point-wise entry points ------------------------------------
+extern "C" int ctp_clearance_dev(ctp_map *m, const double *xyz, int64_t cnt, double *out, void *stream) {
+  REQUIRE(m && cnt >= 0, "bad argument");
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(xyz && out, "null buffer");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_L(m, k_clearance<L><<<grid_for(cnt, 256, m->sm_count * 8), 256, 0, st>>>(m->dev, xyz, cnt, out));
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+extern "C" int ctp_in_collision_dev(ctp_map *m, const double *xyz, int64_t cnt, double clr, uint8_t *out,
+                                    void *stream) {
+  REQUIRE(m && cnt >= 0, "bad argument");
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(xyz && out, "null buffer");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_L(m, k_in_collision<L><<<grid_for(cnt, 256, m->sm_count * 8), 256, 0, st>>>(m->dev, xyz, cnt, clr, out));
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+extern "C" int ctp_gradient_dev(ctp_map *m, const double *xyz, int64_t cnt, double *grad, double *centre,
+                                void *stream) {
+  REQUIRE(m && cnt >= 0, "bad argument");
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(xyz && grad && centre, "null buffer");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_L(m, k_gradient<L><<<grid_for(cnt, 256, m->sm_count * 8), 256, 0, st>>>(m->dev, xyz, cnt, grad, centre));
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+// host-pointer wrappers: stage through the io arena
+struct IoScope {
+  ctp_map *m;
+  explicit IoScope(ctp_map *mm) : m(mm) { m->io.used = 0; }
+};
+
+extern "C" int ctp_clearance(ctp_map *m, const double *xyz, int64_t cnt, double *out) {
+  REQUIRE(m && cnt >= 0, "bad argument");
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(xyz && out, "null buffer");
+  CK(cudaSetDevice(m->device));
+  CKR(arena_reserve(m->io, align_up(cnt * 24) + align_up(cnt * 8)));
+  IoScope sc(m);
+  double *d_x = arena_take<double>(m->io, cnt * 3), *d_o = arena_take<double>(m->io, cnt);
+  CK(cudaMemcpyAsync(d_x, xyz, cnt * 24, cudaMemcpyHostToDevice, 0));
+  CKR(ctp_clearance_dev(m, d_x, cnt, d_o, 0));
+  CK(cudaMemcpyAsync(out, d_o, cnt * 8, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return CTP_OK;
+}
+
+extern "C" int ctp_in_collision(ctp_map *m, const double *xyz, int64_t cnt, double clr, uint8_t *out) {
+  REQUIRE(m && cnt >= 0, "bad argument");
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(xyz && out, "null buffer");
+  CK(cudaSetDevice(m->device));
+  CKR(arena_reserve(m->io, align_up(cnt * 24) + align_up(cnt)));
+  IoScope sc(m);
+  double *d_x = arena_take<double>(m->io, cnt * 3);
+  uint8_t *d_o = arena_take<uint8_t>(m->io, cnt);
+  CK(cudaMemcpyAsync(d_x, xyz, cnt * 24, cudaMemcpyHostToDevice, 0));
+  CKR(ctp_in_collision_dev(m, d_x, cnt, clr, d_o, 0));
+  CK(cudaMemcpyAsync(out, d_o, cnt, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return CTP_OK;
+}
+
+extern "C" int ctp_gradient(ctp_map *m, const double *xyz, int64_t cnt, double *grad, double *centre) {
+  REQUIRE(m && cnt >= 0, "bad argument");
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(xyz && grad && centre, "null buffer");
+  CK(cudaSetDevice(m->device));
+  CKR(arena_reserve(m->io, 3 * align_up(cnt * 24)));
+  IoScope sc(m);
+  double *d_x = arena_take<double>(m->io, cnt * 3), *d_g = arena_take<double>(m->io, cnt * 3),
+         *d_c = arena_take<double>(m->io, cnt * 3);
+  CK(cudaMemcpyAsync(d_x, xyz, cnt * 24, cudaMemcpyHostToDevice, 0));
+  CKR(ctp_gradient_dev(m, d_x, cnt, d_g, d_c, 0));
+  CK(cudaMemcpyAsync(grad, d_g, cnt * 24, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(centre, d_c, cnt * 24, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return CTP_OK;
+}
+
+// ----------------------------------- segment checks ----------------------------------------
+template <int L, int G>
+static int launch_edges_LG(ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr, double cdc, int guards,
+                           const EdgeOut &O, cudaStream_t st) {
+  static int occ = 0;  // resident CTAs per SM for this instantiation
+  if (occ == 0) {
+    int o = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_edge_march<L, G>, 256, 0));
+    occ = o > 0 ? o : 1;
+  }
+  const int64_t groups_per_block = 256 / G;
+  int64_t blocks = (cnt + groups_per_block - 1) / groups_per_block;
+  const int64_t cap = (int64_t)m->sm_count * occ;  // persistent: one resident wave
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_edge_march<L, G><<<(int)blocks, 256, 0, st>>>(m->dev, S, cnt, clr, cdc, guards, O);
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+template <int L>
+static int launch_edges_L(ctp_map *m, int group, const EdgeSrc &S, int64_t cnt, double clr, double cdc,
+                          int guards, const EdgeOut &O, cudaStream_t st) {
+  switch (group) {
+    case 4: return launch_edges_LG<L, 4>(m, S, cnt, clr, cdc, guards, O, st);
+    case 8: return launch_edges_LG<L, 8>(m, S, cnt, clr, cdc, guards, O, st);
+    case 16: return launch_edges_LG<L, 16>(m, S, cnt, clr, cdc, guards, O, st);
+    default: return launch_edges_LG<L, 32>(m, S, cnt, clr, cdc, guards, O, st);
+  }
+}
+
+static int launch_edges(ctp_map *m, int group, const EdgeSrc &S, int64_t cnt, double clr, double cdc, int guards,
+                        const EdgeOut &O, cudaStream_t st) {
+  DISPATCH_L(m, return launch_edges_L<L>(m, group, S, cnt, clr, cdc, guards, O, st));
+  return CTP_OK;
+}
+
+static int check_edge_args(ctp_map *m, int64_t cnt, double cdc, int group) {
+  REQUIRE(m && cnt >= 0, "bad argument");
+  REQUIRE(cdc > 0, "collision_distance_check must be > 0 (topological_prm_clustering.hpp:270-275)");
+  REQUIRE(group == 0 || group == 4 || group == 8 || group == 16 || group == 32, "group must be 0, 4, 8, 16 or 32");
+  return CTP_OK;
+}
+
+extern "C" int ctp_edge_check_dev(ctp_map *m, const double *a, const double *b, int64_t cnt, double clr,
+                                  double cdc, int mode, int group, uint8_t *free_out, double *hit,
+                                  int32_t *hit_idx, int32_t *lookups, void *stream) {
+  CKR(check_edge_args(m, cnt, cdc, group));
+  REQUIRE(mode == CTP_EDGE_NODES || mode == CTP_EDGE_GUARDS, "mode");
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(a && b && free_out, "null buffer");
+  CK(cudaSetDevice(m->device));
+  EdgeSrc S{a, b, nullptr, nullptr, 0, 0, 0};
+  EdgeOut O{free_out, hit, hit_idx, lookups, m->d_lookups};
+  return launch_edges(m, group ? group : 16, S, cnt, clr, cdc, mode == CTP_EDGE_GUARDS, O, (cudaStream_t)stream);
+}
+
+extern "C" int ctp_edge_check_indexed_dev(ctp_map *m, const double *nodes, int64_t n_nodes, const int32_t *from,
+                                          const int32_t *to, int64_t cnt, double clr, double cdc, int group,
+                                          uint8_t *free_out, int32_t *hit_idx, int32_t *lookups, void *stream) {
+  CKR(check_edge_args(m, cnt, cdc, group));
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(nodes && from && to && free_out && n_nodes > 0, "null buffer");
+  CK(cudaSetDevice(m->device));
+  EdgeSrc S{nodes, nullptr, from, to, n_nodes, 1, 1};
+  EdgeOut O{free_out, nullptr, hit_idx, lookups, m->d_lookups};
+  return launch_edges(m, group ? group : 8, S, cnt, clr, cdc, 0, O, (cudaStream_t)stream);
+}
+
+static int auto_group(const double *a, const double *b, int64_t cnt, double cdc) {
+  const int64_t probe = std::min<int64_t>(cnt, 4096);
+  double sum = 0;
+  for (int64_t i = 0; i < probe; i++) {
+    const int64_t e = (cnt / probe) * i;
+    const double dx = b[3 * e] - a[3 * e], dy = b[3 * e + 1] - a[3 * e + 1], dz = b[3 * e + 2] - a[3 * e + 2];
+    const double d = sqrt(dx * dx + dy * dy + dz * dz);
+    if (d == d && d < 1e300) sum += d;
+  }
+  const double samples = sum / (double)probe / cdc + 1.0;
+  return samples <= 5 ? 4 : samples <= 11 ? 8 : samples <= 24 ? 16 : 32;
+}
+
+extern "C" int ctp_edge_check(ctp_map *m, const double *a, const double *b, int64_t cnt, double clr, double cdc,
+                              int mode, int group, uint8_t *free_out, double *hit, int32_t *hit_idx,
+                              int32_t *lookups) {
+  CKR(check_edge_args(m, cnt, cdc, group));
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(a && b && free_out, "null buffer");
+  CK(cudaSetDevice(m->device));
+  CKR(arena_reserve(m->io, 2 * align_up(cnt * 24) + align_up(cnt) + align_up(cnt * 24) + 2 * align_up(cnt * 4)));
+  IoScope sc(m);
+  double *d_a = arena_take<double>(m->io, cnt * 3), *d_b = arena_take<double>(m->io, cnt * 3);
+  uint8_t *d_f = arena_take<uint8_t>(m->io, cnt);
+  double *d_h = hit ? arena_take<double>(m->io, cnt * 3) : nullptr;
+  int32_t *d_hi = hit_idx ? arena_take<int32_t>(m->io, cnt) : nullptr;
+  int32_t *d_l = lookups ? arena_take<int32_t>(m->io, cnt) : nullptr;
+  CK(cudaMemcpyAsync(d_a, a, cnt * 24, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_b, b, cnt * 24, cudaMemcpyHostToDevice, 0));
+  if (group == 0) group = auto_group(a, b, cnt, cdc);
+  CKR(ctp_edge_check_dev(m, d_a, d_b, cnt, clr, cdc, mode, group, d_f, d_h, d_hi, d_l, 0));
+  CK(cudaMemcpyAsync(free_out, d_f, cnt, cudaMemcpyDeviceToHost, 0));
+  if (hit) CK(cudaMemcpyAsync(hit, d_h, cnt * 24, cudaMemcpyDeviceToHost, 0));
+  if (hit_idx) CK(cudaMemcpyAsync(hit_idx, d_hi, cnt * 4, cudaMemcpyDeviceToHost, 0));
+  if (lookups) CK(cudaMemcpyAsync(lookups, d_l, cnt * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return CTP_OK;
+}
+
+extern "C" int ctp_edge_check_indexed(ctp_map *m, const double *nodes, int64_t n_nodes, const int32_t *from,
+                                      const int32_t *to, int64_t cnt, double clr, double cdc, int group,
+                                      uint8_t *free_out, int32_t *hit_idx, int32_t *lookups) {
+  CKR(check_edge_args(m, cnt, cdc, group));
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(nodes && from && to && free_out && n_nodes > 0, "null buffer");
+  for (int64_t i = 0; i < cnt; i++)
+    REQUIRE(from[i] >= 0 && from[i] < n_nodes && to[i] < n_nodes, "edge index out of range");
+  CK(cudaSetDevice(m->device));
+  CKR(arena_reserve(m->io, align_up(n_nodes * 24) + 4 * align_up(cnt * 4) + align_up(cnt)));
+  IoScope sc(m);
+  double *d_n = arena_take<double>(m->io, n_nodes * 3);
+  int32_t *d_from = arena_take<int32_t>(m->io, cnt), *d_to = arena_take<int32_t>(m->io, cnt);
+  uint8_t *d_f = arena_take<uint8_t>(m->io, cnt);
+  int32_t *d_hi = hit_idx ? arena_take<int32_t>(m->io, cnt) : nullptr;
+  int32_t *d_l = lookups ? arena_take<int32_t>(m->io, cnt) : nullptr;
+  CK(cudaMemcpyAsync(d_n, nodes, n_nodes * 24, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_from, from, cnt * 4, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_to, to, cnt * 4, cudaMemcpyHostToDevice, 0));
+  CKR(ctp_edge_check_indexed_dev(m, d_n, n_nodes, d_from, d_to, cnt, clr, cdc, group, d_f, d_hi, d_l, 0));
+  CK(cudaMemcpyAsync(free_out, d_f, cnt, cudaMemcpyDeviceToHost, 0));
+  if (hit_idx) CK(cudaMemcpyAsync(hit_idx, d_hi, cnt * 4, cudaMemcpyDeviceToHost, 0));
+  if (lookups) CK(cudaMemcpyAsync(lookups, d_l, cnt * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return CTP_OK;
+}
+
+// ------------------------------- workspace sizing -------------------------------------------
+static int knn_max_cells(int64_t n) {
+  int64_t c = n / 2 + 64;
+  if (c > (1 << 22)) c = 1 << 22;
+  return (int)c;
+}
+static size_t ws_bytes_reject(int64_t q, int64_t m) {
+  const int64_t nblk = (m + CTP_REJ_BLOCK - 1) / CTP_REJ_BLOCK;
+  return align_up((size_t)q * m) + align_up((size_t)q * nblk * 4);
+}
+static size_t ws_bytes_knn(int64_t q, int64_t n) {
+  const size_t mc = (size_t)knn_max_cells(n);
+  return align_up((size_t)q * sizeof(KnnGrid)) + 2 * align_up((size_t)q * n * 16) + align_up((size_t)q * n * 4) +
+         align_up((size_t)q * mc * 4) + align_up((size_t)q * (mc + 1) * 4);
+}
+static size_t ws_bytes_prm(int64_t q, int64_t n, int k) {
+  return ws_bytes_knn(q, n) + align_up((size_t)q * n * k * 4) + align_up((size_t)q * n * k) +
+         align_up((size_t)q * n * 4) + align_up((size_t)q * 8);
+}
+
+extern "C" int ctp_reserve(ctp_map *m, int64_t q, int64_t n, int64_t cand, int k) {
+  REQUIRE(m && q >= 1 && n >= 2 && cand >= 0 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument");
+  CK(cudaSetDevice(m->device));
+  const size_t need = ws_bytes_reject(q, cand) + ws_bytes_prm(q, n, k) + align_up((size_t)q * n * 24) + (1 << 16);
+  return arena_reserve(m->ws, need);
+}
+
+// ------------------------------- rejection sampling -----------------------------------------
+extern "C" int ctp_sample_reject_dev(ctp_map *m, const double *start, const double *goal, const double *cand,
+                                     int64_t q, int64_t cnt, double clr, int64_t n, double *nodes,
+                                     int32_t *n_filled, int32_t *n_used, uint8_t *accept, void *stream) {
+  REQUIRE(m && q >= 1 && cnt >= 0 && n >= 2, "bad argument");
+  REQUIRE(start && goal && nodes && n_filled && n_used && (cand || cnt == 0), "null buffer");
+  REQUIRE(q <= 65535, "at most 65535 queries per call");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (int)std::max<int64_t>(1, (cnt + CTP_REJ_BLOCK - 1) / CTP_REJ_BLOCK);
+  const size_t keep = m->ws.used;
+  CKR(arena_reserve(m->ws, keep + ws_bytes_reject(q, cnt) + 512));
+  uint8_t *d_acc = accept ? accept : arena_take<uint8_t>(m->ws, (size_t)q * cnt + 1);
+  int32_t *d_bc = arena_take<int32_t>(m->ws, (size_t)q * nblk);
+  m->ws.used = keep;  // scratch is dead once the three kernels below have run (stream order)
+  dim3 grid((unsigned)nblk, (unsigned)q);
+  DISPATCH_L(m, k_reject_flags<L><<<grid, CTP_REJ_BLOCK, 0, st>>>(m->dev, cand, cnt, clr, d_acc, d_bc, nblk));
+  CK(cudaGetLastError());
+  k_reject_scan<<<(unsigned)q, 1024, 0, st>>>(d_bc, nblk, n, n_filled);
+  CK(cudaGetLastError());
+  // n_used defaults to "whole stream consumed"; the scatter pass overwrites it when n-2 were found
+  k_fill_i32<<<grid_for(q, 256, 1024), 256, 0, st>>>(n_used, q, (int32_t)cnt);
+  k_reject_scatter<<<grid, CTP_REJ_BLOCK, 0, st>>>(cand, start, goal, d_acc, d_bc, nblk, cnt, n, nodes, n_used);
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+extern "C" int ctp_sample_reject(ctp_map *m, const double *start, const double *goal, const double *cand,
+                                 int64_t q, int64_t cnt, double clr, int64_t n, double *nodes, int32_t *n_filled,
+                                 int32_t *n_used, uint8_t *accept) {
+  REQUIRE(m && q >= 1 && cnt >= 0 && n >= 2, "bad argument");
+  REQUIRE(start && goal && nodes && n_filled && n_used && (cand || cnt == 0), "null buffer");
+  CK(cudaSetDevice(m->device));
+  CKR(arena_reserve(m->io, 2 * align_up(q * 24) + align_up(q * cnt * 24) + align_up(q * n * 24) +
+                               2 * align_up(q * 4) + align_up(q * cnt + 1)));
+  IoScope sc(m);
+  double *d_s = arena_take<double>(m->io, q * 3), *d_g = arena_take<double>(m->io, q * 3);
+  double *d_c = arena_take<double>(m->io, q * cnt * 3), *d_n = arena_take<double>(m->io, q * n * 3);
+  int32_t *d_nf = arena_take<int32_t>(m->io, q), *d_nu = arena_take<int32_t>(m->io, q);
+  uint8_t *d_acc = arena_take<uint8_t>(m->io, q * cnt + 1);
+  CK(cudaMemcpyAsync(d_s, start, q * 24, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_g, goal, q * 24, cudaMemcpyHostToDevice, 0));
+  if (cnt) CK(cudaMemcpyAsync(d_c, cand, q * cnt * 24, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemsetAsync(d_n, 0, q * n * 24, 0));
+  m->ws.used = 0;
+  CKR(ctp_sample_reject_dev(m, d_s, d_g, d_c, q, cnt, clr, n, d_n, d_nf, d_nu, d_acc, 0));
+  CK(cudaMemcpyAsync(nodes, d_n, q * n * 24, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(n_filled, d_nf, q * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(n_used, d_nu, q * 4, cudaMemcpyDeviceToHost, 0));
+  if (accept && cnt) CK(cudaMemcpyAsync(accept, d_acc, q * cnt, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  for (int64_t i = 0; i < q; i++)
+    if (n_filled[i] < n) return fail(CTP_ERR_NEED_CANDIDATES, "query %lld: only %d of %lld nodes accepted", (long long)i, n_filled[i], (long long)n);
+  return CTP_OK;
+}
+
+// ------------------------------------ candidate sampling -----------------------------------
+extern "C" int ctp_sample_ellipsoid_dev(ctp_map *m, const double *start, const double *goal, int64_t q,
+                                        int64_t cnt, double ratio, int planar, uint64_t seed, double *cand,
+                                        void *stream) {
+  REQUIRE(m && q >= 1 && cnt >= 0 && ratio > 1.0, "bad argument (ratio must be > 1)");
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(start && goal && cand, "null buffer");
+  CK(cudaSetDevice(m->device));
+  k_sample_ellipsoid<<<grid_for(q * cnt, 256, m->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(
+      start, goal, q, cnt, ratio, planar, seed, cand);
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+extern "C" int ctp_sample_ellipsoid(ctp_map *m, const double *start, const double *goal, int64_t q, int64_t cnt,
+                                    double ratio, int planar, uint64_t seed, double *cand) {
+  REQUIRE(m && q >= 1 && cnt >= 0, "bad argument");
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(start && goal && cand, "null buffer");
+  CK(cudaSetDevice(m->device));
+  CKR(arena_reserve(m->io, 2 * align_up(q * 24) + align_up(q * cnt * 24)));
+  IoScope sc(m);
+  double *d_s = arena_take<double>(m->io, q * 3), *d_g = arena_take<double>(m->io, q * 3);
+  double *d_c = arena_take<double>(m->io, q * cnt * 3);
+  CK(cudaMemcpyAsync(d_s, start, q * 24, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_g, goal, q * 24, cudaMemcpyHostToDevice, 0));
+  CKR(ctp_sample_ellipsoid_dev(m, d_s, d_g, q, cnt, ratio, planar, seed, d_c, 0));
+  CK(cudaMemcpyAsync(cand, d_c, q * cnt * 24, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return CTP_OK;
+}
+
+// --------------------------------------- k-NN ----------------------------------------------
+static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *idx, float *d2,
+                      cudaStream_t st) {
+  const int mc = knn_max_cells(n);
+  const int64_t total = q * n;
+  KnnGrid *d_grid = arena_take<KnnGrid>(m->ws, q);
+  float4 *d_pts = arena_take<float4>(m->ws, total), *d_sorted = arena_take<float4>(m->ws, total);
+  int32_t *d_cell_of = arena_take<int32_t>(m->ws, total);
+  int32_t *d_cnt = arena_take<int32_t>(m->ws, (size_t)q * mc);
+  int32_t *d_start = arena_take<int32_t>(m->ws, (size_t)q * (mc + 1));
+  CK(cudaMemsetAsync(d_cnt, 0, (size_t)q * mc * 4, st));
+  k_knn_setup<<<(unsigned)q, 1024, 0, st>>>(nodes, n, mc, d_grid, d_pts);
+  CK(cudaGetLastError());
+  const int blocks = (int)((total + 255) / 256);
+  k_knn_count<<<blocks, 256, 0, st>>>(d_pts, n, total, d_grid, mc, d_cell_of, d_cnt);
+  k_knn_scan<<<(unsigned)q, 1024, 0, st>>>(d_grid, mc, d_cnt, d_start);
+  k_knn_scatter<<<blocks, 256, 0, st>>>(d_pts, n, total, mc, d_cell_of, d_start, d_cnt, d_sorted);
+  CK(cudaGetLastError());
+  const int sblocks = (int)((total + 127) / 128);
+#define KNN_CASE(K) \
+  case K: k_knn_search<K><<<sblocks, 128, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, d2); break;
+  switch (k) {
+    KNN_CASE(1) KNN_CASE(2) KNN_CASE(3) KNN_CASE(4) KNN_CASE(5) KNN_CASE(6) KNN_CASE(7) KNN_CASE(8)
+    KNN_CASE(9) KNN_CASE(10) KNN_CASE(11) KNN_CASE(12) KNN_CASE(13) KNN_CASE(14) KNN_CASE(15) KNN_CASE(16)
+  }
+#undef KNN_CASE
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+extern "C" int ctp_knn_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *idx, float *d2,
+                           void *stream) {
+  REQUIRE(m && q >= 1 && n >= 1 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument (k must be in [1,16])");
+  REQUIRE(nodes && idx, "null buffer");
+  REQUIRE(q * n < ((int64_t)1 << 31), "q*n must fit in int32");
+  CK(cudaSetDevice(m->device));
+  const size_t keep = m->ws.used;
+  CKR(arena_reserve(m->ws, keep + ws_bytes_knn(q, n) + 4096));
+  int rc = knn_launch(m, nodes, q, n, k, idx, d2, (cudaStream_t)stream);
+  m->ws.used = keep;
+  return rc;
+}
+
+extern "C" int ctp_knn(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *idx, float *d2) {
+  REQUIRE(m && q >= 1 && n >= 1 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument (k must be in [1,16])");
+  REQUIRE(nodes && idx, "null buffer");
+  CK(cudaSetDevice(m->device));
+  CKR(arena_reserve(m->io, align_up(q * n * 24) + 2 * align_up(q * n * k * 4)));
+  IoScope sc(m);
+  double *d_n = arena_take<double>(m->io, q * n * 3);
+  int32_t *d_i = arena_take<int32_t>(m->io, q * n * k);
+  float *d_d = d2 ? arena_take<float>(m->io, q * n * k) : nullptr;
+  CK(cudaMemcpyAsync(d_n, nodes, q * n * 24, cudaMemcpyHostToDevice, 0));
+  m->ws.used = 0;
+  CKR(ctp_knn_dev(m, d_n, q, n, k, d_i, d_d, 0));
+  CK(cudaMemcpyAsync(idx, d_i, q * n * k * 4, cudaMemcpyDeviceToHost, 0));
+  if (d2) CK(cudaMemcpyAsync(d2, d_d, q * n * k * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return CTP_OK;
+}
+
+// ------------------------------------- PRM build -------------------------------------------
+extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, double clr,
+                                 double cdc, int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr, int32_t *col,
+                                 double *w, int64_t cap, int64_t *nnz_off, void *stream) {
+  REQUIRE(m && q >= 1 && n >= 2 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument (k must be in [1,16])");
+  REQUIRE(nodes && row_ptr && col && w && nnz_off && cap >= 0, "null buffer");
+  REQUIRE(cdc > 0, "collision_distance_check must be > 0");
+  REQUIRE(q * n * k < ((int64_t)1 << 31), "q*n*k must fit in int32");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t keep = m->ws.used;
+  CKR(arena_reserve(m->ws, keep + ws_bytes_prm(q, n, k) + 8192));
+  const int64_t rows = q * n, edges = rows * k;
+  int32_t *d_nbr = nbr ? nbr : arena_take<int32_t>(m->ws, edges);
+  uint8_t *d_free = directed_free ? directed_free : arena_take<uint8_t>(m->ws, edges);
+  int32_t *d_deg = arena_take<int32_t>(m->ws, rows);
+  int64_t *d_nnz = arena_take<int64_t>(m->ws, q);
+  int rc = knn_launch(m, nodes, q, n, k, d_nbr, nullptr, st);
+  m->ws.used = keep;
+  CKR(rc);
+  // the n*k directed checks (:355-397), 8 lanes per edge: kNN edges are ~5-12 samples long
+  EdgeSrc S{nodes, nullptr, nullptr, d_nbr, n, k, 1};
+  EdgeOut O{d_free, nullptr, nullptr, nullptr, m->d_lookups};
+  CKR(launch_edges(m, 8, S, edges, clr, cdc, 0, O, st));
+  CK(cudaMemsetAsync(d_deg, 0, rows * 4, st));
+  const int eb = (int)((edges + 255) / 256), rb = (int)((rows + 255) / 256);
+  k_csr_degree<<<eb, 256, 0, st>>>(d_nbr, d_free, n, k, edges, d_deg);
+  k_csr_rowptr<<<(unsigned)q, 1024, 0, st>>>(d_deg, n, row_ptr, d_nnz);
+  k_csr_query_offsets<<<1, 1024, 0, st>>>(d_nnz, q, nnz_off);
+  k_csr_fill<<<eb, 256, 0, st>>>(d_nbr, d_free, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
+  k_csr_finish<<<rb, 256, 0, st>>>(nodes, n, rows, row_ptr, nnz_off, cap, col, w);
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+static int build_prm_host_tail(ctp_map *m, int64_t q, int64_t n, int k, int32_t *nbr, uint8_t *directed_free,
+                               int32_t *row_ptr, int32_t *col, double *w, int64_t cap, int64_t *nnz_off,
+                               const int32_t *d_nbr, const uint8_t *d_free, const int32_t *d_rp, const int32_t *d_col,
+                               const double *d_w, const int64_t *d_off) {
+  CK(cudaMemcpyAsync(nnz_off, d_off, (q + 1) * 8, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(row_ptr, d_rp, q * (n + 1) * 4, cudaMemcpyDeviceToHost, 0));
+  if (nbr) CK(cudaMemcpyAsync(nbr, d_nbr, q * n * k * 4, cudaMemcpyDeviceToHost, 0));
+  if (directed_free) CK(cudaMemcpyAsync(directed_free, d_free, q * n * k, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  const int64_t nnz = nnz_off[q];
+  if (nnz > cap) return fail(CTP_ERR_CAPACITY, "CSR needs %lld entries, capacity is %lld", (long long)nnz, (long long)cap);
+  if (nnz) {
+    CK(cudaMemcpyAsync(col, d_col, nnz * 4, cudaMemcpyDeviceToHost, 0));
+    CK(cudaMemcpyAsync(w, d_w, nnz * 8, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+  }
+  return CTP_OK;
+}
+
+extern "C" int ctp_build_prm(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, double clr, double cdc,
+                             int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr, int32_t *col, double *w,
+                             int64_t cap, int64_t *nnz_off) {
+  REQUIRE(m && q >= 1 && n >= 2 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument (k must be in [1,16])");
+  REQUIRE(nodes && row_ptr && col && w && nnz_off, "null buffer");
+  CK(cudaSetDevice(m->device));
+  const int64_t edges = q * n * k, dcap = 2 * edges;
+  CKR(arena_reserve(m->io, align_up(q * n * 24) + align_up(edges * 4) + align_up(edges) + align_up(q * (n + 1) * 4) +
+                               align_up(dcap * 4) + align_up(dcap * 8) + align_up((q + 1) * 8)));
+  IoScope sc(m);
+  double *d_n = arena_take<double>(m->io, q * n * 3);
+  int32_t *d_nbr = arena_take<int32_t>(m->io, edges);
+  uint8_t *d_free = arena_take<uint8_t>(m->io, edges);
+  int32_t *d_rp = arena_take<int32_t>(m->io, q * (n + 1));
+  int32_t *d_col = arena_take<int32_t>(m->io, dcap);
+  double *d_w = arena_take<double>(m->io, dcap);
+  int64_t *d_off = arena_take<int64_t>(m->io, q + 1);
+  CK(cudaMemcpyAsync(d_n, nodes, q * n * 24, cudaMemcpyHostToDevice, 0));
+  m->ws.used = 0;
+  CKR(ctp_build_prm_dev(m, d_n, q, n, k, clr, cdc, d_nbr, d_free, d_rp, d_col, d_w, dcap, d_off, 0));
+  return build_prm_host_tail(m, q, n, k, nbr, directed_free, row_ptr, col, w, cap, nnz_off, d_nbr, d_free, d_rp,
+                             d_col, d_w, d_off);
+}
+
+extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double *goal, const double *cand,
+                                   int64_t q, int64_t cnt, int64_t n, int k, double clr, double cdc, double *nodes,
+                                   int32_t *n_filled, int32_t *row_ptr, int32_t *col, double *w, int64_t cap,
+                                   int64_t *nnz_off) {
+  REQUIRE(m && q >= 1 && n >= 2 && cnt >= 0 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument");
+  REQUIRE(start && goal && cand && nodes && n_filled && row_ptr && col && w && nnz_off, "null buffer");
+  CK(cudaSetDevice(m->device));
+  const int64_t edges = q * n * k, dcap = 2 * edges;
+  CKR(arena_reserve(m->io, 2 * align_up(q * 24) + align_up(q * cnt * 24) + align_up(q * n * 24) + 2 * align_up(q * 4) +
+                               align_up(q * (n + 1) * 4) + align_up(dcap * 4) + align_up(dcap * 8) +
+                               align_up((q + 1) * 8)));
+  IoScope sc(m);
+  double *d_s = arena_take<double>(m->io, q * 3), *d_g = arena_take<double>(m->io, q * 3);
+  double *d_c = arena_take<double>(m->io, q * cnt * 3), *d_n = arena_take<double>(m->io, q * n * 3);
+  int32_t *d_nf = arena_take<int32_t>(m->io, q), *d_nu = arena_take<int32_t>(m->io, q);
+  int32_t *d_rp = arena_take<int32_t>(m->io, q * (n + 1));
+  int32_t *d_col = arena_take<int32_t>(m->io, dcap);
+  double *d_w = arena_take<double>(m->io, dcap);
+  int64_t *d_off = arena_take<int64_t>(m->io, q + 1);
+  CKR(ctp_reserve(m, q, n, cnt, k));
+  CK(cudaMemcpyAsync(d_s, start, q * 24, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_g, goal, q * 24, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_c, cand, q * cnt * 24, cudaMemcpyHostToDevice, 0));
+  m->ws.used = 0;
+  CKR(ctp_sample_reject_dev(m, d_s, d_g, d_c, q, cnt, clr, n, d_n, d_nf, d_nu, nullptr, 0));
+  CK(cudaMemcpyAsync(n_filled, d_nf, q * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  for (int64_t i = 0; i < q; i++)
+    if (n_filled[i] < n)
+      return fail(CTP_ERR_NEED_CANDIDATES, "query %lld: only %d of %lld nodes accepted", (long long)i, n_filled[i], (long long)n);
+  CKR(ctp_build_prm_dev(m, d_n, q, n, k, clr, cdc, nullptr, nullptr, d_rp, d_col, d_w, dcap, d_off, 0));
+  CK(cudaMemcpyAsync(nodes, d_n, q * n * 24, cudaMemcpyDeviceToHost, 0));
+  return build_prm_host_tail(m, q, n, k, nullptr, nullptr, row_ptr, col, w, cap, nnz_off, nullptr, nullptr, d_rp,
+                             d_col, d_w, d_off);
+}
+
+#include "ctp_paths_api.inl"

@@ -1,0 +1,404 @@
+// ctp_device.cuh -- ESDF lookup and segment-march device code (sm_100a).
+//
+// Numerics contract: every FP64 operation below is evaluated in the reference's order with
+// one rounding per operation.  The translation unit is compiled with -fmad=false, so the
+// compiler never contracts a*b+c into an FMA; IEEE division, sqrt, floor/ceil are exact in
+// CUDA.  That is what makes verdicts bit-identical to the CPU restatement (oracle/).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CTP_L_PLAIN 1
+#define CTP_L_CELL8 2
+#define CTP_L_TEX 4
+#define CTP_L_BRICK 8
+
+struct MapDev {
+  double cx, cy, cz;                   // centroid
+  double lox, loy, loz, hix, hiy, hiz; // getMinPos / getMaxPos (src/esdf_map.cpp:75-76)
+  double s1;                           // 2.0 / max_extents_      (src/esdf_map.cpp:137)
+  double s2;                           // num_vexels_per_axis / 2 (src/esdf_map.cpp:139)
+  double nm1;                          // N - 1
+  double nd;                           // N
+  double dp;                           // max_extents_ / (N - 1)  (src/esdf_map.cpp:124)
+  double mex, mey, mez;                // centroid - max_extents_/2 (src/esdf_map.cpp:125)
+  int n;
+  int nb;                              // bricks per axis
+  const float *plain;
+  const float *cell8;
+  const float *brick;
+  cudaTextureObject_t tex;
+};
+
+__device__ __forceinline__ double ctp_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// ---- corner fetch, v[dx*4 + dy*2 + dz] -------------------------------------------------
+template <int L> struct Corners;
+
+template <> struct Corners<CTP_L_PLAIN> {
+  // [x][y][z] exactly as include/esdf_map.hpp:55-66 fills map_data
+  static __device__ __forceinline__ void load(const MapDev &M, int x0, int y0, int z0, float v[8]) {
+    const size_t n = (size_t)M.n;
+    const float *p = M.plain + ((size_t)x0 * n + (size_t)y0) * n + (size_t)z0;
+    const float *q = p + n * n;
+    v[0] = __ldg(p);
+    v[1] = __ldg(p + 1);
+    v[2] = __ldg(p + n);
+    v[3] = __ldg(p + n + 1);
+    v[4] = __ldg(q);
+    v[5] = __ldg(q + 1);
+    v[6] = __ldg(q + n);
+    v[7] = __ldg(q + n + 1);
+  }
+};
+
+template <> struct Corners<CTP_L_CELL8> {
+  // one 32-byte record per cell (x0,y0,z0), x0,y0,z0 in [0, n-2]: exactly one DRAM/L2 sector
+  static __device__ __forceinline__ void load(const MapDev &M, int x0, int y0, int z0, float v[8]) {
+    const size_t n1 = (size_t)(M.n - 1);
+    const float4 *p =
+        reinterpret_cast<const float4 *>(M.cell8 + (((size_t)x0 * n1 + (size_t)y0) * n1 + (size_t)z0) * 8);
+    const float4 a = __ldg(p);
+    const float4 b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+template <> struct Corners<CTP_L_TEX> {
+  // layered 2-D array: layer = x, height = y, width = z.  tld4 returns the 2x2 footprint
+  // around (z0+1, y0+1): .x=(z0,y1) .y=(z1,y1) .z=(z1,y0) .w=(z0,y0)
+  static __device__ __forceinline__ void load(const MapDev &M, int x0, int y0, int z0, float v[8]) {
+    const float fu = (float)(z0 + 1), fv = (float)(y0 + 1);
+    float a0, a1, a2, a3, b0, b1, b2, b3;
+    asm volatile("tld4.r.a2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%7}];"
+                 : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                 : "l"(M.tex), "r"(x0), "f"(fu), "f"(fv));
+    asm volatile("tld4.r.a2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%7}];"
+                 : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                 : "l"(M.tex), "r"(x0 + 1), "f"(fu), "f"(fv));
+    v[0] = a3; v[1] = a2; v[2] = a0; v[3] = a1;
+    v[4] = b3; v[5] = b2; v[6] = b0; v[7] = b1;
+  }
+};
+
+template <> struct Corners<CTP_L_BRICK> {
+  // 4x4x4 bricks of 256 B: offset = brick*64 + (x&3)*16 + (y&3)*4 + (z&3)
+  static __device__ __forceinline__ size_t addr(const MapDev &M, int x, int y, int z) {
+    const size_t nb = (size_t)M.nb;
+    return ((((size_t)(x >> 2) * nb + (size_t)(y >> 2)) * nb + (size_t)(z >> 2)) << 6) +
+           (size_t)(((x & 3) << 4) | ((y & 3) << 2) | (z & 3));
+  }
+  static __device__ __forceinline__ void load(const MapDev &M, int x0, int y0, int z0, float v[8]) {
+    const float *b = M.brick;
+    v[0] = __ldg(b + addr(M, x0, y0, z0));
+    v[1] = __ldg(b + addr(M, x0, y0, z0 + 1));
+    v[2] = __ldg(b + addr(M, x0, y0 + 1, z0));
+    v[3] = __ldg(b + addr(M, x0, y0 + 1, z0 + 1));
+    v[4] = __ldg(b + addr(M, x0 + 1, y0, z0));
+    v[5] = __ldg(b + addr(M, x0 + 1, y0, z0 + 1));
+    v[6] = __ldg(b + addr(M, x0 + 1, y0 + 1, z0));
+    v[7] = __ldg(b + addr(M, x0 + 1, y0 + 1, z0 + 1));
+  }
+};
+
+// ---- ESDFMap::interpolateMapData (src/esdf_map.cpp:78-121) ------------------------------
+// Equivalent formulation of the reference's tests, proven in DESIGN.md section 4:
+//   floor(q) < 0           <=>  q < 0            (NaN q fails q >= 0 as well)
+//   ceil(q)  >= N          <=>  q > N-1
+//   x1 == x0 (q integral)   =>  xd = 0/0 = NaN    => result NaN
+//   otherwise x1 - x0 == 1  =>  xd = (q - x0)/1 = q - floor(q), exact
+template <int L>
+__device__ __forceinline__ double esdf_interp(const MapDev &M, double qx, double qy, double qz) {
+  const int x0 = __double2int_rd(qx), y0 = __double2int_rd(qy), z0 = __double2int_rd(qz);
+  const double fx = (double)x0, fy = (double)y0, fz = (double)z0;
+  const bool ok = (qx >= 0.0) & (qy >= 0.0) & (qz >= 0.0) & (qx <= M.nm1) & (qy <= M.nm1) &
+                  (qz <= M.nm1) & (qx != fx) & (qy != fy) & (qz != fz);
+  if (!ok) return ctp_nan();
+  float v[8];
+  Corners<L>::load(M, x0, y0, z0, v);
+  const double xd = qx - fx, yd = qy - fy, zd = qz - fz;
+  const double omx = 1.0 - xd, omy = 1.0 - yd, omz = 1.0 - zd;
+  const double c00 = omx * (double)v[0] + xd * (double)v[4];
+  const double c01 = omx * (double)v[1] + xd * (double)v[5];
+  const double c10 = omx * (double)v[2] + xd * (double)v[6];
+  const double c11 = omx * (double)v[3] + xd * (double)v[7];
+  const double c0 = omy * c00 + yd * c10;
+  const double c1 = omy * c01 + yd * c11;
+  return omz * c0 + zd * c1;
+}
+
+// world -> index coordinate along one axis (src/esdf_map.cpp:136-139)
+__device__ __forceinline__ double ctp_w2i(double p, double c, double s1, double s2) {
+  return ((p - c) * s1 + 1.0) * s2;
+}
+
+// ---- ESDFMap::getClearence (src/esdf_map.cpp:130-165) -----------------------------------
+// The round()-based index test (:147-155) is implied by interpolateMapData's own range
+// tests (q >= 0 => round(q) >= 0; q <= N-1 => round(q) < N), so it is not evaluated.
+template <int L>
+__device__ __forceinline__ double esdf_clearance(const MapDev &M, double px, double py, double pz) {
+  const bool inside = (px >= M.lox) & (px <= M.hix) & (py >= M.loy) & (py <= M.hiy) &
+                      (pz >= M.loz) & (pz <= M.hiz);
+  if (!inside) return ctp_nan();
+  return esdf_interp<L>(M, ctp_w2i(px, M.cx, M.s1, M.s2), ctp_w2i(py, M.cy, M.s1, M.s2),
+                        ctp_w2i(pz, M.cz, M.s1, M.s2));
+}
+
+// BaseMap::isInCollision (src/base_map.cpp:7-12): !isfinite(c) || c < clearance
+__device__ __forceinline__ bool ctp_collides(double c, double clr) { return !(c >= clr) | isinf(c); }
+
+// ---- ESDFMap::gradientInVoxelCenter (src/esdf_map.cpp:167-227) --------------------------
+template <int L>
+__device__ __forceinline__ void esdf_gradient(const MapDev &M, double px, double py, double pz,
+                                              double g[3], double vc[3]) {
+  const double q[3] = {ctp_w2i(px, M.cx, M.s1, M.s2), ctp_w2i(py, M.cy, M.s1, M.s2),
+                       ctp_w2i(pz, M.cz, M.s1, M.s2)};
+  vc[0] = M.mex + q[0] * M.dp;  // getRealPosFromIndex(pos_in_box) (:181, :123-128)
+  vc[1] = M.mey + q[1] * M.dp;
+  vc[2] = M.mez + q[2] * M.dp;
+  double d[3];
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    const double rr = round(q[ax]);
+    // (int)round(NaN or out of range) is INT_MIN on x86-64: both neighbours out of range
+    const bool sane = (rr >= -2147483648.0) & (rr <= 2147483647.0);
+    const double rp = rr + 1.0, rm = rr - 1.0;
+    double dval = 0.0, dd = 0.0;
+    if (sane & (rp >= 0.0) & (rp < M.nd)) {
+      dval += esdf_interp<L>(M, ax == 0 ? q[0] + 1.0 : q[0], ax == 1 ? q[1] + 1.0 : q[1],
+                             ax == 2 ? q[2] + 1.0 : q[2]);
+      dd += M.nd;
+    }
+    if (sane & (rm >= 0.0) & (rm < M.nd)) {
+      dval -= esdf_interp<L>(M, ax == 0 ? q[0] + -1.0 : q[0], ax == 1 ? q[1] + -1.0 : q[1],
+                             ax == 2 ? q[2] + -1.0 : q[2]);
+      dd += M.nd;
+    }
+    d[ax] = dval / dd;
+  }
+  const double z = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];  // .normalized() (:226)
+  if (z > 0.0) {
+    const double s = sqrt(z);
+    d[0] /= s;
+    d[1] /= s;
+    d[2] /= s;
+  }
+  g[0] = d[0];
+  g[1] = d[1];
+  g[2] = d[2];
+}
+
+// ---- point-wise batch kernels ------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(256) k_clearance(MapDev M, const double *__restrict__ xyz,
+                                                   int64_t m, double *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = esdf_clearance<L>(M, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+}
+
+template <int L>
+__global__ void __launch_bounds__(256) k_in_collision(MapDev M, const double *__restrict__ xyz,
+                                                      int64_t m, double clr,
+                                                      uint8_t *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = ctp_collides(esdf_clearance<L>(M, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), clr);
+}
+
+template <int L>
+__global__ void __launch_bounds__(256) k_gradient(MapDev M, const double *__restrict__ xyz,
+                                                  int64_t m, double *__restrict__ grad,
+                                                  double *__restrict__ centre) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double g[3], c[3];
+    esdf_gradient<L>(M, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], g, c);
+    grad[3 * i] = g[0]; grad[3 * i + 1] = g[1]; grad[3 * i + 2] = g[2];
+    centre[3 * i] = c[0]; centre[3 * i + 1] = c[1]; centre[3 * i + 2] = c[2];
+  }
+}
+
+// ---- segment march (src/base_map.cpp:49-74 and :77-97) ----------------------------------
+// Where the endpoints of edge e come from.
+struct EdgeSrc {
+  const double *a;      // pairs mode: a[e], b[e];  indexed mode: node table
+  const double *b;
+  const int32_t *from;  // indexed mode (may be NULL => from = e / k within a query)
+  const int32_t *to;    // indexed mode: to[e] (local index, <0 = no neighbour)
+  int64_t n;            // nodes per query (indexed)
+  int k;                // neighbours per node when from == NULL
+  int indexed;
+};
+
+struct EdgeOut {
+  uint8_t *free_out;
+  double *hit;
+  int32_t *hit_idx;
+  int32_t *lookups;
+  unsigned long long *total_lookups;  // device counter, one atomic per warp
+};
+
+// One group of G lanes marches one segment, G consecutive samples per step, in the
+// reference's sample order; a warp-wide ballot gives each group its first colliding lane, so
+// the verdict, the first-hit index and the count of lookups "up to and including the first
+// hit" are exactly the sequential ones.  Groups run a persistent strided loop over edges and
+// re-arm independently, so lanes stay busy when neighbouring edges differ in length or
+// exit early.
+template <int L, int G>
+__global__ void __launch_bounds__(256) k_edge_march(MapDev M, EdgeSrc S, int64_t m, double clr,
+                                                    double cdc, int guards, EdgeOut O) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % G;
+  const int gshift = lane - sub;
+  const unsigned gmask = (G == 32) ? full : ((1u << G) - 1u);
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
+  int64_t e = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G - n_groups;
+
+  bool active = false;
+  double ax = 0, ay = 0, az = 0, vx = 0, vy = 0, vz = 0, npts = 1.0;
+  int idx0 = 1, n_last = 0;
+  unsigned long long my_lookups = 0;  // only meaningful on sub == 0
+
+  for (;;) {
+    if (!active) {
+      for (;;) {
+        e += n_groups;
+        if (e >= m) break;
+        const double *pa, *pb;
+        bool missing = false;
+        if (S.indexed) {
+          int64_t fi, ti;
+          const int32_t t = S.to[e];
+          if (S.from) {
+            fi = S.from[e];
+            ti = t;
+          } else {  // batched PRM: e = (query*n + node)*k + slot, indices local to the query
+            const int64_t row = e / S.k;
+            const int64_t qbase = (row / S.n) * S.n;
+            fi = row;
+            ti = qbase + t;
+          }
+          missing = t < 0;
+          pa = S.a + 3 * fi;
+          pb = S.a + 3 * (missing ? fi : ti);
+        } else {
+          pa = S.a + 3 * e;
+          pb = S.b + 3 * e;
+        }
+        double x0 = pa[0], y0 = pa[1], z0 = pa[2];
+        double x1 = pb[0], y1 = pb[1], z1 = pb[2];
+        if (guards) {  // marches from `neigbour` toward `actual` (src/base_map.cpp:82,90)
+          double t0 = x0; x0 = x1; x1 = t0;
+          t0 = y0; y0 = y1; y1 = t0;
+          t0 = z0; z0 = z1; z1 = t0;
+        }
+        vx = x1 - x0;
+        vy = y1 - y0;
+        vz = z1 - z0;
+        ax = x0;
+        ay = y0;
+        az = z0;
+        const double d = sqrt((vx * vx + vy * vy) + vz * vz);
+        npts = ceil((d / cdc) + 1.0);
+        // d < cdc shortcut exists only in ...BetweenNodes (src/base_map.cpp:57-59).
+        // NaN npts: `index < NaN` is false, the reference loop body never runs => free.
+        const bool trivially_free = (!guards && d < cdc) || !(npts == npts) || npts < 2.0;
+        const bool absurd = npts > 2147483647.0;  // reference would spin on int overflow
+        if (missing || trivially_free || absurd) {
+          if (sub == 0) {
+            const bool fr = !missing && !absurd;
+            O.free_out[e] = fr ? 1 : 0;
+            if (O.hit) { O.hit[3 * e] = ctp_nan(); O.hit[3 * e + 1] = ctp_nan(); O.hit[3 * e + 2] = ctp_nan(); }
+            if (O.hit_idx) O.hit_idx[e] = fr ? -1 : -2;
+            if (O.lookups) O.lookups[e] = 0;
+          }
+          continue;
+        }
+        n_last = (int)npts - 1;  // indices 1 .. npts-1 (src/base_map.cpp:64)
+        idx0 = 1;
+        active = true;
+        break;
+      }
+    }
+    if (!__any_sync(full, active)) break;
+
+    const int idx = idx0 + sub;
+    bool coll = false;
+    double px = 0, py = 0, pz = 0;
+    if (active && idx <= n_last) {
+      const double t = (double)idx / npts;  // IEEE division, as (double)index / num_points_path
+      px = ax + vx * t;
+      py = ay + vy * t;
+      pz = az + vz * t;
+      coll = ctp_collides(esdf_clearance<L>(M, px, py, pz), clr);
+    }
+    const unsigned gb = (__ballot_sync(full, coll) >> gshift) & gmask;
+    if (active) {
+      if (gb) {
+        const int first = __ffs(gb) - 1;
+        if (sub == first && O.hit) { O.hit[3 * e] = px; O.hit[3 * e + 1] = py; O.hit[3 * e + 2] = pz; }
+        if (sub == 0) {
+          O.free_out[e] = 0;
+          if (O.hit_idx) O.hit_idx[e] = idx0 + first;
+          if (O.lookups) O.lookups[e] = idx0 + first;
+          my_lookups += (unsigned)(idx0 + first);
+        }
+        active = false;
+      } else {
+        idx0 += G;
+        if (idx0 > n_last) {
+          if (sub == 0) {
+            O.free_out[e] = 1;
+            if (O.hit) { O.hit[3 * e] = ctp_nan(); O.hit[3 * e + 1] = ctp_nan(); O.hit[3 * e + 2] = ctp_nan(); }
+            if (O.hit_idx) O.hit_idx[e] = -1;
+            if (O.lookups) O.lookups[e] = n_last;
+            my_lookups += (unsigned)n_last;
+          }
+          active = false;
+        }
+      }
+    }
+  }
+  if (O.total_lookups) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_lookups += __shfl_xor_sync(full, my_lookups, o);
+    if (lane == 0 && my_lookups) atomicAdd(O.total_lookups, my_lookups);
+  }
+}
+
+// ---- layout builders ----------------------------------------------------------------------
+__global__ void k_build_cell8(const float *__restrict__ plain, int n, float *__restrict__ cell8) {
+  const size_t n1 = (size_t)(n - 1);
+  const size_t cells = n1 * n1 * n1;
+  for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < cells;
+       c += (size_t)gridDim.x * blockDim.x) {
+    const size_t z = c % n1, y = (c / n1) % n1, x = c / (n1 * n1);
+    const float *p = plain + (x * n + y) * n + z;
+    const size_t nn = (size_t)n * n;
+    float4 a = make_float4(p[0], p[1], p[n], p[n + 1]);
+    float4 b = make_float4(p[nn], p[nn + 1], p[nn + n], p[nn + n + 1]);
+    reinterpret_cast<float4 *>(cell8)[2 * c] = a;
+    reinterpret_cast<float4 *>(cell8)[2 * c + 1] = b;
+  }
+}
+
+__global__ void k_build_brick(const float *__restrict__ plain, int n, int nb, float *__restrict__ brick) {
+  const size_t total = (size_t)nb * nb * nb * 64;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total;
+       o += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = o >> 6;
+    const int in = (int)(o & 63);
+    const int bz = (int)(b % nb), by = (int)((b / nb) % nb), bx = (int)(b / ((size_t)nb * nb));
+    const int x = bx * 4 + (in >> 4), y = by * 4 + ((in >> 2) & 3), z = bz * 4 + (in & 3);
+    brick[o] = (x < n && y < n && z < n) ? plain[((size_t)x * n + y) * n + z] : 0.0f;
+  }
+}
+
+__global__ void k_narrow_f64(const double *__restrict__ in, size_t cnt, float *__restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cnt;
+       i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (float)in[i];  // fill_data<double>: map_data is float (include/esdf_map.hpp:43)
+}

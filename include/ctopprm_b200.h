@@ -1,0 +1,194 @@
+/*
+ * ctopprm_b200.h -- C ABI of libctopprm_b200.so: CTopPRM's data-parallel hot path
+ * (ESDF clearance, segment collision checks, PRM build, polyline deformability and
+ * shortening) as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (Myracle1/CTopPRM_Learn, an annotated fork of ctu-mrs/CTopPRM) has no FFI
+ * layer: its seam is the C++ class BaseMap/ESDFMap plus three TopologicalPRMClustering
+ * methods.  Each entry point below names the reference symbol (file:line, relative to the
+ * reference tree) it replaces; include/ctopprm/(asterisk).hpp re-creates the class surface on top.
+ *
+ * Conventions
+ *   - every function returns CTP_OK (0) or a negative CTP_ERR_* code; the message of the last
+ *     failure on the calling thread is available from ctp_last_error().  Nothing here ever
+ *     calls exit() or throws across the boundary.
+ *   - plain pointers and sizes only.  `ctp_x(...)` takes HOST buffers and is synchronous
+ *     (copies in, launches, copies out, waits).  `ctp_x_dev(...)` takes DEVICE buffers that
+ *     live on the map's device and only enqueues work on `stream` (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream).
+ *   - one handle per (map, device).  Calls on one handle share a scratch workspace and must
+ *     be issued on one stream at a time; distinct handles may be driven from distinct host
+ *     threads (one per GPU when work is sharded).
+ *   - points are packed xyz doubles (AoS, 24 B), exactly the layout of the reference's
+ *     Vector<3> (include/common.hpp:657-658).  NaN clearance = outside the map, and NaN^3 is
+ *     the "no hit" sentinel, both preserved (src/base_map.cpp:10,58,73).
+ *   - there is no CPU fallback: without a CUDA device every call fails with CTP_ERR_CUDA.
+ */
+#ifndef CTOPPRM_B200_H
+#define CTOPPRM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTP_OK 0
+#define CTP_ERR_INVALID (-1)       /* bad argument */
+#define CTP_ERR_CUDA (-2)          /* CUDA runtime error (message has the cudaError string) */
+#define CTP_ERR_NOMEM (-3)         /* device allocation failed */
+#define CTP_ERR_NEED_CANDIDATES (-4) /* candidate stream exhausted before n nodes were accepted */
+#define CTP_ERR_SAMPLE_PATH (-5)   /* samplePath cursor overrun: reference exit(1), src/base_map.cpp:127-133 */
+#define CTP_ERR_CAPACITY (-6)      /* caller-provided output capacity too small */
+
+/* device grid layouts (bit flags for ctp_map_create, single value for ctp_map_set_layout) */
+#define CTP_LAYOUT_PLAIN 1 /* [x][y][z] f32 exactly as the .npy record (include/esdf_map.hpp:55-66) */
+#define CTP_LAYOUT_CELL8 2 /* one 32-byte record per cell holding its 8 corners: 1 sector / lookup */
+#define CTP_LAYOUT_TEX 4   /* layered 2-D CUDA array, 2x2 (y,z) footprints fetched with tld4 */
+#define CTP_LAYOUT_BRICK 8 /* 4x4x4-voxel bricks (256 B), keeps the plain footprint L2-friendly */
+
+#define CTP_EDGE_NODES 0  /* BaseMap::isSimplePathFreeBetweenNodes  src/base_map.cpp:49-74 */
+#define CTP_EDGE_GUARDS 1 /* BaseMap::isSimplePathFreeBetweenGuards src/base_map.cpp:77-97 */
+
+typedef struct ctp_map ctp_map;
+
+const char *ctp_last_error(void);
+int ctp_version(void);
+int ctp_device_count(int *count);
+
+/* ---- ESDFMap::load + fill_data (src/esdf_map.cpp:6-72, include/esdf_map.hpp:55-66) ----
+ * vox: n*n*n host floats in .npy order (x*n*n + y*n + z).  The f64 variant narrows to float
+ * as fill_data<double> does.  layouts: OR of CTP_LAYOUT_* to materialise on the device
+ * (PLAIN is always kept); the first set bit in the order TEX, CELL8, BRICK, PLAIN becomes the
+ * active one unless changed with ctp_map_set_layout. */
+int ctp_map_create(const float *vox, int n, const double centroid[3], const double extents[3],
+                   int device, int layouts, ctp_map **out);
+int ctp_map_create_f64(const double *vox, int n, const double centroid[3],
+                       const double extents[3], int device, int layouts, ctp_map **out);
+int ctp_map_destroy(ctp_map *map);
+int ctp_map_set_layout(ctp_map *map, int layout);
+/* ESDFMap::getMinPos/getMaxPos (src/esdf_map.cpp:75-76) and bookkeeping.
+ * info[0..2]=min, [3..5]=max, [6]=n, [7]=active layout, [8]=device, [9]=device bytes held */
+int ctp_map_info(const ctp_map *map, double info[10]);
+/* pre-size the scratch workspace so later _dev calls never allocate (needed before CUDA
+ * graph capture).  q queries x n nodes x m candidates, k neighbours. */
+int ctp_reserve(ctp_map *map, int64_t q, int64_t n, int64_t m, int k);
+/* sum of ESDF lookups executed in reference order by edge-marching kernels since the last
+ * reset (device counter; reading it synchronises the stream). */
+int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int reset);
+
+/* ---- ESDFMap::getClearence (src/esdf_map.cpp:130-165) -> interpolateMapData (:78-121) ---- */
+int ctp_clearance(ctp_map *map, const double *xyz, int64_t m, double *out);
+int ctp_clearance_dev(ctp_map *map, const double *xyz, int64_t m, double *out, void *stream);
+/* ---- BaseMap::isInCollision (src/base_map.cpp:7-12): out[i] = 1 if colliding ---- */
+int ctp_in_collision(ctp_map *map, const double *xyz, int64_t m, double clr, uint8_t *out);
+int ctp_in_collision_dev(ctp_map *map, const double *xyz, int64_t m, double clr, uint8_t *out,
+                         void *stream);
+/* ---- ESDFMap::gradientInVoxelCenter (src/esdf_map.cpp:167-227) ---- */
+int ctp_gradient(ctp_map *map, const double *xyz, int64_t m, double *grad, double *centre);
+int ctp_gradient_dev(ctp_map *map, const double *xyz, int64_t m, double *grad, double *centre,
+                     void *stream);
+
+/* ---- segment checks (src/base_map.cpp:49-74 / :77-97), one directed check per (a[i], b[i]).
+ * free_out[i]=1 if free.  Optional (may be NULL): hit = first colliding sample or NaN^3,
+ * hit_idx = its 1-based march index or -1, lookups = clearance evaluations the reference
+ * would have made (up to and including the first hit).  group = lanes cooperating on one
+ * edge (4, 8, 16, 32; 0 = choose from cdc and the segment lengths). */
+int ctp_edge_check(ctp_map *map, const double *a, const double *b, int64_t m, double clr,
+                   double cdc, int mode, int group, uint8_t *free_out, double *hit,
+                   int32_t *hit_idx, int32_t *lookups);
+int ctp_edge_check_dev(ctp_map *map, const double *a, const double *b, int64_t m, double clr,
+                       double cdc, int mode, int group, uint8_t *free_out, double *hit,
+                       int32_t *hit_idx, int32_t *lookups, void *stream);
+/* same, endpoints given as indices into a node table (nodes: n_nodes x 3) */
+int ctp_edge_check_indexed(ctp_map *map, const double *nodes, int64_t n_nodes,
+                           const int32_t *from, const int32_t *to, int64_t m, double clr,
+                           double cdc, int group, uint8_t *free_out, int32_t *hit_idx,
+                           int32_t *lookups);
+int ctp_edge_check_indexed_dev(ctp_map *map, const double *nodes, int64_t n_nodes,
+                               const int32_t *from, const int32_t *to, int64_t m, double clr,
+                               double cdc, int group, uint8_t *free_out, int32_t *hit_idx,
+                               int32_t *lookups, void *stream);
+
+/* ---- rejection sampling of TopologicalPRMClustering::sampleMultiple
+ * (include/topological_prm_clustering.hpp:299-327), replayed over candidate streams.
+ * q independent queries.  start/goal: q x 3.  cand: q x m x 3 (stream order = draw order of
+ * fillRandomStateInEllipse).  nodes: q x n x 3 with rows 0,1 = start, goal (never tested,
+ * :299-306) and rows 2.. = the first n-2 candidates with !isInCollision, in stream order.
+ * n_filled[q] = rows written (n on success), n_used[q] = candidates the sequential do/while
+ * would have consumed.  accept (optional): q x m bits, 1 = candidate not in collision.
+ * Returns CTP_ERR_NEED_CANDIDATES (outputs still valid) if any query ran out. */
+int ctp_sample_reject(ctp_map *map, const double *start, const double *goal, const double *cand,
+                      int64_t q, int64_t m, double clr, int64_t n, double *nodes,
+                      int32_t *n_filled, int32_t *n_used, uint8_t *accept);
+int ctp_sample_reject_dev(ctp_map *map, const double *start, const double *goal,
+                          const double *cand, int64_t q, int64_t m, double clr, int64_t n,
+                          double *nodes, int32_t *n_filled, int32_t *n_used, uint8_t *accept,
+                          void *stream);
+/* candidate generation on the device: BaseMap::fillRandomStateInEllipse (src/base_map.cpp:29-43)
+ * -> random_ellipsoid_point (src/common.cpp:256-312) with a counter-based generator
+ * (Philox4x32-10 keyed by seed, counter = (query, candidate)); cand: q x m x 3 */
+int ctp_sample_ellipsoid_dev(ctp_map *map, const double *start, const double *goal, int64_t q,
+                             int64_t m, double ratio, int planar, uint64_t seed, double *cand,
+                             void *stream);
+int ctp_sample_ellipsoid(ctp_map *map, const double *start, const double *goal, int64_t q,
+                         int64_t m, double ratio, int planar, uint64_t seed, double *cand);
+
+/* ---- neighbour stage of sampleMultiple (:329-339): exact float32 k-NN.
+ * nodes: q x n x 3 doubles, narrowed to float as :300-326.  idx: q x n x k (self excluded,
+ * ascending (distance, index)), d2 (optional): q x n x k float32 squared distances. */
+int ctp_knn(ctp_map *map, const double *nodes, int64_t q, int64_t n, int k, int32_t *idx,
+            float *d2);
+int ctp_knn_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, int k, int32_t *idx,
+                float *d2, void *stream);
+
+/* ---- PRM build = neighbour stage + the n*k directed checks + symmetric adjacency
+ * (include/topological_prm_clustering.hpp:329-397), for q independent node sets.
+ * Outputs: nbr q x n x k, directed_free q x n x k (both optional), and one CSR per query:
+ * row_ptr q x (n+1) relative to that query's segment, col / w packed back to back with
+ * nnz_off (q+1, int64) giving each query's segment; col ascending within a row;
+ * w = ||to - from|| in FP64 from the double coordinates (:369-371).  cap = capacity of
+ * col / w in entries (2*q*n*k always suffices). */
+int ctp_build_prm(ctp_map *map, const double *nodes, int64_t q, int64_t n, int k, double clr,
+                  double cdc, int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr,
+                  int32_t *col, double *w, int64_t cap, int64_t *nnz_off);
+int ctp_build_prm_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, int k,
+                      double clr, double cdc, int32_t *nbr, uint8_t *directed_free,
+                      int32_t *row_ptr, int32_t *col, double *w, int64_t cap, int64_t *nnz_off,
+                      void *stream);
+/* whole sampleMultiple from host candidate streams to host CSRs in one call (the
+ * end-to-end path bench.py times): ctp_sample_reject + ctp_build_prm without the
+ * intermediate host round trip.  nodes (q x n x 3) is also returned. */
+int ctp_sample_multiple(ctp_map *map, const double *start, const double *goal,
+                        const double *cand, int64_t q, int64_t m, int64_t n, int k, double clr,
+                        double cdc, double *nodes, int32_t *n_filled, int32_t *row_ptr,
+                        int32_t *col, double *w, int64_t cap, int64_t *nnz_off);
+
+/* ---- polylines.  A batch of polylines is a point table pts (total x 3) plus offsets
+ * off (count+1, int32): polyline i = pts[off[i] .. off[i+1]) ---- */
+
+/* BaseMap::samplePath (src/base_map.cpp:105-157): out_off (count+1) gives where each
+ * resampled polyline (int)num_samples[i] points) starts in out. status[i] = 0 or
+ * CTP_ERR_SAMPLE_PATH. */
+int ctp_sample_path(ctp_map *map, const double *pts, const int32_t *off, const double *length,
+                    const double *num_samples, int64_t count, double *out,
+                    const int64_t *out_off, int32_t *status);
+/* BaseMap::isDeformablePath (src/base_map.cpp:160-192) for `pairs` pairs (ia[i], ib[i]) of
+ * polylines; num_check[i] as the caller computes it (ceil(max len / cdc) + 1).
+ * out[i] = 1 deformable, 0 not, CTP_ERR_SAMPLE_PATH (as uint8 0xFB) on overrun. */
+int ctp_deformable(ctp_map *map, const double *pts, const int32_t *off, const double *length,
+                   int64_t count, const int32_t *ia, const int32_t *ib, const double *num_check,
+                   int64_t pairs, double clr, double cdc, uint8_t *out);
+/* TopologicalPRMClustering::shorten_path (include/topological_prm_clustering.hpp:2313-2479)
+ * for `count` polylines at once.  out: count x cap x 3 points, origin: count x cap (index of
+ * the reused input node, -1 for a new push-off node), out_n / out_len / status per polyline
+ * (status 0 ok, 1 = "no point added", original returned; <0 = CTP_ERR_*). */
+int ctp_shorten_path(ctp_map *map, const double *pts, const int32_t *off, const double *length,
+                     int64_t count, int forward, double clr, double cdc, int32_t cap,
+                     double *out, int32_t *origin, int32_t *out_n, double *out_len,
+                     int32_t *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

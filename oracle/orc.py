@@ -1,0 +1,334 @@
+"""ctypes binding of the test oracle (oracle/ctp_oracle.c) and, when built, of the
+reference's own code (oracle/_ref/libctopprm_ref.so).  TEST INFRASTRUCTURE ONLY: imported by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; never by
+the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "_build", "libctp_oracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libctopprm_ref.so")
+
+
+def build(ref_root="/root/reference"):
+    """Compile the oracle (always) and the reference shim build (only where the reference
+    tree is mounted); outputs stay under oracle/_build and oracle/_ref."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+    if os.path.isdir(os.path.join(ref_root, "src")):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref", f"REF={ref_root}"])
+
+
+class _Map(C.Structure):
+    _fields_ = [("vox", C.c_void_p), ("n", C.c_int), ("N", C.c_double), ("c", C.c_double * 3),
+                ("e", C.c_double * 3), ("max_e", C.c_double)]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+_lib = None
+
+
+def _L():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        _lib = C.CDLL(ORACLE_SO)
+        _lib.orc_clearance.restype = C.c_double
+        _lib.orc_interpolate.restype = C.c_double
+        _lib.orc_path_length.restype = C.c_double
+        for f in ("orc_edge_nodes_batch", "orc_edge_guards_batch", "orc_edge_index_batch", "orc_build_prm"):
+            getattr(_lib, f).restype = C.c_int64
+    return _lib
+
+
+class OracleMap:
+    def __init__(self, vox, centroid, extents):
+        self.vox = np.ascontiguousarray(vox, dtype=np.float32)
+        self.n = self.vox.shape[0]
+        self.m = _Map()
+        c = _f64(centroid)
+        e = _f64(extents)
+        _L().orc_map_init(C.byref(self.m), _p(self.vox), C.c_int(self.n), _p(c), _p(e))
+        self.centroid, self.extents = c, e
+
+    def min_pos(self):
+        o = np.empty(3)
+        _L().orc_min_pos(C.byref(self.m), _p(o))
+        return o
+
+    def max_pos(self):
+        o = np.empty(3)
+        _L().orc_max_pos(C.byref(self.m), _p(o))
+        return o
+
+    def interpolate(self, q):
+        q = _f64(q)
+        return _L().orc_interpolate(C.byref(self.m), _p(q))
+
+    def clearance(self, xyz, nthreads=1):
+        xyz = _f64(xyz).reshape(-1, 3)
+        out = np.empty(len(xyz))
+        _L().orc_clearance_batch(C.byref(self.m), _p(xyz), C.c_int64(len(xyz)), _p(out), C.c_int(nthreads))
+        return out
+
+    def gradient(self, xyz, nthreads=1):
+        xyz = _f64(xyz).reshape(-1, 3)
+        g = np.empty_like(xyz)
+        c = np.empty_like(xyz)
+        _L().orc_gradient_batch(C.byref(self.m), _p(xyz), C.c_int64(len(xyz)), _p(g), _p(c), C.c_int(nthreads))
+        return g, c
+
+    def in_collision(self, xyz, clr):
+        c = self.clearance(xyz)
+        return ~np.isfinite(c) | (c < clr)
+
+    def edge_nodes(self, a, b, clr, cdc, nthreads=1, full=True):
+        a = _f64(a).reshape(-1, 3)
+        b = _f64(b).reshape(-1, 3)
+        m = len(a)
+        free = np.empty(m, dtype=np.uint8)
+        hit = np.empty((m, 3)) if full else None
+        hit_idx = np.empty(m, dtype=np.int32) if full else None
+        lookups = np.empty(m, dtype=np.int32) if full else None
+        tot = _L().orc_edge_nodes_batch(C.byref(self.m), _p(a), _p(b), C.c_int64(m), C.c_double(clr), C.c_double(cdc),
+                                        _p(free), _p(hit), _p(hit_idx), _p(lookups), C.c_int(nthreads))
+        return free.astype(bool), hit, hit_idx, lookups, int(tot)
+
+    def edge_guards(self, a, b, clr, cdc, nthreads=1):
+        a = _f64(a).reshape(-1, 3)
+        b = _f64(b).reshape(-1, 3)
+        free = np.empty(len(a), dtype=np.uint8)
+        tot = _L().orc_edge_guards_batch(C.byref(self.m), _p(a), _p(b), C.c_int64(len(a)), C.c_double(clr),
+                                         C.c_double(cdc), _p(free), C.c_int(nthreads))
+        return free.astype(bool), int(tot)
+
+    def edge_index(self, nodes, frm, to, clr, cdc, nthreads=1):
+        nodes = _f64(nodes).reshape(-1, 3)
+        frm = np.ascontiguousarray(frm, dtype=np.int32)
+        to = np.ascontiguousarray(to, dtype=np.int32)
+        free = np.empty(len(frm), dtype=np.uint8)
+        hit_idx = np.empty(len(frm), dtype=np.int32)
+        tot = _L().orc_edge_index_batch(C.byref(self.m), _p(nodes), _p(frm), _p(to), C.c_int64(len(frm)),
+                                        C.c_double(clr), C.c_double(cdc), _p(free), _p(hit_idx), C.c_int(nthreads))
+        return free.astype(bool), hit_idx, int(tot)
+
+    def deformable(self, p1, len1, p2, len2, num_check, clr, cdc):
+        p1 = _f64(p1).reshape(-1, 3)
+        p2 = _f64(p2).reshape(-1, 3)
+        return _L().orc_deformable(C.byref(self.m), _p(p1), C.c_int(len(p1)), C.c_double(len1), _p(p2),
+                                   C.c_int(len(p2)), C.c_double(len2), C.c_double(num_check), C.c_double(clr),
+                                   C.c_double(cdc))
+
+    def deformable_between(self, s, e, b1, b2, clr, cdc):
+        s, e, b1, b2 = (_f64(x) for x in (s, e, b1, b2))
+        return _L().orc_deformable_between(C.byref(self.m), _p(s), _p(e), _p(b1), _p(b2), C.c_double(clr), C.c_double(cdc))
+
+    def path_collision_free(self, pts, clr, cdc):
+        pts = _f64(pts).reshape(-1, 3)
+        hit = np.empty(3)
+        r = _L().orc_path_collision_free(C.byref(self.m), _p(pts), C.c_int(len(pts)), C.c_double(clr), C.c_double(cdc), _p(hit))
+        return r, hit
+
+    def sample_reject(self, start, goal, cand, clr, n):
+        cand = _f64(cand).reshape(-1, 3)
+        s = _f64(start)
+        g = _f64(goal)
+        nodes = np.zeros((n, 3))
+        accept = np.zeros(len(cand), dtype=np.uint8)
+        used = C.c_int64(0)
+        filled = _L().orc_sample_reject(C.byref(self.m), _p(s), _p(g), _p(cand), C.c_int64(len(cand)), C.c_double(clr),
+                                        C.c_int(n), _p(nodes), _p(accept), C.byref(used))
+        return nodes, filled, used.value, accept.astype(bool)
+
+    def build_prm(self, nodes, clr, cdc, k=13, nthreads=1):
+        nodes = _f64(nodes).reshape(-1, 3)
+        n = len(nodes)
+        nbr = np.empty((n, k), dtype=np.int32)
+        dfree = np.empty((n, k), dtype=np.uint8)
+        row_ptr = np.empty(n + 1, dtype=np.int32)
+        col = np.empty(2 * n * k, dtype=np.int32)
+        w = np.empty(2 * n * k)
+        lookups = C.c_int64(0)
+        nnz = _L().orc_build_prm(C.byref(self.m), _p(nodes), C.c_int(n), C.c_int(k), C.c_double(clr), C.c_double(cdc),
+                                 _p(nbr), _p(dfree), _p(row_ptr), _p(col), _p(w), C.byref(lookups), C.c_int(nthreads))
+        return dict(nbr=nbr, directed_free=dfree.astype(bool), row_ptr=row_ptr, col=col[:nnz], w=w[:nnz],
+                    lookups=lookups.value)
+
+    def shorten_path(self, pts, length, forward, clr, cdc, cap=None):
+        pts = _f64(pts).reshape(-1, 3)
+        if cap is None:
+            cap = len(pts) + 64
+        out = np.empty((cap, 3))
+        origin = np.empty(cap, dtype=np.int32)
+        out_len = C.c_double(0)
+        status = C.c_int(0)
+        lookups = C.c_int64(0)
+        n = _L().orc_shorten_path(C.byref(self.m), _p(pts), C.c_int(len(pts)), C.c_double(length), C.c_int(int(forward)),
+                                  C.c_double(clr), C.c_double(cdc), _p(out), _p(origin), C.c_int(cap),
+                                  C.byref(out_len), C.byref(status), C.byref(lookups))
+        return out[:n].copy(), origin[:n].copy(), out_len.value, status.value, lookups.value
+
+    def remove_equivalent(self, paths, lengths, clr, cdc):
+        off = np.zeros(len(paths) + 1, dtype=np.int32)
+        for i, p in enumerate(paths):
+            off[i + 1] = off[i] + len(p)
+        pts = _f64(np.concatenate([np.asarray(p).reshape(-1, 3) for p in paths]))
+        lengths = _f64(lengths)
+        keep = np.empty(len(paths), dtype=np.int32)
+        cnt = _L().orc_remove_equivalent(C.byref(self.m), _p(pts), _p(off), _p(lengths), C.c_int(len(paths)),
+                                         C.c_double(clr), C.c_double(cdc), _p(keep))
+        return keep[:cnt].copy()
+
+
+def knn(nodes, k=13, nthreads=1):
+    nodes = _f64(nodes).reshape(-1, 3)
+    n = len(nodes)
+    idx = np.empty((n, k), dtype=np.int32)
+    d2 = np.empty((n, k), dtype=np.float32)
+    _L().orc_knn(_p(nodes), C.c_int(n), C.c_int(k), _p(idx), _p(d2), C.c_int(nthreads))
+    return idx, d2
+
+
+def sample_path(pts, length, num_samples):
+    pts = _f64(pts).reshape(-1, 3)
+    out = np.empty((int(num_samples), 3))
+    rc = _L().orc_sample_path(_p(pts), C.c_int(len(pts)), C.c_double(length), C.c_double(num_samples), _p(out))
+    return out, rc
+
+
+def path_length(pts):
+    pts = _f64(pts).reshape(-1, 3)
+    return _L().orc_path_length(_p(pts), C.c_int(len(pts)))
+
+
+def ellipsoid_point(A, B, two_major, u, g):
+    A, B, g = _f64(A), _f64(B), _f64(g)
+    o = np.empty(3)
+    _L().orc_ellipsoid_point(_p(A), _p(B), C.c_double(two_major), C.c_double(u), _p(g), _p(o))
+    return o
+
+
+# ------------------------------ the reference's own code ---------------------------------
+class RefMap:
+    """The reference's ESDFMap/BaseMap (src/esdf_map.cpp, src/base_map.cpp) compiled against
+    shim headers into oracle/_ref.  Loads a map FILE through the reference's own loader."""
+
+    def __init__(self, filename):
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(REF_SO)
+        self.L = C.CDLL(REF_SO)
+        self.L.ref_map_load.restype = C.c_void_p
+        self.L.ref_clearance.restype = C.c_double
+        self.L.ref_interpolate.restype = C.c_double
+        self.L.ref_edge_nodes_batch.restype = C.c_int64
+        self.L.ref_edge_index_batch.restype = C.c_int64
+        self.h = C.c_void_p(self.L.ref_map_load(filename.encode()))
+        if not self.h:
+            raise RuntimeError("reference ESDFMap::load failed for " + filename)
+
+    def close(self):
+        if self.h:
+            self.L.ref_map_free(self.h)
+            self.h = None
+
+    def min_pos(self):
+        o = np.empty(3)
+        self.L.ref_min_pos(self.h, _p(o))
+        return o
+
+    def max_pos(self):
+        o = np.empty(3)
+        self.L.ref_max_pos(self.h, _p(o))
+        return o
+
+    def clearance(self, xyz):
+        xyz = _f64(xyz).reshape(-1, 3)
+        out = np.empty(len(xyz))
+        self.L.ref_clearance_batch(self.h, _p(xyz), C.c_int64(len(xyz)), _p(out))
+        return out
+
+    def interpolate(self, q):
+        q = _f64(q)
+        return self.L.ref_interpolate(self.h, _p(q))
+
+    def gradient(self, xyz):
+        xyz = _f64(xyz).reshape(-1, 3)
+        g = np.empty_like(xyz)
+        c = np.empty_like(xyz)
+        self.L.ref_gradient_batch(self.h, _p(xyz), C.c_int64(len(xyz)), _p(g), _p(c))
+        return g, c
+
+    def in_collision(self, xyz, clr):
+        xyz = _f64(xyz).reshape(-1, 3)
+        out = np.empty(len(xyz), dtype=np.uint8)
+        self.L.ref_in_collision_batch(self.h, _p(xyz), C.c_int64(len(xyz)), C.c_double(clr), _p(out))
+        return out.astype(bool)
+
+    def edge_nodes(self, a, b, clr, cdc, want_hit=True):
+        a = _f64(a).reshape(-1, 3)
+        b = _f64(b).reshape(-1, 3)
+        free = np.empty(len(a), dtype=np.uint8)
+        hit = np.empty((len(a), 3)) if want_hit else None
+        self.L.ref_edge_nodes_batch(self.h, _p(a), _p(b), C.c_int64(len(a)), C.c_double(clr), C.c_double(cdc), _p(free), _p(hit))
+        return free.astype(bool), hit
+
+    def edge_index(self, nodes, frm, to, clr, cdc):
+        nodes = _f64(nodes).reshape(-1, 3)
+        frm = np.ascontiguousarray(frm, dtype=np.int32)
+        to = np.ascontiguousarray(to, dtype=np.int32)
+        free = np.empty(len(frm), dtype=np.uint8)
+        self.L.ref_edge_index_batch(self.h, _p(nodes), _p(frm), _p(to), C.c_int64(len(frm)), C.c_double(clr),
+                                    C.c_double(cdc), _p(free))
+        return free.astype(bool)
+
+    def edge_guards(self, a, b, clr, cdc):
+        a = _f64(a).reshape(-1, 3)
+        b = _f64(b).reshape(-1, 3)
+        free = np.empty(len(a), dtype=np.uint8)
+        self.L.ref_edge_guards_batch(self.h, _p(a), _p(b), C.c_int64(len(a)), C.c_double(clr), C.c_double(cdc), _p(free))
+        return free.astype(bool)
+
+    def sample_path(self, pts, length, num_samples):
+        pts = _f64(pts).reshape(-1, 3)
+        out = np.empty((int(num_samples), 3))
+        self.L.ref_sample_path(self.h, _p(pts), C.c_int(len(pts)), C.c_double(length), C.c_double(num_samples), _p(out))
+        return out
+
+    def deformable(self, p1, len1, p2, len2, num_check, clr, cdc):
+        p1 = _f64(p1).reshape(-1, 3)
+        p2 = _f64(p2).reshape(-1, 3)
+        return self.L.ref_deformable(self.h, _p(p1), C.c_int(len(p1)), C.c_double(len1), _p(p2), C.c_int(len(p2)),
+                                     C.c_double(len2), C.c_double(num_check), C.c_double(clr), C.c_double(cdc))
+
+    def deformable_between(self, s, e, b1, b2, clr, cdc):
+        s, e, b1, b2 = (_f64(x) for x in (s, e, b1, b2))
+        return self.L.ref_deformable_between(self.h, _p(s), _p(e), _p(b1), _p(b2), C.c_double(clr), C.c_double(cdc))
+
+    def path_collision_free(self, pts, clr, cdc):
+        pts = _f64(pts).reshape(-1, 3)
+        hit = np.empty(3)
+        r = self.L.ref_path_collision_free(self.h, _p(pts), C.c_int(len(pts)), C.c_double(clr), C.c_double(cdc), _p(hit))
+        return r, hit
+
+    def fill_random_state_in_ellipse(self, s, g, ratio, planar, u, draws):
+        s, g, draws = _f64(s), _f64(g), _f64(draws)
+        self.L.ref_set_draws(C.c_double(u), _p(draws))
+        o = np.empty(3)
+        self.L.ref_fill_random_state_in_ellipse(self.h, _p(s), _p(g), C.c_double(ratio), C.c_int(int(planar)), _p(o))
+        return o
+
+
+def ref_available():
+    return os.path.exists(REF_SO)

@@ -1,0 +1,122 @@
+// C API over the reference's own ESDFMap / BaseMap code (src/esdf_map.cpp, src/base_map.cpp
+// compiled where they lie, against the shim headers in this directory).  Output:
+// oracle/_ref/libctopprm_ref.so.  TEST INFRASTRUCTURE: used to pin the restatement in
+// oracle/ctp_oracle.c and as the "reference"-kind CPU baseline.  Never linked into the product.
+#include <cstring>
+#include <memory>
+#include "esdf_map.hpp"
+#include "../ctp_oracle.h"
+
+namespace {
+thread_local double g_u = 0.5;
+thread_local double g_g[3] = {1, 0, 0};
+typedef HeapNode<Vector<3>> Node;
+Vector<3> V(const double *p) { return Vector<3>(p[0], p[1], p[2]); }
+void put(const Vector<3> &v, double *o) { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+struct Poly {
+  std::vector<Node> store;
+  std::vector<Node *> ptrs;
+  Poly(const double *pts, int n) : store(n) {
+    for (int i = 0; i < n; i++) { store[i].data = V(pts + 3 * i); store[i].id = i; }
+    for (int i = 0; i < n; i++) ptrs.push_back(&store[i]);
+  }
+};
+}  // namespace
+
+// src/common.cpp:256 needs Eigen::JacobiSVD; served by the oracle restatement with the random
+// draws injected through ref_set_draws() so BaseMap::fillRandomStateInEllipse can still run.
+Vector<3> random_ellipsoid_point(Vector<3> A, Vector<3> B, double two_major_length) {
+  double o[3];
+  orc_ellipsoid_point(A.v, B.v, two_major_length, g_u, g_g, o);
+  return V(o);
+}
+
+extern "C" {
+void *ref_map_load(const char *filename) {
+  try {
+    ESDFMap *m = new ESDFMap();
+    m->load(filename);
+    return m;
+  } catch (...) { return nullptr; }
+}
+void ref_map_free(void *h) { delete static_cast<ESDFMap *>(h); }
+void ref_min_pos(void *h, double *o) { put(static_cast<ESDFMap *>(h)->getMinPos(), o); }
+void ref_max_pos(void *h, double *o) { put(static_cast<ESDFMap *>(h)->getMaxPos(), o); }
+double ref_clearance(void *h, const double *p) { return static_cast<ESDFMap *>(h)->getClearence(V(p)); }
+double ref_interpolate(void *h, const double *q) { return static_cast<ESDFMap *>(h)->interpolateMapData(V(q)); }
+void ref_clearance_batch(void *h, const double *p, int64_t n, double *out) {
+  ESDFMap *m = static_cast<ESDFMap *>(h);
+  for (int64_t i = 0; i < n; i++) out[i] = m->getClearence(V(p + 3 * i));
+}
+void ref_gradient_batch(void *h, const double *p, int64_t n, double *g, double *c) {
+  ESDFMap *m = static_cast<ESDFMap *>(h);
+  for (int64_t i = 0; i < n; i++) {
+    auto r = m->gradientInVoxelCenter(V(p + 3 * i));
+    put(r.first, g + 3 * i);
+    put(r.second, c + 3 * i);
+  }
+}
+void ref_in_collision_batch(void *h, const double *p, int64_t n, double clr, uint8_t *out) {
+  ESDFMap *m = static_cast<ESDFMap *>(h);
+  for (int64_t i = 0; i < n; i++) out[i] = m->isInCollision(V(p + 3 * i), clr);
+}
+// returns number of free edges
+int64_t ref_edge_nodes_batch(void *h, const double *a, const double *b, int64_t n, double clr, double cdc,
+                             uint8_t *free_out, double *hit) {
+  ESDFMap *m = static_cast<ESDFMap *>(h);
+  int64_t nfree = 0;
+  for (int64_t i = 0; i < n; i++) {
+    auto r = m->isSimplePathFreeBetweenNodes(V(a + 3 * i), V(b + 3 * i), clr, cdc);
+    if (free_out) free_out[i] = r.first;
+    if (hit) put(r.second, hit + 3 * i);
+    nfree += r.first;
+  }
+  return nfree;
+}
+int64_t ref_edge_index_batch(void *h, const double *nodes, const int32_t *from, const int32_t *to, int64_t n,
+                             double clr, double cdc, uint8_t *free_out) {
+  ESDFMap *m = static_cast<ESDFMap *>(h);
+  int64_t nfree = 0;
+  for (int64_t i = 0; i < n; i++) {
+    bool f = m->isSimplePathFreeBetweenNodes(V(nodes + 3 * (int64_t)from[i]), V(nodes + 3 * (int64_t)to[i]), clr, cdc).first;
+    if (free_out) free_out[i] = f;
+    nfree += f;
+  }
+  return nfree;
+}
+void ref_edge_guards_batch(void *h, const double *a, const double *b, int64_t n, double clr, double cdc,
+                           uint8_t *free_out) {
+  ESDFMap *m = static_cast<ESDFMap *>(h);
+  for (int64_t i = 0; i < n; i++) free_out[i] = m->isSimplePathFreeBetweenGuards(V(a + 3 * i), V(b + 3 * i), clr, cdc);
+}
+void ref_sample_path(void *h, const double *pts, int npts, double len, double num, double *out) {
+  Poly p(pts, npts);
+  auto s = static_cast<ESDFMap *>(h)->samplePath(p.ptrs, len, num);
+  for (size_t i = 0; i < s.size(); i++) put(s[i], out + 3 * i);
+}
+int ref_deformable(void *h, const double *p1, int n1, double l1, const double *p2, int n2, double l2, double num,
+                   double clr, double cdc) {
+  Poly a(p1, n1), b(p2, n2);
+  return static_cast<ESDFMap *>(h)->isDeformablePath(a.ptrs, l1, b.ptrs, l2, num, clr, cdc);
+}
+int ref_deformable_between(void *h, const double *s, const double *e, const double *b1, const double *b2, double clr,
+                           double cdc) {
+  Node ns(V(s)), ne(V(e)), n1(V(b1)), n2(V(b2));
+  return static_cast<ESDFMap *>(h)->isDeformablePathBetween(&ns, &ne, &n1, &n2, clr, cdc);
+}
+int ref_path_collision_free(void *h, const double *pts, int npts, double clr, double cdc, double *hit) {
+  Poly p(pts, npts);
+  path_with_length<Vector<3>> pl;
+  pl.plan = p.ptrs;
+  pl.length = 0;
+  auto r = static_cast<ESDFMap *>(h)->isPathCollisionFree(pl, clr, cdc);
+  put(r.second, hit);
+  return r.first;
+}
+void ref_set_draws(double u, const double *g) { g_u = u; memcpy(g_g, g, 24); }
+void ref_fill_random_state_in_ellipse(void *h, const double *s, const double *g, double ratio, int planar, double *out) {
+  Node ns(V(s)), ng(V(g)), nn;
+  static_cast<ESDFMap *>(h)->fillRandomStateInEllipse(&nn, &ns, &ng, ratio, planar != 0);
+  put(nn.data, out);
+}
+}
