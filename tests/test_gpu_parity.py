@@ -1,0 +1,334 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed golden
+vectors.  Integer/boolean/index outputs and FP64 values are compared BIT-EXACT
+(array_equal with NaN positions identical) -- tighter than north_star's 1e-5 relative."""
+import numpy as np
+import pytest
+
+from ctopprm_learn_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+CLR, CDC = synth.MIN_CLEARANCE, synth.COLLISION_DISTANCE_CHECK
+ALL_LAYOUTS = capi.LAYOUT_PLAIN | capi.LAYOUT_CELL8 | capi.LAYOUT_TEX | capi.LAYOUT_BRICK
+LAYOUTS = [capi.LAYOUT_PLAIN, capi.LAYOUT_CELL8, capi.LAYOUT_TEX, capi.LAYOUT_BRICK]
+
+
+@pytest.fixture(scope="module")
+def gmap(golden):
+    m = capi.DeviceMap(golden["vox"], golden["centroid"], golden["extents"], layouts=ALL_LAYOUTS)
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
+def c1(orc, c1_map):
+    vox, c, e = c1_map
+    m = capi.DeviceMap(vox, c, e, layouts=ALL_LAYOUTS)
+    yield m, orc.OracleMap(vox, c, e), c, e
+    m.close()
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_golden_pointwise(golden, gmap, layout):
+    gmap.set_layout(layout)
+    assert np.array_equal(gmap.get_min_pos(), golden["min_pos"])
+    assert np.array_equal(gmap.get_max_pos(), golden["max_pos"])
+    assert np.array_equal(gmap.clearance(golden["pts"]), golden["clearance"], equal_nan=True)
+    assert np.array_equal(gmap.in_collision(golden["pts"], CLR), golden["in_collision"])
+    g, c = gmap.gradient(golden["pts"][:1500])
+    assert np.array_equal(g, golden["grad"], equal_nan=True)
+    assert np.array_equal(c, golden["centre"], equal_nan=True)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("group", [0, 4, 8, 16, 32])
+def test_golden_edges(golden, gmap, layout, group):
+    gmap.set_layout(layout)
+    free, hit, hit_idx, lookups = gmap.edge_check(golden["a"], golden["b"], CLR, CDC, group=group)
+    assert np.array_equal(free, golden["free_nodes"])
+    assert np.array_equal(hit, golden["hit"], equal_nan=True)
+    assert np.array_equal(lookups[~free], hit_idx[~free])
+    fg = gmap.edge_check(golden["a"], golden["b"], CLR, CDC, mode=capi.EDGE_GUARDS, group=group)[0]
+    assert np.array_equal(fg, golden["free_guards"])
+    f2 = gmap.edge_check(golden["a"], golden["b"], 0.05, 0.11, group=group)[0]
+    assert np.array_equal(f2, golden["free_nodes_alt"])
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_c1_edges_vs_oracle(c1, layout):
+    m, om, c, e = c1
+    m.set_layout(layout)
+    a, b = synth.random_edges(c, e, 200000, 3, lo=0.0, hi=3.0)
+    m.read_lookups()
+    free, hit, hit_idx, lookups = m.edge_check(a, b, CLR, CDC)
+    f0, h0, hi0, l0, tot = om.edge_nodes(a, b, CLR, CDC, nthreads=8)
+    assert np.array_equal(free, f0)
+    assert np.array_equal(hit, h0, equal_nan=True)
+    assert np.array_equal(hit_idx, hi0)
+    assert np.array_equal(lookups, l0)
+    assert m.read_lookups() == tot  # algorithmic lookup counter used by the roofline
+    p = c + (np.random.default_rng(2).random((300000, 3)) - 0.5) * (e + 0.2)
+    assert np.array_equal(m.clearance(p), om.clearance(p, nthreads=8), equal_nan=True)
+
+
+def test_empty_and_invalid(c1):
+    m, om, c, e = c1
+    assert len(m.clearance(np.zeros((0, 3)))) == 0
+    assert len(m.edge_check(np.zeros((0, 3)), np.zeros((0, 3)), CLR, CDC)[0]) == 0
+    with pytest.raises(capi.CtpError):
+        m.edge_check(np.zeros((1, 3)), np.ones((1, 3)), CLR, 0.0)  # cdc == 0 (reference exits)
+    # NaN endpoints: reference loop never runs => free (src/base_map.cpp:57-64)
+    a = np.array([[np.nan, 0, 0]])
+    assert m.edge_check(a, a + 1, CLR, CDC)[0][0] == om.edge_nodes(a, a + 1, CLR, CDC)[0][0]
+
+
+def test_indexed_edges(c1):
+    m, om, c, e = c1
+    rng = np.random.default_rng(7)
+    nodes = c + (rng.random((5000, 3)) - 0.5) * e * 0.95
+    frm = rng.integers(0, 5000, 60000).astype(np.int32)
+    to = rng.integers(0, 5000, 60000).astype(np.int32)
+    free, hit_idx, lookups = m.edge_check_indexed(nodes, frm, to, CLR, CDC)
+    f0, hi0, _ = om.edge_index(nodes, frm, to, CLR, CDC, nthreads=8)
+    assert np.array_equal(free, f0) and np.array_equal(hit_idx, hi0)
+
+
+def _queries(c, e, q, n, seed):
+    s, g = synth.random_queries(c, e, q, seed)
+    cand = np.stack([synth.ellipsoid_candidates(s[i], g[i], 4 * n, seed * 100 + i) for i in range(q)])
+    return s, g, cand
+
+
+def test_sample_reject(c1):
+    m, om, c, e = c1
+    q, n = 5, 700
+    s, g, cand = _queries(c, e, q, n, 21)
+    nodes, n_filled, n_used, accept = m.sample_reject(s, g, cand, CLR, n)
+    for i in range(q):
+        n0, filled, used, acc = om.sample_reject(s[i], g[i], cand[i], CLR, n)
+        assert filled == n == n_filled[i]
+        assert used == n_used[i]
+        assert np.array_equal(nodes[i], n0)
+        assert np.array_equal(accept[i, :used], acc[:used])
+    # candidate stream too short: reported, outputs still consistent
+    nodes2, nf2, nu2, _ = m.sample_reject(s[:1], g[:1], cand[:1, :50], CLR, n, allow_short=True)
+    n0, filled, used, _ = om.sample_reject(s[0], g[0], cand[0, :50], CLR, n)
+    assert nf2[0] == filled < n and nu2[0] == used == 50
+    assert np.array_equal(nodes2[0, :filled], n0[:filled])
+    with pytest.raises(capi.CtpError) as ei:
+        m.sample_reject(s[:1], g[:1], cand[:1, :50], CLR, n)
+    assert ei.value.code == capi.ERR_NEED_CANDIDATES
+
+
+@pytest.mark.parametrize("k", [1, 5, 13, 16])
+def test_knn_exact(c1, orc, k):
+    m, om, c, e = c1
+    rng = np.random.default_rng(k)
+    pts = c + (rng.random((3, 3000, 3)) - 0.5) * e
+    pts[1, :, 2] = c[2]            # planar query (planar: true => every z equal)
+    pts[2, 100:140] = pts[2, 100]  # duplicates: (distance, index) tie-break
+    idx, d2 = m.knn(pts, k)
+    for i in range(3):
+        i0, d0 = orc.knn(pts[i], k, nthreads=8)
+        assert np.array_equal(idx[i], i0)
+        assert np.array_equal(d2[i], d0)
+
+
+def test_knn_tiny(c1, orc):
+    m, om, c, e = c1
+    pts = c + (np.random.default_rng(0).random((1, 9, 3)) - 0.5)
+    idx, d2 = m.knn(pts, 13)  # fewer than k others: -1 padded
+    i0, _ = orc.knn(pts[0], 13)
+    assert np.array_equal(idx[0], i0) and (idx[0, :, 8:] == -1).all()
+
+
+def _csr_equal(got, q, want):
+    lo, hi = got["nnz_off"][q], got["nnz_off"][q + 1]
+    assert np.array_equal(got["row_ptr"][q], want["row_ptr"])
+    assert np.array_equal(got["col"][lo:hi], want["col"])
+    assert np.array_equal(got["w"][lo:hi], want["w"])  # FP64 weights bit-exact
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_build_prm_csr(c1, layout):
+    m, om, c, e = c1
+    m.set_layout(layout)
+    q, n = 3, 1000
+    s, g, cand = _queries(c, e, q, n, 33)
+    nodes = m.sample_reject(s, g, cand, CLR, n)[0]
+    got = m.build_prm(nodes, CLR, CDC)
+    for i in range(q):
+        want = om.build_prm(nodes[i], CLR, CDC, nthreads=8)
+        assert np.array_equal(got["nbr"][i], want["nbr"])
+        assert np.array_equal(got["directed_free"][i], want["directed_free"])
+        _csr_equal(got, i, want)
+        # adjacency is symmetric with equal weights
+        rp, col = want["row_ptr"], want["col"]
+        pairs = {(r, cc) for r in range(n) for cc in col[rp[r]:rp[r + 1]]}
+        assert all((b, a) in pairs for a, b in pairs)
+
+
+def test_sample_multiple_end_to_end(c1):
+    m, om, c, e = c1
+    q, n = 2, 800
+    s, g, cand = _queries(c, e, q, n, 44)
+    out = m.sample_multiple(s, g, cand, n, CLR, CDC)
+    for i in range(q):
+        n0 = om.sample_reject(s[i], g[i], cand[i], CLR, n)[0]
+        assert np.array_equal(out["nodes"][i], n0)
+        want = om.build_prm(n0, CLR, CDC, nthreads=8)
+        _csr_equal(out, i, want)
+
+
+def _split(g, key_pts, key_off):
+    off = g[key_off]
+    return [g[key_pts][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+def test_golden_polylines(golden, gmap):
+    gmap.set_layout(capi.LAYOUT_PLAIN)
+    polys = _split(golden, "poly_pts", "poly_off")
+    lens, nums = golden["poly_len"], golden["poly_num"]
+    out, st = gmap.sample_path(polys, lens, nums)
+    assert (st == 0).all()
+    assert np.array_equal(np.concatenate(out), golden["sampled"])
+    nc = [float(np.ceil(max(lens[i], lens[j]) / CDC) + 1) for i, j in zip(golden["pair_i"], golden["pair_j"])]
+    d = gmap.deformable(polys, lens, golden["pair_i"], golden["pair_j"], nc, 0.02, CDC)
+    assert np.array_equal(d, golden["deformable"].astype(np.uint8))
+    near = list(golden["near_pts"].reshape(3, -1, 3))
+    nl = golden["near_len"]
+    ia, ib = [0, 0, 1], [1, 2, 2]
+    nc = [float(np.ceil(max(nl[i], nl[j]) / CDC) + 1) for i, j in zip(ia, ib)]
+    d = gmap.deformable(near, nl, ia, ib, nc, -10.0, CDC)
+    assert np.array_equal(d, golden["near_deformable"].astype(np.uint8))
+
+
+def _dijkstra_path(row_ptr, col, w, src, dst):
+    import heapq
+    n = len(row_ptr) - 1
+    dist = np.full(n, np.inf)
+    prev = np.full(n, -1)
+    dist[src] = 0
+    pq = [(0.0, src)]
+    while pq:
+        d, u = heapq.heappop(pq)
+        if d > dist[u]:
+            continue
+        if u == dst:
+            break
+        for e in range(row_ptr[u], row_ptr[u + 1]):
+            v = col[e]
+            nd = d + w[e]
+            if nd < dist[v]:
+                dist[v] = nd
+                prev[v] = u
+                heapq.heappush(pq, (nd, v))
+    if not np.isfinite(dist[dst]):
+        return None, np.inf
+    path = [dst]
+    while path[-1] != src:
+        path.append(prev[path[-1]])
+    return path[::-1], dist[dst]
+
+
+@pytest.fixture(scope="module")
+def roadmap_paths(c1):
+    """A few PRM paths on C1 (start->goal and via random waypoints) to shorten/compare."""
+    m, om, c, e = c1
+    n = 1500
+    s, g = synth.default_query(c, e)
+    cand = synth.ellipsoid_candidates(s, g, 6 * n, 5)
+    out = m.sample_multiple(s[None], g[None], cand[None], n, CLR, CDC)
+    nodes = out["nodes"][0]
+    rp, col, w = out["row_ptr"][0], out["col"], out["w"]
+    paths, lens = [], []
+    rng = np.random.default_rng(3)
+    for via in [None] + list(rng.integers(2, n, 6)):
+        if via is None:
+            p, L = _dijkstra_path(rp, col, w, 0, 1)
+        else:
+            p1, L1 = _dijkstra_path(rp, col, w, 0, int(via))
+            p2, L2 = _dijkstra_path(rp, col, w, int(via), 1)
+            if p1 is None or p2 is None:
+                continue
+            p, L = p1 + p2[1:], None
+        if p is None:
+            continue
+        pts = nodes[p]
+        paths.append(pts)
+        lens.append(float(np.sum(np.sqrt(((pts[1:] - pts[:-1]) ** 2).sum(1)))) if L is None else float(L))
+    assert len(paths) >= 3
+    return paths, lens
+
+
+@pytest.mark.parametrize("forward", [True, False])
+def test_shorten_path(c1, orc, roadmap_paths, forward):
+    m, om, c, e = c1
+    m.set_layout(capi.LAYOUT_PLAIN)
+    paths, _ = roadmap_paths
+    lens = [orc.path_length(p) for p in paths]  # calc_path_length (include/dijkstra.hpp:27-38)
+    got_pts, got_origin, got_len, st = m.shorten_path(paths, lens, forward, CLR, CDC, cap=256)
+    for i, p in enumerate(paths):
+        w_pts, w_origin, w_len, w_st, _ = om.shorten_path(p, lens[i], forward, CLR, CDC, cap=256)
+        assert st[i] == w_st
+        assert np.array_equal(got_pts[i], w_pts)
+        assert np.array_equal(got_origin[i], w_origin)
+        assert got_len[i] == w_len
+        if w_st == 0:
+            # reference self-check (:2463-2473)
+            assert abs(orc.path_length(got_pts[i]) - got_len[i]) <= 1e-4
+            assert got_len[i] <= lens[i] + 1e-9
+
+
+def test_deformable_and_remove_equivalent(c1, roadmap_paths):
+    m, om, c, e = c1
+    m.set_layout(capi.LAYOUT_PLAIN)
+    paths, lens = roadmap_paths
+    P = len(paths)
+    ia = [i for i in range(P) for j in range(i + 1, P)]
+    ib = [j for i in range(P) for j in range(i + 1, P)]
+    nc = [float(np.ceil(max(lens[i], lens[j]) / CDC) + 1) for i, j in zip(ia, ib)]
+    d = m.deformable(paths, lens, ia, ib, nc, CLR, CDC)
+    for t, (i, j) in enumerate(zip(ia, ib)):
+        assert d[t] == om.deformable(paths[i], lens[i], paths[j], lens[j], nc[t], CLR, CDC)
+    # removeEquivalentPaths (:2237-2298) replayed on the host from the batched matrix
+    D = {(i, j): bool(v) for i, j, v in zip(ia, ib, d)}
+    keep = list(range(P))
+    i = 0
+    while i < len(keep):
+        shortest, rm = i, []
+        for j in range(i + 1, len(keep)):
+            a, b = keep[i], keep[j]
+            if D[(min(a, b), max(a, b))]:
+                rm.append(j)
+                if lens[b] < lens[keep[shortest]] and (shortest == i or True):
+                    shortest = j if lens[b] < lens[keep[shortest]] else shortest
+        if shortest != i:
+            keep[i] = keep[shortest]
+        for j in reversed(rm):
+            keep.pop(j)
+        i += 1
+    want = om.remove_equivalent(paths, lens, CLR, CDC)
+    assert len(keep) == len(want)
+
+
+def test_sample_ellipsoid_seeded(c1):
+    m, om, c, e = c1
+    s, g = synth.random_queries(c, e, 3, 8)
+    a = m.sample_ellipsoid(s, g, 20000, 1.2, False, 1234)
+    b = m.sample_ellipsoid(s, g, 20000, 1.2, False, 1234)
+    d = m.sample_ellipsoid(s, g, 20000, 1.2, False, 1235)
+    assert np.array_equal(a, b) and not np.array_equal(a, d)
+    for i in range(3):
+        # inside the prolate spheroid: |p-s| + |p-g| <= ratio * |g-s|
+        two_major = 1.2 * np.linalg.norm(g[i] - s[i])
+        sums = np.linalg.norm(a[i] - s[i], axis=1) + np.linalg.norm(a[i] - g[i], axis=1)
+        assert (sums <= two_major * (1 + 1e-12)).all()
+        # uniform in the spheroid: mean at the centre, axial variance a^2/5
+        ctr = (s[i] + g[i]) / 2
+        assert np.allclose(a[i].mean(0), ctr, atol=0.05 * two_major)
+        ax = (g[i] - s[i]) / np.linalg.norm(g[i] - s[i])
+        var = np.var((a[i] - ctr) @ ax)
+        assert abs(var - (two_major / 2) ** 2 / 5) < 0.05 * (two_major / 2) ** 2
+    pl = m.sample_ellipsoid(s, g, 100, 1.2, True, 1)
+    assert (pl[..., 2] == s[:, None, 2]).all()
