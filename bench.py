@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- edge collision checks/s of the CTopPRM PRM-build hot path on B200.
+
+One step = one pass of TopologicalPRMClustering::sampleMultiple
+(include/topological_prm_clustering.hpp:288-401: rejection sampling -> k-NN(13) -> n*13 directed
+segment marches -> symmetric CSR) over a batch of Q independent start-goal queries on the C2 map
+(random columns, 256^3 voxels @ 0.05 m, 10 000 nodes per query -- BASELINE.json configs[1]; the
+batch is the per-GPU shard of configs[3]).  See DESIGN.md section "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # the reference's CPU code
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from ctopprm_learn_b200 import synth  # noqa: E402
+
+METRIC = "edge collision checks/s"
+UNIT = "edge checks/s"
+K_NN = 13
+WORKLOADS = {
+    # name: (map config, nodes per query, default queries per GPU per step, candidates per node)
+    "C2": ("C2", 10000, 512, 4),
+    "C1": ("C1", 1000, 512, 4),
+    "C3": ("C3", 100000, 4, 4),
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def make_queries(c, e, q_total, n, cand_per_node, lo, hi, out=None):
+    """C4 query set (seed 4); rank slice [lo, hi).  Candidate streams: seed 400000 + query id."""
+    s, g = synth.random_queries(c, e, q_total, 4)
+    s, g = s[lo:hi], g[lo:hi]
+    m = cand_per_node * n
+    cand = out if out is not None else np.empty((hi - lo, m, 3))
+    for i in range(hi - lo):
+        cand[i] = synth.ellipsoid_candidates(s[i], g[i], m, 400000 + lo + i)
+    return np.ascontiguousarray(s), np.ascontiguousarray(g), cand
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=mx, samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class CpuArm:
+    """The reference's CPU implementation of the path: oracle/_ref (the reference's own
+    src/esdf_map.cpp + src/base_map.cpp) when it was built, else the oracle port."""
+
+    def __init__(self, vox, c, e):
+        from oracle import orc
+        self.orc = orc
+        orc.build()
+        self.kind = "reference" if orc.ref_available() else "port"
+        self.om = orc.OracleMap(vox, c, e)
+        self.ref = None
+        self.tmp = None
+        if self.kind == "reference":
+            fd, self.tmp = tempfile.mkstemp(suffix=".npy")
+            os.close(fd)
+            synth.write_map(self.tmp, vox, c, e)
+            self.ref = orc.RefMap(self.tmp)  # ESDFMap::load, nested-vector grid as include/esdf_map.hpp:43
+
+    def run(self, s, g, cand, n, clr, cdc, threads):
+        t0 = time.perf_counter()
+        if self.ref is not None:
+            out = self.ref.sample_multiple_batch(s, g, cand, n, clr, cdc, k=K_NN, nthreads=threads)
+        else:
+            out = self.orc.sample_multiple_batch(self.om, s, g, cand, n, clr, cdc, k=K_NN, nthreads=threads)
+        return time.perf_counter() - t0, out
+
+    def close(self):
+        if self.ref is not None:
+            self.ref.close()
+        if self.tmp:
+            os.unlink(self.tmp)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    mapcfg, n, qdef, cpn = WORKLOADS[args.workload]
+    vox, c, e = synth.make_config_map(mapcfg)
+    clr, cdc = synth.MIN_CLEARANCE, synth.COLLISION_DISTANCE_CHECK
+    cores = cpu_cores()
+    arm = CpuArm(vox, c, e)
+    q_total = (args.queries or qdef) * world
+    # bounded sample: one query per core per step (at least 8), the first queries of the same set
+    q_s = args.cpu_queries or max(8, min(cores, 256))
+    s, g, cand = make_queries(c, e, q_total, n, cpn, 0, min(q_s, q_total))
+    q_s = len(s)
+    for _ in range(args.warmup):
+        arm.run(s[:max(1, q_s // 8)], g[:max(1, q_s // 8)], cand[:max(1, q_s // 8)], n, clr, cdc, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, out = arm.run(s, g, cand, n, clr, cdc, cores)
+        t += dt
+    checks = q_s * n * K_NN * args.steps
+    val = checks / t
+    sample = f"{q_s} of {q_total} queries per step (n={n}, {n * K_NN} directed checks each), OpenMP over queries"
+    line = {
+        "metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, n, args.queries or qdef, cpn, world),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ms_per_query": 1e3 * t / args.steps / q_s * min(cores, q_s),
+        "free_edge_fraction": float(out["n_free"].sum() / (q_s * n * K_NN)),
+    }
+    arm.close()
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, n, q, cpn, world):
+    mapcfg = WORKLOADS[name][0]
+    kind, extent, nvox, nobs, seed, _ = synth.CONFIGS[mapcfg]
+    return {
+        "workload": f"{name}: {kind} ESDF {nvox}^3 voxels @ {extent / nvox:.3f} m (seed {seed}), {n}-node PRM per query "
+                    f"(k-NN {K_NN} -> {n * K_NN} directed edge checks), {q} independent start-goal queries per step per GPU "
+                    f"(C4 query set, seed 4), sampleMultiple = reject + kNN + edge march + CSR",
+        "queries_per_step_per_gpu": q, "nodes_per_query": n, "k": K_NN, "candidates_per_query": cpn * n,
+        "min_clearance": synth.MIN_CLEARANCE, "collision_distance_check": synth.COLLISION_DISTANCE_CHECK,
+        "parallelism": f"queries sharded over {world} GPU(s), map replicated, no data-path collective",
+        "l2": "per-step inputs (candidate streams) exceed the 126 MB L2; the ESDF grid is re-read within a step by design",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (default: per workload)")
+    ap.add_argument("--layout", default="auto", choices=["auto", "plain", "cell8", "tex", "brick"])
+    ap.add_argument("--group", type=int, default=0, help="lanes per edge in the march kernel (0 = library default)")
+    ap.add_argument("--cpu-queries", type=int, default=0, help="size of the CPU baseline sample (queries)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ctopprm_learn_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CTopPRM hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    mapcfg, n, qdef, cpn = WORKLOADS[args.workload]
+    q = args.queries or qdef
+    clr, cdc = synth.MIN_CLEARANCE, synth.COLLISION_DISTANCE_CHECK
+    vox, c, e = synth.make_config_map(mapcfg)
+    layouts = {"auto": capi.LAYOUT_PLAIN, "plain": capi.LAYOUT_PLAIN, "cell8": capi.LAYOUT_CELL8,
+               "tex": capi.LAYOUT_TEX, "brick": capi.LAYOUT_BRICK}
+    layout = layouts[args.layout]
+    if args.layout == "auto":
+        layout = capi.DEFAULT_LAYOUT
+    dmap = capi.DeviceMap(vox, c, e, device=local, layouts=layout | capi.LAYOUT_PLAIN)
+    dmap.set_layout(layout)
+    if args.group:
+        dmap.set_prm_group(args.group)
+
+    # this rank's shard of the query set, staged in page-locked host memory
+    m_c = cpn * n
+    cand_h = capi.pinned_empty((q, m_c, 3), np.float64)
+    s_h, g_h, _ = make_queries(c, e, q * world, n, cpn, rank * q, (rank + 1) * q, out=cand_h)
+
+    stream = torch.cuda.current_stream()
+    cand_d = torch.from_numpy(cand_h).to(dev)
+    s_d, g_d = torch.from_numpy(s_h).to(dev), torch.from_numpy(g_h).to(dev)
+    cap = 2 * q * n * K_NN
+    nodes_d = torch.zeros((q, n, 3), dtype=torch.float64, device=dev)
+    n_filled_d = torch.zeros(q, dtype=torch.int32, device=dev)
+    n_used_d = torch.zeros(q, dtype=torch.int32, device=dev)
+    row_ptr_d = torch.zeros((q, n + 1), dtype=torch.int32, device=dev)
+    col_d = torch.zeros(cap, dtype=torch.int32, device=dev)
+    w_d = torch.zeros(cap, dtype=torch.float64, device=dev)
+    nnz_off_d = torch.zeros(q + 1, dtype=torch.int64, device=dev)
+    dmap.reserve(q, n, m_c, K_NN)
+
+    def step():
+        dmap.sample_reject_dev(s_d, g_d, cand_d, q, m_c, clr, n, nodes_d, n_filled_d, n_used_d, stream=stream)
+        dmap.build_prm_dev(nodes_d, q, n, K_NN, clr, cdc, row_ptr_d, col_d, w_d, cap, nnz_off_d, stream=stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    if int(n_filled_d.min()) < n:
+        raise SystemExit("bench.py: a query ran out of candidates; raise candidates_per_query")
+
+    # ---- timed region: device-resident inputs, CUDA events on the launching stream ----
+    dmap.read_lookups(stream)
+    dmap.read_launches()
+    dmap.profile(True)
+    dmap.profile_read()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    stage_ms, stage_calls = dmap.profile_read()
+    dmap.profile(False)
+    lookups = dmap.read_lookups(stream)
+    launches = dmap.read_launches()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    checks_per_step = q * n * K_NN
+    value = checks_per_step * world * args.steps / (ms_max * 1e-3)
+    nnz_total = int(nnz_off_d[q].item())
+    free_frac = None
+
+    # ---- single-query latency (ms per query, PRM-build part), same device path, q = 1 ----
+    def step1():
+        dmap.sample_reject_dev(s_d, g_d, cand_d, 1, m_c, clr, n, nodes_d, n_filled_d, n_used_d, stream=stream)
+        dmap.build_prm_dev(nodes_d, 1, n, K_NN, clr, cdc, row_ptr_d, col_d, w_d, cap, nnz_off_d, stream=stream)
+    for _ in range(5):
+        step1()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(50):
+        step1()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    single_ms = e0.elapsed_time(e1) / 50
+
+    # ---- end to end through the host-pointer C ABI (pinned host buffers, copies timed) ----
+    e2e = None
+    if not args.no_e2e:
+        out = dict(nodes=capi.pinned_empty((q, n, 3), np.float64), n_filled=capi.pinned_empty((q,), np.int32),
+                   row_ptr=capi.pinned_empty((q, n + 1), np.int32), col=capi.pinned_empty((cap,), np.int32),
+                   w=capi.pinned_empty((cap,), np.float64), nnz_off=capi.pinned_empty((q + 1,), np.int64))
+        k2 = args.e2e_steps or max(2, min(args.steps, 5))
+        for _ in range(2):
+            dmap.sample_multiple(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, out=out)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(k2):
+            dmap.sample_multiple(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, out=out)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        nnz_e = int(out["nnz_off"][q])
+        h2d = int(cand_h.nbytes + s_h.nbytes + g_h.nbytes)
+        d2h = int(out["nodes"].nbytes + out["n_filled"].nbytes + out["row_ptr"].nbytes + out["nnz_off"].nbytes
+                  + nnz_e * 12)
+        e2e = {"value": checks_per_step * world * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / k2, "steps": k2,
+               "api": "ctp_sample_multiple (host candidate streams -> host CSR), wall clock, max over ranks"}
+        assert nnz_e == nnz_total, "host-API CSR differs from the device-API CSR"
+
+    # ---- CPU baseline (rank 0, N = 1): bounded sample of the same queries, all host cores ----
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = cpu_cores()
+        arm = CpuArm(vox, c, e)
+        # single-thread probe on one query, then a sample sized for ~10-20 s of wall time
+        t1, o1 = arm.run(s_h[:1], g_h[:1], cand_h[:1], n, clr, cdc, 1)
+        q_s = args.cpu_queries or int(max(min(cores, q), min(q, cores * 12.0 / max(t1, 1e-3))))
+        q_s = max(1, min(q_s, q, 4 * cores if cores >= 8 else 64))
+        tc, oc = arm.run(s_h[:q_s], g_h[:q_s], cand_h[:q_s], n, clr, cdc, cores)
+        cpu = {"value": q_s * n * K_NN / tc, "unit": UNIT, "cores": cores, "kind": arm.kind,
+               "sample": f"first {q_s} of the step's {q} queries, whole sampleMultiple on the host "
+                         f"({'reference src/esdf_map.cpp + src/base_map.cpp via oracle/_ref' if arm.kind == 'reference' else 'oracle port'}), "
+                         f"OpenMP over queries, {tc:.1f} s",
+               "single_thread_value": n * K_NN / t1}
+        # the GPU results for the same queries must agree with the CPU arm
+        rp = row_ptr_d[:q_s].cpu().numpy()
+        gpu_nnz = rp[:, -1].astype(np.int64)
+        parity = {"queries_checked": int(q_s), "nnz_mismatch": int((gpu_nnz != oc["nnz"]).sum()),
+                  "n_filled_mismatch": int((n_filled_d[:q_s].cpu().numpy() != oc["n_filled"]).sum())}
+        free_frac = float(oc["n_free"].sum() / (q_s * n * K_NN))
+        arm.close()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        edge_ms = stage_ms["edges"]
+        launches_edge = max(1, stage_calls["edges"])
+        alg_bytes = lookups * 32.0
+        achieved = alg_bytes / (edge_ms * 1e-3) / 1e9 if edge_ms > 0 else 0.0
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = tr.get(f"{args.workload}:{dmap.layout_name()}", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args.workload, n, q, cpn, world), layout=dmap.layout_name(),
+                           lanes_per_edge=dmap.prm_group()),
+            "ms_per_query": {"batched": ms_max / args.steps / q, "single_query_latency": single_ms},
+            "lookups_per_s": lookups / (ms_max * 1e-3),
+            "stage_ms_per_step": {k_: v / args.steps for k_, v in stage_ms.items()},
+            "roofline": {"bound": "hbm", "kernel": "k_edge_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes_per_launch": alg_bytes / launches_edge,
+                         "lookups_per_launch": lookups / launches_edge, "ms_per_launch": edge_ms / launches_edge,
+                         "share_of_step": edge_ms / ms},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": cpu,
+            "csr_nnz_per_step": nnz_total, "free_edge_fraction": free_frac, "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    dmap.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

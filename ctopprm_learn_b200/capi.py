@@ -9,6 +9,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 LAYOUT_PLAIN, LAYOUT_CELL8, LAYOUT_TEX, LAYOUT_BRICK = 1, 2, 4, 8
+LAYOUT_NAMES = {1: "plain", 2: "cell8", 4: "tex", 8: "brick"}
+DEFAULT_LAYOUT = LAYOUT_PLAIN  # the layout bench.py uses unless told otherwise
 EDGE_NODES, EDGE_GUARDS = 0, 1
 ERR_NEED_CANDIDATES = -4
 
@@ -39,8 +41,14 @@ _SIGS = {
     "ctp_map_destroy": [_P],
     "ctp_map_set_layout": [_P, _I],
     "ctp_map_info": [_P, _P],
+    "ctp_set_prm_group": [_P, _I],
     "ctp_reserve": [_P, _I64, _I64, _I64, _I],
     "ctp_lookup_counter_read": [_P, _P, _P, _I],
+    "ctp_launch_counter_read": [_P, _P, _I],
+    "ctp_profile": [_P, _I],
+    "ctp_profile_read": [_P, _P, _P, _I],
+    "ctp_host_alloc": [_P, C.c_size_t],
+    "ctp_host_free": [_P],
     "ctp_clearance": [_P, _P, _I64, _P],
     "ctp_clearance_dev": [_P, _P, _I64, _P, _P],
     "ctp_in_collision": [_P, _P, _I64, _D, _P],
@@ -84,6 +92,19 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory (ctp_host_alloc); freed with the array."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    p = C.c_void_p()
+    _check(lib().ctp_host_alloc(C.byref(p), max(1, count * dtype.itemsize)))
+    buf = (C.c_char * max(1, count * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lambda addr=p.value: lib().ctp_host_free(C.c_void_p(addr)))
+    return arr
 
 
 def exported_symbols():
@@ -165,9 +186,18 @@ class DeviceMap:
 
     # -- bookkeeping ---------------------------------------------------------------------
     def info(self):
-        a = np.zeros(10)
+        a = np.zeros(12)
         _check(lib().ctp_map_info(self._h, _ptr(a)))
         return a
+
+    def layout_name(self):
+        return LAYOUT_NAMES[int(self.info()[7])]
+
+    def prm_group(self):
+        return int(self.info()[10])
+
+    def set_prm_group(self, group):
+        _check(lib().ctp_set_prm_group(self._h, group))
 
     def get_min_pos(self):
         return self.info()[0:3]
@@ -185,6 +215,23 @@ class DeviceMap:
         v = C.c_uint64(0)
         _check(lib().ctp_lookup_counter_read(self._h, _stream_ptr(stream), C.byref(v), int(reset)))
         return v.value
+
+    def read_launches(self, reset=True):
+        v = C.c_uint64(0)
+        _check(lib().ctp_launch_counter_read(self._h, C.byref(v), int(reset)))
+        return v.value
+
+    STAGES = ("reject", "knn", "edges", "csr")
+
+    def profile(self, enable=True):
+        _check(lib().ctp_profile(self._h, int(enable)))
+
+    def profile_read(self, reset=True):
+        """-> ({stage: device ms}, {stage: spans}) accumulated since the last reset"""
+        ms = np.zeros(len(self.STAGES))
+        calls = np.zeros(len(self.STAGES), dtype=np.int64)
+        _check(lib().ctp_profile_read(self._h, _ptr(ms), _ptr(calls), int(reset)))
+        return dict(zip(self.STAGES, ms.tolist())), dict(zip(self.STAGES, calls.tolist()))
 
     # -- host-pointer API ----------------------------------------------------------------
     def clearance(self, xyz):

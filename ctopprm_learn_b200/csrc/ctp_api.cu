@@ -57,11 +57,43 @@ struct ctp_map {
   float *d_plain = nullptr, *d_cell8 = nullptr, *d_brick = nullptr;
   cudaArray_t arr = nullptr;
   cudaTextureObject_t tex = 0;
+  int tex_shift = 0;
   Arena ws;  // scratch of the _dev entry points
   Arena io;  // device staging of the host-pointer entry points
   unsigned long long *d_lookups = nullptr;
   int sm_count = 148;
   size_t map_bytes = 0;
+  // stage profiling (ctp_profile): pairs of events recorded on the caller's stream
+  unsigned long long launches = 0;  // kernels enqueued by this handle (ctp_launch_counter_read)
+  int prm_group = 8;  // lanes per edge in ctp_build_prm (kNN edges are ~5-12 samples long)
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;    // pool, two per recorded span
+  std::vector<int> prof_stage;         // stage id of span i (events 2i, 2i+1)
+  size_t prof_used = 0;                // spans recorded since the last read
+};
+
+// RAII span: records an event pair around a stage when profiling is on
+struct StageSpan {
+  ctp_map *m;
+  cudaStream_t st;
+  size_t slot = (size_t)-1;
+  StageSpan(ctp_map *mm, int stage, cudaStream_t s) : m(mm), st(s) {
+    if (!m->prof) return;
+    if (m->prof_used * 2 + 2 > m->prof_ev.size()) {
+      for (int i = 0; i < 2; i++) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        m->prof_ev.push_back(e);
+      }
+      m->prof_stage.push_back(stage);
+    }
+    slot = m->prof_used++;
+    m->prof_stage[slot] = stage;
+    cudaEventRecord(m->prof_ev[2 * slot], st);
+  }
+  ~StageSpan() {
+    if (slot != (size_t)-1) cudaEventRecord(m->prof_ev[2 * slot + 1], st);
+  }
 };
 
 static int arena_reserve(Arena &a, size_t bytes) {
@@ -98,6 +130,7 @@ static int map_build_layouts(ctp_map *m) {
     CK(cudaMalloc(&m->d_cell8, bytes));
     m->map_bytes += bytes;
     k_build_cell8<<<m->sm_count * 8, 256>>>(m->d_plain, n, m->d_cell8);
+    m->launches++;
     CK(cudaGetLastError());
   }
   if (m->layouts & CTP_L_BRICK) {
@@ -106,20 +139,26 @@ static int map_build_layouts(ctp_map *m) {
     CK(cudaMalloc(&m->d_brick, bytes));
     m->map_bytes += bytes;
     k_build_brick<<<m->sm_count * 8, 256>>>(m->d_plain, n, nb, m->d_brick);
+    m->launches++;
     CK(cudaGetLastError());
   }
   if (m->layouts & CTP_L_TEX) {
+    // 2-D gather texture, x-slabs laid out as a mosaic (see Corners<CTP_L_TEX>)
+    int shift = 0;
+    while ((size_t)n * (((size_t)n + ((size_t)1 << shift) - 1) >> shift) > 32768 && shift < 16) shift++;
+    const size_t tiles_u = (size_t)1 << shift, tiles_v = ((size_t)n + tiles_u - 1) >> shift;
+    if (tiles_u * n > 32768 || tiles_v * n > 32768)
+      return fail(CTP_ERR_INVALID, "CTP_LAYOUT_TEX supports at most 1024 voxels per axis (2-D gather texture limit)");
+    m->tex_shift = shift;
     cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
-    cudaExtent ext = make_cudaExtent((size_t)n, (size_t)n, (size_t)n);  // width=z, height=y, layers=x
-    CK(cudaMalloc3DArray(&m->arr, &fd, ext, cudaArrayLayered | cudaArrayTextureGather));
-    m->map_bytes += (size_t)n * n * n * 4;
-    cudaMemcpy3DParms cp;
-    memset(&cp, 0, sizeof cp);
-    cp.srcPtr = make_cudaPitchedPtr(m->d_plain, (size_t)n * sizeof(float), (size_t)n, (size_t)n);
-    cp.dstArray = m->arr;
-    cp.extent = ext;
-    cp.kind = cudaMemcpyDeviceToDevice;
-    CK(cudaMemcpy3D(&cp));
+    CK(cudaMallocArray(&m->arr, &fd, tiles_u * n, tiles_v * n, cudaArrayTextureGather));
+    m->map_bytes += tiles_u * tiles_v * (size_t)n * n * 4;
+    for (int x = 0; x < n; x++) {
+      const size_t tu = (size_t)x & (tiles_u - 1), tv = (size_t)x >> shift;
+      CK(cudaMemcpy2DToArrayAsync(m->arr, tu * n * sizeof(float), tv * n, m->d_plain + (size_t)x * n * n,
+                                  (size_t)n * sizeof(float), (size_t)n * sizeof(float), (size_t)n,
+                                  cudaMemcpyDeviceToDevice, 0));
+    }
     cudaResourceDesc rd;
     memset(&rd, 0, sizeof rd);
     rd.resType = cudaResourceTypeArray;
@@ -157,6 +196,8 @@ static void map_fill_params(ctp_map *m, const double c[3], const double e[3]) {
   d.cell8 = m->d_cell8;
   d.brick = m->d_brick;
   d.tex = m->tex;
+  d.tex_cshift = m->tex_shift;
+  d.tex_cmask = (1 << m->tex_shift) - 1;
 }
 
 static int pick_active(int layouts) {
@@ -200,6 +241,7 @@ static int map_create_common(const void *vox, bool is_f64, int n, const double c
         cudaError_t e1 = cudaMemcpy(tmp, (const double *)vox + o, c2 * sizeof(double), cudaMemcpyHostToDevice);
         if (e1 != cudaSuccess) { cudaFree(tmp); CK(e1); }
         k_narrow_f64<<<m->sm_count * 4, 256>>>(tmp, c2, m->d_plain + o);
+        m->launches++;
       }
       cudaError_t e2 = cudaDeviceSynchronize();
       cudaFree(tmp);
@@ -242,6 +284,7 @@ extern "C" int ctp_map_destroy(ctp_map *m) {
   cudaFree(m->d_lookups);
   cudaFree(m->ws.base);
   cudaFree(m->io.base);
+  for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   delete m;
   return CTP_OK;
 }
@@ -255,7 +298,14 @@ extern "C" int ctp_map_set_layout(ctp_map *m, int layout) {
   return CTP_OK;
 }
 
-extern "C" int ctp_map_info(const ctp_map *m, double info[10]) {
+extern "C" int ctp_set_prm_group(ctp_map *m, int group) {
+  REQUIRE(m, "null map");
+  REQUIRE(group == 4 || group == 8 || group == 16 || group == 32, "group must be 4, 8, 16 or 32");
+  m->prm_group = group;
+  return CTP_OK;
+}
+
+extern "C" int ctp_map_info(const ctp_map *m, double info[12]) {
   REQUIRE(m && info, "null");
   info[0] = m->dev.lox; info[1] = m->dev.loy; info[2] = m->dev.loz;
   info[3] = m->dev.hix; info[4] = m->dev.hiy; info[5] = m->dev.hiz;
@@ -263,6 +313,8 @@ extern "C" int ctp_map_info(const ctp_map *m, double info[10]) {
   info[7] = m->active;
   info[8] = m->device;
   info[9] = (double)(m->map_bytes + m->ws.cap + m->io.cap);
+  info[10] = m->prm_group;
+  info[11] = m->sm_count;
   return CTP_OK;
 }
 
@@ -275,6 +327,50 @@ extern "C" int ctp_lookup_counter_read(ctp_map *m, void *stream, uint64_t *looku
   if (reset) CK(cudaMemsetAsync(m->d_lookups, 0, sizeof v, st));
   CK(cudaStreamSynchronize(st));
   *lookups = v;
+  return CTP_OK;
+}
+
+extern "C" int ctp_launch_counter_read(ctp_map *m, uint64_t *launches, int reset) {
+  REQUIRE(m && launches, "null");
+  *launches = m->launches;
+  if (reset) m->launches = 0;
+  return CTP_OK;
+}
+
+extern "C" int ctp_profile(ctp_map *m, int enable) {
+  REQUIRE(m, "null map");
+  m->prof = enable != 0;
+  return CTP_OK;
+}
+
+extern "C" int ctp_profile_read(ctp_map *m, double ms[CTP_STAGE_COUNT], int64_t calls[CTP_STAGE_COUNT], int reset) {
+  REQUIRE(m && ms, "null");
+  CK(cudaSetDevice(m->device));
+  for (int i = 0; i < CTP_STAGE_COUNT; i++) {
+    ms[i] = 0;
+    if (calls) calls[i] = 0;
+  }
+  for (size_t i = 0; i < m->prof_used; i++) {
+    CK(cudaEventSynchronize(m->prof_ev[2 * i + 1]));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]));
+    const int sg = m->prof_stage[i];
+    if (sg >= 0 && sg < CTP_STAGE_COUNT) {
+      ms[sg] += t;
+      if (calls) calls[sg]++;
+    }
+  }
+  if (reset) m->prof_used = 0;
+  return CTP_OK;
+}
+
+extern "C" int ctp_host_alloc(void **ptr, size_t bytes) {
+  REQUIRE(ptr, "null");
+  CK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return CTP_OK;
+}
+extern "C" int ctp_host_free(void *ptr) {
+  if (ptr) CK(cudaFreeHost(ptr));
   return CTP_OK;
 }
 
@@ -301,6 +397,7 @@ extern "C" int ctp_clearance_dev(ctp_map *m, const double *xyz, int64_t cnt, dou
   CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_L(m, k_clearance<L><<<grid_for(cnt, 256, m->sm_count * 8), 256, 0, st>>>(m->dev, xyz, cnt, out));
+  m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
 }
@@ -313,6 +410,7 @@ extern "C" int ctp_in_collision_dev(ctp_map *m, const double *xyz, int64_t cnt, 
   CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_L(m, k_in_collision<L><<<grid_for(cnt, 256, m->sm_count * 8), 256, 0, st>>>(m->dev, xyz, cnt, clr, out));
+  m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
 }
@@ -325,6 +423,7 @@ extern "C" int ctp_gradient_dev(ctp_map *m, const double *xyz, int64_t cnt, doub
   CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_L(m, k_gradient<L><<<grid_for(cnt, 256, m->sm_count * 8), 256, 0, st>>>(m->dev, xyz, cnt, grad, centre));
+  m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
 }
@@ -399,6 +498,7 @@ static int launch_edges_LG(ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   k_edge_march<L, G><<<(int)blocks, 256, 0, st>>>(m->dev, S, cnt, clr, cdc, guards, O);
+  m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
 }
@@ -561,13 +661,18 @@ extern "C" int ctp_sample_reject_dev(ctp_map *m, const double *start, const doub
   int32_t *d_bc = arena_take<int32_t>(m->ws, (size_t)q * nblk);
   m->ws.used = keep;  // scratch is dead once the three kernels below have run (stream order)
   dim3 grid((unsigned)nblk, (unsigned)q);
+  StageSpan span(m, CTP_STAGE_REJECT, st);
   DISPATCH_L(m, k_reject_flags<L><<<grid, CTP_REJ_BLOCK, 0, st>>>(m->dev, cand, cnt, clr, d_acc, d_bc, nblk));
+  m->launches++;
   CK(cudaGetLastError());
   k_reject_scan<<<(unsigned)q, 1024, 0, st>>>(d_bc, nblk, n, n_filled);
+  m->launches++;
   CK(cudaGetLastError());
   // n_used defaults to "whole stream consumed"; the scatter pass overwrites it when n-2 were found
   k_fill_i32<<<grid_for(q, 256, 1024), 256, 0, st>>>(n_used, q, (int32_t)cnt);
+  m->launches++;
   k_reject_scatter<<<grid, CTP_REJ_BLOCK, 0, st>>>(cand, start, goal, d_acc, d_bc, nblk, cnt, n, nodes, n_used);
+  m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
 }
@@ -611,6 +716,7 @@ extern "C" int ctp_sample_ellipsoid_dev(ctp_map *m, const double *start, const d
   CK(cudaSetDevice(m->device));
   k_sample_ellipsoid<<<grid_for(q * cnt, 256, m->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(
       start, goal, q, cnt, ratio, planar, seed, cand);
+  m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
 }
@@ -645,15 +751,19 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
   int32_t *d_start = arena_take<int32_t>(m->ws, (size_t)q * (mc + 1));
   CK(cudaMemsetAsync(d_cnt, 0, (size_t)q * mc * 4, st));
   k_knn_setup<<<(unsigned)q, 1024, 0, st>>>(nodes, n, mc, d_grid, d_pts);
+  m->launches++;
   CK(cudaGetLastError());
   const int blocks = (int)((total + 255) / 256);
   k_knn_count<<<blocks, 256, 0, st>>>(d_pts, n, total, d_grid, mc, d_cell_of, d_cnt);
+  m->launches++;
   k_knn_scan<<<(unsigned)q, 1024, 0, st>>>(d_grid, mc, d_cnt, d_start);
+  m->launches++;
   k_knn_scatter<<<blocks, 256, 0, st>>>(d_pts, n, total, mc, d_cell_of, d_start, d_cnt, d_sorted);
+  m->launches++;
   CK(cudaGetLastError());
   const int sblocks = (int)((total + 127) / 128);
 #define KNN_CASE(K) \
-  case K: k_knn_search<K><<<sblocks, 128, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, d2); break;
+  case K: k_knn_search<K><<<sblocks, 128, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, d2); m->launches++; break;
   switch (k) {
     KNN_CASE(1) KNN_CASE(2) KNN_CASE(3) KNN_CASE(4) KNN_CASE(5) KNN_CASE(6) KNN_CASE(7) KNN_CASE(8)
     KNN_CASE(9) KNN_CASE(10) KNN_CASE(11) KNN_CASE(12) KNN_CASE(13) KNN_CASE(14) KNN_CASE(15) KNN_CASE(16)
@@ -711,20 +821,33 @@ extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int
   uint8_t *d_free = directed_free ? directed_free : arena_take<uint8_t>(m->ws, edges);
   int32_t *d_deg = arena_take<int32_t>(m->ws, rows);
   int64_t *d_nnz = arena_take<int64_t>(m->ws, q);
-  int rc = knn_launch(m, nodes, q, n, k, d_nbr, nullptr, st);
+  int rc;
+  {
+    StageSpan span(m, CTP_STAGE_KNN, st);
+    rc = knn_launch(m, nodes, q, n, k, d_nbr, nullptr, st);
+  }
   m->ws.used = keep;
   CKR(rc);
   // the n*k directed checks (:355-397), 8 lanes per edge: kNN edges are ~5-12 samples long
   EdgeSrc S{nodes, nullptr, nullptr, d_nbr, n, k, 1};
   EdgeOut O{d_free, nullptr, nullptr, nullptr, m->d_lookups};
-  CKR(launch_edges(m, 8, S, edges, clr, cdc, 0, O, st));
+  {
+    StageSpan span(m, CTP_STAGE_EDGES, st);
+    CKR(launch_edges(m, m->prm_group, S, edges, clr, cdc, 0, O, st));
+  }
+  StageSpan span(m, CTP_STAGE_CSR, st);
   CK(cudaMemsetAsync(d_deg, 0, rows * 4, st));
   const int eb = (int)((edges + 255) / 256), rb = (int)((rows + 255) / 256);
   k_csr_degree<<<eb, 256, 0, st>>>(d_nbr, d_free, n, k, edges, d_deg);
+  m->launches++;
   k_csr_rowptr<<<(unsigned)q, 1024, 0, st>>>(d_deg, n, row_ptr, d_nnz);
+  m->launches++;
   k_csr_query_offsets<<<1, 1024, 0, st>>>(d_nnz, q, nnz_off);
+  m->launches++;
   k_csr_fill<<<eb, 256, 0, st>>>(d_nbr, d_free, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
+  m->launches++;
   k_csr_finish<<<rb, 256, 0, st>>>(nodes, n, rows, row_ptr, nnz_off, cap, col, w);
+  m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
 }

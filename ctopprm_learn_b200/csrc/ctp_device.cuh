@@ -24,6 +24,7 @@ struct MapDev {
   double mex, mey, mez;                // centroid - max_extents_/2 (src/esdf_map.cpp:125)
   int n;
   int nb;                              // bricks per axis
+  int tex_cmask, tex_cshift;           // x-slab mosaic of the gather texture: tile (x & cmask, x >> cshift)
   const float *plain;
   const float *cell8;
   const float *brick;
@@ -66,19 +67,24 @@ template <> struct Corners<CTP_L_CELL8> {
 };
 
 template <> struct Corners<CTP_L_TEX> {
-  // layered 2-D array: layer = x, height = y, width = z.  tld4 returns the 2x2 footprint
-  // around (z0+1, y0+1): .x=(z0,y1) .y=(z1,y1) .z=(z1,y0) .w=(z0,y0)
-  static __device__ __forceinline__ void load(const MapDev &M, int x0, int y0, int z0, float v[8]) {
-    const float fu = (float)(z0 + 1), fv = (float)(y0 + 1);
-    float a0, a1, a2, a3, b0, b1, b2, b3;
-    asm volatile("tld4.r.a2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%7}];"
+  // One 2-D gather texture holding the N x-slabs as a mosaic of (y,z) tiles: slab x sits at tile
+  // (x & cmask, x >> cshift), texel (u,v) = (z + tile_u*N, y + tile_v*N).  (Layered arrays reject
+  // cudaArrayTextureGather on this driver.)  tld4 returns the 2x2 footprint around
+  // (z0+1, y0+1): .x=(z0,y1) .y=(z1,y1) .z=(z1,y0) .w=(z0,y0); it never crosses a tile because
+  // z0+1, y0+1 <= N-1 is established by the caller's range test.
+  static __device__ __forceinline__ void gather(const MapDev &M, int x, int y0, int z0, float &v00, float &v01,
+                                                float &v10, float &v11) {
+    const float fu = (float)(z0 + 1 + (x & M.tex_cmask) * M.n);
+    const float fv = (float)(y0 + 1 + (x >> M.tex_cshift) * M.n);
+    float a0, a1, a2, a3;
+    asm volatile("tld4.r.2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6}];"
                  : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
-                 : "l"(M.tex), "r"(x0), "f"(fu), "f"(fv));
-    asm volatile("tld4.r.a2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%7}];"
-                 : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
-                 : "l"(M.tex), "r"(x0 + 1), "f"(fu), "f"(fv));
-    v[0] = a3; v[1] = a2; v[2] = a0; v[3] = a1;
-    v[4] = b3; v[5] = b2; v[6] = b0; v[7] = b1;
+                 : "l"(M.tex), "f"(fu), "f"(fv));
+    v00 = a3; v01 = a2; v10 = a0; v11 = a1;
+  }
+  static __device__ __forceinline__ void load(const MapDev &M, int x0, int y0, int z0, float v[8]) {
+    gather(M, x0, y0, z0, v[0], v[1], v[2], v[3]);
+    gather(M, x0 + 1, y0, z0, v[4], v[5], v[6], v[7]);
   }
 };
 

@@ -33,6 +33,7 @@ extern "C" int ctp_sample_path(ctp_map *m, const double *pts, const int32_t *off
   CK(cudaMemcpyAsync(d_ns, num_samples, count * 8, cudaMemcpyHostToDevice, 0));
   CK(cudaMemcpyAsync(d_oo, out_off, (count + 1) * 8, cudaMemcpyHostToDevice, 0));
   k_sample_path<<<(int)((count + 63) / 64), 64>>>(d_p, d_off, d_len, d_ns, count, d_out, d_oo, d_st);
+  m->launches++;
   CK(cudaGetLastError());
   if (otot) CK(cudaMemcpyAsync(out, d_out, otot * 24, cudaMemcpyDeviceToHost, 0));
   CK(cudaMemcpyAsync(status, d_st, count * 4, cudaMemcpyDeviceToHost, 0));
@@ -78,6 +79,7 @@ extern "C" int ctp_deformable(ctp_map *m, const double *pts, const int32_t *off,
   CK(cudaMemcpyAsync(d_so, soff.data(), (pairs + 1) * 8, cudaMemcpyHostToDevice, 0));
   DISPATCH_L(m, k_deformable<L><<<(unsigned)pairs, CTP_PATH_BLOCK>>>(m->dev, d_p, d_off, d_len, d_ia, d_ib, d_nc, d_so,
                                                                       d_scr, clr, cdc, d_out));
+  m->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d_out, pairs, cudaMemcpyDeviceToHost, 0));
   CK(cudaStreamSynchronize(0));
@@ -122,6 +124,7 @@ extern "C" int ctp_shorten_path(ctp_map *m, const double *pts, const int32_t *of
   CK(cudaMemsetAsync(d_out, 0, count * cap * 24, 0));
   DISPATCH_L(m, k_shorten<L><<<(unsigned)count, CTP_PATH_BLOCK>>>(m->dev, d_p, d_off, d_len, forward, clr, cdc, cap,
                                                                    d_so, d_scr, d_out, d_or, d_on, d_ol, d_st));
+  m->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d_out, count * cap * 24, cudaMemcpyDeviceToHost, 0));
   CK(cudaMemcpyAsync(origin, d_or, count * cap * 4, cudaMemcpyDeviceToHost, 0));

@@ -27,6 +27,7 @@
 #ifndef CTOPPRM_B200_H
 #define CTOPPRM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -44,7 +45,7 @@ extern "C" {
 /* device grid layouts (bit flags for ctp_map_create, single value for ctp_map_set_layout) */
 #define CTP_LAYOUT_PLAIN 1 /* [x][y][z] f32 exactly as the .npy record (include/esdf_map.hpp:55-66) */
 #define CTP_LAYOUT_CELL8 2 /* one 32-byte record per cell holding its 8 corners: 1 sector / lookup */
-#define CTP_LAYOUT_TEX 4   /* layered 2-D CUDA array, 2x2 (y,z) footprints fetched with tld4 */
+#define CTP_LAYOUT_TEX 4   /* 2-D gather texture (x-slab mosaic), 2x2 (y,z) footprints fetched with tld4; n <= 1024 */
 #define CTP_LAYOUT_BRICK 8 /* 4x4x4-voxel bricks (256 B), keeps the plain footprint L2-friendly */
 
 #define CTP_EDGE_NODES 0  /* BaseMap::isSimplePathFreeBetweenNodes  src/base_map.cpp:49-74 */
@@ -68,14 +69,36 @@ int ctp_map_create_f64(const double *vox, int n, const double centroid[3],
 int ctp_map_destroy(ctp_map *map);
 int ctp_map_set_layout(ctp_map *map, int layout);
 /* ESDFMap::getMinPos/getMaxPos (src/esdf_map.cpp:75-76) and bookkeeping.
- * info[0..2]=min, [3..5]=max, [6]=n, [7]=active layout, [8]=device, [9]=device bytes held */
-int ctp_map_info(const ctp_map *map, double info[10]);
+ * info[0..2]=min, [3..5]=max, [6]=n, [7]=active layout, [8]=device, [9]=device bytes held,
+ * [10]=lanes per edge used by ctp_build_prm, [11]=SM count */
+int ctp_map_info(const ctp_map *map, double info[12]);
+/* lanes cooperating on one edge inside ctp_build_prm / ctp_sample_multiple (4, 8, 16 or 32) */
+int ctp_set_prm_group(ctp_map *map, int group);
 /* pre-size the scratch workspace so later _dev calls never allocate (needed before CUDA
  * graph capture).  q queries x n nodes x m candidates, k neighbours. */
 int ctp_reserve(ctp_map *map, int64_t q, int64_t n, int64_t m, int k);
 /* sum of ESDF lookups executed in reference order by edge-marching kernels since the last
  * reset (device counter; reading it synchronises the stream). */
 int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int reset);
+
+/* number of kernels this handle has enqueued since the last reset (host-side counter) */
+int ctp_launch_counter_read(ctp_map *map, uint64_t *launches, int reset);
+/* stage timing of the _dev entry points, the library-side counterpart of the reference's
+ * std::chrono brackets ("prm time clustering", include/topological_prm_clustering.hpp:2557-2561):
+ * while enabled, every stage is bracketed by a CUDA event pair on the caller's stream.
+ * ctp_profile_read waits for the recorded events and returns the summed device ms and the
+ * number of spans per stage since the last reset.  Do not enable during stream capture. */
+#define CTP_STAGE_REJECT 0 /* ctp_sample_reject_dev: clearance test + ordered compaction */
+#define CTP_STAGE_KNN 1    /* neighbour stage of ctp_build_prm_dev */
+#define CTP_STAGE_EDGES 2  /* the n*k directed segment marches (k_edge_march) */
+#define CTP_STAGE_CSR 3    /* symmetric union + CSR emit */
+#define CTP_STAGE_COUNT 4
+int ctp_profile(ctp_map *map, int enable);
+int ctp_profile_read(ctp_map *map, double ms[CTP_STAGE_COUNT], int64_t calls[CTP_STAGE_COUNT], int reset);
+/* page-locked host memory for the host-pointer entry points (plain cudaHostAlloc/cudaFreeHost;
+ * lets a C/C++ caller stage candidate streams and CSR outputs without linking the CUDA runtime) */
+int ctp_host_alloc(void **ptr, size_t bytes);
+int ctp_host_free(void *ptr);
 
 /* ---- ESDFMap::getClearence (src/esdf_map.cpp:130-165) -> interpolateMapData (:78-121) ---- */
 int ctp_clearance(ctp_map *map, const double *xyz, int64_t m, double *out);

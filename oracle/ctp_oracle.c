@@ -489,31 +489,134 @@ void orc_knn(const double *pts64, int n, int k, int32_t *idx, float *d2, int nth
   free(p);
 }
 
+/* Same result as orc_knn (k smallest by (d2, index), self excluded), found through a uniform
+ * grid instead of the O(n^2) scan, so the CPU baseline is not charged for a neighbour search
+ * the reference does with a KD-forest.  tests/test_oracle_prm.py checks it against orc_knn. */
+static inline int knn_less(float da, int32_t ia, float db, int32_t ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+void orc_knn_grid(const double *pts64, int n, int k, int32_t *idx, float *d2, int nthreads) {
+  if (n < 64 || k > 64) {
+    orc_knn(pts64, n, k, idx, d2, nthreads);
+    return;
+  }
+  float *p = (float *)malloc(sizeof(float) * 3 * (size_t)n);
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = 0; i < n; i++)
+    for (int a = 0; a < 3; a++) {
+      float v = (float)pts64[3 * (size_t)i + a];
+      p[3 * (size_t)i + a] = v;
+      if (v < lo[a]) lo[a] = v;
+      if (v > hi[a]) hi[a] = v;
+    }
+  double ext[3], emax = 0;
+  for (int a = 0; a < 3; a++) {
+    ext[a] = (double)hi[a] - (double)lo[a];
+    if (!(ext[a] >= 0)) ext[a] = 0; /* NaN coordinates: everything lands in cell 0 */
+    if (ext[a] > emax) emax = ext[a];
+  }
+  if (!(emax > 0) || !isfinite(emax)) {
+    free(p);
+    orc_knn(pts64, n, k, idx, d2, nthreads);
+    return;
+  }
+  double vol = 1;
+  for (int a = 0; a < 3; a++) vol *= ext[a] > emax * 1e-6 ? ext[a] : emax * 1e-6;
+  double h = cbrt(vol / ((double)n / 2.0));
+  int dim[3];
+  for (;;) {
+    double cells = 1;
+    for (int a = 0; a < 3; a++) {
+      double c = floor(ext[a] / h) + 1;
+      dim[a] = c > 2048 ? 2048 : (int)c;
+      cells *= dim[a];
+    }
+    if (cells <= 4.0 * n + 64) break;
+    h *= 1.25;
+  }
+  const int ncell = dim[0] * dim[1] * dim[2];
+  int32_t *cell_of = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+  int32_t *start = (int32_t *)calloc((size_t)ncell + 1, sizeof(int32_t));
+  int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+  for (int i = 0; i < n; i++) {
+    int c[3];
+    for (int a = 0; a < 3; a++) {
+      double t = floor(((double)p[3 * (size_t)i + a] - (double)lo[a]) / h);
+      c[a] = !(t >= 0) ? 0 : (t >= dim[a] ? dim[a] - 1 : (int)t);
+    }
+    cell_of[i] = (c[2] * dim[1] + c[1]) * dim[0] + c[0];
+    start[cell_of[i] + 1]++;
+  }
+  for (int c = 0; c < ncell; c++) start[c + 1] += start[c];
+  int32_t *cur = (int32_t *)malloc(sizeof(int32_t) * (size_t)ncell);
+  memcpy(cur, start, sizeof(int32_t) * (size_t)ncell);
+  for (int i = 0; i < n; i++) order[cur[cell_of[i]]++] = i;
+  free(cur);
+  int rmax = dim[0] > dim[1] ? dim[0] : dim[1];
+  if (dim[2] > rmax) rmax = dim[2];
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 1 ? nthreads : 1)
+  for (int i = 0; i < n; i++) {
+    float bd[64];
+    int32_t bi[64];
+    int cnt = 0;
+    const float xi = p[3 * (size_t)i], yi = p[3 * (size_t)i + 1], zi = p[3 * (size_t)i + 2];
+    const int ci = cell_of[i];
+    const int cx = ci % dim[0], cy = (ci / dim[0]) % dim[1], cz = ci / (dim[0] * dim[1]);
+    for (int r = 0; r <= rmax; r++) {
+      for (int z = cz - r; z <= cz + r; z++) {
+        if (z < 0 || z >= dim[2]) continue;
+        for (int y = cy - r; y <= cy + r; y++) {
+          if (y < 0 || y >= dim[1]) continue;
+          const int shell_yz = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
+          for (int x = cx - r; x <= cx + r; x += (shell_yz || r == 0) ? 1 : 2 * r) {
+            if (x < 0 || x >= dim[0]) continue;
+            const int c = (z * dim[1] + y) * dim[0] + x;
+            for (int s = start[c]; s < start[c + 1]; s++) {
+              const int j = order[s];
+              if (j == i) continue;
+              const float dx = xi - p[3 * (size_t)j], dy = yi - p[3 * (size_t)j + 1], dz = zi - p[3 * (size_t)j + 2];
+              const float dd = (dx * dx + dy * dy) + dz * dz;
+              if (cnt == k && !knn_less(dd, j, bd[k - 1], bi[k - 1])) continue;
+              int pos = cnt < k ? cnt : k - 1;
+              while (pos > 0 && knn_less(dd, j, bd[pos - 1], bi[pos - 1])) {
+                bd[pos] = bd[pos - 1];
+                bi[pos] = bi[pos - 1];
+                pos--;
+              }
+              bd[pos] = dd;
+              bi[pos] = j;
+              if (cnt < k) cnt++;
+            }
+          }
+        }
+      }
+      /* every unvisited point is more than r*h away along some axis (0.1% slack for the
+       * float binning); strict '<' so equal-distance ties are never cut off */
+      const double lb = (double)r * h * 0.999;
+      if (cnt == k && (double)bd[k - 1] < lb * lb) break;
+    }
+    for (int s = 0; s < k; s++) {
+      idx[(size_t)i * k + s] = s < cnt ? bi[s] : -1;
+      if (d2) d2[(size_t)i * k + s] = s < cnt ? bd[s] : INFINITY;
+    }
+  }
+  free(p);
+  free(cell_of);
+  free(start);
+  free(order);
+}
+
 static int cmp_i32(const void *a, const void *b) {
   int32_t x = *(const int32_t *)a, y = *(const int32_t *)b;
   return (x > y) - (x < y);
 }
 
-int64_t orc_build_prm(const orc_map *m, const double *nodes, int n, int k, double clr,
-                      double cdc, int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr,
-                      int32_t *col, double *w, int64_t *lookups, int nthreads) {
-  /* include/topological_prm_clustering.hpp:329-397 */
-  orc_knn(nodes, n, k, nbr, NULL, nthreads);
-  int64_t total = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : total) \
-    num_threads(nthreads > 1 ? nthreads : 1)
-  for (int64_t e = 0; e < (int64_t)n * k; e++) {
-    int from = (int)(e / k);
-    int to = nbr[e];
-    int32_t nl = 0;
-    int f = 0;
-    if (to >= 0) f = orc_edge_nodes(m, nodes + 3 * (size_t)from, nodes + 3 * (size_t)to, clr, cdc,
-                                     NULL, NULL, &nl);
-    directed_free[e] = (uint8_t)f;
-    total += nl;
-  }
-  if (lookups) *lookups = total;
-  /* symmetric union: visibility_node_ids[to] = visibility_node_ids[from] = norm (:378,384) */
+/* symmetric union of the free directed edges as CSR (cols ascending):
+ * visibility_node_ids[to] = visibility_node_ids[from] = norm (:378,384) */
+int64_t orc_csr_from_directed(const double *nodes, int n, int k, const int32_t *nbr,
+                              const uint8_t *directed_free, int32_t *row_ptr, int32_t *col,
+                              double *w) {
   int32_t *deg = (int32_t *)calloc((size_t)n + 1, sizeof(int32_t));
   for (int64_t e = 0; e < (int64_t)n * k; e++)
     if (directed_free[e]) {
@@ -552,6 +655,73 @@ int64_t orc_build_prm(const orc_map *m, const double *nodes, int n, int k, doubl
   free(tmp_ptr);
   free(tmp);
   return nnz;
+}
+
+int64_t orc_build_prm(const orc_map *m, const double *nodes, int n, int k, double clr,
+                      double cdc, int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr,
+                      int32_t *col, double *w, int64_t *lookups, int nthreads) {
+  /* include/topological_prm_clustering.hpp:329-397 */
+  orc_knn_grid(nodes, n, k, nbr, NULL, nthreads);
+  int64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : total) \
+    num_threads(nthreads > 1 ? nthreads : 1)
+  for (int64_t e = 0; e < (int64_t)n * k; e++) {
+    int from = (int)(e / k);
+    int to = nbr[e];
+    int32_t nl = 0;
+    int f = 0;
+    if (to >= 0) f = orc_edge_nodes(m, nodes + 3 * (size_t)from, nodes + 3 * (size_t)to, clr, cdc,
+                                     NULL, NULL, &nl);
+    directed_free[e] = (uint8_t)f;
+    total += nl;
+  }
+  if (lookups) *lookups = total;
+  return orc_csr_from_directed(nodes, n, k, nbr, directed_free, row_ptr, col, w);
+}
+
+/* Whole sampleMultiple (:288-401) for q independent queries, OpenMP over queries: the CPU
+ * "port" baseline bench.py times.  cand: q x M x 3.  Per query outputs: n_filled, number of
+ * free directed edges, nnz, lookups; optional full outputs (may be NULL): nodes q x n x 3,
+ * row_ptr q x (n+1), col/w q x 2nk.  returns the number of queries that ran out of candidates. */
+int orc_sample_multiple_batch(const orc_map *m, const double *start, const double *goal,
+                              const double *cand, int q, int64_t M, int n, int k, double clr,
+                              double cdc, int nthreads, int32_t *n_filled, int64_t *n_free,
+                              int64_t *nnz, int64_t *lookups, double *nodes_out,
+                              int32_t *row_ptr_out, int32_t *col_out, double *w_out) {
+  int short_q = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : short_q) \
+    num_threads(nthreads > 1 ? nthreads : 1)
+  for (int qi = 0; qi < q; qi++) {
+    const size_t cap = 2 * (size_t)n * k;
+    double *nodes = nodes_out ? nodes_out + 3 * (size_t)qi * n : (double *)malloc(24 * (size_t)n);
+    int32_t *nbr = (int32_t *)malloc(4 * (size_t)n * k);
+    uint8_t *fr = (uint8_t *)malloc((size_t)n * k);
+    int32_t *rp = row_ptr_out ? row_ptr_out + (size_t)qi * (n + 1) : (int32_t *)malloc(4 * ((size_t)n + 1));
+    int32_t *col = col_out ? col_out + (size_t)qi * cap : (int32_t *)malloc(4 * cap);
+    double *w = w_out ? w_out + (size_t)qi * cap : (double *)malloc(8 * cap);
+    int64_t used = 0, lk = 0;
+    const int filled = orc_sample_reject(m, start + 3 * (size_t)qi, goal + 3 * (size_t)qi,
+                                         cand + 3 * (size_t)qi * M, M, clr, n, nodes, NULL, &used);
+    n_filled[qi] = filled;
+    if (filled < n) {
+      short_q++;
+      n_free[qi] = nnz[qi] = 0;
+      if (lookups) lookups[qi] = 0;
+    } else {
+      nnz[qi] = orc_build_prm(m, nodes, n, k, clr, cdc, nbr, fr, rp, col, w, &lk, 1);
+      int64_t f = 0;
+      for (size_t e = 0; e < (size_t)n * k; e++) f += fr[e];
+      n_free[qi] = f;
+      if (lookups) lookups[qi] = lk;
+    }
+    if (!nodes_out) free(nodes);
+    free(nbr);
+    free(fr);
+    if (!row_ptr_out) free(rp);
+    if (!col_out) free(col);
+    if (!w_out) free(w);
+  }
+  return short_q;
 }
 
 /* ---------------------------------- path shortening ----------------------------------- */

@@ -117,6 +117,19 @@ int orc_sample_reject(const orc_map *m, const double start[3], const double goal
  * pts64: n x 3 doubles, narrowed to float exactly as :300-326 does.  idx: n x k, d2: n x k. */
 void orc_knn(const double *pts64, int n, int k, int32_t *idx, float *d2, int nthreads);
 
+/* same result through a uniform grid (used by orc_build_prm; checked against orc_knn) */
+void orc_knn_grid(const double *pts64, int n, int k, int32_t *idx, float *d2, int nthreads);
+/* :374-385 symmetric union of the free directed edges as CSR; returns nnz */
+int64_t orc_csr_from_directed(const double *nodes, int n, int k, const int32_t *nbr,
+                              const uint8_t *directed_free, int32_t *row_ptr, int32_t *col,
+                              double *w);
+/* whole sampleMultiple (:288-401) for q queries, OpenMP over queries (CPU "port" baseline) */
+int orc_sample_multiple_batch(const orc_map *m, const double *start, const double *goal,
+                              const double *cand, int q, int64_t M, int n, int k, double clr,
+                              double cdc, int nthreads, int32_t *n_filled, int64_t *n_free,
+                              int64_t *nnz, int64_t *lookups, double *nodes_out,
+                              int32_t *row_ptr_out, int32_t *col_out, double *w_out);
+
 /* :355-397 directed checks + symmetric adjacency as CSR (cols ascending).
  * directed_free: n x k.  row_ptr: n+1, col/w sized for 2*n*k.  returns nnz. */
 int64_t orc_build_prm(const orc_map *m, const double *nodes, int n, int k, double clr,

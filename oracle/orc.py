@@ -192,6 +192,46 @@ class OracleMap:
         return keep[:cnt].copy()
 
 
+def _sample_multiple_batch(fn, handle, start, goal, cand, n, k, clr, cdc, nthreads, full, with_lookups):
+    start = _f64(start).reshape(-1, 3)
+    goal = _f64(goal).reshape(-1, 3)
+    q = len(start)
+    cand = _f64(cand).reshape(q, -1, 3)
+    M = cand.shape[1]
+    n_filled = np.zeros(q, dtype=np.int32)
+    n_free = np.zeros(q, dtype=np.int64)
+    nnz = np.zeros(q, dtype=np.int64)
+    lookups = np.zeros(q, dtype=np.int64)
+    out = dict(n_filled=n_filled, n_free=n_free, nnz=nnz)
+    bufs = [None] * 4
+    if full:
+        bufs = [np.empty((q, n, 3)), np.empty((q, n + 1), dtype=np.int32), np.empty((q, 2 * n * k), dtype=np.int32),
+                np.empty((q, 2 * n * k))]
+        out.update(nodes=bufs[0], row_ptr=bufs[1], col=bufs[2], w=bufs[3])
+    args = [handle, _p(start), _p(goal), _p(cand), C.c_int(q), C.c_int64(M), C.c_int(n), C.c_int(k), C.c_double(clr),
+            C.c_double(cdc), C.c_int(nthreads), _p(n_filled), _p(n_free), _p(nnz)]
+    if with_lookups:
+        args.append(_p(lookups))
+        out["lookups"] = lookups
+    out["short"] = fn(*args, *[_p(b) for b in bufs])
+    return out
+
+
+def sample_multiple_batch(om, start, goal, cand, n, clr, cdc, k=13, nthreads=1, full=False):
+    """orc_sample_multiple_batch: whole sampleMultiple for q queries with the restatement."""
+    return _sample_multiple_batch(_L().orc_sample_multiple_batch, C.byref(om.m), start, goal, cand, n, k, clr, cdc,
+                                  nthreads, full, True)
+
+
+def knn_grid(nodes, k=13, nthreads=1):
+    nodes = _f64(nodes).reshape(-1, 3)
+    n = len(nodes)
+    idx = np.empty((n, k), dtype=np.int32)
+    d2 = np.empty((n, k), dtype=np.float32)
+    _L().orc_knn_grid(_p(nodes), C.c_int(n), C.c_int(k), _p(idx), _p(d2), C.c_int(nthreads))
+    return idx, d2
+
+
 def knn(nodes, k=13, nthreads=1):
     nodes = _f64(nodes).reshape(-1, 3)
     n = len(nodes)
@@ -321,6 +361,11 @@ class RefMap:
         hit = np.empty(3)
         r = self.L.ref_path_collision_free(self.h, _p(pts), C.c_int(len(pts)), C.c_double(clr), C.c_double(cdc), _p(hit))
         return r, hit
+
+    def sample_multiple_batch(self, start, goal, cand, n, clr, cdc, k=13, nthreads=1, full=False):
+        """ref_sample_multiple_batch: every clearance test done by the reference's own code."""
+        return _sample_multiple_batch(self.L.ref_sample_multiple_batch, self.h, start, goal, cand, n, k, clr, cdc,
+                                      nthreads, full, False)
 
     def fill_random_state_in_ellipse(self, s, g, ratio, planar, u, draws):
         s, g, draws = _f64(s), _f64(g), _f64(draws)

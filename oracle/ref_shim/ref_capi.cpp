@@ -113,6 +113,60 @@ int ref_path_collision_free(void *h, const double *pts, int npts, double clr, do
   put(r.second, hit);
   return r.first;
 }
+// Whole TopologicalPRMClustering::sampleMultiple (include/topological_prm_clustering.hpp:288-401)
+// for q independent queries with the REFERENCE'S OWN isInCollision / isSimplePathFreeBetweenNodes
+// doing every clearance test; the planner header itself cannot be compiled (FLANN, Eigen, yaml-cpp
+// absent; common.hpp broken), so the loop structure (:299-327 rejection, :355-397 directed checks and
+// symmetric adjacency) is driven from here and the neighbour stage is the oracle's exact k-NN.
+// OpenMP over queries: the reference is single-threaded, but its map is read-only, so independent
+// queries can use every host core ("reference" CPU baseline of bench.py).
+int ref_sample_multiple_batch(void *h, const double *start, const double *goal, const double *cand, int q, int64_t M,
+                              int n, int k, double clr, double cdc, int nthreads, int32_t *n_filled, int64_t *n_free,
+                              int64_t *nnz, double *nodes_out, int32_t *row_ptr_out, int32_t *col_out, double *w_out) {
+  ESDFMap *m = static_cast<ESDFMap *>(h);
+  int short_q = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : short_q) num_threads(nthreads > 1 ? nthreads : 1)
+  for (int qi = 0; qi < q; qi++) {
+    const size_t cap = 2 * (size_t)n * k;
+    std::vector<double> nodes_v;
+    std::vector<int32_t> rp_v, col_v;
+    std::vector<double> w_v;
+    double *nodes = nodes_out ? nodes_out + 3 * (size_t)qi * n : (nodes_v.resize(3 * (size_t)n), nodes_v.data());
+    int32_t *rp = row_ptr_out ? row_ptr_out + (size_t)qi * (n + 1) : (rp_v.resize((size_t)n + 1), rp_v.data());
+    int32_t *col = col_out ? col_out + (size_t)qi * cap : (col_v.resize(cap), col_v.data());
+    double *w = w_out ? w_out + (size_t)qi * cap : (w_v.resize(cap), w_v.data());
+    std::vector<int32_t> nbr((size_t)n * k);
+    std::vector<uint8_t> fr((size_t)n * k);
+    memcpy(nodes, start + 3 * (size_t)qi, 24);
+    memcpy(nodes + 3, goal + 3 * (size_t)qi, 24);
+    int filled = 2;
+    const double *cq = cand + 3 * (size_t)qi * M;
+    for (int64_t c = 0; c < M && filled < n; c++)
+      if (!m->isInCollision(V(cq + 3 * c), clr)) {
+        memcpy(nodes + 3 * (size_t)filled, cq + 3 * c, 24);
+        filled++;
+      }
+    n_filled[qi] = filled;
+    if (filled < n) {
+      short_q++;
+      n_free[qi] = nnz[qi] = 0;
+      continue;
+    }
+    orc_knn_grid(nodes, n, k, nbr.data(), nullptr, 1);
+    int64_t f = 0;
+    for (size_t e = 0; e < (size_t)n * k; e++) {
+      const int to = nbr[e];
+      bool ok = false;
+      if (to >= 0) ok = m->isSimplePathFreeBetweenNodes(V(nodes + 3 * (e / k)), V(nodes + 3 * (size_t)to), clr, cdc).first;
+      fr[e] = ok;
+      f += ok;
+    }
+    n_free[qi] = f;
+    nnz[qi] = orc_csr_from_directed(nodes, n, k, nbr.data(), fr.data(), rp, col, w);
+  }
+  return short_q;
+}
+
 void ref_set_draws(double u, const double *g) { g_u = u; memcpy(g_g, g, 24); }
 void ref_fill_random_state_in_ellipse(void *h, const double *s, const double *g, double ratio, int planar, double *out) {
   Node ns(V(s)), ng(V(g)), nn;

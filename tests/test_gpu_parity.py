@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) against the oracle and the committed golden
 vectors.  Integer/boolean/index outputs and FP64 values are compared BIT-EXACT
 (array_equal with NaN positions identical) -- tighter than north_star's 1e-5 relative."""
+import os
+
 import numpy as np
 import pytest
 
@@ -9,8 +11,8 @@ from ctopprm_learn_b200 import capi, synth
 pytestmark = pytest.mark.gpu
 
 CLR, CDC = synth.MIN_CLEARANCE, synth.COLLISION_DISTANCE_CHECK
-ALL_LAYOUTS = capi.LAYOUT_PLAIN | capi.LAYOUT_CELL8 | capi.LAYOUT_TEX | capi.LAYOUT_BRICK
-LAYOUTS = [capi.LAYOUT_PLAIN, capi.LAYOUT_CELL8, capi.LAYOUT_TEX, capi.LAYOUT_BRICK]
+ALL_LAYOUTS = int(os.environ.get("CTP_TEST_LAYOUTS", capi.LAYOUT_PLAIN | capi.LAYOUT_CELL8 | capi.LAYOUT_TEX | capi.LAYOUT_BRICK))
+LAYOUTS = [l for l in (capi.LAYOUT_PLAIN, capi.LAYOUT_CELL8, capi.LAYOUT_TEX, capi.LAYOUT_BRICK) if l & ALL_LAYOUTS]
 
 
 @pytest.fixture(scope="module")

@@ -1,0 +1,80 @@
+"""Host-side checks of the oracle's PRM-build pieces: the grid k-NN against the O(n^2)
+definition, and the batched sampleMultiple of the restatement against the reference's own
+collision code (oracle/_ref) where it is built."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from ctopprm_learn_b200 import synth
+
+CLR, CDC = synth.MIN_CLEARANCE, synth.COLLISION_DISTANCE_CHECK
+
+
+@pytest.mark.parametrize("n,k", [(70, 13), (2500, 13), (4000, 5), (3000, 16)])
+def test_knn_grid_equals_bruteforce(orc, n, k):
+    rng = np.random.default_rng(n + k)
+    pts = rng.random((n, 3)) * np.array([12.0, 9.0, 3.0])
+    pts[10:30] = pts[10]                 # duplicates: (distance, index) tie-break
+    if n == 4000:
+        pts[:, 2] = 1.25                 # planar
+    i0, d0 = orc.knn(pts, k, nthreads=4)
+    i1, d1 = orc.knn_grid(pts, k, nthreads=4)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+
+
+def test_knn_grid_lattice_ties(orc):
+    # regular lattice: many exactly equal distances
+    g = np.stack(np.meshgrid(np.arange(12.0), np.arange(12.0), np.arange(12.0), indexing="ij"), -1).reshape(-1, 3) * 0.25
+    i0, d0 = orc.knn(g, 13, nthreads=4)
+    i1, d1 = orc.knn_grid(g, 13, nthreads=4)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+
+
+def _queries(c, e, q, n, seed):
+    s, g = synth.random_queries(c, e, q, seed)
+    cand = np.stack([synth.ellipsoid_candidates(s[i], g[i], 4 * n, seed * 100 + i) for i in range(q)])
+    return s, g, cand
+
+
+def test_sample_multiple_batch_matches_single(orc, c1_map):
+    vox, c, e = c1_map
+    om = orc.OracleMap(vox, c, e)
+    q, n = 3, 400
+    s, g, cand = _queries(c, e, q, n, 9)
+    out = orc.sample_multiple_batch(om, s, g, cand, n, CLR, CDC, nthreads=3, full=True)
+    assert out["short"] == 0
+    for i in range(q):
+        nodes = om.sample_reject(s[i], g[i], cand[i], CLR, n)[0]
+        assert np.array_equal(out["nodes"][i], nodes)
+        want = om.build_prm(nodes, CLR, CDC)
+        nnz = int(out["nnz"][i])
+        assert nnz == len(want["col"]) and out["n_free"][i] == want["directed_free"].sum()
+        assert np.array_equal(out["row_ptr"][i], want["row_ptr"])
+        assert np.array_equal(out["col"][i, :nnz], want["col"]) and np.array_equal(out["w"][i, :nnz], want["w"])
+        assert out["lookups"][i] == want["lookups"]
+
+
+def test_reference_sample_multiple_equals_restatement(orc, c1_map):
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref not built")
+    vox, c, e = c1_map
+    fn = tempfile.mktemp(suffix=".npy")
+    synth.write_map(fn, vox, c, e)
+    ref = orc.RefMap(fn)
+    om = orc.OracleMap(vox, c, e)
+    q, n = 4, 500
+    s, g, cand = _queries(c, e, q, n, 5)
+    a = orc.sample_multiple_batch(om, s, g, cand, n, CLR, CDC, nthreads=4, full=True)
+    b = ref.sample_multiple_batch(s, g, cand, n, CLR, CDC, nthreads=4, full=True)
+    for key in ("n_filled", "n_free", "nnz", "nodes", "row_ptr"):
+        assert np.array_equal(a[key], b[key]), key
+    for i in range(q):
+        nnz = int(a["nnz"][i])
+        assert np.array_equal(a["col"][i, :nnz], b["col"][i, :nnz]) and np.array_equal(a["w"][i, :nnz], b["w"][i, :nnz])
+    # candidate stream too short is reported, not fatal
+    short = ref.sample_multiple_batch(s[:1], g[:1], cand[:1, :40], n, CLR, CDC)
+    assert short["short"] == 1 and short["n_filled"][0] < n
+    ref.close()
+    os.unlink(fn)
