@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--cpu-queries", type=int, default=0, help="size of the CPU baseline sample (queries)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="skip the single-query latency leg")
     ap.add_argument("--e2e-steps", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -319,16 +320,18 @@ def main():
     def step1():
         dmap.sample_reject_dev(s_d, g_d, cand_d, 1, m_c, clr, n, nodes_d, n_filled_d, n_used_d, stream=stream)
         dmap.build_prm_dev(nodes_d, 1, n, K_NN, clr, cdc, row_ptr_d, col_d, w_d, cap, nnz_off_d, stream=stream)
-    for _ in range(5):
-        step1()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(50):
-        step1()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    single_ms = e0.elapsed_time(e1) / 50
+    single_ms = None
+    if not args.no_single:
+        for _ in range(5):
+            step1()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(50):
+            step1()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        single_ms = e0.elapsed_time(e1) / 50
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers, copies timed) ----
     e2e = None

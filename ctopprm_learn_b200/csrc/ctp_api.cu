@@ -65,7 +65,7 @@ struct ctp_map {
   size_t map_bytes = 0;
   // stage profiling (ctp_profile): pairs of events recorded on the caller's stream
   unsigned long long launches = 0;  // kernels enqueued by this handle (ctp_launch_counter_read)
-  int prm_group = 8;  // lanes per edge in ctp_build_prm (kNN edges are ~5-12 samples long)
+  int prm_group = 1;  // ctp_build_prm: 1 = flat lookup-parallel kernel (kNN edges are ~3-12 samples long)
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;    // pool, two per recorded span
   std::vector<int> prof_stage;         // stage id of span i (events 2i, 2i+1)
@@ -300,7 +300,7 @@ extern "C" int ctp_map_set_layout(ctp_map *m, int layout) {
 
 extern "C" int ctp_set_prm_group(ctp_map *m, int group) {
   REQUIRE(m, "null map");
-  REQUIRE(group == 4 || group == 8 || group == 16 || group == 32, "group must be 4, 8, 16 or 32");
+  REQUIRE(group == 1 || group == 4 || group == 8 || group == 16 || group == 32, "group must be 1, 4, 8, 16 or 32");
   m->prm_group = group;
   return CTP_OK;
 }
@@ -504,9 +504,30 @@ static int launch_edges_LG(ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr
 }
 
 template <int L>
+static int launch_edges_flat(ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr, double cdc, int guards,
+                             const EdgeOut &O, cudaStream_t st) {
+  static int occ = 0;
+  if (occ == 0) {
+    int o = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_edge_flat<L>, 32 * CTP_FLAT_WARPS, 0));
+    occ = o > 0 ? o : 1;
+  }
+  const int64_t per_block = 32 * CTP_FLAT_WARPS;
+  int64_t blocks = (cnt + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)m->sm_count * occ;  // persistent: one resident wave
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_edge_flat<L><<<(int)blocks, 32 * CTP_FLAT_WARPS, 0, st>>>(m->dev, S, cnt, clr, cdc, guards, O);
+  m->launches++;
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+template <int L>
 static int launch_edges_L(ctp_map *m, int group, const EdgeSrc &S, int64_t cnt, double clr, double cdc,
                           int guards, const EdgeOut &O, cudaStream_t st) {
   switch (group) {
+    case 1: return launch_edges_flat<L>(m, S, cnt, clr, cdc, guards, O, st);
     case 4: return launch_edges_LG<L, 4>(m, S, cnt, clr, cdc, guards, O, st);
     case 8: return launch_edges_LG<L, 8>(m, S, cnt, clr, cdc, guards, O, st);
     case 16: return launch_edges_LG<L, 16>(m, S, cnt, clr, cdc, guards, O, st);
@@ -523,7 +544,8 @@ static int launch_edges(ctp_map *m, int group, const EdgeSrc &S, int64_t cnt, do
 static int check_edge_args(ctp_map *m, int64_t cnt, double cdc, int group) {
   REQUIRE(m && cnt >= 0, "bad argument");
   REQUIRE(cdc > 0, "collision_distance_check must be > 0 (topological_prm_clustering.hpp:270-275)");
-  REQUIRE(group == 0 || group == 4 || group == 8 || group == 16 || group == 32, "group must be 0, 4, 8, 16 or 32");
+  REQUIRE(group == 0 || group == 1 || group == 4 || group == 8 || group == 16 || group == 32,
+          "group must be 0, 1, 4, 8, 16 or 32");
   return CTP_OK;
 }
 
@@ -549,7 +571,7 @@ extern "C" int ctp_edge_check_indexed_dev(ctp_map *m, const double *nodes, int64
   CK(cudaSetDevice(m->device));
   EdgeSrc S{nodes, nullptr, from, to, n_nodes, 1, 1};
   EdgeOut O{free_out, nullptr, hit_idx, lookups, m->d_lookups};
-  return launch_edges(m, group ? group : 8, S, cnt, clr, cdc, 0, O, (cudaStream_t)stream);
+  return launch_edges(m, group ? group : 1, S, cnt, clr, cdc, 0, O, (cudaStream_t)stream);
 }
 
 static int auto_group(const double *a, const double *b, int64_t cnt, double cdc) {
@@ -562,7 +584,7 @@ static int auto_group(const double *a, const double *b, int64_t cnt, double cdc)
     if (d == d && d < 1e300) sum += d;
   }
   const double samples = sum / (double)probe / cdc + 1.0;
-  return samples <= 5 ? 4 : samples <= 11 ? 8 : samples <= 24 ? 16 : 32;
+  return samples <= 16 ? 1 : samples <= 24 ? 16 : 32;
 }
 
 extern "C" int ctp_edge_check(ctp_map *m, const double *a, const double *b, int64_t cnt, double clr, double cdc,

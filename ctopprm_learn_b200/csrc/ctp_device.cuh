@@ -375,6 +375,160 @@ __global__ void __launch_bounds__(256) k_edge_march(MapDev M, EdgeSrc S, int64_t
   }
 }
 
+// ---- flat (lookup-parallel) segment check -------------------------------------------------
+// For the PRM build the n*k candidate edges are short (a handful of samples each) and almost all
+// free, so lanes-per-edge marching wastes most issue slots on per-edge setup and idle lanes.  Here
+// a warp takes 32 edges, one per lane for the setup (endpoints, length, sample count), then lays
+// the samples of all 32 edges out back to back and works through them 32 at a time: every lane
+// evaluates one ESDF lookup per step regardless of which edge it belongs to.  A colliding sample
+// records its march index with a shared-memory atomicMin, so the verdict, the first-hit index and
+// the reference-order lookup count are exactly the sequential ones.  Long edges are processed in
+// rounds of CTP_FLAT_R samples per edge; an edge stops at the first round that found a hit.
+#define CTP_FLAT_R 16
+#define CTP_FLAT_WARPS 8
+
+// endpoints + sample count of edge e, exactly as k_edge_march arms an edge.
+// returns 0 = march needed, 1 = free without lookups, 2 = not free without lookups (missing / absurd)
+__device__ __forceinline__ int ctp_arm_edge(const EdgeSrc &S, int64_t e, int guards, double cdc, double &ax,
+                                            double &ay, double &az, double &vx, double &vy, double &vz,
+                                            double &npts, int &n_last) {
+  const double *pa, *pb;
+  bool missing = false;
+  if (S.indexed) {
+    int64_t fi, ti;
+    const int32_t t = S.to[e];
+    if (S.from) {
+      fi = S.from[e];
+      ti = t;
+    } else {  // batched PRM: e = (query*n + node)*k + slot, indices local to the query
+      const int64_t row = e / S.k;
+      const int64_t qbase = (row / S.n) * S.n;
+      fi = row;
+      ti = qbase + t;
+    }
+    missing = t < 0;
+    pa = S.a + 3 * fi;
+    pb = S.a + 3 * (missing ? fi : ti);
+  } else {
+    pa = S.a + 3 * e;
+    pb = S.b + 3 * e;
+  }
+  double x0 = pa[0], y0 = pa[1], z0 = pa[2];
+  double x1 = pb[0], y1 = pb[1], z1 = pb[2];
+  if (guards) {  // marches from `neigbour` toward `actual` (src/base_map.cpp:82,90)
+    double t0 = x0; x0 = x1; x1 = t0;
+    t0 = y0; y0 = y1; y1 = t0;
+    t0 = z0; z0 = z1; z1 = t0;
+  }
+  vx = x1 - x0;
+  vy = y1 - y0;
+  vz = z1 - z0;
+  ax = x0;
+  ay = y0;
+  az = z0;
+  const double d = sqrt((vx * vx + vy * vy) + vz * vz);
+  npts = ceil((d / cdc) + 1.0);
+  n_last = 0;
+  // d < cdc shortcut exists only in ...BetweenNodes (src/base_map.cpp:57-59).
+  // NaN npts: `index < NaN` is false, the reference loop body never runs => free.
+  const bool trivially_free = (!guards && d < cdc) || !(npts == npts) || npts < 2.0;
+  const bool absurd = npts > 2147483647.0;  // reference would spin on int overflow
+  if (missing || absurd) return 2;
+  if (trivially_free) return 1;
+  n_last = (int)npts - 1;  // indices 1 .. npts-1 (src/base_map.cpp:64)
+  return 0;
+}
+
+template <int L>
+__global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, EdgeSrc S, int64_t m, double clr,
+                                                                   double cdc, int guards, EdgeOut O) {
+  __shared__ double s_par[CTP_FLAT_WARPS][7][32];
+  __shared__ int s_first[CTP_FLAT_WARPS][32];
+  __shared__ int2 s_ob[CTP_FLAT_WARPS][32];
+  __shared__ uint8_t s_slot[CTP_FLAT_WARPS][32 * CTP_FLAT_R];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double(*par)[32] = s_par[w];
+  int *first = s_first[w];
+  int2 *ob = s_ob[w];
+  uint8_t *slot = s_slot[w];
+  const int64_t n_warps = (int64_t)gridDim.x * CTP_FLAT_WARPS;
+  const int64_t n_chunks = (m + 31) >> 5;
+  unsigned long long my_lookups = 0;
+
+  for (int64_t chunk = (int64_t)blockIdx.x * CTP_FLAT_WARPS + w; chunk < n_chunks; chunk += n_warps) {
+    const int64_t e = (chunk << 5) + lane;
+    double ax = 0, ay = 0, az = 0, vx = 0, vy = 0, vz = 0, npts = 1.0;
+    int n_last = 0, state = 3;  // 3 = lane has no edge
+    if (e < m) state = ctp_arm_edge(S, e, guards, cdc, ax, ay, az, vx, vy, vz, npts, n_last);
+    par[0][lane] = ax; par[1][lane] = ay; par[2][lane] = az;
+    par[3][lane] = vx; par[4][lane] = vy; par[5][lane] = vz;
+    par[6][lane] = npts;
+    first[lane] = 0x7fffffff;
+    bool alive = state == 0;
+    int base = 1;
+    for (;;) {
+      const int c = alive ? min(CTP_FLAT_R, n_last - base + 1) : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(full, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(full, incl, 31);
+      if (total == 0) break;
+      const int off = incl - c;
+      ob[lane] = make_int2(off, base);
+      for (int j = 0; j < c; j++) slot[off + j] = (uint8_t)lane;
+      __syncwarp();
+      for (int t = lane; t < total; t += 32) {
+        const int el = slot[t];
+        const int2 o2 = ob[el];
+        const int idx = o2.y + (t - o2.x);
+        const double tt = (double)idx / par[6][el];  // (double)index / num_points_path
+        const double px = par[0][el] + par[3][el] * tt;
+        const double py = par[1][el] + par[4][el] * tt;
+        const double pz = par[2][el] + par[5][el] * tt;
+        if (ctp_collides(esdf_clearance<L>(M, px, py, pz), clr)) atomicMin(&first[el], idx);
+      }
+      __syncwarp();
+      if (alive) {
+        if (first[lane] != 0x7fffffff) alive = false;
+        else {
+          base += c;
+          alive = base <= n_last;
+        }
+      }
+    }
+    if (state != 3) {
+      const int f = first[lane];
+      const bool blocked = f != 0x7fffffff;
+      const bool fr = state == 2 ? false : !blocked;
+      O.free_out[e] = fr ? 1 : 0;
+      if (O.hit) {
+        double hx = ctp_nan(), hy = ctp_nan(), hz = ctp_nan();
+        if (blocked) {
+          const double tt = (double)f / npts;
+          hx = ax + vx * tt;
+          hy = ay + vy * tt;
+          hz = az + vz * tt;
+        }
+        O.hit[3 * e] = hx; O.hit[3 * e + 1] = hy; O.hit[3 * e + 2] = hz;
+      }
+      if (O.hit_idx) O.hit_idx[e] = blocked ? f : (state == 2 ? -2 : -1);
+      const int lk = blocked ? f : n_last;
+      if (O.lookups) O.lookups[e] = lk;
+      my_lookups += (unsigned)lk;
+    }
+    __syncwarp();  // the next chunk reuses the warp's shared arrays
+  }
+  if (O.total_lookups) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_lookups += __shfl_xor_sync(full, my_lookups, o);
+    if (lane == 0 && my_lookups) atomicAdd(O.total_lookups, my_lookups);
+  }
+}
+
 // ---- layout builders ----------------------------------------------------------------------
 __global__ void k_build_cell8(const float *__restrict__ plain, int n, float *__restrict__ cell8) {
   const size_t n1 = (size_t)(n - 1);

@@ -72,7 +72,7 @@ int ctp_map_set_layout(ctp_map *map, int layout);
  * info[0..2]=min, [3..5]=max, [6]=n, [7]=active layout, [8]=device, [9]=device bytes held,
  * [10]=lanes per edge used by ctp_build_prm, [11]=SM count */
 int ctp_map_info(const ctp_map *map, double info[12]);
-/* lanes cooperating on one edge inside ctp_build_prm / ctp_sample_multiple (4, 8, 16 or 32) */
+/* edge kernel used inside ctp_build_prm / ctp_sample_multiple: 1 (flat, default), 4, 8, 16 or 32 */
 int ctp_set_prm_group(ctp_map *map, int group);
 /* pre-size the scratch workspace so later _dev calls never allocate (needed before CUDA
  * graph capture).  q queries x n nodes x m candidates, k neighbours. */
@@ -116,7 +116,9 @@ int ctp_gradient_dev(ctp_map *map, const double *xyz, int64_t m, double *grad, d
  * free_out[i]=1 if free.  Optional (may be NULL): hit = first colliding sample or NaN^3,
  * hit_idx = its 1-based march index or -1, lookups = clearance evaluations the reference
  * would have made (up to and including the first hit).  group = lanes cooperating on one
- * edge (4, 8, 16, 32; 0 = choose from cdc and the segment lengths). */
+ * edge (4, 8, 16, 32), or 1 = the flat lookup-parallel kernel (one lane per sample across 32
+ * edges; best for short, mostly free edges such as the k-NN candidates); 0 = choose from cdc
+ * and the segment lengths. */
 int ctp_edge_check(ctp_map *map, const double *a, const double *b, int64_t m, double clr,
                    double cdc, int mode, int group, uint8_t *free_out, double *hit,
                    int32_t *hit_idx, int32_t *lookups);
