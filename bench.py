@@ -213,6 +213,8 @@ def main():
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (default: per workload)")
     ap.add_argument("--layout", default="auto", choices=["auto", "plain", "cell8", "tex", "brick"])
     ap.add_argument("--group", type=int, default=0, help="lanes per edge in the march kernel (0 = library default)")
+    ap.add_argument("--knn-per-cell", type=float, default=0.0)
+    ap.add_argument("--knn-ring", action="store_true", help="ring-search k-NN only (no tile kernel)")
     ap.add_argument("--cpu-queries", type=int, default=0, help="size of the CPU baseline sample (queries)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -251,6 +253,10 @@ def main():
     dmap.set_layout(layout)
     if args.group:
         dmap.set_prm_group(args.group)
+    if args.knn_per_cell:
+        dmap.set_tunable(capi.TUNE_KNN_PER_CELL, args.knn_per_cell)
+    if args.knn_ring:
+        dmap.set_tunable(capi.TUNE_KNN_TILE, 0)
 
     # this rank's shard of the query set, staged in page-locked host memory
     m_c = cpn * n

@@ -12,6 +12,7 @@ LAYOUT_PLAIN, LAYOUT_CELL8, LAYOUT_TEX, LAYOUT_BRICK = 1, 2, 4, 8
 LAYOUT_NAMES = {1: "plain", 2: "cell8", 4: "tex", 8: "brick"}
 DEFAULT_LAYOUT = LAYOUT_PLAIN  # the layout bench.py uses unless told otherwise
 EDGE_NODES, EDGE_GUARDS = 0, 1
+TUNE_KNN_PER_CELL, TUNE_KNN_TILE = 0, 1
 ERR_NEED_CANDIDATES = -4
 
 _lib = None
@@ -42,6 +43,7 @@ _SIGS = {
     "ctp_map_set_layout": [_P, _I],
     "ctp_map_info": [_P, _P],
     "ctp_set_prm_group": [_P, _I],
+    "ctp_set_tunable": [_P, _I, _D],
     "ctp_reserve": [_P, _I64, _I64, _I64, _I],
     "ctp_lookup_counter_read": [_P, _P, _P, _I],
     "ctp_launch_counter_read": [_P, _P, _I],
@@ -195,6 +197,9 @@ class DeviceMap:
 
     def prm_group(self):
         return int(self.info()[10])
+
+    def set_tunable(self, key, value):
+        _check(lib().ctp_set_tunable(self._h, key, float(value)))
 
     def set_prm_group(self, group):
         _check(lib().ctp_set_prm_group(self._h, group))

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -64,6 +65,8 @@ struct ctp_map {
   int sm_count = 148;
   size_t map_bytes = 0;
   // stage profiling (ctp_profile): pairs of events recorded on the caller's stream
+  double knn_per_cell = 22.0;  // expected points inside a ball of one cell size (see k_knn_setup)
+  int knn_tile = 1;           // 1 = tile kernel + ring-search fallback, 0 = ring search only
   unsigned long long launches = 0;  // kernels enqueued by this handle (ctp_launch_counter_read)
   int prm_group = 1;  // ctp_build_prm: 1 = flat lookup-parallel kernel (kNN edges are ~3-12 samples long)
   bool prof = false;
@@ -303,6 +306,21 @@ extern "C" int ctp_set_prm_group(ctp_map *m, int group) {
   REQUIRE(group == 1 || group == 4 || group == 8 || group == 16 || group == 32, "group must be 1, 4, 8, 16 or 32");
   m->prm_group = group;
   return CTP_OK;
+}
+
+extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
+  REQUIRE(m, "null map");
+  switch (key) {
+    case CTP_TUNE_KNN_PER_CELL:
+      REQUIRE(value >= 1.0 && value <= 256.0, "expected points per ball must be in [1, 256]");
+      m->knn_per_cell = value;
+      return CTP_OK;
+    case CTP_TUNE_KNN_TILE:
+      m->knn_tile = value != 0.0;
+      return CTP_OK;
+    default:
+      return fail(CTP_ERR_INVALID, "ctp_set_tunable: unknown key %d", key);
+  }
 }
 
 extern "C" int ctp_map_info(const ctp_map *m, double info[12]) {
@@ -557,7 +575,7 @@ extern "C" int ctp_edge_check_dev(ctp_map *m, const double *a, const double *b, 
   if (cnt == 0) return CTP_OK;
   REQUIRE(a && b && free_out, "null buffer");
   CK(cudaSetDevice(m->device));
-  EdgeSrc S{a, b, nullptr, nullptr, 0, 0, 0};
+  EdgeSrc S{a, b, nullptr, nullptr, 0, 0, 0, 0};
   EdgeOut O{free_out, hit, hit_idx, lookups, m->d_lookups};
   return launch_edges(m, group ? group : 16, S, cnt, clr, cdc, mode == CTP_EDGE_GUARDS, O, (cudaStream_t)stream);
 }
@@ -569,7 +587,7 @@ extern "C" int ctp_edge_check_indexed_dev(ctp_map *m, const double *nodes, int64
   if (cnt == 0) return CTP_OK;
   REQUIRE(nodes && from && to && free_out && n_nodes > 0, "null buffer");
   CK(cudaSetDevice(m->device));
-  EdgeSrc S{nodes, nullptr, from, to, n_nodes, 1, 1};
+  EdgeSrc S{nodes, nullptr, from, to, n_nodes, 1, 1, 1};
   EdgeOut O{free_out, nullptr, hit_idx, lookups, m->d_lookups};
   return launch_edges(m, group ? group : 1, S, cnt, clr, cdc, 0, O, (cudaStream_t)stream);
 }
@@ -642,7 +660,7 @@ extern "C" int ctp_edge_check_indexed(ctp_map *m, const double *nodes, int64_t n
 
 // ------------------------------- workspace sizing -------------------------------------------
 static int knn_max_cells(int64_t n) {
-  int64_t c = n / 2 + 64;
+  int64_t c = 2 * n + 64;
   if (c > (1 << 22)) c = 1 << 22;
   return (int)c;
 }
@@ -652,11 +670,11 @@ static size_t ws_bytes_reject(int64_t q, int64_t m) {
 }
 static size_t ws_bytes_knn(int64_t q, int64_t n) {
   const size_t mc = (size_t)knn_max_cells(n);
-  return align_up((size_t)q * sizeof(KnnGrid)) + 2 * align_up((size_t)q * n * 16) + align_up((size_t)q * n * 4) +
-         align_up((size_t)q * mc * 4) + align_up((size_t)q * (mc + 1) * 4);
+  return align_up((size_t)q * sizeof(KnnGrid)) + 2 * align_up((size_t)q * n * 16) + 2 * align_up((size_t)q * n * 4) +
+         align_up((size_t)q * mc * 4) + align_up((size_t)q * (mc + 1) * 4) + 512;
 }
 static size_t ws_bytes_prm(int64_t q, int64_t n, int k) {
-  return ws_bytes_knn(q, n) + align_up((size_t)q * n * k * 4) + align_up((size_t)q * n * k) +
+  return ws_bytes_knn(q, n) + align_up((size_t)q * n * csr_ns(k) * 4) + 2 * align_up((size_t)q * n * k) +
          align_up((size_t)q * n * 4) + align_up((size_t)q * 8);
 }
 
@@ -762,8 +780,8 @@ extern "C" int ctp_sample_ellipsoid(ctp_map *m, const double *start, const doubl
 }
 
 // --------------------------------------- k-NN ----------------------------------------------
-static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *idx, float *d2,
-                      cudaStream_t st) {
+static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *idx, int idx_stride,
+                      float *d2, cudaStream_t st) {
   const int mc = knn_max_cells(n);
   const int64_t total = q * n;
   KnnGrid *d_grid = arena_take<KnnGrid>(m->ws, q);
@@ -771,8 +789,10 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
   int32_t *d_cell_of = arena_take<int32_t>(m->ws, total);
   int32_t *d_cnt = arena_take<int32_t>(m->ws, (size_t)q * mc);
   int32_t *d_start = arena_take<int32_t>(m->ws, (size_t)q * (mc + 1));
+  int32_t *d_fb = arena_take<int32_t>(m->ws, total);
+  int32_t *d_fbn = arena_take<int32_t>(m->ws, 1);
   CK(cudaMemsetAsync(d_cnt, 0, (size_t)q * mc * 4, st));
-  k_knn_setup<<<(unsigned)q, 1024, 0, st>>>(nodes, n, mc, d_grid, d_pts);
+  k_knn_setup<<<(unsigned)q, 1024, 0, st>>>(nodes, n, mc, m->knn_per_cell, d_grid, d_pts);
   m->launches++;
   CK(cudaGetLastError());
   const int blocks = (int)((total + 255) / 256);
@@ -783,14 +803,45 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
   k_knn_scatter<<<blocks, 256, 0, st>>>(d_pts, n, total, mc, d_cell_of, d_start, d_cnt, d_sorted);
   m->launches++;
   CK(cudaGetLastError());
-  const int sblocks = (int)((total + 127) / 128);
-#define KNN_CASE(K) \
-  case K: k_knn_search<K><<<sblocks, 128, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, d2); m->launches++; break;
-  switch (k) {
-    KNN_CASE(1) KNN_CASE(2) KNN_CASE(3) KNN_CASE(4) KNN_CASE(5) KNN_CASE(6) KNN_CASE(7) KNN_CASE(8)
-    KNN_CASE(9) KNN_CASE(10) KNN_CASE(11) KNN_CASE(12) KNN_CASE(13) KNN_CASE(14) KNN_CASE(15) KNN_CASE(16)
-  }
+  if (m->knn_tile && n > 4 * k) {
+    CK(cudaMemsetAsync(d_fbn, 0, 4, st));
+    // a query's tiles are shared by bpq CTAs; enough CTAs overall to fill the machine several times
+    const int bpq = (int)std::max<int64_t>(8, ((int64_t)m->sm_count * 16 + q - 1) / q);
+    const dim3 tgrid((unsigned)bpq, (unsigned)q);
+    const int lblocks = m->sm_count * 8;
+#define KNN_CASE(K)                                                                                               \
+  case K:                                                                                                         \
+    k_knn_tile<K><<<tgrid, CTP_KNN_TILE_THREADS, 0, st>>>(d_sorted, n, d_grid, mc, d_start, idx, idx_stride, d2,  \
+                                                          d_fb, d_fbn);                                           \
+    k_knn_search_list<K><<<lblocks, 128, 0, st>>>(d_sorted, n, d_fb, d_fbn, d_grid, mc, d_start, idx, idx_stride, \
+                                                  d2);                                                            \
+    m->launches += 2;                                                                                             \
+    break;
+    switch (k) {
+      KNN_CASE(1) KNN_CASE(2) KNN_CASE(3) KNN_CASE(4) KNN_CASE(5) KNN_CASE(6) KNN_CASE(7) KNN_CASE(8)
+      KNN_CASE(9) KNN_CASE(10) KNN_CASE(11) KNN_CASE(12) KNN_CASE(13) KNN_CASE(14) KNN_CASE(15) KNN_CASE(16)
+    }
 #undef KNN_CASE
+    if (getenv("CTP_DEBUG_KNN")) {
+      int fb = 0;
+      cudaMemcpyAsync(&fb, d_fbn, 4, cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "[ctp] knn: %lld points, %d redone by the ring search (%.2f%%)\n", (long long)total, fb,
+              100.0 * fb / (double)total);
+    }
+  } else {
+    const int sblocks = (int)((total + 127) / 128);
+#define KNN_CASE(K)                                                                                            \
+  case K:                                                                                                      \
+    k_knn_search<K><<<sblocks, 128, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, idx_stride, d2);   \
+    m->launches++;                                                                                             \
+    break;
+    switch (k) {
+      KNN_CASE(1) KNN_CASE(2) KNN_CASE(3) KNN_CASE(4) KNN_CASE(5) KNN_CASE(6) KNN_CASE(7) KNN_CASE(8)
+      KNN_CASE(9) KNN_CASE(10) KNN_CASE(11) KNN_CASE(12) KNN_CASE(13) KNN_CASE(14) KNN_CASE(15) KNN_CASE(16)
+    }
+#undef KNN_CASE
+  }
   CK(cudaGetLastError());
   return CTP_OK;
 }
@@ -803,7 +854,7 @@ extern "C" int ctp_knn_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n
   CK(cudaSetDevice(m->device));
   const size_t keep = m->ws.used;
   CKR(arena_reserve(m->ws, keep + ws_bytes_knn(q, n) + 4096));
-  int rc = knn_launch(m, nodes, q, n, k, idx, d2, (cudaStream_t)stream);
+  int rc = knn_launch(m, nodes, q, n, k, idx, k, d2, (cudaStream_t)stream);
   m->ws.used = keep;
   return rc;
 }
@@ -839,37 +890,46 @@ extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int
   const size_t keep = m->ws.used;
   CKR(arena_reserve(m->ws, keep + ws_bytes_prm(q, n, k) + 8192));
   const int64_t rows = q * n, edges = rows * k;
-  int32_t *d_nbr = nbr ? nbr : arena_take<int32_t>(m->ws, edges);
+  const int ns = csr_ns(k);
+  int32_t *d_rec = arena_take<int32_t>(m->ws, rows * ns);  // per node: k neighbour ids + free-edge mask
   uint8_t *d_free = directed_free ? directed_free : arena_take<uint8_t>(m->ws, edges);
+  uint8_t *d_flag = arena_take<uint8_t>(m->ws, edges);
   int32_t *d_deg = arena_take<int32_t>(m->ws, rows);
   int64_t *d_nnz = arena_take<int64_t>(m->ws, q);
   int rc;
   {
     StageSpan span(m, CTP_STAGE_KNN, st);
-    rc = knn_launch(m, nodes, q, n, k, d_nbr, nullptr, st);
+    rc = knn_launch(m, nodes, q, n, k, d_rec, ns, nullptr, st);
   }
   m->ws.used = keep;
   CKR(rc);
-  // the n*k directed checks (:355-397), 8 lanes per edge: kNN edges are ~5-12 samples long
-  EdgeSrc S{nodes, nullptr, nullptr, d_nbr, n, k, 1};
+  // the n*k directed checks (:355-397)
+  EdgeSrc S{nodes, nullptr, nullptr, d_rec, n, k, 1, ns};
   EdgeOut O{d_free, nullptr, nullptr, nullptr, m->d_lookups};
   {
     StageSpan span(m, CTP_STAGE_EDGES, st);
     CKR(launch_edges(m, m->prm_group, S, edges, clr, cdc, 0, O, st));
   }
   StageSpan span(m, CTP_STAGE_CSR, st);
-  CK(cudaMemsetAsync(d_deg, 0, rows * 4, st));
   const int eb = (int)((edges + 255) / 256), rb = (int)((rows + 255) / 256);
-  k_csr_degree<<<eb, 256, 0, st>>>(d_nbr, d_free, n, k, edges, d_deg);
+  k_csr_rowmask<<<rb, 256, 0, st>>>(d_free, k, ns, rows, d_rec, d_deg);
+  m->launches++;
+  if (ns == 16) k_csr_degree<16><<<eb, 256, 0, st>>>(d_rec, d_free, n, k, edges, d_flag, d_deg);
+  else k_csr_degree<32><<<eb, 256, 0, st>>>(d_rec, d_free, n, k, edges, d_flag, d_deg);
   m->launches++;
   k_csr_rowptr<<<(unsigned)q, 1024, 0, st>>>(d_deg, n, row_ptr, d_nnz);
   m->launches++;
   k_csr_query_offsets<<<1, 1024, 0, st>>>(d_nnz, q, nnz_off);
   m->launches++;
-  k_csr_fill<<<eb, 256, 0, st>>>(d_nbr, d_free, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
+  if (ns == 16) k_csr_fill<16><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
+  else k_csr_fill<32><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
   m->launches++;
   k_csr_finish<<<rb, 256, 0, st>>>(nodes, n, rows, row_ptr, nnz_off, cap, col, w);
   m->launches++;
+  if (nbr) {
+    k_rec_to_nbr<<<eb, 256, 0, st>>>(d_rec, ns, k, edges, nbr);
+    m->launches++;
+  }
   CK(cudaGetLastError());
   return CTP_OK;
 }

@@ -236,6 +236,7 @@ struct EdgeSrc {
   int64_t n;            // nodes per query (indexed)
   int k;                // neighbours per node when from == NULL
   int indexed;
+  int to_stride;        // from == NULL: to[row * to_stride + slot]
 };
 
 struct EdgeOut {
@@ -245,6 +246,64 @@ struct EdgeOut {
   int32_t *lookups;
   unsigned long long *total_lookups;  // device counter, one atomic per warp
 };
+
+// endpoints + sample count of edge e (src/base_map.cpp:52-63).
+// returns 0 = march needed, 1 = free without lookups, 2 = not free without lookups (missing / absurd)
+__device__ __forceinline__ int ctp_arm_edge(const EdgeSrc &S, int64_t e, int guards, double cdc, double &ax,
+                                            double &ay, double &az, double &vx, double &vy, double &vz,
+                                            double &npts, int &n_last) {
+  const double *pa, *pb;
+  bool missing = false;
+  if (S.indexed) {
+    int64_t fi, ti;
+    int32_t t;
+    int64_t row = 0, qbase = 0;
+    if (S.from) {
+      t = S.to[e];
+    } else {  // batched PRM: e = (query*n + node)*k + slot; neighbour ids are local to the query
+      row = e / S.k;
+      qbase = (row / S.n) * S.n;
+      t = S.to[row * S.to_stride + (e - row * S.k)];
+    }
+    if (S.from) {
+      fi = S.from[e];
+      ti = t;
+    } else {
+      fi = row;
+      ti = qbase + t;
+    }
+    missing = t < 0;
+    pa = S.a + 3 * fi;
+    pb = S.a + 3 * (missing ? fi : ti);
+  } else {
+    pa = S.a + 3 * e;
+    pb = S.b + 3 * e;
+  }
+  double x0 = pa[0], y0 = pa[1], z0 = pa[2];
+  double x1 = pb[0], y1 = pb[1], z1 = pb[2];
+  if (guards) {  // marches from `neigbour` toward `actual` (src/base_map.cpp:82,90)
+    double t0 = x0; x0 = x1; x1 = t0;
+    t0 = y0; y0 = y1; y1 = t0;
+    t0 = z0; z0 = z1; z1 = t0;
+  }
+  vx = x1 - x0;
+  vy = y1 - y0;
+  vz = z1 - z0;
+  ax = x0;
+  ay = y0;
+  az = z0;
+  const double d = sqrt((vx * vx + vy * vy) + vz * vz);
+  npts = ceil((d / cdc) + 1.0);
+  n_last = 0;
+  // d < cdc shortcut exists only in ...BetweenNodes (src/base_map.cpp:57-59).
+  // NaN npts: `index < NaN` is false, the reference loop body never runs => free.
+  const bool trivially_free = (!guards && d < cdc) || !(npts == npts) || npts < 2.0;
+  const bool absurd = npts > 2147483647.0;  // reference would spin on int overflow
+  if (missing || absurd) return 2;
+  if (trivially_free) return 1;
+  n_last = (int)npts - 1;  // indices 1 .. npts-1 (src/base_map.cpp:64)
+  return 0;
+}
 
 // One group of G lanes marches one segment, G consecutive samples per step, in the
 // reference's sample order; a warp-wide ballot gives each group its first colliding lane, so
@@ -273,57 +332,16 @@ __global__ void __launch_bounds__(256) k_edge_march(MapDev M, EdgeSrc S, int64_t
       for (;;) {
         e += n_groups;
         if (e >= m) break;
-        const double *pa, *pb;
-        bool missing = false;
-        if (S.indexed) {
-          int64_t fi, ti;
-          const int32_t t = S.to[e];
-          if (S.from) {
-            fi = S.from[e];
-            ti = t;
-          } else {  // batched PRM: e = (query*n + node)*k + slot, indices local to the query
-            const int64_t row = e / S.k;
-            const int64_t qbase = (row / S.n) * S.n;
-            fi = row;
-            ti = qbase + t;
-          }
-          missing = t < 0;
-          pa = S.a + 3 * fi;
-          pb = S.a + 3 * (missing ? fi : ti);
-        } else {
-          pa = S.a + 3 * e;
-          pb = S.b + 3 * e;
-        }
-        double x0 = pa[0], y0 = pa[1], z0 = pa[2];
-        double x1 = pb[0], y1 = pb[1], z1 = pb[2];
-        if (guards) {  // marches from `neigbour` toward `actual` (src/base_map.cpp:82,90)
-          double t0 = x0; x0 = x1; x1 = t0;
-          t0 = y0; y0 = y1; y1 = t0;
-          t0 = z0; z0 = z1; z1 = t0;
-        }
-        vx = x1 - x0;
-        vy = y1 - y0;
-        vz = z1 - z0;
-        ax = x0;
-        ay = y0;
-        az = z0;
-        const double d = sqrt((vx * vx + vy * vy) + vz * vz);
-        npts = ceil((d / cdc) + 1.0);
-        // d < cdc shortcut exists only in ...BetweenNodes (src/base_map.cpp:57-59).
-        // NaN npts: `index < NaN` is false, the reference loop body never runs => free.
-        const bool trivially_free = (!guards && d < cdc) || !(npts == npts) || npts < 2.0;
-        const bool absurd = npts > 2147483647.0;  // reference would spin on int overflow
-        if (missing || trivially_free || absurd) {
+        const int state = ctp_arm_edge(S, e, guards, cdc, ax, ay, az, vx, vy, vz, npts, n_last);
+        if (state != 0) {
           if (sub == 0) {
-            const bool fr = !missing && !absurd;
-            O.free_out[e] = fr ? 1 : 0;
+            O.free_out[e] = state == 1 ? 1 : 0;
             if (O.hit) { O.hit[3 * e] = ctp_nan(); O.hit[3 * e + 1] = ctp_nan(); O.hit[3 * e + 2] = ctp_nan(); }
-            if (O.hit_idx) O.hit_idx[e] = fr ? -1 : -2;
+            if (O.hit_idx) O.hit_idx[e] = state == 1 ? -1 : -2;
             if (O.lookups) O.lookups[e] = 0;
           }
           continue;
         }
-        n_last = (int)npts - 1;  // indices 1 .. npts-1 (src/base_map.cpp:64)
         idx0 = 1;
         active = true;
         break;
@@ -386,58 +404,6 @@ __global__ void __launch_bounds__(256) k_edge_march(MapDev M, EdgeSrc S, int64_t
 // rounds of CTP_FLAT_R samples per edge; an edge stops at the first round that found a hit.
 #define CTP_FLAT_R 16
 #define CTP_FLAT_WARPS 8
-
-// endpoints + sample count of edge e, exactly as k_edge_march arms an edge.
-// returns 0 = march needed, 1 = free without lookups, 2 = not free without lookups (missing / absurd)
-__device__ __forceinline__ int ctp_arm_edge(const EdgeSrc &S, int64_t e, int guards, double cdc, double &ax,
-                                            double &ay, double &az, double &vx, double &vy, double &vz,
-                                            double &npts, int &n_last) {
-  const double *pa, *pb;
-  bool missing = false;
-  if (S.indexed) {
-    int64_t fi, ti;
-    const int32_t t = S.to[e];
-    if (S.from) {
-      fi = S.from[e];
-      ti = t;
-    } else {  // batched PRM: e = (query*n + node)*k + slot, indices local to the query
-      const int64_t row = e / S.k;
-      const int64_t qbase = (row / S.n) * S.n;
-      fi = row;
-      ti = qbase + t;
-    }
-    missing = t < 0;
-    pa = S.a + 3 * fi;
-    pb = S.a + 3 * (missing ? fi : ti);
-  } else {
-    pa = S.a + 3 * e;
-    pb = S.b + 3 * e;
-  }
-  double x0 = pa[0], y0 = pa[1], z0 = pa[2];
-  double x1 = pb[0], y1 = pb[1], z1 = pb[2];
-  if (guards) {  // marches from `neigbour` toward `actual` (src/base_map.cpp:82,90)
-    double t0 = x0; x0 = x1; x1 = t0;
-    t0 = y0; y0 = y1; y1 = t0;
-    t0 = z0; z0 = z1; z1 = t0;
-  }
-  vx = x1 - x0;
-  vy = y1 - y0;
-  vz = z1 - z0;
-  ax = x0;
-  ay = y0;
-  az = z0;
-  const double d = sqrt((vx * vx + vy * vy) + vz * vz);
-  npts = ceil((d / cdc) + 1.0);
-  n_last = 0;
-  // d < cdc shortcut exists only in ...BetweenNodes (src/base_map.cpp:57-59).
-  // NaN npts: `index < NaN` is false, the reference loop body never runs => free.
-  const bool trivially_free = (!guards && d < cdc) || !(npts == npts) || npts < 2.0;
-  const bool absurd = npts > 2147483647.0;  // reference would spin on int overflow
-  if (missing || absurd) return 2;
-  if (trivially_free) return 1;
-  n_last = (int)npts - 1;  // indices 1 .. npts-1 (src/base_map.cpp:64)
-  return 0;
-}
 
 template <int L>
 __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, EdgeSrc S, int64_t m, double clr,

@@ -129,11 +129,13 @@ __device__ __forceinline__ int knn_cell_1d(float x, float lo, float inv_h, int d
   return c < 0 ? 0 : (c >= dim ? dim - 1 : c);
 }
 
-// one CTA per query: float bounding box, then a grid of about n/CTP_KNN_PER_CELL cells
-#define CTP_KNN_TARGET_PER_CELL 2.0
+// one CTA per query: float bounding box, a coarse occupancy bitmap to estimate the volume the
+// points actually fill (an ellipsoid clipped by the map and by obstacles fills a third of its
+// box or less), then a cell size h such that a ball of radius h is expected to hold `in_ball`
+// points -- the quantity the tile search's completeness test depends on.
 __global__ void __launch_bounds__(1024) k_knn_setup(const double *__restrict__ nodes, int64_t n,
-                                                    int max_cells, KnnGrid *__restrict__ grids,
-                                                    float4 *__restrict__ pts) {
+                                                    int max_cells, double in_ball,
+                                                    KnnGrid *__restrict__ grids, float4 *__restrict__ pts) {
   const int64_t q = blockIdx.x;
   const double *nq = nodes + 3 * q * n;
   float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
@@ -145,6 +147,9 @@ __global__ void __launch_bounds__(1024) k_knn_setup(const double *__restrict__ n
     lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
   }
   __shared__ float s_lo[3][32], s_hi[3][32];
+  __shared__ float s_blo[3], s_binv[3];
+  __shared__ int s_bg[3];
+  __shared__ unsigned s_occ[128];  // up to 16^3 coarse cells
 #pragma unroll
   for (int a = 0; a < 3; a++) {
 #pragma unroll
@@ -154,22 +159,54 @@ __global__ void __launch_bounds__(1024) k_knn_setup(const double *__restrict__ n
     }
     if ((threadIdx.x & 31) == 0) { s_lo[a][threadIdx.x >> 5] = lo[a]; s_hi[a][threadIdx.x >> 5] = hi[a]; }
   }
+  if (threadIdx.x < 128) s_occ[threadIdx.x] = 0;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) / 32;
+  double e[3], emax = 0;
+  for (int a = 0; a < 3; a++) {
+    for (int w = 0; w < nw; w++) { lo[a] = fminf(lo[a], s_lo[a][w]); hi[a] = fmaxf(hi[a], s_hi[a][w]); }
+    e[a] = (double)hi[a] - (double)lo[a];
+    if (!(e[a] >= 0)) e[a] = 0;  // NaN coordinates
+    emax = fmax(emax, e[a]);
+  }
+  if (!(emax > 0) || !(emax < 1e300)) emax = 1.0;
+  const int G = n >= 4000 ? 16 : (n >= 500 ? 8 : (n >= 64 ? 4 : 2));
+  if (threadIdx.x == 0) {
+    for (int a = 0; a < 3; a++) {
+      const bool flat = !(e[a] > emax * 1e-3);  // degenerate axis (planar: true => every z equal)
+      s_bg[a] = flat ? 1 : G;
+      s_blo[a] = lo[a];
+      s_binv[a] = flat ? 0.f : (float)(G / e[a]);
+    }
+  }
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float4 p = pts[q * n + i];
+    const int cx = min(max((int)((p.x - s_blo[0]) * s_binv[0]), 0), s_bg[0] - 1);
+    const int cy = min(max((int)((p.y - s_blo[1]) * s_binv[1]), 0), s_bg[1] - 1);
+    const int cz = min(max((int)((p.z - s_blo[2]) * s_binv[2]), 0), s_bg[2] - 1);
+    const int c = (cz * s_bg[1] + cy) * s_bg[0] + cx;
+    atomicOr(&s_occ[c >> 5], 1u << (c & 31));
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int nw = (blockDim.x + 31) / 32;
+    int occ = 0;
+    for (int w = 0; w < 128; w++) occ += __popc(s_occ[w]);
+    if (occ < 1) occ = 1;
+    // D-dimensional measure of the occupied coarse cells and the radius whose D-ball holds in_ball points
+    int D = 0;
+    double vol = (double)occ;
     for (int a = 0; a < 3; a++)
-      for (int w = 0; w < nw; w++) { lo[a] = fminf(lo[a], s_lo[a][w]); hi[a] = fmaxf(hi[a], s_hi[a][w]); }
-    double e[3], emax = 0;
-    for (int a = 0; a < 3; a++) { e[a] = (double)hi[a] - (double)lo[a]; emax = fmax(emax, e[a]); }
-    if (!(emax > 0)) emax = 1.0;
-    for (int a = 0; a < 3; a++) e[a] = fmax(e[a], emax * 1e-6);
-    double target = (double)n / CTP_KNN_TARGET_PER_CELL;
-    if (target > max_cells) target = max_cells;
-    if (target < 1) target = 1;
-    // thin axes get one cell; h from the volume spanned by the remaining axes
-    double h = cbrt(e[0] * e[1] * e[2] / target);
+      if (s_bg[a] > 1) { D++; vol *= e[a] / s_bg[a]; }
+    double h;
+    const double per_point = vol / (double)n;
+    if (D == 3) h = cbrt(in_ball * per_point / 4.18879);
+    else if (D == 2) h = sqrt(in_ball * per_point / 3.14159);
+    else if (D == 1) h = in_ball * per_point / 2.0;
+    else h = emax;
+    if (!(h > emax * 1e-7)) h = emax * 1e-7;
     int d[3];
-    for (int it = 0; it < 64; it++) {
+    for (int it = 0; it < 256; it++) {
       long long prod = 1;
       for (int a = 0; a < 3; a++) {
         double c = floor(e[a] / h);
@@ -177,7 +214,7 @@ __global__ void __launch_bounds__(1024) k_knn_setup(const double *__restrict__ n
         prod *= d[a];
       }
       if (prod <= max_cells) break;
-      h *= 1.2;
+      h *= 1.1;
     }
     KnnGrid g;
     g.lox = lo[0]; g.loy = lo[1]; g.loz = lo[2];
@@ -288,12 +325,10 @@ template <int K> struct TopK {
 // one thread per (cell-sorted) point: expand Chebyshev rings of cells until the k-th best
 // squared distance is strictly below the squared distance to the unvisited region.
 template <int K>
-__global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ sorted, int64_t n, int64_t total,
-                                                    const KnnGrid *__restrict__ grids, int cell_stride,
-                                                    const int32_t *__restrict__ cell_start,
-                                                    int32_t *__restrict__ idx, float *__restrict__ d2out) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= total) return;
+__device__ __forceinline__ void knn_ring_search(int64_t t, const float4 *__restrict__ sorted, int64_t n,
+                                                const KnnGrid *__restrict__ grids, int cell_stride,
+                                                const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx,
+                                                int idx_stride, float *__restrict__ d2out) {
   const int64_t q = t / n;
   const KnnGrid g = grids[q];
   const float4 me = sorted[t];
@@ -338,7 +373,7 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
     const double lb = (double)r * g.h * 0.999;
     if (best.id[K - 1] != 0x7fffffff && (double)best.d[K - 1] < lb * lb) break;
   }
-  int32_t *oi = idx + (q * n + self) * K;
+  int32_t *oi = idx + (q * n + self) * idx_stride;
 #pragma unroll
   for (int s = 0; s < K; s++) oi[s] = best.id[s] == 0x7fffffff ? -1 : best.id[s];
   if (d2out) {
@@ -348,28 +383,229 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
   }
 }
 
+template <int K>
+__global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ sorted, int64_t n, int64_t total,
+                                                    const KnnGrid *__restrict__ grids, int cell_stride,
+                                                    const int32_t *__restrict__ cell_start,
+                                                    int32_t *__restrict__ idx, int idx_stride,
+                                                    float *__restrict__ d2out) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  knn_ring_search<K>(t, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out);
+}
+
+// ring search over the queries the tile pass could not finish (positions in the sorted array)
+template <int K>
+__global__ void __launch_bounds__(128) k_knn_search_list(const float4 *__restrict__ sorted, int64_t n,
+                                                         const int32_t *__restrict__ list,
+                                                         const int32_t *__restrict__ count,
+                                                         const KnnGrid *__restrict__ grids, int cell_stride,
+                                                         const int32_t *__restrict__ cell_start,
+                                                         int32_t *__restrict__ idx, int idx_stride,
+                                                         float *__restrict__ d2out) {
+  const int cnt = *count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
+    knn_ring_search<K>(list[i], sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out);
+}
+
+// ---- tile search: the fast path ---------------------------------------------------------------
+// A CTA takes a tile of TX x 2 x 2 cells.  The points of the tile plus a one-cell halo
+// ((TX+2) x 4 x 4 cells = 16 contiguous runs of the cell-sorted array) are staged in shared memory
+// once; every thread then owns one query point of the tile and scans the SAME staged list
+// (broadcast reads, no divergence).  Anything farther than 0.999 h cannot be ruled complete by the
+// halo, and anything nearer is guaranteed to be in it, so the scan only keeps candidates with
+// d2 < (0.999 h)^2 -- appended branch-free to a per-thread column in shared memory -- and the k
+// best of those are the exact answer whenever at least k were kept.  The top-k insertion network
+// therefore runs over ~20-30 survivors instead of diverging on every one of the ~500 candidates.
+// Queries with fewer than k (sparse borders) or more than CTP_KNN_KEEP survivors are appended to a
+// list and redone by the ring search (k_knn_search_list).
+#define CTP_KNN_TX 4
+#define CTP_KNN_TILE_THREADS 128
+#define CTP_KNN_TILE_CAP 1024
+#define CTP_KNN_KEEP 40
+
+template <int K>
+__global__ void __launch_bounds__(CTP_KNN_TILE_THREADS)
+k_knn_tile(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restrict__ grids, int cell_stride, const int32_t *__restrict__ cell_start,
+           int32_t *__restrict__ idx, int idx_stride, float *__restrict__ d2out,
+           int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
+  __shared__ float4 s_c[CTP_KNN_TILE_CAP];
+  __shared__ uint16_t s_keep[CTP_KNN_KEEP][CTP_KNN_TILE_THREADS];  // survivor columns (index into s_c)
+  __shared__ int s_cb[17], s_cs[16];  // candidate runs: prefix count, start in the sorted array
+  __shared__ int s_qb[5], s_qs[4];    // query runs (the tile's own cells)
+  const int tid = threadIdx.x;
+  // blockIdx.y = query; the gridDim.x CTAs of a query stride over its tiles
+  const int64_t q = blockIdx.y;
+  const KnnGrid g = grids[q];
+  const int tx = (g.dx + CTP_KNN_TX - 1) / CTP_KNN_TX, ty = (g.dy + 1) >> 1, tz = (g.dz + 1) >> 1;
+  const int n_tiles = tx * ty * tz;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int x0 = (tile % tx) * CTP_KNN_TX, y0 = ((tile / tx) % ty) * 2, z0 = (tile / (tx * ty)) * 2;
+    const int32_t *st = cell_start + q * (cell_stride + 1);
+    const float4 *sq = sorted + q * n;
+    __syncthreads();  // previous item's shared arrays are no longer read
+    if (tid < 32) {
+      int len = 0;
+      if (tid < 16) {  // candidate run (dy, dz) in [-1, 2]^2, x cells x0-1 .. x0+TX
+        const int y = y0 - 1 + (tid & 3), z = z0 - 1 + (tid >> 2);
+        int b = 0, e = 0;
+        if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
+          const int row = (z * g.dy + y) * g.dx;
+          b = st[row + max(x0 - 1, 0)];
+          e = st[row + min(x0 + CTP_KNN_TX, g.dx - 1) + 1];
+        }
+        s_cs[tid] = b;
+        len = e - b;
+      } else if (tid < 20) {  // query run (dy, dz) in [0, 1]^2, x cells x0 .. x0+TX-1
+        const int r = tid - 16;
+        const int y = y0 + (r & 1), z = z0 + (r >> 1);
+        int b = 0, e = 0;
+        if (y < g.dy && z < g.dz) {
+          const int row = (z * g.dy + y) * g.dx;
+          b = st[row + x0];
+          e = st[row + min(x0 + CTP_KNN_TX - 1, g.dx - 1) + 1];
+        }
+        s_qs[r] = b;
+        len = e - b;
+      }
+      // inclusive scans: lanes 0..15 (candidates) and 16..19 (queries) separately
+      int incl = len;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 15) >= o) incl += t;
+      }
+      if (tid < 16) s_cb[tid + 1] = incl;
+      else if (tid < 20) s_qb[tid - 15] = incl;
+      if (tid == 0) { s_cb[0] = 0; s_qb[0] = 0; }
+    }
+    __syncthreads();
+    const int n_query = s_qb[4], n_cand = s_cb[16];
+    if (n_query == 0) continue;
+    const float lb = (float)(g.h * 0.999);
+    const float lb2 = lb * lb;  // rounding here only shifts which queries take the fallback
+    for (int qb = 0; qb < n_query; qb += CTP_KNN_TILE_THREADS) {
+      const int qi = qb + tid;
+      const bool have = qi < n_query;
+      float4 me = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      int qpos = 0;
+      if (have) {
+        int r = 0;
+#pragma unroll
+        for (int t = 1; t < 4; t++) r += (qi >= s_qb[t]) ? 1 : 0;
+        qpos = s_qs[r] + (qi - s_qb[r]);
+        me = sq[qpos];
+      }
+      const int self = __float_as_int(me.w);
+      const float my_lb2 = have ? lb2 : -1.f;  // idle threads keep nothing
+      TopK<K> best;
+      best.init();
+      bool redo = false;
+      for (int cb = 0; cb < n_cand; cb += CTP_KNN_TILE_CAP) {
+        const int cnt = min(CTP_KNN_TILE_CAP, n_cand - cb);
+        __syncthreads();
+        for (int i = tid; i < cnt; i += CTP_KNN_TILE_THREADS) {
+          const int ci = cb + i;
+          int r = 0;
+#pragma unroll
+          for (int t = 1; t < 16; t++) r += (ci >= s_cb[t]) ? 1 : 0;
+          s_c[i] = sq[s_cs[r] + (ci - s_cb[r])];
+        }
+        __syncthreads();
+        int kept = 0;
+#pragma unroll 4
+        for (int c = 0; c < cnt; c++) {
+          const float4 o = s_c[c];
+          const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+          const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+          const bool keep = (dd < my_lb2) & (__float_as_int(o.w) != self);
+          if (keep) s_keep[min(kept, CTP_KNN_KEEP - 1)][tid] = (uint16_t)c;
+          kept += keep ? 1 : 0;
+        }
+        redo |= kept > CTP_KNN_KEEP;
+        kept = min(kept, CTP_KNN_KEEP);
+        for (int t = 0; t < kept; t++) {
+          const float4 o = s_c[s_keep[t][tid]];
+          const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+          const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+          best.push(dd, __float_as_int(o.w));
+        }
+      }
+      if (have) {
+        if (!redo && best.id[K - 1] != 0x7fffffff) {
+          int32_t *oi = idx + (q * n + self) * idx_stride;
+#pragma unroll
+          for (int s = 0; s < K; s++) oi[s] = best.id[s];
+          if (d2out) {
+            float *od = d2out + (q * n + self) * K;
+#pragma unroll
+            for (int s = 0; s < K; s++) od[s] = best.d[s];
+          }
+        } else {
+          fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + qpos);
+        }
+      }
+    }
+  }
+}
+
 // =========================== symmetric CSR emit (:374-385) ================================
 // {i,j} is an edge iff free(i->j) with j in kNN(i), or free(j->i) with i in kNN(j); both map
 // entries are written on success, so the adjacency is the symmetric union.
+//
+// Working layout: one 64-byte (NS = 16 ints; 128-byte for k = 16) record per node holding its k
+// neighbour ids and, in the last int, the bit mask of its free directed edges.  "Does row j list
+// i as a free neighbour" is then NS/4 16-byte loads of one record instead of 2k scalar loads.
 
-// does row j list i as a free neighbour?
-__device__ __forceinline__ bool csr_has_free(const int32_t *__restrict__ nbr, const uint8_t *__restrict__ fr,
-                                             int64_t row, int k, int target) {
-  bool f = false;
-  for (int s = 0; s < k; s++) f |= (nbr[row * k + s] == target) & (fr[row * k + s] != 0);
-  return f;
+__host__ __device__ __forceinline__ int csr_ns(int k) { return k <= 15 ? 16 : 32; }
+
+// free bytes of a row -> mask in the record; out-degree seeds deg[]
+__global__ void __launch_bounds__(256) k_csr_rowmask(const uint8_t *__restrict__ fr, int k, int ns, int64_t total_rows,
+                                                     int32_t *__restrict__ rec, int32_t *__restrict__ deg) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= total_rows) return;
+  unsigned mask = 0;
+  for (int s = 0; s < k; s++) mask |= (fr[row * k + s] ? 1u : 0u) << s;
+  rec[row * ns + ns - 1] = (int)mask;
+  deg[row] = __popc(mask);
 }
 
-__global__ void __launch_bounds__(256) k_csr_degree(const int32_t *__restrict__ nbr, const uint8_t *__restrict__ fr,
+template <int NS>
+__device__ __forceinline__ bool csr_lists_free(const int32_t *__restrict__ rec, int64_t row, int k, int target) {
+  const int4 *r4 = reinterpret_cast<const int4 *>(rec + row * NS);
+  int v[NS];
+#pragma unroll
+  for (int t = 0; t < NS / 4; t++) {
+    const int4 q = __ldg(r4 + t);
+    v[4 * t] = q.x; v[4 * t + 1] = q.y; v[4 * t + 2] = q.z; v[4 * t + 3] = q.w;
+  }
+  const unsigned mask = (unsigned)v[NS - 1];
+  unsigned hit = 0;
+#pragma unroll
+  for (int s = 0; s < NS - 1; s++) hit |= (v[s] == target ? 1u : 0u) << s;
+  if (NS == 32) hit |= 0;  // k <= 16 < 31 slots
+  return (hit & mask & ((1u << k) - 1u)) != 0;
+}
+
+// per directed edge: flag 0 = blocked, 1 = free and the reverse edge is listed free as well,
+// 2 = free and the reverse is not (row j gets the extra entry i)
+template <int NS>
+__global__ void __launch_bounds__(256) k_csr_degree(const int32_t *__restrict__ rec, const uint8_t *__restrict__ fr,
                                                     int64_t n, int k, int64_t total_edges,
-                                                    int32_t *__restrict__ deg) {
+                                                    uint8_t *__restrict__ flag, int32_t *__restrict__ deg) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= total_edges || !fr[e]) return;
+  if (e >= total_edges) return;
+  if (!fr[e]) {
+    flag[e] = 0;
+    return;
+  }
   const int64_t row = e / k;
+  const int slot = (int)(e - row * k);
   const int64_t qbase = (row / n) * n;
-  const int i = (int)(row - qbase), j = nbr[e];
-  atomicAdd(deg + row, 1);
-  if (!csr_has_free(nbr, fr, qbase + j, k, i)) atomicAdd(deg + qbase + j, 1);
+  const int i = (int)(row - qbase), j = rec[row * NS + slot];
+  const bool rev = csr_lists_free<NS>(rec, qbase + j, k, i);
+  flag[e] = rev ? 1 : 2;
+  if (!rev) atomicAdd(deg + qbase + j, 1);
 }
 
 // one CTA per query: row_ptr (relative) = exclusive scan of degrees; nnz per query
@@ -457,30 +693,39 @@ __global__ void __launch_bounds__(1024) k_csr_query_offsets(const int64_t *__res
   if (threadIdx.x == 0) nnz_off[q] = carry;
 }
 
-__global__ void __launch_bounds__(256) k_csr_fill(const int32_t *__restrict__ nbr, const uint8_t *__restrict__ fr,
+// own free neighbours go to the head of the row in slot order (rank from the mask, no atomics);
+// the extra entries contributed by other rows follow, placed with a per-row cursor
+template <int NS>
+__global__ void __launch_bounds__(256) k_csr_fill(const int32_t *__restrict__ rec, const uint8_t *__restrict__ flag,
                                                   int64_t n, int k, int64_t total_edges,
                                                   const int32_t *__restrict__ row_ptr,
                                                   const int64_t *__restrict__ nnz_off, int64_t cap,
                                                   int32_t *__restrict__ cursor, int32_t *__restrict__ col) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= total_edges || !fr[e]) return;
+  if (e >= total_edges) return;
+  const int fl = flag[e];
+  if (!fl) return;
   const int64_t row = e / k;
+  const int slot = (int)(e - row * k);
   const int64_t q = row / n, qbase = q * n;
-  const int i = (int)(row - qbase), j = nbr[e];
+  const int i = (int)(row - qbase), j = rec[row * NS + slot];
   const int32_t *rp = row_ptr + q * (n + 1);
   const int64_t base = nnz_off[q];
   {
-    const int64_t pos = base + rp[i] + atomicAdd(cursor + row, 1);
+    const unsigned mask = (unsigned)rec[row * NS + NS - 1];
+    const int64_t pos = base + rp[i] + __popc(mask & ((1u << slot) - 1u));
     if (pos < cap) col[pos] = j;
   }
-  if (!csr_has_free(nbr, fr, qbase + j, k, i)) {
-    const int64_t pos = base + rp[j] + atomicAdd(cursor + qbase + j, 1);
+  if (fl == 2) {
+    const unsigned mj = (unsigned)rec[(qbase + j) * NS + NS - 1];
+    const int64_t pos = base + rp[j] + __popc(mj) + atomicAdd(cursor + qbase + j, 1);
     if (pos < cap) col[pos] = i;
   }
 }
 
-// one thread per row: sort columns ascending (rows are short), then the FP64 weights
-// ||to - from|| from the double coordinates (:369-371)
+// one thread per row: sort columns ascending (rows are short: staged in a per-thread array),
+// then the FP64 weights ||to - from|| from the double coordinates (:369-371)
+#define CTP_CSR_LOCAL 40
 __global__ void __launch_bounds__(256) k_csr_finish(const double *__restrict__ nodes, int64_t n, int64_t total_rows,
                                                     const int32_t *__restrict__ row_ptr,
                                                     const int64_t *__restrict__ nnz_off, int64_t cap,
@@ -491,7 +736,30 @@ __global__ void __launch_bounds__(256) k_csr_finish(const double *__restrict__ n
   const int32_t *rp = row_ptr + q * (n + 1);
   const int64_t b = nnz_off[q] + rp[i], e = nnz_off[q] + rp[i + 1];
   if (e > cap) return;
-  for (int64_t a = b + 1; a < e; a++) {
+  const int len = (int)(e - b);
+  const double mx = nodes[3 * row], my = nodes[3 * row + 1], mz = nodes[3 * row + 2];
+  const double *nq = nodes + 3 * q * n;
+  if (len <= CTP_CSR_LOCAL) {
+    int32_t c[CTP_CSR_LOCAL];
+    for (int a = 0; a < len; a++) {
+      const int32_t key = col[b + a];
+      int p = a - 1;
+      while (p >= 0 && c[p] > key) {
+        c[p + 1] = c[p];
+        p--;
+      }
+      c[p + 1] = key;
+    }
+    for (int a = 0; a < len; a++) {
+      const int32_t cj = c[a];
+      col[b + a] = cj;
+      const double *o = nq + 3 * (int64_t)cj;
+      const double dx = o[0] - mx, dy = o[1] - my, dz = o[2] - mz;
+      w[b + a] = sqrt((dx * dx + dy * dy) + dz * dz);
+    }
+    return;
+  }
+  for (int64_t a = b + 1; a < e; a++) {  // very high in-degree: sort in place
     const int32_t key = col[a];
     int64_t p = a - 1;
     while (p >= b && col[p] > key) {
@@ -500,10 +768,18 @@ __global__ void __launch_bounds__(256) k_csr_finish(const double *__restrict__ n
     }
     col[p + 1] = key;
   }
-  const double *me = nodes + 3 * row;
   for (int64_t a = b; a < e; a++) {
-    const double *o = nodes + 3 * (q * n + col[a]);
-    const double dx = o[0] - me[0], dy = o[1] - me[1], dz = o[2] - me[2];
+    const double *o = nq + 3 * (int64_t)col[a];
+    const double dx = o[0] - mx, dy = o[1] - my, dz = o[2] - mz;
     w[a] = sqrt((dx * dx + dy * dy) + dz * dz);
   }
+}
+
+// neighbour records (stride NS) -> dense user-visible k-NN table (stride k)
+__global__ void __launch_bounds__(256) k_rec_to_nbr(const int32_t *__restrict__ rec, int ns, int k, int64_t total_edges,
+                                                    int32_t *__restrict__ nbr) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= total_edges) return;
+  const int64_t row = e / k;
+  nbr[e] = rec[row * ns + (e - row * k)];
 }

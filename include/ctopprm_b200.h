@@ -81,6 +81,10 @@ int ctp_reserve(ctp_map *map, int64_t q, int64_t n, int64_t m, int k);
  * reset (device counter; reading it synchronises the stream). */
 int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int reset);
 
+/* implementation knobs (defaults are the tuned ones; exposed for benchmarking) */
+#define CTP_TUNE_KNN_PER_CELL 0 /* k-NN grid: expected points inside a ball of one cell size (default 22) */
+#define CTP_TUNE_KNN_TILE 1     /* 1 = shared-memory tile search + ring-search fallback (default), 0 = ring search only */
+int ctp_set_tunable(ctp_map *map, int key, double value);
 /* number of kernels this handle has enqueued since the last reset (host-side counter) */
 int ctp_launch_counter_read(ctp_map *map, uint64_t *launches, int reset);
 /* stage timing of the _dev entry points, the library-side counterpart of the reference's

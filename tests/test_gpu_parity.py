@@ -171,6 +171,31 @@ def test_build_prm_csr(c1, layout):
         assert all((b, a) in pairs for a, b in pairs)
 
 
+@pytest.mark.parametrize("k", [3, 15, 16])
+def test_build_prm_other_k(c1, k):
+    m, om, c, e = c1
+    m.set_layout(capi.LAYOUT_PLAIN)
+    q, n = 2, 600
+    s, g, cand = _queries(c, e, q, n, 50 + k)
+    nodes = m.sample_reject(s, g, cand, CLR, n)[0]
+    got = m.build_prm(nodes, CLR, CDC, k=k)
+    for i in range(q):
+        want = om.build_prm(nodes[i], CLR, CDC, k=k, nthreads=8)
+        assert np.array_equal(got["nbr"][i], want["nbr"])
+        assert np.array_equal(got["directed_free"][i], want["directed_free"])
+        _csr_equal(got, i, want)
+
+
+def test_build_prm_fewer_nodes_than_k(c1):
+    m, om, c, e = c1
+    s, g, cand = _queries(c, e, 1, 9, 77)
+    nodes = m.sample_reject(s, g, cand, CLR, 9)[0]
+    got = m.build_prm(nodes, CLR, CDC)  # rows are padded with -1 neighbours
+    want = om.build_prm(nodes[0], CLR, CDC)
+    assert np.array_equal(got["nbr"][0], want["nbr"]) and (got["nbr"][0][:, 8:] == -1).all()
+    _csr_equal(got, 0, want)
+
+
 def test_sample_multiple_end_to_end(c1):
     m, om, c, e = c1
     q, n = 2, 800
