@@ -69,6 +69,13 @@ struct ctp_map {
   int knn_tile = 1;           // 1 = tile kernel + ring-search fallback, 0 = ring search only
   unsigned long long launches = 0;  // kernels enqueued by this handle (ctp_launch_counter_read)
   int prm_group = 1;  // ctp_build_prm: 1 = flat lookup-parallel kernel (kNN edges are ~3-12 samples long)
+  // chunk pipeline of the host-pointer ctp_sample_multiple
+  bool pipe_ready = false;
+  cudaStream_t pipe_st[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_in[2], ev_comp[2], ev_small[2], ev_out[2];
+  int64_t *h_off = nullptr;  // pinned staging of per-chunk CSR offsets
+  int64_t h_off_cap = 0;
+  int64_t pipe_chunk = 0;    // queries per chunk (0 = automatic)
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;    // pool, two per recorded span
   std::vector<int> prof_stage;         // stage id of span i (events 2i, 2i+1)
@@ -288,6 +295,16 @@ extern "C" int ctp_map_destroy(ctp_map *m) {
   cudaFree(m->ws.base);
   cudaFree(m->io.base);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+  if (m->pipe_ready) {
+    for (int i = 0; i < 4; i++) cudaStreamDestroy(m->pipe_st[i]);
+    for (int i = 0; i < 2; i++) {
+      cudaEventDestroy(m->ev_in[i]);
+      cudaEventDestroy(m->ev_comp[i]);
+      cudaEventDestroy(m->ev_small[i]);
+      cudaEventDestroy(m->ev_out[i]);
+    }
+  }
+  if (m->h_off) cudaFreeHost(m->h_off);
   delete m;
   return CTP_OK;
 }
@@ -317,6 +334,10 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
       return CTP_OK;
     case CTP_TUNE_KNN_TILE:
       m->knn_tile = value != 0.0;
+      return CTP_OK;
+    case CTP_TUNE_PIPE_CHUNK:
+      REQUIRE(value >= 0 && value <= 65535, "queries per chunk must be in [0, 65535]");
+      m->pipe_chunk = (int64_t)value;
       return CTP_OK;
     default:
       return fail(CTP_ERR_INVALID, "ctp_set_tunable: unknown key %d", key);
@@ -977,40 +998,134 @@ extern "C" int ctp_build_prm(ctp_map *m, const double *nodes, int64_t q, int64_t
                              d_col, d_w, d_off);
 }
 
+// Host candidate streams -> host CSRs.  The q queries are cut into chunks that flow through
+// streams for the host->device copy, the kernels and the device->host copies with double-buffered device staging, so
+// the PCIe transfers in both directions overlap the kernels; with page-locked host buffers
+// (ctp_host_alloc) the call runs at the speed of the slowest of the three.
+struct PipeBuf {
+  double *d_s, *d_g, *d_c, *d_n;
+  int32_t *d_nf, *d_nu, *d_rp, *d_col;
+  double *d_w;
+  int64_t *d_off;
+};
+
+static int pipe_init(ctp_map *m) {
+  if (m->pipe_ready) return CTP_OK;
+  for (int i = 0; i < 4; i++) CK(cudaStreamCreateWithFlags(&m->pipe_st[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_comp[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_small[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_out[i], cudaEventDisableTiming));
+  }
+  m->pipe_ready = true;
+  return CTP_OK;
+}
+
 extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double *goal, const double *cand,
                                    int64_t q, int64_t cnt, int64_t n, int k, double clr, double cdc, double *nodes,
                                    int32_t *n_filled, int32_t *row_ptr, int32_t *col, double *w, int64_t cap,
                                    int64_t *nnz_off) {
   REQUIRE(m && q >= 1 && n >= 2 && cnt >= 0 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument");
   REQUIRE(start && goal && cand && nodes && n_filled && row_ptr && col && w && nnz_off, "null buffer");
+  REQUIRE(cdc > 0, "collision_distance_check must be > 0");
   CK(cudaSetDevice(m->device));
-  const int64_t edges = q * n * k, dcap = 2 * edges;
-  CKR(arena_reserve(m->io, 2 * align_up(q * 24) + align_up(q * cnt * 24) + align_up(q * n * 24) + 2 * align_up(q * 4) +
-                               align_up(q * (n + 1) * 4) + align_up(dcap * 4) + align_up(dcap * 8) +
-                               align_up((q + 1) * 8)));
+  CKR(pipe_init(m));
+  // chunk size: about 8M directed edges per chunk, at least 1 query, at most 65535 (grid.y limits)
+  int64_t qc = m->pipe_chunk > 0 ? m->pipe_chunk : std::max<int64_t>(1, (8 << 20) / (n * k));
+  qc = std::min<int64_t>(std::min<int64_t>(qc, q), 65535);
+  REQUIRE(qc * n * k < ((int64_t)1 << 31), "n*k too large for one chunk");
+  const int64_t n_chunks = (q + qc - 1) / qc;
+  const int nbuf = n_chunks > 1 ? 2 : 1;
+  const int64_t ecap = 2 * qc * n * k;  // CSR entries a chunk can produce
+  size_t per = 2 * align_up(qc * 24) + align_up(qc * cnt * 24) + align_up(qc * n * 24) + 2 * align_up(qc * 4) +
+               align_up(qc * (n + 1) * 4) + align_up(ecap * 4) + align_up(ecap * 8) + align_up((qc + 1) * 8);
+  CKR(arena_reserve(m->io, nbuf * per + 4096));
+  CKR(ctp_reserve(m, qc, n, cnt, k));
+  if (m->h_off_cap < 2 * (qc + 1)) {
+    if (m->h_off) cudaFreeHost(m->h_off);
+    m->h_off = nullptr;
+    CK(cudaHostAlloc((void **)&m->h_off, 2 * (qc + 1) * sizeof(int64_t), cudaHostAllocDefault));
+    m->h_off_cap = 2 * (qc + 1);
+  }
   IoScope sc(m);
-  double *d_s = arena_take<double>(m->io, q * 3), *d_g = arena_take<double>(m->io, q * 3);
-  double *d_c = arena_take<double>(m->io, q * cnt * 3), *d_n = arena_take<double>(m->io, q * n * 3);
-  int32_t *d_nf = arena_take<int32_t>(m->io, q), *d_nu = arena_take<int32_t>(m->io, q);
-  int32_t *d_rp = arena_take<int32_t>(m->io, q * (n + 1));
-  int32_t *d_col = arena_take<int32_t>(m->io, dcap);
-  double *d_w = arena_take<double>(m->io, dcap);
-  int64_t *d_off = arena_take<int64_t>(m->io, q + 1);
-  CKR(ctp_reserve(m, q, n, cnt, k));
-  CK(cudaMemcpyAsync(d_s, start, q * 24, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_g, goal, q * 24, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_c, cand, q * cnt * 24, cudaMemcpyHostToDevice, 0));
-  m->ws.used = 0;
-  CKR(ctp_sample_reject_dev(m, d_s, d_g, d_c, q, cnt, clr, n, d_n, d_nf, d_nu, nullptr, 0));
-  CK(cudaMemcpyAsync(n_filled, d_nf, q * 4, cudaMemcpyDeviceToHost, 0));
-  CK(cudaStreamSynchronize(0));
+  PipeBuf B[2];
+  for (int i = 0; i < nbuf; i++) {
+    B[i].d_s = arena_take<double>(m->io, qc * 3);
+    B[i].d_g = arena_take<double>(m->io, qc * 3);
+    B[i].d_c = arena_take<double>(m->io, qc * cnt * 3);
+    B[i].d_n = arena_take<double>(m->io, qc * n * 3);
+    B[i].d_nf = arena_take<int32_t>(m->io, qc);
+    B[i].d_nu = arena_take<int32_t>(m->io, qc);
+    B[i].d_rp = arena_take<int32_t>(m->io, qc * (n + 1));
+    B[i].d_col = arena_take<int32_t>(m->io, ecap);
+    B[i].d_w = arena_take<double>(m->io, ecap);
+    B[i].d_off = arena_take<int64_t>(m->io, qc + 1);
+  }
+  cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1], s_out = m->pipe_st[2], s_small = m->pipe_st[3];
+  int64_t base = 0;     // CSR entries emitted by the chunks finished so far
+  int rc_deferred = CTP_OK;
+  nnz_off[0] = 0;
+  // second half of a chunk: once its offsets are on the host, copy exactly nnz col/w entries out
+  auto finish = [&](int64_t c) -> int {
+    const int bi = (int)(c % nbuf);
+    const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
+    CK(cudaEventSynchronize(m->ev_small[bi]));
+    const int64_t *ho = m->h_off + (size_t)bi * (qc + 1);
+    const int64_t nnz = ho[qn];
+    for (int64_t i = 1; i <= qn; i++) nnz_off[q0 + i] = base + ho[i];
+    if (base + nnz > cap) {
+      if (rc_deferred == CTP_OK)
+        rc_deferred = fail(CTP_ERR_CAPACITY, "CSR needs more than %lld entries", (long long)cap);
+    } else if (nnz) {
+      CK(cudaMemcpyAsync(col + base, B[bi].d_col, nnz * 4, cudaMemcpyDeviceToHost, s_out));
+      CK(cudaMemcpyAsync(w + base, B[bi].d_w, nnz * 8, cudaMemcpyDeviceToHost, s_out));
+    }
+    CK(cudaEventRecord(m->ev_out[bi], s_out));
+    base += nnz;
+    return CTP_OK;
+  };
+  for (int64_t c = 0; c < n_chunks; c++) {
+    const int bi = (int)(c % nbuf);
+    const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
+    PipeBuf &b = B[bi];
+    // inputs of chunk c: the staging buffer was last read by the kernels of chunk c - nbuf
+    if (c >= nbuf) CK(cudaStreamWaitEvent(s_in, m->ev_comp[bi], 0));
+    CK(cudaMemcpyAsync(b.d_s, start + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
+    CK(cudaMemcpyAsync(b.d_g, goal + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
+    if (cnt) CK(cudaMemcpyAsync(b.d_c, cand + 3 * q0 * cnt, qn * cnt * 24, cudaMemcpyHostToDevice, s_in));
+    CK(cudaEventRecord(m->ev_in[bi], s_in));
+    // kernels: outputs of chunk c - nbuf must have left the buffer
+    CK(cudaStreamWaitEvent(s_comp, m->ev_in[bi], 0));
+    if (c >= nbuf) CK(cudaStreamWaitEvent(s_comp, m->ev_out[bi], 0));
+    m->ws.used = 0;
+    CK(cudaMemsetAsync(b.d_n, 0, qn * n * 24, s_comp));  // rows of a query that runs out of candidates stay defined
+    CKR(ctp_sample_reject_dev(m, b.d_s, b.d_g, b.d_c, qn, cnt, clr, n, b.d_n, b.d_nf, b.d_nu, nullptr, s_comp));
+    CKR(ctp_build_prm_dev(m, b.d_n, qn, n, k, clr, cdc, nullptr, nullptr, b.d_rp, b.d_col, b.d_w, ecap, b.d_off,
+                          s_comp));
+    CK(cudaEventRecord(m->ev_comp[bi], s_comp));
+    // the previous chunk's col/w go out while this chunk computes
+    if (c >= 1) CKR(finish(c - 1));
+    // this chunk's offsets (own stream: they must not queue behind the big copies) ...
+    CK(cudaStreamWaitEvent(s_small, m->ev_comp[bi], 0));
+    CK(cudaMemcpyAsync(m->h_off + (size_t)bi * (qc + 1), b.d_off, (qn + 1) * 8, cudaMemcpyDeviceToHost, s_small));
+    CK(cudaMemcpyAsync(n_filled + q0, b.d_nf, qn * 4, cudaMemcpyDeviceToHost, s_small));
+    CK(cudaEventRecord(m->ev_small[bi], s_small));
+    // ... and its fixed-size outputs
+    CK(cudaStreamWaitEvent(s_out, m->ev_comp[bi], 0));
+    CK(cudaMemcpyAsync(nodes + 3 * q0 * n, b.d_n, qn * n * 24, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(row_ptr + q0 * (n + 1), b.d_rp, qn * (n + 1) * 4, cudaMemcpyDeviceToHost, s_out));
+  }
+  CKR(finish(n_chunks - 1));
+  CK(cudaStreamSynchronize(s_out));
+  CK(cudaStreamSynchronize(s_small));
+  CK(cudaStreamSynchronize(s_comp));
+  if (rc_deferred != CTP_OK) return rc_deferred;
   for (int64_t i = 0; i < q; i++)
     if (n_filled[i] < n)
-      return fail(CTP_ERR_NEED_CANDIDATES, "query %lld: only %d of %lld nodes accepted", (long long)i, n_filled[i], (long long)n);
-  CKR(ctp_build_prm_dev(m, d_n, q, n, k, clr, cdc, nullptr, nullptr, d_rp, d_col, d_w, dcap, d_off, 0));
-  CK(cudaMemcpyAsync(nodes, d_n, q * n * 24, cudaMemcpyDeviceToHost, 0));
-  return build_prm_host_tail(m, q, n, k, nullptr, nullptr, row_ptr, col, w, cap, nnz_off, nullptr, nullptr, d_rp,
-                             d_col, d_w, d_off);
+      return fail(CTP_ERR_NEED_CANDIDATES, "query %lld: only %d of %lld nodes accepted (candidate stream exhausted)",
+                  (long long)i, n_filled[i], (long long)n);
+  return CTP_OK;
 }
 
 #include "ctp_paths_api.inl"

@@ -411,14 +411,16 @@ __global__ void __launch_bounds__(128) k_knn_search_list(const float4 *__restric
 // ---- tile search: the fast path ---------------------------------------------------------------
 // A CTA takes a tile of TX x 2 x 2 cells.  The points of the tile plus a one-cell halo
 // ((TX+2) x 4 x 4 cells = 16 contiguous runs of the cell-sorted array) are staged in shared memory
-// once; every thread then owns one query point of the tile and scans the SAME staged list
-// (broadcast reads, no divergence).  Anything farther than 0.999 h cannot be ruled complete by the
-// halo, and anything nearer is guaranteed to be in it, so the scan only keeps candidates with
-// d2 < (0.999 h)^2 -- appended branch-free to a per-thread column in shared memory -- and the k
-// best of those are the exact answer whenever at least k were kept.  The top-k insertion network
-// therefore runs over ~20-30 survivors instead of diverging on every one of the ~500 candidates.
-// Queries with fewer than k (sparse borders) or more than CTP_KNN_KEEP survivors are appended to a
-// list and redone by the ring search (k_knn_search_list).
+// once, together with the position of every cell boundary inside the staged list.  Every thread
+// then owns one query point of the tile and scans the 3 x 3 x 3 cells around its own cell (nine
+// runs of three cells) out of shared memory.  Anything farther than 0.999 h cannot be ruled
+// complete by those 27 cells, and anything nearer is guaranteed to be in them, so the scan only
+// keeps candidates with d2 < (0.999 h)^2 -- appended branch-free to a per-thread column in shared
+// memory -- and the k best of those are the exact answer whenever at least k were kept.  The top-k
+// insertion network therefore runs over ~20-30 survivors instead of diverging on every candidate.
+// Queries with fewer than k (sparse borders) or more than CTP_KNN_KEEP survivors, and tiles whose
+// halo does not fit the staging buffer, are appended to a list and redone by the ring search
+// (k_knn_search_list).
 #define CTP_KNN_TX 4
 #define CTP_KNN_TILE_THREADS 128
 #define CTP_KNN_TILE_CAP 1024
@@ -426,24 +428,27 @@ __global__ void __launch_bounds__(128) k_knn_search_list(const float4 *__restric
 
 template <int K>
 __global__ void __launch_bounds__(CTP_KNN_TILE_THREADS)
-k_knn_tile(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restrict__ grids, int cell_stride, const int32_t *__restrict__ cell_start,
-           int32_t *__restrict__ idx, int idx_stride, float *__restrict__ d2out,
-           int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
+k_knn_tile(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restrict__ grids, int cell_stride,
+           const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
+           float *__restrict__ d2out, int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
   __shared__ float4 s_c[CTP_KNN_TILE_CAP];
   __shared__ uint16_t s_keep[CTP_KNN_KEEP][CTP_KNN_TILE_THREADS];  // survivor columns (index into s_c)
-  __shared__ int s_cb[17], s_cs[16];  // candidate runs: prefix count, start in the sorted array
-  __shared__ int s_qb[5], s_qs[4];    // query runs (the tile's own cells)
+  __shared__ int s_cb[17], s_cs[16];        // candidate runs: prefix count, start in the sorted array
+  __shared__ int s_cell[16][CTP_KNN_TX + 3];  // staged position of each cell boundary of a run
+  __shared__ int s_qb[5], s_qs[4];          // query runs (the tile's own cells)
   const int tid = threadIdx.x;
   // blockIdx.y = query; the gridDim.x CTAs of a query stride over its tiles
   const int64_t q = blockIdx.y;
   const KnnGrid g = grids[q];
   const int tx = (g.dx + CTP_KNN_TX - 1) / CTP_KNN_TX, ty = (g.dy + 1) >> 1, tz = (g.dz + 1) >> 1;
   const int n_tiles = tx * ty * tz;
+  const int32_t *st = cell_start + q * (cell_stride + 1);
+  const float4 *sq = sorted + q * n;
+  const float lb = (float)(g.h * 0.999);
+  const float lb2 = lb * lb;  // rounding here only shifts which queries take the fallback
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int x0 = (tile % tx) * CTP_KNN_TX, y0 = ((tile / tx) % ty) * 2, z0 = (tile / (tx * ty)) * 2;
-    const int32_t *st = cell_start + q * (cell_stride + 1);
-    const float4 *sq = sorted + q * n;
-    __syncthreads();  // previous item's shared arrays are no longer read
+    __syncthreads();  // previous tile's shared arrays are no longer read
     if (tid < 32) {
       int len = 0;
       if (tid < 16) {  // candidate run (dy, dz) in [-1, 2]^2, x cells x0-1 .. x0+TX
@@ -482,68 +487,87 @@ k_knn_tile(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restri
     __syncthreads();
     const int n_query = s_qb[4], n_cand = s_cb[16];
     if (n_query == 0) continue;
-    const float lb = (float)(g.h * 0.999);
-    const float lb2 = lb * lb;  // rounding here only shifts which queries take the fallback
-    for (int qb = 0; qb < n_query; qb += CTP_KNN_TILE_THREADS) {
-      const int qi = qb + tid;
-      const bool have = qi < n_query;
-      float4 me = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-      int qpos = 0;
-      if (have) {
+    if (n_cand > CTP_KNN_TILE_CAP) {  // unusually dense halo: the ring search takes the whole tile
+      for (int qi = tid; qi < n_query; qi += CTP_KNN_TILE_THREADS) {
         int r = 0;
 #pragma unroll
         for (int t = 1; t < 4; t++) r += (qi >= s_qb[t]) ? 1 : 0;
-        qpos = s_qs[r] + (qi - s_qb[r]);
-        me = sq[qpos];
+        fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + s_qs[r] + (qi - s_qb[r]));
       }
+      continue;
+    }
+    // cell boundaries inside the staged list
+    if (tid < 16 * (CTP_KNN_TX + 3)) {
+      const int r = tid / (CTP_KNN_TX + 3), t = tid - r * (CTP_KNN_TX + 3);
+      const int y = y0 - 1 + (r & 3), z = z0 - 1 + (r >> 2);
+      int pos = s_cb[r];
+      if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
+        const int row = (z * g.dy + y) * g.dx;
+        const int xlo = max(x0 - 1, 0), xhi = min(x0 + CTP_KNN_TX, g.dx - 1);
+        const int gb = min(max(x0 - 1 + t, xlo), xhi + 1);
+        pos += st[row + gb] - s_cs[r];
+      }
+      s_cell[r][t] = pos;
+    }
+    for (int i = tid; i < n_cand; i += CTP_KNN_TILE_THREADS) {
+      int r = 0;
+#pragma unroll
+      for (int t = 1; t < 16; t++) r += (i >= s_cb[t]) ? 1 : 0;
+      s_c[i] = sq[s_cs[r] + (i - s_cb[r])];
+    }
+    __syncthreads();
+    for (int qb = 0; qb < n_query; qb += CTP_KNN_TILE_THREADS) {
+      const int qi = qb + tid;
+      if (qi >= n_query) break;  // no barrier below this point
+      int r = 0;
+#pragma unroll
+      for (int t = 1; t < 4; t++) r += (qi >= s_qb[t]) ? 1 : 0;
+      const int qpos = s_qs[r] + (qi - s_qb[r]);
+      const float4 me = sq[qpos];
       const int self = __float_as_int(me.w);
-      const float my_lb2 = have ? lb2 : -1.f;  // idle threads keep nothing
+      const int lx = knn_cell_1d(me.x, g.lox, g.inv_h, g.dx) - x0;  // cell inside the tile
+      const int ly = knn_cell_1d(me.y, g.loy, g.inv_h, g.dy) - y0;
+      const int lz = knn_cell_1d(me.z, g.loz, g.inv_h, g.dz) - z0;
+      int kept = 0;
+#pragma unroll
+      for (int dz = 0; dz < 3; dz++) {
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++) {
+          const int run = (lz + dz) * 4 + (ly + dy);
+          const int pb = s_cell[run][lx], pe = s_cell[run][lx + 3];
+          for (int c = pb; c < pe; c++) {
+            const float4 o = s_c[c];
+            const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+            const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+            const bool keep = dd < lb2;
+            if (keep) s_keep[min(kept, CTP_KNN_KEEP - 1)][tid] = (uint16_t)c;
+            kept += keep ? 1 : 0;
+          }
+        }
+      }
+      // kept includes the query itself (d2 = 0)
       TopK<K> best;
       best.init();
-      bool redo = false;
-      for (int cb = 0; cb < n_cand; cb += CTP_KNN_TILE_CAP) {
-        const int cnt = min(CTP_KNN_TILE_CAP, n_cand - cb);
-        __syncthreads();
-        for (int i = tid; i < cnt; i += CTP_KNN_TILE_THREADS) {
-          const int ci = cb + i;
-          int r = 0;
-#pragma unroll
-          for (int t = 1; t < 16; t++) r += (ci >= s_cb[t]) ? 1 : 0;
-          s_c[i] = sq[s_cs[r] + (ci - s_cb[r])];
-        }
-        __syncthreads();
-        int kept = 0;
-#pragma unroll 4
-        for (int c = 0; c < cnt; c++) {
-          const float4 o = s_c[c];
-          const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
-          const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
-          const bool keep = (dd < my_lb2) & (__float_as_int(o.w) != self);
-          if (keep) s_keep[min(kept, CTP_KNN_KEEP - 1)][tid] = (uint16_t)c;
-          kept += keep ? 1 : 0;
-        }
-        redo |= kept > CTP_KNN_KEEP;
-        kept = min(kept, CTP_KNN_KEEP);
-        for (int t = 0; t < kept; t++) {
-          const float4 o = s_c[s_keep[t][tid]];
-          const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
-          const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
-          best.push(dd, __float_as_int(o.w));
-        }
+      const bool redo = kept > CTP_KNN_KEEP;
+      kept = min(kept, CTP_KNN_KEEP);
+      for (int t = 0; t < kept; t++) {
+        const float4 o = s_c[s_keep[t][tid]];
+        const int j = __float_as_int(o.w);
+        const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+        const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+        if (j != self) best.push(dd, j);
       }
-      if (have) {
-        if (!redo && best.id[K - 1] != 0x7fffffff) {
-          int32_t *oi = idx + (q * n + self) * idx_stride;
+      if (!redo && best.id[K - 1] != 0x7fffffff) {
+        int32_t *oi = idx + (q * n + self) * idx_stride;
 #pragma unroll
-          for (int s = 0; s < K; s++) oi[s] = best.id[s];
-          if (d2out) {
-            float *od = d2out + (q * n + self) * K;
+        for (int s = 0; s < K; s++) oi[s] = best.id[s];
+        if (d2out) {
+          float *od = d2out + (q * n + self) * K;
 #pragma unroll
-            for (int s = 0; s < K; s++) od[s] = best.d[s];
-          }
-        } else {
-          fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + qpos);
+          for (int s = 0; s < K; s++) od[s] = best.d[s];
         }
+      } else {
+        fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + qpos);
       }
     }
   }

@@ -84,6 +84,7 @@ int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int r
 /* implementation knobs (defaults are the tuned ones; exposed for benchmarking) */
 #define CTP_TUNE_KNN_PER_CELL 0 /* k-NN grid: expected points inside a ball of one cell size (default 22) */
 #define CTP_TUNE_KNN_TILE 1     /* 1 = shared-memory tile search + ring-search fallback (default), 0 = ring search only */
+#define CTP_TUNE_PIPE_CHUNK 2   /* queries per chunk of the ctp_sample_multiple copy/compute pipeline (0 = automatic) */
 int ctp_set_tunable(ctp_map *map, int key, double value);
 /* number of kernels this handle has enqueued since the last reset (host-side counter) */
 int ctp_launch_counter_read(ctp_map *map, uint64_t *launches, int reset);
@@ -187,7 +188,11 @@ int ctp_build_prm_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, i
                       void *stream);
 /* whole sampleMultiple from host candidate streams to host CSRs in one call (the
  * end-to-end path bench.py times): ctp_sample_reject + ctp_build_prm without the
- * intermediate host round trip.  nodes (q x n x 3) is also returned. */
+ * intermediate host round trip.  nodes (q x n x 3) is also returned.  The queries are cut
+ * into chunks whose host->device copies, kernels and device->host copies overlap on three
+ * streams; pass page-locked buffers (ctp_host_alloc) to get the overlap.  When a candidate
+ * stream runs out, the other queries' outputs are still complete and the call returns
+ * CTP_ERR_NEED_CANDIDATES (n_filled tells which). */
 int ctp_sample_multiple(ctp_map *map, const double *start, const double *goal,
                         const double *cand, int64_t q, int64_t m, int64_t n, int k, double clr,
                         double cdc, double *nodes, int32_t *n_filled, int32_t *row_ptr,

@@ -208,6 +208,41 @@ def test_sample_multiple_end_to_end(c1):
         _csr_equal(out, i, want)
 
 
+@pytest.mark.parametrize("chunk", [1, 2, 3])
+def test_sample_multiple_chunk_pipeline(c1, chunk):
+    """the host API cuts the queries into chunks on three streams; results must not depend on it"""
+    m, om, c, e = c1
+    q, n = 5, 500
+    s, g, cand = _queries(c, e, q, n, 61)
+    pin = {k_: capi.pinned_empty(v.shape, v.dtype) for k_, v in dict(s=s, g=g, cand=cand).items()}
+    pin["s"][:], pin["g"][:], pin["cand"][:] = s, g, cand
+    m.set_tunable(capi.TUNE_PIPE_CHUNK, chunk)
+    try:
+        out = m.sample_multiple(pin["s"], pin["g"], pin["cand"], n, CLR, CDC)
+    finally:
+        m.set_tunable(capi.TUNE_PIPE_CHUNK, 0)
+    assert out["nnz_off"][0] == 0
+    for i in range(q):
+        n0 = om.sample_reject(s[i], g[i], cand[i], CLR, n)[0]
+        assert np.array_equal(out["nodes"][i], n0)
+        _csr_equal(out, i, om.build_prm(n0, CLR, CDC, nthreads=8))
+
+
+def test_sample_multiple_short_stream(c1):
+    m, om, c, e = c1
+    q, n = 3, 400
+    s, g, cand = _queries(c, e, q, n, 62)
+    cand = cand.copy()
+    cand[1, 100:] = c - e  # query 1: every later candidate lies outside the map
+    m.set_tunable(capi.TUNE_PIPE_CHUNK, 1)
+    try:
+        with pytest.raises(capi.CtpError) as ei:
+            m.sample_multiple(s, g, cand, n, CLR, CDC)
+    finally:
+        m.set_tunable(capi.TUNE_PIPE_CHUNK, 0)
+    assert ei.value.code == capi.ERR_NEED_CANDIDATES
+
+
 def _split(g, key_pts, key_off):
     off = g[key_off]
     return [g[key_pts][off[i]:off[i + 1]] for i in range(len(off) - 1)]
