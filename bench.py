@@ -249,7 +249,7 @@ def main():
                "tex": capi.LAYOUT_TEX, "brick": capi.LAYOUT_BRICK}
     layout = layouts[args.layout]
     if args.layout == "auto":
-        layout = capi.DEFAULT_LAYOUT
+        layout = capi.DEFAULT_LAYOUT if vox.shape[0] <= 1024 else capi.LAYOUT_PLAIN
     dmap = capi.DeviceMap(vox, c, e, device=local, layouts=layout | capi.LAYOUT_PLAIN)
     dmap.set_layout(layout)
     if args.group:

@@ -1,0 +1,327 @@
+// topological_prm_clustering.cpp -- TopologicalPRMClustering<Vector<3>> on the C ABI.
+#include "ctopprm/topological_prm_clustering.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <chrono>
+#include <fstream>
+
+typedef Vector<3> V3;
+typedef HeapNode<V3> Node;
+typedef path_with_length<V3> Path;
+typedef TopologicalPRMClustering<V3> Planner;
+
+template <> std::shared_ptr<BaseMap> Planner::map_ = nullptr;
+template <> std::string Planner::output_folder_ = "./";
+template <> double Planner::collision_distance_check_ = 0;
+template <> double Planner::min_clearance_ = 0;
+template <> double Planner::cutoof_distance_ratio_to_shortest_ = 0;
+template <> double Planner::min_allowed = 0;
+template <> uint64_t Planner::sampling_seed = 1;
+template <>
+std::function<std::vector<Path>(Planner &, const Path &)> Planner::cluster_stage =
+    [](Planner &, const Path &shortest) { return std::vector<Path>{shortest}; };
+
+namespace {
+[[noreturn]] void die(const char *what) {
+  ERROR(what << ": " << ctp_last_error());
+  exit(1);
+}
+ctp_map *handleOf(const std::shared_ptr<BaseMap> &m, const char *who) {
+  if (!m || !m->deviceMap()) throw std::runtime_error(std::string(who) + ": the map is not resident on a device");
+  return m->deviceMap();
+}
+void packPaths(const std::vector<Path> &paths, std::vector<double> &pts, std::vector<int32_t> &off, std::vector<double> &len) {
+  off.assign(1, 0);
+  pts.clear();
+  len.clear();
+  for (auto &p : paths) {
+    for (auto *n : p.plan) pts.insert(pts.end(), n->data.data(), n->data.data() + 3);
+    off.push_back((int32_t)(pts.size() / 3));
+    len.push_back(p.length);
+  }
+}
+}  // namespace
+
+template <>
+Planner::TopologicalPRMClustering(const YAML::Node &planner_config, std::shared_ptr<BaseMap> map, std::string output_folder,
+                                  V3 start, V3 end, double, double) {
+  map_ = map;
+  output_folder_ = output_folder;
+  start_ = new Node(start);
+  start_->city_node = true;
+  start_->id = 0;
+  end_ = new Node(end);
+  end_->city_node = true;
+  end_->id = 1;
+  // the eleven keys of the reference constructor (:257-269)
+  num_clusters_ = loadParam<int>(planner_config, "num_clusters");
+  max_clusters_ = loadParam<int>(planner_config, "max_clusters");
+  min_clusters_ = loadParam<int>(planner_config, "min_clusters");
+  min_ratio_ = loadParam<double>(planner_config, "min_ratio");
+  planar_ = loadParam<bool>(planner_config, "planar");
+  max_path_length_ratio_ = loadParam<double>(planner_config, "max_path_length_ratio");
+  cutoof_distance_ratio_to_shortest_ = loadParam<double>(planner_config, "cutoof_distance_ratio_to_shortest");
+  min_clearance_ = loadParam<double>(planner_config, "min_clearance");
+  collision_distance_check_ = loadParam<double>(planner_config, "collision_distance_check");
+  ellipse_ratio_major_axis_focal_length_ = loadParam<double>(planner_config, "ellipse_ratio_major_axis_focal_length");
+  if (collision_distance_check_ == 0) {
+    ERROR("you need to specify collision_distance_check for sampling-based motion planning");
+    exit(1);
+  }
+}
+
+template <> void Planner::setBorders(V3 min_position, V3 max_position) {
+  min_position_ = min_position;
+  max_position_ = max_position;
+  position_range_ = max_position - min_position;
+}
+
+// PRM construction (:288-401): candidates -> rejection -> k-NN(13) -> directed checks -> symmetric
+// adjacency, one ctp_sample_multiple call; the CSR is re-materialised into visibility_node_ids.
+template <> void Planner::sampleMultiple(const int num_samples) {
+  ctp_map *h = handleOf(map_, "sampleMultiple");
+  const int n = num_samples, k = num_nn - 1;
+  if (n < 2) return;
+  std::vector<double> nodes((size_t)n * 3), w((size_t)2 * n * k);
+  std::vector<int32_t> row_ptr((size_t)n + 1), col((size_t)2 * n * k);
+  int32_t n_filled = 0;
+  int64_t nnz_off[2] = {0, 0};
+  std::vector<V3> cand = candidate_stream_;
+  const bool generated = cand.empty();
+  int64_t m = generated ? 4 * (int64_t)n : (int64_t)cand.size();
+  for (int attempt = 0;; attempt++) {
+    if (generated) {
+      cand.resize((size_t)m);
+      if (ctp_sample_ellipsoid(h, start_->data.data(), end_->data.data(), 1, m, ellipse_ratio_major_axis_focal_length_,
+                               planar_ ? 1 : 0, sampling_seed, cand[0].data()) != CTP_OK)
+        die("ctp_sample_ellipsoid");
+    }
+    const int rc = ctp_sample_multiple(h, start_->data.data(), end_->data.data(), cand[0].data(), 1, m, n, k, min_clearance_,
+                                       collision_distance_check_, nodes.data(), &n_filled, row_ptr.data(), col.data(),
+                                       w.data(), (int64_t)col.size(), nnz_off);
+    if (rc == CTP_OK) break;
+    if (rc == CTP_ERR_NEED_CANDIDATES && generated && attempt < 6) {
+      m *= 4;  // the reference's do/while would simply keep drawing (:314-317)
+      continue;
+    }
+    die("ctp_sample_multiple");
+  }
+  nodes_.assign((size_t)n, nullptr);
+  nodes_[0] = start_;
+  nodes_[1] = end_;
+  for (int i = 2; i < n; i++) {
+    nodes_[i] = new Node(V3(nodes[3 * (size_t)i], nodes[3 * (size_t)i + 1], nodes[3 * (size_t)i + 2]));
+    nodes_[i]->id = i;
+  }
+  for (int i = 0; i < n; i++)
+    for (int32_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) nodes_[i]->visibility_node_ids[nodes_[col[e]]] = w[e];
+}
+
+template <> std::vector<Path> Planner::findShortestPath() { return dijkstra.findPath(0, {1}, nodes_); }
+
+template <> std::vector<V3> Planner::samplePath(std::vector<Node *> path, const double length_tot, const double num_samples) {
+  return map_->samplePath(path, length_tot, num_samples);
+}
+
+// shorten_path (:2313-2479) for many polylines at once.  New push-off points become new HeapNodes;
+// reused input nodes keep their identity; consecutive nodes of a shortened path are linked in
+// visibility_node_ids as the reference does (:2414-2415, :2448-2449).
+template <> std::vector<Path> Planner::shorten_paths(const std::vector<Path> &paths, bool forward) {
+  if (paths.empty()) return {};
+  ctp_map *h = handleOf(map_, "shorten_path");
+  std::vector<double> pts, len;
+  std::vector<int32_t> off;
+  packPaths(paths, pts, off, len);
+  const int64_t count = (int64_t)paths.size();
+  int32_t cap = 0;
+  for (auto &p : paths) cap = std::max<int32_t>(cap, (int32_t)p.plan.size());
+  cap += 64;
+  for (;;) {
+    std::vector<double> out((size_t)count * cap * 3), out_len((size_t)count);
+    std::vector<int32_t> origin((size_t)count * cap), out_n((size_t)count), status((size_t)count);
+    if (ctp_shorten_path(h, pts.data(), off.data(), len.data(), count, forward ? 1 : 0, min_clearance_,
+                         collision_distance_check_, cap, out.data(), origin.data(), out_n.data(), out_len.data(),
+                         status.data()) != CTP_OK)
+      die("ctp_shorten_path");
+    bool grow = false;
+    for (int64_t i = 0; i < count; i++) grow |= status[i] == CTP_ERR_CAPACITY;
+    if (grow) {
+      cap *= 2;
+      continue;
+    }
+    std::vector<Path> res((size_t)count);
+    for (int64_t i = 0; i < count; i++) {
+      if (status[i] == 1) {  // "no point added to shortened path after collision": original path (:2423-2427)
+        INFO("no point added to shortened path after collision");
+        res[i] = paths[i];
+        continue;
+      }
+      if (status[i] == CTP_ERR_SAMPLE_PATH) {
+        ERROR("samplePath: sampling beyond the path end");
+        exit(1);
+      }
+      if (status[i] != 0) {  // the reference's self-check (:2463-2473) ends the program
+        ERROR("shortened path length does not equal lenght of its parts");
+        exit(1);
+      }
+      Path s;
+      s.from_id = paths[i].from_id;
+      s.to_id = paths[i].to_id;
+      s.length = out_len[i];
+      for (int32_t a = 0; a < out_n[i]; a++) {
+        const int32_t o = origin[(size_t)i * cap + a];
+        Node *nd;
+        if (o >= 0) nd = paths[i].plan[o];
+        else {
+          const double *q = &out[((size_t)i * cap + a) * 3];
+          nd = new Node(V3(q[0], q[1], q[2]));
+        }
+        if (!s.plan.empty()) {
+          Node *prev = s.plan.back();
+          const double d = (nd->data - prev->data).norm();
+          prev->visibility_node_ids[nd] = d;
+          nd->visibility_node_ids[prev] = d;
+        }
+        s.plan.push_back(nd);
+      }
+      res[i] = s;
+    }
+    return res;
+  }
+}
+
+template <> Path Planner::shorten_path(Path path, bool forward) { return shorten_paths({path}, forward)[0]; }
+
+template <> std::vector<Path> Planner::removeTooLongPaths(std::vector<Path> paths) {
+  std::vector<Path> proned = paths;
+  double min_length = DBL_MAX;
+  for (auto &p : proned)
+    if (p.length < min_length && p.length > min_allowed) min_length = p.length;
+  for (int i = (int)proned.size() - 1; i >= 0; i--)
+    if (proned[i].length > cutoof_distance_ratio_to_shortest_ * min_length || proned[i].length < min_allowed)
+      proned.erase(proned.begin() + i);
+  return proned;
+}
+
+// removeEquivalentPaths (:2237-2298).  The reference only ever compares ORIGINAL paths (a slot that
+// was replaced by a shorter equivalent is never compared again), so the whole upper-triangular
+// deformability matrix is one batch and the keep-shortest bookkeeping is replayed on the host.
+template <> std::vector<Path> Planner::removeEquivalentPaths(std::vector<Path> paths) {
+  const int P = (int)paths.size();
+  if (P <= 1) return paths;
+  std::vector<std::vector<Node *>> plans;
+  std::vector<double> lens;
+  for (auto &p : paths) {
+    plans.push_back(p.plan);
+    lens.push_back(p.length);
+  }
+  std::vector<int> ia, ib;
+  std::vector<double> num;
+  for (int i = 0; i < P; i++)
+    for (int j = i + 1; j < P; j++) {
+      ia.push_back(i);
+      ib.push_back(j);
+      const double larger = lens[i] > lens[j] ? lens[i] : lens[j];
+      num.push_back(std::ceil(larger / collision_distance_check_) + 1);
+    }
+  const std::vector<uint8_t> def = map_->isDeformablePathBatch(plans, lens, ia, ib, num, min_clearance_, collision_distance_check_);
+  auto deformable = [&](int a, int b) {
+    if (a > b) std::swap(a, b);
+    // pair (a, b), a < b, sits at a*P - a(a+1)/2 + (b - a - 1)
+    return def[(size_t)a * P - (size_t)a * (a + 1) / 2 + (size_t)(b - a - 1)] == 1;
+  };
+  std::vector<int> keep(P);
+  for (int i = 0; i < P; i++) keep[i] = i;
+  size_t i = 0;
+  while (i < keep.size()) {
+    size_t shortest = i;
+    double shortest_len = lens[keep[i]];
+    std::vector<size_t> rm;
+    for (size_t j = i + 1; j < keep.size(); j++)
+      if (deformable(keep[i], keep[j])) {
+        rm.push_back(j);
+        if (lens[keep[j]] < shortest_len) {
+          shortest = j;
+          shortest_len = lens[keep[j]];
+        }
+      }
+    if (shortest != i) keep[i] = keep[shortest];
+    for (size_t t = rm.size(); t-- > 0;) keep.erase(keep.begin() + (long)rm[t]);
+    i++;
+  }
+  std::vector<Path> out;
+  for (int id : keep) out.push_back(paths[id]);
+  return out;
+}
+
+// ---- CSV writers: node rows "x,y,z", edge rows "x0,y0,z0,x1,y1,z1" (:2066-2150; consumer
+// columns_2(...).py:20-33 tells them apart by column count).  Default ostream precision.
+template <> void Planner::saveRoadmapDense(std::string filename) {
+  std::ofstream f(filename);
+  if (!f.is_open()) return;
+  for (auto *n : nodes_) f << n->data(0) << "," << n->data(1) << "," << n->data(2) << std::endl;
+  for (auto *n : nodes_)
+    for (auto &nb : n->visibility_node_ids)
+      f << n->data(0) << "," << n->data(1) << "," << n->data(2) << "," << nb.first->data(0) << "," << nb.first->data(1) << ","
+        << nb.first->data(2) << std::endl;
+}
+
+template <> void Planner::savePath(std::string filename, std::vector<Node *> path) {
+  std::ofstream f(filename);
+  if (!f.is_open()) return;
+  for (size_t i = 1; i < path.size(); i++)
+    f << path[i - 1]->data(0) << "," << path[i - 1]->data(1) << "," << path[i - 1]->data(2) << "," << path[i]->data(0) << ","
+      << path[i]->data(1) << "," << path[i]->data(2) << std::endl;
+}
+
+template <> void Planner::savePathSamples(std::string filename, std::vector<V3> path) {
+  std::ofstream f(filename);
+  if (!f.is_open()) return;
+  for (size_t i = 1; i < path.size(); i++)
+    f << path[i - 1](0) << "," << path[i - 1](1) << "," << path[i - 1](2) << "," << path[i](0) << "," << path[i](1) << ","
+      << path[i](2) << std::endl;
+}
+
+// static entry point (:2489-2684): per consecutive gate pair, PRM build -> Dijkstra -> [cluster stage]
+// -> shorten both directions -> prune long -> prune equivalent -> shorten again -> prune equivalent
+// -> sort by length.  Phase timers keep the reference's names (:2561,2568,2605).
+template <>
+std::vector<std::vector<Path>> Planner::find_geometrical_paths(const YAML::Node &planner_config, std::shared_ptr<BaseMap> map,
+                                                               std::vector<V3> &gates, std::string output_folder) {
+  auto now = [] { return std::chrono::high_resolution_clock::now(); };
+  auto ms = [](auto a, auto b) { return std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() * 1e-6; };
+  std::vector<std::vector<Path>> paths_between_gates;
+  if (gates.size() < 2) return paths_between_gates;
+  const int num_samples_between_gate = (int)loadParam<double>(planner_config, "num_samples_between_gate");
+  paths_between_gates.resize(gates.size() - 1);
+  for (size_t i = 0; i + 1 < gates.size(); i++) {
+    Planner prm(planner_config, map, output_folder, gates[i], gates[i + 1]);
+    prm.setBorders(map->getMinPos(), map->getMaxPos());
+    auto t0 = now();
+    prm.sampleMultiple(num_samples_between_gate);
+    auto t1 = now();
+    INFO_GREEN("prm time clustering " << ms(t0, t1) << " ms");
+    std::vector<Path> shortest = prm.findShortestPath();
+    auto t2 = now();
+    INFO_GREEN("djikstra time clustering " << ms(t1, t2) << " ms");
+    if (shortest.empty() || shortest[0].plan.empty()) return paths_between_gates;  // :2569-2572
+    prm.max_path_length_ = shortest[0].length * prm.max_path_length_ratio_;
+    std::vector<Path> found = cluster_stage(prm, shortest[0]);
+    prm.saveRoadmapDense(output_folder + "roadmap_all" + std::to_string(i) + ".csv");
+    INFO_GREEN("algorithm time clustering " << ms(t0, now()) << " ms");
+    auto both_ways = [](std::vector<Path> in) {  // shorten_path(false) then shorten_path(true) (:2612-2625)
+      return shorten_paths(shorten_paths(in, false), true);
+    };
+    std::vector<Path> shortened = both_ways(found);
+    shortened = removeTooLongPaths(shortened);
+    shortened = removeEquivalentPaths(shortened);
+    shortened = both_ways(shortened);
+    shortened = removeEquivalentPaths(shortened);
+    std::sort(shortened.begin(), shortened.end(), [](const Path &a, const Path &b) { return a.length < b.length; });
+    paths_between_gates[i] = shortened;
+  }
+  return paths_between_gates;
+}
+
+template class TopologicalPRMClustering<Vector<3>>;

@@ -1,0 +1,216 @@
+"""ctypes view of libctopprm_host.so: the C++ class surface of include/ctopprm/*.hpp (ESDFMap, BaseMap,
+TopologicalPRMClustering) driven through the flat test entry points of csrc/host/host_capi.cpp.
+Used by the parity tests; a C++ caller includes the headers directly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+DEFAULT_YAML = """\
+# builder-authored defaults (BASELINE.md section 4); the reference ships no YAML
+map_type: ESDF
+map: {map}
+min_clearance: {clr}
+check_collisions: true
+collision_distance_check: {cdc}
+ellipse_ratio_major_axis_focal_length: 1.2
+planar: {planar}
+num_samples_between_gate: {n}
+num_clusters: 2
+min_clusters: 2
+max_clusters: 10
+min_ratio: 1.1
+max_path_length_ratio: 1.5
+cutoof_distance_ratio_to_shortest: 1.3
+start:
+  position: [{s[0]}, {s[1]}, {s[2]}]
+end:
+  position: [{g[0]}, {g[1]}, {g[2]}]
+"""
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libctopprm_host.so")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(lib_path()):
+            raise ImportError(lib_path() + " is missing: run __graft_entry__.build()")
+        L = C.CDLL(lib_path())
+        L.ctph_map_load.restype = C.c_void_p
+        L.ctph_planner_new.restype = C.c_void_p
+        L.ctph_get_clearence.restype = C.c_double
+        L.ctph_planner_graph.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def yaml_get(text, key):
+    buf = C.create_string_buffer(256)
+    ok = lib().ctph_yaml_get(text.encode(), key.encode(), buf, 256)
+    return buf.value.decode() if ok else None
+
+
+class HostMap:
+    """ESDFMap (include/ctopprm/esdf_map.hpp) loaded from a map FILE."""
+
+    def __init__(self, filename, device=0, layouts=0):
+        self.h = C.c_void_p(lib().ctph_map_load(filename.encode(), device, layouts))
+        if not self.h:
+            raise RuntimeError("ESDFMap::load failed for " + filename)
+
+    def close(self):
+        if self.h:
+            lib().ctph_map_free(self.h)
+            self.h = None
+
+    def get_clearence(self, p):
+        p = _f(p)
+        return lib().ctph_get_clearence(self.h, _p(p))
+
+    def min_max(self):
+        o = np.empty(6)
+        lib().ctph_min_max(self.h, _p(o))
+        return o[:3], o[3:]
+
+    def gradient(self, p):
+        p = _f(p)
+        g, c = np.empty(3), np.empty(3)
+        lib().ctph_gradient(self.h, _p(p), _p(g), _p(c))
+        return g, c
+
+    def real_pos_from_index(self, q):
+        q = _f(q)
+        o = np.empty(3)
+        lib().ctph_real_pos_from_index(self.h, _p(q), _p(o))
+        return o
+
+    def in_collision(self, p, clr):
+        p = _f(p)
+        return bool(lib().ctph_in_collision(self.h, _p(p), C.c_double(clr)))
+
+    def edge_nodes(self, a, b, clr, cdc):
+        a, b = _f(a), _f(b)
+        hit = np.empty(3)
+        r = lib().ctph_edge_nodes(self.h, _p(a), _p(b), C.c_double(clr), C.c_double(cdc), _p(hit))
+        return bool(r), hit
+
+    def edge_guards(self, a, b, clr, cdc):
+        a, b = _f(a), _f(b)
+        return bool(lib().ctph_edge_guards(self.h, _p(a), _p(b), C.c_double(clr), C.c_double(cdc)))
+
+    def path_collision_free(self, pts, clr, cdc):
+        pts = _f(pts).reshape(-1, 3)
+        hit = np.empty(3)
+        r = lib().ctph_path_collision_free(self.h, _p(pts), len(pts), C.c_double(clr), C.c_double(cdc), _p(hit))
+        return bool(r), hit
+
+    def deformable(self, p1, l1, p2, l2, num, clr, cdc):
+        p1, p2 = _f(p1).reshape(-1, 3), _f(p2).reshape(-1, 3)
+        return lib().ctph_deformable(self.h, _p(p1), len(p1), C.c_double(l1), _p(p2), len(p2), C.c_double(l2),
+                                     C.c_double(num), C.c_double(clr), C.c_double(cdc))
+
+    def deformable_between(self, s, e, b1, b2, clr, cdc):
+        s, e, b1, b2 = (_f(x) for x in (s, e, b1, b2))
+        return lib().ctph_deformable_between(self.h, _p(s), _p(e), _p(b1), _p(b2), C.c_double(clr), C.c_double(cdc))
+
+    def sample_path(self, pts, length, num):
+        pts = _f(pts).reshape(-1, 3)
+        out = np.empty((int(num), 3))
+        lib().ctph_sample_path(self.h, _p(pts), len(pts), C.c_double(length), C.c_double(num), _p(out))
+        return out
+
+    def fill_random_state_in_ellipse(self, s, g, ratio, planar, seed, count):
+        s, g = _f(s), _f(g)
+        out = np.empty((count, 3))
+        lib().ctph_fill_random_state_in_ellipse(self.h, _p(s), _p(g), C.c_double(ratio), int(planar), C.c_uint64(seed),
+                                                count, _p(out))
+        return out
+
+    def find_geometrical_paths(self, yaml_text, start, goal, out_dir, cap=64):
+        s, g = _f(start), _f(goal)
+        lens = np.empty(cap)
+        n = lib().ctph_find_geometrical_paths(self.h, yaml_text.encode(), _p(s), _p(g), out_dir.encode(), _p(lens), cap)
+        return lens[:min(n, cap)]
+
+
+class HostPlanner:
+    """TopologicalPRMClustering<Vector<3>> (include/ctopprm/topological_prm_clustering.hpp)."""
+
+    def __init__(self, hmap, yaml_text, start, goal):
+        s, g = _f(start), _f(goal)
+        self.map = hmap
+        self.h = C.c_void_p(lib().ctph_planner_new(hmap.h, yaml_text.encode(), _p(s), _p(g)))
+        if not self.h:
+            raise RuntimeError("planner construction failed")
+
+    def close(self):
+        if self.h:
+            lib().ctph_planner_free(self.h)
+            self.h = None
+
+    def set_candidates(self, cand):
+        cand = _f(cand).reshape(-1, 3)
+        lib().ctph_planner_set_candidates(self.h, _p(cand), C.c_int64(len(cand)))
+
+    def sample_multiple(self, n):
+        lib().ctph_planner_sample_multiple(self.h, n)
+        self.n = n
+
+    def graph(self, k=13):
+        n = self.n
+        nodes = np.empty((n, 3))
+        row_ptr = np.empty(n + 1, dtype=np.int32)
+        cap = 2 * n * k + 64
+        col = np.empty(cap, dtype=np.int32)
+        w = np.empty(cap)
+        nnz = lib().ctph_planner_graph(self.h, _p(nodes), _p(row_ptr), _p(col), _p(w), C.c_int64(cap))
+        assert nnz >= 0
+        return nodes, row_ptr, col[:nnz], w[:nnz]
+
+    def shortest(self, cap=4096):
+        ids = np.empty(cap, dtype=np.int32)
+        length = C.c_double(0)
+        cnt = lib().ctph_planner_shortest(self.h, _p(ids), cap, C.byref(length))
+        return ids[:min(cnt, cap)].copy(), length.value
+
+
+def shorten_path(pts, length, forward, cap=512):
+    pts = _f(pts).reshape(-1, 3)
+    out = np.empty((cap, 3))
+    out_len = C.c_double(0)
+    n = lib().ctph_shorten_path(_p(pts), len(pts), C.c_double(length), int(forward), _p(out), cap, C.byref(out_len))
+    return out[:n].copy(), out_len.value
+
+
+def remove_equivalent(paths, lengths):
+    off = np.zeros(len(paths) + 1, dtype=np.int32)
+    for i, p in enumerate(paths):
+        off[i + 1] = off[i] + len(p)
+    pts = _f(np.concatenate([np.asarray(p).reshape(-1, 3) for p in paths]))
+    lengths = _f(lengths)
+    keep = np.empty(len(paths), dtype=np.int32)
+    n = lib().ctph_remove_equivalent(_p(pts), _p(off), _p(lengths), len(paths), _p(keep))
+    return keep[:n].copy()
+
+
+def remove_too_long(lengths):
+    lengths = _f(lengths)
+    keep = np.empty(len(lengths), dtype=np.int32)
+    n = lib().ctph_remove_too_long(_p(lengths), len(lengths), _p(keep))
+    return keep[:n].copy()

@@ -1,0 +1,76 @@
+// topological_prm_clustering.hpp -- the accelerated stages of the reference's
+// TopologicalPRMClustering<T> (include/topological_prm_clustering.hpp) behind the same method
+// names: sampleMultiple (:288-401), findShortestPath (:2172), shorten_path (:2313-2479),
+// removeTooLongPaths (:2193-2222), removeEquivalentPaths (:2237-2298), the roadmap CSV writers
+// (:2066-2150) and the static entry point find_geometrical_paths (:2489-2684).  The cluster stage
+// between Dijkstra and shortening (clusterGraph, wavefrontFill, addCentroid, cluster DFS -- host
+// glue) is not re-implemented here: find_geometrical_paths calls the hook
+// `cluster_stage` where the reference calls clusterGraph() (:2591); by default the hook returns the
+// shortest path only.  INTEGRATION.md shows how the reference's own clusterGraph plugs in.
+#pragma once
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "base_map.hpp"
+#include "common.hpp"
+#include "dijkstra.hpp"
+
+#define PRECISION (1E-4)  // reference :27
+
+template <class T> class TopologicalPRMClustering {
+ public:
+  TopologicalPRMClustering(const YAML::Node &planner_config, std::shared_ptr<BaseMap> map, std::string output_folder,
+                           T start, T end, double start_yaw_deg = NAN, double end_yaw_deg = NAN);
+  void sampleMultiple(const int num_samples);
+  void setBorders(Vector<3> min_position, Vector<3> max_position);
+  void saveRoadmapDense(std::string filename);
+  static void savePath(std::string filename, std::vector<HeapNode<T> *> path);
+  static void savePathSamples(std::string filename, std::vector<T> path);
+  static path_with_length<T> shorten_path(path_with_length<T> path, bool forward = true);
+  // batched form: all paths in one launch (one CTA per polyline)
+  static std::vector<path_with_length<T>> shorten_paths(const std::vector<path_with_length<T>> &paths, bool forward = true);
+  static std::vector<path_with_length<T>> removeTooLongPaths(std::vector<path_with_length<T>> paths);
+  static std::vector<path_with_length<T>> removeEquivalentPaths(std::vector<path_with_length<T>> paths);
+  std::vector<path_with_length<T>> findShortestPath();
+  static std::vector<Vector<3>> samplePath(std::vector<HeapNode<Vector<3>> *> path, const double length_tot,
+                                           const double num_samples);
+  static std::vector<std::vector<path_with_length<Vector<3>>>> find_geometrical_paths(
+      const YAML::Node &planner_config, std::shared_ptr<BaseMap> map, std::vector<Vector<3>> &gates_with_start_end_poses,
+      std::string output_folder);
+  double getEllipseRatioMajorAxis() { return ellipse_ratio_major_axis_focal_length_; }
+  void setEllipseRatioMajorAxis(const double r) { ellipse_ratio_major_axis_focal_length_ = r; }
+
+  // ---- additions of the accelerated build ----
+  const std::vector<HeapNode<T> *> &nodes() const { return nodes_; }
+  // candidate stream for the next sampleMultiple (draw order of fillRandomStateInEllipse); when unset
+  // the candidates are generated on the device from `sampling_seed`
+  void setCandidateStream(const std::vector<Vector<3>> &cand) { candidate_stream_ = cand; }
+  static uint64_t sampling_seed;
+  // where the reference runs clusterGraph(); receives the planner after Dijkstra and returns the
+  // candidate paths to shorten and filter
+  static std::function<std::vector<path_with_length<T>>(TopologicalPRMClustering<T> &, const path_with_length<T> &)>
+      cluster_stage;
+  static constexpr int num_nn = 14;  // reference :291 (13 neighbours + self)
+
+ private:
+  std::vector<HeapNode<T> *> nodes_;
+  std::vector<Vector<3>> candidate_stream_;
+  int num_clusters_, max_clusters_, min_clusters_;
+  double min_ratio_;
+  double max_path_length_ratio_;
+  double max_path_length_ = 0;
+  static std::shared_ptr<BaseMap> map_;
+  static std::string output_folder_;
+  static double collision_distance_check_;
+  static double min_clearance_;
+  static double cutoof_distance_ratio_to_shortest_;
+  static double min_allowed;
+  double ellipse_ratio_major_axis_focal_length_;
+  HeapNode<T> *start_;
+  HeapNode<T> *end_;
+  bool planar_;
+  Vector<3> min_position_, max_position_, position_range_;
+  Dijkstra<T> dijkstra;
+};

@@ -1,0 +1,211 @@
+"""The C++ class surface (include/ctopprm/*.hpp: ESDFMap, BaseMap, TopologicalPRMClustering) on top of the
+C ABI.  CPU part: the library loads, exports its entry points, and the YAML subset reader handles the
+planner's schema.  GPU part: the classes give the reference's results (golden vectors from the
+reference's own code, and the oracle)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from ctopprm_learn_b200 import hostlib, synth
+
+CLR, CDC = synth.MIN_CLEARANCE, synth.COLLISION_DISTANCE_CHECK
+
+
+def test_host_library_loads_and_exports():
+    L = hostlib.lib()
+    for name in ("ctph_map_load", "ctph_get_clearence", "ctph_edge_nodes", "ctph_deformable", "ctph_sample_path",
+                 "ctph_planner_new", "ctph_planner_sample_multiple", "ctph_planner_graph", "ctph_shorten_path",
+                 "ctph_remove_equivalent", "ctph_find_geometrical_paths"):
+        assert hasattr(L, name)
+
+
+def test_yaml_subset_reader():
+    y = hostlib.DEFAULT_YAML.format(map="maps/x.npy", clr=0.2, cdc=0.05, planar="false", n=1000, s=[1.0, 2.5, -3.0],
+                                    g=[4, 5, 6])
+    assert hostlib.yaml_get(y, "min_clearance") == "0.2"
+    assert hostlib.yaml_get(y, "map") == "maps/x.npy"
+    assert hostlib.yaml_get(y, "start.position") == "[1.0, 2.5, -3.0]"
+    assert hostlib.yaml_get(y, "end.position") == "[4, 5, 6]"
+    assert hostlib.yaml_get(y, "cutoof_distance_ratio_to_shortest") == "1.3"
+    assert hostlib.yaml_get(y, "nope") is None and hostlib.yaml_get(y, "start.nope") is None
+    assert hostlib.yaml_get("a: 1 # comment\nb:\n  c:\n    d: 'q'\ne: 2\n", "b.c.d") == "'q'"
+
+
+def test_missing_map_file_is_reported():
+    with pytest.raises(RuntimeError):
+        hostlib.HostMap("/nonexistent/map.npy")
+
+
+@pytest.fixture(scope="module")
+def gold_host(golden):
+    fn = tempfile.mktemp(suffix=".npy")
+    synth.write_map(fn, golden["vox"], golden["centroid"], golden["extents"])
+    m = hostlib.HostMap(fn)
+    yield m
+    m.close()
+    os.unlink(fn)
+
+
+@pytest.mark.gpu
+def test_esdf_map_scalar_surface(golden, gold_host):
+    m = gold_host
+    lo, hi = m.min_max()
+    assert np.array_equal(lo, golden["min_pos"]) and np.array_equal(hi, golden["max_pos"])
+    for i in list(range(0, 4000, 97)) + list(range(4000, 4068)):
+        p = golden["pts"][i]
+        got = m.get_clearence(p)
+        want = golden["clearance"][i]
+        assert (np.isnan(got) and np.isnan(want)) or got == want
+        assert m.in_collision(p, CLR) == bool(golden["in_collision"][i])
+    for i in range(0, 1500, 61):
+        g, c = m.gradient(golden["pts"][i])
+        assert np.array_equal(g, golden["grad"][i], equal_nan=True) and np.array_equal(c, golden["centre"][i], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_base_map_segment_surface(golden, gold_host):
+    m = gold_host
+    for i in list(range(12)) + list(range(12, 3000, 59)):
+        fr, hit = m.edge_nodes(golden["a"][i], golden["b"][i], CLR, CDC)
+        assert fr == bool(golden["free_nodes"][i])
+        assert np.array_equal(hit, golden["hit"][i], equal_nan=True)
+        assert m.edge_guards(golden["a"][i], golden["b"][i], CLR, CDC) == bool(golden["free_guards"][i])
+
+
+def _split(g, key_pts, key_off):
+    off = g[key_off]
+    return [g[key_pts][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+@pytest.mark.gpu
+def test_base_map_polyline_surface(golden, gold_host):
+    m = gold_host
+    polys = _split(golden, "poly_pts", "poly_off")
+    lens, nums = golden["poly_len"], golden["poly_num"]
+    pos = 0
+    for p, L, k in zip(polys, lens, nums):
+        assert np.array_equal(m.sample_path(p, L, k), golden["sampled"][pos:pos + int(k)])
+        pos += int(k)
+    for i, j, want in zip(golden["pair_i"], golden["pair_j"], golden["deformable"]):
+        k = float(np.ceil(max(lens[i], lens[j]) / CDC) + 1)
+        assert m.deformable(polys[i], lens[i], polys[j], lens[j], k, 0.02, CDC) == want
+    q = golden["quad"]
+    assert m.deformable_between(q[0], q[1], q[2], q[3], -10.0, CDC) == golden["deformable_between"][0]
+    assert m.deformable_between(q[0], q[1], q[2], q[3], CLR, CDC) == golden["deformable_between"][1]
+    for p, want, hit in zip(polys, golden["path_free"], golden["path_free_hit"]):
+        r, h = m.path_collision_free(p, CLR, CDC)
+        assert r == bool(want) and np.array_equal(h, hit, equal_nan=True)
+
+
+@pytest.fixture(scope="module")
+def c1_host(orc, c1_map):
+    vox, c, e = c1_map
+    fn = tempfile.mktemp(suffix=".npy")
+    synth.write_map(fn, vox, c, e)
+    m = hostlib.HostMap(fn)
+    yield m, orc.OracleMap(vox, c, e), c, e, fn
+    m.close()
+    os.unlink(fn)
+
+
+def _yaml(fn, n, s, g, planar=False):
+    return hostlib.DEFAULT_YAML.format(map=fn, clr=CLR, cdc=CDC, planar="true" if planar else "false", n=n, s=list(s), g=list(g))
+
+
+@pytest.mark.gpu
+def test_planner_sample_multiple_from_shared_sample_file(c1_host, orc):
+    m, om, c, e, fn = c1_host
+    n = 1200
+    s, g = synth.default_query(c, e)
+    cand = synth.ellipsoid_candidates(s, g, 5 * n, 17)
+    pl = hostlib.HostPlanner(m, _yaml(fn, n, s, g), s, g)
+    pl.set_candidates(cand)
+    pl.sample_multiple(n)
+    nodes, row_ptr, col, w = pl.graph()
+    want_nodes = om.sample_reject(s, g, cand, CLR, n)[0]
+    assert np.array_equal(nodes, want_nodes)
+    want = om.build_prm(want_nodes, CLR, CDC, nthreads=8)
+    assert np.array_equal(row_ptr, want["row_ptr"]) and np.array_equal(col, want["col"]) and np.array_equal(w, want["w"])
+    ids, length = pl.shortest()
+    assert ids[0] == 0 and ids[-1] == 1
+    # Dijkstra over the re-materialised HeapNode graph: same length as over the oracle's CSR
+    import heapq
+    dist = np.full(n, np.inf)
+    dist[0] = 0
+    pq = [(0.0, 0)]
+    while pq:
+        d, u = heapq.heappop(pq)
+        if d > dist[u]:
+            continue
+        for t in range(want["row_ptr"][u], want["row_ptr"][u + 1]):
+            v = want["col"][t]
+            if d + want["w"][t] < dist[v]:
+                dist[v] = d + want["w"][t]
+                heapq.heappush(pq, (dist[v], v))
+    assert abs(length - dist[1]) <= 1e-5 * dist[1]
+    # shorten_path through the class (static, uses the planner's statics) against the oracle
+    path = nodes[ids]
+    plen = orc.path_length(path)
+    for forward in (True, False):
+        got_pts, got_len = hostlib.shorten_path(path, plen, forward)
+        w_pts, _, w_len, w_st, _ = om.shorten_path(path, plen, forward, CLR, CDC, cap=512)
+        assert np.array_equal(got_pts, w_pts) and (got_len == w_len or w_st == 1)
+    pl.close()
+
+
+@pytest.mark.gpu
+def test_planner_device_sampling_and_entry_point(c1_host):
+    m, om, c, e, fn = c1_host
+    n = 800
+    s, g = synth.default_query(c, e)
+    pl = hostlib.HostPlanner(m, _yaml(fn, n, s, g), s, g)
+    pl.sample_multiple(n)  # candidates generated on the device (seeded Philox)
+    nodes, row_ptr, col, w = pl.graph()
+    assert np.array_equal(nodes[0], s) and np.array_equal(nodes[1], g)
+    clear = om.clearance(nodes[2:])
+    assert (clear >= CLR).all()  # every sampled node passed the rejection test
+    want = om.build_prm(nodes, CLR, CDC, nthreads=8)
+    assert np.array_equal(col, want["col"]) and np.array_equal(w, want["w"])
+    pl.close()
+    with tempfile.TemporaryDirectory() as d:
+        lens = m.find_geometrical_paths(_yaml(fn, n, s, g), s, g, d + "/")
+        assert len(lens) >= 1 and np.isfinite(lens).all() and lens[0] >= np.linalg.norm(g - s) - 1e-9
+        rows = open(os.path.join(d, "roadmap_all0.csv")).read().strip().split("\n")
+        assert len(rows[0].split(",")) == 3 and len(rows[-1].split(",")) == 6  # nodes then edges
+        assert sum(1 for r in rows if len(r.split(",")) == 3) == n
+
+
+@pytest.mark.gpu
+def test_remove_equivalent_and_too_long(c1_host, orc):
+    m, om, c, e, fn = c1_host
+    s, g = synth.default_query(c, e)
+    pl = hostlib.HostPlanner(m, _yaml(fn, 100, s, g), s, g)  # sets the planner statics (clearance, cdc, map)
+    rng = np.random.default_rng(4)
+    base = np.stack([s + (g - s) * t for t in np.linspace(0, 1, 6)])
+    paths = []
+    for i in range(6):
+        p = base.copy()
+        p[1:-1] += rng.standard_normal((4, 3)) * (0.05 if i < 3 else 1.5)
+        paths.append(p)
+    lens = [orc.path_length(p) for p in paths]
+    got = hostlib.remove_equivalent(paths, lens)
+    want = om.remove_equivalent(paths, lens, CLR, CDC)
+    assert np.array_equal(got, want)
+    keep = hostlib.remove_too_long([1.0, 1.2, 1.31, 5.0, 1.29])
+    assert list(keep) == [0, 1, 4]
+    pl.close()
+
+
+@pytest.mark.gpu
+def test_fill_random_state_in_ellipse(c1_host):
+    m, om, c, e, fn = c1_host
+    s, g = synth.default_query(c, e)
+    a = m.fill_random_state_in_ellipse(s, g, 1.2, False, 99, 300)
+    b = m.fill_random_state_in_ellipse(s, g, 1.2, False, 99, 300)
+    assert np.array_equal(a, b) and len(np.unique(a, axis=0)) == 300
+    two_major = 1.2 * np.linalg.norm(g - s)
+    assert (np.linalg.norm(a - s, axis=1) + np.linalg.norm(a - g, axis=1) <= two_major * (1 + 1e-12)).all()
+    p = m.fill_random_state_in_ellipse(s, g, 1.2, True, 5, 10)
+    assert (p[:, 2] == s[2]).all()
