@@ -69,6 +69,8 @@ _SIGS = {
     "ctp_knn_dev": [_P, _P, _I64, _I64, _I, _P, _P, _P],
     "ctp_build_prm": [_P, _P, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
     "ctp_build_prm_dev": [_P, _P, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P, _P],
+    "ctp_csr_from_directed": [_P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _I64, _P],
+    "ctp_csr_from_directed_dev": [_P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _I64, _P, _P],
     "ctp_sample_multiple": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
     "ctp_sample_path": [_P, _P, _P, _P, _P, _I64, _P, _P, _P],
     "ctp_deformable": [_P, _P, _P, _P, _I64, _P, _P, _P, _I64, _D, _D, _P],
@@ -331,6 +333,24 @@ class DeviceMap:
                                    _ptr(col), _ptr(w), cap, _ptr(off)))
         nnz = int(off[q])
         return dict(nbr=nbr, directed_free=dfree.astype(bool), row_ptr=row_ptr, col=col[:nnz], w=w[:nnz], nnz_off=off)
+
+    def csr_from_directed(self, nodes, nbr, directed_free):
+        nodes = _np(nodes, np.float64)
+        if nodes.ndim == 2:
+            nodes = nodes[None]
+        q, n, _ = nodes.shape
+        nbr = _np(nbr, np.int32).reshape(q, n, -1)
+        k = nbr.shape[2]
+        fr = _np(directed_free, np.uint8).reshape(q, n, k)
+        cap = 2 * q * n * k
+        row_ptr = np.empty((q, n + 1), dtype=np.int32)
+        col = np.empty(cap, dtype=np.int32)
+        w = np.empty(cap)
+        off = np.empty(q + 1, dtype=np.int64)
+        _check(lib().ctp_csr_from_directed(self._h, _ptr(nodes), q, n, k, _ptr(nbr), _ptr(fr), _ptr(row_ptr), _ptr(col),
+                                           _ptr(w), cap, _ptr(off)))
+        nnz = int(off[q])
+        return dict(row_ptr=row_ptr, col=col[:nnz], w=w[:nnz], nnz_off=off)
 
     def sample_multiple(self, start, goal, cand, n, clr, cdc, k=13, out=None):
         """TopologicalPRMClustering::sampleMultiple from host candidates to host CSR."""

@@ -899,6 +899,32 @@ extern "C" int ctp_knn(ctp_map *m, const double *nodes, int64_t q, int64_t n, in
 }
 
 // ------------------------------------- PRM build -------------------------------------------
+// symmetric union of the free directed edges -> CSR (:374-385); rec holds the neighbour ids
+static int csr_emit(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *d_rec, const uint8_t *d_free,
+                    uint8_t *d_flag, int32_t *d_deg, int64_t *d_nnz, int32_t *row_ptr, int32_t *col, double *w,
+                    int64_t cap, int64_t *nnz_off, cudaStream_t st) {
+  const int64_t rows = q * n, edges = rows * k;
+  const int ns = csr_ns(k);
+  StageSpan span(m, CTP_STAGE_CSR, st);
+  const int eb = (int)((edges + 255) / 256), rb = (int)((rows + 255) / 256);
+  k_csr_rowmask<<<rb, 256, 0, st>>>(d_free, k, ns, rows, d_rec, d_deg);
+  m->launches++;
+  if (ns == 16) k_csr_degree<16><<<eb, 256, 0, st>>>(d_rec, d_free, n, k, edges, d_flag, d_deg);
+  else k_csr_degree<32><<<eb, 256, 0, st>>>(d_rec, d_free, n, k, edges, d_flag, d_deg);
+  m->launches++;
+  k_csr_rowptr<<<(unsigned)q, 1024, 0, st>>>(d_deg, n, row_ptr, d_nnz);
+  m->launches++;
+  k_csr_query_offsets<<<1, 1024, 0, st>>>(d_nnz, q, nnz_off);
+  m->launches++;
+  if (ns == 16) k_csr_fill<16><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
+  else k_csr_fill<32><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
+  m->launches++;
+  k_csr_finish<<<rb, 256, 0, st>>>(nodes, n, rows, row_ptr, nnz_off, cap, col, w);
+  m->launches++;
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
 extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, double clr,
                                  double cdc, int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr, int32_t *col,
                                  double *w, int64_t cap, int64_t *nnz_off, void *stream) {
@@ -931,24 +957,9 @@ extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int
     StageSpan span(m, CTP_STAGE_EDGES, st);
     CKR(launch_edges(m, m->prm_group, S, edges, clr, cdc, 0, O, st));
   }
-  StageSpan span(m, CTP_STAGE_CSR, st);
-  const int eb = (int)((edges + 255) / 256), rb = (int)((rows + 255) / 256);
-  k_csr_rowmask<<<rb, 256, 0, st>>>(d_free, k, ns, rows, d_rec, d_deg);
-  m->launches++;
-  if (ns == 16) k_csr_degree<16><<<eb, 256, 0, st>>>(d_rec, d_free, n, k, edges, d_flag, d_deg);
-  else k_csr_degree<32><<<eb, 256, 0, st>>>(d_rec, d_free, n, k, edges, d_flag, d_deg);
-  m->launches++;
-  k_csr_rowptr<<<(unsigned)q, 1024, 0, st>>>(d_deg, n, row_ptr, d_nnz);
-  m->launches++;
-  k_csr_query_offsets<<<1, 1024, 0, st>>>(d_nnz, q, nnz_off);
-  m->launches++;
-  if (ns == 16) k_csr_fill<16><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
-  else k_csr_fill<32><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
-  m->launches++;
-  k_csr_finish<<<rb, 256, 0, st>>>(nodes, n, rows, row_ptr, nnz_off, cap, col, w);
-  m->launches++;
+  CKR(csr_emit(m, nodes, q, n, k, d_rec, d_free, d_flag, d_deg, d_nnz, row_ptr, col, w, cap, nnz_off, st));
   if (nbr) {
-    k_rec_to_nbr<<<eb, 256, 0, st>>>(d_rec, ns, k, edges, nbr);
+    k_rec_to_nbr<<<(int)((edges + 255) / 256), 256, 0, st>>>(d_rec, ns, k, edges, nbr);
     m->launches++;
   }
   CK(cudaGetLastError());
@@ -996,6 +1007,57 @@ extern "C" int ctp_build_prm(ctp_map *m, const double *nodes, int64_t q, int64_t
   CKR(ctp_build_prm_dev(m, d_n, q, n, k, clr, cdc, d_nbr, d_free, d_rp, d_col, d_w, dcap, d_off, 0));
   return build_prm_host_tail(m, q, n, k, nbr, directed_free, row_ptr, col, w, cap, nnz_off, d_nbr, d_free, d_rp,
                              d_col, d_w, d_off);
+}
+
+// CSR from a given k-NN table and its directed verdicts (the merge step when the n*k checks were
+// sharded over several GPUs): same symmetric-union rule as ctp_build_prm
+extern "C" int ctp_csr_from_directed_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, const int32_t *nbr,
+                                         const uint8_t *directed_free, int32_t *row_ptr, int32_t *col, double *w,
+                                         int64_t cap, int64_t *nnz_off, void *stream) {
+  REQUIRE(m && q >= 1 && n >= 2 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument (k must be in [1,16])");
+  REQUIRE(nodes && nbr && directed_free && row_ptr && col && w && nnz_off && cap >= 0, "null buffer");
+  REQUIRE(q * n * k < ((int64_t)1 << 31), "q*n*k must fit in int32");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t keep = m->ws.used;
+  CKR(arena_reserve(m->ws, keep + ws_bytes_prm(q, n, k) + 8192));
+  const int64_t rows = q * n, edges = rows * k;
+  const int ns = csr_ns(k);
+  int32_t *d_rec = arena_take<int32_t>(m->ws, rows * ns);
+  uint8_t *d_flag = arena_take<uint8_t>(m->ws, edges);
+  int32_t *d_deg = arena_take<int32_t>(m->ws, rows);
+  int64_t *d_nnz = arena_take<int64_t>(m->ws, q);
+  m->ws.used = keep;
+  k_nbr_to_rec<<<(int)((edges + 255) / 256), 256, 0, st>>>(nbr, ns, k, edges, d_rec);
+  m->launches++;
+  return csr_emit(m, nodes, q, n, k, d_rec, directed_free, d_flag, d_deg, d_nnz, row_ptr, col, w, cap, nnz_off, st);
+}
+
+extern "C" int ctp_csr_from_directed(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, const int32_t *nbr,
+                                     const uint8_t *directed_free, int32_t *row_ptr, int32_t *col, double *w, int64_t cap,
+                                     int64_t *nnz_off) {
+  REQUIRE(m && q >= 1 && n >= 2 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument (k must be in [1,16])");
+  REQUIRE(nodes && nbr && directed_free && row_ptr && col && w && nnz_off, "null buffer");
+  CK(cudaSetDevice(m->device));
+  const int64_t edges = q * n * k, dcap = 2 * edges;
+  for (int64_t i = 0; i < edges; i++) REQUIRE(nbr[i] < n, "neighbour index out of range");
+  CKR(arena_reserve(m->io, align_up(q * n * 24) + align_up(edges * 4) + align_up(edges) + align_up(q * (n + 1) * 4) +
+                               align_up(dcap * 4) + align_up(dcap * 8) + align_up((q + 1) * 8)));
+  IoScope sc(m);
+  double *d_n = arena_take<double>(m->io, q * n * 3);
+  int32_t *d_nbr = arena_take<int32_t>(m->io, edges);
+  uint8_t *d_free = arena_take<uint8_t>(m->io, edges);
+  int32_t *d_rp = arena_take<int32_t>(m->io, q * (n + 1));
+  int32_t *d_col = arena_take<int32_t>(m->io, dcap);
+  double *d_w = arena_take<double>(m->io, dcap);
+  int64_t *d_off = arena_take<int64_t>(m->io, q + 1);
+  CK(cudaMemcpyAsync(d_n, nodes, q * n * 24, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_nbr, nbr, edges * 4, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_free, directed_free, edges, cudaMemcpyHostToDevice, 0));
+  m->ws.used = 0;
+  CKR(ctp_csr_from_directed_dev(m, d_n, q, n, k, d_nbr, d_free, d_rp, d_col, d_w, dcap, d_off, 0));
+  return build_prm_host_tail(m, q, n, k, nullptr, nullptr, row_ptr, col, w, cap, nnz_off, nullptr, nullptr, d_rp, d_col,
+                             d_w, d_off);
 }
 
 // Host candidate streams -> host CSRs.  The q queries are cut into chunks that flow through

@@ -799,6 +799,15 @@ __global__ void __launch_bounds__(256) k_csr_finish(const double *__restrict__ n
   }
 }
 
+// dense k-NN table (stride k) -> neighbour records (stride NS)
+__global__ void __launch_bounds__(256) k_nbr_to_rec(const int32_t *__restrict__ nbr, int ns, int k, int64_t total_edges,
+                                                    int32_t *__restrict__ rec) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= total_edges) return;
+  const int64_t row = e / k;
+  rec[row * ns + (e - row * k)] = nbr[e];
+}
+
 // neighbour records (stride NS) -> dense user-visible k-NN table (stride k)
 __global__ void __launch_bounds__(256) k_rec_to_nbr(const int32_t *__restrict__ rec, int ns, int k, int64_t total_edges,
                                                     int32_t *__restrict__ nbr) {

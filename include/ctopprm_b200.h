@@ -186,6 +186,15 @@ int ctp_build_prm_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, i
                       double clr, double cdc, int32_t *nbr, uint8_t *directed_free,
                       int32_t *row_ptr, int32_t *col, double *w, int64_t cap, int64_t *nnz_off,
                       void *stream);
+/* the merge step when the n*k directed checks were sharded (several GPUs each checking a range of
+ * source rows with ctp_edge_check_indexed): CSR from a given k-NN table nbr (q x n x k, -1 = no
+ * neighbour) and its verdicts directed_free (q x n x k), same symmetric-union rule (:374-385). */
+int ctp_csr_from_directed(ctp_map *map, const double *nodes, int64_t q, int64_t n, int k,
+                          const int32_t *nbr, const uint8_t *directed_free, int32_t *row_ptr,
+                          int32_t *col, double *w, int64_t cap, int64_t *nnz_off);
+int ctp_csr_from_directed_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, int k,
+                              const int32_t *nbr, const uint8_t *directed_free, int32_t *row_ptr,
+                              int32_t *col, double *w, int64_t cap, int64_t *nnz_off, void *stream);
 /* whole sampleMultiple from host candidate streams to host CSRs in one call (the
  * end-to-end path bench.py times): ctp_sample_reject + ctp_build_prm without the
  * intermediate host round trip.  nodes (q x n x 3) is also returned.  The queries are cut

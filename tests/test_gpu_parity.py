@@ -395,3 +395,35 @@ def test_sample_ellipsoid_seeded(c1):
         assert abs(var - (two_major / 2) ** 2 / 5) < 0.05 * (two_major / 2) ** 2
     pl = m.sample_ellipsoid(s, g, 100, 1.2, True, 1)
     assert (pl[..., 2] == s[:, None, 2]).all()
+
+
+def test_csr_from_directed(c1):
+    m, om, c, e = c1
+    s, g, cand = _queries(c, e, 2, 500, 91)
+    nodes = m.sample_reject(s, g, cand, CLR, 500)[0]
+    full = m.build_prm(nodes, CLR, CDC)
+    got = m.csr_from_directed(nodes, full["nbr"], full["directed_free"])
+    assert np.array_equal(got["row_ptr"], full["row_ptr"]) and np.array_equal(got["col"], full["col"])
+    assert np.array_equal(got["w"], full["w"]) and np.array_equal(got["nnz_off"], full["nnz_off"])
+
+
+def test_sharded_single_query_device_backend(c1):
+    """sharded.sample_multiple_sharded with the product backend (one rank; 2-rank logic: tests/test_sharded_gloo.py)"""
+    import torch.distributed as dist
+    from ctopprm_learn_b200 import sharded
+    m, om, c, e = c1
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29617")
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        n = 900
+        s, g = synth.default_query(c, e)
+        cand = synth.ellipsoid_candidates(s, g, 5 * n, 13)
+        out = sharded.sample_multiple_sharded(sharded.DeviceBackend(m), s, g, cand, n, CLR, CDC)
+    finally:
+        dist.destroy_process_group()
+    want_nodes = om.sample_reject(s, g, cand, CLR, n)[0]
+    want = om.build_prm(want_nodes, CLR, CDC, nthreads=8)
+    assert np.array_equal(out["nodes"], want_nodes) and np.array_equal(out["directed_free"], want["directed_free"])
+    assert np.array_equal(out["row_ptr"], want["row_ptr"]) and np.array_equal(out["col"], want["col"])
+    assert np.array_equal(out["w"], want["w"])
