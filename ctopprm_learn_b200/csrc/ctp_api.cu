@@ -66,7 +66,7 @@ struct ctp_map {
   size_t map_bytes = 0;
   // stage profiling (ctp_profile): pairs of events recorded on the caller's stream
   double knn_per_cell = 22.0;  // expected points inside a ball of one cell size (see k_knn_setup)
-  int knn_tile = 1;           // 1 = tile kernel + ring-search fallback, 0 = ring search only
+  int knn_tile = 3;           // 3 = direct, 2 = cell, 1 = tile kernel (all + ring-search fallback), 0 = ring search only
   unsigned long long launches = 0;  // kernels enqueued by this handle (ctp_launch_counter_read)
   int prm_group = 1;  // ctp_build_prm: 1 = flat lookup-parallel kernel (kNN edges are ~3-12 samples long)
   // chunk pipeline of the host-pointer ctp_sample_multiple
@@ -333,7 +333,7 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
       m->knn_per_cell = value;
       return CTP_OK;
     case CTP_TUNE_KNN_TILE:
-      m->knn_tile = value != 0.0;
+      m->knn_tile = (int)value;
       return CTP_OK;
     case CTP_TUNE_PIPE_CHUNK:
       REQUIRE(value >= 0 && value <= 65535, "queries per chunk must be in [0, 65535]");
@@ -832,8 +832,16 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
     const int lblocks = m->sm_count * 8;
 #define KNN_CASE(K)                                                                                               \
   case K:                                                                                                         \
-    k_knn_tile<K><<<tgrid, CTP_KNN_TILE_THREADS, 0, st>>>(d_sorted, n, d_grid, mc, d_start, idx, idx_stride, d2,  \
-                                                          d_fb, d_fbn);                                           \
+    if (m->knn_tile == 3)                                                                                         \
+      k_knn_direct<K><<<(int)((total + CTP_KNN_DIRECT_THREADS - 1) / CTP_KNN_DIRECT_THREADS),                     \
+                        CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, idx_stride, \
+                                                         d2, d_fb, d_fbn);                                        \
+    else if (m->knn_tile == 2)                                                                                    \
+      k_knn_cell<K><<<tgrid, 32 * CTP_KNN_CELL_WARPS, 0, st>>>(d_sorted, n, d_grid, mc, d_start, idx, idx_stride, \
+                                                               d2, d_fb, d_fbn);                                  \
+    else                                                                                                          \
+      k_knn_tile<K><<<tgrid, CTP_KNN_TILE_THREADS, 0, st>>>(d_sorted, n, d_grid, mc, d_start, idx, idx_stride,    \
+                                                            d2, d_fb, d_fbn);                                     \
     k_knn_search_list<K><<<lblocks, 128, 0, st>>>(d_sorted, n, d_fb, d_fbn, d_grid, mc, d_start, idx, idx_stride, \
                                                   d2);                                                            \
     m->launches += 2;                                                                                             \

@@ -573,6 +573,305 @@ k_knn_tile(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restri
   }
 }
 
+// ---- direct search: one thread per cell-sorted point, survivors in shared-memory columns ---------
+// Thread t owns sorted point t (neighbouring threads sit in the same or adjacent cells, so their
+// candidate reads hit the same L1 lines).  It scans the nine runs of its 27 cells straight from
+// memory and appends every candidate with d2 < (0.999 h)^2 branch-free to its own column of (d2, index)
+// keys in shared memory; the top-k insertion network then runs over the ~20 survivors only.  Exact
+// whenever at least k survived; sparse points retry once over the 5 x 5 x 5 cells with radius
+// 2 * 0.999 h, and what is still short goes to the ring-search list.
+#define CTP_KNN_DIRECT_THREADS 128
+#define CTP_KNN_DIRECT_KEEP 40
+
+template <int K>
+__global__ void __launch_bounds__(CTP_KNN_DIRECT_THREADS)
+k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const KnnGrid *__restrict__ grids,
+             int cell_stride, const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
+             float *__restrict__ d2out, int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
+  __shared__ unsigned long long s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
+  const int tid = threadIdx.x;
+  const int64_t t = blockIdx.x * (int64_t)CTP_KNN_DIRECT_THREADS + tid;
+  if (t >= total) return;
+  const int64_t q = t / n;
+  const KnnGrid g = grids[q];
+  const float4 me = sorted[t];
+  const int self = __float_as_int(me.w);
+  const float4 *sq = sorted + q * n;
+  const int32_t *st = cell_start + q * (cell_stride + 1);
+  const int cx = knn_cell_1d(me.x, g.lox, g.inv_h, g.dx);
+  const int cy = knn_cell_1d(me.y, g.loy, g.inv_h, g.dy);
+  const int cz = knn_cell_1d(me.z, g.loz, g.inv_h, g.dz);
+  const float lb = (float)(g.h * 0.999);
+  float thr2 = lb * lb;  // rounding here only shifts which queries take the wider search
+  int kept = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const int R = pass + 1;  // pass 0: 3 x 3 x 3 cells, pass 1: 5 x 5 x 5 cells with twice the radius
+    kept = 0;
+    const int xa = max(cx - R, 0), xb = min(cx + R, g.dx - 1);
+    for (int z = max(cz - R, 0); z <= min(cz + R, g.dz - 1); z++) {
+      for (int y = max(cy - R, 0); y <= min(cy + R, g.dy - 1); y++) {
+        const int row = (z * g.dy + y) * g.dx;
+        const int pb = st[row + xa], pe = st[row + xb + 1];
+        for (int c = pb; c < pe; c++) {
+          const float4 o = sq[c];
+          const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+          const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+          const int j = __float_as_int(o.w);
+          const bool keep = (dd < thr2) & (j != self);
+          if (keep) s_keep[min(kept, CTP_KNN_DIRECT_KEEP - 1)][tid] = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)j;
+          kept += keep ? 1 : 0;
+        }
+      }
+    }
+    if (kept >= K || pass == 1) break;
+    // sparse: widen, but only as far as the density seen so far suggests is needed for ~2k points
+    // (kept in a ball of radius lb -> 2k in a ball of radius lb * cbrt(2k / kept)), at most 2 lb
+    const float grow = fminf(2.f, cbrtf((float)(2 * K) / (float)max(kept, 1)));
+    const float wide = grow * lb;
+    thr2 = wide * wide;
+  }
+  if (kept < K || kept > CTP_KNN_DIRECT_KEEP) {
+    fb_list[atomicAdd(fb_count, 1)] = (int32_t)t;
+    return;
+  }
+  TopK<K> best;
+  best.init();
+  for (int u = 0; u < kept; u++) {
+    const unsigned long long key = s_keep[u][tid];
+    best.push(__uint_as_float((unsigned)(key >> 32)), (int)(unsigned)key);
+  }
+  int32_t *oi = idx + (q * n + self) * idx_stride;
+#pragma unroll
+  for (int s2 = 0; s2 < K; s2++) oi[s2] = best.id[s2];
+  if (d2out) {
+    float *od = d2out + (q * n + self) * K;
+#pragma unroll
+    for (int s2 = 0; s2 < K; s2++) od[s2] = best.d[s2];
+  }
+}
+
+// ---- cell search: lanes over candidates ------------------------------------------------------
+// All points of one grid cell share the same 27-cell candidate set.  A warp takes a cell, keeps the
+// candidates (about 27 x the cell density, up to 32 * CTP_KNN_SLOTS; streamed from memory when
+// there are more) in registers, one to a few per lane, and then serves the cell's points one after
+// the other: every lane computes the exact float32 squared distance of the query to its candidates;
+// the survivors with d2 < (0.999 h)^2 -- anything nearer is guaranteed to be among the candidates,
+// anything farther cannot be ranked -- are appended as (d2, index) keys to a 64-entry buffer by
+// ballot/popc; whenever more than 32 are pending a 64-wide bitonic network keeps the k best and
+// tightens the threshold.  A final 32-wide network sorts what is left; lanes 0..k-1 then hold the
+// answer and write it with one coalesced store.  No per-thread top-k state, no divergence.
+// Fewer than k survivors (sparse borders of the point cloud): the same procedure over the
+// 5 x 5 x 5 cells with radius 2 * 0.999 h.  Only queries with fewer than k points within 2h go
+// to the ring-search list.
+#define CTP_KNN_SLOTS 8
+#define CTP_KNN_CELL_WARPS 8
+
+__device__ __forceinline__ unsigned long long knn_min64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long knn_max64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
+
+// 32 keys, one per lane, ascending over lanes
+__device__ __forceinline__ unsigned long long knn_sort32(unsigned long long key, int lane) {
+#pragma unroll
+  for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, jj);
+      const bool take_min = (((lane & kk) == 0) == ((lane & jj) == 0));
+      key = take_min ? knn_min64(other, key) : knn_max64(other, key);
+    }
+  }
+  return key;
+}
+
+// 64 keys, element e = lane (key) or lane + 32 (key2), ascending; afterwards `key` of lanes 0..31 holds
+// the 32 smallest in order
+__device__ __noinline__ unsigned long long knn_sort64_low(unsigned long long key, unsigned long long key2, int lane) {
+#pragma unroll
+  for (int kk = 2; kk <= 64; kk <<= 1) {
+#pragma unroll
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      if (jj == 32) {  // partner is the other register of the same lane (kk == 64: ascending)
+        const unsigned long long mn = knn_min64(key, key2), mx = knn_max64(key, key2);
+        key = mn;
+        key2 = mx;
+      } else {
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, key, jj), o2 = __shfl_xor_sync(0xffffffffu, key2, jj);
+        const bool lower = (lane & jj) == 0;
+        const bool up1 = (lane & kk) == 0, up2 = ((lane + 32) & kk) == 0;
+        key = (up1 == lower) ? knn_min64(o1, key) : knn_max64(o1, key);
+        key2 = (up2 == lower) ? knn_min64(o2, key2) : knn_max64(o2, key2);
+      }
+    }
+  }
+  return key;
+}
+
+// warp-wide: append the lanes' surviving (dd, j) keys; with more than 32 pending keep the K best
+template <int K>
+__device__ __forceinline__ void knn_offer(bool surv, float dd, int j, int &base, float &thr, unsigned long long *keys,
+                                          int lane, unsigned lt_mask) {
+  const unsigned b = __ballot_sync(0xffffffffu, surv);
+  if (b == 0) return;
+  const int pos = base + __popc(b & lt_mask);
+  if (surv) keys[pos] = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)j;
+  base += __popc(b);
+  if (base > 32) {
+    __syncwarp();
+    unsigned long long k1 = lane < base ? keys[lane] : 0xffffffffffffffffull;
+    unsigned long long k2 = lane + 32 < base ? keys[lane + 32] : 0xffffffffffffffffull;
+    k1 = knn_sort64_low(k1, k2, lane);
+    if (lane < K) keys[lane] = k1;
+    base = K;
+    // later candidates must beat (or tie in distance with) the current k-th
+    thr = __uint_as_float((unsigned)(__shfl_sync(0xffffffffu, k1, K - 1) >> 32));
+    __syncwarp();
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(32 * CTP_KNN_CELL_WARPS)
+k_knn_cell(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restrict__ grids, int cell_stride,
+           const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
+           float *__restrict__ d2out, int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
+  __shared__ unsigned long long s_key[CTP_KNN_CELL_WARPS][64];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned long long *keys = s_key[w];
+  const int64_t q = blockIdx.y;
+  const KnnGrid g = grids[q];
+  const int32_t *st = cell_start + q * (cell_stride + 1);
+  const float4 *sq = sorted + q * n;
+  const float lb = (float)(g.h * 0.999);
+  const float lb2 = lb * lb;  // rounding here only shifts which queries take the wider search
+  const float wide = 2.f * lb;
+  const float wide2 = wide * wide;
+  const float inf = __int_as_float(0x7f800000);
+  const int n_warps = gridDim.x * CTP_KNN_CELL_WARPS;
+  for (int cell = blockIdx.x * CTP_KNN_CELL_WARPS + w; cell < g.ncell; cell += n_warps) {
+    const int qb = st[cell], qe = st[cell + 1];
+    if (qb == qe) continue;
+    const int cx = cell % g.dx, cy = (cell / g.dx) % g.dy, cz = cell / (g.dx * g.dy);
+    // nine candidate runs (dy, dz) in [-1, 1]^2, x cells cx-1 .. cx+1; lane r < 9 fetches run r
+    int rb = 0, rlen = 0;
+    if (lane < 9) {
+      const int y = cy - 1 + lane % 3, z = cz - 1 + lane / 3;
+      if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
+        const int row = (z * g.dy + y) * g.dx;
+        rb = st[row + max(cx - 1, 0)];
+        rlen = st[row + min(cx + 1, g.dx - 1) + 1] - rb;
+      }
+    }
+    int incl = rlen;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const int t = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int n_cand = __shfl_sync(full, incl, 8);
+    const bool in_regs = n_cand <= 32 * CTP_KNN_SLOTS;
+    // candidate i of the flattened runs sits at rb[r] + (i - excl[r]); each lane takes i = lane + 32 s
+    float4 cand[CTP_KNN_SLOTS];
+    if (in_regs) {
+      const int excl = incl - rlen;
+#pragma unroll
+      for (int s = 0; s < CTP_KNN_SLOTS; s++) {
+        const int i = lane + 32 * s;
+        int r = 0;
+#pragma unroll
+        for (int t = 1; t < 9; t++) r += (i >= __shfl_sync(full, excl, t)) ? 1 : 0;
+        const int pos = __shfl_sync(full, rb, r) + (i - __shfl_sync(full, excl, r));
+        cand[s] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (i < n_cand) cand[s] = sq[pos];
+      }
+    }
+    const int n_slots = (n_cand + 31) >> 5;
+    int rb5 = 0, rlen5 = -1;  // the 25 runs of the 5 x 5 x 5 neighbourhood, fetched on first use
+    for (int p = qb; p < qe; p++) {
+      const float4 me = sq[p];
+      const int self = __float_as_int(me.w);
+      int base = 0;
+      float thr = inf;
+      if (in_regs) {
+#pragma unroll
+        for (int s = 0; s < CTP_KNN_SLOTS; s++) {
+          if (s < n_slots) {
+            const float ddx = me.x - cand[s].x, ddy = me.y - cand[s].y, ddz = me.z - cand[s].z;
+            const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+            const int j = __float_as_int(cand[s].w);
+            knn_offer<K>((dd < lb2) & (dd <= thr) & (j != self) & (j >= 0), dd, j, base, thr, keys, lane, lt_mask);
+          }
+        }
+      } else {  // unusually dense neighbourhood: stream the nine runs
+        for (int r = 0; r < 9; r++) {
+          const int b0 = __shfl_sync(full, rb, r), len = __shfl_sync(full, rlen, r);
+          for (int i0 = 0; i0 < len; i0 += 32) {
+            const int i = i0 + lane;
+            bool surv = false;
+            float dd = 0.f;
+            int j = -1;
+            if (i < len) {
+              const float4 o = sq[b0 + i];
+              const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+              dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+              j = __float_as_int(o.w);
+              surv = (dd < lb2) & (dd <= thr) & (j != self);
+            }
+            knn_offer<K>(surv, dd, j, base, thr, keys, lane, lt_mask);
+          }
+        }
+      }
+      if (base < K) {
+        // sparse neighbourhood: widen to 5 x 5 x 5 cells; everything within 2 * 0.999 h is in there
+        if (rlen5 < 0) {
+          rlen5 = 0;
+          if (lane < 25) {
+            const int y = cy - 2 + lane % 5, z = cz - 2 + lane / 5;
+            if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
+              const int row = (z * g.dy + y) * g.dx;
+              rb5 = st[row + max(cx - 2, 0)];
+              rlen5 = st[row + min(cx + 2, g.dx - 1) + 1] - rb5;
+            }
+          }
+        }
+        __syncwarp();
+        base = 0;
+        thr = inf;
+        for (int r = 0; r < 25; r++) {
+          const int b0 = __shfl_sync(full, rb5, r), len = __shfl_sync(full, rlen5, r);
+          for (int i0 = 0; i0 < len; i0 += 32) {
+            const int i = i0 + lane;
+            bool surv = false;
+            float dd = 0.f;
+            int j = -1;
+            if (i < len) {
+              const float4 o = sq[b0 + i];
+              const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+              dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+              j = __float_as_int(o.w);
+              surv = (dd < wide2) & (dd <= thr) & (j != self);
+            }
+            knn_offer<K>(surv, dd, j, base, thr, keys, lane, lt_mask);
+          }
+        }
+      }
+      if (base < K) {  // fewer than k points within 2h
+        if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + p);
+        __syncwarp();
+        continue;
+      }
+      __syncwarp();
+      unsigned long long key = lane < base ? keys[lane] : 0xffffffffffffffffull;
+      __syncwarp();  // the next query overwrites the buffer
+      key = knn_sort32(key, lane);
+      if (lane < K) {
+        idx[(q * n + self) * idx_stride + lane] = (int)(unsigned)key;
+        if (d2out) d2out[(q * n + self) * K + lane] = __uint_as_float((unsigned)(key >> 32));
+      }
+    }
+  }
+}
+
 // =========================== symmetric CSR emit (:374-385) ================================
 // {i,j} is an edge iff free(i->j) with j in kNN(i), or free(j->i) with i in kNN(j); both map
 // entries are written on success, so the adjacency is the symmetric union.
