@@ -36,7 +36,7 @@ WORKLOADS = {
     # name: (map config, nodes per query, default queries per GPU per step, candidates per node)
     "C2": ("C2", 10000, 512, 4),
     "C1": ("C1", 1000, 512, 4),
-    "C3": ("C3", 100000, 4, 4),
+    "C3": ("C3", 100000, 4, 16),
 }
 
 

@@ -117,13 +117,16 @@ template <> struct Corners<CTP_L_BRICK> {
 template <int L>
 __device__ __forceinline__ double esdf_interp(const MapDev &M, double qx, double qy, double qz) {
   const int x0 = __double2int_rd(qx), y0 = __double2int_rd(qy), z0 = __double2int_rd(qz);
-  const double fx = (double)x0, fy = (double)y0, fz = (double)z0;
-  const bool ok = (qx >= 0.0) & (qy >= 0.0) & (qz >= 0.0) & (qx <= M.nm1) & (qy <= M.nm1) &
-                  (qz <= M.nm1) & (qx != fx) & (qy != fy) & (qz != fz);
+  const double xd = qx - (double)x0, yd = qy - (double)y0, zd = qz - (double)z0;
+  // q in [0, N-1] and not integral  <=>  floor(q) in [0, N-2] and q - floor(q) > 0; a NaN q gives
+  // a NaN fraction and fails the '>' (the conversion saturates for out-of-range q, which the
+  // unsigned range test rejects)
+  const unsigned nm2 = (unsigned)(M.n - 2);
+  const bool ok = ((unsigned)x0 <= nm2) & ((unsigned)y0 <= nm2) & ((unsigned)z0 <= nm2) & (xd > 0.0) & (yd > 0.0) &
+                  (zd > 0.0);
   if (!ok) return ctp_nan();
   float v[8];
   Corners<L>::load(M, x0, y0, z0, v);
-  const double xd = qx - fx, yd = qy - fy, zd = qz - fz;
   const double omx = 1.0 - xd, omy = 1.0 - yd, omz = 1.0 - zd;
   const double c00 = omx * (double)v[0] + xd * (double)v[4];
   const double c01 = omx * (double)v[1] + xd * (double)v[5];
@@ -402,13 +405,25 @@ __global__ void __launch_bounds__(256) k_edge_march(MapDev M, EdgeSrc S, int64_t
 // records its march index with a shared-memory atomicMin, so the verdict, the first-hit index and
 // the reference-order lookup count are exactly the sequential ones.  Long edges are processed in
 // rounds of CTP_FLAT_R samples per edge; an edge stops at the first round that found a hit.
+// (double)idx / npts for the small integers of a segment march, without the division sequence:
+// with r = 1/npts correctly rounded, q0 = idx*r is within an ulp or so of the quotient, the
+// remainder idx - q0*npts is exact in one fma, and the corrected q0 + rem*r rounds to the correctly
+// rounded quotient.  Verified exhaustively for every 1 <= idx < npts <= 65536 by
+// tests/csrc/div_identity.c; longer marches take the true division.
+#define CTP_DIV_SMALL_LIMIT 65536.0
+__device__ __forceinline__ double ctp_div_small(double a, double b, double rb) {
+  if (b > CTP_DIV_SMALL_LIMIT) return a / b;
+  const double q0 = a * rb;
+  return __fma_rn(__fma_rn(-q0, b, a), rb, q0);
+}
+
 #define CTP_FLAT_R 16
 #define CTP_FLAT_WARPS 8
 
 template <int L>
 __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, EdgeSrc S, int64_t m, double clr,
                                                                    double cdc, int guards, EdgeOut O) {
-  __shared__ double s_par[CTP_FLAT_WARPS][7][32];
+  __shared__ double s_par[CTP_FLAT_WARPS][8][32];
   __shared__ int s_first[CTP_FLAT_WARPS][32];
   __shared__ int2 s_ob[CTP_FLAT_WARPS][32];
   __shared__ uint8_t s_slot[CTP_FLAT_WARPS][32 * CTP_FLAT_R];
@@ -430,6 +445,7 @@ __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, Edg
     par[0][lane] = ax; par[1][lane] = ay; par[2][lane] = az;
     par[3][lane] = vx; par[4][lane] = vy; par[5][lane] = vz;
     par[6][lane] = npts;
+    par[7][lane] = 1.0 / npts;
     first[lane] = 0x7fffffff;
     bool alive = state == 0;
     int base = 1;
@@ -451,7 +467,7 @@ __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, Edg
         const int el = slot[t];
         const int2 o2 = ob[el];
         const int idx = o2.y + (t - o2.x);
-        const double tt = (double)idx / par[6][el];  // (double)index / num_points_path
+        const double tt = ctp_div_small((double)idx, par[6][el], par[7][el]);  // (double)index / num_points_path
         const double px = par[0][el] + par[3][el] * tt;
         const double py = par[1][el] + par[4][el] * tt;
         const double pz = par[2][el] + par[5][el] * tt;

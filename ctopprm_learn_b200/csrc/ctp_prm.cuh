@@ -1064,8 +1064,10 @@ __global__ void __launch_bounds__(256) k_csr_finish(const double *__restrict__ n
   const double *nq = nodes + 3 * q * n;
   if (len <= CTP_CSR_LOCAL) {
     int32_t c[CTP_CSR_LOCAL];
-    for (int a = 0; a < len; a++) {
-      const int32_t key = col[b + a];
+#pragma unroll 8
+    for (int a = 0; a < len; a++) c[a] = col[b + a];  // independent loads first
+    for (int a = 1; a < len; a++) {
+      const int32_t key = c[a];
       int p = a - 1;
       while (p >= 0 && c[p] > key) {
         c[p + 1] = c[p];
@@ -1073,6 +1075,7 @@ __global__ void __launch_bounds__(256) k_csr_finish(const double *__restrict__ n
       }
       c[p + 1] = key;
     }
+#pragma unroll 4
     for (int a = 0; a < len; a++) {
       const int32_t cj = c[a];
       col[b + a] = cj;

@@ -427,3 +427,17 @@ def test_sharded_single_query_device_backend(c1):
     assert np.array_equal(out["nodes"], want_nodes) and np.array_equal(out["directed_free"], want["directed_free"])
     assert np.array_equal(out["row_ptr"], want["row_ptr"]) and np.array_equal(out["col"], want["col"])
     assert np.array_equal(out["w"], want["w"])
+
+
+@pytest.mark.parametrize("group", [1, 8])
+def test_very_long_marches(c1, group):
+    """more than 65536 samples per edge: beyond the range of the verified division shortcut"""
+    m, om, c, e = c1
+    m.set_layout(capi.LAYOUT_PLAIN)
+    a, b = synth.random_edges(c, e, 64, 5, lo=7.0, hi=12.0)
+    cdc = 1e-4
+    free, hit, hit_idx, lookups = m.edge_check(a, b, -5.0, cdc, group=group)  # clearance -5: nothing collides inside the map
+    f0, h0, hi0, l0, _ = om.edge_nodes(a, b, -5.0, cdc, nthreads=8)
+    assert (l0 > 65536).any()
+    assert np.array_equal(free, f0) and np.array_equal(hit, h0, equal_nan=True)
+    assert np.array_equal(hit_idx, hi0) and np.array_equal(lookups, l0)

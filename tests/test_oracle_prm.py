@@ -78,3 +78,14 @@ def test_reference_sample_multiple_equals_restatement(orc, c1_map):
     assert short["short"] == 1 and short["n_filled"][0] < n
     ref.close()
     os.unlink(fn)
+
+
+def test_division_shortcut_identity_is_exhaustively_exact(tmp_path):
+    """k_edge_flat computes idx/npts as fma(fma(-q0, npts, idx), r, q0) with r = 1/npts for npts <= 65536;
+    tests/csrc/div_identity.c checks every (idx, npts) pair against the true IEEE quotient."""
+    import subprocess
+    src = os.path.join(os.path.dirname(__file__), "csrc", "div_identity.c")
+    exe = str(tmp_path / "div_identity")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-o", exe, src, "-lm"])
+    out = subprocess.check_output([exe, "65536"]).decode().split()
+    assert int(out[0]) == 0 and int(out[1]) == 65536 * 65535 // 2 - 0
