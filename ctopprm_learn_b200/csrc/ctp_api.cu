@@ -66,7 +66,7 @@ struct ctp_map {
   size_t map_bytes = 0;
   // stage profiling (ctp_profile): pairs of events recorded on the caller's stream
   double knn_per_cell = 22.0;  // expected points inside a ball of one cell size (see k_knn_setup)
-  int knn_tile = 3;           // 3 = direct, 2 = cell, 1 = tile kernel (all + ring-search fallback), 0 = ring search only
+  int knn_tile = 3;           // 4 = cell2 (+ direct list), 3 = direct, 2 = cell, 1 = tile (all + ring-search fallback), 0 = ring only
   unsigned long long launches = 0;  // kernels enqueued by this handle (ctp_launch_counter_read)
   int prm_group = 1;  // ctp_build_prm: 1 = flat lookup-parallel kernel (kNN edges are ~3-12 samples long)
   // chunk pipeline of the host-pointer ctp_sample_multiple
@@ -691,7 +691,7 @@ static size_t ws_bytes_reject(int64_t q, int64_t m) {
 }
 static size_t ws_bytes_knn(int64_t q, int64_t n) {
   const size_t mc = (size_t)knn_max_cells(n);
-  return align_up((size_t)q * sizeof(KnnGrid)) + 2 * align_up((size_t)q * n * 16) + 2 * align_up((size_t)q * n * 4) +
+  return align_up((size_t)q * sizeof(KnnGrid)) + 2 * align_up((size_t)q * n * 16) + 3 * align_up((size_t)q * n * 4) + align_up((size_t)q * n) +
          align_up((size_t)q * mc * 4) + align_up((size_t)q * (mc + 1) * 4) + 512;
 }
 static size_t ws_bytes_prm(int64_t q, int64_t n, int k) {
@@ -810,8 +810,9 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
   int32_t *d_cell_of = arena_take<int32_t>(m->ws, total);
   int32_t *d_cnt = arena_take<int32_t>(m->ws, (size_t)q * mc);
   int32_t *d_start = arena_take<int32_t>(m->ws, (size_t)q * (mc + 1));
-  int32_t *d_fb = arena_take<int32_t>(m->ws, total);
-  int32_t *d_fbn = arena_take<int32_t>(m->ws, 1);
+  int32_t *d_fb = arena_take<int32_t>(m->ws, total), *d_fb2 = arena_take<int32_t>(m->ws, total);
+  int32_t *d_fbn = arena_take<int32_t>(m->ws, 2);  // [0] ring-search list, [1] direct-search list
+  uint8_t *d_fbk = arena_take<uint8_t>(m->ws, total);
   CK(cudaMemsetAsync(d_cnt, 0, (size_t)q * mc * 4, st));
   k_knn_setup<<<(unsigned)q, 1024, 0, st>>>(nodes, n, mc, m->knn_per_cell, d_grid, d_pts);
   m->launches++;
@@ -825,25 +826,37 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
   m->launches++;
   CK(cudaGetLastError());
   if (m->knn_tile && n > 4 * k) {
-    CK(cudaMemsetAsync(d_fbn, 0, 4, st));
+    CK(cudaMemsetAsync(d_fbn, 0, 8, st));
     // a query's tiles are shared by bpq CTAs; enough CTAs overall to fill the machine several times
     const int bpq = (int)std::max<int64_t>(8, ((int64_t)m->sm_count * 16 + q - 1) / q);
     const dim3 tgrid((unsigned)bpq, (unsigned)q);
     const int lblocks = m->sm_count * 8;
 #define KNN_CASE(K)                                                                                               \
   case K:                                                                                                         \
-    if (m->knn_tile == 3)                                                                                         \
+    if (m->knn_tile == 4) {                                                                                       \
+      k_knn_cell2<K><<<tgrid, 32 * CTP_KNN_C2_WARPS, 0, st>>>(d_sorted, n, d_grid, mc, d_start, idx, idx_stride,  \
+                                                              d2, d_fb2, d_fbn + 1);                              \
+      k_knn_direct_list<K><<<lblocks, CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, d_fb2, nullptr, d_fbn + 1, 0, \
+                                                                      d_grid, mc, d_start, idx, idx_stride, d2,   \
+                                                                      d_fb, d_fbn);                               \
+      m->launches++;                                                                                              \
+    } else if (m->knn_tile == 3) {                                                                                \
       k_knn_direct<K><<<(int)((total + CTP_KNN_DIRECT_THREADS - 1) / CTP_KNN_DIRECT_THREADS),                     \
                         CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, idx_stride, \
-                                                         d2, d_fb, d_fbn);                                        \
+                                                         d2, d_fb2, d_fbk, d_fbn + 1);                            \
+      k_knn_direct_list<K><<<lblocks, CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, d_fb2, d_fbk, d_fbn + 1, 1,   \
+                                                                      d_grid, mc, d_start, idx, idx_stride, d2,   \
+                                                                      d_fb, d_fbn);                               \
+      m->launches++;                                                                                              \
+    }                                                                                                             \
     else if (m->knn_tile == 2)                                                                                    \
       k_knn_cell<K><<<tgrid, 32 * CTP_KNN_CELL_WARPS, 0, st>>>(d_sorted, n, d_grid, mc, d_start, idx, idx_stride, \
                                                                d2, d_fb, d_fbn);                                  \
     else                                                                                                          \
       k_knn_tile<K><<<tgrid, CTP_KNN_TILE_THREADS, 0, st>>>(d_sorted, n, d_grid, mc, d_start, idx, idx_stride,    \
                                                             d2, d_fb, d_fbn);                                     \
-    k_knn_search_list<K><<<lblocks, 128, 0, st>>>(d_sorted, n, d_fb, d_fbn, d_grid, mc, d_start, idx, idx_stride, \
-                                                  d2);                                                            \
+    k_knn_ring_warp<K><<<lblocks, 32 * CTP_KNN_RW_WARPS, 0, st>>>(d_sorted, n, d_fb, d_fbn, d_grid, mc, d_start,  \
+                                                                  idx, idx_stride, d2);                          \
     m->launches += 2;                                                                                             \
     break;
     switch (k) {
@@ -852,11 +865,11 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
     }
 #undef KNN_CASE
     if (getenv("CTP_DEBUG_KNN")) {
-      int fb = 0;
-      cudaMemcpyAsync(&fb, d_fbn, 4, cudaMemcpyDeviceToHost, st);
+      int fb[2] = {0, 0};
+      cudaMemcpyAsync(fb, d_fbn, 8, cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
-      fprintf(stderr, "[ctp] knn: %lld points, %d redone by the ring search (%.2f%%)\n", (long long)total, fb,
-              100.0 * fb / (double)total);
+      fprintf(stderr, "[ctp] knn: %lld points, %d redone by the direct search (%.2f%%), %d by the ring search (%.2f%%)\n",
+              (long long)total, fb[1], 100.0 * fb[1] / (double)total, fb[0], 100.0 * fb[0] / (double)total);
     }
   } else {
     const int sblocks = (int)((total + 127) / 128);

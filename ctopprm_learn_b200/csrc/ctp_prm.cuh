@@ -583,15 +583,19 @@ k_knn_tile(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restri
 #define CTP_KNN_DIRECT_THREADS 128
 #define CTP_KNN_DIRECT_KEEP 40
 
+// Passes: 0 = the 3 x 3 x 3 cells with radius 0.999 h; 1, 2 = wider balls for sparse points, only as
+// wide as the density seen so far suggests is needed for ~2k points (kept in a ball of radius lb ->
+// 2k in a ball of radius lb * cbrt(2k / kept)), at most (pass + 1) cells.  k_knn_direct runs pass 0
+// for every point and lists the sparse ones with their survivor count; k_knn_direct_list runs the
+// wider passes for the listed points only, so dense points never wait for sparse lanes.
 template <int K>
-__global__ void __launch_bounds__(CTP_KNN_DIRECT_THREADS)
-k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const KnnGrid *__restrict__ grids,
-             int cell_stride, const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
-             float *__restrict__ d2out, int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
-  __shared__ unsigned long long s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
-  const int tid = threadIdx.x;
-  const int64_t t = blockIdx.x * (int64_t)CTP_KNN_DIRECT_THREADS + tid;
-  if (t >= total) return;
+__device__ __forceinline__ void knn_direct_point(int64_t t, int tid, unsigned long long (*s_keep)[CTP_KNN_DIRECT_THREADS],
+                                                 const float4 *__restrict__ sorted, int64_t n,
+                                                 const KnnGrid *__restrict__ grids, int cell_stride,
+                                                 const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx,
+                                                 int idx_stride, float *__restrict__ d2out, int pass_lo, int pass_hi,
+                                                 int kept_in, int32_t *__restrict__ fb_list,
+                                                 uint8_t *__restrict__ fb_kept, int32_t *__restrict__ fb_count) {
   const int64_t q = t / n;
   const KnnGrid g = grids[q];
   const float4 me = sorted[t];
@@ -601,11 +605,14 @@ k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const 
   const int cx = knn_cell_1d(me.x, g.lox, g.inv_h, g.dx);
   const int cy = knn_cell_1d(me.y, g.loy, g.inv_h, g.dy);
   const int cz = knn_cell_1d(me.z, g.loz, g.inv_h, g.dz);
-  const float lb = (float)(g.h * 0.999);
-  float thr2 = lb * lb;  // rounding here only shifts which queries take the wider search
-  int kept = 0;
-  for (int pass = 0; pass < 2; pass++) {
-    const int R = pass + 1;  // pass 0: 3 x 3 x 3 cells, pass 1: 5 x 5 x 5 cells with twice the radius
+  const float lb = (float)(g.h * 0.999);  // rounding here only shifts which points take the wider search
+  int kept = 0, kept_prev = kept_in;
+  bool done = false;
+  for (int pass = pass_lo; pass <= pass_hi; pass++) {
+    const float grow = pass == 0 ? 1.f : fminf((float)(pass + 1), cbrtf((float)(2 * K) / (float)max(kept_prev, 1)));
+    const int R = pass == 0 ? 1 : (grow > 2.f ? 3 : 2);
+    const float wide = grow * lb;
+    const float thr2 = wide * wide;
     kept = 0;
     const int xa = max(cx - R, 0), xb = min(cx + R, g.dx - 1);
     for (int z = max(cz - R, 0); z <= min(cz + R, g.dz - 1); z++) {
@@ -623,15 +630,16 @@ k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const 
         }
       }
     }
-    if (kept >= K || pass == 1) break;
-    // sparse: widen, but only as far as the density seen so far suggests is needed for ~2k points
-    // (kept in a ball of radius lb -> 2k in a ball of radius lb * cbrt(2k / kept)), at most 2 lb
-    const float grow = fminf(2.f, cbrtf((float)(2 * K) / (float)max(kept, 1)));
-    const float wide = grow * lb;
-    thr2 = wide * wide;
+    if (kept >= K) {
+      done = kept <= CTP_KNN_DIRECT_KEEP;
+      break;
+    }
+    kept_prev = kept;
   }
-  if (kept < K || kept > CTP_KNN_DIRECT_KEEP) {
-    fb_list[atomicAdd(fb_count, 1)] = (int32_t)t;
+  if (!done) {
+    const int pos = atomicAdd(fb_count, 1);
+    fb_list[pos] = (int32_t)t;
+    if (fb_kept) fb_kept[pos] = (uint8_t)min(kept, 255);
     return;
   }
   TopK<K> best;
@@ -647,6 +655,142 @@ k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const 
     float *od = d2out + (q * n + self) * K;
 #pragma unroll
     for (int s2 = 0; s2 < K; s2++) od[s2] = best.d[s2];
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(CTP_KNN_DIRECT_THREADS)
+k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const KnnGrid *__restrict__ grids,
+             int cell_stride, const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
+             float *__restrict__ d2out, int32_t *__restrict__ fb_list, uint8_t *__restrict__ fb_kept,
+             int32_t *__restrict__ fb_count) {
+  __shared__ unsigned long long s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
+  const int64_t t = blockIdx.x * (int64_t)CTP_KNN_DIRECT_THREADS + threadIdx.x;
+  if (t >= total) return;
+  knn_direct_point<K>(t, threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out, 0, 0, 0,
+                      fb_list, fb_kept, fb_count);
+}
+
+// the wider passes over a list of positions in the sorted array (kept = survivors of the pass before)
+template <int K>
+__global__ void __launch_bounds__(CTP_KNN_DIRECT_THREADS)
+k_knn_direct_list(const float4 *__restrict__ sorted, int64_t n, const int32_t *__restrict__ list,
+                  const uint8_t *__restrict__ list_kept, const int32_t *__restrict__ count, int pass_lo,
+                  const KnnGrid *__restrict__ grids, int cell_stride, const int32_t *__restrict__ cell_start,
+                  int32_t *__restrict__ idx, int idx_stride, float *__restrict__ d2out,
+                  int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
+  __shared__ unsigned long long s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
+  const int cnt = *count;
+  for (int i = blockIdx.x * CTP_KNN_DIRECT_THREADS + threadIdx.x; i < cnt; i += gridDim.x * CTP_KNN_DIRECT_THREADS)
+    knn_direct_point<K>(list[i], threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out,
+                        pass_lo, 2, list_kept ? list_kept[i] : 0, fb_list, nullptr, fb_count);
+}
+
+// ---- cell search, two-dimensional: lanes = (query of the cell) x (slice of the candidates) --------
+// All points of one grid cell share the same 27-cell candidate set.  A warp takes a cell, stages the
+// candidates in shared memory, and splits its lanes into nq groups of S = 32 / nq lanes: group qi
+// serves query qi, lane sl of the group scans candidates sl, sl + S, ...  Every lane does the exact
+// float32 distance of ITS query to ITS candidate (no divergence: all lanes run the same loop) and
+// appends survivors with d2 < (0.999 h)^2 -- anything nearer is guaranteed to be among the
+// candidates, anything farther cannot be ranked -- to the query's key list in shared memory.  The
+// group then ranks the ~20 survivors against each other ((d2, index) order) and the ones with rank
+// < k write themselves to the output row.  Exact whenever at least k survived; otherwise (sparse
+// borders, more than 32 survivors, more candidates than fit) the query goes to the list served by
+// k_knn_direct_list.
+#define CTP_KNN_C2_WARPS 4
+#define CTP_KNN_C2_CAND 240
+#define CTP_KNN_C2_KEEP 32
+
+template <int K>
+__global__ void __launch_bounds__(32 * CTP_KNN_C2_WARPS)
+k_knn_cell2(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restrict__ grids, int cell_stride,
+            const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
+            float *__restrict__ d2out, int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
+  __shared__ float4 s_cand[CTP_KNN_C2_WARPS][CTP_KNN_C2_CAND];
+  __shared__ unsigned long long s_keys[CTP_KNN_C2_WARPS][CTP_KNN_C2_KEEP][32];  // [entry][query slot]
+  __shared__ int s_cnt[CTP_KNN_C2_WARPS][32];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float4 *cand = s_cand[w];
+  unsigned long long(*keys)[32] = s_keys[w];
+  int *cnt = s_cnt[w];
+  const int64_t q = blockIdx.y;
+  const KnnGrid g = grids[q];
+  const int32_t *st = cell_start + q * (cell_stride + 1);
+  const float4 *sq = sorted + q * n;
+  const float lb = (float)(g.h * 0.999);
+  const float lb2 = lb * lb;  // rounding here only shifts which queries take the fallback
+  const int n_warps = gridDim.x * CTP_KNN_C2_WARPS;
+  for (int cell = blockIdx.x * CTP_KNN_C2_WARPS + w; cell < g.ncell; cell += n_warps) {
+    const int qb = st[cell], qe = st[cell + 1];
+    if (qb == qe) continue;
+    const int cx = cell % g.dx, cy = (cell / g.dx) % g.dy, cz = cell / (g.dx * g.dy);
+    // nine candidate runs (dy, dz) in [-1, 1]^2, x cells cx-1 .. cx+1; lane r < 9 fetches run r
+    int rb = 0, rlen = 0;
+    if (lane < 9) {
+      const int y = cy - 1 + lane % 3, z = cz - 1 + lane / 3;
+      if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
+        const int row = (z * g.dy + y) * g.dx;
+        rb = st[row + max(cx - 1, 0)];
+        rlen = st[row + min(cx + 1, g.dx - 1) + 1] - rb;
+      }
+    }
+    int incl = rlen;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const int t = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int n_cand = __shfl_sync(full, incl, 8);
+    if (n_cand > CTP_KNN_C2_CAND) {  // unusually dense neighbourhood
+      for (int p = qb + lane; p < qe; p += 32) fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + p);
+      continue;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+      const int b0 = __shfl_sync(full, rb, r), len = __shfl_sync(full, rlen, r), off = __shfl_sync(full, incl, r) - len;
+      for (int i = lane; i < len; i += 32) cand[off + i] = sq[b0 + i];
+    }
+    for (int q0 = qb; q0 < qe; q0 += 32) {
+      const int nq = min(32, qe - q0);
+      const int S = 32 / nq;
+      const int qi = lane / S, sl = lane - qi * S;
+      const bool have = qi < nq;
+      cnt[lane] = 0;
+      __syncwarp();
+      const float4 me = sq[q0 + (have ? qi : 0)];
+      const int self = __float_as_int(me.w);
+      const float my_lb2 = have ? lb2 : -1.f;
+      for (int c = sl; c < n_cand; c += S) {
+        const float4 o = cand[c];
+        const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+        const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+        const int j = __float_as_int(o.w);
+        if ((dd < my_lb2) & (j != self)) {
+          const int pos = atomicAdd(&cnt[qi], 1);
+          if (pos < CTP_KNN_C2_KEEP) keys[pos][qi] = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)j;
+        }
+      }
+      __syncwarp();
+      const int T = have ? cnt[qi] : 0;
+      if (have && (T < K || T > CTP_KNN_C2_KEEP)) {
+        if (sl == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + q0 + qi);
+      } else if (have) {
+        int32_t *oi = idx + (q * n + self) * idx_stride;
+        float *od = d2out ? d2out + (q * n + self) * K : nullptr;
+        for (int u = sl; u < T; u += S) {
+          const unsigned long long key = keys[u][qi];
+          int rank = 0;
+          for (int x = 0; x < T; x++) rank += (keys[x][qi] < key) ? 1 : 0;
+          if (rank < K) {
+            oi[rank] = (int)(unsigned)key;
+            if (od) od[rank] = __uint_as_float((unsigned)(key >> 32));
+          }
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -869,6 +1013,100 @@ k_knn_cell(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restri
         if (d2out) d2out[(q * n + self) * K + lane] = __uint_as_float((unsigned)(key >> 32));
       }
     }
+  }
+}
+
+// ---- ring search, one warp per listed point ------------------------------------------------------
+// What the direct passes could not finish (isolated points, very uneven density) is few but needs
+// many cells: a warp walks the Chebyshev rings around the point's cell, lanes over the candidates of
+// each row, survivors kept with knn_offer; after each ring the k best so far are sorted and the search
+// stops as soon as the k-th is strictly nearer than the ring just completed (0.999 r h).
+#define CTP_KNN_RW_WARPS 4
+
+template <int K>
+__global__ void __launch_bounds__(32 * CTP_KNN_RW_WARPS)
+k_knn_ring_warp(const float4 *__restrict__ sorted, int64_t n, const int32_t *__restrict__ list,
+                const int32_t *__restrict__ count, const KnnGrid *__restrict__ grids, int cell_stride,
+                const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
+                float *__restrict__ d2out) {
+  __shared__ unsigned long long s_key[CTP_KNN_RW_WARPS][64];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned long long *keys = s_key[w];
+  const int cnt = *count;
+  const int n_warps = gridDim.x * CTP_KNN_RW_WARPS;
+  for (int li = blockIdx.x * CTP_KNN_RW_WARPS + w; li < cnt; li += n_warps) {
+    const int64_t t = list[li];
+    const int64_t q = t / n;
+    const KnnGrid g = grids[q];
+    const float4 me = sorted[t];
+    const int self = __float_as_int(me.w);
+    const float4 *sq = sorted + q * n;
+    const int32_t *st = cell_start + q * (cell_stride + 1);
+    const int cx = knn_cell_1d(me.x, g.lox, g.inv_h, g.dx);
+    const int cy = knn_cell_1d(me.y, g.loy, g.inv_h, g.dy);
+    const int cz = knn_cell_1d(me.z, g.loz, g.inv_h, g.dz);
+    int base = 0;
+    float thr = __int_as_float(0x7f800000);
+    unsigned long long key = 0xffffffffffffffffull;
+    const int rmax = max(max(g.dx, g.dy), g.dz);
+    __syncwarp();
+    for (int r = 0; r <= rmax; r++) {
+      const int z0 = cz - r, z1 = cz + r, y0 = cy - r, y1 = cy + r;
+      for (int z = max(z0, 0); z <= min(z1, g.dz - 1); z++) {
+        const bool zface = (z == z0) | (z == z1);
+        for (int y = max(y0, 0); y <= min(y1, g.dy - 1); y++) {
+          const bool face = zface | (y == y0) | (y == y1);
+          const int nseg = (face || r == 0) ? 1 : 2;  // inside the shell only the two x end cells are new
+          for (int sgi = 0; sgi < nseg; sgi++) {
+            int xa, xb;
+            if (nseg == 1) { xa = cx - r; xb = cx + r; }
+            else { xa = xb = (sgi == 0 ? cx - r : cx + r); }
+            if (xb < 0 || xa >= g.dx) continue;
+            xa = max(xa, 0);
+            xb = min(xb, g.dx - 1);
+            const int row = (z * g.dy + y) * g.dx;
+            const int b0 = st[row + xa], len = st[row + xb + 1] - b0;
+            for (int i0 = 0; i0 < len; i0 += 32) {
+              const int i = i0 + lane;
+              bool surv = false;
+              float dd = 0.f;
+              int j = -1;
+              if (i < len) {
+                const float4 o = sq[b0 + i];
+                const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+                dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+                j = __float_as_int(o.w);
+                surv = (dd <= thr) & (j != self);
+              }
+              knn_offer<K>(surv, dd, j, base, thr, keys, lane, lt_mask);
+            }
+          }
+        }
+      }
+      if (base >= K) {  // k best so far, sorted; tighten; stop when the ring just completed bounds the k-th
+        __syncwarp();
+        key = knn_sort32(lane < base ? keys[lane] : 0xffffffffffffffffull, lane);
+        __syncwarp();
+        if (lane < K) keys[lane] = key;
+        base = K;
+        thr = __uint_as_float((unsigned)(__shfl_sync(full, key, K - 1) >> 32));
+        __syncwarp();
+        const double lbd = (double)r * g.h * 0.999;
+        if ((double)thr < lbd * lbd) break;
+      }
+    }
+    if (base < K) {  // fewer than k other points exist: sorted prefix, padded with -1
+      __syncwarp();
+      key = knn_sort32(lane < base ? keys[lane] : 0xffffffffffffffffull, lane);
+    }
+    if (lane < K) {
+      const bool valid = lane < base;
+      idx[(q * n + self) * idx_stride + lane] = valid ? (int)(unsigned)key : -1;
+      if (d2out) d2out[(q * n + self) * K + lane] = valid ? __uint_as_float((unsigned)(key >> 32)) : __int_as_float(0x7f800000);
+    }
+    __syncwarp();
   }
 }
 

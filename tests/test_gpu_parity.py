@@ -441,3 +441,29 @@ def test_very_long_marches(c1, group):
     assert (l0 > 65536).any()
     assert np.array_equal(free, f0) and np.array_equal(hit, h0, equal_nan=True)
     assert np.array_equal(hit_idx, hi0) and np.array_equal(lookups, l0)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_knn_uneven_density_all_kernels(c1, orc, mode):
+    """clusters, isolated outliers, duplicates and a thin slab: every search kernel and its fallbacks"""
+    m, om, c, e = c1
+    rng = np.random.default_rng(100 + mode)
+    sets = []
+    a = np.concatenate([c + rng.standard_normal((2500, 3)) * 0.15,          # tight cluster
+                        c + (rng.random((60, 3)) - 0.5) * e,                # isolated outliers
+                        c + np.array([3.0, 3.0, 0]) + rng.standard_normal((400, 3)) * 0.6])
+    sets.append(a)
+    b = c + (rng.random((2960, 3)) - 0.5) * e
+    b[:, 2] = c[2] + (rng.random(2960) - 0.5) * 0.02                         # thin slab
+    b[500:560] = b[500]                                                       # 60 duplicates
+    sets.append(b)
+    pts = np.stack(sets)
+    m.set_tunable(capi.TUNE_KNN_TILE, mode)
+    try:
+        idx, d2 = m.knn(pts, 13)
+    finally:
+        m.set_tunable(capi.TUNE_KNN_TILE, 3)
+    for i in range(2):
+        i0, d0 = orc.knn_grid(pts[i], 13, nthreads=8)
+        assert np.array_equal(idx[i], i0)
+        assert np.array_equal(d2[i], d0)
