@@ -203,6 +203,56 @@ def workload_config(name, n, q, cpn, world):
     }
 
 
+def run_paths_leg(dmap, nodes_d, row_ptr_d, col_d, w_d, nnz_off_d, nq, n, clr, cdc):
+    """Shortest roadmap paths of the first nq queries (host Dijkstra over the CSR handed back, as the
+    reference does), then one ctp_shorten_path batch per direction and one all-pairs ctp_deformable batch
+    per query group -- the batched forms of shorten_path / removeEquivalentPaths."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import dijkstra
+    nodes = nodes_d[:nq].cpu().numpy()
+    rp = row_ptr_d[:nq].cpu().numpy()
+    off = nnz_off_d[:nq + 1].cpu().numpy()
+    lo, hi = int(off[0]), int(off[nq])
+    col = col_d[lo:hi].cpu().numpy()
+    w = w_d[lo:hi].cpu().numpy()
+    paths, lens = [], []
+    for i in range(nq):
+        a, b = int(off[i]) - lo, int(off[i + 1]) - lo
+        g = csr_matrix((w[a:b], col[a:b], rp[i]), shape=(n, n))
+        dist, pred = dijkstra(g, directed=True, indices=0, return_predecessors=True)
+        if not np.isfinite(dist[1]):
+            continue
+        p = [1]
+        while p[-1] != 0:
+            p.append(int(pred[p[-1]]))
+        pts = nodes[i][p[::-1]]
+        paths.append(pts)
+        lens.append(float(np.sum(np.sqrt(((pts[1:] - pts[:-1]) ** 2).sum(1)))))
+    if len(paths) < 2:
+        return None
+    cap = max(len(p) for p in paths) + 64
+    dmap.shorten_path(paths, lens, False, clr, cdc, cap=cap)  # warm-up
+    t0 = time.perf_counter()
+    back = dmap.shorten_path(paths, lens, False, clr, cdc, cap=cap)
+    fwd = dmap.shorten_path(back[0], list(back[2]), True, clr, cdc, cap=cap)
+    t_short = time.perf_counter() - t0
+    sp, sl = fwd[0], list(fwd[2])
+    P = len(sp)
+    ia = [i for i in range(P) for j in range(i + 1, P)]
+    ib = [j for i in range(P) for j in range(i + 1, P)]
+    nc = [float(np.ceil(max(sl[i], sl[j]) / cdc) + 1) for i, j in zip(ia, ib)]
+    dmap.deformable(sp, sl, ia[:8], ib[:8], nc[:8], clr, cdc)  # warm-up
+    t0 = time.perf_counter()
+    d = dmap.deformable(sp, sl, ia, ib, nc, clr, cdc)
+    t_def = time.perf_counter() - t0
+    return {"polylines": P, "mean_nodes_per_path": float(np.mean([len(p) for p in paths])),
+            "shorten_both_directions_ms": 1e3 * t_short, "shortened_mean_nodes": float(np.mean([len(p) for p in sp])),
+            "length_ratio_after_shortening": float(np.sum(sl) / np.sum(lens)),
+            "deformable_pairs": len(ia), "deformable_ms": 1e3 * t_def, "deformable_true": int((d == 1).sum()),
+            "connectors_checked_upper_bound": int(np.sum(nc)),
+            "api": "ctp_shorten_path / ctp_deformable (host buffers, wall clock)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,6 +271,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="skip the single-query latency leg")
+    ap.add_argument("--no-paths", action="store_true", help="skip the shortening / mutual-visibility leg")
     ap.add_argument("--e2e-steps", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -333,6 +384,7 @@ def main():
         dmap.sample_reject_dev(s_d, g_d, cand_d, 1, m_c, clr, n, nodes_d, n_filled_d, n_used_d, stream=stream)
         dmap.build_prm_dev(nodes_d, 1, n, K_NN, clr, cdc, row_ptr_d, col_d, w_d, cap, nnz_off_d, stream=stream)
     single_ms = None
+    single_graph_ms = None
     if not args.no_single:
         for _ in range(5):
             step1()
@@ -344,6 +396,34 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         single_ms = e0.elapsed_time(e1) / 50
+        # the same launches replayed from one CUDA graph (no per-launch host cost)
+        try:
+            side = torch.cuda.Stream()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                cs = torch.cuda.current_stream()
+                dmap.sample_reject_dev(s_d, g_d, cand_d, 1, m_c, clr, n, nodes_d, n_filled_d, n_used_d, stream=cs)
+                dmap.build_prm_dev(nodes_d, 1, n, K_NN, clr, cdc, row_ptr_d, col_d, w_d, cap, nnz_off_d, stream=cs)
+            for _ in range(5):
+                graph.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(50):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            single_graph_ms = e0.elapsed_time(e1) / 50
+        except Exception as ex:  # capture is an optimisation of the launch path only
+            single_graph_ms = None
+            print(f"bench.py: CUDA graph capture skipped: {ex}", file=sys.stderr)
+
+    # ---- clustering-stage batches on the same map: shorten_path and pairwise isDeformablePath ----
+    paths_leg = None
+    if rank == 0 and not args.no_paths:
+        try:
+            paths_leg = run_paths_leg(dmap, nodes_d, row_ptr_d, col_d, w_d, nnz_off_d, min(q, 64), n, clr, cdc)
+        except Exception as ex:
+            print(f"bench.py: paths leg skipped: {ex}", file=sys.stderr)
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers, copies timed) ----
     e2e = None
@@ -420,7 +500,9 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args.workload, n, q, cpn, world), layout=dmap.layout_name(),
                            lanes_per_edge=dmap.prm_group()),
-            "ms_per_query": {"batched": ms_max / args.steps / q, "single_query_latency": single_ms},
+            "ms_per_query": {"batched": ms_max / args.steps / q, "single_query_latency": single_ms,
+                             "single_query_latency_cuda_graph": single_graph_ms},
+            "paths": paths_leg,
             "lookups_per_s": lookups / (ms_max * 1e-3),
             "stage_ms_per_step": {k_: v / args.steps for k_, v in stage_ms.items()},
             "roofline": {"bound": "hbm", "kernel": "k_edge_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
