@@ -74,7 +74,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -163,7 +163,7 @@ def run_reference(args, rank, world):
     arm = CpuArm(vox, c, e)
     q_total = (args.queries or qdef) * world
     # bounded sample: one query per core per step (at least 8), the first queries of the same set
-    q_s = args.cpu_queries or max(8, min(cores, 256))
+    q_s = args.cpu_queries or max(8, min(4 * cores, 512))
     s, g, cand = make_queries(c, e, q_total, n, cpn, 0, min(q_s, q_total))
     q_s = len(s)
     for _ in range(args.warmup):
@@ -256,7 +256,7 @@ def run_paths_leg(dmap, nodes_d, row_ptr_d, col_d, w_d, nnz_off_d, nq, n, clr, c
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
@@ -461,8 +461,9 @@ def main():
         arm = CpuArm(vox, c, e)
         # single-thread probe on one query, then a sample sized for ~10-20 s of wall time
         t1, o1 = arm.run(s_h[:1], g_h[:1], cand_h[:1], n, clr, cdc, 1)
-        q_s = args.cpu_queries or int(max(min(cores, q), min(q, cores * 12.0 / max(t1, 1e-3))))
-        q_s = max(1, min(q_s, q, 4 * cores if cores >= 8 else 64))
+        # as many of the step's queries as fit in ~20 s of wall time on these cores (all of them if possible)
+        q_s = args.cpu_queries or int(min(q, max(cores, cores * 20.0 / max(t1, 1e-3))))
+        q_s = max(1, min(q_s, q))
         tc, oc = arm.run(s_h[:q_s], g_h[:q_s], cand_h[:q_s], n, clr, cdc, cores)
         cpu = {"value": q_s * n * K_NN / tc, "unit": UNIT, "cores": cores, "kind": arm.kind,
                "sample": f"first {q_s} of the step's {q} queries, whole sampleMultiple on the host "
@@ -505,7 +506,7 @@ def main():
             "paths": paths_leg,
             "lookups_per_s": lookups / (ms_max * 1e-3),
             "stage_ms_per_step": {k_: v / args.steps for k_, v in stage_ms.items()},
-            "roofline": {"bound": "hbm", "kernel": "k_edge_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_edge_flat" if dmap.prm_group() == 1 else "k_edge_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": alg_bytes / launches_edge,

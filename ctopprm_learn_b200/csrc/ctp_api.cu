@@ -696,6 +696,7 @@ static size_t ws_bytes_knn(int64_t q, int64_t n) {
 }
 static size_t ws_bytes_prm(int64_t q, int64_t n, int k) {
   return ws_bytes_knn(q, n) + align_up((size_t)q * n * csr_ns(k) * 4) + 2 * align_up((size_t)q * n * k) +
+         align_up((size_t)q * n * k * 8) +
          align_up((size_t)q * n * 4) + align_up((size_t)q * 8);
 }
 
@@ -922,8 +923,8 @@ extern "C" int ctp_knn(ctp_map *m, const double *nodes, int64_t q, int64_t n, in
 // ------------------------------------- PRM build -------------------------------------------
 // symmetric union of the free directed edges -> CSR (:374-385); rec holds the neighbour ids
 static int csr_emit(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *d_rec, const uint8_t *d_free,
-                    uint8_t *d_flag, int32_t *d_deg, int64_t *d_nnz, int32_t *row_ptr, int32_t *col, double *w,
-                    int64_t cap, int64_t *nnz_off, cudaStream_t st) {
+                    uint8_t *d_flag, int32_t *d_deg, int64_t *d_nnz, int32_t *d_coltmp, int32_t *row_ptr, int32_t *col,
+                    double *w, int64_t cap, int64_t *nnz_off, cudaStream_t st) {
   const int64_t rows = q * n, edges = rows * k;
   const int ns = csr_ns(k);
   StageSpan span(m, CTP_STAGE_CSR, st);
@@ -937,10 +938,12 @@ static int csr_emit(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k
   m->launches++;
   k_csr_query_offsets<<<1, 1024, 0, st>>>(d_nnz, q, nnz_off);
   m->launches++;
-  if (ns == 16) k_csr_fill<16><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
-  else k_csr_fill<32><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, cap, d_deg, col);
+  // unsorted rows go to scratch (at most 2 entries per directed edge), the finish pass ranks them into col
+  const int64_t tcap = std::min<int64_t>(cap, 2 * edges);
+  if (ns == 16) k_csr_fill<16><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, tcap, d_deg, d_coltmp);
+  else k_csr_fill<32><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, tcap, d_deg, d_coltmp);
   m->launches++;
-  k_csr_finish<<<rb, 256, 0, st>>>(nodes, n, rows, row_ptr, nnz_off, cap, col, w);
+  k_csr_finish_flat<<<(int)((rows + 255) / 256), 256, 0, st>>>(nodes, n, rows, row_ptr, nnz_off, tcap, d_coltmp, col, w);
   m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
@@ -964,6 +967,7 @@ extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int
   uint8_t *d_flag = arena_take<uint8_t>(m->ws, edges);
   int32_t *d_deg = arena_take<int32_t>(m->ws, rows);
   int64_t *d_nnz = arena_take<int64_t>(m->ws, q);
+  int32_t *d_coltmp = arena_take<int32_t>(m->ws, 2 * edges);
   int rc;
   {
     StageSpan span(m, CTP_STAGE_KNN, st);
@@ -978,7 +982,7 @@ extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int
     StageSpan span(m, CTP_STAGE_EDGES, st);
     CKR(launch_edges(m, m->prm_group, S, edges, clr, cdc, 0, O, st));
   }
-  CKR(csr_emit(m, nodes, q, n, k, d_rec, d_free, d_flag, d_deg, d_nnz, row_ptr, col, w, cap, nnz_off, st));
+  CKR(csr_emit(m, nodes, q, n, k, d_rec, d_free, d_flag, d_deg, d_nnz, d_coltmp, row_ptr, col, w, cap, nnz_off, st));
   if (nbr) {
     k_rec_to_nbr<<<(int)((edges + 255) / 256), 256, 0, st>>>(d_rec, ns, k, edges, nbr);
     m->launches++;
@@ -1048,10 +1052,11 @@ extern "C" int ctp_csr_from_directed_dev(ctp_map *m, const double *nodes, int64_
   uint8_t *d_flag = arena_take<uint8_t>(m->ws, edges);
   int32_t *d_deg = arena_take<int32_t>(m->ws, rows);
   int64_t *d_nnz = arena_take<int64_t>(m->ws, q);
+  int32_t *d_coltmp = arena_take<int32_t>(m->ws, 2 * edges);
   m->ws.used = keep;
   k_nbr_to_rec<<<(int)((edges + 255) / 256), 256, 0, st>>>(nbr, ns, k, edges, d_rec);
   m->launches++;
-  return csr_emit(m, nodes, q, n, k, d_rec, directed_free, d_flag, d_deg, d_nnz, row_ptr, col, w, cap, nnz_off, st);
+  return csr_emit(m, nodes, q, n, k, d_rec, directed_free, d_flag, d_deg, d_nnz, d_coltmp, row_ptr, col, w, cap, nnz_off, st);
 }
 
 extern "C" int ctp_csr_from_directed(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, const int32_t *nbr,

@@ -1348,6 +1348,67 @@ __global__ void __launch_bounds__(256) k_nbr_to_rec(const int32_t *__restrict__ 
   rec[row * ns + (e - row * k)] = nbr[e];
 }
 
+// one thread per CSR ENTRY (a warp takes 32 consecutive rows and walks their entries in flat order):
+// the entry's final position is its rank among the row's column ids (they are distinct), so the
+// ascending order needs no per-thread sort and every load/store is coalesced; the FP64 weight
+// ||to - from|| (:369-371) is computed on the way out.  col_in -> col / w (out of place).
+__global__ void __launch_bounds__(256) k_csr_finish_flat(const double *__restrict__ nodes, int64_t n, int64_t total_rows,
+                                                         const int32_t *__restrict__ row_ptr,
+                                                         const int64_t *__restrict__ nnz_off, int64_t cap,
+                                                         const int32_t *__restrict__ col_in, int32_t *__restrict__ col,
+                                                         double *__restrict__ w) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (r0 >= total_rows) return;
+  // lane l: global start/end of row r0 + l (rows of one warp may straddle two queries)
+  const int64_t row = r0 + lane;
+  int64_t rb = 0, re = 0;
+  if (row < total_rows) {
+    const int64_t q = row / n, i = row - q * n;
+    const int32_t *rp = row_ptr + q * (n + 1);
+    rb = nnz_off[q] + rp[i];
+    re = nnz_off[q] + rp[i + 1];
+  }
+  const int len = (int)(re - rb);
+  int incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(full, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(full, incl, 31);
+  for (int e0 = 0; e0 < total; e0 += 32) {
+    const int e = e0 + lane;
+    // owner lane = number of rows whose inclusive prefix is <= e
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int probe = __shfl_sync(full, incl, lo + step - 1);
+      if (probe <= e) lo += step;
+    }
+    const int owner = min(lo, 31);
+    const int64_t obeg = __shfl_sync(full, rb, owner);
+    const int olen = __shfl_sync(full, len, owner);
+    const int oexcl = __shfl_sync(full, incl, owner) - olen;
+    if (e < total) {
+      if (obeg + olen <= cap) {
+        const int32_t c = col_in[obeg + (e - oexcl)];
+        int rank = 0;
+#pragma unroll 4
+        for (int x = 0; x < olen; x++) rank += (__ldg(col_in + obeg + x) < c) ? 1 : 0;
+        const int64_t orow = r0 + owner;
+        const int64_t oq = orow / n;
+        const double *me = nodes + 3 * orow;
+        const double *o = nodes + 3 * (oq * n + c);
+        const double dx = o[0] - me[0], dy = o[1] - me[1], dz = o[2] - me[2];
+        col[obeg + rank] = c;
+        w[obeg + rank] = sqrt((dx * dx + dy * dy) + dz * dz);
+      }
+    }
+  }
+}
+
 // neighbour records (stride NS) -> dense user-visible k-NN table (stride k)
 __global__ void __launch_bounds__(256) k_rec_to_nbr(const int32_t *__restrict__ rec, int ns, int k, int64_t total_edges,
                                                     int32_t *__restrict__ nbr) {
