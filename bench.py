@@ -265,7 +265,7 @@ def main():
     ap.add_argument("--group", type=int, default=0, help="lanes per edge in the march kernel (0 = library default)")
     ap.add_argument("--knn-per-cell", type=float, default=0.0)
     ap.add_argument("--knn-ring", action="store_true", help="ring-search k-NN only (no tile kernel)")
-    ap.add_argument("--knn-mode", type=int, default=-1, help="0 ring, 1 tile, 2 cell")
+    ap.add_argument("--knn-mode", type=int, default=-1, help="0 per-thread ring search, 1 direct search (default)")
     ap.add_argument("--pipe-chunk", type=int, default=0, help="queries per chunk of the e2e copy/compute pipeline")
     ap.add_argument("--cpu-queries", type=int, default=0, help="size of the CPU baseline sample (queries)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -66,7 +66,7 @@ struct ctp_map {
   size_t map_bytes = 0;
   // stage profiling (ctp_profile): pairs of events recorded on the caller's stream
   double knn_per_cell = 22.0;  // expected points inside a ball of one cell size (see k_knn_setup)
-  int knn_tile = 3;           // 4 = cell2 (+ direct list), 3 = direct, 2 = cell, 1 = tile (all + ring-search fallback), 0 = ring only
+  int knn_tile = 1;           // 1 = direct search + listed wider passes + warp ring search, 0 = per-thread ring search only
   unsigned long long launches = 0;  // kernels enqueued by this handle (ctp_launch_counter_read)
   int prm_group = 1;  // ctp_build_prm: 1 = flat lookup-parallel kernel (kNN edges are ~3-12 samples long)
   // chunk pipeline of the host-pointer ctp_sample_multiple
@@ -333,7 +333,7 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
       m->knn_per_cell = value;
       return CTP_OK;
     case CTP_TUNE_KNN_TILE:
-      m->knn_tile = (int)value;
+      m->knn_tile = value != 0.0;
       return CTP_OK;
     case CTP_TUNE_PIPE_CHUNK:
       REQUIRE(value >= 0 && value <= 65535, "queries per chunk must be in [0, 65535]");
@@ -828,37 +828,18 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
   CK(cudaGetLastError());
   if (m->knn_tile && n > 4 * k) {
     CK(cudaMemsetAsync(d_fbn, 0, 8, st));
-    // a query's tiles are shared by bpq CTAs; enough CTAs overall to fill the machine several times
-    const int bpq = (int)std::max<int64_t>(8, ((int64_t)m->sm_count * 16 + q - 1) / q);
-    const dim3 tgrid((unsigned)bpq, (unsigned)q);
     const int lblocks = m->sm_count * 8;
 #define KNN_CASE(K)                                                                                               \
   case K:                                                                                                         \
-    if (m->knn_tile == 4) {                                                                                       \
-      k_knn_cell2<K><<<tgrid, 32 * CTP_KNN_C2_WARPS, 0, st>>>(d_sorted, n, d_grid, mc, d_start, idx, idx_stride,  \
-                                                              d2, d_fb2, d_fbn + 1);                              \
-      k_knn_direct_list<K><<<lblocks, CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, d_fb2, nullptr, d_fbn + 1, 0, \
-                                                                      d_grid, mc, d_start, idx, idx_stride, d2,   \
-                                                                      d_fb, d_fbn);                               \
-      m->launches++;                                                                                              \
-    } else if (m->knn_tile == 3) {                                                                                \
-      k_knn_direct<K><<<(int)((total + CTP_KNN_DIRECT_THREADS - 1) / CTP_KNN_DIRECT_THREADS),                     \
-                        CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, idx_stride, \
-                                                         d2, d_fb2, d_fbk, d_fbn + 1);                            \
-      k_knn_direct_list<K><<<lblocks, CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, d_fb2, d_fbk, d_fbn + 1, 1,   \
-                                                                      d_grid, mc, d_start, idx, idx_stride, d2,   \
-                                                                      d_fb, d_fbn);                               \
-      m->launches++;                                                                                              \
-    }                                                                                                             \
-    else if (m->knn_tile == 2)                                                                                    \
-      k_knn_cell<K><<<tgrid, 32 * CTP_KNN_CELL_WARPS, 0, st>>>(d_sorted, n, d_grid, mc, d_start, idx, idx_stride, \
-                                                               d2, d_fb, d_fbn);                                  \
-    else                                                                                                          \
-      k_knn_tile<K><<<tgrid, CTP_KNN_TILE_THREADS, 0, st>>>(d_sorted, n, d_grid, mc, d_start, idx, idx_stride,    \
-                                                            d2, d_fb, d_fbn);                                     \
+    k_knn_direct<K><<<(int)((total + CTP_KNN_DIRECT_THREADS - 1) / CTP_KNN_DIRECT_THREADS),                       \
+                      CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, idx_stride,   \
+                                                       d2, d_fb2, d_fbk, d_fbn + 1);                              \
+    k_knn_direct_list<K><<<lblocks, CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, d_fb2, d_fbk, d_fbn + 1, 1,     \
+                                                                    d_grid, mc, d_start, idx, idx_stride, d2,     \
+                                                                    d_fb, d_fbn);                                 \
     k_knn_ring_warp<K><<<lblocks, 32 * CTP_KNN_RW_WARPS, 0, st>>>(d_sorted, n, d_fb, d_fbn, d_grid, mc, d_start,  \
                                                                   idx, idx_stride, d2);                          \
-    m->launches += 2;                                                                                             \
+    m->launches += 3;                                                                                             \
     break;
     switch (k) {
       KNN_CASE(1) KNN_CASE(2) KNN_CASE(3) KNN_CASE(4) KNN_CASE(5) KNN_CASE(6) KNN_CASE(7) KNN_CASE(8)

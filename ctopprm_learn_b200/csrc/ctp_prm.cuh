@@ -394,185 +394,6 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
   knn_ring_search<K>(t, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out);
 }
 
-// ring search over the queries the tile pass could not finish (positions in the sorted array)
-template <int K>
-__global__ void __launch_bounds__(128) k_knn_search_list(const float4 *__restrict__ sorted, int64_t n,
-                                                         const int32_t *__restrict__ list,
-                                                         const int32_t *__restrict__ count,
-                                                         const KnnGrid *__restrict__ grids, int cell_stride,
-                                                         const int32_t *__restrict__ cell_start,
-                                                         int32_t *__restrict__ idx, int idx_stride,
-                                                         float *__restrict__ d2out) {
-  const int cnt = *count;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
-    knn_ring_search<K>(list[i], sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out);
-}
-
-// ---- tile search: the fast path ---------------------------------------------------------------
-// A CTA takes a tile of TX x 2 x 2 cells.  The points of the tile plus a one-cell halo
-// ((TX+2) x 4 x 4 cells = 16 contiguous runs of the cell-sorted array) are staged in shared memory
-// once, together with the position of every cell boundary inside the staged list.  Every thread
-// then owns one query point of the tile and scans the 3 x 3 x 3 cells around its own cell (nine
-// runs of three cells) out of shared memory.  Anything farther than 0.999 h cannot be ruled
-// complete by those 27 cells, and anything nearer is guaranteed to be in them, so the scan only
-// keeps candidates with d2 < (0.999 h)^2 -- appended branch-free to a per-thread column in shared
-// memory -- and the k best of those are the exact answer whenever at least k were kept.  The top-k
-// insertion network therefore runs over ~20-30 survivors instead of diverging on every candidate.
-// Queries with fewer than k (sparse borders) or more than CTP_KNN_KEEP survivors, and tiles whose
-// halo does not fit the staging buffer, are appended to a list and redone by the ring search
-// (k_knn_search_list).
-#define CTP_KNN_TX 4
-#define CTP_KNN_TILE_THREADS 128
-#define CTP_KNN_TILE_CAP 1024
-#define CTP_KNN_KEEP 40
-
-template <int K>
-__global__ void __launch_bounds__(CTP_KNN_TILE_THREADS)
-k_knn_tile(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restrict__ grids, int cell_stride,
-           const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
-           float *__restrict__ d2out, int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
-  __shared__ float4 s_c[CTP_KNN_TILE_CAP];
-  __shared__ uint16_t s_keep[CTP_KNN_KEEP][CTP_KNN_TILE_THREADS];  // survivor columns (index into s_c)
-  __shared__ int s_cb[17], s_cs[16];        // candidate runs: prefix count, start in the sorted array
-  __shared__ int s_cell[16][CTP_KNN_TX + 3];  // staged position of each cell boundary of a run
-  __shared__ int s_qb[5], s_qs[4];          // query runs (the tile's own cells)
-  const int tid = threadIdx.x;
-  // blockIdx.y = query; the gridDim.x CTAs of a query stride over its tiles
-  const int64_t q = blockIdx.y;
-  const KnnGrid g = grids[q];
-  const int tx = (g.dx + CTP_KNN_TX - 1) / CTP_KNN_TX, ty = (g.dy + 1) >> 1, tz = (g.dz + 1) >> 1;
-  const int n_tiles = tx * ty * tz;
-  const int32_t *st = cell_start + q * (cell_stride + 1);
-  const float4 *sq = sorted + q * n;
-  const float lb = (float)(g.h * 0.999);
-  const float lb2 = lb * lb;  // rounding here only shifts which queries take the fallback
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int x0 = (tile % tx) * CTP_KNN_TX, y0 = ((tile / tx) % ty) * 2, z0 = (tile / (tx * ty)) * 2;
-    __syncthreads();  // previous tile's shared arrays are no longer read
-    if (tid < 32) {
-      int len = 0;
-      if (tid < 16) {  // candidate run (dy, dz) in [-1, 2]^2, x cells x0-1 .. x0+TX
-        const int y = y0 - 1 + (tid & 3), z = z0 - 1 + (tid >> 2);
-        int b = 0, e = 0;
-        if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
-          const int row = (z * g.dy + y) * g.dx;
-          b = st[row + max(x0 - 1, 0)];
-          e = st[row + min(x0 + CTP_KNN_TX, g.dx - 1) + 1];
-        }
-        s_cs[tid] = b;
-        len = e - b;
-      } else if (tid < 20) {  // query run (dy, dz) in [0, 1]^2, x cells x0 .. x0+TX-1
-        const int r = tid - 16;
-        const int y = y0 + (r & 1), z = z0 + (r >> 1);
-        int b = 0, e = 0;
-        if (y < g.dy && z < g.dz) {
-          const int row = (z * g.dy + y) * g.dx;
-          b = st[row + x0];
-          e = st[row + min(x0 + CTP_KNN_TX - 1, g.dx - 1) + 1];
-        }
-        s_qs[r] = b;
-        len = e - b;
-      }
-      // inclusive scans: lanes 0..15 (candidates) and 16..19 (queries) separately
-      int incl = len;
-#pragma unroll
-      for (int o = 1; o < 16; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((tid & 15) >= o) incl += t;
-      }
-      if (tid < 16) s_cb[tid + 1] = incl;
-      else if (tid < 20) s_qb[tid - 15] = incl;
-      if (tid == 0) { s_cb[0] = 0; s_qb[0] = 0; }
-    }
-    __syncthreads();
-    const int n_query = s_qb[4], n_cand = s_cb[16];
-    if (n_query == 0) continue;
-    if (n_cand > CTP_KNN_TILE_CAP) {  // unusually dense halo: the ring search takes the whole tile
-      for (int qi = tid; qi < n_query; qi += CTP_KNN_TILE_THREADS) {
-        int r = 0;
-#pragma unroll
-        for (int t = 1; t < 4; t++) r += (qi >= s_qb[t]) ? 1 : 0;
-        fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + s_qs[r] + (qi - s_qb[r]));
-      }
-      continue;
-    }
-    // cell boundaries inside the staged list
-    if (tid < 16 * (CTP_KNN_TX + 3)) {
-      const int r = tid / (CTP_KNN_TX + 3), t = tid - r * (CTP_KNN_TX + 3);
-      const int y = y0 - 1 + (r & 3), z = z0 - 1 + (r >> 2);
-      int pos = s_cb[r];
-      if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
-        const int row = (z * g.dy + y) * g.dx;
-        const int xlo = max(x0 - 1, 0), xhi = min(x0 + CTP_KNN_TX, g.dx - 1);
-        const int gb = min(max(x0 - 1 + t, xlo), xhi + 1);
-        pos += st[row + gb] - s_cs[r];
-      }
-      s_cell[r][t] = pos;
-    }
-    for (int i = tid; i < n_cand; i += CTP_KNN_TILE_THREADS) {
-      int r = 0;
-#pragma unroll
-      for (int t = 1; t < 16; t++) r += (i >= s_cb[t]) ? 1 : 0;
-      s_c[i] = sq[s_cs[r] + (i - s_cb[r])];
-    }
-    __syncthreads();
-    for (int qb = 0; qb < n_query; qb += CTP_KNN_TILE_THREADS) {
-      const int qi = qb + tid;
-      if (qi >= n_query) break;  // no barrier below this point
-      int r = 0;
-#pragma unroll
-      for (int t = 1; t < 4; t++) r += (qi >= s_qb[t]) ? 1 : 0;
-      const int qpos = s_qs[r] + (qi - s_qb[r]);
-      const float4 me = sq[qpos];
-      const int self = __float_as_int(me.w);
-      const int lx = knn_cell_1d(me.x, g.lox, g.inv_h, g.dx) - x0;  // cell inside the tile
-      const int ly = knn_cell_1d(me.y, g.loy, g.inv_h, g.dy) - y0;
-      const int lz = knn_cell_1d(me.z, g.loz, g.inv_h, g.dz) - z0;
-      int kept = 0;
-#pragma unroll
-      for (int dz = 0; dz < 3; dz++) {
-#pragma unroll
-        for (int dy = 0; dy < 3; dy++) {
-          const int run = (lz + dz) * 4 + (ly + dy);
-          const int pb = s_cell[run][lx], pe = s_cell[run][lx + 3];
-          for (int c = pb; c < pe; c++) {
-            const float4 o = s_c[c];
-            const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
-            const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
-            const bool keep = dd < lb2;
-            if (keep) s_keep[min(kept, CTP_KNN_KEEP - 1)][tid] = (uint16_t)c;
-            kept += keep ? 1 : 0;
-          }
-        }
-      }
-      // kept includes the query itself (d2 = 0)
-      TopK<K> best;
-      best.init();
-      const bool redo = kept > CTP_KNN_KEEP;
-      kept = min(kept, CTP_KNN_KEEP);
-      for (int t = 0; t < kept; t++) {
-        const float4 o = s_c[s_keep[t][tid]];
-        const int j = __float_as_int(o.w);
-        const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
-        const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
-        if (j != self) best.push(dd, j);
-      }
-      if (!redo && best.id[K - 1] != 0x7fffffff) {
-        int32_t *oi = idx + (q * n + self) * idx_stride;
-#pragma unroll
-        for (int s = 0; s < K; s++) oi[s] = best.id[s];
-        if (d2out) {
-          float *od = d2out + (q * n + self) * K;
-#pragma unroll
-          for (int s = 0; s < K; s++) od[s] = best.d[s];
-        }
-      } else {
-        fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + qpos);
-      }
-    }
-  }
-}
-
 // ---- direct search: one thread per cell-sorted point, survivors in shared-memory columns ---------
 // Thread t owns sorted point t (neighbouring threads sit in the same or adjacent cells, so their
 // candidate reads hit the same L1 lines).  It scans the nine runs of its 27 cells straight from
@@ -686,130 +507,7 @@ k_knn_direct_list(const float4 *__restrict__ sorted, int64_t n, const int32_t *_
                         pass_lo, 2, list_kept ? list_kept[i] : 0, fb_list, nullptr, fb_count);
 }
 
-// ---- cell search, two-dimensional: lanes = (query of the cell) x (slice of the candidates) --------
-// All points of one grid cell share the same 27-cell candidate set.  A warp takes a cell, stages the
-// candidates in shared memory, and splits its lanes into nq groups of S = 32 / nq lanes: group qi
-// serves query qi, lane sl of the group scans candidates sl, sl + S, ...  Every lane does the exact
-// float32 distance of ITS query to ITS candidate (no divergence: all lanes run the same loop) and
-// appends survivors with d2 < (0.999 h)^2 -- anything nearer is guaranteed to be among the
-// candidates, anything farther cannot be ranked -- to the query's key list in shared memory.  The
-// group then ranks the ~20 survivors against each other ((d2, index) order) and the ones with rank
-// < k write themselves to the output row.  Exact whenever at least k survived; otherwise (sparse
-// borders, more than 32 survivors, more candidates than fit) the query goes to the list served by
-// k_knn_direct_list.
-#define CTP_KNN_C2_WARPS 4
-#define CTP_KNN_C2_CAND 240
-#define CTP_KNN_C2_KEEP 32
-
-template <int K>
-__global__ void __launch_bounds__(32 * CTP_KNN_C2_WARPS)
-k_knn_cell2(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restrict__ grids, int cell_stride,
-            const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
-            float *__restrict__ d2out, int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
-  __shared__ float4 s_cand[CTP_KNN_C2_WARPS][CTP_KNN_C2_CAND];
-  __shared__ unsigned long long s_keys[CTP_KNN_C2_WARPS][CTP_KNN_C2_KEEP][32];  // [entry][query slot]
-  __shared__ int s_cnt[CTP_KNN_C2_WARPS][32];
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float4 *cand = s_cand[w];
-  unsigned long long(*keys)[32] = s_keys[w];
-  int *cnt = s_cnt[w];
-  const int64_t q = blockIdx.y;
-  const KnnGrid g = grids[q];
-  const int32_t *st = cell_start + q * (cell_stride + 1);
-  const float4 *sq = sorted + q * n;
-  const float lb = (float)(g.h * 0.999);
-  const float lb2 = lb * lb;  // rounding here only shifts which queries take the fallback
-  const int n_warps = gridDim.x * CTP_KNN_C2_WARPS;
-  for (int cell = blockIdx.x * CTP_KNN_C2_WARPS + w; cell < g.ncell; cell += n_warps) {
-    const int qb = st[cell], qe = st[cell + 1];
-    if (qb == qe) continue;
-    const int cx = cell % g.dx, cy = (cell / g.dx) % g.dy, cz = cell / (g.dx * g.dy);
-    // nine candidate runs (dy, dz) in [-1, 1]^2, x cells cx-1 .. cx+1; lane r < 9 fetches run r
-    int rb = 0, rlen = 0;
-    if (lane < 9) {
-      const int y = cy - 1 + lane % 3, z = cz - 1 + lane / 3;
-      if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
-        const int row = (z * g.dy + y) * g.dx;
-        rb = st[row + max(cx - 1, 0)];
-        rlen = st[row + min(cx + 1, g.dx - 1) + 1] - rb;
-      }
-    }
-    int incl = rlen;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-      const int t = __shfl_up_sync(full, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const int n_cand = __shfl_sync(full, incl, 8);
-    if (n_cand > CTP_KNN_C2_CAND) {  // unusually dense neighbourhood
-      for (int p = qb + lane; p < qe; p += 32) fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + p);
-      continue;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-      const int b0 = __shfl_sync(full, rb, r), len = __shfl_sync(full, rlen, r), off = __shfl_sync(full, incl, r) - len;
-      for (int i = lane; i < len; i += 32) cand[off + i] = sq[b0 + i];
-    }
-    for (int q0 = qb; q0 < qe; q0 += 32) {
-      const int nq = min(32, qe - q0);
-      const int S = 32 / nq;
-      const int qi = lane / S, sl = lane - qi * S;
-      const bool have = qi < nq;
-      cnt[lane] = 0;
-      __syncwarp();
-      const float4 me = sq[q0 + (have ? qi : 0)];
-      const int self = __float_as_int(me.w);
-      const float my_lb2 = have ? lb2 : -1.f;
-      for (int c = sl; c < n_cand; c += S) {
-        const float4 o = cand[c];
-        const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
-        const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
-        const int j = __float_as_int(o.w);
-        if ((dd < my_lb2) & (j != self)) {
-          const int pos = atomicAdd(&cnt[qi], 1);
-          if (pos < CTP_KNN_C2_KEEP) keys[pos][qi] = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)j;
-        }
-      }
-      __syncwarp();
-      const int T = have ? cnt[qi] : 0;
-      if (have && (T < K || T > CTP_KNN_C2_KEEP)) {
-        if (sl == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + q0 + qi);
-      } else if (have) {
-        int32_t *oi = idx + (q * n + self) * idx_stride;
-        float *od = d2out ? d2out + (q * n + self) * K : nullptr;
-        for (int u = sl; u < T; u += S) {
-          const unsigned long long key = keys[u][qi];
-          int rank = 0;
-          for (int x = 0; x < T; x++) rank += (keys[x][qi] < key) ? 1 : 0;
-          if (rank < K) {
-            oi[rank] = (int)(unsigned)key;
-            if (od) od[rank] = __uint_as_float((unsigned)(key >> 32));
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
-
-// ---- cell search: lanes over candidates ------------------------------------------------------
-// All points of one grid cell share the same 27-cell candidate set.  A warp takes a cell, keeps the
-// candidates (about 27 x the cell density, up to 32 * CTP_KNN_SLOTS; streamed from memory when
-// there are more) in registers, one to a few per lane, and then serves the cell's points one after
-// the other: every lane computes the exact float32 squared distance of the query to its candidates;
-// the survivors with d2 < (0.999 h)^2 -- anything nearer is guaranteed to be among the candidates,
-// anything farther cannot be ranked -- are appended as (d2, index) keys to a 64-entry buffer by
-// ballot/popc; whenever more than 32 are pending a 64-wide bitonic network keeps the k best and
-// tightens the threshold.  A final 32-wide network sorts what is left; lanes 0..k-1 then hold the
-// answer and write it with one coalesced store.  No per-thread top-k state, no divergence.
-// Fewer than k survivors (sparse borders of the point cloud): the same procedure over the
-// 5 x 5 x 5 cells with radius 2 * 0.999 h.  Only queries with fewer than k points within 2h go
-// to the ring-search list.
-#define CTP_KNN_SLOTS 8
-#define CTP_KNN_CELL_WARPS 8
-
+// ---- warp-level selection helpers: (d2, index) keys, bitonic networks over the lanes ------------
 __device__ __forceinline__ unsigned long long knn_min64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 __device__ __forceinline__ unsigned long long knn_max64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
 
@@ -869,150 +567,6 @@ __device__ __forceinline__ void knn_offer(bool surv, float dd, int j, int &base,
     // later candidates must beat (or tie in distance with) the current k-th
     thr = __uint_as_float((unsigned)(__shfl_sync(0xffffffffu, k1, K - 1) >> 32));
     __syncwarp();
-  }
-}
-
-template <int K>
-__global__ void __launch_bounds__(32 * CTP_KNN_CELL_WARPS)
-k_knn_cell(const float4 *__restrict__ sorted, int64_t n, const KnnGrid *__restrict__ grids, int cell_stride,
-           const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
-           float *__restrict__ d2out, int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
-  __shared__ unsigned long long s_key[CTP_KNN_CELL_WARPS][64];
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  unsigned long long *keys = s_key[w];
-  const int64_t q = blockIdx.y;
-  const KnnGrid g = grids[q];
-  const int32_t *st = cell_start + q * (cell_stride + 1);
-  const float4 *sq = sorted + q * n;
-  const float lb = (float)(g.h * 0.999);
-  const float lb2 = lb * lb;  // rounding here only shifts which queries take the wider search
-  const float wide = 2.f * lb;
-  const float wide2 = wide * wide;
-  const float inf = __int_as_float(0x7f800000);
-  const int n_warps = gridDim.x * CTP_KNN_CELL_WARPS;
-  for (int cell = blockIdx.x * CTP_KNN_CELL_WARPS + w; cell < g.ncell; cell += n_warps) {
-    const int qb = st[cell], qe = st[cell + 1];
-    if (qb == qe) continue;
-    const int cx = cell % g.dx, cy = (cell / g.dx) % g.dy, cz = cell / (g.dx * g.dy);
-    // nine candidate runs (dy, dz) in [-1, 1]^2, x cells cx-1 .. cx+1; lane r < 9 fetches run r
-    int rb = 0, rlen = 0;
-    if (lane < 9) {
-      const int y = cy - 1 + lane % 3, z = cz - 1 + lane / 3;
-      if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
-        const int row = (z * g.dy + y) * g.dx;
-        rb = st[row + max(cx - 1, 0)];
-        rlen = st[row + min(cx + 1, g.dx - 1) + 1] - rb;
-      }
-    }
-    int incl = rlen;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-      const int t = __shfl_up_sync(full, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const int n_cand = __shfl_sync(full, incl, 8);
-    const bool in_regs = n_cand <= 32 * CTP_KNN_SLOTS;
-    // candidate i of the flattened runs sits at rb[r] + (i - excl[r]); each lane takes i = lane + 32 s
-    float4 cand[CTP_KNN_SLOTS];
-    if (in_regs) {
-      const int excl = incl - rlen;
-#pragma unroll
-      for (int s = 0; s < CTP_KNN_SLOTS; s++) {
-        const int i = lane + 32 * s;
-        int r = 0;
-#pragma unroll
-        for (int t = 1; t < 9; t++) r += (i >= __shfl_sync(full, excl, t)) ? 1 : 0;
-        const int pos = __shfl_sync(full, rb, r) + (i - __shfl_sync(full, excl, r));
-        cand[s] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        if (i < n_cand) cand[s] = sq[pos];
-      }
-    }
-    const int n_slots = (n_cand + 31) >> 5;
-    int rb5 = 0, rlen5 = -1;  // the 25 runs of the 5 x 5 x 5 neighbourhood, fetched on first use
-    for (int p = qb; p < qe; p++) {
-      const float4 me = sq[p];
-      const int self = __float_as_int(me.w);
-      int base = 0;
-      float thr = inf;
-      if (in_regs) {
-#pragma unroll
-        for (int s = 0; s < CTP_KNN_SLOTS; s++) {
-          if (s < n_slots) {
-            const float ddx = me.x - cand[s].x, ddy = me.y - cand[s].y, ddz = me.z - cand[s].z;
-            const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
-            const int j = __float_as_int(cand[s].w);
-            knn_offer<K>((dd < lb2) & (dd <= thr) & (j != self) & (j >= 0), dd, j, base, thr, keys, lane, lt_mask);
-          }
-        }
-      } else {  // unusually dense neighbourhood: stream the nine runs
-        for (int r = 0; r < 9; r++) {
-          const int b0 = __shfl_sync(full, rb, r), len = __shfl_sync(full, rlen, r);
-          for (int i0 = 0; i0 < len; i0 += 32) {
-            const int i = i0 + lane;
-            bool surv = false;
-            float dd = 0.f;
-            int j = -1;
-            if (i < len) {
-              const float4 o = sq[b0 + i];
-              const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
-              dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
-              j = __float_as_int(o.w);
-              surv = (dd < lb2) & (dd <= thr) & (j != self);
-            }
-            knn_offer<K>(surv, dd, j, base, thr, keys, lane, lt_mask);
-          }
-        }
-      }
-      if (base < K) {
-        // sparse neighbourhood: widen to 5 x 5 x 5 cells; everything within 2 * 0.999 h is in there
-        if (rlen5 < 0) {
-          rlen5 = 0;
-          if (lane < 25) {
-            const int y = cy - 2 + lane % 5, z = cz - 2 + lane / 5;
-            if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
-              const int row = (z * g.dy + y) * g.dx;
-              rb5 = st[row + max(cx - 2, 0)];
-              rlen5 = st[row + min(cx + 2, g.dx - 1) + 1] - rb5;
-            }
-          }
-        }
-        __syncwarp();
-        base = 0;
-        thr = inf;
-        for (int r = 0; r < 25; r++) {
-          const int b0 = __shfl_sync(full, rb5, r), len = __shfl_sync(full, rlen5, r);
-          for (int i0 = 0; i0 < len; i0 += 32) {
-            const int i = i0 + lane;
-            bool surv = false;
-            float dd = 0.f;
-            int j = -1;
-            if (i < len) {
-              const float4 o = sq[b0 + i];
-              const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
-              dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
-              j = __float_as_int(o.w);
-              surv = (dd < wide2) & (dd <= thr) & (j != self);
-            }
-            knn_offer<K>(surv, dd, j, base, thr, keys, lane, lt_mask);
-          }
-        }
-      }
-      if (base < K) {  // fewer than k points within 2h
-        if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)(q * n + p);
-        __syncwarp();
-        continue;
-      }
-      __syncwarp();
-      unsigned long long key = lane < base ? keys[lane] : 0xffffffffffffffffull;
-      __syncwarp();  // the next query overwrites the buffer
-      key = knn_sort32(key, lane);
-      if (lane < K) {
-        idx[(q * n + self) * idx_stride + lane] = (int)(unsigned)key;
-        if (d2out) d2out[(q * n + self) * K + lane] = __uint_as_float((unsigned)(key >> 32));
-      }
-    }
   }
 }
 
@@ -1284,70 +838,6 @@ __global__ void __launch_bounds__(256) k_csr_fill(const int32_t *__restrict__ re
   }
 }
 
-// one thread per row: sort columns ascending (rows are short: staged in a per-thread array),
-// then the FP64 weights ||to - from|| from the double coordinates (:369-371)
-#define CTP_CSR_LOCAL 40
-__global__ void __launch_bounds__(256) k_csr_finish(const double *__restrict__ nodes, int64_t n, int64_t total_rows,
-                                                    const int32_t *__restrict__ row_ptr,
-                                                    const int64_t *__restrict__ nnz_off, int64_t cap,
-                                                    int32_t *__restrict__ col, double *__restrict__ w) {
-  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (row >= total_rows) return;
-  const int64_t q = row / n, i = row - q * n;
-  const int32_t *rp = row_ptr + q * (n + 1);
-  const int64_t b = nnz_off[q] + rp[i], e = nnz_off[q] + rp[i + 1];
-  if (e > cap) return;
-  const int len = (int)(e - b);
-  const double mx = nodes[3 * row], my = nodes[3 * row + 1], mz = nodes[3 * row + 2];
-  const double *nq = nodes + 3 * q * n;
-  if (len <= CTP_CSR_LOCAL) {
-    int32_t c[CTP_CSR_LOCAL];
-#pragma unroll 8
-    for (int a = 0; a < len; a++) c[a] = col[b + a];  // independent loads first
-    for (int a = 1; a < len; a++) {
-      const int32_t key = c[a];
-      int p = a - 1;
-      while (p >= 0 && c[p] > key) {
-        c[p + 1] = c[p];
-        p--;
-      }
-      c[p + 1] = key;
-    }
-#pragma unroll 4
-    for (int a = 0; a < len; a++) {
-      const int32_t cj = c[a];
-      col[b + a] = cj;
-      const double *o = nq + 3 * (int64_t)cj;
-      const double dx = o[0] - mx, dy = o[1] - my, dz = o[2] - mz;
-      w[b + a] = sqrt((dx * dx + dy * dy) + dz * dz);
-    }
-    return;
-  }
-  for (int64_t a = b + 1; a < e; a++) {  // very high in-degree: sort in place
-    const int32_t key = col[a];
-    int64_t p = a - 1;
-    while (p >= b && col[p] > key) {
-      col[p + 1] = col[p];
-      p--;
-    }
-    col[p + 1] = key;
-  }
-  for (int64_t a = b; a < e; a++) {
-    const double *o = nq + 3 * (int64_t)col[a];
-    const double dx = o[0] - mx, dy = o[1] - my, dz = o[2] - mz;
-    w[a] = sqrt((dx * dx + dy * dy) + dz * dz);
-  }
-}
-
-// dense k-NN table (stride k) -> neighbour records (stride NS)
-__global__ void __launch_bounds__(256) k_nbr_to_rec(const int32_t *__restrict__ nbr, int ns, int k, int64_t total_edges,
-                                                    int32_t *__restrict__ rec) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= total_edges) return;
-  const int64_t row = e / k;
-  rec[row * ns + (e - row * k)] = nbr[e];
-}
-
 // one thread per CSR ENTRY (a warp takes 32 consecutive rows and walks their entries in flat order):
 // the entry's final position is its rank among the row's column ids (they are distinct), so the
 // ascending order needs no per-thread sort and every load/store is coalesced; the FP64 weight
@@ -1407,6 +897,15 @@ __global__ void __launch_bounds__(256) k_csr_finish_flat(const double *__restric
       }
     }
   }
+}
+
+// dense k-NN table (stride k) -> neighbour records (stride NS)
+__global__ void __launch_bounds__(256) k_nbr_to_rec(const int32_t *__restrict__ nbr, int ns, int k, int64_t total_edges,
+                                                    int32_t *__restrict__ rec) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= total_edges) return;
+  const int64_t row = e / k;
+  rec[row * ns + (e - row * k)] = nbr[e];
 }
 
 // neighbour records (stride NS) -> dense user-visible k-NN table (stride k)

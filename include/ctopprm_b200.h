@@ -83,7 +83,7 @@ int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int r
 
 /* implementation knobs (defaults are the tuned ones; exposed for benchmarking) */
 #define CTP_TUNE_KNN_PER_CELL 0 /* k-NN grid: expected points inside a ball of one cell size (default 22) */
-#define CTP_TUNE_KNN_TILE 1     /* k-NN search kernel: 2 = warp-per-cell (default), 1 = shared-memory tile, 0 = ring search only */
+#define CTP_TUNE_KNN_TILE 1     /* k-NN search: 1 = direct search with listed wider passes (default), 0 = per-thread ring search only */
 #define CTP_TUNE_PIPE_CHUNK 2   /* queries per chunk of the ctp_sample_multiple copy/compute pipeline (0 = automatic) */
 int ctp_set_tunable(ctp_map *map, int key, double value);
 /* number of kernels this handle has enqueued since the last reset (host-side counter) */
