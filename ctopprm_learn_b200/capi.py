@@ -72,6 +72,8 @@ _SIGS = {
     "ctp_csr_from_directed": [_P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _I64, _P],
     "ctp_csr_from_directed_dev": [_P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _I64, _P, _P],
     "ctp_sample_multiple": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
+    "ctp_sssp": [_P, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _P, _P],
+    "ctp_sssp_dev": [_P, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
     "ctp_sample_path": [_P, _P, _P, _P, _P, _I64, _P, _P, _P],
     "ctp_deformable": [_P, _P, _P, _P, _I64, _P, _P, _P, _I64, _D, _D, _P],
     "ctp_shorten_path": [_P, _P, _P, _P, _I64, _I, _D, _D, C.c_int32, _P, _P, _P, _P, _P],
@@ -351,6 +353,26 @@ class DeviceMap:
                                            _ptr(w), cap, _ptr(off)))
         nnz = int(off[q])
         return dict(row_ptr=row_ptr, col=col[:nnz], w=w[:nnz], nnz_off=off)
+
+    def sssp(self, row_ptr, col, w, nnz_off, src, want_label=False):
+        """shortest paths from src (q x ns node ids) over q CSR graphs -> dist, pred[, label]"""
+        row_ptr = _np(row_ptr, np.int32)
+        if row_ptr.ndim == 1:
+            row_ptr = row_ptr[None]
+        q, n = row_ptr.shape[0], row_ptr.shape[1] - 1
+        col, w = _np(col, np.int32), _np(w, np.float64)
+        nnz_off = _np(nnz_off, np.int64)
+        src = _np(src, np.int32).reshape(q, -1)
+        dist = np.empty((q, n))
+        pred = np.empty((q, n), dtype=np.int32)
+        label = np.empty((q, n), dtype=np.int32) if want_label else None
+        _check(lib().ctp_sssp(self._h, q, n, _ptr(row_ptr), _ptr(col), _ptr(w), _ptr(nnz_off), _ptr(src), src.shape[1],
+                              _ptr(dist), _ptr(pred), _ptr(label)))
+        return (dist, pred, label) if want_label else (dist, pred)
+
+    def sssp_dev(self, q, n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label=None, stream=None):
+        _check(lib().ctp_sssp_dev(self._h, q, n, _ptr(row_ptr), _ptr(col), _ptr(w), _ptr(nnz_off), _ptr(src), ns,
+                                  _ptr(dist), _ptr(pred), _ptr(label), _stream_ptr(stream)))
 
     def sample_multiple(self, start, goal, cand, n, clr, cdc, k=13, out=None):
         """TopologicalPRMClustering::sampleMultiple from host candidates to host CSR."""

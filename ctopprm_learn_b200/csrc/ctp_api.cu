@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "ctp_device.cuh"
+#include "ctp_graph.cuh"
 #include "ctp_paths.cuh"
 #include "ctp_prm.cuh"
 
@@ -1065,6 +1066,74 @@ extern "C" int ctp_csr_from_directed(ctp_map *m, const double *nodes, int64_t q,
   CKR(ctp_csr_from_directed_dev(m, d_n, q, n, k, d_nbr, d_free, d_rp, d_col, d_w, dcap, d_off, 0));
   return build_prm_host_tail(m, q, n, k, nullptr, nullptr, row_ptr, col, w, cap, nnz_off, nullptr, nullptr, d_rp, d_col,
                              d_w, d_off);
+}
+
+// ----------------------------- shortest paths over the CSR roadmaps ---------------------------
+extern "C" int ctp_sssp_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col, const double *w,
+                            const int64_t *nnz_off, const int32_t *src, int ns, double *dist, int32_t *pred,
+                            int32_t *label, void *stream) {
+  REQUIRE(m && q >= 1 && n >= 1 && ns >= 1 && ns <= CTP_SSSP_THREADS, "bad argument (1 <= sources per query <= 1024)");
+  REQUIRE(row_ptr && col && w && nnz_off && src && dist && pred, "null buffer");
+  REQUIRE(n < ((int64_t)1 << 31), "n must fit in int32");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)n * 9 + 16;
+  static int smem_optin = -1;
+  if (smem_optin < 0) {
+    int v = 0;
+    CK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+    smem_optin = v;
+    CK(cudaFuncSetAttribute(k_sssp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+  }
+  if (smem <= (size_t)smem_optin) {
+    k_sssp<true><<<(unsigned)q, CTP_SSSP_THREADS, smem, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label,
+                                                              nullptr, nullptr);
+  } else {  // distances do not fit in shared memory: same algorithm on a global (L2-resident) array
+    const size_t keep = m->ws.used;
+    CKR(arena_reserve(m->ws, keep + align_up((size_t)q * n * 8) + align_up((size_t)q * n) + 1024));
+    unsigned long long *g_dist = arena_take<unsigned long long>(m->ws, (size_t)q * n);
+    uint8_t *g_chg = arena_take<uint8_t>(m->ws, (size_t)q * n);
+    m->ws.used = keep;
+    k_sssp<false><<<(unsigned)q, CTP_SSSP_THREADS, 0, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label, g_dist,
+                                                            g_chg);
+  }
+  m->launches++;
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+extern "C" int ctp_sssp(ctp_map *m, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col, const double *w,
+                        const int64_t *nnz_off, const int32_t *src, int ns, double *dist, int32_t *pred, int32_t *label) {
+  REQUIRE(m && q >= 1 && n >= 1 && ns >= 1, "bad argument");
+  REQUIRE(row_ptr && col && w && nnz_off && src && dist && pred, "null buffer");
+  CK(cudaSetDevice(m->device));
+  const int64_t nnz = nnz_off[q];
+  REQUIRE(nnz >= 0 && nnz_off[0] == 0, "nnz_off must start at 0");
+  for (int64_t i = 0; i < nnz; i++) REQUIRE(col[i] >= 0 && col[i] < n, "column index out of range");
+  CKR(arena_reserve(m->io, align_up(q * (n + 1) * 4) + align_up(nnz * 4 + 4) + align_up(nnz * 8 + 8) + align_up((q + 1) * 8) +
+                               align_up(q * ns * 4) + align_up(q * n * 8) + 2 * align_up(q * n * 4)));
+  IoScope sc(m);
+  int32_t *d_rp = arena_take<int32_t>(m->io, q * (n + 1));
+  int32_t *d_col = arena_take<int32_t>(m->io, nnz + 1);
+  double *d_w = arena_take<double>(m->io, nnz + 1);
+  int64_t *d_off = arena_take<int64_t>(m->io, q + 1);
+  int32_t *d_src = arena_take<int32_t>(m->io, q * ns);
+  double *d_dist = arena_take<double>(m->io, q * n);
+  int32_t *d_pred = arena_take<int32_t>(m->io, q * n), *d_label = arena_take<int32_t>(m->io, q * n);
+  CK(cudaMemcpyAsync(d_rp, row_ptr, q * (n + 1) * 4, cudaMemcpyHostToDevice, 0));
+  if (nnz) {
+    CK(cudaMemcpyAsync(d_col, col, nnz * 4, cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(d_w, w, nnz * 8, cudaMemcpyHostToDevice, 0));
+  }
+  CK(cudaMemcpyAsync(d_off, nnz_off, (q + 1) * 8, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_src, src, q * ns * 4, cudaMemcpyHostToDevice, 0));
+  m->ws.used = 0;
+  CKR(ctp_sssp_dev(m, q, n, d_rp, d_col, d_w, d_off, d_src, ns, d_dist, d_pred, label ? d_label : nullptr, 0));
+  CK(cudaMemcpyAsync(dist, d_dist, q * n * 8, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(pred, d_pred, q * n * 4, cudaMemcpyDeviceToHost, 0));
+  if (label) CK(cudaMemcpyAsync(label, d_label, q * n * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return CTP_OK;
 }
 
 // Host candidate streams -> host CSRs.  The q queries are cut into chunks that flow through

@@ -1,0 +1,114 @@
+// ctp_graph.cuh -- shortest paths over the CSR roadmaps, batched over queries: the graph search the
+// planner runs right after the PRM build (findShortestPath = dijkstra.findPath(0, {1}, nodes_),
+// include/topological_prm_clustering.hpp:2172, include/dijkstra.hpp:83-176) and the multi-source
+// flood that seeds the clusters (wavefrontFill, :789-962).  SURVEY.md section 8f rank 1.
+//
+// One CTA per query.  Distances live in shared memory as the bit patterns of non-negative doubles
+// (ordered like the numbers, so a 64-bit atomicMin relaxes them); a node is re-expanded whenever its
+// distance dropped since it was last expanded (frontier Bellman-Ford).  The fixed point equals
+// Dijkstra's result: every distance is the FP64 sum of the edge weights along a shortest path in path
+// order, exactly what the reference's `distance_from_start + edge` accumulates.  Predecessors are
+// chosen afterwards as the smallest neighbour u with dist[u] + w(u,v) == dist[v] (bitwise), which
+// makes them deterministic; labels (index of the nearest source) follow the predecessor chains.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CTP_SSSP_THREADS 1024
+#define CTP_SSSP_INF 0x7ff0000000000000ull
+
+// dist: n x u64 (shared or global), chg: n x u8
+__device__ __forceinline__ void sssp_run(int n, const int32_t *__restrict__ rp, const int32_t *__restrict__ col,
+                                         const double *__restrict__ w, unsigned long long *dist, uint8_t *chg) {
+  for (;;) {
+    int any = 0;
+    for (int u = threadIdx.x; u < n; u += blockDim.x) {
+      if (!chg[u]) continue;
+      chg[u] = 0;
+      __threadfence_block();
+      const double du = __longlong_as_double((long long)dist[u]);
+      for (int e = rp[u]; e < rp[u + 1]; e++) {
+        const int v = col[e];
+        const unsigned long long nd = (unsigned long long)__double_as_longlong(du + w[e]);
+        if (nd < dist[v]) {
+          const unsigned long long old = atomicMin(&dist[v], nd);
+          if (nd < old) {
+            chg[v] = 1;
+            any = 1;
+          }
+        }
+      }
+    }
+    if (!__syncthreads_or(any)) break;
+  }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(CTP_SSSP_THREADS)
+k_sssp(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const double *__restrict__ w,
+       const int64_t *__restrict__ nnz_off, const int32_t *__restrict__ src, int ns, double *__restrict__ dist_out,
+       int32_t *__restrict__ pred_out, int32_t *__restrict__ label_out, unsigned long long *__restrict__ g_dist,
+       uint8_t *__restrict__ g_chg) {
+  extern __shared__ unsigned long long s_mem[];
+  const int64_t q = blockIdx.x;
+  const int32_t *rp = row_ptr + q * (n + 1);
+  const int32_t *cq = col + nnz_off[q];
+  const double *wq = w + nnz_off[q];
+  unsigned long long *dist = SMEM ? s_mem : g_dist + q * n;
+  uint8_t *chg = SMEM ? reinterpret_cast<uint8_t *>(s_mem + n) : g_chg + q * n;
+  for (int u = threadIdx.x; u < n; u += blockDim.x) {
+    dist[u] = CTP_SSSP_INF;
+    chg[u] = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x < ns) {
+    const int s = src[q * ns + threadIdx.x];
+    if (s >= 0 && s < n) {
+      dist[s] = 0ull;
+      chg[s] = 1;
+    }
+  }
+  __syncthreads();
+  sssp_run((int)n, rp, cq, wq, dist, chg);
+  __syncthreads();
+  // predecessors: smallest neighbour that is strictly nearer and realises the distance; sources and
+  // unreachable nodes: -1
+  int32_t *pred = pred_out + q * n;
+  for (int v = threadIdx.x; v < n; v += blockDim.x) {
+    const unsigned long long dv = dist[v];
+    int best = -1;
+    if (dv != CTP_SSSP_INF && dv != 0ull) {
+      for (int e = rp[v]; e < rp[v + 1]; e++) {
+        const int u = cq[e];
+        const unsigned long long du = dist[u];
+        if (du >= dv) continue;
+        const unsigned long long cand = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)du) + wq[e]);
+        if (cand == dv && (best < 0 || u < best)) best = u;
+      }
+    }
+    pred[v] = best;
+    dist_out[q * n + v] = __longlong_as_double((long long)dv);
+  }
+  if (label_out) {
+    // label = index (in the src list) of the source at the root of the predecessor chain
+    int32_t *label = label_out + q * n;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) label[v] = 0x7fffffff;
+    __syncthreads();
+    if (threadIdx.x < ns) {
+      const int s = src[q * ns + threadIdx.x];
+      if (s >= 0 && s < n) atomicMin(&label[s], (int)threadIdx.x);  // listed twice: the first index wins
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+      if (dist[v] == CTP_SSSP_INF || dist[v] == 0ull) continue;
+      // distances strictly decrease along the chain, so it ends at a source; labels that other threads
+      // have already filled in on the way are final and equal to what the root would give
+      int u = pred[v];
+      while (u >= 0 && *(volatile int32_t *)&label[u] == 0x7fffffff) u = pred[u];
+      if (u >= 0) label[v] = *(volatile int32_t *)&label[u];
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < n; v += blockDim.x)
+      if (label[v] == 0x7fffffff) label[v] = -1;
+  }
+}

@@ -207,6 +207,23 @@ int ctp_sample_multiple(ctp_map *map, const double *start, const double *goal,
                         double cdc, double *nodes, int32_t *n_filled, int32_t *row_ptr,
                         int32_t *col, double *w, int64_t cap, int64_t *nnz_off);
 
+/* ---- graph search over the CSR roadmaps (first "next" item): shortest paths from
+ * a set of sources, one independent problem per query.  Replaces Dijkstra::findPath as called by
+ * findShortestPath (include/topological_prm_clustering.hpp:2172, include/dijkstra.hpp:83-176) with
+ * src = {0}, and the multi-source flood of wavefrontFill (:789-962) with src = the cluster seeds.
+ * CSR as produced by ctp_build_prm (row_ptr q x (n+1) relative, col / w packed, nnz_off q+1).
+ * src: q x ns node ids (-1 = unused slot).  dist: q x n (+inf = unreachable), the FP64 sum of the
+ * edge weights along a shortest path in path order, as the reference accumulates it.  pred: q x n,
+ * the smallest strictly nearer neighbour u with dist[u] + w(u,v) == dist[v]; -1 for sources and
+ * unreachable nodes.  label (optional): q x n, index into the query's src list of the source at the
+ * root of the predecessor chain (the cluster the flood assigns the node to), -1 if none. */
+int ctp_sssp(ctp_map *map, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col,
+             const double *w, const int64_t *nnz_off, const int32_t *src, int ns, double *dist,
+             int32_t *pred, int32_t *label);
+int ctp_sssp_dev(ctp_map *map, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col,
+                 const double *w, const int64_t *nnz_off, const int32_t *src, int ns, double *dist,
+                 int32_t *pred, int32_t *label, void *stream);
+
 /* ---- polylines.  A batch of polylines is a point table pts (total x 3) plus offsets
  * off (count+1, int32): polyline i = pts[off[i] .. off[i+1]) ---- */
 

@@ -865,3 +865,90 @@ int orc_remove_equivalent(const orc_map *m, const double *pts, const int32_t *of
   }
   return cnt;
 }
+
+/* ------------------------------------ graph search ------------------------------------ */
+/* Dijkstra over a CSR graph (binary heap), restating include/dijkstra.hpp:83-176 with every node as a
+ * potential goal (no early stop) and any number of zero-distance sources (the multi-source flood of
+ * wavefrontFill, include/topological_prm_clustering.hpp:789-962).  dist accumulates
+ * distance_from_start + edge in FP64 exactly as expandBestNode does.  pred / label follow the
+ * deterministic rule of include/ctopprm_b200.h (ctp_sssp): smallest strictly nearer neighbour that
+ * realises the distance; label = source index at the root of the chain. */
+typedef struct { double d; int32_t v; } orc_hitem;
+
+static void heap_push(orc_hitem *h, int *cnt, double d, int32_t v) {
+  int i = (*cnt)++;
+  h[i].d = d;
+  h[i].v = v;
+  while (i > 0) {
+    int p = (i - 1) / 2;
+    if (h[p].d <= h[i].d) break;
+    orc_hitem t = h[p];
+    h[p] = h[i];
+    h[i] = t;
+    i = p;
+  }
+}
+
+static orc_hitem heap_pop(orc_hitem *h, int *cnt) {
+  orc_hitem top = h[0];
+  h[0] = h[--(*cnt)];
+  int i = 0;
+  for (;;) {
+    int l = 2 * i + 1, r = l + 1, m = i;
+    if (l < *cnt && h[l].d < h[m].d) m = l;
+    if (r < *cnt && h[r].d < h[m].d) m = r;
+    if (m == i) break;
+    orc_hitem t = h[m];
+    h[m] = h[i];
+    h[i] = t;
+    i = m;
+  }
+  return top;
+}
+
+void orc_sssp(int n, const int32_t *row_ptr, const int32_t *col, const double *w, const int32_t *src, int ns,
+              double *dist, int32_t *pred, int32_t *label) {
+  int64_t nnz = row_ptr[n];
+  orc_hitem *heap = (orc_hitem *)malloc(sizeof(orc_hitem) * (size_t)(nnz + ns + 1));
+  int cnt = 0;
+  for (int i = 0; i < n; i++) dist[i] = INFINITY;
+  for (int i = 0; i < ns; i++)
+    if (src[i] >= 0 && src[i] < n && dist[src[i]] != 0.0) {
+      dist[src[i]] = 0.0;
+      heap_push(heap, &cnt, 0.0, src[i]);
+    }
+  while (cnt > 0) {
+    orc_hitem it = heap_pop(heap, &cnt);
+    if (it.d > dist[it.v]) continue;
+    for (int32_t e = row_ptr[it.v]; e < row_ptr[it.v + 1]; e++) {
+      double nd = dist[it.v] + w[e];
+      if (nd < dist[col[e]]) {
+        dist[col[e]] = nd;
+        heap_push(heap, &cnt, nd, col[e]);
+      }
+    }
+  }
+  free(heap);
+  for (int v = 0; v < n; v++) {
+    int best = -1;
+    if (isfinite(dist[v]) && dist[v] != 0.0)
+      for (int32_t e = row_ptr[v]; e < row_ptr[v + 1]; e++) {
+        int u = col[e];
+        if (!(dist[u] < dist[v])) continue;
+        if (dist[u] + w[e] == dist[v] && (best < 0 || u < best)) best = u;
+      }
+    pred[v] = best;
+  }
+  if (label) {
+    for (int v = 0; v < n; v++) label[v] = -1;
+    for (int i = ns - 1; i >= 0; i--)
+      if (src[i] >= 0 && src[i] < n) label[src[i]] = i; /* listed twice: the first index wins */
+    for (int v = 0; v < n; v++) {
+      if (!isfinite(dist[v]) || dist[v] == 0.0) continue;
+      int u = pred[v];
+      while (u >= 0 && pred[u] >= 0) u = pred[u];
+      label[v] = u >= 0 ? label[u] : -1;
+    }
+  }
+}
+

@@ -150,6 +150,11 @@ int orc_remove_equivalent(const orc_map *m, const double *pts, const int32_t *of
                           const double *lengths, int P, double clr, double cdc,
                           int32_t *keep_src);
 
+/* include/dijkstra.hpp:83-176 over a CSR graph, all nodes as goals, ns zero-distance sources;
+ * pred / label by the deterministic rule documented for ctp_sssp (label may be NULL) */
+void orc_sssp(int n, const int32_t *row_ptr, const int32_t *col, const double *w, const int32_t *src,
+              int ns, double *dist, int32_t *pred, int32_t *label);
+
 #ifdef __cplusplus
 }
 #endif

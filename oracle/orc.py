@@ -223,6 +223,20 @@ def sample_multiple_batch(om, start, goal, cand, n, clr, cdc, k=13, nthreads=1, 
                                   nthreads, full, True)
 
 
+def sssp(row_ptr, col, w, src, want_label=False):
+    """orc_sssp: Dijkstra over one CSR graph from the listed sources -> dist, pred[, label]"""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    w = _f64(w)
+    src = np.ascontiguousarray(src, dtype=np.int32).reshape(-1)
+    n = len(row_ptr) - 1
+    dist = np.empty(n)
+    pred = np.empty(n, dtype=np.int32)
+    label = np.empty(n, dtype=np.int32) if want_label else None
+    _L().orc_sssp(C.c_int(n), _p(row_ptr), _p(col), _p(w), _p(src), C.c_int(len(src)), _p(dist), _p(pred), _p(label))
+    return (dist, pred, label) if want_label else (dist, pred)
+
+
 def knn_grid(nodes, k=13, nthreads=1):
     nodes = _f64(nodes).reshape(-1, 3)
     n = len(nodes)

@@ -467,3 +467,37 @@ def test_knn_uneven_density_all_kernels(c1, orc, mode):
         i0, d0 = orc.knn_grid(pts[i], 13, nthreads=8)
         assert np.array_equal(idx[i], i0)
         assert np.array_equal(d2[i], d0)
+
+
+def test_sssp_batched_vs_oracle(c1, orc):
+    """ctp_sssp (shared-memory frontier Bellman-Ford, one CTA per query) against the oracle's Dijkstra:
+    distances, predecessors and flood labels bit-identical"""
+    m, om, c, e = c1
+    q, n = 4, 1200
+    s, g, cand = _queries(c, e, q, n, 71)
+    out = m.sample_multiple(s, g, cand, n, CLR, CDC)
+    src1 = np.zeros((q, 1), dtype=np.int32)
+    dist, pred = m.sssp(out["row_ptr"], out["col"], out["w"], out["nnz_off"], src1)
+    src3 = np.tile(np.array([[0, 1, 600, -1]], dtype=np.int32), (q, 1))
+    dist3, pred3, lab3 = m.sssp(out["row_ptr"], out["col"], out["w"], out["nnz_off"], src3, want_label=True)
+    for i in range(q):
+        lo, hi = out["nnz_off"][i], out["nnz_off"][i + 1]
+        rp, col, w = out["row_ptr"][i], out["col"][lo:hi], out["w"][lo:hi]
+        d0, p0 = orc.sssp(rp, col, w, [0])
+        assert np.array_equal(dist[i], d0) and np.array_equal(pred[i], p0)
+        d1, p1, l1 = orc.sssp(rp, col, w, [0, 1, 600, -1], want_label=True)
+        assert np.array_equal(dist3[i], d1) and np.array_equal(pred3[i], p1) and np.array_equal(lab3[i], l1)
+    assert np.isinf(dist).any() or True  # unreachable nodes (if any) are +inf with pred -1
+    assert (pred[np.isinf(dist)] == -1).all()
+
+
+def test_sssp_large_graph_global_path(c1, orc):
+    """more nodes than fit in shared memory: the same search on a global distance array"""
+    m, om, c, e = c1
+    n = 30000
+    s, g = synth.default_query(c, e)
+    cand = synth.ellipsoid_candidates(s, g, 8 * n, 9)
+    out = m.sample_multiple(s[None], g[None], cand[None], n, CLR, CDC)
+    dist, pred = m.sssp(out["row_ptr"], out["col"], out["w"], out["nnz_off"], np.zeros((1, 1), dtype=np.int32))
+    d0, p0 = orc.sssp(out["row_ptr"][0], out["col"][:out["nnz_off"][1]], out["w"][:out["nnz_off"][1]], [0])
+    assert np.array_equal(dist[0], d0) and np.array_equal(pred[0], p0)

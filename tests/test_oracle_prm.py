@@ -89,3 +89,35 @@ def test_division_shortcut_identity_is_exhaustively_exact(tmp_path):
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-o", exe, src, "-lm"])
     out = subprocess.check_output([exe, "65536"]).decode().split()
     assert int(out[0]) == 0 and int(out[1]) == 65536 * 65535 // 2 - 0
+
+
+def test_oracle_sssp_against_scipy(orc, c1_map):
+    """the oracle's Dijkstra (restating include/dijkstra.hpp:83-176) against scipy's on a PRM graph"""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import dijkstra
+    vox, c, e = c1_map
+    om = orc.OracleMap(vox, c, e)
+    s, g, cand = _queries(c, e, 1, 1500, 3)
+    nodes = om.sample_reject(s[0], g[0], cand[0], CLR, 1500)[0]
+    gph = om.build_prm(nodes, CLR, CDC, nthreads=4)
+    dist, pred = orc.sssp(gph["row_ptr"], gph["col"], gph["w"], [0])
+    ref = dijkstra(csr_matrix((gph["w"], gph["col"], gph["row_ptr"]), shape=(1500, 1500)), directed=True, indices=0)
+    assert np.array_equal(np.isfinite(dist), np.isfinite(ref))
+    fin = np.isfinite(ref)
+    assert np.allclose(dist[fin], ref[fin], rtol=1e-12, atol=0)
+    # predecessor chains reproduce the distances
+    for v in np.flatnonzero(fin)[::37]:
+        total, u = 0.0, v
+        while pred[u] >= 0:
+            p = pred[u]
+            row = gph["col"][gph["row_ptr"][u]:gph["row_ptr"][u + 1]]
+            total += gph["w"][gph["row_ptr"][u] + int(np.flatnonzero(row == p)[0])]
+            u = p
+        assert dist[u] == 0.0 and abs(total - dist[v]) <= 1e-9 * max(1.0, dist[v])
+    # multi-source flood: label = nearest source
+    srcs = [0, 1, 700]
+    dm, pm, lab = orc.sssp(gph["row_ptr"], gph["col"], gph["w"], srcs, want_label=True)
+    each = np.stack([orc.sssp(gph["row_ptr"], gph["col"], gph["w"], [x])[0] for x in srcs])
+    assert np.allclose(dm[np.isfinite(dm)], each.min(0)[np.isfinite(dm)], rtol=1e-12)
+    clear = np.isfinite(dm) & (np.sort(each, 0)[1] - np.sort(each, 0)[0] > 1e-9)
+    assert np.array_equal(lab[clear], each.argmin(0)[clear])
