@@ -272,6 +272,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="skip the single-query latency leg")
     ap.add_argument("--no-paths", action="store_true", help="skip the shortening / mutual-visibility leg")
+    ap.add_argument("--no-sssp", action="store_true", help="skip the shortest-path leg")
     ap.add_argument("--e2e-steps", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -417,6 +418,47 @@ def main():
             single_graph_ms = None
             print(f"bench.py: CUDA graph capture skipped: {ex}", file=sys.stderr)
 
+    # ---- graph search right after the build: shortest start->goal path of every query, on the device CSR ----
+    sssp_leg = None
+    if not args.no_sssp:
+        src_d = torch.zeros((q, 1), dtype=torch.int32, device=dev)
+        dist_d = torch.zeros((q, n), dtype=torch.float64, device=dev)
+        pred_d = torch.zeros((q, n), dtype=torch.int32, device=dev)
+
+        def sssp_step():
+            dmap.sssp_dev(q, n, row_ptr_d, col_d, w_d, nnz_off_d, src_d, 1, dist_d, pred_d, stream=stream)
+        for _ in range(3):
+            sssp_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(args.steps, 10))
+        e0.record(stream)
+        for _ in range(reps):
+            sssp_step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        sssp_ms = e0.elapsed_time(e1) / reps
+        reach = float(torch.isfinite(dist_d[:, 1]).float().mean().item())
+        sssp_leg = {"ms_per_step": sssp_ms, "queries": q, "ms_per_query_batched": sssp_ms / q,
+                    "goal_reachable_fraction": reach,
+                    "api": "ctp_sssp_dev (one CTA per query, distances in shared memory), CUDA events"}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            # CPU: the oracle's binary-heap Dijkstra (include/dijkstra.hpp:83-176 restated) on the same CSRs
+            from oracle import orc as _orc
+            kq = min(q, 16)
+            rp_h = row_ptr_d[:kq].cpu().numpy()
+            off_h = nnz_off_d[:kq + 1].cpu().numpy()
+            col_h = col_d[:int(off_h[kq])].cpu().numpy()
+            w_h = w_d[:int(off_h[kq])].cpu().numpy()
+            t0 = time.perf_counter()
+            mism = 0
+            for i in range(kq):
+                d0, _ = _orc.sssp(rp_h[i], col_h[off_h[i]:off_h[i + 1]], w_h[off_h[i]:off_h[i + 1]], [0])
+                mism += int(not np.array_equal(d0, dist_d[i].cpu().numpy()))
+            t_cpu = time.perf_counter() - t0
+            sssp_leg["cpu_ms_per_query_single_thread"] = 1e3 * t_cpu / kq
+            sssp_leg["distance_mismatch_queries"] = mism
+
     # ---- clustering-stage batches on the same map: shorten_path and pairwise isDeformablePath ----
     paths_leg = None
     if rank == 0 and not args.no_paths:
@@ -503,7 +545,7 @@ def main():
                            lanes_per_edge=dmap.prm_group()),
             "ms_per_query": {"batched": ms_max / args.steps / q, "single_query_latency": single_ms,
                              "single_query_latency_cuda_graph": single_graph_ms},
-            "paths": paths_leg,
+            "paths": paths_leg, "shortest_path": sssp_leg,
             "lookups_per_s": lookups / (ms_max * 1e-3),
             "stage_ms_per_step": {k_: v / args.steps for k_, v in stage_ms.items()},
             "roofline": {"bound": "hbm", "kernel": "k_edge_flat" if dmap.prm_group() == 1 else "k_edge_march", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -148,6 +148,17 @@ int ctph_planner_shortest(void *p, int32_t *ids, int cap, double *length) {
     if (c < cap) ids[c++] = n->id;
   return (int)r[0].plan.size();
 }
+int ctph_planner_flood(void *p, const int32_t *seeds, int ns, double *dist, int32_t *pred, int32_t *cluster) {
+  std::vector<int> sd(seeds, seeds + ns), pr, cl;
+  std::vector<double> d;
+  PL(p)->floodFromSeeds(sd, d, pr, cl);
+  for (size_t i = 0; i < d.size(); i++) {
+    dist[i] = d[i];
+    pred[i] = pr[i];
+    cluster[i] = cl[i];
+  }
+  return (int)d.size();
+}
 // static shorten_path on a polyline given as points; needs a planner to have been constructed (statics)
 int ctph_shorten_path(const double *pts, int npts, double length, int forward, double *out, int cap, double *out_len) {
   Poly poly(pts, npts);

@@ -116,9 +116,61 @@ template <> void Planner::sampleMultiple(const int num_samples) {
   }
   for (int i = 0; i < n; i++)
     for (int32_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) nodes_[i]->visibility_node_ids[nodes_[col[e]]] = w[e];
+  csr_row_ptr_ = row_ptr;
+  csr_col_.assign(col.begin(), col.begin() + nnz_off[1]);
+  csr_w_.assign(w.begin(), w.begin() + nnz_off[1]);
 }
 
-template <> std::vector<Path> Planner::findShortestPath() { return dijkstra.findPath(0, {1}, nodes_); }
+// findShortestPath (:2172) = dijkstra.findPath(0, {1}, nodes_): on the device over the CSR the PRM build
+// returned (ctp_sssp); distance_from_start / previous_point of every node are filled in as the
+// reference's Dijkstra leaves them for the nodes it settles.
+template <> std::vector<Path> Planner::findShortestPath() {
+  const int n = (int)nodes_.size();
+  if (n < 2 || (int)csr_row_ptr_.size() != n + 1) return dijkstra.findPath(0, {1}, nodes_);
+  ctp_map *h = handleOf(map_, "findShortestPath");
+  std::vector<double> dist((size_t)n);
+  std::vector<int32_t> pred((size_t)n);
+  const int64_t nnz_off[2] = {0, (int64_t)csr_col_.size()};
+  const int32_t src = 0;
+  if (ctp_sssp(h, 1, n, csr_row_ptr_.data(), csr_col_.data(), csr_w_.data(), nnz_off, &src, 1, dist.data(), pred.data(),
+               nullptr) != CTP_OK)
+    die("ctp_sssp");
+  for (int i = 0; i < n; i++) {
+    nodes_[i]->distance_from_start = std::isfinite(dist[i]) ? dist[i] : DBL_MAX;
+    nodes_[i]->previous_point = pred[i] >= 0 ? nodes_[pred[i]] : nullptr;
+  }
+  nodes_[0]->previous_point = nodes_[0];
+  Path p;
+  p.from_id = 0;
+  p.to_id = 1;
+  if (!std::isfinite(dist[1])) {  // no path: length "infinite", empty plan (include/dijkstra.hpp:165-171)
+    p.length = DBL_MAX;
+    return {p};
+  }
+  p.length = dist[1];
+  std::vector<Node *> rev;
+  for (Node *c = nodes_[1]; c != nodes_[0]; c = c->previous_point) rev.push_back(c);
+  rev.push_back(nodes_[0]);
+  p.plan.assign(rev.rbegin(), rev.rend());
+  return {p};
+}
+
+template <>
+void Planner::floodFromSeeds(const std::vector<int> &seed_ids, std::vector<double> &dist, std::vector<int> &pred,
+                             std::vector<int> &cluster) {
+  const int n = (int)nodes_.size();
+  if ((int)csr_row_ptr_.size() != n + 1) throw std::runtime_error("floodFromSeeds: call sampleMultiple first");
+  ctp_map *h = handleOf(map_, "floodFromSeeds");
+  dist.assign((size_t)n, 0.0);
+  std::vector<int32_t> p32((size_t)n), l32((size_t)n), src(seed_ids.begin(), seed_ids.end());
+  const int64_t nnz_off[2] = {0, (int64_t)csr_col_.size()};
+  if (ctp_sssp(h, 1, n, csr_row_ptr_.data(), csr_col_.data(), csr_w_.data(), nnz_off, src.data(), (int)src.size(),
+               dist.data(), p32.data(), l32.data()) != CTP_OK)
+    die("ctp_sssp");
+  pred.assign(p32.begin(), p32.end());
+  cluster.assign(l32.begin(), l32.end());
+  for (int i = 0; i < n; i++) nodes_[i]->cluster_id = cluster[i];
+}
 
 template <> std::vector<V3> Planner::samplePath(std::vector<Node *> path, const double length_tot, const double num_samples) {
   return map_->samplePath(path, length_tot, num_samples);

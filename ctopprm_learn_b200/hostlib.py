@@ -183,6 +183,14 @@ class HostPlanner:
         assert nnz >= 0
         return nodes, row_ptr, col[:nnz], w[:nnz]
 
+    def flood(self, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+        dist = np.empty(self.n)
+        pred = np.empty(self.n, dtype=np.int32)
+        cluster = np.empty(self.n, dtype=np.int32)
+        lib().ctph_planner_flood(self.h, _p(seeds), len(seeds), _p(dist), _p(pred), _p(cluster))
+        return dist, pred, cluster
+
     def shortest(self, cap=4096):
         ids = np.empty(cap, dtype=np.int32)
         length = C.c_double(0)

@@ -29,7 +29,8 @@ template <typename T> struct path_with_length {
 
 template <class T> class Dijkstra {
  public:
-  // shortest paths from graph[start_index] to every graph[goal]; unreachable goals are omitted
+  // shortest paths from graph[start_index] to every graph[goal]; an unreachable goal yields an entry with
+  // an empty plan and length DBL_MAX, as the reference does (:165-171)
   std::vector<path_with_length<T>> findPath(int start_index, std::vector<int> goal_indexes,
                                             std::vector<HeapNode<T> *> &graph) {
     for (auto *n : graph) {
@@ -58,11 +59,15 @@ template <class T> class Dijkstra {
     std::vector<path_with_length<T>> out;
     for (int g : goal_indexes) {
       HeapNode<T> *goal = graph[g];
-      if (goal->previous_point == nullptr) continue;
       path_with_length<T> p;
-      p.length = goal->distance_from_start;
       p.from_id = graph[start_index]->id;
       p.to_id = goal->id;
+      if (goal->previous_point == nullptr) {
+        p.length = DBL_MAX;
+        out.push_back(p);
+        continue;
+      }
+      p.length = goal->distance_from_start;
       std::vector<HeapNode<T> *> rev;
       for (HeapNode<T> *c = goal; c != graph[start_index]; c = c->previous_point) rev.push_back(c);
       rev.push_back(graph[start_index]);

@@ -34,6 +34,10 @@ template <class T> class TopologicalPRMClustering {
   static std::vector<path_with_length<T>> removeTooLongPaths(std::vector<path_with_length<T>> paths);
   static std::vector<path_with_length<T>> removeEquivalentPaths(std::vector<path_with_length<T>> paths);
   std::vector<path_with_length<T>> findShortestPath();
+  // multi-source flood over the roadmap (the core of wavefrontFill, :789-962): for every node the
+  // distance to the nearest seed, the predecessor towards it and the index of that seed
+  void floodFromSeeds(const std::vector<int> &seed_ids, std::vector<double> &dist, std::vector<int> &pred,
+                      std::vector<int> &cluster);
   static std::vector<Vector<3>> samplePath(std::vector<HeapNode<Vector<3>> *> path, const double length_tot,
                                            const double num_samples);
   static std::vector<std::vector<path_with_length<Vector<3>>>> find_geometrical_paths(
@@ -57,6 +61,9 @@ template <class T> class TopologicalPRMClustering {
  private:
   std::vector<HeapNode<T> *> nodes_;
   std::vector<Vector<3>> candidate_stream_;
+  // CSR of the roadmap as sampleMultiple received it from the device (input of the device graph search)
+  std::vector<int32_t> csr_row_ptr_, csr_col_;
+  std::vector<double> csr_w_;
   int num_clusters_, max_clusters_, min_clusters_;
   double min_ratio_;
   double max_path_length_ratio_;

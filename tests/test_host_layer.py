@@ -145,6 +145,17 @@ def test_planner_sample_multiple_from_shared_sample_file(c1_host, orc):
                 dist[v] = d + want["w"][t]
                 heapq.heappush(pq, (dist[v], v))
     assert abs(length - dist[1]) <= 1e-5 * dist[1]
+    # findShortestPath ran on the device (ctp_sssp): identical to the oracle's Dijkstra over the same CSR
+    d0, p0 = orc.sssp(want["row_ptr"], want["col"], want["w"], [0])
+    assert length == d0[1]
+    chain = [1]
+    while chain[-1] != 0:
+        chain.append(int(p0[chain[-1]]))
+    assert np.array_equal(ids, chain[::-1])
+    # multi-source flood (core of wavefrontFill) through the class
+    dist, pred, cluster = pl.flood([0, 1, 500])
+    dm, pm, lm = orc.sssp(want["row_ptr"], want["col"], want["w"], [0, 1, 500], want_label=True)
+    assert np.array_equal(dist, dm) and np.array_equal(pred, pm) and np.array_equal(cluster, lm)
     # shorten_path through the class (static, uses the planner's statics) against the oracle
     path = nodes[ids]
     plen = orc.path_length(path)
