@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--knn-per-cell", type=float, default=0.0)
     ap.add_argument("--knn-ring", action="store_true", help="ring-search k-NN only (no tile kernel)")
     ap.add_argument("--knn-mode", type=int, default=-1, help="0 per-thread ring search, 1 direct search (default)")
+    ap.add_argument("--edge-order", type=int, default=-1, help="1 cell-sorted row order in the edge kernel (default), 0 node order")
     ap.add_argument("--pipe-chunk", type=int, default=0, help="queries per chunk of the e2e copy/compute pipeline")
     ap.add_argument("--cpu-queries", type=int, default=0, help="size of the CPU baseline sample (queries)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -309,6 +310,8 @@ def main():
         dmap.set_prm_group(args.group)
     if args.knn_per_cell:
         dmap.set_tunable(capi.TUNE_KNN_PER_CELL, args.knn_per_cell)
+    if args.edge_order >= 0:
+        dmap.set_tunable(capi.TUNE_EDGE_ORDER, args.edge_order)
     if args.pipe_chunk:
         dmap.set_tunable(capi.TUNE_PIPE_CHUNK, args.pipe_chunk)
     if args.knn_mode >= 0:

@@ -67,6 +67,8 @@ struct ctp_map {
   size_t map_bytes = 0;
   // stage profiling (ctp_profile): pairs of events recorded on the caller's stream
   double knn_per_cell = 22.0;  // expected points inside a ball of one cell size (see k_knn_setup)
+  int edge_order = -1;        // edge kernel walks rows in cell-sorted order (1), node order (0), or decides (-1):
+                              // sorted pays off when the gathers leave the L2 (grid > ~100 MB) or are not texture fetches
   int knn_tile = 1;           // 1 = direct search + listed wider passes + warp ring search, 0 = per-thread ring search only
   unsigned long long launches = 0;  // kernels enqueued by this handle (ctp_launch_counter_read)
   int prm_group = 1;  // ctp_build_prm: 1 = flat lookup-parallel kernel (kNN edges are ~3-12 samples long)
@@ -336,6 +338,9 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
     case CTP_TUNE_KNN_TILE:
       m->knn_tile = value != 0.0;
       return CTP_OK;
+    case CTP_TUNE_EDGE_ORDER:
+      m->edge_order = value < 0 ? -1 : (value != 0.0);
+      return CTP_OK;
     case CTP_TUNE_PIPE_CHUNK:
       REQUIRE(value >= 0 && value <= 65535, "queries per chunk must be in [0, 65535]");
       m->pipe_chunk = (int64_t)value;
@@ -597,7 +602,7 @@ extern "C" int ctp_edge_check_dev(ctp_map *m, const double *a, const double *b, 
   if (cnt == 0) return CTP_OK;
   REQUIRE(a && b && free_out, "null buffer");
   CK(cudaSetDevice(m->device));
-  EdgeSrc S{a, b, nullptr, nullptr, 0, 0, 0, 0};
+  EdgeSrc S{a, b, nullptr, nullptr, 0, 0, 0, 0, nullptr};
   EdgeOut O{free_out, hit, hit_idx, lookups, m->d_lookups};
   return launch_edges(m, group ? group : 16, S, cnt, clr, cdc, mode == CTP_EDGE_GUARDS, O, (cudaStream_t)stream);
 }
@@ -609,7 +614,7 @@ extern "C" int ctp_edge_check_indexed_dev(ctp_map *m, const double *nodes, int64
   if (cnt == 0) return CTP_OK;
   REQUIRE(nodes && from && to && free_out && n_nodes > 0, "null buffer");
   CK(cudaSetDevice(m->device));
-  EdgeSrc S{nodes, nullptr, from, to, n_nodes, 1, 1, 1};
+  EdgeSrc S{nodes, nullptr, from, to, n_nodes, 1, 1, 1, nullptr};
   EdgeOut O{free_out, nullptr, hit_idx, lookups, m->d_lookups};
   return launch_edges(m, group ? group : 1, S, cnt, clr, cdc, 0, O, (cudaStream_t)stream);
 }
@@ -804,7 +809,7 @@ extern "C" int ctp_sample_ellipsoid(ctp_map *m, const double *start, const doubl
 
 // --------------------------------------- k-NN ----------------------------------------------
 static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *idx, int idx_stride,
-                      float *d2, cudaStream_t st) {
+                      float *d2, cudaStream_t st, const float4 **sorted_out = nullptr) {
   const int mc = knn_max_cells(n);
   const int64_t total = q * n;
   KnnGrid *d_grid = arena_take<KnnGrid>(m->ws, q);
@@ -812,6 +817,7 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
   int32_t *d_cell_of = arena_take<int32_t>(m->ws, total);
   int32_t *d_cnt = arena_take<int32_t>(m->ws, (size_t)q * mc);
   int32_t *d_start = arena_take<int32_t>(m->ws, (size_t)q * (mc + 1));
+  if (sorted_out) *sorted_out = d_sorted;
   int32_t *d_fb = arena_take<int32_t>(m->ws, total), *d_fb2 = arena_take<int32_t>(m->ws, total);
   int32_t *d_fbn = arena_take<int32_t>(m->ws, 2);  // [0] ring-search list, [1] direct-search list
   uint8_t *d_fbk = arena_take<uint8_t>(m->ws, total);
@@ -950,15 +956,21 @@ extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int
   int32_t *d_deg = arena_take<int32_t>(m->ws, rows);
   int64_t *d_nnz = arena_take<int64_t>(m->ws, q);
   int32_t *d_coltmp = arena_take<int32_t>(m->ws, 2 * edges);
+  const float4 *d_sorted_keep = nullptr;
   int rc;
   {
     StageSpan span(m, CTP_STAGE_KNN, st);
-    rc = knn_launch(m, nodes, q, n, k, d_rec, ns, nullptr, st);
+    rc = knn_launch(m, nodes, q, n, k, d_rec, ns, nullptr, st, &d_sorted_keep);
   }
+  // the k-NN scratch is dead except for the cell-sorted points, which the edge kernel reads; nothing
+  // below takes from the arena again, so the block stays intact until this call returns
   m->ws.used = keep;
   CKR(rc);
   // the n*k directed checks (:355-397)
-  EdgeSrc S{nodes, nullptr, nullptr, d_rec, n, k, 1, ns};
+  // the flat kernel can walk the rows in the k-NN stage's cell-sorted order (spatial locality of the gathers)
+  const bool use_order = m->edge_order >= 0 ? m->edge_order != 0
+                                            : ((size_t)m->n * m->n * m->n * 4 > ((size_t)100 << 20) || m->active != CTP_L_TEX);
+  EdgeSrc S{nodes, nullptr, nullptr, d_rec, n, k, 1, ns, (m->prm_group == 1 && use_order) ? d_sorted_keep : nullptr};
   EdgeOut O{d_free, nullptr, nullptr, nullptr, m->d_lookups};
   {
     StageSpan span(m, CTP_STAGE_EDGES, st);

@@ -240,7 +240,19 @@ struct EdgeSrc {
   int k;                // neighbours per node when from == NULL
   int indexed;
   int to_stride;        // from == NULL: to[row * to_stride + slot]
+  const float4 *order;  // from == NULL, optional: work item r*k + slot takes the row whose id is order[r].w
+                        // (the k-NN stage's cell-sorted points), so that neighbouring work items march
+                        // through neighbouring voxels; outputs stay indexed by the original edge number
 };
+
+// work item -> edge number (identity unless S.order is set)
+__device__ __forceinline__ int64_t ctp_edge_of_item(const EdgeSrc &S, int64_t item) {
+  if (!S.order) return item;
+  const int64_t r = item / S.k;
+  const int64_t qbase = (r / S.n) * S.n;
+  const int64_t row = qbase + __float_as_int(S.order[r].w);
+  return row * S.k + (item - r * S.k);
+}
 
 struct EdgeOut {
   uint8_t *free_out;
@@ -438,10 +450,11 @@ __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, Edg
   unsigned long long my_lookups = 0;
 
   for (int64_t chunk = (int64_t)blockIdx.x * CTP_FLAT_WARPS + w; chunk < n_chunks; chunk += n_warps) {
-    const int64_t e = (chunk << 5) + lane;
+    const int64_t item = (chunk << 5) + lane;
+    const int64_t e = item < m ? ctp_edge_of_item(S, item) : item;
     double ax = 0, ay = 0, az = 0, vx = 0, vy = 0, vz = 0, npts = 1.0;
     int n_last = 0, state = 3;  // 3 = lane has no edge
-    if (e < m) state = ctp_arm_edge(S, e, guards, cdc, ax, ay, az, vx, vy, vz, npts, n_last);
+    if (item < m) state = ctp_arm_edge(S, e, guards, cdc, ax, ay, az, vx, vy, vz, npts, n_last);
     par[0][lane] = ax; par[1][lane] = ay; par[2][lane] = az;
     par[3][lane] = vx; par[4][lane] = vy; par[5][lane] = vz;
     par[6][lane] = npts;

@@ -1,3 +1,3 @@
 python -m pytest tests -m gpu -q -x --timeout 300 2>&1 | tail -3
-python bench.py --steps 10 --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err; tail -3 gpurun_out/b.err; python tools/bsum.py sssp < gpurun_out/b.json; python -c "
-import json; d=json.load(open('gpurun_out/b.json')); print(json.dumps({k:d[k] for k in ('ms_per_query','shortest_path','cpu_baseline')}, indent=1))"
+for O in 0 1; do for L in tex plain; do python bench.py --steps 10 --layout $L --edge-order $O --no-cpu --no-e2e --no-single --no-paths --no-sssp | python tools/bsum.py order${O}_$L; done; done
+for O in 0 1; do python bench.py --workload C3 --steps 5 --edge-order $O --no-cpu --no-e2e --no-single --no-paths --no-sssp | python tools/bsum.py C3_order$O; done
