@@ -297,29 +297,30 @@ __global__ void __launch_bounds__(256) k_knn_scatter(const float4 *__restrict__ 
   sorted[q * n + pos] = pts[t];
 }
 
+// k best (d2, index) pairs of a thread, ascending; one 64-bit key per pair (the bit pattern of a
+// non-negative float orders like the number, so key order == (distance, index) order)
 template <int K> struct TopK {
-  float d[K];
-  int id[K];
+  unsigned long long key[K];
   __device__ __forceinline__ void init() {
 #pragma unroll
-    for (int s = 0; s < K; s++) { d[s] = __int_as_float(0x7f800000); id[s] = 0x7fffffff; }
+    for (int s = 0; s < K; s++) key[s] = 0x7f8000007fffffffull;  // (+inf, INT_MAX)
   }
   __device__ __forceinline__ void push(float dd, int j) {
-    if (dd < d[K - 1] || (dd == d[K - 1] && j < id[K - 1])) {
-      d[K - 1] = dd;
-      id[K - 1] = j;
+    const unsigned long long k = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)j;
+    if (k < key[K - 1]) {
+      key[K - 1] = k;
 #pragma unroll
       for (int s = K - 1; s > 0; s--) {
-        const bool sw = d[s] < d[s - 1] || (d[s] == d[s - 1] && id[s] < id[s - 1]);
-        const float td = sw ? d[s - 1] : d[s];
-        const int ti = sw ? id[s - 1] : id[s];
-        d[s - 1] = sw ? d[s] : d[s - 1];
-        id[s - 1] = sw ? id[s] : id[s - 1];
-        d[s] = td;
-        id[s] = ti;
+        const bool sw = key[s] < key[s - 1];
+        const unsigned long long lo = sw ? key[s] : key[s - 1], hi = sw ? key[s - 1] : key[s];
+        key[s - 1] = lo;
+        key[s] = hi;
       }
     }
   }
+  __device__ __forceinline__ float d(int s) const { return __uint_as_float((unsigned)(key[s] >> 32)); }
+  __device__ __forceinline__ int id(int s) const { return (int)(unsigned)key[s]; }
+  __device__ __forceinline__ bool full() const { return id(K - 1) != 0x7fffffff; }
 };
 
 // one thread per (cell-sorted) point: expand Chebyshev rings of cells until the k-th best
@@ -371,15 +372,15 @@ __device__ __forceinline__ void knn_ring_search(int64_t t, const float4 *__restr
     // everything outside the visited cube is farther than r*h along some axis (0.1% slack
     // covers float binning round-off); strict '<' so equal-distance ties are never skipped
     const double lb = (double)r * g.h * 0.999;
-    if (best.id[K - 1] != 0x7fffffff && (double)best.d[K - 1] < lb * lb) break;
+    if (best.full() && (double)best.d(K - 1) < lb * lb) break;
   }
   int32_t *oi = idx + (q * n + self) * idx_stride;
 #pragma unroll
-  for (int s = 0; s < K; s++) oi[s] = best.id[s] == 0x7fffffff ? -1 : best.id[s];
+  for (int s = 0; s < K; s++) oi[s] = best.id(s) == 0x7fffffff ? -1 : best.id(s);
   if (d2out) {
     float *od = d2out + (q * n + self) * K;
 #pragma unroll
-    for (int s = 0; s < K; s++) od[s] = best.d[s];
+    for (int s = 0; s < K; s++) od[s] = best.d(s);
   }
 }
 
@@ -471,11 +472,11 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, unsigned lo
   }
   int32_t *oi = idx + (q * n + self) * idx_stride;
 #pragma unroll
-  for (int s2 = 0; s2 < K; s2++) oi[s2] = best.id[s2];
+  for (int s2 = 0; s2 < K; s2++) oi[s2] = best.id(s2);
   if (d2out) {
     float *od = d2out + (q * n + self) * K;
 #pragma unroll
-    for (int s2 = 0; s2 < K; s2++) od[s2] = best.d[s2];
+    for (int s2 = 0; s2 < K; s2++) od[s2] = best.d(s2);
   }
 }
 
