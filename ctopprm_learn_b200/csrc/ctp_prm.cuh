@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
 // whenever at least k survived; sparse points retry once over the 5 x 5 x 5 cells with radius
 // 2 * 0.999 h, and what is still short goes to the ring-search list.
 #define CTP_KNN_DIRECT_THREADS 128
-#define CTP_KNN_DIRECT_KEEP 40
+#define CTP_KNN_DIRECT_KEEP 48
 
 // Passes: 0 = the 3 x 3 x 3 cells with radius 0.999 h; 1, 2 = wider balls for sparse points, only as
 // wide as the density seen so far suggests is needed for ~2k points (kept in a ball of radius lb ->
