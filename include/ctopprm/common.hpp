@@ -19,7 +19,7 @@ typedef double Scalar;
 #ifndef CTOPPRM_QUIET
 #define INFO(x) do { std::cerr << x << std::endl; } while (0)
 #else
-#define INFO(x) do { } while (0)
+#define INFO(x) do { if (false) std::cerr << x; } while (0)
 #endif
 #define INFO_GREEN(x) INFO(x)
 #define INFO_RED(x) INFO(x)
