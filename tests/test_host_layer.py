@@ -220,3 +220,41 @@ def test_fill_random_state_in_ellipse(c1_host):
     assert (np.linalg.norm(a - s, axis=1) + np.linalg.norm(a - g, axis=1) <= two_major * (1 + 1e-12)).all()
     p = m.fill_random_state_in_ellipse(s, g, 1.2, True, 5, 10)
     assert (p[:, 2] == s[2]).all()
+
+
+@pytest.mark.gpu
+def test_example_main_writes_the_reference_csv_outputs(c1_host, tmp_path):
+    """examples/ctopprm_main.cpp: YAML -> ESDFMap::load -> find_geometrical_paths -> the CSVs of src/main.cpp:269-305"""
+    import subprocess
+    from conftest import ROOT
+    m, om, c, e, fn = c1_host
+    exe = str(tmp_path / "ctopprm_main")
+    libdir = os.path.join(ROOT, "ctopprm_learn_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "ctopprm_main.cpp"), "-L" + libdir, "-lctopprm_host", "-lctopprm_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    cfg = tmp_path / "cfg.yaml"
+    cfg.write_text(open(os.path.join(ROOT, "configs", "default.yaml")).read().replace("maps/columns_c1.npy", fn))
+    out = str(tmp_path) + "/out_"
+    # the reference names its metric files <output_folder><config path>method_...csv (src/main.cpp:269-271)
+    r = subprocess.run([exe, "--config", "cfg.yaml", "--output_folder", out], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    assert "number of paths found" in r.stdout
+    tag = out + "cfg.yaml"
+    num = float(open(tag + "method_clustering_num.csv").read().split()[-1])
+    secs = float(open(tag + "method_clustering_time.csv").read().split()[-1])
+    assert num >= 1 and secs > 0
+    lens = [float(x) for x in open(tag + "method_clustering_length.csv").read().split()]
+    assert len(lens) == int(num) and lens == sorted(lens)
+    rows = open(out + "roadmap_clustering_roadmap_shortened_unique_path0_0.csv").read().strip().split("\n")
+    assert all(len(r_.split(",")) == 6 for r_ in rows)
+    first, last = [float(x) for x in rows[0].split(",")[:3]], [float(x) for x in rows[-1].split(",")[3:]]
+    s, g = synth.default_query(c, e)
+    assert np.allclose(first, s, atol=1e-3) and np.allclose(last, g, atol=1e-3)  # 6 significant digits in the CSV
+    # sum of the printed segment lengths ~ reported length (the reference's own invariant, :2463-2473)
+    seg = np.array([[float(x) for x in r_.split(",")] for r_ in rows])
+    assert abs(np.sqrt(((seg[:, 3:] - seg[:, :3]) ** 2).sum(1)).sum() - lens[0]) < 1e-3
+    # a missing map file ends the program the way cnpy does in the reference (uncaught std::runtime_error)
+    r2 = subprocess.run([exe, "--config", "cfg.yaml", "--output_folder", out, "--map", "/nonexistent.npy"], capture_output=True,
+                        text=True, cwd=str(tmp_path))
+    assert r2.returncode != 0 and "Unable to open file" in r2.stderr
