@@ -501,3 +501,66 @@ def test_sssp_large_graph_global_path(c1, orc):
     dist, pred = m.sssp(out["row_ptr"], out["col"], out["w"], out["nnz_off"], np.zeros((1, 1), dtype=np.int32))
     d0, p0 = orc.sssp(out["row_ptr"][0], out["col"][:out["nnz_off"][1]], out["w"][:out["nnz_off"][1]], [0])
     assert np.array_equal(dist[0], d0) and np.array_equal(pred[0], p0)
+
+
+@pytest.fixture(scope="module")
+def c2(orc):
+    vox, c, e = synth.make_config_map("C2")
+    m = capi.DeviceMap(vox, c, e, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX)
+    yield m, orc.OracleMap(vox, c, e), c, e
+    m.close()
+
+
+def test_c2_full_size_queries_vs_oracle(c2):
+    """BASELINE configs[1] at full size (256^3 grid, 10 000 nodes, 130 000 directed checks per query)"""
+    m, om, c, e = c2
+    q, n = 3, 10000
+    s, g, cand = _queries(c, e, q, n, 4)
+    m.set_layout(capi.LAYOUT_TEX)
+    out = m.sample_multiple(s, g, cand, n, CLR, CDC)
+    for i in range(q):
+        n0 = om.sample_reject(s[i], g[i], cand[i], CLR, n)[0]
+        assert np.array_equal(out["nodes"][i], n0)
+        _csr_equal(out, i, om.build_prm(n0, CLR, CDC, nthreads=8))
+
+
+def test_large_roadmap_properties(c2):
+    """100 000 nodes (the node count of configs[2]): properties that do not need the oracle's full run --
+    symmetric adjacency with equal weights, ascending columns, weights = FP64 distances, every listed
+    directed verdict reproduced by the point-wise segment check, k-NN distances ascending and exact"""
+    m, om, c, e = c2
+    n, k = 100000, 13
+    s, g = synth.default_query(c, e)
+    cand = synth.ellipsoid_candidates(s, g, 4 * n, 77)
+    m.set_layout(capi.LAYOUT_TEX)
+    nodes = m.sample_reject(s[None], g[None], cand[None], CLR, n)[0]
+    out = m.build_prm(nodes, CLR, CDC)
+    rp, col, w = out["row_ptr"][0], out["col"], out["w"]
+    assert rp[-1] == len(col)
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    assert (np.diff(col)[np.diff(rows) == 0] > 0).all()          # ascending within a row, no duplicates
+    key = rows.astype(np.int64) * n + col
+    rkey = col.astype(np.int64) * n + rows
+    order = np.argsort(rkey, kind="stable")
+    assert np.array_equal(np.sort(key), rkey[order])              # (i, j) present <=> (j, i) present
+    assert np.array_equal(w[order], w[np.argsort(key, kind="stable")])  # ... with the same weight
+    d = nodes[0][col] - nodes[0][rows]
+    assert np.array_equal(w, np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]))
+    # directed verdicts against the generic point-wise kernel on a sample of edges
+    nbr, fr = out["nbr"][0], out["directed_free"][0]
+    pick = np.random.default_rng(0).integers(0, n * k, 200000)
+    a, b = nodes[0][pick // k], nodes[0][nbr.reshape(-1)[pick]]
+    free = m.edge_check(a, b, CLR, CDC, group=8)[0]
+    assert np.array_equal(free, fr.reshape(-1)[pick])
+    # adjacency = union of the free directed edges
+    want = set(map(tuple, np.stack([np.repeat(np.arange(n), k)[fr.reshape(-1)], nbr.reshape(-1)[fr.reshape(-1)]], 1)))
+    got = set(zip(rows.tolist(), col.tolist()))
+    assert got == want | {(j, i) for i, j in want}
+    # k-NN on a sample of rows against brute force in float32
+    p32 = nodes[0].astype(np.float32)
+    for i in np.random.default_rng(1).integers(0, n, 40):
+        dd = p32[i] - p32
+        d2 = (dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1]) + dd[:, 2] * dd[:, 2]
+        d2[i] = np.inf
+        o = np.lexsort((np.arange(n), d2))[:k]
+        assert np.array_equal(nbr[i], o)
