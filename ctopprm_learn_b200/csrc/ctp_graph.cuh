@@ -27,14 +27,28 @@ __device__ __forceinline__ void sssp_run(int n, const int32_t *__restrict__ rp, 
       chg[u] = 0;
       __threadfence_block();
       const double du = __longlong_as_double((long long)dist[u]);
-      for (int e = rp[u]; e < rp[u + 1]; e++) {
-        const int v = col[e];
-        const unsigned long long nd = (unsigned long long)__double_as_longlong(du + w[e]);
-        if (nd < dist[v]) {
-          const unsigned long long old = atomicMin(&dist[v], nd);
-          if (nd < old) {
-            chg[v] = 1;
-            any = 1;
+      const int eb = rp[u], ee = rp[u + 1];
+      // four edges per step: their (col, w) loads are issued together, the relaxations follow
+      for (int e = eb; e < ee; e += 4) {
+        int vv[4];
+        double ww[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const bool in = e + t < ee;
+          vv[t] = in ? __ldg(col + e + t) : -1;
+          ww[t] = in ? __ldg(w + e + t) : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          if (vv[t] < 0) continue;
+          const int v = vv[t];
+          const unsigned long long nd = (unsigned long long)__double_as_longlong(du + ww[t]);
+          if (nd < dist[v]) {
+            const unsigned long long old = atomicMin(&dist[v], nd);
+            if (nd < old) {
+              chg[v] = 1;
+              any = 1;
+            }
           }
         }
       }
