@@ -498,6 +498,33 @@ def main():
                "api": "ctp_sample_multiple (host candidate streams -> host CSR), wall clock, max over ranks"}
         assert nnz_e == nnz_total, "host-API CSR differs from the device-API CSR"
 
+    # ---- end to end per query: host candidates -> host start->goal paths (PRM build + shortest path) ----
+    e2e_query = None
+    if not args.no_e2e and not args.no_sssp:
+        pcap = 512
+        qout = dict(path_ids=capi.pinned_empty((q, pcap), np.int32), path_xyz=capi.pinned_empty((q, pcap, 3), np.float64),
+                    path_n=capi.pinned_empty((q,), np.int32), length=capi.pinned_empty((q,), np.float64),
+                    n_filled=capi.pinned_empty((q,), np.int32))
+        for _ in range(2):
+            dmap.query_paths(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, path_cap=pcap, out=qout)
+        sync_all()
+        k3 = args.e2e_steps or max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k3):
+            dmap.query_paths(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, path_cap=pcap, out=qout)
+        torch.cuda.synchronize()
+        dtq = time.perf_counter() - t0
+        ttq = torch.tensor([dtq], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ttq, op=dist.ReduceOp.MAX)
+        dtq = float(ttq.item())
+        e2e_query = {"ms_per_query": 1e3 * dtq / k3 / q, "ms_per_step": 1e3 * dtq / k3, "queries_per_step_per_gpu": q,
+                     "edge_checks_per_s": checks_per_step * world * k3 / dtq,
+                     "paths_found_fraction": float((qout["path_n"] > 0).mean()),
+                     "h2d_bytes_per_step": int(cand_h.nbytes + s_h.nbytes + g_h.nbytes),
+                     "d2h_bytes_per_step": int(sum(v.nbytes for v in qout.values())),
+                     "api": "ctp_query_paths (host candidate streams -> host start->goal paths; roadmaps stay on the device)"}
+
     # ---- CPU baseline (rank 0, N = 1): bounded sample of the same queries, all host cores ----
     cpu = None
     parity = None
@@ -548,7 +575,7 @@ def main():
                            lanes_per_edge=dmap.prm_group()),
             "ms_per_query": {"batched": ms_max / args.steps / q, "single_query_latency": single_ms,
                              "single_query_latency_cuda_graph": single_graph_ms},
-            "paths": paths_leg, "shortest_path": sssp_leg,
+            "paths": paths_leg, "shortest_path": sssp_leg, "e2e_query": e2e_query,
             "lookups_per_s": lookups / (ms_max * 1e-3),
             "stage_ms_per_step": {k_: v / args.steps for k_, v in stage_ms.items()},
             "roofline": {"bound": "hbm", "kernel": "k_edge_flat" if dmap.prm_group() == 1 else "k_edge_march", "achieved": achieved, "peak": peak, "unit": "GB/s",

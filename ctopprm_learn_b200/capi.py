@@ -74,6 +74,7 @@ _SIGS = {
     "ctp_sample_multiple": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
     "ctp_sssp": [_P, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "ctp_sssp_dev": [_P, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
+    "ctp_query_paths": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, C.c_int32, _P, _P, _P, _P, _P],
     "ctp_sample_path": [_P, _P, _P, _P, _P, _I64, _P, _P, _P],
     "ctp_deformable": [_P, _P, _P, _P, _I64, _P, _P, _P, _I64, _D, _D, _P],
     "ctp_shorten_path": [_P, _P, _P, _P, _I64, _I, _D, _D, C.c_int32, _P, _P, _P, _P, _P],
@@ -389,6 +390,21 @@ class DeviceMap:
         _check(lib().ctp_sample_multiple(self._h, _ptr(start), _ptr(goal), _ptr(cand), q, m, n, k, clr, cdc,
                                          _ptr(out["nodes"]), _ptr(out["n_filled"]), _ptr(out["row_ptr"]),
                                          _ptr(out["col"]), _ptr(out["w"]), cap, _ptr(out["nnz_off"])))
+        return out
+
+    def query_paths(self, start, goal, cand, n, clr, cdc, k=13, path_cap=512, out=None):
+        """PRM build + shortest start->goal path per query; only the paths come back to the host"""
+        start = _np(start, np.float64).reshape(-1, 3)
+        goal = _np(goal, np.float64).reshape(-1, 3)
+        q = len(start)
+        cand = _np(cand, np.float64).reshape(q, -1, 3)
+        m = cand.shape[1]
+        if out is None:
+            out = dict(path_ids=np.empty((q, path_cap), dtype=np.int32), path_xyz=np.empty((q, path_cap, 3)),
+                       path_n=np.empty(q, dtype=np.int32), length=np.empty(q), n_filled=np.empty(q, dtype=np.int32))
+        _check(lib().ctp_query_paths(self._h, _ptr(start), _ptr(goal), _ptr(cand), q, m, n, k, clr, cdc, path_cap,
+                                     _ptr(out["path_ids"]), _ptr(out["path_xyz"]), _ptr(out["path_n"]),
+                                     _ptr(out["length"]), _ptr(out["n_filled"])))
         return out
 
     @staticmethod

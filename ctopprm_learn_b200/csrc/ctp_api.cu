@@ -1278,4 +1278,92 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
   return CTP_OK;
 }
 
+// PRM build + shortest start->goal path per query, host candidate streams in, host paths out.  Same
+// chunk pipeline as ctp_sample_multiple, but the roadmaps never leave the device: per query only the
+// path (ids, coordinates), its length and the accepted-node count come back.
+extern "C" int ctp_query_paths(ctp_map *m, const double *start, const double *goal, const double *cand, int64_t q,
+                               int64_t cnt, int64_t n, int k, double clr, double cdc, int32_t path_cap, int32_t *path_ids,
+                               double *path_xyz, int32_t *path_n, double *length, int32_t *n_filled) {
+  REQUIRE(m && q >= 1 && n >= 2 && cnt >= 0 && k >= 1 && k <= CTP_KNN_MAXK && path_cap >= 2, "bad argument");
+  REQUIRE(start && goal && cand && path_ids && path_xyz && path_n && length && n_filled, "null buffer");
+  REQUIRE(cdc > 0, "collision_distance_check must be > 0");
+  CK(cudaSetDevice(m->device));
+  CKR(pipe_init(m));
+  // larger chunks than ctp_sample_multiple: the per-query CTAs of the graph search need about a machine's worth of
+  // queries per launch, and there is no large device->host copy to hide
+  int64_t qc = m->pipe_chunk > 0 ? m->pipe_chunk : std::max<int64_t>(1, (16 << 20) / (n * k));
+  qc = std::min<int64_t>(std::min<int64_t>(qc, q), 65535);
+  REQUIRE(qc * n * k < ((int64_t)1 << 31), "n*k too large for one chunk");
+  const int64_t n_chunks = (q + qc - 1) / qc;
+  const int nbuf = n_chunks > 1 ? 2 : 1;
+  const int64_t ecap = 2 * qc * n * k;
+  // inputs and small outputs are double-buffered; the roadmap itself (CSR, distances) is reused chunk after chunk
+  const size_t per = 2 * align_up(qc * 24) + align_up(qc * cnt * 24) + align_up(qc * 4) + align_up(qc * path_cap * 4) +
+                     align_up(qc * path_cap * 24) + align_up(qc * 4) + align_up(qc * 8);
+  const size_t shared = align_up(qc * n * 24) + align_up(qc * 4) + align_up(qc * (n + 1) * 4) + align_up(ecap * 4) +
+                        align_up(ecap * 8) + align_up((qc + 1) * 8) + align_up(qc * n * 8) + align_up(qc * n * 4) +
+                        align_up(qc * 4);
+  CKR(arena_reserve(m->io, nbuf * per + shared + 8192));
+  CKR(ctp_reserve(m, qc, n, cnt, k));
+  IoScope sc(m);
+  struct QBuf { double *d_s, *d_g, *d_c; int32_t *d_nf, *d_pid; double *d_pxyz; int32_t *d_pn; double *d_len; } B[2];
+  for (int i = 0; i < nbuf; i++) {
+    B[i].d_s = arena_take<double>(m->io, qc * 3);
+    B[i].d_g = arena_take<double>(m->io, qc * 3);
+    B[i].d_c = arena_take<double>(m->io, qc * cnt * 3);
+    B[i].d_nf = arena_take<int32_t>(m->io, qc);
+    B[i].d_pid = arena_take<int32_t>(m->io, qc * path_cap);
+    B[i].d_pxyz = arena_take<double>(m->io, qc * path_cap * 3);
+    B[i].d_pn = arena_take<int32_t>(m->io, qc);
+    B[i].d_len = arena_take<double>(m->io, qc);
+  }
+  double *d_n = arena_take<double>(m->io, qc * n * 3);
+  int32_t *d_nu = arena_take<int32_t>(m->io, qc);
+  int32_t *d_rp = arena_take<int32_t>(m->io, qc * (n + 1));
+  int32_t *d_col = arena_take<int32_t>(m->io, ecap);
+  double *d_w = arena_take<double>(m->io, ecap);
+  int64_t *d_off = arena_take<int64_t>(m->io, qc + 1);
+  double *d_dist = arena_take<double>(m->io, qc * n);
+  int32_t *d_pred = arena_take<int32_t>(m->io, qc * n);
+  int32_t *d_src = arena_take<int32_t>(m->io, qc);
+  cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1], s_out = m->pipe_st[2];
+  CK(cudaMemsetAsync(d_src, 0, qc * 4, s_comp));  // every search starts at node 0 (= start, :299-306)
+  for (int64_t c = 0; c < n_chunks; c++) {
+    const int bi = (int)(c % nbuf);
+    const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
+    QBuf &b = B[bi];
+    if (c >= nbuf) CK(cudaStreamWaitEvent(s_in, m->ev_comp[bi], 0));
+    CK(cudaMemcpyAsync(b.d_s, start + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
+    CK(cudaMemcpyAsync(b.d_g, goal + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
+    if (cnt) CK(cudaMemcpyAsync(b.d_c, cand + 3 * q0 * cnt, qn * cnt * 24, cudaMemcpyHostToDevice, s_in));
+    CK(cudaEventRecord(m->ev_in[bi], s_in));
+    CK(cudaStreamWaitEvent(s_comp, m->ev_in[bi], 0));
+    if (c >= nbuf) CK(cudaStreamWaitEvent(s_comp, m->ev_out[bi], 0));
+    m->ws.used = 0;
+    CK(cudaMemsetAsync(d_n, 0, qn * n * 24, s_comp));
+    CKR(ctp_sample_reject_dev(m, b.d_s, b.d_g, b.d_c, qn, cnt, clr, n, d_n, b.d_nf, d_nu, nullptr, s_comp));
+    CKR(ctp_build_prm_dev(m, d_n, qn, n, k, clr, cdc, nullptr, nullptr, d_rp, d_col, d_w, ecap, d_off, s_comp));
+    CKR(ctp_sssp_dev(m, qn, n, d_rp, d_col, d_w, d_off, d_src, 1, d_dist, d_pred, nullptr, s_comp));
+    k_extract_paths<<<(int)((qn + 127) / 128), 128, 0, s_comp>>>(qn, n, d_n, d_dist, d_pred, 0, 1, path_cap, b.d_pid,
+                                                                 b.d_pxyz, b.d_pn, b.d_len);
+    m->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(m->ev_comp[bi], s_comp));
+    CK(cudaStreamWaitEvent(s_out, m->ev_comp[bi], 0));
+    CK(cudaMemcpyAsync(path_ids + q0 * path_cap, b.d_pid, qn * path_cap * 4, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(path_xyz + 3 * q0 * path_cap, b.d_pxyz, qn * path_cap * 24, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(path_n + q0, b.d_pn, qn * 4, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(length + q0, b.d_len, qn * 8, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(n_filled + q0, b.d_nf, qn * 4, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaEventRecord(m->ev_out[bi], s_out));
+  }
+  CK(cudaStreamSynchronize(s_out));
+  CK(cudaStreamSynchronize(s_comp));
+  for (int64_t i = 0; i < q; i++)
+    if (n_filled[i] < n)
+      return fail(CTP_ERR_NEED_CANDIDATES, "query %lld: only %d of %lld nodes accepted (candidate stream exhausted)",
+                  (long long)i, n_filled[i], (long long)n);
+  return CTP_OK;
+}
+
 #include "ctp_paths_api.inl"

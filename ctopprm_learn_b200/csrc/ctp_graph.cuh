@@ -126,3 +126,41 @@ k_sssp(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict
       if (label[v] == 0x7fffffff) label[v] = -1;
   }
 }
+
+// start -> goal path of every query from the predecessor array: node ids (in the query's node
+// numbering) and coordinates, written start first.  path_n = 0 when the goal is unreachable or the
+// path does not fit path_cap.
+__global__ void __launch_bounds__(128) k_extract_paths(int64_t q, int64_t n, const double *__restrict__ nodes,
+                                                       const double *__restrict__ dist, const int32_t *__restrict__ pred,
+                                                       int src_node, int goal_node, int path_cap,
+                                                       int32_t *__restrict__ path_ids, double *__restrict__ path_xyz,
+                                                       int32_t *__restrict__ path_n, double *__restrict__ length) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= q) return;
+  const double d = dist[i * n + goal_node];
+  const int32_t *pr = pred + i * n;
+  length[i] = d;
+  int cnt = 0;
+  if (d < __longlong_as_double(0x7ff0000000000000LL)) {
+    cnt = 1;
+    for (int u = goal_node; u != src_node && cnt <= n; u = pr[u]) {
+      if (pr[u] < 0) { cnt = 0; break; }
+      cnt++;
+    }
+    if (cnt > path_cap) cnt = 0;
+  }
+  path_n[i] = cnt;
+  int32_t *ids = path_ids + i * path_cap;
+  double *xyz = path_xyz + 3 * i * path_cap;
+  int u = goal_node;
+  for (int p = cnt - 1; p >= 0; p--) {
+    ids[p] = u;
+    const double *c = nodes + 3 * (i * n + u);
+    xyz[3 * p] = c[0];
+    xyz[3 * p + 1] = c[1];
+    xyz[3 * p + 2] = c[2];
+    u = p > 0 ? pr[u] : u;
+  }
+  for (int p = cnt; p < path_cap; p++) ids[p] = -1;
+}
+

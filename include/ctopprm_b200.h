@@ -225,6 +225,17 @@ int ctp_sssp_dev(ctp_map *map, int64_t q, int64_t n, const int32_t *row_ptr, con
                  const double *w, const int64_t *nnz_off, const int32_t *src, int ns, double *dist,
                  int32_t *pred, int32_t *label, void *stream);
 
+/* The planner's first two phases in one call (find_geometrical_paths :2558-2572: sampleMultiple, then
+ * findShortestPath), for q independent queries: host candidate streams in, host start->goal paths
+ * out; the roadmaps stay on the device.  path_ids: q x path_cap node ids in the query's own node
+ * numbering (0 = start, 1 = goal, 2.. = accepted candidates in stream order), -1 padded; path_xyz:
+ * q x path_cap x 3 coordinates; path_n[q] = nodes on the path (0 = goal unreachable or path longer
+ * than path_cap); length[q] = its length (+inf if unreachable); n_filled as ctp_sample_multiple. */
+int ctp_query_paths(ctp_map *map, const double *start, const double *goal, const double *cand,
+                    int64_t q, int64_t m, int64_t n, int k, double clr, double cdc, int32_t path_cap,
+                    int32_t *path_ids, double *path_xyz, int32_t *path_n, double *length,
+                    int32_t *n_filled);
+
 /* ---- polylines.  A batch of polylines is a point table pts (total x 3) plus offsets
  * off (count+1, int32): polyline i = pts[off[i] .. off[i+1]) ---- */
 

@@ -564,3 +564,37 @@ def test_large_roadmap_properties(c2):
         d2[i] = np.inf
         o = np.lexsort((np.arange(n), d2))[:k]
         assert np.array_equal(nbr[i], o)
+
+
+@pytest.mark.parametrize("chunk", [0, 2])
+def test_query_paths_end_to_end(c1, orc, chunk):
+    """ctp_query_paths: host candidates -> host start->goal paths, roadmaps stay on the device"""
+    m, om, c, e = c1
+    q, n = 5, 900
+    s, g, cand = _queries(c, e, q, n, 81)
+    s[0], g[0] = synth.default_query(c, e)  # at least one query with start and goal in free space
+    cand[0] = synth.ellipsoid_candidates(s[0], g[0], cand.shape[1], 3)
+    m.set_tunable(capi.TUNE_PIPE_CHUNK, chunk)
+    try:
+        out = m.query_paths(s, g, cand, n, CLR, CDC, path_cap=256)
+    finally:
+        m.set_tunable(capi.TUNE_PIPE_CHUNK, 0)
+    reached = 0
+    for i in range(q):
+        nodes = om.sample_reject(s[i], g[i], cand[i], CLR, n)[0]
+        gph = om.build_prm(nodes, CLR, CDC, nthreads=8)
+        d0, p0 = orc.sssp(gph["row_ptr"], gph["col"], gph["w"], [0])
+        assert out["n_filled"][i] == n
+        if not np.isfinite(d0[1]):
+            assert out["path_n"][i] == 0 and np.isinf(out["length"][i])
+            continue
+        reached += 1
+        chain = [1]
+        while chain[-1] != 0:
+            chain.append(int(p0[chain[-1]]))
+        chain = chain[::-1]
+        k_ = out["path_n"][i]
+        assert out["length"][i] == d0[1] and k_ == len(chain)
+        assert np.array_equal(out["path_ids"][i, :k_], chain) and (out["path_ids"][i, k_:] == -1).all()
+        assert np.array_equal(out["path_xyz"][i, :k_], nodes[chain])
+    assert reached >= 1
