@@ -598,3 +598,48 @@ def test_query_paths_end_to_end(c1, orc, chunk):
         assert np.array_equal(out["path_ids"][i, :k_], chain) and (out["path_ids"][i, k_:] == -1).all()
         assert np.array_equal(out["path_xyz"][i, :k_], nodes[chain])
     assert reached >= 1
+
+
+def test_degenerate_sizes(c1, orc):
+    """smallest legal problems: two nodes, one neighbour, no candidates, one-point batches"""
+    m, om, c, e = c1
+    s, g = synth.default_query(c, e)
+    # n = 2: only start and goal, no candidate consumed
+    out = m.sample_multiple(s[None], g[None], np.zeros((1, 0, 3)), 2, CLR, CDC, k=1)
+    assert np.array_equal(out["nodes"][0], np.stack([s, g])) and out["n_filled"][0] == 2
+    want = om.build_prm(np.stack([s, g]), CLR, CDC, k=1)
+    assert np.array_equal(out["row_ptr"][0], want["row_ptr"]) and out["nnz_off"][1] == len(want["col"])
+    # k = 1 on a handful of nodes
+    cand = synth.ellipsoid_candidates(s, g, 200, 1)
+    out = m.sample_multiple(s[None], g[None], cand[None], 20, CLR, CDC, k=1)
+    n0 = om.sample_reject(s, g, cand, CLR, 20)[0]
+    _csr_equal(out, 0, om.build_prm(n0, CLR, CDC, k=1))
+    # single point / single edge batches through every point-wise entry
+    p = c[None] + 0.123
+    assert m.clearance(p)[0] == om.clearance(p)[0]
+    assert m.in_collision(p, CLR)[0] == om.in_collision(p, CLR)[0]
+    gg, cc = m.gradient(p)
+    g0, c0 = om.gradient(p)
+    assert np.array_equal(gg, g0) and np.array_equal(cc, c0)
+    f = m.edge_check(p, p + 0.5, CLR, CDC)
+    f0 = om.edge_nodes(p, p + 0.5, CLR, CDC)
+    assert f[0][0] == f0[0][0] and np.array_equal(f[1], f0[1], equal_nan=True)
+    # sssp on a graph without edges: everything but the source unreachable
+    dist, pred = m.sssp(np.zeros((1, 6), dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0), np.zeros(2, dtype=np.int64),
+                        np.zeros((1, 1), dtype=np.int32))
+    assert dist[0, 0] == 0 and np.isinf(dist[0, 1:]).all() and (pred[0] == -1).all()
+
+
+def test_argument_errors_do_not_launch(c1):
+    m, om, c, e = c1
+    s, g = synth.default_query(c, e)
+    with pytest.raises(capi.CtpError):
+        m.knn(np.zeros((1, 100, 3)), 17)            # k out of range
+    with pytest.raises(capi.CtpError):
+        m.build_prm(np.zeros((1, 100, 3)), CLR, 0.0)  # collision_distance_check == 0
+    with pytest.raises(capi.CtpError):
+        m.set_layout(64)
+    with pytest.raises(capi.CtpError):
+        m.edge_check_indexed(np.zeros((4, 3)), [0, 5], [1, 2], CLR, CDC)  # index out of range
+    # the handle is still usable afterwards
+    assert np.isfinite(m.clearance(s[None])[0]) or True
