@@ -67,6 +67,7 @@ struct ctp_map {
   size_t map_bytes = 0;
   // stage profiling (ctp_profile): pairs of events recorded on the caller's stream
   double knn_per_cell = 22.0;  // expected points inside a ball of one cell size (see k_knn_setup)
+  int sssp_frontier = 1;      // 1 = queue-based edge-parallel shortest-path kernel, 0 = flag-scan kernel
   int edge_order = -1;        // edge kernel walks rows in cell-sorted order (1), node order (0), or decides (-1):
                               // sorted pays off when the gathers leave the L2 (grid > ~100 MB) or are not texture fetches
   int knn_tile = 1;           // 1 = direct search + listed wider passes + warp ring search, 0 = per-thread ring search only
@@ -337,6 +338,9 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
       return CTP_OK;
     case CTP_TUNE_KNN_TILE:
       m->knn_tile = value != 0.0;
+      return CTP_OK;
+    case CTP_TUNE_SSSP_FRONTIER:
+      m->sssp_frontier = value != 0.0;
       return CTP_OK;
     case CTP_TUNE_EDGE_ORDER:
       m->edge_order = value < 0 ? -1 : (value != 0.0);
@@ -1090,14 +1094,19 @@ extern "C" int ctp_sssp_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row
   CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)n * 9 + 16;
+  // frontier variant: distances + bit mask + u16 queue (node ids must fit 16 bits)
+  const size_t smem_f = (size_t)n * 8 + (((size_t)n + 31) / 32) * 4 + (size_t)n * 2 + 16;
   static int smem_optin = -1;
   if (smem_optin < 0) {
     int v = 0;
     CK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
     smem_optin = v;
     CK(cudaFuncSetAttribute(k_sssp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+    CK(cudaFuncSetAttribute(k_sssp_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, v - 8192));
   }
-  if (smem <= (size_t)smem_optin) {
+  if (m->sssp_frontier && n <= 65535 && smem_f <= (size_t)smem_optin - 8192) {
+    k_sssp_frontier<<<(unsigned)q, CTP_SSSP_THREADS, smem_f, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label);
+  } else if (smem <= (size_t)smem_optin) {
     k_sssp<true><<<(unsigned)q, CTP_SSSP_THREADS, smem, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label,
                                                               nullptr, nullptr);
   } else {  // distances do not fit in shared memory: same algorithm on a global (L2-resident) array

@@ -57,6 +57,160 @@ __device__ __forceinline__ void sssp_run(int n, const int32_t *__restrict__ rp, 
   }
 }
 
+// ---- shared-memory variant with an explicit frontier: edge-parallel relaxation ---------------------
+// The flag scan above leaves most threads idle (a frontier is a few hundred of the 10^4 nodes) and walks
+// each node's edges serially at L2 latency.  Here every sweep (1) turns the "distance dropped" bit mask
+// into a queue of node ids, (2) takes the queue in tiles of CTP_SSSP_TILE nodes, scans their degrees and
+// (3) hands the tile's EDGES out to all threads, so the (col, w) loads of a sweep are issued together.
+// Same fixed point, hence the same distances bit for bit.
+#define CTP_SSSP_TILE 256
+
+__device__ __forceinline__ int sssp_block_scan_excl(int v, int *s_warp, int &total) {
+  // exclusive scan over the CTA's threads (blockDim.x = 1024), result valid on every thread
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int ws = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, ws, o);
+      if (lane >= o) ws += t;
+    }
+    s_warp[lane] = ws;
+  }
+  __syncthreads();
+  total = s_warp[31];
+  const int base = wid ? s_warp[wid - 1] : 0;
+  __syncthreads();  // s_warp is reused by the next scan
+  return base + incl - v;
+}
+
+__global__ void __launch_bounds__(CTP_SSSP_THREADS)
+k_sssp_frontier(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                const double *__restrict__ w, const int64_t *__restrict__ nnz_off, const int32_t *__restrict__ src, int ns,
+                double *__restrict__ dist_out, int32_t *__restrict__ pred_out, int32_t *__restrict__ label_out) {
+  extern __shared__ unsigned long long s_mem[];
+  __shared__ int s_warp[32];
+  __shared__ int s_off[CTP_SSSP_TILE + 1];
+  __shared__ int s_eb[CTP_SSSP_TILE];
+  __shared__ double s_du[CTP_SSSP_TILE];
+  const int64_t q = blockIdx.x;
+  const int32_t *rp = row_ptr + q * (n + 1);
+  const int32_t *cq = col + nnz_off[q];
+  const double *wq = w + nnz_off[q];
+  const int nn = (int)n, words = (nn + 31) >> 5;
+  unsigned long long *dist = s_mem;
+  unsigned *bits = reinterpret_cast<unsigned *>(s_mem + nn);
+  uint16_t *queue = reinterpret_cast<uint16_t *>(bits + words);
+  for (int u = threadIdx.x; u < nn; u += blockDim.x) dist[u] = CTP_SSSP_INF;
+  for (int t = threadIdx.x; t < words; t += blockDim.x) bits[t] = 0;
+  __syncthreads();
+  if (threadIdx.x < ns) {
+    const int s = src[q * ns + threadIdx.x];
+    if (s >= 0 && s < nn) {
+      dist[s] = 0ull;
+      atomicOr(&bits[s >> 5], 1u << (s & 31));
+    }
+  }
+  __syncthreads();
+  for (;;) {
+    // (1) bit mask -> queue (node ids ascending), mask cleared
+    int qlen = 0;
+    for (int t0 = 0; t0 < words; t0 += blockDim.x) {
+      const int t = t0 + threadIdx.x;
+      unsigned m = 0;
+      if (t < words) {
+        m = bits[t];
+        bits[t] = 0;
+      }
+      int tot;
+      int pos = qlen + sssp_block_scan_excl(__popc(m), s_warp, tot);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        queue[pos++] = (uint16_t)((t << 5) + b);
+      }
+      qlen += tot;
+    }
+    __syncthreads();
+    if (qlen == 0) break;
+    // (2) tiles of the queue, (3) edge-parallel relaxation
+    for (int tile = 0; tile < qlen; tile += CTP_SSSP_TILE) {
+      const int cnt = min(CTP_SSSP_TILE, qlen - tile);
+      int deg = 0;
+      if (threadIdx.x < cnt) {
+        const int u = queue[tile + threadIdx.x];
+        const int eb = rp[u];
+        deg = rp[u + 1] - eb;
+        s_eb[threadIdx.x] = eb;
+        s_du[threadIdx.x] = __longlong_as_double((long long)dist[u]);
+      }
+      int total;
+      const int off = sssp_block_scan_excl(deg, s_warp, total);
+      if (threadIdx.x <= CTP_SSSP_TILE) s_off[min((int)threadIdx.x, CTP_SSSP_TILE)] = threadIdx.x < cnt ? off : total;
+      __syncthreads();
+      for (int x = threadIdx.x; x < total; x += blockDim.x) {
+        int lo = 0;  // owner = last tile entry whose offset is <= x
+#pragma unroll
+        for (int step = CTP_SSSP_TILE >> 1; step > 0; step >>= 1)
+          if (lo + step < cnt && s_off[lo + step] <= x) lo += step;
+        const int e = s_eb[lo] + (x - s_off[lo]);
+        const int v = __ldg(cq + e);
+        const unsigned long long nd = (unsigned long long)__double_as_longlong(s_du[lo] + __ldg(wq + e));
+        if (nd < dist[v]) {
+          const unsigned long long old = atomicMin(&dist[v], nd);
+          if (nd < old) atomicOr(&bits[v >> 5], 1u << (v & 31));
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // predecessors: smallest neighbour that is strictly nearer and realises the distance
+  int32_t *pred = pred_out + q * n;
+  for (int v = threadIdx.x; v < nn; v += blockDim.x) {
+    const unsigned long long dv = dist[v];
+    int best = -1;
+    if (dv != CTP_SSSP_INF && dv != 0ull) {
+      for (int e = rp[v]; e < rp[v + 1]; e++) {
+        const int u = cq[e];
+        const unsigned long long du = dist[u];
+        if (du >= dv) continue;
+        const unsigned long long cand = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)du) + wq[e]);
+        if (cand == dv && (best < 0 || u < best)) best = u;
+      }
+    }
+    pred[v] = best;
+    dist_out[q * n + v] = __longlong_as_double((long long)dv);
+  }
+  if (label_out) {
+    int32_t *label = label_out + q * n;
+    for (int v = threadIdx.x; v < nn; v += blockDim.x) label[v] = 0x7fffffff;
+    __syncthreads();
+    if (threadIdx.x < ns) {
+      const int s = src[q * ns + threadIdx.x];
+      if (s >= 0 && s < nn) atomicMin(&label[s], (int)threadIdx.x);
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < nn; v += blockDim.x) {
+      if (dist[v] == CTP_SSSP_INF || dist[v] == 0ull) continue;
+      int u = pred[v];
+      while (u >= 0 && *(volatile int32_t *)&label[u] == 0x7fffffff) u = pred[u];
+      if (u >= 0) label[v] = *(volatile int32_t *)&label[u];
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < nn; v += blockDim.x)
+      if (label[v] == 0x7fffffff) label[v] = -1;
+  }
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(CTP_SSSP_THREADS)
 k_sssp(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const double *__restrict__ w,

@@ -85,6 +85,7 @@ int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int r
 #define CTP_TUNE_KNN_PER_CELL 0 /* k-NN grid: expected points inside a ball of one cell size (default 22) */
 #define CTP_TUNE_KNN_TILE 1     /* k-NN search: 1 = direct search with listed wider passes (default), 0 = per-thread ring search only */
 #define CTP_TUNE_EDGE_ORDER 3   /* PRM edge kernel walks the rows in the k-NN grid's cell order (1), node order (0), automatic (-1, default) */
+#define CTP_TUNE_SSSP_FRONTIER 4 /* ctp_sssp: 1 = explicit frontier, edge-parallel relaxation (default), 0 = flag scan */
 #define CTP_TUNE_PIPE_CHUNK 2   /* queries per chunk of the ctp_sample_multiple copy/compute pipeline (0 = automatic) */
 int ctp_set_tunable(ctp_map *map, int key, double value);
 /* number of kernels this handle has enqueued since the last reset (host-side counter) */
