@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
 // 2 * 0.999 h, and what is still short goes to the ring-search list.
 #define CTP_KNN_DIRECT_THREADS 128
 #define CTP_KNN_DIRECT_KEEP 48
+#define CTP_KNN_SMALL_LIST 8192
 
 // Passes: 0 = the 3 x 3 x 3 cells with radius 0.999 h; 1, 2 = wider balls for sparse points, only as
 // wide as the density seen so far suggests is needed for ~2k points (kept in a ball of radius lb ->
@@ -503,6 +504,13 @@ k_knn_direct_list(const float4 *__restrict__ sorted, int64_t n, const int32_t *_
                   int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
   __shared__ unsigned long long s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
   const int cnt = *count;
+  if (cnt <= CTP_KNN_SMALL_LIST) {
+    // latency regime (a single query lists a few hundred points): one thread per point would walk
+    // ~10^2 cells serially; hand them to the warp-cooperative ring search instead
+    for (int i = blockIdx.x * CTP_KNN_DIRECT_THREADS + threadIdx.x; i < cnt; i += gridDim.x * CTP_KNN_DIRECT_THREADS)
+      fb_list[atomicAdd(fb_count, 1)] = list[i];
+    return;
+  }
   for (int i = blockIdx.x * CTP_KNN_DIRECT_THREADS + threadIdx.x; i < cnt; i += gridDim.x * CTP_KNN_DIRECT_THREADS)
     knn_direct_point<K>(list[i], threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out,
                         pass_lo, 2, list_kept ? list_kept[i] : 0, fb_list, nullptr, fb_count);
