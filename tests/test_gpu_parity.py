@@ -671,3 +671,26 @@ def test_two_phase_candidate_upload(c1, head):
     m.set_tunable(capi.TUNE_PIPE_HEAD, 2.3)
     for key in ("path_ids", "path_n", "length", "n_filled"):
         assert np.array_equal(pout[key], ref[key]), key
+
+
+def test_multi_map_sweep(orc):
+    """BASELINE configs[4] in small: several procedurally generated ESDFs (seeds 100..), one handle and one
+    batch of queries per map, every result against the oracle on the same map"""
+    clr, cdc = CLR, CDC
+    handles = []
+    try:
+        for seed in range(100, 104):
+            vox, c, e = synth.random_columns_esdf(96, 9.6, 30, seed)
+            handles.append((capi.DeviceMap(vox, c, e, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX), orc.OracleMap(vox, c, e), c, e, seed))
+        for m, om, c, e, seed in handles:  # all maps resident at once; batches interleaved map by map
+            q, n = 2, 600
+            s, g = synth.random_queries(c, e, q, seed)
+            cand = np.stack([synth.ellipsoid_candidates(s[i], g[i], 6 * n, seed * 10 + i) for i in range(q)])
+            out = m.sample_multiple(s, g, cand, n, clr, cdc)
+            for i in range(q):
+                n0 = om.sample_reject(s[i], g[i], cand[i], clr, n)[0]
+                assert np.array_equal(out["nodes"][i], n0)
+                _csr_equal(out, i, om.build_prm(n0, clr, cdc, nthreads=8))
+    finally:
+        for h in handles:
+            h[0].close()
