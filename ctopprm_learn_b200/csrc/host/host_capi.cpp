@@ -159,6 +159,27 @@ int ctph_planner_flood(void *p, const int32_t *seeds, int ns, double *dist, int3
   }
   return (int)d.size();
 }
+// isNewHomotopyClassBatch on P (min, max) pairs given as packed polylines (2P polylines: mins then maxes)
+int ctph_new_homotopy_batch(const double *pts, const int32_t *off, const double *lens, int P, uint8_t *out) {
+  std::vector<std::unique_ptr<Poly>> polys;
+  std::vector<Path> mn, mx;
+  for (int i = 0; i < 2 * P; i++) {
+    polys.emplace_back(new Poly(pts + 3 * off[i], off[i + 1] - off[i]));
+    Path p;
+    p.plan = polys.back()->ptrs;
+    p.length = lens[i];
+    (i < P ? mn : mx).push_back(p);
+  }
+  auto r = Planner::isNewHomotopyClassBatch(mn, mx);
+  for (int i = 0; i < P; i++) out[i] = r[i];
+  return P;
+}
+int ctph_planner_seed_accepted(void *p, int candidate_id, const int32_t *seed_ids, int ns) {
+  const auto &ns_ = PL(p)->nodes();
+  std::vector<Node *> seeds;
+  for (int i = 0; i < ns; i++) seeds.push_back(ns_[seed_ids[i]]);
+  return PL(p)->isNewSeedAccepted(ns_[candidate_id], seeds);
+}
 // static shorten_path on a polyline given as points; needs a planner to have been constructed (statics)
 int ctph_shorten_path(const double *pts, int npts, double length, int forward, double *out, int cap, double *out_len) {
   Poly poly(pts, npts);

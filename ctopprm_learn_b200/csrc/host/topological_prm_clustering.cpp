@@ -307,6 +307,52 @@ template <> std::vector<Path> Planner::removeEquivalentPaths(std::vector<Path> p
   return out;
 }
 
+template <>
+std::vector<uint8_t> Planner::isNewHomotopyClassBatch(const std::vector<Path> &min_paths, const std::vector<Path> &max_paths,
+                                                      std::vector<Path> *shortened_min) {
+  if (min_paths.size() != max_paths.size()) throw std::runtime_error("isNewHomotopyClassBatch: size mismatch");
+  const size_t P = min_paths.size();
+  if (P == 0) return {};
+  std::vector<Path> mn = shorten_paths(shorten_paths(min_paths, false), true);   // :1702-1703
+  std::vector<Path> mx = shorten_paths(shorten_paths(max_paths, true), false);   // :1706-1707
+  std::vector<std::vector<Node *>> plans;
+  std::vector<double> lens, num;
+  std::vector<int> ia, ib;
+  for (size_t i = 0; i < P; i++) {
+    plans.push_back(mn[i].plan);
+    lens.push_back(mn[i].length);
+  }
+  for (size_t i = 0; i < P; i++) {
+    plans.push_back(mx[i].plan);
+    lens.push_back(mx[i].length);
+    ia.push_back((int)i);
+    ib.push_back((int)(P + i));
+    const double larger = mn[i].length > mx[i].length ? mn[i].length : mx[i].length;  // std::max (:1711-1712)
+    num.push_back(std::ceil(larger / collision_distance_check_) + 1);
+  }
+  if (shortened_min) *shortened_min = mn;
+  return map_->isDeformablePathBatch(plans, lens, ia, ib, num, min_clearance_, collision_distance_check_);
+}
+
+template <> bool Planner::isNewSeedAccepted(Node *candidate, const std::vector<Node *> &seeds) {
+  // sequential form (:1861-1882): stop at the first seed that is a roadmap neighbour or visible; here all
+  // segment checks go out in one batch and the same decision is read off the verdicts
+  std::vector<V3> a, b;
+  for (Node *sd : seeds) {
+    if (sd->visibility_node_ids.count(candidate) > 0) return false;
+    a.push_back(sd->data);
+    b.push_back(candidate->data);
+  }
+  if (seeds.empty()) return false;
+  const std::vector<uint8_t> free = map_->isSimplePathFreeBetweenNodesBatch(a, b, min_clearance_, collision_distance_check_);
+  int blocked = 0;
+  for (uint8_t f : free) {
+    if (f) return false;
+    blocked++;
+  }
+  return blocked >= 2;
+}
+
 // ---- CSV writers: node rows "x,y,z", edge rows "x0,y0,z0,x1,y1,z1" (:2066-2150; consumer
 // columns_2(...).py:20-33 tells them apart by column count).  Default ostream precision.
 template <> void Planner::saveRoadmapDense(std::string filename) {

@@ -191,6 +191,10 @@ class HostPlanner:
         lib().ctph_planner_flood(self.h, _p(seeds), len(seeds), _p(dist), _p(pred), _p(cluster))
         return dist, pred, cluster
 
+    def seed_accepted(self, candidate_id, seed_ids):
+        seed_ids = np.ascontiguousarray(seed_ids, dtype=np.int32)
+        return bool(lib().ctph_planner_seed_accepted(self.h, int(candidate_id), _p(seed_ids), len(seed_ids)))
+
     def shortest(self, cap=4096):
         ids = np.empty(cap, dtype=np.int32)
         length = C.c_double(0)
@@ -215,6 +219,18 @@ def remove_equivalent(paths, lengths):
     keep = np.empty(len(paths), dtype=np.int32)
     n = lib().ctph_remove_equivalent(_p(pts), _p(off), _p(lengths), len(paths), _p(keep))
     return keep[:n].copy()
+
+
+def new_homotopy_batch(min_paths, max_paths, min_lens, max_lens):
+    paths = list(min_paths) + list(max_paths)
+    off = np.zeros(len(paths) + 1, dtype=np.int32)
+    for i, p in enumerate(paths):
+        off[i + 1] = off[i] + len(p)
+    pts = _f(np.concatenate([np.asarray(p).reshape(-1, 3) for p in paths]))
+    lens = _f(list(min_lens) + list(max_lens))
+    out = np.empty(len(min_paths), dtype=np.uint8)
+    lib().ctph_new_homotopy_batch(_p(pts), _p(off), _p(lens), len(min_paths), _p(out))
+    return out
 
 
 def remove_too_long(lengths):

@@ -34,6 +34,16 @@ template <class T> class TopologicalPRMClustering {
   static std::vector<path_with_length<T>> removeTooLongPaths(std::vector<path_with_length<T>> paths);
   static std::vector<path_with_length<T>> removeEquivalentPaths(std::vector<path_with_length<T>> paths);
   std::vector<path_with_length<T>> findShortestPath();
+  // the decision at the end of isNewHomotopyClass (:1702-1726) for a batch of (min, max) connection path
+  // pairs: shorten min backward then forward, max forward then backward, then isDeformablePath at
+  // ceil(longer / cdc) + 1 connectors.  All pairs share four shorten launches and one deformability launch.
+  // shortened_min (optional) receives the shortened min paths (the reference stores them in min_cluster_paths_).
+  static std::vector<uint8_t> isNewHomotopyClassBatch(const std::vector<path_with_length<T>> &min_paths,
+                                                      const std::vector<path_with_length<T>> &max_paths,
+                                                      std::vector<path_with_length<T>> *shortened_min = nullptr);
+  // the seed test of clusterGraph (:1856-1888): a candidate becomes a new cluster seed iff it is not a roadmap
+  // neighbour of any seed, sees none of them along a straight segment, and there are at least two seeds
+  bool isNewSeedAccepted(HeapNode<T> *candidate, const std::vector<HeapNode<T> *> &seeds);
   // multi-source flood over the roadmap (the core of wavefrontFill, :789-962): for every node the
   // distance to the nearest seed, the predecessor towards it and the index of that seed
   void floodFromSeeds(const std::vector<int> &seed_ids, std::vector<double> &dist, std::vector<int> &pred,

@@ -258,3 +258,64 @@ def test_example_main_writes_the_reference_csv_outputs(c1_host, tmp_path):
     r2 = subprocess.run([exe, "--config", "cfg.yaml", "--output_folder", out, "--map", "/nonexistent.npy"], capture_output=True,
                         text=True, cwd=str(tmp_path))
     assert r2.returncode != 0 and "Unable to open file" in r2.stderr
+
+
+@pytest.mark.gpu
+def test_homotopy_decision_and_seed_test(c1_host, orc):
+    """the tail of isNewHomotopyClass (:1702-1726) and the seed visibility test of clusterGraph (:1856-1888),
+    batched through the C++ layer, against the same composition of oracle functions"""
+    m, om, c, e, fn = c1_host
+    n = 900
+    s, g = synth.default_query(c, e)
+    cand = synth.ellipsoid_candidates(s, g, 5 * n, 23)
+    pl = hostlib.HostPlanner(m, _yaml(fn, n, s, g), s, g)
+    pl.set_candidates(cand)
+    pl.sample_multiple(n)
+    nodes, row_ptr, col, w = pl.graph()
+    # path pairs: shortest paths via two different waypoints (min/max connections of a cluster pair look like this)
+    d0, p0 = orc.sssp(row_ptr, col, w, [0])
+    d1, p1 = orc.sssp(row_ptr, col, w, [1])
+
+    def via(v):
+        a = [v]
+        while a[-1] != 0:
+            a.append(int(p0[a[-1]]))
+        b = [v]
+        while b[-1] != 1:
+            b.append(int(p1[b[-1]]))
+        return nodes[a[::-1] + b[1:]]
+    reach = np.flatnonzero(np.isfinite(d0) & np.isfinite(d1))
+    rng = np.random.default_rng(6)
+    wps = rng.choice(reach[2:], 8, replace=False)
+    mins = [via(int(v)) for v in wps[:4]]
+    maxs = [via(int(v)) for v in wps[4:]]
+    ml = [orc.path_length(p) for p in mins]
+    xl = [orc.path_length(p) for p in maxs]
+    got = hostlib.new_homotopy_batch(mins, maxs, ml, xl)
+    for i in range(4):
+        a, _, la, sa, _ = om.shorten_path(mins[i], ml[i], False, CLR, CDC, cap=1024)
+        a, _, la, sa2, _ = om.shorten_path(a, la, True, CLR, CDC, cap=1024)
+        b, _, lb, sb, _ = om.shorten_path(maxs[i], xl[i], True, CLR, CDC, cap=1024)
+        b, _, lb, sb2, _ = om.shorten_path(b, lb, False, CLR, CDC, cap=1024)
+        k = float(np.ceil(max(la, lb) / CDC) + 1)
+        assert got[i] == om.deformable(a, la, b, lb, k, CLR, CDC)
+    # seed test: candidate accepted iff no seed is a neighbour / visible and there are >= 2 seeds
+    adj = {(r, cc) for r in range(n) for cc in col[row_ptr[r]:row_ptr[r + 1]]}
+    seeds = [int(x) for x in rng.choice(reach[2:], 3, replace=False)]
+    for cand_id in rng.choice(reach[2:], 30, replace=False):
+        cand_id = int(cand_id)
+        if cand_id in seeds:
+            continue
+        want = True
+        blocked = 0
+        for sd in seeds:
+            if (sd, cand_id) in adj:
+                want = False
+                break
+            if om.edge_nodes(nodes[sd][None], nodes[cand_id][None], CLR, CDC)[0][0]:
+                want = False
+                break
+            blocked += 1
+        want = want and blocked >= 2
+        assert pl.seed_accepted(cand_id, seeds) == want
+    pl.close()
