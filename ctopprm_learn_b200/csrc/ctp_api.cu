@@ -579,7 +579,7 @@ static int launch_edges_flat(ctp_map *m, const EdgeSrc &S, int64_t cnt, double c
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_edge_flat<L>, 32 * CTP_FLAT_WARPS, 0));
     occ = o > 0 ? o : 1;
   }
-  const int64_t per_block = 32 * CTP_FLAT_WARPS;
+  const int64_t per_block = CTP_FLAT_EPW * CTP_FLAT_WARPS;
   int64_t blocks = (cnt + per_block - 1) / per_block;
   const int64_t cap = (int64_t)m->sm_count * occ;  // persistent: one resident wave
   if (blocks > cap) blocks = cap;

@@ -432,49 +432,70 @@ __device__ __forceinline__ double ctp_div_small(double a, double b, double rb) {
 #define CTP_FLAT_R 16
 #define CTP_FLAT_WARPS 8
 
+// (64 edges per warp, two per lane: the sample loop then runs ~11 full steps instead of ~5.4 with a
+// partly empty last one)
+#define CTP_FLAT_EPW 64
 template <int L>
 __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, EdgeSrc S, int64_t m, double clr,
                                                                    double cdc, int guards, EdgeOut O) {
-  __shared__ double s_par[CTP_FLAT_WARPS][8][32];
-  __shared__ int s_first[CTP_FLAT_WARPS][32];
-  __shared__ int2 s_ob[CTP_FLAT_WARPS][32];
-  __shared__ uint8_t s_slot[CTP_FLAT_WARPS][32 * CTP_FLAT_R];
+  __shared__ double s_par[CTP_FLAT_WARPS][8][CTP_FLAT_EPW];
+  __shared__ int s_first[CTP_FLAT_WARPS][CTP_FLAT_EPW];
+  __shared__ int2 s_ob[CTP_FLAT_WARPS][CTP_FLAT_EPW];
+  __shared__ uint8_t s_slot[CTP_FLAT_WARPS][CTP_FLAT_EPW * CTP_FLAT_R];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double(*par)[32] = s_par[w];
+  double(*par)[CTP_FLAT_EPW] = s_par[w];
   int *first = s_first[w];
   int2 *ob = s_ob[w];
   uint8_t *slot = s_slot[w];
   const int64_t n_warps = (int64_t)gridDim.x * CTP_FLAT_WARPS;
-  const int64_t n_chunks = (m + 31) >> 5;
+  const int64_t n_chunks = (m + CTP_FLAT_EPW - 1) / CTP_FLAT_EPW;
   unsigned long long my_lookups = 0;
 
   for (int64_t chunk = (int64_t)blockIdx.x * CTP_FLAT_WARPS + w; chunk < n_chunks; chunk += n_warps) {
-    const int64_t item = (chunk << 5) + lane;
-    const int64_t e = item < m ? ctp_edge_of_item(S, item) : item;
-    double ax = 0, ay = 0, az = 0, vx = 0, vy = 0, vz = 0, npts = 1.0;
-    int n_last = 0, state = 3;  // 3 = lane has no edge
-    if (item < m) state = ctp_arm_edge(S, e, guards, cdc, ax, ay, az, vx, vy, vz, npts, n_last);
-    par[0][lane] = ax; par[1][lane] = ay; par[2][lane] = az;
-    par[3][lane] = vx; par[4][lane] = vy; par[5][lane] = vz;
-    par[6][lane] = npts;
-    par[7][lane] = 1.0 / npts;
-    first[lane] = 0x7fffffff;
-    bool alive = state == 0;
-    int base = 1;
+    // lane owns edges `lane` and `lane + 32` of the chunk
+    int64_t e[2];
+    int n_last[2], state[2], base[2];
+    bool alive[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int el = lane + 32 * h;
+      const int64_t item = chunk * CTP_FLAT_EPW + el;
+      e[h] = item < m ? ctp_edge_of_item(S, item) : item;
+      double ax = 0, ay = 0, az = 0, vx = 0, vy = 0, vz = 0, npts = 1.0;
+      n_last[h] = 0;
+      state[h] = 3;  // 3 = no edge
+      if (item < m) state[h] = ctp_arm_edge(S, e[h], guards, cdc, ax, ay, az, vx, vy, vz, npts, n_last[h]);
+      par[0][el] = ax; par[1][el] = ay; par[2][el] = az;
+      par[3][el] = vx; par[4][el] = vy; par[5][el] = vz;
+      par[6][el] = npts;
+      par[7][el] = 1.0 / npts;
+      first[el] = 0x7fffffff;
+      alive[h] = state[h] == 0;
+      base[h] = 1;
+    }
     for (;;) {
-      const int c = alive ? min(CTP_FLAT_R, n_last - base + 1) : 0;
-      int incl = c;
+      int c[2], incl[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        c[h] = alive[h] ? min(CTP_FLAT_R, n_last[h] - base[h] + 1) : 0;
+        incl[h] = c[h];
+      }
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(full, incl, o);
-        if (lane >= o) incl += t;
+        const int t0 = __shfl_up_sync(full, incl[0], o), t1 = __shfl_up_sync(full, incl[1], o);
+        if (lane >= o) { incl[0] += t0; incl[1] += t1; }
       }
-      const int total = __shfl_sync(full, incl, 31);
+      const int tot0 = __shfl_sync(full, incl[0], 31);
+      const int total = tot0 + __shfl_sync(full, incl[1], 31);
       if (total == 0) break;
-      const int off = incl - c;
-      ob[lane] = make_int2(off, base);
-      for (int j = 0; j < c; j++) slot[off + j] = (uint8_t)lane;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int el = lane + 32 * h;
+        const int off = (h ? tot0 : 0) + incl[h] - c[h];
+        ob[el] = make_int2(off, base[h]);
+        for (int j = 0; j < c[h]; j++) slot[off + j] = (uint8_t)el;
+      }
       __syncwarp();
       for (int t = lane; t < total; t += 32) {
         const int el = slot[t];
@@ -487,32 +508,37 @@ __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, Edg
         if (ctp_collides(esdf_clearance<L>(M, px, py, pz), clr)) atomicMin(&first[el], idx);
       }
       __syncwarp();
-      if (alive) {
-        if (first[lane] != 0x7fffffff) alive = false;
-        else {
-          base += c;
-          alive = base <= n_last;
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+        if (alive[h]) {
+          if (first[lane + 32 * h] != 0x7fffffff) alive[h] = false;
+          else {
+            base[h] += c[h];
+            alive[h] = base[h] <= n_last[h];
+          }
         }
-      }
     }
-    if (state != 3) {
-      const int f = first[lane];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      if (state[h] == 3) continue;
+      const int el = lane + 32 * h;
+      const int f = first[el];
       const bool blocked = f != 0x7fffffff;
-      const bool fr = state == 2 ? false : !blocked;
-      O.free_out[e] = fr ? 1 : 0;
+      const bool fr = state[h] == 2 ? false : !blocked;
+      O.free_out[e[h]] = fr ? 1 : 0;
       if (O.hit) {
         double hx = ctp_nan(), hy = ctp_nan(), hz = ctp_nan();
         if (blocked) {
-          const double tt = (double)f / npts;
-          hx = ax + vx * tt;
-          hy = ay + vy * tt;
-          hz = az + vz * tt;
+          const double tt = (double)f / par[6][el];
+          hx = par[0][el] + par[3][el] * tt;
+          hy = par[1][el] + par[4][el] * tt;
+          hz = par[2][el] + par[5][el] * tt;
         }
-        O.hit[3 * e] = hx; O.hit[3 * e + 1] = hy; O.hit[3 * e + 2] = hz;
+        O.hit[3 * e[h]] = hx; O.hit[3 * e[h] + 1] = hy; O.hit[3 * e[h] + 2] = hz;
       }
-      if (O.hit_idx) O.hit_idx[e] = blocked ? f : (state == 2 ? -2 : -1);
-      const int lk = blocked ? f : n_last;
-      if (O.lookups) O.lookups[e] = lk;
+      if (O.hit_idx) O.hit_idx[e[h]] = blocked ? f : (state[h] == 2 ? -2 : -1);
+      const int lk = blocked ? f : n_last[h];
+      if (O.lookups) O.lookups[e[h]] = lk;
       my_lookups += (unsigned)lk;
     }
     __syncwarp();  // the next chunk reuses the warp's shared arrays
