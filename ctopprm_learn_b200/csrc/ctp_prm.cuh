@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
 // for every point and lists the sparse ones with their survivor count; k_knn_direct_list runs the
 // wider passes for the listed points only, so dense points never wait for sparse lanes.
 template <int K>
-__device__ __forceinline__ void knn_direct_point(int64_t t, int tid, unsigned long long (*s_keep)[CTP_KNN_DIRECT_THREADS],
+__device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s_keep)[CTP_KNN_DIRECT_THREADS],
                                                  const float4 *__restrict__ sorted, int64_t n,
                                                  const KnnGrid *__restrict__ grids, int cell_stride,
                                                  const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx,
@@ -449,7 +449,7 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, unsigned lo
           const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
           const int j = __float_as_int(o.w);
           const bool keep = (dd < thr2) & (j != self);
-          if (keep) s_keep[min(kept, CTP_KNN_DIRECT_KEEP - 1)][tid] = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)j;
+          if (keep) s_keep[min(kept, CTP_KNN_DIRECT_KEEP - 1)][tid] = c;  // position in the sorted array; d2 is recomputed below
           kept += keep ? 1 : 0;
         }
       }
@@ -469,8 +469,9 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, unsigned lo
   TopK<K> best;
   best.init();
   for (int u = 0; u < kept; u++) {
-    const unsigned long long key = s_keep[u][tid];
-    best.push(__uint_as_float((unsigned)(key >> 32)), (int)(unsigned)key);
+    const float4 o = __ldg(sq + s_keep[u][tid]);
+    const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+    best.push((ddx * ddx + ddy * ddy) + ddz * ddz, __float_as_int(o.w));
   }
   int32_t *oi = idx + (q * n + self) * idx_stride;
 #pragma unroll
@@ -488,7 +489,7 @@ k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const 
              int cell_stride, const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
              float *__restrict__ d2out, int32_t *__restrict__ fb_list, uint8_t *__restrict__ fb_kept,
              int32_t *__restrict__ fb_count) {
-  __shared__ unsigned long long s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
+  __shared__ int32_t s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
   const int64_t t = blockIdx.x * (int64_t)CTP_KNN_DIRECT_THREADS + threadIdx.x;
   if (t >= total) return;
   knn_direct_point<K>(t, threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out, 0, 0, 0,
@@ -503,7 +504,7 @@ k_knn_direct_list(const float4 *__restrict__ sorted, int64_t n, const int32_t *_
                   const KnnGrid *__restrict__ grids, int cell_stride, const int32_t *__restrict__ cell_start,
                   int32_t *__restrict__ idx, int idx_stride, float *__restrict__ d2out,
                   int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
-  __shared__ unsigned long long s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
+  __shared__ int32_t s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
   const int cnt = *count;
   if (cnt <= CTP_KNN_SMALL_LIST) {
     // latency regime (a single query lists a few hundred points): one thread per point would walk
