@@ -942,14 +942,17 @@ extern "C" int ctp_knn(ctp_map *m, const double *nodes, int64_t q, int64_t n, in
 static int csr_emit(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *d_rec, const uint8_t *d_free,
                     uint8_t *d_flag, int32_t *d_deg, int64_t *d_nnz, int32_t *d_coltmp, int32_t *row_ptr, int32_t *col,
                     double *w, int64_t cap, int64_t *nnz_off, cudaStream_t st) {
+  // 32-byte rows of 16-bit ids for the reverse-edge test when they fit.  They borrow the unsorted-column
+  // scratch: k_csr_degree is their only reader and k_csr_fill, the first writer of that scratch, runs after it.
+  uint16_t *d_rec16 = (n <= 65535 && k <= 14) ? reinterpret_cast<uint16_t *>(d_coltmp) : nullptr;
   const int64_t rows = q * n, edges = rows * k;
   const int ns = csr_ns(k);
   StageSpan span(m, CTP_STAGE_CSR, st);
   const int eb = (int)((edges + 255) / 256), rb = (int)((rows + 255) / 256);
-  k_csr_rowmask<<<rb, 256, 0, st>>>(d_free, k, ns, rows, d_rec, d_deg);
+  k_csr_rowmask<<<rb, 256, 0, st>>>(d_free, k, ns, rows, d_rec, d_deg, d_rec16);
   m->launches++;
-  if (ns == 16) k_csr_degree<16><<<eb, 256, 0, st>>>(d_rec, d_free, n, k, edges, d_flag, d_deg);
-  else k_csr_degree<32><<<eb, 256, 0, st>>>(d_rec, d_free, n, k, edges, d_flag, d_deg);
+  if (ns == 16) k_csr_degree<16><<<eb, 256, 0, st>>>(d_rec, d_rec16, d_free, n, k, edges, d_flag, d_deg);
+  else k_csr_degree<32><<<eb, 256, 0, st>>>(d_rec, nullptr, d_free, n, k, edges, d_flag, d_deg);
   m->launches++;
   k_csr_rowptr<<<(unsigned)q, 1024, 0, st>>>(d_deg, n, row_ptr, d_nnz);
   m->launches++;

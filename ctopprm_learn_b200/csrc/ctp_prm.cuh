@@ -685,15 +685,46 @@ k_knn_ring_warp(const float4 *__restrict__ sorted, int64_t n, const int32_t *__r
 
 __host__ __device__ __forceinline__ int csr_ns(int k) { return k <= 15 ? 16 : 32; }
 
-// free bytes of a row -> mask in the record; out-degree seeds deg[]
+// free bytes of a row -> mask in the record; out-degree seeds deg[].  When every node id fits 16 bits
+// (n <= 65535, k <= 14) the row is also written as a 32-byte record of 16-bit ids (slot 15 = mask, absent
+// neighbours = 0xffff), which halves the gather of the reverse-edge test.
 __global__ void __launch_bounds__(256) k_csr_rowmask(const uint8_t *__restrict__ fr, int k, int ns, int64_t total_rows,
-                                                     int32_t *__restrict__ rec, int32_t *__restrict__ deg) {
+                                                     int32_t *__restrict__ rec, int32_t *__restrict__ deg,
+                                                     uint16_t *__restrict__ rec16) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (row >= total_rows) return;
   unsigned mask = 0;
   for (int s = 0; s < k; s++) mask |= (fr[row * k + s] ? 1u : 0u) << s;
   rec[row * ns + ns - 1] = (int)mask;
   deg[row] = __popc(mask);
+  if (rec16) {
+    unsigned short v[16];
+#pragma unroll
+    for (int s = 0; s < 15; s++) v[s] = s < k ? (unsigned short)rec[row * ns + s] : (unsigned short)0xffff;  // -1 -> 0xffff
+    v[15] = (unsigned short)mask;
+    uint4 lo, hi;
+    lo.x = v[0] | (v[1] << 16); lo.y = v[2] | (v[3] << 16); lo.z = v[4] | (v[5] << 16); lo.w = v[6] | (v[7] << 16);
+    hi.x = v[8] | (v[9] << 16); hi.y = v[10] | (v[11] << 16); hi.z = v[12] | (v[13] << 16); hi.w = v[14] | (v[15] << 16);
+    uint4 *o = reinterpret_cast<uint4 *>(rec16 + row * 16);
+    o[0] = lo;
+    o[1] = hi;
+  }
+}
+
+// does the 32-byte record of row `row` list `target` as a free neighbour?
+__device__ __forceinline__ bool csr_lists_free16(const uint16_t *__restrict__ rec16, int64_t row, int k, int target) {
+  const uint4 *r4 = reinterpret_cast<const uint4 *>(rec16 + row * 16);
+  const uint4 lo = __ldg(r4), hi = __ldg(r4 + 1);
+  const unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  const unsigned mask = w[7] >> 16;
+  const unsigned t = (unsigned)target & 0xffffu;
+  unsigned hit = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    hit |= ((w[i] & 0xffffu) == t ? 1u : 0u) << (2 * i);
+    hit |= ((w[i] >> 16) == t ? 1u : 0u) << (2 * i + 1);
+  }
+  return (hit & mask & ((1u << k) - 1u)) != 0;
 }
 
 template <int NS>
@@ -716,8 +747,8 @@ __device__ __forceinline__ bool csr_lists_free(const int32_t *__restrict__ rec, 
 // per directed edge: flag 0 = blocked, 1 = free and the reverse edge is listed free as well,
 // 2 = free and the reverse is not (row j gets the extra entry i)
 template <int NS>
-__global__ void __launch_bounds__(256) k_csr_degree(const int32_t *__restrict__ rec, const uint8_t *__restrict__ fr,
-                                                    int64_t n, int k, int64_t total_edges,
+__global__ void __launch_bounds__(256) k_csr_degree(const int32_t *__restrict__ rec, const uint16_t *__restrict__ rec16,
+                                                    const uint8_t *__restrict__ fr, int64_t n, int k, int64_t total_edges,
                                                     uint8_t *__restrict__ flag, int32_t *__restrict__ deg) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= total_edges) return;
@@ -729,7 +760,7 @@ __global__ void __launch_bounds__(256) k_csr_degree(const int32_t *__restrict__ 
   const int slot = (int)(e - row * k);
   const int64_t qbase = (row / n) * n;
   const int i = (int)(row - qbase), j = rec[row * NS + slot];
-  const bool rev = csr_lists_free<NS>(rec, qbase + j, k, i);
+  const bool rev = rec16 ? csr_lists_free16(rec16, qbase + j, k, i) : csr_lists_free<NS>(rec, qbase + j, k, i);
   flag[e] = rev ? 1 : 2;
   if (!rev) atomicAdd(deg + qbase + j, 1);
 }
