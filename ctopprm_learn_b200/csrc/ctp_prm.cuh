@@ -434,7 +434,7 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s
   bool done = false;
   for (int pass = pass_lo; pass <= pass_hi; pass++) {
     const float grow = pass == 0 ? 1.f : fminf((float)(pass + 1), cbrtf((float)(2 * K) / (float)max(kept_prev, 1)));
-    const int R = pass == 0 ? 1 : (grow > 2.f ? 3 : 2);
+    const int R = (pass == 0 || grow <= 1.f) ? 1 : (grow > 2.f ? 3 : 2);  // overflowed points shrink: 27 cells suffice
     const float wide = grow * lb;
     const float thr2 = wide * wide;
     kept = 0;
