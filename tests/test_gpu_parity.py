@@ -694,3 +694,73 @@ def test_multi_map_sweep(orc):
     finally:
         for h in handles:
             h[0].close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_differential(orc, seed):
+    """random map size / extents / clearance / step / k / node count / layout: whole sampleMultiple, the
+    generic segment check, gradients, shortest paths and one shorten + deformability round against the oracle"""
+    rng = np.random.default_rng(1000 + seed)
+    nvox = int(rng.integers(24, 90))
+    extent = float(rng.uniform(2.0, 9.0))
+    vox, c, e = synth.random_columns_esdf(nvox, extent, int(rng.integers(3, 25)), seed)
+    vox = (vox + 0.01 * rng.standard_normal(vox.shape)).astype(np.float32)
+    if seed % 3 == 0:
+        e = e * np.array([1.0, rng.uniform(0.6, 1.0), rng.uniform(0.5, 1.0)])  # non-cubic extents (bound test vs index scaling)
+    clr = float(rng.choice([0.0, 0.05, 0.1, 0.2, -0.3]))
+    cdc = float(rng.choice([0.02, 0.05, 0.11, 0.3]))
+    k = int(rng.choice([1, 4, 13, 15, 16]))
+    n = int(rng.integers(k + 40, 700))
+    layout = [capi.LAYOUT_PLAIN, capi.LAYOUT_CELL8, capi.LAYOUT_TEX, capi.LAYOUT_BRICK][seed % 4]
+    m = capi.DeviceMap(vox, c, e, layouts=capi.LAYOUT_PLAIN | layout)
+    om = orc.OracleMap(vox, c, e)
+    try:
+        m.set_layout(layout)
+        q = 2
+        s = c + (rng.random((q, 3)) - 0.5) * e * 0.7
+        g = c + (rng.random((q, 3)) - 0.5) * e * 0.7
+        if seed % 4 == 1:
+            s[:, 2] = g[:, 2] = c[2] + 0.0137  # planar queries
+        cand = np.stack([synth.ellipsoid_candidates(s[i], g[i], 40 * n, seed * 7 + i, ratio=1.3, planar=(seed % 4 == 1))
+                         for i in range(q)])
+        try:
+            out = m.sample_multiple(s, g, cand, n, clr, cdc, k=k)
+        except capi.CtpError as ex:  # very cluttered random map: both sides must agree that the stream ran out
+            assert ex.code == capi.ERR_NEED_CANDIDATES
+            assert any(om.sample_reject(s[i], g[i], cand[i], clr, n)[1] < n for i in range(q))
+            return
+        for i in range(q):
+            n0 = om.sample_reject(s[i], g[i], cand[i], clr, n)[0]
+            assert np.array_equal(out["nodes"][i], n0)
+            want = om.build_prm(n0, clr, cdc, k=k, nthreads=4)
+            _csr_equal(out, i, want)
+            d0, p0 = orc.sssp(want["row_ptr"], want["col"], want["w"], [0])
+            lo, hi = out["nnz_off"][i], out["nnz_off"][i + 1]
+            dist, pred = m.sssp(out["row_ptr"][i], out["col"][lo:hi], out["w"][lo:hi], np.array([0, hi - lo]), [[0]])
+            assert np.array_equal(dist[0], d0) and np.array_equal(pred[0], p0)
+            if np.isfinite(d0[1]):
+                chain = [1]
+                while chain[-1] != 0:
+                    chain.append(int(p0[chain[-1]]))
+                path = n0[chain[::-1]]
+                plen = orc.path_length(path)
+                for forward in (True, False):
+                    gp, go, gl, gs = m.shorten_path([path], [plen], forward, clr, cdc, cap=len(path) + 200)
+                    wp, wo, wl, ws, _ = om.shorten_path(path, plen, forward, clr, cdc, cap=len(path) + 200)
+                    assert gs[0] == ws and np.array_equal(gp[0], wp) and gl[0] == wl
+                nc = float(np.ceil(max(plen, gl[0]) / cdc) + 1)
+                assert m.deformable([path, gp[0]], [plen, gl[0]], [0], [1], [nc], clr, cdc)[0] == \
+                    om.deformable(path, plen, gp[0], gl[0], nc, clr, cdc)
+        a, b = synth.random_edges(c, e, 3000, seed, lo=0.0, hi=extent * 0.7)
+        for grp in (0, 1, 8):
+            f, h, hi_, lk = m.edge_check(a, b, clr, cdc, group=grp)
+            f0, h0, hi0, lk0, _ = om.edge_nodes(a, b, clr, cdc, nthreads=4)
+            assert np.array_equal(f, f0) and np.array_equal(h, h0, equal_nan=True) and np.array_equal(hi_, hi0)
+            assert np.array_equal(lk, lk0)
+        p = c + (rng.random((2000, 3)) - 0.5) * (e + 0.3)
+        assert np.array_equal(m.clearance(p), om.clearance(p), equal_nan=True)
+        gg, cc = m.gradient(p[:500])
+        g0, c0 = om.gradient(p[:500])
+        assert np.array_equal(gg, g0, equal_nan=True) and np.array_equal(cc, c0, equal_nan=True)
+    finally:
+        m.close()
