@@ -1299,7 +1299,12 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
   int64_t qc = m->pipe_chunk > 0 ? m->pipe_chunk : std::max<int64_t>(1, (8 << 20) / (n * k));
   qc = std::min<int64_t>(std::min<int64_t>(qc, q), 65535);
   REQUIRE(qc * n * k < ((int64_t)1 << 31), "n*k too large for one chunk");
-  const int64_t n_chunks = (q + qc - 1) / qc;
+  // chunk boundaries: a short first chunk gets the device->host stream going early, the rest are qc long
+  std::vector<int64_t> cs;  // chunk c covers queries [cs[c], cs[c+1])
+  cs.push_back(0);
+  if (q > qc) cs.push_back(std::max<int64_t>(1, qc / 4));
+  while (cs.back() < q) cs.push_back(std::min<int64_t>(q, cs.back() + qc));
+  const int64_t n_chunks = (int64_t)cs.size() - 1;
   const int nbuf = n_chunks > 1 ? 2 : 1;
   const int64_t head = pipe_head(m, n, cnt);
   const int64_t ecap = 2 * qc * n * k;  // CSR entries a chunk can produce
@@ -1330,7 +1335,7 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
   // last part of a chunk: once its offsets are on the host, copy exactly nnz col/w entries out
   auto finish = [&](int64_t c) -> int {
     const int bi = (int)(c % nbuf);
-    const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
+    const int64_t q0 = cs[c], qn = cs[c + 1] - q0;
     CK(cudaEventSynchronize(m->ev_small[bi]));
     const int64_t *ho = m->h_off + (size_t)bi * (qc + 1);
     const int64_t nnz = ho[qn];
@@ -1350,7 +1355,7 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
   // stage B of chunk c: (refill,) build, fixed-size outputs; the previous chunk's col/w leave first
   auto stage_b = [&](int64_t c) -> int {
     const int bi = (int)(c % nbuf);
-    const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
+    const int64_t q0 = cs[c], qn = cs[c + 1] - q0;
     CKR(pipe_stage_b_refill(m, F[bi], bi, cand, q0, qn, cnt, head, n, clr, m->h_nf + (size_t)bi * qc));
     CKR(ctp_build_prm_dev(m, F[bi].d_n, qn, n, k, clr, cdc, nullptr, nullptr, B[bi].d_rp, B[bi].d_col, B[bi].d_w, ecap,
                           B[bi].d_off, s_comp));
@@ -1371,7 +1376,7 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
     if (c >= 1) CKR(stage_b(c - 1));
     if (c < n_chunks) {
       const int bi = (int)(c % nbuf);
-      const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
+      const int64_t q0 = cs[c], qn = cs[c + 1] - q0;
       CKR(pipe_stage_a(m, F[bi], bi, start, goal, cand, q0, qn, cnt, head, n, clr, c >= nbuf, m->h_nf + (size_t)bi * qc));
     }
   }
