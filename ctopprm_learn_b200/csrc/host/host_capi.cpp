@@ -148,6 +148,10 @@ int ctph_planner_shortest(void *p, int32_t *ids, int cap, double *length) {
     if (c < cap) ids[c++] = n->id;
   return (int)r[0].plan.size();
 }
+void ctph_planner_save_roadmaps(void *p, const char *dense_file, const char *csr_file) {
+  PL(p)->saveRoadmapDense(dense_file);
+  PL(p)->saveRoadmapFromCSR(csr_file);
+}
 int ctph_planner_flood(void *p, const int32_t *seeds, int ns, double *dist, int32_t *pred, int32_t *cluster) {
   std::vector<int> sd(seeds, seeds + ns), pr, cl;
   std::vector<double> d;

@@ -365,6 +365,18 @@ template <> void Planner::saveRoadmapDense(std::string filename) {
         << nb.first->data(2) << std::endl;
 }
 
+template <>
+void Planner::saveRoadmapCSR(std::string filename, const double *nodes, int n, const int32_t *row_ptr, const int32_t *col) {
+  std::ofstream f(filename);
+  if (!f.is_open()) return;
+  for (int i = 0; i < n; i++) f << nodes[3 * i] << "," << nodes[3 * i + 1] << "," << nodes[3 * i + 2] << std::endl;
+  for (int i = 0; i < n; i++)
+    for (int32_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
+      const double *a = nodes + 3 * i, *b = nodes + 3 * col[e];
+      f << a[0] << "," << a[1] << "," << a[2] << "," << b[0] << "," << b[1] << "," << b[2] << std::endl;
+    }
+}
+
 template <> void Planner::savePath(std::string filename, std::vector<Node *> path) {
   std::ofstream f(filename);
   if (!f.is_open()) return;

@@ -183,6 +183,9 @@ class HostPlanner:
         assert nnz >= 0
         return nodes, row_ptr, col[:nnz], w[:nnz]
 
+    def save_roadmaps(self, dense_file, csr_file):
+        lib().ctph_planner_save_roadmaps(self.h, dense_file.encode(), csr_file.encode())
+
     def flood(self, seeds):
         seeds = np.ascontiguousarray(seeds, dtype=np.int32)
         dist = np.empty(self.n)

@@ -27,6 +27,14 @@ template <class T> class TopologicalPRMClustering {
   void setBorders(Vector<3> min_position, Vector<3> max_position);
   void saveRoadmapDense(std::string filename);
   static void savePath(std::string filename, std::vector<HeapNode<T> *> path);
+  // the same file as saveRoadmapDense, written straight from the CSR the device handed back (no pointer graph):
+  // n node rows "x,y,z", then one 6-column edge row per CSR entry
+  static void saveRoadmapCSR(std::string filename, const double *nodes, int n, const int32_t *row_ptr, const int32_t *col);
+  void saveRoadmapFromCSR(std::string filename) {
+    std::vector<double> xyz;
+    for (auto *nd : nodes_) xyz.insert(xyz.end(), nd->data.data(), nd->data.data() + 3);
+    saveRoadmapCSR(filename, xyz.data(), (int)nodes_.size(), csr_row_ptr_.data(), csr_col_.data());
+  }
   static void savePathSamples(std::string filename, std::vector<T> path);
   static path_with_length<T> shorten_path(path_with_length<T> path, bool forward = true);
   // batched form: all paths in one launch (one CTA per polyline)

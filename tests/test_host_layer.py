@@ -152,6 +152,14 @@ def test_planner_sample_multiple_from_shared_sample_file(c1_host, orc):
     while chain[-1] != 0:
         chain.append(int(p0[chain[-1]]))
     assert np.array_equal(ids, chain[::-1])
+    # roadmap CSV from the pointer graph and straight from the CSR: same node rows, same set of edge rows
+    import tempfile as _tf
+    with _tf.TemporaryDirectory() as d_:
+        pl.save_roadmaps(d_ + "/dense.csv", d_ + "/csr.csv")
+        a_rows = open(d_ + "/dense.csv").read().strip().split("\n")
+        b_rows = open(d_ + "/csr.csv").read().strip().split("\n")
+        assert a_rows[:n] == b_rows[:n] and len(a_rows) == len(b_rows) == n + len(col)
+        assert sorted(a_rows[n:]) == sorted(b_rows[n:])
     # multi-source flood (core of wavefrontFill) through the class
     dist, pred, cluster = pl.flood([0, 1, 500])
     dm, pm, lm = orc.sssp(want["row_ptr"], want["col"], want["w"], [0, 1, 500], want_label=True)
