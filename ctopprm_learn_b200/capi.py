@@ -39,6 +39,8 @@ _SIGS = {
     "ctp_device_count": [_P],
     "ctp_map_create": [_P, _I, _P, _P, _I, _I, _P],
     "ctp_map_create_f64": [_P, _I, _P, _P, _I, _I, _P],
+    "ctp_map_create_columns": [_I, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "ctp_map_download": [_P, _P],
     "ctp_map_destroy": [_P],
     "ctp_map_set_layout": [_P, _I],
     "ctp_map_info": [_P, _P],
@@ -171,6 +173,26 @@ class DeviceMap:
             _check(L.ctp_map_create(_ptr(v), self.n, _ptr(self.centroid), _ptr(self.extents), device, layouts, C.byref(h)))
         self._h = h
         self.device = device
+
+    @classmethod
+    def columns(cls, n, centroid, extents, cx, cy, r, device=0, layouts=LAYOUT_PLAIN):
+        """procedural ESDF of vertical cylinders generated on the device (ctp_map_create_columns)"""
+        self = cls.__new__(cls)
+        self.n = int(n)
+        self.centroid = _np(centroid, np.float64)
+        self.extents = _np(extents, np.float64)
+        cx, cy, r = _np(cx, np.float64), _np(cy, np.float64), _np(r, np.float64)
+        h = C.c_void_p()
+        _check(lib().ctp_map_create_columns(self.n, _ptr(self.centroid), _ptr(self.extents), _ptr(cx), _ptr(cy), _ptr(r),
+                                            len(cx), device, layouts, C.byref(h)))
+        self._h = h
+        self.device = device
+        return self
+
+    def download(self):
+        vox = np.empty((self.n, self.n, self.n), dtype=np.float32)
+        _check(lib().ctp_map_download(self._h, _ptr(vox)))
+        return vox
 
     @classmethod
     def load(cls, filename, device=0, layouts=LAYOUT_PLAIN):

@@ -289,6 +289,71 @@ extern "C" int ctp_map_create_f64(const double *vox, int n, const double c[3], c
   return map_create_common(vox, true, n, c, e, device, layouts, out);
 }
 
+// ESDF of vertical cylinders generated on the device (no host grid, no host->device copy of N^3 floats)
+extern "C" int ctp_map_create_columns(int n, const double c[3], const double e[3], const double *cx, const double *cy,
+                                      const double *r, int n_col, int device, int layouts, ctp_map **out) {
+  REQUIRE(c && e && out && (n_col == 0 || (cx && cy && r)), "null argument");
+  REQUIRE(n >= 2 && n <= 2048 && n_col >= 0, "voxels per axis must be in [2, 2048]");
+  REQUIRE((layouts & ~15) == 0, "unknown layout bits");
+  REQUIRE(e[0] == e[1] && e[1] == e[2], "the generator places voxels on a cubic lattice: extents must be equal");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+  CK(cudaSetDevice(device));
+  ctp_map *m = new (std::nothrow) ctp_map();
+  if (!m) return fail(CTP_ERR_NOMEM, "host allocation failed");
+  m->device = device;
+  m->n = n;
+  m->layouts = layouts | CTP_L_PLAIN;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
+  const size_t cnt = (size_t)n * n * n;
+  auto body = [&]() -> int {
+    CK(cudaMalloc(&m->d_plain, cnt * sizeof(float)));
+    m->map_bytes += cnt * sizeof(float);
+    double *d_par = nullptr;
+    float *d_slab = nullptr;
+    CK(cudaMalloc(&d_par, (size_t)std::max(1, n_col) * 3 * sizeof(double)));
+    cudaError_t e1 = cudaMalloc(&d_slab, (size_t)n * n * sizeof(float));
+    if (e1 != cudaSuccess) { cudaFree(d_par); CK(e1); }
+    if (n_col) {
+      cudaMemcpy(d_par, cx, n_col * 8, cudaMemcpyHostToDevice);
+      cudaMemcpy(d_par + n_col, cy, n_col * 8, cudaMemcpyHostToDevice);
+      cudaMemcpy(d_par + 2 * n_col, r, n_col * 8, cudaMemcpyHostToDevice);
+    }
+    // voxel i sits at (c - E/2) + i * (E/N): same expression and operation order as synth.axis_coords
+    const double step = e[0] / (double)n;
+    k_gen_columns<<<(n * n + 255) / 256, 256>>>(n, c[0] - e[0] / 2, c[1] - e[1] / 2, step, d_par, d_par + n_col,
+                                                d_par + 2 * n_col, n_col, d_slab);
+    k_broadcast_z<<<m->sm_count * 8, 256>>>(d_slab, n, m->d_plain);
+    cudaError_t e2 = cudaDeviceSynchronize();
+    cudaFree(d_par);
+    cudaFree(d_slab);
+    CK(e2);
+    CK(cudaMalloc(&m->d_lookups, sizeof(unsigned long long)));
+    CK(cudaMemset(m->d_lookups, 0, sizeof(unsigned long long)));
+    CKR(map_build_layouts(m));
+    return CTP_OK;
+  };
+  const int rc = body();
+  if (rc != CTP_OK) {
+    ctp_map_destroy(m);
+    return rc;
+  }
+  m->active = pick_active(m->layouts);
+  map_fill_params(m, c, e);
+  *out = m;
+  return CTP_OK;
+}
+
+// the grid back on the host, in .npy order (x*n*n + y*n + z)
+extern "C" int ctp_map_download(ctp_map *m, float *vox) {
+  REQUIRE(m && vox, "null");
+  CK(cudaSetDevice(m->device));
+  CK(cudaMemcpy(vox, m->d_plain, (size_t)m->n * m->n * m->n * sizeof(float), cudaMemcpyDeviceToHost));
+  return CTP_OK;
+}
+
 extern "C" int ctp_map_destroy(ctp_map *m) {
   if (!m) return CTP_OK;
   cudaSetDevice(m->device);

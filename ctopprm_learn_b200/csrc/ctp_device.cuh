@@ -583,3 +583,31 @@ __global__ void k_narrow_f64(const double *__restrict__ in, size_t cnt, float *_
        i += (size_t)gridDim.x * blockDim.x)
     out[i] = (float)in[i];  // fill_data<double>: map_data is float (include/esdf_map.hpp:43)
 }
+
+// ---- procedural ESDF on the device ------------------------------------
+// Signed distance to a set of vertical cylinders, min_i(sqrt(dx^2 + dy^2) - r_i), constant along z, written
+// in the .npy order of the reference grid.  Voxel i of an axis sits at (c - E/2) + i * (E/N), the inverse of
+// the world->index map of src/esdf_map.cpp:136-139.  FP64 with one rounding per operation, narrowed to f32
+// at the end: bit-identical to ctopprm_learn_b200/synth.py:columns_field.
+__global__ void __launch_bounds__(256) k_gen_columns(int n, double x_lo, double y_lo, double step,
+                                                     const double *__restrict__ cx, const double *__restrict__ cy,
+                                                     const double *__restrict__ r, int n_col, float *__restrict__ slab) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * n) return;
+  const int xi = t / n, yi = t - xi * n;
+  const double x = x_lo + (double)xi * step, y = y_lo + (double)yi * step;
+  double best = __longlong_as_double(0x7ff0000000000000LL);
+  for (int i = 0; i < n_col; i++) {
+    const double dx = x - cx[i], dy = y - cy[i];
+    const double d = sqrt(dx * dx + dy * dy) - r[i];
+    best = d < best ? d : best;  // np.minimum keeps the first argument on ties and propagates NaN the same way
+  }
+  slab[t] = (float)best;
+}
+
+__global__ void __launch_bounds__(256) k_broadcast_z(const float *__restrict__ slab, int n, float *__restrict__ vox) {
+  const size_t total = (size_t)n * n * n;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x)
+    vox[o] = slab[o / n];
+}
+

@@ -44,12 +44,32 @@ def random_columns_esdf(n: int, extent: float, n_col: int, seed: int):
     r = 0.15 + rng.random(n_col) * 0.45
     x = axis_coords(c, extent, n, 0)
     y = axis_coords(c, extent, n, 1)
-    d2 = np.full((n, n), np.inf)
-    for i in range(n_col):
-        d = np.hypot(x[:, None] - cx[i], y[None, :] - cy[i]) - r[i]
-        np.minimum(d2, d, out=d2)
-    vox = np.ascontiguousarray(np.broadcast_to(d2[:, :, None], (n, n, n)), dtype=np.float32)
+    vox = columns_field(n, c, extent, cx, cy, r)
     return vox, c, np.array([extent] * 3, dtype=np.float64)
+
+
+def column_params(n_col: int, extent: float, seed: int):
+    """centres and radii of the random columns of seed `seed` (what random_columns_esdf draws)"""
+    rng = np.random.default_rng(seed)
+    c = centroid_for(extent)
+    cx = c[0] + (rng.random(n_col) - 0.5) * extent
+    cy = c[1] + (rng.random(n_col) - 0.5) * extent
+    r = 0.15 + rng.random(n_col) * 0.45
+    return c, cx, cy, r
+
+
+def columns_field(n: int, c, extent: float, cx, cy, r):
+    """signed distance to a set of vertical cylinders, min_i(sqrt(dx^2 + dy^2) - r_i), FP64 with one rounding
+    per operation (the order ctp_map_create_columns evaluates it in, so both give the same floats)"""
+    x = axis_coords(c, extent, n, 0)
+    y = axis_coords(c, extent, n, 1)
+    d2 = np.full((n, n), np.inf)
+    for i in range(len(cx)):
+        dx = x[:, None] - cx[i]
+        dy = y[None, :] - cy[i]
+        d = np.sqrt(dx * dx + dy * dy) - r[i]
+        np.minimum(d2, d, out=d2)
+    return np.ascontiguousarray(np.broadcast_to(d2[:, :, None], (n, n, n)), dtype=np.float32)
 
 
 def forest_esdf(n: int, extent: float, n_trunk: int, seed: int, n_canopy: int | None = None,

@@ -66,6 +66,14 @@ int ctp_map_create(const float *vox, int n, const double centroid[3], const doub
                    int device, int layouts, ctp_map **out);
 int ctp_map_create_f64(const double *vox, int n, const double centroid[3],
                        const double extents[3], int device, int layouts, ctp_map **out);
+/* procedural map generated on the device (multi-map sweeps without a host grid): signed
+ * distance to n_col vertical cylinders (centres cx, cy, radii r), constant along z, cubic extents.  Voxel i of
+ * an axis sits at (centroid - E/2) + i * (E/N), the inverse of the index map of src/esdf_map.cpp:136-139. */
+int ctp_map_create_columns(int n, const double centroid[3], const double extents[3], const double *cx,
+                           const double *cy, const double *r, int n_col, int device, int layouts,
+                           ctp_map **out);
+/* the f32 grid back on the host in .npy order (to write a map file in map.py's format) */
+int ctp_map_download(ctp_map *map, float *vox);
 int ctp_map_destroy(ctp_map *map);
 int ctp_map_set_layout(ctp_map *map, int layout);
 /* ESDFMap::getMinPos/getMaxPos (src/esdf_map.cpp:75-76) and bookkeeping.

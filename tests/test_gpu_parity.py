@@ -764,3 +764,27 @@ def test_randomized_differential(orc, seed):
         assert np.array_equal(gg, g0, equal_nan=True) and np.array_equal(cc, c0, equal_nan=True)
     finally:
         m.close()
+
+
+def test_device_generated_columns_map(orc):
+    """ctp_map_create_columns: the procedural ESDF generated on the device equals synth.columns_field bit for bit,
+    and a roadmap built on it equals the oracle's on the host-generated grid"""
+    n, extent, n_col, seed = 96, 9.6, 30, 123
+    c, cx, cy, r = synth.column_params(n_col, extent, seed)
+    vox, c2, e = synth.random_columns_esdf(n, extent, n_col, seed)
+    assert np.array_equal(c, c2)
+    m = capi.DeviceMap.columns(n, c, e, cx, cy, r, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX)
+    try:
+        assert np.array_equal(m.download(), vox)
+        om = orc.OracleMap(vox, c, e)
+        s, g = synth.random_queries(c, e, 1, 5)
+        cand = synth.ellipsoid_candidates(s[0], g[0], 6000, 9)
+        m.set_layout(capi.LAYOUT_TEX)
+        out = m.sample_multiple(s, g, cand[None], 600, CLR, CDC)
+        n0 = om.sample_reject(s[0], g[0], cand, CLR, 600)[0]
+        assert np.array_equal(out["nodes"][0], n0)
+        _csr_equal(out, 0, om.build_prm(n0, CLR, CDC, nthreads=8))
+    finally:
+        m.close()
+    with pytest.raises(capi.CtpError):
+        capi.DeviceMap.columns(32, c, e * np.array([1, 0.5, 1]), cx, cy, r)  # non-cubic extents
