@@ -253,13 +253,195 @@ def run_paths_leg(dmap, nodes_d, row_ptr_d, col_d, w_d, nnz_off_d, nq, n, clr, c
             "api": "ctp_shorten_path / ctp_deformable (host buffers, wall clock)"}
 
 
+def run_multimap(args, rank, world):
+    """--workload C5 (BASELINE configs[4]): a sweep over procedurally generated maps, one handle and one batch of
+    queries per map.  64 maps per GPU per step (seeds 100 + 64*rank ...), random columns 256^3 as C2, generated
+    on the device; 8 queries of 10 000 nodes per map.  Same metric: directed edge checks / s over the whole
+    sampleMultiple."""
+    import torch
+    import torch.distributed as dist
+    from ctopprm_learn_b200 import capi
+
+    local = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    kind, extent, nvox, n_col, _, n = synth.CONFIGS["C2"]
+    n_maps, qpm, cpn = args.maps or 64, 8, 4
+    clr, cdc = synth.MIN_CLEARANCE, synth.COLLISION_DISTANCE_CHECK
+    e = np.array([extent] * 3)
+    m_c = cpn * n
+    maps, s_l, g_l, cand_l = [], [], [], []
+    t0 = time.perf_counter()
+    for mi in range(n_maps):
+        seed = 100 + rank * n_maps + mi
+        c, cx, cy, r = synth.column_params(n_col, extent, seed)
+        dm = capi.DeviceMap.columns(nvox, c, e, cx, cy, r, device=local, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX)
+        dm.set_layout(capi.LAYOUT_TEX)
+        dm.reserve(qpm, n, m_c, K_NN)
+        maps.append(dm)
+        s, g = synth.random_queries(c, e, qpm, seed)
+        s_l.append(s)
+        g_l.append(g)
+        cand_l.append(np.stack([synth.ellipsoid_candidates(s[i], g[i], m_c, seed * 1000 + i) for i in range(qpm)]))
+    t_setup = time.perf_counter() - t0
+    q = n_maps * qpm
+    T = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    s_d, g_d = T(np.concatenate(s_l), None), T(np.concatenate(g_l), None)
+    cand_d = T(np.concatenate(cand_l), None)
+    cap = 2 * qpm * n * K_NN
+    nodes_d = torch.zeros((q, n, 3), dtype=torch.float64, device=dev)
+    nf_d = torch.zeros(q, dtype=torch.int32, device=dev)
+    nu_d = torch.zeros(q, dtype=torch.int32, device=dev)
+    rp_d = torch.zeros((q, n + 1), dtype=torch.int32, device=dev)
+    col_d = torch.zeros((n_maps, cap), dtype=torch.int32, device=dev)
+    w_d = torch.zeros((n_maps, cap), dtype=torch.float64, device=dev)
+    off_d = torch.zeros((n_maps, qpm + 1), dtype=torch.int64, device=dev)
+    streams = [torch.cuda.Stream() for _ in range(max(1, args.map_streams))]
+    main = torch.cuda.current_stream()
+
+    def step():
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for st in streams:
+            st.wait_event(ev)
+        for mi, dm in enumerate(maps):
+            st = streams[mi % len(streams)]
+            a, b = mi * qpm, (mi + 1) * qpm
+            dm.sample_reject_dev(s_d[a:b], g_d[a:b], cand_d[a:b], qpm, m_c, clr, n, nodes_d[a:b], nf_d[a:b], nu_d[a:b], stream=st)
+            dm.build_prm_dev(nodes_d[a:b], qpm, n, K_NN, clr, cdc, rp_d[a:b], col_d[mi], w_d[mi], cap, off_d[mi], stream=st)
+        for st in streams:
+            e2 = torch.cuda.Event()
+            e2.record(st)
+            main.wait_event(e2)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    if int(nf_d.min()) < n:
+        raise SystemExit("bench.py: a query ran out of candidates")
+    for dm in maps:
+        dm.read_lookups()
+        dm.read_launches()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record(main)
+    for _ in range(args.steps):
+        step()
+    ev1.record(main)
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    lookups = sum(dm.read_lookups() for dm in maps)
+    launches = sum(dm.read_launches() for dm in maps)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    checks = q * n * K_NN
+    value = checks * world * args.steps / (ms_max * 1e-3)
+    # end to end: per map, host candidate streams -> host CSR
+    e2e = None
+    if not args.no_e2e:
+        from concurrent.futures import ThreadPoolExecutor
+        n_thr = max(1, args.map_threads)
+        outs = [dict(nodes=capi.pinned_empty((qpm, n, 3), np.float64), n_filled=capi.pinned_empty((qpm,), np.int32),
+                     row_ptr=capi.pinned_empty((qpm, n + 1), np.int32), col=capi.pinned_empty((cap,), np.int32),
+                     w=capi.pinned_empty((cap,), np.float64), nnz_off=capi.pinned_empty((qpm + 1,), np.int64))
+                for _ in range(n_thr)]
+        pins = []
+        for mi in range(n_maps):
+            pc = capi.pinned_empty(cand_l[mi].shape, np.float64)
+            pc[:] = cand_l[mi]
+            pins.append(pc)
+        pool = ThreadPoolExecutor(n_thr)
+
+        def e2e_worker(t):
+            # distinct handles may be driven from distinct host threads (INTEGRATION.md); ctypes drops the GIL
+            for mi in range(t, n_maps, n_thr):
+                maps[mi].sample_multiple(s_l[mi], g_l[mi], pins[mi], n, clr, cdc, k=K_NN, out=outs[t])
+
+        def e2e_step():
+            list(pool.map(e2e_worker, range(n_thr)))
+        e2e_step()
+        sync_all()
+        for dm in maps:
+            dm.read_io()
+        k2 = 2
+        t0 = time.perf_counter()
+        for _ in range(k2):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        io = [dm.read_io() for dm in maps]
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": checks * world * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(x[0] for x in io) // k2),
+               "d2h_bytes_per_step": int(sum(x[1] for x in io) // k2), "ms_per_step": 1e3 * dt / k2, "steps": k2,
+               "api": f"ctp_sample_multiple per map (host candidate streams -> host CSR), {n_thr} host threads over the "
+                      "handles, wall clock, max over ranks"}
+        pool.shutdown()
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = min(cpu_cores(), qpm)  # the reference arm threads over the queries of one map
+        tc, bad, done = 0.0, 0, 0
+        for mi, dm in enumerate(maps):  # every map of the step, until ~20 s of host work
+            arm = CpuArm(dm.download(), synth.column_params(n_col, extent, 100 + mi)[0], e)
+            t1, oc = arm.run(s_l[mi], g_l[mi], cand_l[mi], n, clr, cdc, cores)
+            arm.close()
+            tc += t1
+            done += 1
+            gpu_nnz = rp_d[mi * qpm:(mi + 1) * qpm, -1].cpu().numpy().astype(np.int64)
+            bad += int((gpu_nnz != oc["nnz"]).sum())
+            if tc > 20.0:
+                break
+        cpu = {"value": done * qpm * n * K_NN / tc, "unit": UNIT, "cores": cores, "kind": arm.kind,
+               "sample": f"the first {done} maps of the step (grids downloaded from the device), {qpm} queries each, whole "
+                         f"sampleMultiple on the host, OpenMP over queries, {tc:.1f} s"}
+        parity = {"queries_checked": done * qpm, "nnz_mismatch": bad}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C5: multi-map sweep, {n_maps} procedurally generated random-columns ESDFs per GPU per step "
+                                       f"({nvox}^3 @ {extent / nvox:.3f} m, seeds 100.., generated on the device), {qpm} queries of {n} "
+                                       f"nodes per map, one device handle per map, {len(streams)} streams",
+                           "maps_per_step_per_gpu": n_maps, "queries_per_map": qpm, "nodes_per_query": n, "k": K_NN,
+                           "parallelism": f"maps sharded over {world} GPU(s), no data-path collective",
+                           "l2": f"{n_maps} grids of 64 MiB are swept per step: {n_maps * 64} MiB >> 126 MB L2",
+                           "map_setup_s": t_setup},
+                "lookups_per_s": lookups / (ms_max * 1e-3), "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+                "cpu_baseline": cpu, "parity": parity}
+        print(json.dumps(line), flush=True)
+    for dm in maps:
+        dm.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C5"])
+    ap.add_argument("--maps", type=int, default=0, help="C5: maps per GPU per step (default 64)")
+    ap.add_argument("--map-streams", type=int, default=4, help="C5: streams the per-map batches are spread over")
+    ap.add_argument("--map-threads", type=int, default=4, help="C5 e2e: host threads driving the map handles")
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (default: per workload)")
     ap.add_argument("--layout", default="auto", choices=["auto", "plain", "cell8", "tex", "brick"])
     ap.add_argument("--group", type=int, default=0, help="lanes per edge in the march kernel (0 = library default)")
@@ -279,6 +461,12 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.workload == "C5":
+        if args.impl == "reference":
+            args.workload = "C2"  # the CPU arm of the sweep is the C2 arm: same grid size, nodes and checks per query
+        else:
+            run_multimap(args, rank, world)
+            return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
