@@ -40,6 +40,7 @@ _SIGS = {
     "ctp_map_create": [_P, _I, _P, _P, _I, _I, _P],
     "ctp_map_create_f64": [_P, _I, _P, _P, _I, _I, _P],
     "ctp_map_create_columns": [_I, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "ctp_map_create_occupancy": [_P, _I, _P, _P, _I, _I, _P, _P],
     "ctp_map_download": [_P, _P],
     "ctp_map_destroy": [_P],
     "ctp_map_set_layout": [_P, _I],
@@ -188,6 +189,25 @@ class DeviceMap:
         self._h = h
         self.device = device
         return self
+
+    @classmethod
+    def from_occupancy(cls, occ, centroid, extents, device=0, layouts=LAYOUT_PLAIN, want_d2=False):
+        """exact signed EDT of a voxel occupancy grid on the device (ctp_map_create_occupancy);
+        with want_d2 returns (map, signed integer squared voxel distances)"""
+        occ = _np(np.asarray(occ) != 0, np.uint8)
+        if occ.ndim != 3 or len(set(occ.shape)) != 1:
+            raise ValueError("occupancy grid must be n x n x n")
+        self = cls.__new__(cls)
+        self.n = int(occ.shape[0])
+        self.centroid = _np(centroid, np.float64)
+        self.extents = _np(extents, np.float64)
+        d2 = np.empty(occ.shape, dtype=np.int32) if want_d2 else None
+        h = C.c_void_p()
+        _check(lib().ctp_map_create_occupancy(_ptr(occ), self.n, _ptr(self.centroid), _ptr(self.extents), device, layouts,
+                                              _ptr(d2) if want_d2 else None, C.byref(h)))
+        self._h = h
+        self.device = device
+        return (self, d2) if want_d2 else self
 
     def download(self):
         vox = np.empty((self.n, self.n, self.n), dtype=np.float32)

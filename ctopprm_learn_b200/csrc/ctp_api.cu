@@ -15,6 +15,7 @@
 
 #include "ctp_device.cuh"
 #include "ctp_graph.cuh"
+#include "ctp_edt.cuh"
 #include "ctp_paths.cuh"
 #include "ctp_prm.cuh"
 
@@ -289,11 +290,12 @@ extern "C" int ctp_map_create_f64(const double *vox, int n, const double c[3], c
   return map_create_common(vox, true, n, c, e, device, layouts, out);
 }
 
-// ESDF of vertical cylinders generated on the device (no host grid, no host->device copy of N^3 floats)
-extern "C" int ctp_map_create_columns(int n, const double c[3], const double e[3], const double *cx, const double *cy,
-                                      const double *r, int n_col, int device, int layouts, ctp_map **out) {
-  REQUIRE(c && e && out && (n_col == 0 || (cx && cy && r)), "null argument");
-  REQUIRE(n >= 2 && n <= 2048 && n_col >= 0, "voxels per axis must be in [2, 2048]");
+// common part of the generators: a handle whose plain grid is produced on the device by `fill`
+template <typename Fill>
+static int map_create_generated(int n, const double c[3], const double e[3], int device, int layouts, ctp_map **out,
+                                Fill fill) {
+  REQUIRE(c && e && out, "null argument");
+  REQUIRE(n >= 2 && n <= 2048, "voxels per axis must be in [2, 2048]");
   REQUIRE((layouts & ~15) == 0, "unknown layout bits");
   REQUIRE(e[0] == e[1] && e[1] == e[2], "the generator places voxels on a cubic lattice: extents must be equal");
   int ndev = 0;
@@ -311,25 +313,7 @@ extern "C" int ctp_map_create_columns(int n, const double c[3], const double e[3
   auto body = [&]() -> int {
     CK(cudaMalloc(&m->d_plain, cnt * sizeof(float)));
     m->map_bytes += cnt * sizeof(float);
-    double *d_par = nullptr;
-    float *d_slab = nullptr;
-    CK(cudaMalloc(&d_par, (size_t)std::max(1, n_col) * 3 * sizeof(double)));
-    cudaError_t e1 = cudaMalloc(&d_slab, (size_t)n * n * sizeof(float));
-    if (e1 != cudaSuccess) { cudaFree(d_par); CK(e1); }
-    if (n_col) {
-      cudaMemcpy(d_par, cx, n_col * 8, cudaMemcpyHostToDevice);
-      cudaMemcpy(d_par + n_col, cy, n_col * 8, cudaMemcpyHostToDevice);
-      cudaMemcpy(d_par + 2 * n_col, r, n_col * 8, cudaMemcpyHostToDevice);
-    }
-    // voxel i sits at (c - E/2) + i * (E/N): same expression and operation order as synth.axis_coords
-    const double step = e[0] / (double)n;
-    k_gen_columns<<<(n * n + 255) / 256, 256>>>(n, c[0] - e[0] / 2, c[1] - e[1] / 2, step, d_par, d_par + n_col,
-                                                d_par + 2 * n_col, n_col, d_slab);
-    k_broadcast_z<<<m->sm_count * 8, 256>>>(d_slab, n, m->d_plain);
-    cudaError_t e2 = cudaDeviceSynchronize();
-    cudaFree(d_par);
-    cudaFree(d_slab);
-    CK(e2);
+    CKR(fill(m));
     CK(cudaMalloc(&m->d_lookups, sizeof(unsigned long long)));
     CK(cudaMemset(m->d_lookups, 0, sizeof(unsigned long long)));
     CKR(map_build_layouts(m));
@@ -344,6 +328,79 @@ extern "C" int ctp_map_create_columns(int n, const double c[3], const double e[3
   map_fill_params(m, c, e);
   *out = m;
   return CTP_OK;
+}
+
+// frees a list of device pointers on scope exit
+struct DevScratch {
+  std::vector<void *> p;
+  ~DevScratch() { for (void *x : p) cudaFree(x); }
+  template <typename T> cudaError_t get(T **out, size_t bytes) {
+    void *v = nullptr;
+    cudaError_t e = cudaMalloc(&v, bytes ? bytes : 1);
+    if (e == cudaSuccess) p.push_back(v);
+    *out = (T *)v;
+    return e;
+  }
+};
+
+// ESDF of vertical cylinders generated on the device (no host grid, no host->device copy of N^3 floats)
+extern "C" int ctp_map_create_columns(int n, const double c[3], const double e[3], const double *cx, const double *cy,
+                                      const double *r, int n_col, int device, int layouts, ctp_map **out) {
+  REQUIRE(n_col >= 0 && (n_col == 0 || (cx && cy && r)), "null argument");
+  return map_create_generated(n, c, e, device, layouts, out, [&](ctp_map *m) -> int {
+    DevScratch sc;
+    double *d_par = nullptr;
+    float *d_slab = nullptr;
+    CK(sc.get(&d_par, (size_t)std::max(1, n_col) * 3 * sizeof(double)));
+    CK(sc.get(&d_slab, (size_t)n * n * sizeof(float)));
+    if (n_col) {
+      CK(cudaMemcpy(d_par, cx, n_col * 8, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d_par + n_col, cy, n_col * 8, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d_par + 2 * n_col, r, n_col * 8, cudaMemcpyHostToDevice));
+    }
+    // voxel i sits at (c - E/2) + i * (E/N): same expression and operation order as synth.axis_coords
+    const double step = e[0] / (double)n;
+    k_gen_columns<<<(n * n + 255) / 256, 256>>>(n, c[0] - e[0] / 2, c[1] - e[1] / 2, step, d_par, d_par + n_col,
+                                                d_par + 2 * n_col, n_col, d_slab);
+    k_broadcast_z<<<m->sm_count * 8, 256>>>(d_slab, n, m->d_plain);
+    CK(cudaDeviceSynchronize());
+    return CTP_OK;
+  });
+}
+
+// exact signed Euclidean distance field of a voxel occupancy grid (ctp_edt.cuh); occ in .npy order, non-zero =
+// occupied.  d2_signed (optional, host, n^3 int32) receives the exact squared voxel distances (negative inside).
+extern "C" int ctp_map_create_occupancy(const uint8_t *occ, int n, const double c[3], const double e[3], int device,
+                                        int layouts, int32_t *d2_signed, ctp_map **out) {
+  REQUIRE(occ, "null argument");
+  return map_create_generated(n, c, e, device, layouts, out, [&](ctp_map *m) -> int {
+    DevScratch sc;
+    const size_t cnt = (size_t)n * n * n;
+    const int64_t lines = (int64_t)n * n;
+    uint8_t *d_occ = nullptr;
+    int32_t *d_a = nullptr, *d_b = nullptr, *d_d2 = nullptr;
+    uint16_t *d_s = nullptr, *d_t = nullptr;
+    CK(sc.get(&d_occ, cnt));
+    CK(sc.get(&d_a, cnt * 4));
+    CK(sc.get(&d_b, cnt * 4));
+    CK(sc.get(&d_s, cnt * 2));
+    CK(sc.get(&d_t, cnt * 2));
+    if (d2_signed) CK(sc.get(&d_d2, cnt * 4));
+    CK(cudaMemcpy(d_occ, occ, cnt, cudaMemcpyHostToDevice));
+    const double pitch = e[0] / (double)n;
+    for (int feat = 1; feat >= 0; feat--) {
+      k_edt_scan_z<<<(unsigned)((lines + 7) / 8), 256>>>(d_occ, n, feat, d_a);
+      // along y: lines (x, z), element stride n, line base x*n*n + z
+      k_edt_envelope<<<(unsigned)((lines + 255) / 256), 256>>>(d_a, n, lines, n, (int64_t)n * n, n, d_s, d_t, d_b);
+      // along x: lines (y, z), element stride n*n, line base y*n + z
+      k_edt_envelope<<<(unsigned)((lines + 255) / 256), 256>>>(d_b, n, lines, lines, 0, (int64_t)n * n, d_s, d_t, d_a);
+      k_edt_emit<<<m->sm_count * 8, 256>>>(d_a, d_occ, n, pitch, feat, m->d_plain, d_d2);
+      m->launches += 4;
+    }
+    CK(cudaDeviceSynchronize());
+    if (d2_signed) CK(cudaMemcpy(d2_signed, d_d2, cnt * 4, cudaMemcpyDeviceToHost));
+    return CTP_OK;
+  });
 }
 
 // the grid back on the host, in .npy order (x*n*n + y*n + z)

@@ -105,6 +105,48 @@ void ESDFMap::loadFromMemory(const float *vox, int n, const Vector<3> &c, const 
     die("ctp_map_create");
 }
 
+void ESDFMap::loadFromOccupancy(const unsigned char *occ, int n, const Vector<3> &c, const Vector<3> &e) {
+  centroid = c;
+  extents = e;
+  num_vexels_per_axis = n;
+  max_extents_ = extents.maxCoeff();
+  if (handle_) ctp_map_destroy(handle_);
+  handle_ = nullptr;
+  if (ctp_map_create_occupancy(occ, n, c.data(), e.data(), device_, n <= 1024 ? layouts_ : (layouts_ & ~CTP_LAYOUT_TEX) | CTP_LAYOUT_PLAIN, nullptr, &handle_) != CTP_OK)
+    die("ctp_map_create_occupancy");
+}
+
+namespace {
+// one NPY v1 record: magic, version 1.0, little-endian header length, dict padded so that the data starts on a
+// 64-byte boundary (what np.save writes and np.load / cnpy read back)
+void writeNpy(FILE *fp, const char *descr, const std::vector<size_t> &shape, const void *data, size_t bytes) {
+  std::string dict = std::string("{'descr': '") + descr + "', 'fortran_order': False, 'shape': (";
+  for (size_t i = 0; i < shape.size(); i++) dict += std::to_string(shape[i]) + (shape.size() == 1 || i + 1 < shape.size() ? "," : "");
+  dict += "), }";
+  while ((10 + dict.size() + 1) % 64 != 0) dict += ' ';
+  dict += '\n';
+  const unsigned short hlen = (unsigned short)dict.size();
+  const unsigned char pre[10] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, (unsigned char)(hlen & 0xff), (unsigned char)(hlen >> 8)};
+  if (fwrite(pre, 1, 10, fp) != 10 || fwrite(dict.data(), 1, dict.size(), fp) != dict.size() ||
+      (bytes && fwrite(data, 1, bytes, fp) != bytes))
+    throw std::runtime_error("npy: short write");
+}
+}  // namespace
+
+void ESDFMap::save(const std::string &filename) {
+  const size_t n = (size_t)num_vexels_per_axis;
+  std::vector<float> vox(n * n * n);
+  if (ctp_map_download(requireHandle("save"), vox.data()) != CTP_OK) die("ctp_map_download");
+  FILE *fp = fopen(filename.c_str(), "wb");
+  if (!fp) throw std::runtime_error("ESDFMap::save: unable to open " + filename);
+  std::unique_ptr<FILE, int (*)(FILE *)> guard(fp, fclose);
+  const long long res = (long long)n;
+  writeNpy(fp, "<f4", {n, n, n}, vox.data(), vox.size() * sizeof(float));
+  writeNpy(fp, "<f8", {3}, centroid.data(), 24);
+  writeNpy(fp, "<f8", {3}, extents.data(), 24);
+  writeNpy(fp, "<i8", {}, &res, 8);
+}
+
 double ESDFMap::getClearence(const Vector<3> pos) {
   double out;
   if (ctp_clearance(requireHandle("getClearence"), pos.data(), 1, &out) != CTP_OK) die("ctp_clearance");

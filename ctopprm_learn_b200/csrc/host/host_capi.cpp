@@ -44,6 +44,22 @@ void *ctph_map_load(const char *filename, int device, int layouts) {
     return nullptr;
   }
 }
+void *ctph_map_from_occupancy(const unsigned char *occ, int n, const double *c, const double *e, int device, int layouts) {
+  ESDFMap::setDevice(device);
+  if (layouts) ESDFMap::setLayouts(layouts);
+  auto *b = new MapBox{std::make_shared<ESDFMap>()};
+  b->map->loadFromOccupancy(occ, n, V(c), V(e));
+  return b;
+}
+int ctph_map_save(void *h, const char *filename) {
+  try {
+    static_cast<MapBox *>(h)->map->save(filename);
+    return 0;
+  } catch (const std::exception &e) {
+    fprintf(stderr, "ctph_map_save: %s\n", e.what());
+    return -1;
+  }
+}
 void ctph_map_free(void *h) { delete static_cast<MapBox *>(h); }
 #define MAP(h) (static_cast<MapBox *>(h)->map)
 double ctph_get_clearence(void *h, const double *p) { return MAP(h)->getClearence(V(p)); }

@@ -45,6 +45,7 @@ def lib():
             raise ImportError(lib_path() + " is missing: run __graft_entry__.build()")
         L = C.CDLL(lib_path())
         L.ctph_map_load.restype = C.c_void_p
+        L.ctph_map_from_occupancy.restype = C.c_void_p
         L.ctph_planner_new.restype = C.c_void_p
         L.ctph_get_clearence.restype = C.c_double
         L.ctph_planner_graph.restype = C.c_int64
@@ -73,6 +74,20 @@ class HostMap:
         self.h = C.c_void_p(lib().ctph_map_load(filename.encode(), device, layouts))
         if not self.h:
             raise RuntimeError("ESDFMap::load failed for " + filename)
+
+    @classmethod
+    def from_occupancy(cls, occ, centroid, extents, device=0, layouts=0):
+        """ESDFMap::loadFromOccupancy: exact signed distance transform of a voxel occupancy grid on the device"""
+        occ = np.ascontiguousarray(np.asarray(occ) != 0, dtype=np.uint8)
+        c, e = _f(centroid), _f(extents)
+        self = cls.__new__(cls)
+        self.h = C.c_void_p(lib().ctph_map_from_occupancy(_p(occ), occ.shape[0], _p(c), _p(e), device, layouts))
+        return self
+
+    def save(self, filename):
+        """ESDFMap::save: the four NPY records of map.py:124-132"""
+        if lib().ctph_map_save(self.h, filename.encode()) != 0:
+            raise RuntimeError("ESDFMap::save failed for " + filename)
 
     def close(self):
         if self.h:

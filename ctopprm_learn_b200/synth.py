@@ -219,3 +219,18 @@ def random_edges(centroid, extents, m: int, seed: int, lo: float = 0.2, hi: floa
     d /= np.linalg.norm(d, axis=1)[:, None]
     b = a + d * (lo + rng.random(m) * (hi - lo))[:, None]
     return np.ascontiguousarray(a), np.ascontiguousarray(b)
+
+
+def blocks_occupancy(n, n_box, seed, fill=None):
+    """seeded voxel occupancy grid: n_box axis-aligned boxes (and, with fill, random single voxels of that
+    density) -- input of the device distance transform (ctp_map_create_occupancy)"""
+    rng = np.random.default_rng(seed)
+    occ = np.zeros((n, n, n), dtype=np.uint8)
+    for _ in range(n_box):
+        lo = rng.integers(0, n, 3)
+        sz = rng.integers(1, max(2, n // 6), 3)
+        hi = np.minimum(lo + sz, n)
+        occ[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = 1
+    if fill:
+        occ |= (rng.random((n, n, n)) < fill).astype(np.uint8)
+    return occ

@@ -14,6 +14,11 @@ class ESDFMap : public BaseMap {
   void load(std::string filename) override;
   // the same from memory (vox in .npy order x*n*n + y*n + z)
   void loadFromMemory(const float *vox, int n, const Vector<3> &centroid, const Vector<3> &extents);
+  // the voxel grid -> distance field step of the map pipeline (map.py:49-73) on the device: exact signed
+  // Euclidean distance transform of an n^3 occupancy grid (non-zero = occupied), cubic extents
+  void loadFromOccupancy(const unsigned char *occ, int n, const Vector<3> &centroid, const Vector<3> &extents);
+  // write the map as the four NPY records of map.py:124-132 (f4 voxels, centroid, extents, resolution)
+  void save(const std::string &filename);
   double getClearence(const Vector<3> pos) override;                                  // :130-165
   Vector<3> getMinPos() override;                                                     // :75
   Vector<3> getMaxPos() override;                                                     // :76

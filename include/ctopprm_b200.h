@@ -72,6 +72,13 @@ int ctp_map_create_f64(const double *vox, int n, const double centroid[3],
 int ctp_map_create_columns(int n, const double centroid[3], const double extents[3], const double *cx,
                            const double *cy, const double *r, int n_col, int device, int layouts,
                            ctp_map **out);
+/* map from a voxel occupancy grid (the voxel grid -> signed distance step of the map pipeline, map.py:49-73, as an
+ * exact Euclidean distance transform on the device).  occ: n^3 bytes in .npy order, non-zero = occupied; cubic
+ * extents, voxel pitch p = E/N.  Field: free voxel -> +p*sqrt(d2) to the nearest occupied voxel, occupied voxel ->
+ * -p*sqrt(d2) to the nearest free voxel, d2 the exact integer squared voxel distance (3*n*n when the grid holds no
+ * voxel of the other kind).  d2_signed (optional host buffer, n^3 int32): those squared distances, negative inside. */
+int ctp_map_create_occupancy(const uint8_t *occ, int n, const double centroid[3], const double extents[3],
+                             int device, int layouts, int32_t *d2_signed, ctp_map **out);
 /* the f32 grid back on the host in .npy order (to write a map file in map.py's format) */
 int ctp_map_download(ctp_map *map, float *vox);
 int ctp_map_destroy(ctp_map *map);

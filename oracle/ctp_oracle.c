@@ -952,3 +952,43 @@ void orc_sssp(int n, const int32_t *row_ptr, const int32_t *col, const double *w
   }
 }
 
+
+/* ---- exact EDT by definition (checker for the device EDT; see ctp_oracle.h) ------------------------- */
+static void edt_axis_min(const int64_t *g, int64_t *out, int n, size_t stride, size_t n_lines_a, size_t stride_a,
+                         size_t n_lines_b, size_t stride_b) {
+  for (size_t a = 0; a < n_lines_a; a++)
+    for (size_t b = 0; b < n_lines_b; b++) {
+      const size_t base = a * stride_a + b * stride_b;
+      for (int u = 0; u < n; u++) {
+        int64_t best = INT64_MAX;
+        for (int i = 0; i < n; i++) {
+          const int64_t v = (int64_t)(u - i) * (u - i) + g[base + (size_t)i * stride];
+          if (v < best) best = v;
+        }
+        out[base + (size_t)u * stride] = best;
+      }
+    }
+}
+
+void orc_edt_signed(const unsigned char *occ, int n, double pitch, float *vox, int32_t *d2s) {
+  const size_t cnt = (size_t)n * n * n;
+  const int64_t INF = (int64_t)1 << 40;
+  int64_t *a = (int64_t *)malloc(cnt * sizeof(int64_t));
+  int64_t *b = (int64_t *)malloc(cnt * sizeof(int64_t));
+  for (int feat = 1; feat >= 0; feat--) {
+    for (size_t o = 0; o < cnt; o++) a[o] = ((occ[o] != 0) == (feat != 0)) ? 0 : INF;
+    edt_axis_min(a, b, n, 1, (size_t)n, (size_t)n * n, (size_t)n, (size_t)n);            /* along z */
+    edt_axis_min(b, a, n, (size_t)n, (size_t)n, (size_t)n * n, (size_t)n, 1);            /* along y */
+    edt_axis_min(a, b, n, (size_t)n * n, (size_t)n, (size_t)n, (size_t)n, 1);            /* along x */
+    for (size_t o = 0; o < cnt; o++) {
+      if ((occ[o] != 0) == (feat != 0)) continue;
+      int64_t v = b[o];
+      if (v >= INF) v = 3 * (int64_t)n * n;
+      const double d = pitch * sqrt((double)v);
+      if (vox) vox[o] = (float)(feat ? d : -d);
+      if (d2s) d2s[o] = (int32_t)(feat ? v : -v);
+    }
+  }
+  free(a);
+  free(b);
+}

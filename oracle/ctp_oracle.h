@@ -155,6 +155,13 @@ int orc_remove_equivalent(const orc_map *m, const double *pts, const int32_t *of
 void orc_sssp(int n, const int32_t *row_ptr, const int32_t *col, const double *w, const int32_t *src,
               int ns, double *dist, int32_t *pred, int32_t *label);
 
+/* exact signed squared Euclidean distance transform of an n^3 occupancy grid (.npy order), by definition
+ * (separable brute-force minimisation, O(n^4)): the checker for ctp_map_create_occupancy.  The map pipeline's
+ * own distance field comes from mesh_to_sdf (map.py:49-73, not in this image): parity unpinned at that
+ * boundary, pinned here against scipy.ndimage.distance_transform_edt in tests/test_oracle_prm.py.
+ * vox (optional): pitch * sqrt(d2) signed, as f32; d2s (optional): signed squared voxel distances. */
+void orc_edt_signed(const unsigned char *occ, int n, double pitch, float *vox, int32_t *d2s);
+
 #ifdef __cplusplus
 }
 #endif

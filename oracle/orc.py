@@ -237,6 +237,16 @@ def sssp(row_ptr, col, w, src, want_label=False):
     return (dist, pred, label) if want_label else (dist, pred)
 
 
+def edt_signed(occ, pitch):
+    """orc_edt_signed: exact signed EDT of an occupancy grid by definition -> (f32 field, signed int32 d2)"""
+    occ = np.ascontiguousarray(np.asarray(occ) != 0, dtype=np.uint8)
+    n = occ.shape[0]
+    vox = np.empty(occ.shape, dtype=np.float32)
+    d2 = np.empty(occ.shape, dtype=np.int32)
+    _L().orc_edt_signed(_p(occ), C.c_int(n), C.c_double(pitch), _p(vox), _p(d2))
+    return vox, d2
+
+
 def knn_grid(nodes, k=13, nthreads=1):
     nodes = _f64(nodes).reshape(-1, 3)
     n = len(nodes)

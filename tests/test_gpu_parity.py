@@ -788,3 +788,73 @@ def test_device_generated_columns_map(orc):
         m.close()
     with pytest.raises(capi.CtpError):
         capi.DeviceMap.columns(32, c, e * np.array([1, 0.5, 1]), cx, cy, r)  # non-cubic extents
+
+
+@pytest.mark.parametrize("n,n_box,fill,seed", [(2, 0, 0.5, 1), (7, 1, 0.05, 2), (33, 4, 0.002, 3), (64, 20, None, 4),
+                                               (96, 3, None, 5)])
+def test_device_distance_transform_exact(orc, n, n_box, fill, seed):
+    """ctp_map_create_occupancy: exact signed EDT on the device == the oracle's by-definition transform, squared
+    distances and f32 field bit for bit"""
+    occ = synth.blocks_occupancy(n, n_box, seed, fill)
+    e = np.array([n * 0.1] * 3)
+    c = np.array([0.013, -0.007, e[2] / 2 + 0.011])
+    m, d2 = capi.DeviceMap.from_occupancy(occ, c, e, want_d2=True)
+    try:
+        vox0, d20 = orc.edt_signed(occ, e[0] / n)
+        assert np.array_equal(d2, d20)
+        assert np.array_equal(m.download(), vox0)
+    finally:
+        m.close()
+
+
+def test_device_distance_transform_degenerate_and_large(orc):
+    ndi = pytest.importorskip("scipy.ndimage")
+    e = np.array([6.4] * 3)
+    c = np.zeros(3)
+    for fillv, want in ((0, 3 * 16 * 16), (1, -3 * 16 * 16)):
+        m, d2 = capi.DeviceMap.from_occupancy(np.full((16, 16, 16), fillv, np.uint8), c, e, want_d2=True)
+        assert (d2 == want).all()
+        m.close()
+    # one occupied voxel in a corner / one free voxel in a full grid
+    occ = np.zeros((40, 40, 40), np.uint8)
+    occ[0, 39, 0] = 1
+    m, d2 = capi.DeviceMap.from_occupancy(occ, c, e, want_d2=True)
+    i = np.indices(occ.shape)
+    assert np.array_equal(np.where(occ != 0, -1, d2), np.where(occ != 0, -1, i[0] ** 2 + (i[1] - 39) ** 2 + i[2] ** 2))
+    m.close()
+    m, d2 = capi.DeviceMap.from_occupancy(1 - occ, c, e, want_d2=True)
+    assert np.array_equal(np.where(occ != 0, 1, d2), np.where(occ != 0, 1, -(i[0] ** 2 + (i[1] - 39) ** 2 + i[2] ** 2)))
+    m.close()
+    # 256^3 against scipy (the oracle's O(n^4) definition would take minutes here)
+    n = 256
+    occ = synth.blocks_occupancy(n, 60, 11)
+    m, d2 = capi.DeviceMap.from_occupancy(occ, c, np.array([12.8] * 3), want_d2=True)
+    out = ndi.distance_transform_edt(occ == 0)
+    ins = ndi.distance_transform_edt(occ != 0)
+    ref = np.rint(out ** 2).astype(np.int64) - np.rint(ins ** 2).astype(np.int64)
+    assert np.array_equal(d2, ref)
+    m.close()
+    with pytest.raises(capi.CtpError):
+        capi.DeviceMap.from_occupancy(occ[:8, :8, :8], c, np.array([1.0, 2.0, 1.0]))
+
+
+def test_roadmap_on_distance_transform_map(orc):
+    """a roadmap built on a device-generated EDT map equals the oracle's on the downloaded grid"""
+    n = 96
+    occ = synth.blocks_occupancy(n, 25, 21)
+    e = np.array([9.6] * 3)
+    c = np.array([0.013, -0.007, e[2] / 2 + 0.011])
+    m = capi.DeviceMap.from_occupancy(occ, c, e, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX)
+    try:
+        vox = m.download()
+        om = orc.OracleMap(vox, c, e)
+        s, g = synth.random_queries(c, e, 1, 5)
+        cand = synth.ellipsoid_candidates(s[0], g[0], 8000, 9)
+        m.set_layout(capi.LAYOUT_TEX)
+        out = m.sample_multiple(s, g, cand[None], 500, CLR, CDC)
+        n0 = om.sample_reject(s[0], g[0], cand, CLR, 500)[0]
+        assert int(out["n_filled"][0]) == 500
+        assert np.array_equal(out["nodes"][0], n0)
+        _csr_equal(out, 0, om.build_prm(n0, CLR, CDC, nthreads=8))
+    finally:
+        m.close()

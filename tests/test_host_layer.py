@@ -327,3 +327,29 @@ def test_homotopy_decision_and_seed_test(c1_host, orc):
         want = want and blocked >= 2
         assert pl.seed_accepted(cand_id, seeds) == want
     pl.close()
+
+
+@pytest.mark.gpu
+def test_map_from_occupancy_saved_in_the_map_file_format(orc, tmp_path):
+    """ESDFMap::loadFromOccupancy + save: the device distance transform written as the four NPY records of
+    map.py:124-132; numpy reads the file back, the loader accepts it, the field is the oracle's"""
+    n = 48
+    occ = synth.blocks_occupancy(n, 10, 31)
+    e = np.array([4.8] * 3)
+    c = np.array([0.013, -0.007, e[2] / 2 + 0.011])
+    m = hostlib.HostMap.from_occupancy(occ, c, e)
+    fn = str(tmp_path / "edt_map.npy")
+    m.save(fn)
+    vox, c2, e2, res = synth.read_map(fn)
+    assert vox.dtype == np.float32 and vox.shape == (n, n, n) and int(res) == n
+    assert np.array_equal(c2, c) and np.array_equal(e2, e)
+    assert np.array_equal(vox, orc.edt_signed(occ, e[0] / n)[0])
+    m2 = hostlib.HostMap(fn)
+    om = orc.OracleMap(vox, c, e)
+    pts = c + (np.random.default_rng(3).random((64, 3)) - 0.5) * e
+    want = om.clearance(pts)
+    for p, w in zip(pts, want):
+        assert m.get_clearence(p) == w or (np.isnan(w) and np.isnan(m.get_clearence(p)))
+        assert m2.get_clearence(p) == w or (np.isnan(w) and np.isnan(m2.get_clearence(p)))
+    m.close()
+    m2.close()

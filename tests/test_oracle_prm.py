@@ -121,3 +121,29 @@ def test_oracle_sssp_against_scipy(orc, c1_map):
     assert np.allclose(dm[np.isfinite(dm)], each.min(0)[np.isfinite(dm)], rtol=1e-12)
     clear = np.isfinite(dm) & (np.sort(each, 0)[1] - np.sort(each, 0)[0] > 1e-9)
     assert np.array_equal(lab[clear], each.argmin(0)[clear])
+
+
+def test_edt_oracle_matches_scipy_and_definition(orc):
+    """orc_edt_signed (checker of the device distance transform) against scipy.ndimage.distance_transform_edt and,
+    on a tiny grid, against the O(n^6) definition"""
+    ndi = pytest.importorskip("scipy.ndimage")
+    for n, n_box, fill, seed in ((6, 1, 0.05, 1), (24, 5, 0.001, 2), (40, 12, None, 3)):
+        occ = synth.blocks_occupancy(n, n_box, seed, fill)
+        vox, d2 = orc.edt_signed(occ, 0.1)
+        out = ndi.distance_transform_edt(occ == 0)
+        ins = ndi.distance_transform_edt(occ != 0)
+        ref = np.rint(out ** 2).astype(np.int64) - np.rint(ins ** 2).astype(np.int64)
+        assert np.array_equal(d2, ref)
+        want = np.where(d2 >= 0, 0.1 * np.sqrt(np.abs(d2).astype(np.float64)), -(0.1 * np.sqrt(np.abs(d2).astype(np.float64))))
+        assert np.array_equal(vox, want.astype(np.float32))
+        if n == 6:
+            idx = np.argwhere(np.ones_like(occ)).astype(np.int64)
+            dd = ((idx[:, None, :] - idx[None, :, :]) ** 2).sum(-1)
+            o = occ.reshape(-1) != 0
+            brute = np.where(o, -np.where(~o[None, :], dd, 1 << 40).min(1), np.where(o[None, :], dd, 1 << 40).min(1))
+            assert np.array_equal(d2.reshape(-1), brute)
+    # no voxel of the other kind: the documented sentinel 3 n^2
+    _, d2 = orc.edt_signed(np.zeros((5, 5, 5), np.uint8), 1.0)
+    assert (d2 == 75).all()
+    _, d2 = orc.edt_signed(np.ones((5, 5, 5), np.uint8), 1.0)
+    assert (d2 == -75).all()
