@@ -84,6 +84,7 @@ struct ctp_map {
   double pipe_head_factor = 2.3;  // candidates per node uploaded before the rest of a stream is asked for (0 = all)
   int64_t h_off_cap = 0;
   int64_t pipe_chunk = 0;    // queries per chunk (0 = automatic)
+  int64_t pipe_nu_seen = 0;  // largest n_used (candidates consumed by a query) seen by the running pipeline call
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;    // pool, two per recorded span
   std::vector<int> prof_stage;         // stage id of span i (events 2i, 2i+1)
@@ -1342,7 +1343,7 @@ static int pipe_host_staging(ctp_map *m, int64_t qc) {
   m->h_nf = nullptr;
   m->h_off_cap = 0;
   CK(cudaHostAlloc((void **)&m->h_off, 2 * (qc + 1) * sizeof(int64_t), cudaHostAllocDefault));
-  CK(cudaHostAlloc((void **)&m->h_nf, 2 * (qc + 1) * sizeof(int32_t), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void **)&m->h_nf, 4 * (qc + 1) * sizeof(int32_t), cudaHostAllocDefault));  // accept counts, then n_used
   m->h_off_cap = 2 * (qc + 1);
   return CTP_OK;
 }
@@ -1356,25 +1357,33 @@ static int pipe_host_staging(ctp_map *m, int64_t qc) {
 struct PipeFront {
   double *d_s, *d_g, *d_c, *d_n;
   int32_t *d_nf, *d_nu;
+  int64_t head = 0;  // candidates per query uploaded up front for the chunk now in this buffer
 };
 
+// How much of each stream goes up front: the configured multiple of n for the first chunk, afterwards what the
+// chunks seen so far needed (largest n_used + 6 %), so a map with a low acceptance rate stops paying refills
+// and one with a high rate stops uploading candidates nobody looks at.
 static int64_t pipe_head(const ctp_map *m, int64_t n, int64_t cnt) {
-  const int64_t head = (int64_t)(m->pipe_head_factor * (double)n) + 256;
-  return (m->pipe_head_factor <= 0 || head >= cnt) ? cnt : head;
+  if (m->pipe_head_factor <= 0) return cnt;
+  int64_t head = (int64_t)(m->pipe_head_factor * (double)n) + 256;
+  if (m->pipe_nu_seen > 0) head = m->pipe_nu_seen + m->pipe_nu_seen / 16 + 256;
+  return head >= cnt ? cnt : head;
 }
 
 // stage A: copy the head of the chunk's streams, run the rejection over it, start the n_filled read back
-static int pipe_stage_a(ctp_map *m, const PipeFront &b, int bi, const double *start, const double *goal, const double *cand,
-                        int64_t q0, int64_t qn, int64_t cnt, int64_t head, int64_t n, double clr, bool wait_reuse,
-                        int32_t *h_nf) {
+static int pipe_stage_a(ctp_map *m, PipeFront &b, int bi, const double *start, const double *goal, const double *cand,
+                        int64_t q0, int64_t qn, int64_t cnt, int64_t n, double clr, bool wait_reuse, int32_t *h_nf,
+                        int32_t *h_nu) {
   cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1], s_small = m->pipe_st[3];
+  const int64_t head = pipe_head(m, n, cnt);
+  b.head = head;
   if (wait_reuse) CK(cudaStreamWaitEvent(s_in, m->ev_comp[bi], 0));  // the staging buffer's last reader
   CK(cudaMemcpyAsync(b.d_s, start + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
   CK(cudaMemcpyAsync(b.d_g, goal + 3 * q0, qn * 24, cudaMemcpyHostToDevice, s_in));
   if (head)
     CK(cudaMemcpy2DAsync(b.d_c, cnt * 24, cand + 3 * q0 * cnt, cnt * 24, head * 24, qn, cudaMemcpyHostToDevice, s_in));
   m->io_h2d += (unsigned long long)qn * (48 + head * 24);
-  m->io_d2h += (unsigned long long)qn * 4;
+  m->io_d2h += (unsigned long long)qn * 8;
   CK(cudaEventRecord(m->ev_in[bi], s_in));
   CK(cudaStreamWaitEvent(s_comp, m->ev_in[bi], 0));
   if (wait_reuse) CK(cudaStreamWaitEvent(s_comp, m->ev_out[bi], 0));  // outputs of the buffer's previous chunk have left
@@ -1384,22 +1393,39 @@ static int pipe_stage_a(ctp_map *m, const PipeFront &b, int bi, const double *st
   CK(cudaEventRecord(m->ev_rejd[bi], s_comp));
   CK(cudaStreamWaitEvent(s_small, m->ev_rejd[bi], 0));
   CK(cudaMemcpyAsync(h_nf, b.d_nf, qn * 4, cudaMemcpyDeviceToHost, s_small));
+  CK(cudaMemcpyAsync(h_nu, b.d_nu, qn * 4, cudaMemcpyDeviceToHost, s_small));
   CK(cudaEventRecord(m->ev_rej[bi], s_small));
   return CTP_OK;
 }
 
-// start of stage B: wait for the head's verdict; if a query is short, bring the tails and redo the rejection
+// start of stage B: wait for the head's verdict; the queries that are still short get the rest of their streams
+// (runs of consecutive short queries share one strided copy) and the rejection is redone over the chunk -- a query
+// that was not short takes its first n accepted candidates from the head either way, so what lies behind its
+// head (left over from an earlier chunk) does not matter
 static int pipe_stage_b_refill(ctp_map *m, const PipeFront &b, int bi, const double *cand, int64_t q0, int64_t qn,
-                               int64_t cnt, int64_t head, int64_t n, double clr, const int32_t *h_nf) {
+                               int64_t cnt, int64_t n, double clr, const int32_t *h_nf, const int32_t *h_nu) {
   cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1];
   CK(cudaEventSynchronize(m->ev_rej[bi]));
+  const int64_t head = b.head;
   if (head >= cnt) return CTP_OK;
   bool is_short = false;
-  for (int64_t i = 0; i < qn; i++) is_short |= h_nf[i] < n;
+  int64_t nu_max = 0;
+  for (int64_t i = 0; i < qn; i++) {
+    is_short |= h_nf[i] < n;
+    nu_max = std::max<int64_t>(nu_max, h_nu[i]);
+  }
+  if (is_short) nu_max = std::max(nu_max, std::min(cnt, head + head / 4));  // needed more than the head: guess 25 % more
+  m->pipe_nu_seen = std::max(m->pipe_nu_seen, nu_max);
   if (!is_short) return CTP_OK;
-  CK(cudaMemcpy2DAsync(b.d_c + 3 * head, cnt * 24, cand + 3 * (q0 * cnt + head), cnt * 24, (cnt - head) * 24, qn,
-                       cudaMemcpyHostToDevice, s_in));
-  m->io_h2d += (unsigned long long)qn * (cnt - head) * 24;
+  for (int64_t i = 0; i < qn;) {
+    if (h_nf[i] >= n) { i++; continue; }
+    int64_t j = i + 1;
+    while (j < qn && h_nf[j] < n) j++;
+    CK(cudaMemcpy2DAsync(b.d_c + 3 * (i * cnt + head), cnt * 24, cand + 3 * ((q0 + i) * cnt + head), cnt * 24,
+                         (cnt - head) * 24, j - i, cudaMemcpyHostToDevice, s_in));
+    m->io_h2d += (unsigned long long)(j - i) * (cnt - head) * 24;
+    i = j;
+  }
   CK(cudaEventRecord(m->ev_in[bi], s_in));
   CK(cudaStreamWaitEvent(s_comp, m->ev_in[bi], 0));
   m->ws.used = 0;
@@ -1428,7 +1454,7 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
   while (cs.back() < q) cs.push_back(std::min<int64_t>(q, cs.back() + qc));
   const int64_t n_chunks = (int64_t)cs.size() - 1;
   const int nbuf = n_chunks > 1 ? 2 : 1;
-  const int64_t head = pipe_head(m, n, cnt);
+  m->pipe_nu_seen = 0;  // the up-front share of the streams adapts within this call only
   const int64_t ecap = 2 * qc * n * k;  // CSR entries a chunk can produce
   size_t per = 2 * align_up(qc * 24) + align_up(qc * cnt * 24) + align_up(qc * n * 24) + 2 * align_up(qc * 4) +
                align_up(qc * (n + 1) * 4) + align_up(ecap * 4) + align_up(ecap * 8) + align_up((qc + 1) * 8);
@@ -1478,7 +1504,8 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
   auto stage_b = [&](int64_t c) -> int {
     const int bi = (int)(c % nbuf);
     const int64_t q0 = cs[c], qn = cs[c + 1] - q0;
-    CKR(pipe_stage_b_refill(m, F[bi], bi, cand, q0, qn, cnt, head, n, clr, m->h_nf + (size_t)bi * qc));
+    CKR(pipe_stage_b_refill(m, F[bi], bi, cand, q0, qn, cnt, n, clr, m->h_nf + (size_t)bi * qc,
+                            m->h_nf + (size_t)(2 + bi) * (qc + 1)));
     CKR(ctp_build_prm_dev(m, F[bi].d_n, qn, n, k, clr, cdc, nullptr, nullptr, B[bi].d_rp, B[bi].d_col, B[bi].d_w, ecap,
                           B[bi].d_off, s_comp));
     CK(cudaEventRecord(m->ev_comp[bi], s_comp));
@@ -1499,7 +1526,8 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
     if (c < n_chunks) {
       const int bi = (int)(c % nbuf);
       const int64_t q0 = cs[c], qn = cs[c + 1] - q0;
-      CKR(pipe_stage_a(m, F[bi], bi, start, goal, cand, q0, qn, cnt, head, n, clr, c >= nbuf, m->h_nf + (size_t)bi * qc));
+      CKR(pipe_stage_a(m, F[bi], bi, start, goal, cand, q0, qn, cnt, n, clr, c >= nbuf, m->h_nf + (size_t)bi * qc,
+                       m->h_nf + (size_t)(2 + bi) * (qc + 1)));
     }
   }
   CKR(finish(n_chunks - 1));
@@ -1532,7 +1560,7 @@ extern "C" int ctp_query_paths(ctp_map *m, const double *start, const double *go
   REQUIRE(qc * n * k < ((int64_t)1 << 31), "n*k too large for one chunk");
   const int64_t n_chunks = (q + qc - 1) / qc;
   const int nbuf = n_chunks > 1 ? 2 : 1;
-  const int64_t head = pipe_head(m, n, cnt);
+  m->pipe_nu_seen = 0;  // the up-front share of the streams adapts within this call only
   const int64_t ecap = 2 * qc * n * k;
   // inputs, nodes and the small outputs are double-buffered; CSR and distances are reused chunk after chunk
   const size_t per = 2 * align_up(qc * 24) + align_up(qc * cnt * 24) + align_up(qc * n * 24) + 2 * align_up(qc * 4) +
@@ -1569,7 +1597,8 @@ extern "C" int ctp_query_paths(ctp_map *m, const double *start, const double *go
   auto stage_b = [&](int64_t c) -> int {
     const int bi = (int)(c % nbuf);
     const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
-    CKR(pipe_stage_b_refill(m, F[bi], bi, cand, q0, qn, cnt, head, n, clr, m->h_nf + (size_t)bi * qc));
+    CKR(pipe_stage_b_refill(m, F[bi], bi, cand, q0, qn, cnt, n, clr, m->h_nf + (size_t)bi * qc,
+                            m->h_nf + (size_t)(2 + bi) * (qc + 1)));
     CKR(ctp_build_prm_dev(m, F[bi].d_n, qn, n, k, clr, cdc, nullptr, nullptr, d_rp, d_col, d_w, ecap, d_off, s_comp));
     CKR(ctp_sssp_dev(m, qn, n, d_rp, d_col, d_w, d_off, d_src, 1, d_dist, d_pred, nullptr, s_comp));
     k_extract_paths<<<(int)((qn + 127) / 128), 128, 0, s_comp>>>(qn, n, F[bi].d_n, d_dist, d_pred, 0, 1, path_cap,
@@ -1592,7 +1621,8 @@ extern "C" int ctp_query_paths(ctp_map *m, const double *start, const double *go
     if (c < n_chunks) {
       const int bi = (int)(c % nbuf);
       const int64_t q0 = c * qc, qn = std::min(qc, q - q0);
-      CKR(pipe_stage_a(m, F[bi], bi, start, goal, cand, q0, qn, cnt, head, n, clr, c >= nbuf, m->h_nf + (size_t)bi * qc));
+      CKR(pipe_stage_a(m, F[bi], bi, start, goal, cand, q0, qn, cnt, n, clr, c >= nbuf, m->h_nf + (size_t)bi * qc,
+                       m->h_nf + (size_t)(2 + bi) * (qc + 1)));
     }
   }
   CK(cudaStreamSynchronize(s_out));

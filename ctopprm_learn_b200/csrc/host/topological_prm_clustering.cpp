@@ -114,8 +114,11 @@ template <> void Planner::sampleMultiple(const int num_samples) {
     nodes_[i] = new Node(V3(nodes[3 * (size_t)i], nodes[3 * (size_t)i + 1], nodes[3 * (size_t)i + 2]));
     nodes_[i]->id = i;
   }
-  for (int i = 0; i < n; i++)
-    for (int32_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) nodes_[i]->visibility_node_ids[nodes_[col[e]]] = w[e];
+  for (int i = 0; i < n; i++) {
+    auto &adj = nodes_[i]->visibility_node_ids;
+    adj.reserve((size_t)(row_ptr[i + 1] - row_ptr[i]));  // one bucket array per node, no rehash
+    for (int32_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) adj[nodes_[col[e]]] = w[e];
+  }
   csr_row_ptr_ = row_ptr;
   csr_col_.assign(col.begin(), col.begin() + nnz_off[1]);
   csr_w_.assign(w.begin(), w.begin() + nnz_off[1]);

@@ -858,3 +858,32 @@ def test_roadmap_on_distance_transform_map(orc):
         _csr_equal(out, 0, om.build_prm(n0, CLR, CDC, nthreads=8))
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("chunk", [12, 4])
+def test_refill_of_scattered_short_queries(c1, chunk):
+    """about half of the queries of a chunk need more than the candidates uploaded up front, scattered over the
+    chunk: only their tails follow (what lies behind the head of the others is left over from earlier chunks),
+    and later chunks adapt the up-front share; outputs must equal the oracle's for every query"""
+    m, om, c, e = c1
+    q, n = 12, 400
+    s, g, cand = _queries(c, e, q, n, 77)
+    ref = [om.sample_reject(s[i], g[i], cand[i], CLR, n) for i in range(q)]
+    nu = np.array([r[2] for r in ref])
+    head_cand = int(np.median(nu))
+    assert head_cand > 256 and (nu > head_cand).any() and (nu <= head_cand).any()
+    m.set_tunable(capi.TUNE_PIPE_HEAD, (head_cand - 256) / n)
+    m.set_tunable(capi.TUNE_PIPE_CHUNK, chunk)
+    try:
+        # a first call with other queries leaves foreign candidates behind every head
+        s2, g2, cand2 = _queries(c, e, q, n, 78)
+        m.sample_multiple(s2, g2, cand2, n, CLR, CDC)
+        out = m.sample_multiple(s, g, cand, n, CLR, CDC)
+        pout = m.query_paths(s, g, cand, n, CLR, CDC, path_cap=256)
+    finally:
+        m.set_tunable(capi.TUNE_PIPE_HEAD, 2.3)
+        m.set_tunable(capi.TUNE_PIPE_CHUNK, 0)
+    for i in range(q):
+        assert int(out["n_filled"][i]) == n and int(pout["n_filled"][i]) == n
+        assert np.array_equal(out["nodes"][i], ref[i][0])
+        _csr_equal(out, i, om.build_prm(ref[i][0], CLR, CDC, nthreads=8))
