@@ -330,6 +330,47 @@ def run_multimap(args, rank, world):
     for dm in maps:
         dm.read_lookups()
         dm.read_launches()
+    # optional: capture each map's batch once and replay the 64 graphs over the same streams (18 launches of 8
+    # queries each per map; measured 12.0 vs 12.1 ms per step -- the sweep is bound by the small batches, not by launches)
+    launches_per_step = None
+    if args.map_graphs:
+        step()
+        sync_all()
+        launches_per_step = sum(dm.read_launches() for dm in maps)
+        graphs = []
+        cap_stream = torch.cuda.Stream()
+        for mi, dm in enumerate(maps):
+            a, b = mi * qpm, (mi + 1) * qpm
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=cap_stream):
+                cs = torch.cuda.current_stream()
+                dm.sample_reject_dev(s_d[a:b], g_d[a:b], cand_d[a:b], qpm, m_c, clr, n, nodes_d[a:b], nf_d[a:b], nu_d[a:b], stream=cs)
+                dm.build_prm_dev(nodes_d[a:b], qpm, n, K_NN, clr, cdc, rp_d[a:b], col_d[mi], w_d[mi], cap, off_d[mi], stream=cs)
+            graphs.append(gr)
+        eager_step = step
+
+        def step():  # noqa: F811
+            ev = torch.cuda.Event()
+            ev.record(main)
+            for st in streams:
+                st.wait_event(ev)
+            for mi, gr in enumerate(graphs):
+                with torch.cuda.stream(streams[mi % len(streams)]):
+                    gr.replay()
+            for st in streams:
+                e2 = torch.cuda.Event()
+                e2.record(st)
+                main.wait_event(e2)
+        rp_ref = rp_d.clone()
+        rp_d.zero_()
+        for _ in range(3):
+            step()
+        sync_all()
+        if not torch.equal(rp_ref, rp_d):
+            raise SystemExit("bench.py: graph replay produced different roadmaps")
+        for dm in maps:
+            dm.read_lookups()
+            dm.read_launches()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -344,6 +385,8 @@ def run_multimap(args, rank, world):
     clk = clocks.stop() if rank == 0 else None
     lookups = sum(dm.read_lookups() for dm in maps)
     launches = sum(dm.read_launches() for dm in maps)
+    if launches_per_step is not None:
+        launches = launches_per_step * args.steps  # replayed graph nodes: the same kernels, counted when captured
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -418,7 +461,8 @@ def run_multimap(args, rank, world):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"C5: multi-map sweep, {n_maps} procedurally generated random-columns ESDFs per GPU per step "
                                        f"({nvox}^3 @ {extent / nvox:.3f} m, seeds 100.., generated on the device), {qpm} queries of {n} "
-                                       f"nodes per map, one device handle per map, {len(streams)} streams",
+                                       f"nodes per map, one device handle per map, {len(streams)} streams"
+                                       + (", each map's batch replayed from a CUDA graph" if args.map_graphs else ""),
                            "maps_per_step_per_gpu": n_maps, "queries_per_map": qpm, "nodes_per_query": n, "k": K_NN,
                            "parallelism": f"maps sharded over {world} GPU(s), no data-path collective",
                            "l2": f"{n_maps} grids of 64 MiB are swept per step: {n_maps * 64} MiB >> 126 MB L2",
@@ -441,6 +485,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C5"])
     ap.add_argument("--maps", type=int, default=0, help="C5: maps per GPU per step (default 64)")
     ap.add_argument("--map-streams", type=int, default=4, help="C5: streams the per-map batches are spread over")
+    ap.add_argument("--map-graphs", action="store_true", help="C5: replay each map's batch from a CUDA graph (measured: no gain, the sweep is not launch-bound)")
     ap.add_argument("--map-threads", type=int, default=4, help="C5 e2e: host threads driving the map handles")
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (default: per workload)")
     ap.add_argument("--layout", default="auto", choices=["auto", "plain", "cell8", "tex", "brick"])
