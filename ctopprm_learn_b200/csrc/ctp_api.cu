@@ -84,6 +84,7 @@ struct ctp_map {
   double pipe_head_factor = 2.3;  // candidates per node uploaded before the rest of a stream is asked for (0 = all)
   int64_t h_off_cap = 0;
   int64_t pipe_chunk = 0;    // queries per chunk (0 = automatic)
+  unsigned knn_smem_set = 0;  // bit K: the dynamic shared-memory limit of the k-NN kernels <K> has been raised
   int64_t pipe_nu_seen = 0;  // largest n_used (candidates consumed by a query) seen by the running pipeline call
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;    // pool, two per recorded span
@@ -990,12 +991,18 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
     const int lblocks = m->sm_count * 8;
 #define KNN_CASE(K)                                                                                               \
   case K:                                                                                                         \
+    if (!(m->knn_smem_set & (1u << K))) {                                                                         \
+      CK(cudaFuncSetAttribute(k_knn_direct<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, CTP_KNN_DIRECT_SMEM)); \
+      CK(cudaFuncSetAttribute(k_knn_direct_list<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
+                              CTP_KNN_DIRECT_SMEM));                                                              \
+      m->knn_smem_set |= 1u << K;                                                                                 \
+    }                                                                                                             \
     k_knn_direct<K><<<(int)((total + CTP_KNN_DIRECT_THREADS - 1) / CTP_KNN_DIRECT_THREADS),                       \
-                      CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, idx_stride,   \
-                                                       d2, d_fb2, d_fbk, d_fbn + 1);                              \
-    k_knn_direct_list<K><<<lblocks, CTP_KNN_DIRECT_THREADS, 0, st>>>(d_sorted, n, d_fb2, d_fbk, d_fbn + 1, 1,     \
-                                                                    d_grid, mc, d_start, idx, idx_stride, d2,     \
-                                                                    d_fb, d_fbn);                                 \
+                      CTP_KNN_DIRECT_THREADS, CTP_KNN_DIRECT_SMEM, st>>>(d_sorted, n, total, d_grid, mc, d_start,  \
+                                                                         idx, idx_stride, d2, d_fb2, d_fbk,       \
+                                                                         d_fbn + 1);                              \
+    k_knn_direct_list<K><<<lblocks, CTP_KNN_DIRECT_THREADS, CTP_KNN_DIRECT_SMEM, st>>>(                           \
+        d_sorted, n, d_fb2, d_fbk, d_fbn + 1, 1, d_grid, mc, d_start, idx, idx_stride, d2, d_fb, d_fbn);          \
     k_knn_ring_warp<K><<<lblocks, 32 * CTP_KNN_RW_WARPS, 0, st>>>(d_sorted, n, d_fb, d_fbn, d_grid, mc, d_start,  \
                                                                   idx, idx_stride, d2);                          \
     m->launches += 3;                                                                                             \

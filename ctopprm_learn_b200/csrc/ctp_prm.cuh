@@ -403,9 +403,12 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
 // keys in shared memory; the top-k insertion network then runs over the ~20 survivors only.  Exact
 // whenever at least k survived; sparse points retry once over the 5 x 5 x 5 cells with radius
 // 2 * 0.999 h, and what is still short goes to the ring-search list.
-#define CTP_KNN_DIRECT_THREADS 128
+#ifndef CTP_KNN_DIRECT_THREADS
+#define CTP_KNN_DIRECT_THREADS 256  // measured: 64 -> 2.92, 128 -> 2.80, 256 -> 2.73, 512 -> 2.82 ms per C2 step
+#endif
 #define CTP_KNN_DIRECT_KEEP 48
 #define CTP_KNN_SMALL_LIST 8192
+#define CTP_KNN_DIRECT_SMEM (CTP_KNN_DIRECT_KEEP * CTP_KNN_DIRECT_THREADS * 4)
 
 // Passes: 0 = the 3 x 3 x 3 cells with radius 0.999 h; 1, 2 = wider balls for sparse points, only as
 // wide as the density seen so far suggests is needed for ~2k points (kept in a ball of radius lb ->
@@ -430,13 +433,15 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s
   const int cy = knn_cell_1d(me.y, g.loy, g.inv_h, g.dy);
   const int cz = knn_cell_1d(me.z, g.loz, g.inv_h, g.dz);
   const float lb = (float)(g.h * 0.999);  // rounding here only shifts which points take the wider search
-  int kept = 0, kept_prev = kept_in;
+  const int selfpos = (int)(t - q * n);
+  int kept = 0, kept_prev = kept_in;  // kept counts the point itself as well (d2 = 0 always passes the filter)
   bool done = false;
+  float thr2 = 0.f;
   for (int pass = pass_lo; pass <= pass_hi; pass++) {
     const float grow = pass == 0 ? 1.f : fminf((float)(pass + 1), cbrtf((float)(2 * K) / (float)max(kept_prev, 1)));
     const int R = (pass == 0 || grow <= 1.f) ? 1 : (grow > 2.f ? 3 : 2);  // overflowed points shrink: 27 cells suffice
     const float wide = grow * lb;
-    const float thr2 = wide * wide;
+    thr2 = wide * wide;
     kept = 0;
     const int xa = max(cx - R, 0), xb = min(cx + R, g.dx - 1);
     for (int z = max(cz - R, 0); z <= min(cz + R, g.dz - 1); z++) {
@@ -446,32 +451,40 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s
         for (int c = pb; c < pe; c++) {
           const float4 o = sq[c];
           const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
-          const float dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
-          const int j = __float_as_int(o.w);
-          const bool keep = (dd < thr2) & (j != self);
-          if (keep) s_keep[min(kept, CTP_KNN_DIRECT_KEEP - 1)][tid] = c;  // position in the sorted array; d2 is recomputed below
+          // filter only: fused, so a few ulp off the distance the selection uses below; the margin on the
+          // k-th survivor after the selection makes up for it
+          const float dd = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+          const bool keep = dd < thr2;
+          if (keep) s_keep[min(kept, CTP_KNN_DIRECT_KEEP - 1)][tid] = c;  // position in the sorted array
           kept += keep ? 1 : 0;
         }
       }
     }
-    if (kept >= K) {
+    if (kept > K) {  // k others besides the point itself
       done = kept <= CTP_KNN_DIRECT_KEEP;
       break;
     }
-    kept_prev = kept;
+    kept_prev = kept - 1;
+  }
+  TopK<K> best;
+  if (done) {
+    best.init();
+    for (int u = 0; u < kept; u++) {
+      const int pos = s_keep[u][tid];
+      if (pos == selfpos) continue;
+      const float4 o = __ldg(sq + pos);
+      const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
+      best.push((ddx * ddx + ddy * ddy) + ddz * ddz, __float_as_int(o.w));
+    }
+    // a candidate the fused filter dropped has d2 >= thr2 * (1 - 2^-22): with the k-th survivor below
+    // thr2 * (1 - 1e-5) none of them can belong to the k nearest
+    done = best.d(K - 1) < thr2 * 0.99999f;
   }
   if (!done) {
     const int pos = atomicAdd(fb_count, 1);
     fb_list[pos] = (int32_t)t;
-    if (fb_kept) fb_kept[pos] = (uint8_t)min(kept, 255);
+    if (fb_kept) fb_kept[pos] = (uint8_t)min(max(kept - 1, 0), 255);
     return;
-  }
-  TopK<K> best;
-  best.init();
-  for (int u = 0; u < kept; u++) {
-    const float4 o = __ldg(sq + s_keep[u][tid]);
-    const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
-    best.push((ddx * ddx + ddy * ddy) + ddz * ddz, __float_as_int(o.w));
   }
   int32_t *oi = idx + (q * n + self) * idx_stride;
 #pragma unroll
@@ -489,7 +502,8 @@ k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const 
              int cell_stride, const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
              float *__restrict__ d2out, int32_t *__restrict__ fb_list, uint8_t *__restrict__ fb_kept,
              int32_t *__restrict__ fb_count) {
-  __shared__ int32_t s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
+  extern __shared__ int32_t s_keep_raw[];  // CTP_KNN_DIRECT_SMEM bytes, passed at launch
+  int32_t(*s_keep)[CTP_KNN_DIRECT_THREADS] = reinterpret_cast<int32_t(*)[CTP_KNN_DIRECT_THREADS]>(s_keep_raw);
   const int64_t t = blockIdx.x * (int64_t)CTP_KNN_DIRECT_THREADS + threadIdx.x;
   if (t >= total) return;
   knn_direct_point<K>(t, threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out, 0, 0, 0,
@@ -504,7 +518,8 @@ k_knn_direct_list(const float4 *__restrict__ sorted, int64_t n, const int32_t *_
                   const KnnGrid *__restrict__ grids, int cell_stride, const int32_t *__restrict__ cell_start,
                   int32_t *__restrict__ idx, int idx_stride, float *__restrict__ d2out,
                   int32_t *__restrict__ fb_list, int32_t *__restrict__ fb_count) {
-  __shared__ int32_t s_keep[CTP_KNN_DIRECT_KEEP][CTP_KNN_DIRECT_THREADS];
+  extern __shared__ int32_t s_keep_raw[];  // CTP_KNN_DIRECT_SMEM bytes, passed at launch
+  int32_t(*s_keep)[CTP_KNN_DIRECT_THREADS] = reinterpret_cast<int32_t(*)[CTP_KNN_DIRECT_THREADS]>(s_keep_raw);
   const int cnt = *count;
   if (cnt <= CTP_KNN_SMALL_LIST) {
     // latency regime (a single query lists a few hundred points): one thread per point would walk
