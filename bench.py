@@ -236,15 +236,22 @@ def run_paths_leg(dmap, nodes_d, row_ptr_d, col_d, w_d, nnz_off_d, nq, n, clr, c
     back = dmap.shorten_path(paths, lens, False, clr, cdc, cap=cap)
     fwd = dmap.shorten_path(back[0], list(back[2]), True, clr, cdc, cap=cap)
     t_short = time.perf_counter() - t0
+    t0 = time.perf_counter()  # second pass: best of two (a wall-clock millisecond is easily doubled by a host hiccup)
+    back = dmap.shorten_path(paths, lens, False, clr, cdc, cap=cap)
+    fwd = dmap.shorten_path(back[0], list(back[2]), True, clr, cdc, cap=cap)
+    t_short = min(t_short, time.perf_counter() - t0)
     sp, sl = fwd[0], list(fwd[2])
     P = len(sp)
     ia = [i for i in range(P) for j in range(i + 1, P)]
     ib = [j for i in range(P) for j in range(i + 1, P)]
     nc = [float(np.ceil(max(sl[i], sl[j]) / cdc) + 1) for i, j in zip(ia, ib)]
-    dmap.deformable(sp, sl, ia[:8], ib[:8], nc[:8], clr, cdc)  # warm-up
+    dmap.deformable(sp, sl, ia, ib, nc, clr, cdc)  # warm-up (same size: the scratch arena grows on first use)
     t0 = time.perf_counter()
     d = dmap.deformable(sp, sl, ia, ib, nc, clr, cdc)
     t_def = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    d = dmap.deformable(sp, sl, ia, ib, nc, clr, cdc)
+    t_def = min(t_def, time.perf_counter() - t0)
     return {"polylines": P, "mean_nodes_per_path": float(np.mean([len(p) for p in paths])),
             "shorten_both_directions_ms": 1e3 * t_short, "shortened_mean_nodes": float(np.mean([len(p) for p in sp])),
             "length_ratio_after_shortening": float(np.sum(sl) / np.sum(lens)),

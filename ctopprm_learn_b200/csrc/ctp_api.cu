@@ -1081,8 +1081,12 @@ static int csr_emit(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k
   const int eb = (int)((edges + 255) / 256), rb = (int)((rows + 255) / 256);
   k_csr_rowmask<<<rb, 256, 0, st>>>(d_free, k, ns, rows, d_rec, d_deg, d_rec16);
   m->launches++;
-  if (ns == 16) k_csr_degree<16><<<eb, 256, 0, st>>>(d_rec, d_rec16, d_free, n, k, edges, d_flag, d_deg);
-  else k_csr_degree<32><<<eb, 256, 0, st>>>(d_rec, nullptr, d_free, n, k, edges, d_flag, d_deg);
+  CsrSplit sp;
+  sp.small = edges < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
+  sp.dk = ctp_div_make((uint32_t)k);
+  sp.dn = ctp_div_make(sp.small ? (uint32_t)n : 1u);
+  if (ns == 16) k_csr_degree<16><<<eb, 256, 0, st>>>(d_rec, d_rec16, d_free, n, k, edges, sp, d_flag, d_deg);
+  else k_csr_degree<32><<<eb, 256, 0, st>>>(d_rec, nullptr, d_free, n, k, edges, sp, d_flag, d_deg);
   m->launches++;
   k_csr_rowptr<<<(unsigned)q, 1024, 0, st>>>(d_deg, n, row_ptr, d_nnz);
   m->launches++;
@@ -1090,10 +1094,10 @@ static int csr_emit(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k
   m->launches++;
   // unsorted rows go to scratch (at most 2 entries per directed edge), the finish pass ranks them into col
   const int64_t tcap = std::min<int64_t>(cap, 2 * edges);
-  if (ns == 16) k_csr_fill<16><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, tcap, d_deg, d_coltmp);
-  else k_csr_fill<32><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, row_ptr, nnz_off, tcap, d_deg, d_coltmp);
+  if (ns == 16) k_csr_fill<16><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, sp, row_ptr, nnz_off, tcap, d_deg, d_coltmp);
+  else k_csr_fill<32><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, sp, row_ptr, nnz_off, tcap, d_deg, d_coltmp);
   m->launches++;
-  k_csr_finish_flat<<<(int)((rows + 255) / 256), 256, 0, st>>>(nodes, n, rows, row_ptr, nnz_off, tcap, d_coltmp, col, w);
+  k_csr_finish_flat<<<(int)((rows + 255) / 256), 256, 0, st>>>(nodes, n, rows, sp, row_ptr, nnz_off, tcap, d_coltmp, col, w);
   m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
@@ -1133,6 +1137,9 @@ extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int
   const bool use_order = m->edge_order >= 0 ? m->edge_order != 0
                                             : ((size_t)m->n * m->n * m->n * 4 > ((size_t)100 << 20) || m->active != CTP_L_TEX);
   EdgeSrc S{nodes, nullptr, nullptr, d_rec, n, k, 1, ns, (m->prm_group == 1 && use_order) ? d_sorted_keep : nullptr};
+  S.small = edges < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
+  S.dk = ctp_div_make((uint32_t)k);
+  S.dn = ctp_div_make(S.small ? (uint32_t)n : 1u);
   EdgeOut O{d_free, nullptr, nullptr, nullptr, m->d_lookups};
   {
     StageSpan span(m, CTP_STAGE_EDGES, st);

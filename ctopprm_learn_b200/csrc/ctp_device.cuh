@@ -229,6 +229,27 @@ __global__ void __launch_bounds__(256) k_gradient(MapDev M, const double *__rest
   }
 }
 
+// Exact division of 0 <= x < 2^31 by a run-time constant 1 <= d < 2^31 as one widening multiply and a shift:
+// with s = ceil(log2 d) and mul = floor(2^(31+s) / d) + 1, floor(x / d) = (x * mul) >> (31 + s)  (the excess
+// x * e / (d * 2^(31+s)), e <= d <= 2^s, stays below 1/d).  The per-edge kernels (edge march, CSR) split a flat
+// edge index into (query, row, slot) with two of these instead of two emulated 64-bit divisions; tests/csrc/div_identity.c
+// checks the identity.  `small` = every index of the launch is below 2^31 (else the 64-bit path is taken).
+struct CtpDiv {
+  uint32_t d, mul;
+  int sh;
+};
+__host__ __device__ __forceinline__ CtpDiv ctp_div_make(uint32_t d) {
+  int s = 0;
+  while ((1ull << s) < d) s++;
+  CtpDiv r;
+  r.d = d;
+  r.mul = (uint32_t)(((1ull << (31 + s)) / d) + 1ull);
+  r.sh = 31 + s;
+  return r;
+}
+__host__ __device__ __forceinline__ uint32_t ctp_div_u31(uint32_t x, CtpDiv v) {
+  return (uint32_t)(((unsigned long long)x * v.mul) >> v.sh);
+}
 // ---- segment march (src/base_map.cpp:49-74 and :77-97) ----------------------------------
 // Where the endpoints of edge e come from.
 struct EdgeSrc {
@@ -243,13 +264,22 @@ struct EdgeSrc {
   const float4 *order;  // from == NULL, optional: work item r*k + slot takes the row whose id is order[r].w
                         // (the k-NN stage's cell-sorted points), so that neighbouring work items march
                         // through neighbouring voxels; outputs stay indexed by the original edge number
+  CtpDiv dk, dn;        // from == NULL: division by k and by n (valid when small != 0)
+  int small;            // every edge index of the launch is below 2^31
 };
 
 // work item -> edge number (identity unless S.order is set)
 __device__ __forceinline__ int64_t ctp_edge_of_item(const EdgeSrc &S, int64_t item) {
   if (!S.order) return item;
-  const int64_t r = item / S.k;
-  const int64_t qbase = (r / S.n) * S.n;
+  int64_t r, qbase;
+  if (S.small) {
+    const uint32_t r32 = ctp_div_u31((uint32_t)item, S.dk);
+    r = r32;
+    qbase = (int64_t)(ctp_div_u31(r32, S.dn) * (uint32_t)S.n);
+  } else {
+    r = item / S.k;
+    qbase = (r / S.n) * S.n;
+  }
   const int64_t row = qbase + __float_as_int(S.order[r].w);
   return row * S.k + (item - r * S.k);
 }
@@ -276,8 +306,14 @@ __device__ __forceinline__ int ctp_arm_edge(const EdgeSrc &S, int64_t e, int gua
     if (S.from) {
       t = S.to[e];
     } else {  // batched PRM: e = (query*n + node)*k + slot; neighbour ids are local to the query
-      row = e / S.k;
-      qbase = (row / S.n) * S.n;
+      if (S.small) {
+        const uint32_t r32 = ctp_div_u31((uint32_t)e, S.dk);
+        row = r32;
+        qbase = (int64_t)(ctp_div_u31(r32, S.dn) * (uint32_t)S.n);
+      } else {
+        row = e / S.k;
+        qbase = (row / S.n) * S.n;
+      }
       t = S.to[row * S.to_stride + (e - row * S.k)];
     }
     if (S.from) {

@@ -700,6 +700,30 @@ k_knn_ring_warp(const float4 *__restrict__ sorted, int64_t n, const int32_t *__r
 
 __host__ __device__ __forceinline__ int csr_ns(int k) { return k <= 15 ? 16 : 32; }
 
+struct CsrSplit {
+  CtpDiv dk, dn;  // by k (edge -> row), by n (row -> query)
+  int small;
+};
+__device__ __forceinline__ void csr_edge_split(int64_t e, int64_t n, int k, const CsrSplit &sp, int64_t &row, int &slot,
+                                               int64_t &qbase, int &i) {
+  if (sp.small) {
+    const uint32_t r = ctp_div_u31((uint32_t)e, sp.dk);
+    const uint32_t q = ctp_div_u31(r, sp.dn);
+    row = r;
+    slot = (int)((uint32_t)e - r * (uint32_t)k);
+    qbase = (int64_t)(q * (uint32_t)n);
+    i = (int)(r - q * (uint32_t)n);
+  } else {
+    row = e / k;
+    slot = (int)(e - row * k);
+    qbase = (row / n) * n;
+    i = (int)(row - qbase);
+  }
+}
+__device__ __forceinline__ int64_t csr_row_query(int64_t row, int64_t n, const CsrSplit &sp) {
+  return sp.small ? (int64_t)ctp_div_u31((uint32_t)row, sp.dn) : row / n;
+}
+
 // free bytes of a row -> mask in the record; out-degree seeds deg[].  When every node id fits 16 bits
 // (n <= 65535, k <= 14) the row is also written as a 32-byte record of 16-bit ids (slot 15 = mask, absent
 // neighbours = 0xffff), which halves the gather of the reverse-edge test.
@@ -766,17 +790,17 @@ __device__ __forceinline__ bool csr_lists_free(const int32_t *__restrict__ rec, 
 template <int NS>
 __global__ void __launch_bounds__(256) k_csr_degree(const int32_t *__restrict__ rec, const uint16_t *__restrict__ rec16,
                                                     const uint8_t *__restrict__ fr, int64_t n, int k, int64_t total_edges,
-                                                    uint8_t *__restrict__ flag, int32_t *__restrict__ deg) {
+                                                    CsrSplit sp, uint8_t *__restrict__ flag, int32_t *__restrict__ deg) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= total_edges) return;
   if (!fr[e]) {
     flag[e] = 0;
     return;
   }
-  const int64_t row = e / k;
-  const int slot = (int)(e - row * k);
-  const int64_t qbase = (row / n) * n;
-  const int i = (int)(row - qbase), j = rec[row * NS + slot];
+  int64_t row, qbase;
+  int slot, i;
+  csr_edge_split(e, n, k, sp, row, slot, qbase, i);
+  const int j = rec[row * NS + slot];
   const bool rev = rec16 ? csr_lists_free16(rec16, qbase + j, k, i) : csr_lists_free<NS>(rec, qbase + j, k, i);
   flag[e] = rev ? 1 : 2;
   if (!rev) atomicAdd(deg + qbase + j, 1);
@@ -871,7 +895,7 @@ __global__ void __launch_bounds__(1024) k_csr_query_offsets(const int64_t *__res
 // the extra entries contributed by other rows follow, placed with a per-row cursor
 template <int NS>
 __global__ void __launch_bounds__(256) k_csr_fill(const int32_t *__restrict__ rec, const uint8_t *__restrict__ flag,
-                                                  int64_t n, int k, int64_t total_edges,
+                                                  int64_t n, int k, int64_t total_edges, CsrSplit sp,
                                                   const int32_t *__restrict__ row_ptr,
                                                   const int64_t *__restrict__ nnz_off, int64_t cap,
                                                   int32_t *__restrict__ cursor, int32_t *__restrict__ col) {
@@ -879,10 +903,11 @@ __global__ void __launch_bounds__(256) k_csr_fill(const int32_t *__restrict__ re
   if (e >= total_edges) return;
   const int fl = flag[e];
   if (!fl) return;
-  const int64_t row = e / k;
-  const int slot = (int)(e - row * k);
-  const int64_t q = row / n, qbase = q * n;
-  const int i = (int)(row - qbase), j = rec[row * NS + slot];
+  int64_t row, qbase;
+  int slot, i;
+  csr_edge_split(e, n, k, sp, row, slot, qbase, i);
+  const int64_t q = csr_row_query(row, n, sp);
+  const int j = rec[row * NS + slot];
   const int32_t *rp = row_ptr + q * (n + 1);
   const int64_t base = nnz_off[q];
   {
@@ -902,7 +927,7 @@ __global__ void __launch_bounds__(256) k_csr_fill(const int32_t *__restrict__ re
 // ascending order needs no per-thread sort and every load/store is coalesced; the FP64 weight
 // ||to - from|| (:369-371) is computed on the way out.  col_in -> col / w (out of place).
 __global__ void __launch_bounds__(256) k_csr_finish_flat(const double *__restrict__ nodes, int64_t n, int64_t total_rows,
-                                                         const int32_t *__restrict__ row_ptr,
+                                                         CsrSplit sp, const int32_t *__restrict__ row_ptr,
                                                          const int64_t *__restrict__ nnz_off, int64_t cap,
                                                          const int32_t *__restrict__ col_in, int32_t *__restrict__ col,
                                                          double *__restrict__ w) {
@@ -914,7 +939,7 @@ __global__ void __launch_bounds__(256) k_csr_finish_flat(const double *__restric
   const int64_t row = r0 + lane;
   int64_t rb = 0, re = 0;
   if (row < total_rows) {
-    const int64_t q = row / n, i = row - q * n;
+    const int64_t q = csr_row_query(row, n, sp), i = row - q * n;
     const int32_t *rp = row_ptr + q * (n + 1);
     rb = nnz_off[q] + rp[i];
     re = nnz_off[q] + rp[i + 1];
@@ -947,7 +972,7 @@ __global__ void __launch_bounds__(256) k_csr_finish_flat(const double *__restric
 #pragma unroll 4
         for (int x = 0; x < olen; x++) rank += (__ldg(col_in + obeg + x) < c) ? 1 : 0;
         const int64_t orow = r0 + owner;
-        const int64_t oq = orow / n;
+        const int64_t oq = csr_row_query(orow, n, sp);
         const double *me = nodes + 3 * orow;
         const double *o = nodes + 3 * (oq * n + c);
         const double dx = o[0] - me[0], dy = o[1] - me[1], dz = o[2] - me[2];

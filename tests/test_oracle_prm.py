@@ -91,6 +91,18 @@ def test_division_shortcut_identity_is_exhaustively_exact(tmp_path):
     assert int(out[0]) == 0 and int(out[1]) == 65536 * 65535 // 2 - 0
 
 
+def test_multiply_shift_division_identity(tmp_path):
+    """the CSR kernels split flat edge indices with floor(x / d) = (x * mul) >> sh (ctp_prm.cuh, ctp_div_make);
+    tests/csrc/udiv_identity.c checks the identity at the boundary cases of every d up to 300 000 and on
+    2*10^7 random (x, d) pairs below 2^31"""
+    import subprocess
+    src = os.path.join(os.path.dirname(__file__), "csrc", "udiv_identity.c")
+    exe = str(tmp_path / "udiv_identity")
+    subprocess.check_call(["gcc", "-O2", "-o", exe, src])
+    out = subprocess.check_output([exe, "300000"]).decode().split()
+    assert int(out[0]) == 0 and int(out[1]) > 2 * 10 ** 7
+
+
 def test_oracle_sssp_against_scipy(orc, c1_map):
     """the oracle's Dijkstra (restating include/dijkstra.hpp:83-176) against scipy's on a PRM graph"""
     from scipy.sparse import csr_matrix
