@@ -112,6 +112,29 @@ class ClockSampler:
         return out
 
 
+# The contract is ONE JSON line on stdout.  Libraries below us write there too (NCCL prints its version banner on
+# stdout when NCCL_DEBUG asks for it), so file descriptor 1 is pointed at stderr for the whole run and the line
+# goes out through a private duplicate of the original stdout.
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def cpu_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -186,7 +209,7 @@ def run_reference(args, rank, world):
         "free_edge_fraction": float(out["n_free"].sum() / (q_s * n * K_NN)),
     }
     arm.close()
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def workload_config(name, n, q, cpn, world):
@@ -476,7 +499,7 @@ def run_multimap(args, rank, world):
                            "map_setup_s": t_setup},
                 "lookups_per_s": lookups / (ms_max * 1e-3), "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
                 "cpu_baseline": cpu, "parity": parity}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     for dm in maps:
         dm.close()
     if world > 1:
@@ -512,6 +535,7 @@ def main():
     ap.add_argument("--no-planner", action="store_true", help="skip the C++ class-surface single-query leg")
     ap.add_argument("--e2e-steps", type=int, default=0)
     args = ap.parse_args()
+    guard_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -876,7 +900,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": cpu,
             "csr_nnz_per_step": nnz_total, "free_edge_fraction": free_frac, "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     dmap.close()
     if world > 1:
         dist.destroy_process_group()
