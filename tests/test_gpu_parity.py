@@ -887,3 +887,41 @@ def test_refill_of_scattered_short_queries(c1, chunk):
         assert int(out["n_filled"][i]) == n and int(pout["n_filled"][i]) == n
         assert np.array_equal(out["nodes"][i], ref[i][0])
         _csr_equal(out, i, om.build_prm(ref[i][0], CLR, CDC, nthreads=8))
+
+
+def test_distinct_handles_from_distinct_host_threads(orc):
+    """one handle per (map, device), distinct handles may be driven from distinct host threads --
+    three maps, three threads running the chunk pipeline concurrently, each result equal to the serial one and to
+    the oracle"""
+    from concurrent.futures import ThreadPoolExecutor
+    handles = []
+    try:
+        for seed in (201, 202, 203):
+            c, cx, cy, r = synth.column_params(25, 9.6, seed)
+            e = np.array([9.6] * 3)
+            m = capi.DeviceMap.columns(96, c, e, cx, cy, r, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX)
+            m.set_layout(capi.LAYOUT_TEX)
+            m.set_tunable(capi.TUNE_PIPE_CHUNK, 2)
+            q, n = 5, 500
+            s, g = synth.random_queries(c, e, q, seed)
+            cand = np.stack([synth.ellipsoid_candidates(s[i], g[i], 6 * n, seed * 10 + i) for i in range(q)])
+            handles.append((m, c, e, s, g, cand, n))
+        serial = [h[0].sample_multiple(h[3], h[4], h[5], h[6], CLR, CDC) for h in handles]
+
+        def work(h):
+            outs = [h[0].sample_multiple(h[3], h[4], h[5], h[6], CLR, CDC) for _ in range(4)]
+            return outs[-1]
+        with ThreadPoolExecutor(3) as pool:
+            threaded = list(pool.map(work, handles))
+        for h, a, b in zip(handles, serial, threaded):
+            for key in ("nodes", "n_filled", "row_ptr", "nnz_off"):
+                assert np.array_equal(a[key], b[key]), key
+            nnz = int(a["nnz_off"][-1])
+            assert np.array_equal(a["col"][:nnz], b["col"][:nnz]) and np.array_equal(a["w"][:nnz], b["w"][:nnz])
+            om = orc.OracleMap(h[0].download(), h[1], h[2])
+            n0 = om.sample_reject(h[3][0], h[4][0], h[5][0], CLR, h[6])[0]
+            assert np.array_equal(b["nodes"][0], n0)
+            _csr_equal(b, 0, om.build_prm(n0, CLR, CDC, nthreads=8))
+    finally:
+        for h in handles:
+            h[0].close()
