@@ -460,8 +460,7 @@ __global__ void __launch_bounds__(256) k_edge_march(MapDev M, EdgeSrc S, int64_t
 // tests/csrc/div_identity.c; longer marches take the true division.
 #define CTP_DIV_SMALL_LIMIT 65536.0
 __device__ __forceinline__ double ctp_div_small(double a, double b, double rb) {
-  if (b > CTP_DIV_SMALL_LIMIT) return a / b;
-  const double q0 = a * rb;
+  const double q0 = a * rb;  // caller guarantees b <= CTP_DIV_SMALL_LIMIT
   return __fma_rn(__fma_rn(-q0, b, a), rb, q0);
 }
 
@@ -509,6 +508,18 @@ __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, Edg
       first[el] = 0x7fffffff;
       alive[h] = state[h] == 0;
       base[h] = 1;
+      if (alive[h] && npts > CTP_DIV_SMALL_LIMIT) {
+        // a march of more than 65536 samples (kilometres at the usual spacing) is outside the range the
+        // division shortcut is verified for: the owning lane walks it alone with the true division
+        alive[h] = false;
+        for (int idx = 1; idx <= n_last[h]; idx++) {
+          const double tt = (double)idx / npts;
+          if (ctp_collides(esdf_clearance<L>(M, ax + vx * tt, ay + vy * tt, az + vz * tt), clr)) {
+            first[el] = idx;
+            break;
+          }
+        }
+      }
     }
     for (;;) {
       int c[2], incl[2];
