@@ -12,7 +12,7 @@ LAYOUT_PLAIN, LAYOUT_CELL8, LAYOUT_TEX, LAYOUT_BRICK = 1, 2, 4, 8
 LAYOUT_NAMES = {1: "plain", 2: "cell8", 4: "tex", 8: "brick"}
 DEFAULT_LAYOUT = LAYOUT_TEX  # the layout bench.py uses unless told otherwise (fastest measured; n <= 1024)
 EDGE_NODES, EDGE_GUARDS = 0, 1
-TUNE_KNN_PER_CELL, TUNE_KNN_TILE, TUNE_PIPE_CHUNK, TUNE_EDGE_ORDER, TUNE_SSSP_FRONTIER, TUNE_PIPE_HEAD = 0, 1, 2, 3, 4, 5
+TUNE_KNN_PER_CELL, TUNE_KNN_TILE, TUNE_PIPE_CHUNK, TUNE_EDGE_ORDER, TUNE_SSSP_FRONTIER, TUNE_PIPE_HEAD, TUNE_SSSP_CLUSTER = 0, 1, 2, 3, 4, 5, 6
 ERR_NEED_CANDIDATES = -4
 
 _lib = None

@@ -68,6 +68,7 @@ struct ctp_map {
   size_t map_bytes = 0;
   // stage profiling (ctp_profile): pairs of events recorded on the caller's stream
   double knn_per_cell = 22.0;  // expected points inside a ball of one cell size (see k_knn_setup)
+  int sssp_cluster = -1;      // shortest paths on a cluster of 8 CTAs per query: -1 automatic, 0 never, 1 whenever possible
   int sssp_frontier = 1;      // 1 = queue-based edge-parallel shortest-path kernel, 0 = flag-scan kernel
   int edge_order = -1;        // edge kernel walks rows in cell-sorted order (1), node order (0), or decides (-1):
                               // sorted pays off when the gathers leave the L2 (grid > ~100 MB) or are not texture fetches
@@ -472,6 +473,9 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
     case CTP_TUNE_PIPE_HEAD:
       REQUIRE(value >= 0 && value <= 1e6, "head factor must be >= 0");
       m->pipe_head_factor = value;
+      return CTP_OK;
+    case CTP_TUNE_SSSP_CLUSTER:
+      m->sssp_cluster = value < 0 ? -1 : (value != 0.0);
       return CTP_OK;
     case CTP_TUNE_SSSP_FRONTIER:
       m->sssp_frontier = value != 0.0;
@@ -1268,8 +1272,30 @@ extern "C" int ctp_sssp_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row
     smem_optin = v;
     CK(cudaFuncSetAttribute(k_sssp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
     CK(cudaFuncSetAttribute(k_sssp_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, v - 8192));
+    CK(cudaFuncSetAttribute(k_sssp_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, v - 8192));
   }
-  if (m->sssp_frontier && n <= 65535 && smem_f <= (size_t)smem_optin - 8192) {
+  // one query per cluster of 8 CTAs (distances sliced over distributed shared memory): when few queries are in
+  // flight, or when a query does not fit one CTA's shared memory
+  const int slice = (int)(((n + CTP_SSSP_CL - 1) / CTP_SSSP_CL + 31) / 32 * 32);
+  const size_t smem_c = (size_t)slice * 8 + (size_t)(slice / 32) * 8 + 16;  // distances, frontier words, their snapshot
+  const bool fits_one = n <= 65535 && smem_f <= (size_t)smem_optin - 8192;
+  const bool cluster_ok = m->sssp_frontier && !label && smem_c <= (size_t)smem_optin - 8192 && n >= 64;
+  const bool want_cluster = m->sssp_cluster < 0 ? (q * CTP_SSSP_CL <= 2 * (int64_t)m->sm_count || !fits_one) : m->sssp_cluster != 0;
+  if (cluster_ok && want_cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(q * CTP_SSSP_CL));
+    cfg.blockDim = dim3(CTP_SSSP_CL_THREADS);
+    cfg.dynamicSmemBytes = smem_c;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTP_SSSP_CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k_sssp_cluster, n, slice, row_ptr, col, w, nnz_off, src, ns, dist, pred));
+  } else if (m->sssp_frontier && fits_one) {
     k_sssp_frontier<<<(unsigned)q, CTP_SSSP_THREADS, smem_f, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label);
   } else if (smem <= (size_t)smem_optin) {
     k_sssp<true><<<(unsigned)q, CTP_SSSP_THREADS, smem, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label,

@@ -469,10 +469,12 @@ def test_knn_uneven_density_all_kernels(c1, orc, mode):
         assert np.array_equal(d2[i], d0)
 
 
-def test_sssp_batched_vs_oracle(c1, orc):
-    """ctp_sssp (shared-memory frontier Bellman-Ford, one CTA per query) against the oracle's Dijkstra:
-    distances, predecessors and flood labels bit-identical"""
+@pytest.mark.parametrize("cluster", [0, 1])
+def test_sssp_batched_vs_oracle(c1, orc, cluster):
+    """ctp_sssp (shared-memory frontier Bellman-Ford, one CTA or one 8-CTA cluster per query) against the
+    oracle's Dijkstra: distances, predecessors and flood labels bit-identical"""
     m, om, c, e = c1
+    m.set_tunable(capi.TUNE_SSSP_CLUSTER, cluster)
     q, n = 4, 1200
     s, g, cand = _queries(c, e, q, n, 71)
     out = m.sample_multiple(s, g, cand, n, CLR, CDC)
@@ -489,16 +491,53 @@ def test_sssp_batched_vs_oracle(c1, orc):
         assert np.array_equal(dist3[i], d1) and np.array_equal(pred3[i], p1) and np.array_equal(lab3[i], l1)
     assert np.isinf(dist).any() or True  # unreachable nodes (if any) are +inf with pred -1
     assert (pred[np.isinf(dist)] == -1).all()
+    m.set_tunable(capi.TUNE_SSSP_CLUSTER, -1)
 
 
-def test_sssp_large_graph_global_path(c1, orc):
-    """more nodes than fit in shared memory: the same search on a global distance array"""
+@pytest.mark.parametrize("n,deg,seed", [(64, 3, 1), (65, 2, 2), (257, 1, 3), (1000, 4, 4), (4097, 3, 5), (20000, 2, 6)])
+def test_sssp_cluster_on_synthetic_graphs(c1, orc, n, deg, seed):
+    """the cluster kernel (distances sliced over the distributed shared memory of 8 CTAs) on random symmetric
+    graphs with sizes that do not divide into slices, several components and several sources"""
+    m = c1[0]
+    rng = np.random.default_rng(seed)
+    a = np.repeat(np.arange(n), deg)
+    b = rng.integers(0, n, n * deg)
+    keep = a != b
+    a, b = a[keep], b[keep]
+    pair = np.unique(np.stack([np.minimum(a, b), np.maximum(a, b)], 1), axis=0)
+    wgt = rng.random(len(pair)) + 0.01
+    rows = np.concatenate([pair[:, 0], pair[:, 1]])
+    cols = np.concatenate([pair[:, 1], pair[:, 0]])
+    ww = np.concatenate([wgt, wgt])
+    order = np.lexsort((cols, rows))
+    rows, cols, ww = rows[order], cols[order].astype(np.int32), ww[order]
+    rp = np.zeros(n + 1, dtype=np.int32)
+    np.add.at(rp, rows + 1, 1)
+    rp = np.cumsum(rp).astype(np.int32)
+    off = np.array([0, len(cols)], dtype=np.int64)
+    srcs = [0, n - 1, n // 2]
+    want = orc.sssp(rp, cols, ww, srcs)
+    try:
+        for cluster in (1, 0):
+            m.set_tunable(capi.TUNE_SSSP_CLUSTER, cluster)
+            dist, pred = m.sssp(rp[None], cols, ww, off, np.array([srcs], dtype=np.int32))
+            assert np.array_equal(dist[0], want[0]) and np.array_equal(pred[0], want[1]), cluster
+    finally:
+        m.set_tunable(capi.TUNE_SSSP_CLUSTER, -1)
+
+
+@pytest.mark.parametrize("cluster", [0, 1])
+def test_sssp_large_graph_global_path(c1, orc, cluster):
+    """more nodes than fit in one CTA's shared memory: the same search on a global distance array (cluster = 0)
+    or sliced over the shared memory of a cluster (cluster = 1, the default for such graphs)"""
     m, om, c, e = c1
+    m.set_tunable(capi.TUNE_SSSP_CLUSTER, cluster)
     n = 30000
     s, g = synth.default_query(c, e)
     cand = synth.ellipsoid_candidates(s, g, 8 * n, 9)
     out = m.sample_multiple(s[None], g[None], cand[None], n, CLR, CDC)
     dist, pred = m.sssp(out["row_ptr"], out["col"], out["w"], out["nnz_off"], np.zeros((1, 1), dtype=np.int32))
+    m.set_tunable(capi.TUNE_SSSP_CLUSTER, -1)
     d0, p0 = orc.sssp(out["row_ptr"][0], out["col"][:out["nnz_off"][1]], out["w"][:out["nnz_off"][1]], [0])
     assert np.array_equal(dist[0], d0) and np.array_equal(pred[0], p0)
 

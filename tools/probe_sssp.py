@@ -31,7 +31,14 @@ def build():
     m.build_prm_dev(nodes, 1, n, k, 0.2, 0.05, rp, col, w, cap, off, stream=st)
 def search():
     m.sssp_dev(1, n, rp, col, w, off, src, 1, dist, pred, stream=st)
-for f, name in ((build, "PRM build"), (search, "shortest path")):
+def search_one_cta():
+    m.set_tunable(capi.TUNE_SSSP_CLUSTER, 0)
+    search()
+    m.set_tunable(capi.TUNE_SSSP_CLUSTER, -1)
+build(); torch.cuda.synchronize()
+search(); d_cluster = dist.clone(); search_one_cta(); torch.cuda.synchronize()
+print("cluster == one CTA:", bool(torch.equal(d_cluster, dist)))
+for f, name in ((build, "PRM build"), (search, "shortest path (cluster of 8 CTAs)"), (search_one_cta, "shortest path (one CTA)")):
     for _ in range(5): f()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
