@@ -710,9 +710,28 @@ def main():
         torch.cuda.synchronize()
         sssp_ms = e0.elapsed_time(e1) / reps
         reach = float(torch.isfinite(dist_d[:, 1]).float().mean().item())
+        # one query alone: the library spreads it over a cluster of 8 CTAs (distributed shared memory)
+        qi = int(torch.isfinite(dist_d[:, 1]).float().argmax().item())
+        off1 = (nnz_off_d[qi:qi + 2] - nnz_off_d[qi]).contiguous()
+        lo1, hi1 = int(nnz_off_d[qi].item()), int(nnz_off_d[qi + 1].item())
+        col1, w1, rp1 = col_d[lo1:hi1], w_d[lo1:hi1], row_ptr_d[qi:qi + 1]
+        d1 = torch.zeros((1, n), dtype=torch.float64, device=dev)
+        p1 = torch.zeros((1, n), dtype=torch.int32, device=dev)
+        for _ in range(5):
+            dmap.sssp_dev(1, n, rp1, col1, w1, off1, src_d[:1], 1, d1, p1, stream=stream)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(50):
+            dmap.sssp_dev(1, n, rp1, col1, w1, off1, src_d[:1], 1, d1, p1, stream=stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        single_sssp_ms = e0.elapsed_time(e1) / 50
+        if not torch.equal(d1[0], dist_d[qi]):
+            raise SystemExit("bench.py: single-query shortest paths differ from the batched ones")
         sssp_leg = {"ms_per_step": sssp_ms, "queries": q, "ms_per_query_batched": sssp_ms / q,
-                    "goal_reachable_fraction": reach,
-                    "api": "ctp_sssp_dev (one CTA per query, distances in shared memory), CUDA events"}
+                    "single_query_latency_ms": single_sssp_ms, "goal_reachable_fraction": reach,
+                    "api": "ctp_sssp_dev, CUDA events (batched: one CTA per query, distances in shared memory; one query "
+                           "alone: a cluster of 8 CTAs, distances sliced over distributed shared memory)"}
         if rank == 0 and world == 1 and not args.no_cpu:
             # CPU: the oracle's binary-heap Dijkstra (include/dijkstra.hpp:83-176 restated) on the same CSRs
             from oracle import orc as _orc
