@@ -217,8 +217,8 @@ k_sssp_frontier(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *_
 // cluster: a CTA owns the nodes [rank * slice, (rank + 1) * slice), keeps their distances, frontier bits and
 // queue in its own shared memory and walks the out-edges of its frontier; a relaxation that lands in another
 // slice is a 64-bit atomicMin on that CTA's shared memory through the cluster's distributed-shared-memory
-// window.  Two cluster barriers per sweep (frontier bits are cleared before anyone may set them again; all
-// relaxations land before the next frontier is taken over); within a sweep a warp takes a frontier word and its
+// window.  One cluster barrier per sweep (two frontier bit arrays take turns, a rotating flag per CTA says whether
+// anything was improved); within a sweep a warp takes a frontier word and its
 // lanes the out-edges of one node at a time -- the per-CTA frontier is a few dozen nodes, so this beats the
 // scan-and-search distribution of the one-CTA kernel.  Used when few queries are in flight (a single query keeps
 // 8 SMs busy instead of one) and when a query's distances do not fit one CTA's shared memory (up to ~170 000
@@ -234,7 +234,7 @@ k_sssp_cluster(int64_t n, int slice, const int32_t *__restrict__ row_ptr, const 
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ unsigned long long s_mem[];
-  __shared__ int s_any[CTP_SSSP_CL];
+  __shared__ int s_work[3];
   const int rank = (int)cluster.block_rank();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int64_t q = blockIdx.x / CTP_SSSP_CL;
@@ -246,10 +246,14 @@ k_sssp_cluster(int64_t n, int slice, const int32_t *__restrict__ row_ptr, const 
   const int mine = max(0, min(slice, nn - lo));  // nodes this CTA owns
   const int words = slice >> 5;
   unsigned long long *dist = s_mem;
-  unsigned *bits = reinterpret_cast<unsigned *>(s_mem + slice);  // frontier of the next sweep (set by anyone)
-  unsigned *snap = bits + words;                                 // frontier of this sweep (own copy)
+  // two frontier bit arrays: sweep k consumes B[k & 1] (its owner only) while relaxations set bits in B[(k + 1) & 1]
+  // of whichever CTA owns the target; s_work[k % 3] of the owner is raised along with a bit, so that after the ONE
+  // cluster barrier of the sweep everybody learns from the eight flags whether another sweep is needed
+  unsigned *bits0 = reinterpret_cast<unsigned *>(s_mem + slice);
+  unsigned *bits1 = bits0 + words;
   for (int u = threadIdx.x; u < slice; u += blockDim.x) dist[u] = CTP_SSSP_INF;
-  for (int t = threadIdx.x; t < words; t += blockDim.x) bits[t] = 0;
+  for (int t = threadIdx.x; t < 2 * words; t += blockDim.x) bits0[t] = 0;
+  if (threadIdx.x < 3) s_work[threadIdx.x] = 0;
   cluster.sync();
   if (rank == 0)
     for (int i = threadIdx.x; i < ns; i += blockDim.x) {
@@ -257,30 +261,25 @@ k_sssp_cluster(int64_t n, int slice, const int32_t *__restrict__ row_ptr, const 
       if (s >= 0 && s < nn) {
         const int owner = s / slice, ls = s - owner * slice;
         cluster.map_shared_rank(dist, owner)[ls] = 0ull;
-        atomicOr(cluster.map_shared_rank(bits, owner) + (ls >> 5), 1u << (ls & 31));
+        atomicOr(cluster.map_shared_rank(bits0, owner) + (ls >> 5), 1u << (ls & 31));
+        cluster.map_shared_rank(s_work, owner)[2] = 1;  // "sweep -1"
       }
     }
   cluster.sync();
-  for (;;) {
-    // (1) take over the frontier words, clear them for the relaxations of this sweep
-    int have = 0;
-    for (int t = threadIdx.x; t < words; t += blockDim.x) {
-      const unsigned m = bits[t];
-      snap[t] = m;
-      bits[t] = 0;
-      have |= m != 0;
-    }
-    have = __syncthreads_or(have);
-    if (threadIdx.x < CTP_SSSP_CL) cluster.map_shared_rank(s_any, threadIdx.x)[rank] = have;
-    cluster.sync();
-    int any = 0;
-#pragma unroll
-    for (int r = 0; r < CTP_SSSP_CL; r++) any |= s_any[r];
-    if (any == 0) break;  // every CTA of the cluster sees the same eight flags
-    // (2) a warp per frontier word, its lanes over the out-edges of one node at a time; a relaxation goes to
-    // whichever slice owns the target
+  for (int k = 0;; k++) {
+    // did the previous sweep (or the sources) leave work anywhere in the cluster?
+    int work = 0;
+    if (threadIdx.x < CTP_SSSP_CL) work = cluster.map_shared_rank(s_work, threadIdx.x)[(k + 2) % 3];
+    if (__syncthreads_or(work) == 0) break;  // the same eight flags on every CTA
+    if (threadIdx.x == 0) s_work[(k + 1) % 3] = 0;  // last read before the previous barrier, next raised after this sweep's
+    unsigned *cur = (k & 1) ? bits1 : bits0;
+    unsigned *nxt = (k & 1) ? bits0 : bits1;
+    int *flag = s_work + (k % 3);
+    // a warp per frontier word, its lanes over the out-edges of one node at a time
     for (int word = warp; word < words; word += n_warps) {
-      unsigned m = snap[word];
+      unsigned m = cur[word];
+      __syncwarp();
+      if (lane == 0 && m) cur[word] = 0;
       while (m) {  // a frontier word rarely holds more than one or two nodes: the whole warp takes one node at a time
         const int lu = (word << 5) + __ffs(m) - 1;  // (8 or 16 lanes per node measured slower: 0.42 / 0.34 ms against 0.29 ms)
         m &= m - 1;
@@ -293,14 +292,15 @@ k_sssp_cluster(int64_t n, int slice, const int32_t *__restrict__ row_ptr, const 
           unsigned long long *rd = cluster.map_shared_rank(dist, owner) + lv;
           // 64-bit minimum as a compare-and-swap loop: a 64-bit atomicMin on shared memory is emulated under a
           // CTA-local lock, which a relaxation arriving from another CTA of the cluster would not respect
-          unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(rd);
-          while (nd < cur) {
-            const unsigned long long prev = atomicCAS(rd, cur, nd);
-            if (prev == cur) {
-              atomicOr(cluster.map_shared_rank(bits, owner) + (lv >> 5), 1u << (lv & 31));
+          unsigned long long cur_d = *reinterpret_cast<volatile unsigned long long *>(rd);
+          while (nd < cur_d) {
+            const unsigned long long prev = atomicCAS(rd, cur_d, nd);
+            if (prev == cur_d) {
+              atomicOr(cluster.map_shared_rank(nxt, owner) + (lv >> 5), 1u << (lv & 31));
+              *reinterpret_cast<volatile int *>(cluster.map_shared_rank(flag, owner)) = 1;
               break;
             }
-            cur = prev;
+            cur_d = prev;
           }
         }
       }
