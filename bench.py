@@ -531,6 +531,7 @@ def main():
     ap.add_argument("--no-single", action="store_true", help="skip the single-query latency leg")
     ap.add_argument("--no-paths", action="store_true", help="skip the shortening / mutual-visibility leg")
     ap.add_argument("--no-sssp", action="store_true", help="skip the shortest-path leg")
+    ap.add_argument("--no-cell8", action="store_true", help="large grids: do not materialise the CELL8 records for the rejection stage")
     ap.add_argument("--pipe-head", type=float, default=0.0, help="candidates uploaded up front, as a multiple of n")
     ap.add_argument("--no-planner", action="store_true", help="skip the C++ class-surface single-query leg")
     ap.add_argument("--e2e-steps", type=int, default=0)
@@ -570,7 +571,10 @@ def main():
     layout = layouts[args.layout]
     if args.layout == "auto":
         layout = capi.DEFAULT_LAYOUT if vox.shape[0] <= 1024 else capi.LAYOUT_PLAIN
-    dmap = capi.DeviceMap(vox, c, e, device=local, layouts=layout | capi.LAYOUT_PLAIN)
+    extra = 0
+    if args.layout == "auto" and vox.nbytes > (100 << 20) and not args.no_cell8:
+        extra = capi.LAYOUT_CELL8  # grid beyond the L2: one-sector records for the scattered lookups of the rejection
+    dmap = capi.DeviceMap(vox, c, e, device=local, layouts=layout | capi.LAYOUT_PLAIN | extra)
     dmap.set_layout(layout)
     if args.group:
         dmap.set_prm_group(args.group)
@@ -903,7 +907,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args.workload, n, q, cpn, world), layout=dmap.layout_name(),
+            "config": dict(workload_config(args.workload, n, q, cpn, world),
+                           layout=dmap.layout_name() + (" (edge march) + cell8 (rejection)" if extra else ""),
                            lanes_per_edge=dmap.prm_group()),
             "ms_per_query": {"batched": ms_max / args.steps / q, "single_query_latency": single_ms,
                              "single_query_latency_cuda_graph": single_graph_ms, "class_surface": planner_leg},

@@ -85,6 +85,7 @@ struct ctp_map {
   double pipe_head_factor = 2.3;  // candidates per node uploaded before the rest of a stream is asked for (0 = all)
   int64_t h_off_cap = 0;
   int64_t pipe_chunk = 0;    // queries per chunk (0 = automatic)
+  bool reject_layout_auto = true;  // large grids: rejection reads the CELL8 records when they exist
   unsigned knn_smem_set = 0;  // bit K: the dynamic shared-memory limit of the k-NN kernels <K> has been raised
   int64_t pipe_nu_seen = 0;  // largest n_used (candidates consumed by a query) seen by the running pipeline call
   bool prof = false;
@@ -876,7 +877,16 @@ static int sample_reject_launch(ctp_map *m, const double *start, const double *g
   m->ws.used = keep;  // scratch is dead once the three kernels below have run (stream order)
   dim3 grid((unsigned)nblk, (unsigned)q);
   StageSpan span(m, CTP_STAGE_REJECT, st);
-  DISPATCH_L(m, k_reject_flags<L><<<grid, CTP_REJ_BLOCK, 0, st>>>(m->dev, cand, cnt, stride, clr, d_acc, d_bc, nblk));
+  // Candidates are scattered over the whole ellipsoid: one isolated lookup each.  When the grid does not fit the L2
+  // and the one-sector-per-lookup records (CELL8, 8x the memory) were materialised, the rejection reads those -- one
+  // DRAM sector per candidate instead of the four of two texture gathers (C3: 0.38 -> 0.22 ms) -- while the edge
+  // marches, whose consecutive samples share sectors, stay on the active layout.
+  const bool big = (size_t)m->n * m->n * m->n * 4 > ((size_t)100 << 20);
+  if (big && (m->layouts & CTP_L_CELL8) && m->reject_layout_auto) {
+    k_reject_flags<CTP_L_CELL8><<<grid, CTP_REJ_BLOCK, 0, st>>>(m->dev, cand, cnt, stride, clr, d_acc, d_bc, nblk);
+  } else {
+    DISPATCH_L(m, k_reject_flags<L><<<grid, CTP_REJ_BLOCK, 0, st>>>(m->dev, cand, cnt, stride, clr, d_acc, d_bc, nblk));
+  }
   m->launches++;
   CK(cudaGetLastError());
   k_reject_scan<<<(unsigned)q, 1024, 0, st>>>(d_bc, nblk, n, n_filled);
@@ -1294,8 +1304,15 @@ extern "C" int ctp_sssp_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, k_sssp_cluster, n, slice, row_ptr, col, w, nnz_off, src, ns, dist, pred));
-  } else if (m->sssp_frontier && fits_one) {
+    if (cudaLaunchKernelEx(&cfg, k_sssp_cluster, n, slice, row_ptr, col, w, nnz_off, src, ns, dist, pred) == cudaSuccess) {
+      m->launches++;
+      return CTP_OK;
+    }
+    // a device or partition that cannot co-schedule the cluster: forget the error, use the one-CTA kernels from now on
+    cudaGetLastError();
+    m->sssp_cluster = 0;
+  }
+  if (m->sssp_frontier && fits_one) {
     k_sssp_frontier<<<(unsigned)q, CTP_SSSP_THREADS, smem_f, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label);
   } else if (smem <= (size_t)smem_optin) {
     k_sssp<true><<<(unsigned)q, CTP_SSSP_THREADS, smem, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label,

@@ -964,3 +964,25 @@ def test_distinct_handles_from_distinct_host_threads(orc):
     finally:
         for h in handles:
             h[0].close()
+
+
+def test_rejection_on_cell8_records_for_large_grids(orc):
+    """a grid beyond the L2 with the CELL8 records materialised: the rejection stage reads those, the edge march the
+    active layout; nodes and roadmap must equal the oracle's either way (272^3 f32 = 77 MiB is below the switch,
+    304^3 = 107 MiB above it)"""
+    for nvox in (272, 304):
+        vox, c, e = synth.random_columns_esdf(nvox, nvox * 0.05, 60, 7)
+        m = capi.DeviceMap(vox, c, e, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX | capi.LAYOUT_CELL8)
+        try:
+            m.set_layout(capi.LAYOUT_TEX)
+            om = orc.OracleMap(vox, c, e)
+            q, n = 2, 700
+            s, g = synth.random_queries(c, e, q, 3)
+            cand = np.stack([synth.ellipsoid_candidates(s[i], g[i], 6 * n, 30 + i) for i in range(q)])
+            out = m.sample_multiple(s, g, cand, n, CLR, CDC)
+            for i in range(q):
+                n0 = om.sample_reject(s[i], g[i], cand[i], CLR, n)[0]
+                assert np.array_equal(out["nodes"][i], n0)
+                _csr_equal(out, i, om.build_prm(n0, CLR, CDC, nthreads=8))
+        finally:
+            m.close()
