@@ -1427,6 +1427,16 @@ static int64_t pipe_head(const ctp_map *m, int64_t n, int64_t cnt) {
   return head >= cnt ? cnt : head;
 }
 
+// Queries per chunk: about `edges` directed edges of work per chunk -- but a handful of very large queries (C3: 4
+// queries of 1.3 M edges) would then share one chunk and nothing would overlap, so the batch is cut into at least
+// four chunks as long as a chunk keeps a million edges of work.
+static int64_t pipe_auto_chunk(int64_t q, int64_t n, int k, int64_t edges) {
+  const int64_t per_query = std::max<int64_t>(1, n * k);
+  int64_t qc = std::max<int64_t>(1, edges / per_query);
+  const int64_t quarter = (q + 3) / 4, floor_q = ((int64_t)1 << 20) / per_query + 1;
+  return std::max<int64_t>(1, std::min(qc, std::max(quarter, floor_q)));
+}
+
 // stage A: copy the head of the chunk's streams, run the rejection over it, start the n_filled read back
 static int pipe_stage_a(ctp_map *m, PipeFront &b, int bi, const double *start, const double *goal, const double *cand,
                         int64_t q0, int64_t qn, int64_t cnt, int64_t n, double clr, bool wait_reuse, int32_t *h_nf,
@@ -1501,7 +1511,7 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
   CK(cudaSetDevice(m->device));
   CKR(pipe_init(m));
   // chunk size: about 8M directed edges per chunk, at least 1 query, at most 65535 (grid.y limits)
-  int64_t qc = m->pipe_chunk > 0 ? m->pipe_chunk : std::max<int64_t>(1, (8 << 20) / (n * k));
+  int64_t qc = m->pipe_chunk > 0 ? m->pipe_chunk : pipe_auto_chunk(q, n, k, 8 << 20);
   qc = std::min<int64_t>(std::min<int64_t>(qc, q), 65535);
   REQUIRE(qc * n * k < ((int64_t)1 << 31), "n*k too large for one chunk");
   // chunk boundaries: a short first chunk gets the device->host stream going early, the rest are qc long
@@ -1612,7 +1622,7 @@ extern "C" int ctp_query_paths(ctp_map *m, const double *start, const double *go
   CKR(pipe_init(m));
   // larger chunks than ctp_sample_multiple: the per-query CTAs of the graph search need about a machine's worth of
   // queries per launch, and there is no large device->host copy to hide
-  int64_t qc = m->pipe_chunk > 0 ? m->pipe_chunk : std::max<int64_t>(1, (16 << 20) / (n * k));
+  int64_t qc = m->pipe_chunk > 0 ? m->pipe_chunk : pipe_auto_chunk(q, n, k, 16 << 20);
   qc = std::min<int64_t>(std::min<int64_t>(qc, q), 65535);
   REQUIRE(qc * n * k < ((int64_t)1 << 31), "n*k too large for one chunk");
   const int64_t n_chunks = (q + qc - 1) / qc;
