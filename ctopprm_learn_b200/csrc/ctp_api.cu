@@ -86,6 +86,7 @@ struct ctp_map {
   int64_t h_off_cap = 0;
   int64_t pipe_chunk = 0;    // queries per chunk (0 = automatic)
   bool reject_layout_auto = true;  // large grids: rejection reads the CELL8 records when they exist
+  int sssp_smem_optin = -1;   // opt-in shared memory per CTA of this device, -1 until the graph kernels were configured
   unsigned knn_smem_set = 0;  // bit K: the dynamic shared-memory limit of the k-NN kernels <K> has been raised
   int64_t pipe_nu_seen = 0;  // largest n_used (candidates consumed by a query) seen by the running pipeline call
   bool prof = false;
@@ -1275,7 +1276,8 @@ extern "C" int ctp_sssp_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row
   const size_t smem = (size_t)n * 9 + 16;
   // frontier variant: distances + bit mask + u16 queue (node ids must fit 16 bits)
   const size_t smem_f = (size_t)n * 8 + (((size_t)n + 31) / 32) * 4 + (size_t)n * 2 + 16;
-  static int smem_optin = -1;
+  // per handle, not per process: function attributes belong to the device the handle lives on
+  int &smem_optin = m->sssp_smem_optin;
   if (smem_optin < 0) {
     int v = 0;
     CK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));

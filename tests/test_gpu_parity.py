@@ -986,3 +986,32 @@ def test_rejection_on_cell8_records_for_large_grids(orc):
                 _csr_equal(out, i, om.build_prm(n0, CLR, CDC, nthreads=8))
         finally:
             m.close()
+
+
+def test_two_devices_in_one_process(orc):
+    """one handle per (map, device): the same map on cuda:0 and cuda:1 of one process, every stage (k-NN kernels with
+    raised shared-memory limits, cluster shortest paths) configured per device; skipped on a single-GPU box"""
+    import ctypes
+    cnt = ctypes.c_int(0)
+    capi.lib().ctp_device_count(ctypes.byref(cnt))
+    if cnt.value < 2:
+        pytest.skip("needs two GPUs")
+    vox, c, e = synth.make_config_map("C1")
+    om = orc.OracleMap(vox, c, e)
+    q, n = 3, 900
+    s, g, cand = _queries(c, e, q, n, 55)
+    outs = []
+    for dev in (0, 1):
+        m = capi.DeviceMap(vox, c, e, device=dev, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX)
+        try:
+            m.set_layout(capi.LAYOUT_TEX)
+            out = m.sample_multiple(s, g, cand, n, CLR, CDC)
+            dist, pred = m.sssp(out["row_ptr"], out["col"], out["w"], out["nnz_off"], np.zeros((q, 1), np.int32))
+            outs.append((out, dist, pred))
+        finally:
+            m.close()
+    for key in ("nodes", "row_ptr", "nnz_off"):
+        assert np.array_equal(outs[0][0][key], outs[1][0][key])
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    n0 = om.sample_reject(s[0], g[0], cand[0], CLR, n)[0]
+    _csr_equal(outs[1][0], 0, om.build_prm(n0, CLR, CDC, nthreads=8))
