@@ -506,13 +506,149 @@ def run_multimap(args, rank, world):
         dist.destroy_process_group()
 
 
+def run_microbench(args, rank, world):
+    """--workload MU (SURVEY 8d / BASELINE.md section 4, row "mu"): the gather kernel alone.  2^24 random directed
+    segments per GPU per step, uniform start, isotropic direction, length U[0.2, 1.5] m, on the C2 map (--mu-map C3
+    for the 4 GiB grid), one ctp_edge_check_dev call per step.  Same metric: directed edge checks / s."""
+    import torch
+    import torch.distributed as dist
+    from ctopprm_learn_b200 import capi
+
+    local = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    clr, cdc = synth.MIN_CLEARANCE, synth.COLLISION_DISTANCE_CHECK
+    vox, c, e = synth.make_config_map(args.mu_map)
+    layouts = {"auto": capi.DEFAULT_LAYOUT, "plain": capi.LAYOUT_PLAIN, "cell8": capi.LAYOUT_CELL8, "tex": capi.LAYOUT_TEX,
+               "brick": capi.LAYOUT_BRICK}
+    layout = layouts[args.layout]
+    dmap = capi.DeviceMap(vox, c, e, device=local, layouts=layout | capi.LAYOUT_PLAIN)
+    dmap.set_layout(layout)
+    m_e = args.mu_edges
+    a_h, b_h = synth.random_edges(c, e, m_e, 1000 + rank)
+    a_d, b_d = torch.from_numpy(a_h).to(dev), torch.from_numpy(b_h).to(dev)
+    free_d = torch.zeros(m_e, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        dmap.edge_check_dev(a_d, b_d, clr, cdc, free_d, group=1, stream=stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dmap.read_lookups()
+    dmap.read_launches()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    lookups = dmap.read_lookups()
+    launches = dmap.read_launches()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = m_e * world * args.steps / (ms_max * 1e-3)
+    free_frac = float(free_d.float().mean().item())
+    # end to end: host segments in, host verdicts out (pinned)
+    e2e = None
+    if not args.no_e2e:
+        pa, pb = capi.pinned_empty(a_h.shape, np.float64), capi.pinned_empty(b_h.shape, np.float64)
+        pa[:], pb[:] = a_h, b_h
+        dmap.edge_check(pa, pb, clr, cdc)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fr = dmap.edge_check(pa, pb, clr, cdc)[0]
+        dt = (time.perf_counter() - t0) / 3
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        # bytes from the arrays the call copies: two endpoints in; verdict, first-hit point, its index, lookup count out
+        e2e = {"value": m_e * world / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(m_e * 48),
+               "d2h_bytes_per_step": int(m_e * (1 + 24 + 4 + 4)), "ms_per_step": 1e3 * float(tt.item()),
+               "api": "ctp_edge_check (host segments -> host verdicts, first-hit points and indices), wall clock"}
+        if not np.array_equal(fr, free_d.cpu().numpy().astype(bool)):
+            raise SystemExit("bench.py: host and device entry points disagree")
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from concurrent.futures import ThreadPoolExecutor
+        cores = cpu_cores()
+        arm = CpuArm(vox, c, e)
+        m_s = min(m_e, 1 << 21)
+        bounds = np.linspace(0, m_s, cores + 1).astype(np.int64)
+
+        def part(i):
+            lo, hi = int(bounds[i]), int(bounds[i + 1])
+            if arm.ref is not None:
+                return arm.ref.edge_nodes(a_h[lo:hi], b_h[lo:hi], clr, cdc, want_hit=False)[0]
+            return arm.om.edge_nodes(a_h[lo:hi], b_h[lo:hi], clr, cdc, nthreads=1, full=False)[0]
+        t0 = time.perf_counter()
+        one = part(0)
+        t1 = time.perf_counter() - t0
+        with ThreadPoolExecutor(cores) as pool:
+            t0 = time.perf_counter()
+            parts = list(pool.map(part, range(cores)))
+            tc = time.perf_counter() - t0
+        want = np.concatenate(parts)
+        got = free_d[:m_s].cpu().numpy().astype(bool)
+        cpu = {"value": m_s / tc, "unit": UNIT, "cores": cores, "kind": arm.kind,
+               "sample": f"first {m_s} segments of the step, isSimplePathFreeBetweenNodes one by one, {cores} host threads "
+                         f"over slices, {tc:.1f} s", "single_thread_value": len(one) / t1}
+        parity = {"segments_checked": int(m_s), "verdict_mismatch": int((want != got).sum())}
+        arm.close()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6553.0))
+        ms_launch = ms_max / args.steps
+        achieved = lookups / args.steps * 32.0 / (ms_launch * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"MU: gather-kernel microbench, {m_e} random directed segments per GPU per step (length "
+                                       f"U[0.2, 1.5] m) on the {args.mu_map} map ({vox.shape[0]}^3 voxels), one ctp_edge_check_dev "
+                                       "call per step", "segments_per_step_per_gpu": m_e, "layout": dmap.layout_name(),
+                           "min_clearance": clr, "collision_distance_check": cdc,
+                           "l2": f"endpoints ({m_e * 48 >> 20} MiB per step) exceed the 126 MB L2; the grid is re-read by design"},
+                "lookups_per_s": lookups / (ms_max * 1e-3), "lookups_per_segment": lookups / args.steps / m_e,
+                "free_edge_fraction": free_frac,
+                "roofline": {"bound": "hbm", "kernel": "k_edge_flat", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+                             "ms_per_launch": ms_launch},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": cpu, "parity": parity}
+        emit_line(line)
+    dmap.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C5"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C5", "MU"])
+    ap.add_argument("--mu-map", default="C2", choices=["C1", "C2", "C3"], help="MU: map of the gather-kernel microbench")
+    ap.add_argument("--mu-edges", type=int, default=1 << 24, help="MU: random segments per GPU per step")
     ap.add_argument("--maps", type=int, default=0, help="C5: maps per GPU per step (default 64)")
     ap.add_argument("--map-streams", type=int, default=4, help="C5: streams the per-map batches are spread over")
     ap.add_argument("--map-graphs", action="store_true", help="C5: replay each map's batch from a CUDA graph (measured: no gain, the sweep is not launch-bound)")
@@ -540,6 +676,11 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.workload == "MU" and args.impl != "reference":
+        run_microbench(args, rank, world)
+        return
+    if args.workload == "MU":
+        args.workload = "C2"  # no separate CPU arm for the microbench: its own cpu_baseline leg carries the comparison
     if args.workload == "C5":
         if args.impl == "reference":
             args.workload = "C2"  # the CPU arm of the sweep is the C2 arm: same grid size, nodes and checks per query
