@@ -735,7 +735,7 @@ def test_multi_map_sweep(orc):
             h[0].close()
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CTP_SOAK_SEEDS", "12"))))  # CTP_SOAK_SEEDS=200 for a soak run
 def test_randomized_differential(orc, seed):
     """random map size / extents / clearance / step / k / node count / layout: whole sampleMultiple, the
     generic segment check, gradients, shortest paths and one shorten + deformability round against the oracle"""
