@@ -312,14 +312,19 @@ class DeviceMap:
         _check(lib().ctp_gradient(self._h, _ptr(xyz), len(xyz), _ptr(g), _ptr(c)))
         return g, c
 
-    def edge_check(self, a, b, clr, cdc, mode=EDGE_NODES, group=0):
+    def edge_check(self, a, b, clr, cdc, mode=EDGE_NODES, group=0, pinned=False, out=None):
+        """out: (free u8, hit f64 x3, hit_idx i32, lookups i32) arrays to reuse (e.g. page-locked ones)"""
         a = _np(a, np.float64).reshape(-1, 3)
         b = _np(b, np.float64).reshape(-1, 3)
         m = len(a)
-        free = np.empty(m, dtype=np.uint8)
-        hit = np.empty((m, 3))
-        hit_idx = np.empty(m, dtype=np.int32)
-        lookups = np.empty(m, dtype=np.int32)
+        if out is not None:
+            free, hit, hit_idx, lookups = out
+        else:
+            alloc = pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dtype=dt))
+            free = alloc((m,), np.uint8)
+            hit = alloc((m, 3), np.float64)
+            hit_idx = alloc((m,), np.int32)
+            lookups = alloc((m,), np.int32)
         _check(lib().ctp_edge_check(self._h, _ptr(a), _ptr(b), m, clr, cdc, mode, group, _ptr(free), _ptr(hit),
                                     _ptr(hit_idx), _ptr(lookups)))
         return free.astype(bool), hit, hit_idx, lookups

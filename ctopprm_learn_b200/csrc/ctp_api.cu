@@ -771,6 +771,8 @@ extern "C" int ctp_edge_check_indexed_dev(ctp_map *m, const double *nodes, int64
   return launch_edges(m, group ? group : 1, S, cnt, clr, cdc, 0, O, (cudaStream_t)stream);
 }
 
+static int pipe_init(ctp_map *m);  // streams and events of the chunk pipelines (defined with them below)
+
 static int auto_group(const double *a, const double *b, int64_t cnt, double cdc) {
   const int64_t probe = std::min<int64_t>(cnt, 4096);
   double sum = 0;
@@ -791,6 +793,51 @@ extern "C" int ctp_edge_check(ctp_map *m, const double *a, const double *b, int6
   if (cnt == 0) return CTP_OK;
   REQUIRE(a && b && free_out, "null buffer");
   CK(cudaSetDevice(m->device));
+  if (group == 0) group = auto_group(a, b, cnt, cdc);
+  const int64_t CH = (int64_t)1 << 20;  // segments per chunk of the copy / compute / copy pipeline
+  if (cnt > 2 * CH) {
+    // large batches: endpoints go up, verdicts come back and the kernel runs on three streams over double-buffered
+    // chunks, so that with page-locked host buffers the call costs the slower of the two copy directions
+    CKR(pipe_init(m));
+    const size_t per = 2 * align_up(CH * 24) + align_up(CH) + align_up(CH * 24) + 2 * align_up(CH * 4);
+    CKR(arena_reserve(m->io, 2 * per + 1024));
+    IoScope sc(m);
+    struct { double *a, *b, *h; uint8_t *f; int32_t *hi, *l; } B[2];
+    for (int i = 0; i < 2; i++) {
+      B[i].a = arena_take<double>(m->io, CH * 3);
+      B[i].b = arena_take<double>(m->io, CH * 3);
+      B[i].f = arena_take<uint8_t>(m->io, CH);
+      B[i].h = hit ? arena_take<double>(m->io, CH * 3) : nullptr;
+      B[i].hi = hit_idx ? arena_take<int32_t>(m->io, CH) : nullptr;
+      B[i].l = lookups ? arena_take<int32_t>(m->io, CH) : nullptr;
+    }
+    cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1], s_out = m->pipe_st[2];
+    const int64_t n_chunks = (cnt + CH - 1) / CH;
+    for (int64_t c = 0; c < n_chunks; c++) {
+      const int bi = (int)(c & 1);
+      const int64_t e0 = c * CH, len = std::min(CH, cnt - e0);
+      if (c >= 2) CK(cudaStreamWaitEvent(s_in, m->ev_comp[bi], 0));  // the kernel that read this buffer last
+      CK(cudaMemcpyAsync(B[bi].a, a + 3 * e0, len * 24, cudaMemcpyHostToDevice, s_in));
+      CK(cudaMemcpyAsync(B[bi].b, b + 3 * e0, len * 24, cudaMemcpyHostToDevice, s_in));
+      CK(cudaEventRecord(m->ev_in[bi], s_in));
+      CK(cudaStreamWaitEvent(s_comp, m->ev_in[bi], 0));
+      if (c >= 2) CK(cudaStreamWaitEvent(s_comp, m->ev_out[bi], 0));  // its previous outputs have left
+      CKR(ctp_edge_check_dev(m, B[bi].a, B[bi].b, len, clr, cdc, mode, group, B[bi].f, B[bi].h, B[bi].hi, B[bi].l, s_comp));
+      CK(cudaEventRecord(m->ev_comp[bi], s_comp));
+      CK(cudaStreamWaitEvent(s_out, m->ev_comp[bi], 0));
+      CK(cudaMemcpyAsync(free_out + e0, B[bi].f, len, cudaMemcpyDeviceToHost, s_out));
+      if (hit) CK(cudaMemcpyAsync(hit + 3 * e0, B[bi].h, len * 24, cudaMemcpyDeviceToHost, s_out));
+      if (hit_idx) CK(cudaMemcpyAsync(hit_idx + e0, B[bi].hi, len * 4, cudaMemcpyDeviceToHost, s_out));
+      if (lookups) CK(cudaMemcpyAsync(lookups + e0, B[bi].l, len * 4, cudaMemcpyDeviceToHost, s_out));
+      CK(cudaEventRecord(m->ev_out[bi], s_out));
+    }
+    m->io_h2d += (unsigned long long)cnt * 48;
+    m->io_d2h += (unsigned long long)cnt * (1 + (hit ? 24 : 0) + (hit_idx ? 4 : 0) + (lookups ? 4 : 0));
+    CK(cudaStreamSynchronize(s_out));
+    CK(cudaStreamSynchronize(s_comp));
+    CK(cudaStreamSynchronize(s_in));
+    return CTP_OK;
+  }
   CKR(arena_reserve(m->io, 2 * align_up(cnt * 24) + align_up(cnt) + align_up(cnt * 24) + 2 * align_up(cnt * 4)));
   IoScope sc(m);
   double *d_a = arena_take<double>(m->io, cnt * 3), *d_b = arena_take<double>(m->io, cnt * 3);
@@ -800,7 +847,6 @@ extern "C" int ctp_edge_check(ctp_map *m, const double *a, const double *b, int6
   int32_t *d_l = lookups ? arena_take<int32_t>(m->io, cnt) : nullptr;
   CK(cudaMemcpyAsync(d_a, a, cnt * 24, cudaMemcpyHostToDevice, 0));
   CK(cudaMemcpyAsync(d_b, b, cnt * 24, cudaMemcpyHostToDevice, 0));
-  if (group == 0) group = auto_group(a, b, cnt, cdc);
   CKR(ctp_edge_check_dev(m, d_a, d_b, cnt, clr, cdc, mode, group, d_f, d_h, d_hi, d_l, 0));
   CK(cudaMemcpyAsync(free_out, d_f, cnt, cudaMemcpyDeviceToHost, 0));
   if (hit) CK(cudaMemcpyAsync(hit, d_h, cnt * 24, cudaMemcpyDeviceToHost, 0));

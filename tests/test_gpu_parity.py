@@ -1015,3 +1015,29 @@ def test_two_devices_in_one_process(orc):
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
     n0 = om.sample_reject(s[0], g[0], cand[0], CLR, n)[0]
     _csr_equal(outs[1][0], 0, om.build_prm(n0, CLR, CDC, nthreads=8))
+
+
+def test_large_segment_batch_through_the_chunked_host_path(c1):
+    """ctp_edge_check with more than 2^21 segments runs as a copy / compute / copy pipeline over chunks of 2^20:
+    every output must equal the single-shot device path's"""
+    import torch
+    m, om, c, e = c1
+    cnt = (1 << 21) + (1 << 20) + 12345
+    a, b = synth.random_edges(c, e, cnt, 5, lo=0.0, hi=1.2)
+    free, hit, hit_idx, lookups = m.edge_check(a, b, CLR, CDC, group=1)
+    dev = torch.device("cuda")
+    a_d, b_d = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    f_d = torch.zeros(cnt, dtype=torch.uint8, device=dev)
+    h_d = torch.zeros((cnt, 3), dtype=torch.float64, device=dev)
+    hi_d = torch.zeros(cnt, dtype=torch.int32, device=dev)
+    l_d = torch.zeros(cnt, dtype=torch.int32, device=dev)
+    m.edge_check_dev(a_d, b_d, CLR, CDC, f_d, group=1, hit=h_d, hit_idx=hi_d, lookups=l_d)
+    torch.cuda.synchronize()
+    assert np.array_equal(free, f_d.cpu().numpy().astype(bool))
+    assert np.array_equal(hit, h_d.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(hit_idx, hi_d.cpu().numpy()) and np.array_equal(lookups, l_d.cpu().numpy())
+    f0 = om.edge_nodes(a[:200000], b[:200000], CLR, CDC, nthreads=8)[0]
+    assert np.array_equal(free[:200000], f0)
+    # pinned outputs, verdicts only
+    fr2 = m.edge_check(a, b, CLR, CDC, group=1, pinned=True)[0]
+    assert np.array_equal(fr2, free)
