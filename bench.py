@@ -857,7 +857,7 @@ def main():
         torch.cuda.synchronize()
         sssp_ms = e0.elapsed_time(e1) / reps
         reach = float(torch.isfinite(dist_d[:, 1]).float().mean().item())
-        # one query alone: the library spreads it over a cluster of 8 CTAs (distributed shared memory)
+        # one query alone: the library spreads it over a cluster of 16 CTAs (distributed shared memory, rows staged on chip)
         qi = int(torch.isfinite(dist_d[:, 1]).float().argmax().item())
         off1 = (nnz_off_d[qi:qi + 2] - nnz_off_d[qi]).contiguous()
         lo1, hi1 = int(nnz_off_d[qi].item()), int(nnz_off_d[qi + 1].item())
@@ -878,7 +878,7 @@ def main():
         sssp_leg = {"ms_per_step": sssp_ms, "queries": q, "ms_per_query_batched": sssp_ms / q,
                     "single_query_latency_ms": single_sssp_ms, "goal_reachable_fraction": reach,
                     "api": "ctp_sssp_dev, CUDA events (batched: one CTA per query, distances in shared memory; one query "
-                           "alone: a cluster of 8 CTAs, distances sliced over distributed shared memory)"}
+                           "alone: a cluster of 16 CTAs, distances sliced over distributed shared memory, its rows staged on chip)"}
         if rank == 0 and world == 1 and not args.no_cpu:
             # CPU: the oracle's binary-heap Dijkstra (include/dijkstra.hpp:83-176 restated) on the same CSRs
             from oracle import orc as _orc

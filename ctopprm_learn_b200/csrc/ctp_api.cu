@@ -86,6 +86,7 @@ struct ctp_map {
   int64_t h_off_cap = 0;
   int64_t pipe_chunk = 0;    // queries per chunk (0 = automatic)
   bool reject_layout_auto = true;  // large grids: rejection reads the CELL8 records when they exist
+  bool sssp_cluster_big = true;  // clusters of 16 CTAs (opt-in size) are tried for very small batches until one fails
   int sssp_smem_optin = -1;   // opt-in shared memory per CTA of this device, -1 until the graph kernels were configured
   unsigned knn_smem_set = 0;  // bit K: the dynamic shared-memory limit of the k-NN kernels <K> has been raised
   int64_t pipe_nu_seen = 0;  // largest n_used (candidates consumed by a query) seen by the running pipeline call
@@ -1330,35 +1331,59 @@ extern "C" int ctp_sssp_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row
     smem_optin = v;
     CK(cudaFuncSetAttribute(k_sssp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
     CK(cudaFuncSetAttribute(k_sssp_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, v - 8192));
-    CK(cudaFuncSetAttribute(k_sssp_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, v - 8192));
+    CK(cudaFuncSetAttribute(k_sssp_cluster<CTP_SSSP_CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, v - 8192));
+    CK(cudaFuncSetAttribute(k_sssp_cluster<CTP_SSSP_CL_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, v - 8192));
+    if (cudaFuncSetAttribute(k_sssp_cluster<CTP_SSSP_CL_BIG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      m->sssp_cluster_big = false;
+    }
   }
-  // one query per cluster of 8 CTAs (distances sliced over distributed shared memory): when few queries are in
-  // flight, or when a query does not fit one CTA's shared memory
-  const int slice = (int)(((n + CTP_SSSP_CL - 1) / CTP_SSSP_CL + 31) / 32 * 32);
-  const size_t smem_c = (size_t)slice * 8 + (size_t)(slice / 32) * 8 + 16;  // distances, frontier words, their snapshot
+  // one query per cluster of CTAs (distances sliced over distributed shared memory): when few queries are in
+  // flight, or when a query does not fit one CTA's shared memory.  16 CTAs (opt-in cluster size) when the GPU would
+  // otherwise idle: twice the shared memory, so the rows of a 10^4-node roadmap are staged on chip as well.
   const bool fits_one = n <= 65535 && smem_f <= (size_t)smem_optin - 8192;
-  const bool cluster_ok = m->sssp_frontier && !label && smem_c <= (size_t)smem_optin - 8192 && n >= 64;
-  const bool want_cluster = m->sssp_cluster < 0 ? (q * CTP_SSSP_CL <= 2 * (int64_t)m->sm_count || !fits_one) : m->sssp_cluster != 0;
-  if (cluster_ok && want_cluster) {
+  auto launch_cluster = [&](int CL) -> bool {
+    const int slice = (int)(((n + CL - 1) / CL + 31) / 32 * 32);
+    const size_t base = sssp_cluster_smem(slice, 0), limit = (size_t)smem_optin - 8192;
+    if (base > limit) return false;
+    int cap_e = (int)std::min<size_t>((limit - base) / 12, (size_t)1 << 24);
+    if (cap_e < 4 * slice) cap_e = 0;  // not worth staging
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(q * CTP_SSSP_CL));
+    cfg.gridDim = dim3((unsigned)(q * CL));
     cfg.blockDim = dim3(CTP_SSSP_CL_THREADS);
-    cfg.dynamicSmemBytes = smem_c;
+    cfg.dynamicSmemBytes = sssp_cluster_smem(slice, cap_e);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CTP_SSSP_CL;
+    attr[0].val.clusterDim.x = (unsigned)CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, k_sssp_cluster, n, slice, row_ptr, col, w, nnz_off, src, ns, dist, pred) == cudaSuccess) {
+    cudaError_t e = CL == CTP_SSSP_CL_BIG
+                        ? cudaLaunchKernelEx(&cfg, k_sssp_cluster<CTP_SSSP_CL_BIG>, n, slice, cap_e, row_ptr, col, w, nnz_off, src,
+                                             ns, dist, pred)
+                        : cudaLaunchKernelEx(&cfg, k_sssp_cluster<CTP_SSSP_CL>, n, slice, cap_e, row_ptr, col, w, nnz_off, src, ns,
+                                             dist, pred);
+    if (e != cudaSuccess) cudaGetLastError();  // forget it: the caller falls back
+    return e == cudaSuccess;
+  };
+  const bool cluster_ok = m->sssp_frontier && !label && n >= 64;
+  const bool want_cluster = m->sssp_cluster < 0 ? (q * CTP_SSSP_CL <= 2 * (int64_t)m->sm_count || !fits_one) : m->sssp_cluster != 0;
+  if (cluster_ok && want_cluster) {
+    if (m->sssp_cluster_big && q * CTP_SSSP_CL_BIG <= 2 * (int64_t)m->sm_count && n >= 1024) {
+      if (launch_cluster(CTP_SSSP_CL_BIG)) {
+        m->launches++;
+        return CTP_OK;
+      }
+      m->sssp_cluster_big = false;  // this device or partition cannot co-schedule 16 CTAs
+    }
+    if (launch_cluster(CTP_SSSP_CL)) {
       m->launches++;
       return CTP_OK;
     }
-    // a device or partition that cannot co-schedule the cluster: forget the error, use the one-CTA kernels from now on
-    cudaGetLastError();
-    m->sssp_cluster = 0;
+    if (sssp_cluster_smem((int)(((n + CTP_SSSP_CL - 1) / CTP_SSSP_CL + 31) / 32 * 32), 0) <= (size_t)smem_optin - 8192)
+      m->sssp_cluster = 0;  // the launch itself failed: use the one-CTA kernels from now on
   }
   if (m->sssp_frontier && fits_one) {
     k_sssp_frontier<<<(unsigned)q, CTP_SSSP_THREADS, smem_f, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label);

@@ -223,12 +223,21 @@ k_sssp_frontier(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *_
 // scan-and-search distribution of the one-CTA kernel.  Used when few queries are in flight (a single query keeps
 // 8 SMs busy instead of one) and when a query's distances do not fit one CTA's shared memory (up to ~170 000
 // nodes stay on chip).  Same fixed point, so the distances are Dijkstra's bit for bit.
-#define CTP_SSSP_CL 8
+#define CTP_SSSP_CL 8        // portable cluster size
+#define CTP_SSSP_CL_BIG 16   // opt-in cluster size: twice the shared memory, enough to hold a 10^4-node roadmap's rows
 #ifndef CTP_SSSP_CL_THREADS
 #define CTP_SSSP_CL_THREADS 1024
 #endif
+// bytes of dynamic shared memory for a slice of `slice` nodes and room for `cap_e` staged CSR entries
+__host__ __device__ inline size_t sssp_cluster_smem(int slice, int cap_e) {
+  return (size_t)slice * 8 + (size_t)cap_e * 8 + (size_t)(slice / 32) * 8 + (size_t)(slice + 1) * 4 + (size_t)cap_e * 4 + 16;
+}
+// CL = CTAs per cluster.  cap_e > 0: a CTA whose rows hold at most cap_e entries copies them (row offsets, column
+// ids, weights) into its shared memory first, so that a sweep reads the roadmap on chip instead of paying two L2
+// round trips per frontier node after every barrier (the barrier's acquire invalidates the L1).
+template <int CL>
 __global__ void __launch_bounds__(CTP_SSSP_CL_THREADS)
-k_sssp_cluster(int64_t n, int slice, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+k_sssp_cluster(int64_t n, int slice, int cap_e, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                const double *__restrict__ w, const int64_t *__restrict__ nnz_off, const int32_t *__restrict__ src, int ns,
                double *__restrict__ dist_out, int32_t *__restrict__ pred_out) {
   namespace cg = cooperative_groups;
@@ -237,7 +246,7 @@ k_sssp_cluster(int64_t n, int slice, const int32_t *__restrict__ row_ptr, const 
   __shared__ int s_work[3];
   const int rank = (int)cluster.block_rank();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  const int64_t q = blockIdx.x / CTP_SSSP_CL;
+  const int64_t q = blockIdx.x / CL;
   const int32_t *rp = row_ptr + q * (n + 1);
   const int32_t *cq = col + nnz_off[q];
   const double *wq = w + nnz_off[q];
@@ -246,14 +255,28 @@ k_sssp_cluster(int64_t n, int slice, const int32_t *__restrict__ row_ptr, const 
   const int mine = max(0, min(slice, nn - lo));  // nodes this CTA owns
   const int words = slice >> 5;
   unsigned long long *dist = s_mem;
+  double *s_w = reinterpret_cast<double *>(s_mem + slice);
   // two frontier bit arrays: sweep k consumes B[k & 1] (its owner only) while relaxations set bits in B[(k + 1) & 1]
   // of whichever CTA owns the target; s_work[k % 3] of the owner is raised along with a bit, so that after the ONE
-  // cluster barrier of the sweep everybody learns from the eight flags whether another sweep is needed
-  unsigned *bits0 = reinterpret_cast<unsigned *>(s_mem + slice);
+  // cluster barrier of the sweep everybody learns from the CL flags whether another sweep is needed
+  unsigned *bits0 = reinterpret_cast<unsigned *>(s_w + cap_e);
   unsigned *bits1 = bits0 + words;
+  int32_t *s_rp = reinterpret_cast<int32_t *>(bits1 + words);
+  int32_t *s_col = s_rp + slice + 1;
   for (int u = threadIdx.x; u < slice; u += blockDim.x) dist[u] = CTP_SSSP_INF;
   for (int t = threadIdx.x; t < 2 * words; t += blockDim.x) bits0[t] = 0;
   if (threadIdx.x < 3) s_work[threadIdx.x] = 0;
+  // stage the rows this CTA owns
+  const int e_base = mine > 0 ? rp[lo] : 0;
+  const int e_cnt = mine > 0 ? rp[lo + mine] - e_base : 0;
+  const bool staged = cap_e > 0 && e_cnt <= cap_e;
+  if (staged) {
+    for (int i = threadIdx.x; i <= mine; i += blockDim.x) s_rp[i] = rp[lo + i] - e_base;
+    for (int i = threadIdx.x; i < e_cnt; i += blockDim.x) {
+      s_col[i] = __ldg(cq + e_base + i);
+      s_w[i] = __ldg(wq + e_base + i);
+    }
+  }
   cluster.sync();
   if (rank == 0)
     for (int i = threadIdx.x; i < ns; i += blockDim.x) {
@@ -269,8 +292,8 @@ k_sssp_cluster(int64_t n, int slice, const int32_t *__restrict__ row_ptr, const 
   for (int k = 0;; k++) {
     // did the previous sweep (or the sources) leave work anywhere in the cluster?
     int work = 0;
-    if (threadIdx.x < CTP_SSSP_CL) work = cluster.map_shared_rank(s_work, threadIdx.x)[(k + 2) % 3];
-    if (__syncthreads_or(work) == 0) break;  // the same eight flags on every CTA
+    if (threadIdx.x < CL) work = cluster.map_shared_rank(s_work, threadIdx.x)[(k + 2) % 3];
+    if (__syncthreads_or(work) == 0) break;  // the same CL flags on every CTA
     if (threadIdx.x == 0) s_work[(k + 1) % 3] = 0;  // last read before the previous barrier, next raised after this sweep's
     unsigned *cur = (k & 1) ? bits1 : bits0;
     unsigned *nxt = (k & 1) ? bits0 : bits1;
@@ -284,10 +307,11 @@ k_sssp_cluster(int64_t n, int slice, const int32_t *__restrict__ row_ptr, const 
         const int lu = (word << 5) + __ffs(m) - 1;  // (8 or 16 lanes per node measured slower: 0.42 / 0.34 ms against 0.29 ms)
         m &= m - 1;
         const double du = __longlong_as_double((long long)dist[lu]);
-        const int eb = rp[lo + lu], ee = rp[lo + lu + 1];
+        const int eb = staged ? s_rp[lu] : rp[lo + lu], ee = staged ? s_rp[lu + 1] : rp[lo + lu + 1];
         for (int e = eb + lane; e < ee; e += 32) {
-          const int v = __ldg(cq + e);
-          const unsigned long long nd = (unsigned long long)__double_as_longlong(du + __ldg(wq + e));
+          const int v = staged ? s_col[e] : __ldg(cq + e);
+          const double we = staged ? s_w[e] : __ldg(wq + e);
+          const unsigned long long nd = (unsigned long long)__double_as_longlong(du + we);
           const int owner = v / slice, lv = v - owner * slice;
           unsigned long long *rd = cluster.map_shared_rank(dist, owner) + lv;
           // 64-bit minimum as a compare-and-swap loop: a 64-bit atomicMin on shared memory is emulated under a
@@ -314,12 +338,14 @@ k_sssp_cluster(int64_t n, int slice, const int32_t *__restrict__ row_ptr, const 
     const unsigned long long dv = dist[lv];
     int best = -1;
     if (dv != CTP_SSSP_INF && dv != 0ull) {
-      for (int e = rp[v]; e < rp[v + 1]; e++) {
-        const int u = cq[e];
+      const int eb = staged ? s_rp[lv] : rp[v], ee = staged ? s_rp[lv + 1] : rp[v + 1];
+      for (int e = eb; e < ee; e++) {
+        const int u = staged ? s_col[e] : cq[e];
         const int owner = u / slice;
         const unsigned long long du = cluster.map_shared_rank(dist, owner)[u - owner * slice];
         if (du >= dv) continue;
-        const unsigned long long cand = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)du) + wq[e]);
+        const double we = staged ? s_w[e] : wq[e];
+        const unsigned long long cand = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)du) + we);
         if (cand == dv && (best < 0 || u < best)) best = u;
       }
     }

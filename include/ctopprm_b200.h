@@ -103,7 +103,7 @@ int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int r
 #define CTP_TUNE_SSSP_FRONTIER 4 /* ctp_sssp: 1 = explicit frontier, edge-parallel relaxation (default), 0 = flag scan */
 #define CTP_TUNE_PIPE_HEAD 5     /* chunk pipelines: upload value*n (+256) candidates per query first, the tails only if a query
                                    of the chunk is still short (default 2.3; 0 = always upload whole streams) */
-#define CTP_TUNE_SSSP_CLUSTER 6  /* ctp_sssp: one query per cluster of 8 CTAs, distances in distributed shared memory: 1 whenever possible, 0 never, -1 automatic (default: few queries in flight, or a query too large for one CTA) */
+#define CTP_TUNE_SSSP_CLUSTER 6  /* ctp_sssp: one query per cluster of 8 or 16 CTAs, distances (and, with 16, the rows) in distributed shared memory: 1 whenever possible, 0 never, -1 automatic (default: few queries in flight, or a query too large for one CTA) */
 #define CTP_TUNE_PIPE_CHUNK 2   /* queries per chunk of the ctp_sample_multiple copy/compute pipeline (0 = automatic) */
 int ctp_set_tunable(ctp_map *map, int key, double value);
 /* number of kernels this handle has enqueued since the last reset (host-side counter) */

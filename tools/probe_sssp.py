@@ -38,7 +38,7 @@ def search_one_cta():
 build(); torch.cuda.synchronize()
 search(); d_cluster = dist.clone(); search_one_cta(); torch.cuda.synchronize()
 print("cluster == one CTA:", bool(torch.equal(d_cluster, dist)))
-for f, name in ((build, "PRM build"), (search, "shortest path (cluster of 8 CTAs)"), (search_one_cta, "shortest path (one CTA)")):
+for f, name in ((build, "PRM build"), (search, "shortest path (cluster of 16 CTAs, rows staged on chip)"), (search_one_cta, "shortest path (one CTA)")):
     for _ in range(5): f()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
