@@ -331,20 +331,53 @@ def run_multimap(args, rank, world):
     streams = [torch.cuda.Stream() for _ in range(max(1, args.map_streams))]
     main = torch.cuda.current_stream()
 
-    def step():
+    nbr_d = torch.zeros((q, n, K_NN), dtype=torch.int32, device=dev)
+    fr_d = torch.zeros((q, n, K_NN), dtype=torch.uint8, device=dev)
+    col_all = torch.zeros(n_maps * cap, dtype=torch.int32, device=dev)
+    w_all = torch.zeros(n_maps * cap, dtype=torch.float64, device=dev)
+    off_all = torch.zeros(q + 1, dtype=torch.int64, device=dev)
+    maps[0].reserve(q, n, m_c, K_NN)  # the handle that runs the map-independent stages for the whole step
+
+    def fan_out():
         ev = torch.cuda.Event()
         ev.record(main)
         for st in streams:
             st.wait_event(ev)
+
+    def fan_in():
+        for st in streams:
+            e2 = torch.cuda.Event()
+            e2.record(st)
+            main.wait_event(e2)
+
+    def step_per_map():
+        fan_out()
         for mi, dm in enumerate(maps):
             st = streams[mi % len(streams)]
             a, b = mi * qpm, (mi + 1) * qpm
             dm.sample_reject_dev(s_d[a:b], g_d[a:b], cand_d[a:b], qpm, m_c, clr, n, nodes_d[a:b], nf_d[a:b], nu_d[a:b], stream=st)
             dm.build_prm_dev(nodes_d[a:b], qpm, n, K_NN, clr, cdc, rp_d[a:b], col_d[mi], w_d[mi], cap, off_d[mi], stream=st)
-        for st in streams:
-            e2 = torch.cuda.Event()
-            e2.record(st)
-            main.wait_event(e2)
+        fan_in()
+
+    def step_staged():
+        # rejection and the directed checks map by map; the neighbour and adjacency stages never look at a map and
+        # run once over all queries of the step (ctp_knn_dev / ctp_edge_check_knn_dev / ctp_csr_from_directed_dev)
+        fan_out()
+        for mi, dm in enumerate(maps):
+            st = streams[mi % len(streams)]
+            a, b = mi * qpm, (mi + 1) * qpm
+            dm.sample_reject_dev(s_d[a:b], g_d[a:b], cand_d[a:b], qpm, m_c, clr, n, nodes_d[a:b], nf_d[a:b], nu_d[a:b], stream=st)
+        fan_in()
+        maps[0].knn_dev(nodes_d, q, n, K_NN, nbr_d, stream=main)
+        fan_out()
+        for mi, dm in enumerate(maps):
+            st = streams[mi % len(streams)]
+            a, b = mi * qpm, (mi + 1) * qpm
+            dm.edge_check_knn_dev(nodes_d[a:b], qpm, n, K_NN, nbr_d[a:b], clr, cdc, fr_d[a:b], stream=st)
+        fan_in()
+        maps[0].csr_from_directed_dev(nodes_d, q, n, K_NN, nbr_d, fr_d, rp_d, col_all, w_all, n_maps * cap, off_all, stream=main)
+
+    step = step_per_map if args.c5_per_map else step_staged
 
     def sync_all():
         torch.cuda.synchronize()
@@ -492,7 +525,10 @@ def run_multimap(args, rank, world):
                 "config": {"workload": f"C5: multi-map sweep, {n_maps} procedurally generated random-columns ESDFs per GPU per step "
                                        f"({nvox}^3 @ {extent / nvox:.3f} m, seeds 100.., generated on the device), {qpm} queries of {n} "
                                        f"nodes per map, one device handle per map, {len(streams)} streams"
-                                       + (", each map's batch replayed from a CUDA graph" if args.map_graphs else ""),
+                                       + (", each map's batch replayed from a CUDA graph" if args.map_graphs else "")
+                                       + (", whole build per map" if (args.c5_per_map or args.map_graphs) else
+                                          "; rejection and directed checks map by map, the map-independent neighbour and "
+                                          "adjacency stages once over all queries of the step"),
                            "maps_per_step_per_gpu": n_maps, "queries_per_map": qpm, "nodes_per_query": n, "k": K_NN,
                            "parallelism": f"maps sharded over {world} GPU(s), no data-path collective",
                            "l2": f"{n_maps} grids of 64 MiB are swept per step: {n_maps * 64} MiB >> 126 MB L2",
@@ -653,6 +689,7 @@ def main():
     ap.add_argument("--mu-edges", type=int, default=1 << 24, help="MU: random segments per GPU per step")
     ap.add_argument("--maps", type=int, default=0, help="C5: maps per GPU per step (default 64)")
     ap.add_argument("--map-streams", type=int, default=4, help="C5: streams the per-map batches are spread over")
+    ap.add_argument("--c5-per-map", action="store_true", help="C5: whole build per map (ctp_build_prm_dev) instead of the staged sweep")
     ap.add_argument("--map-graphs", action="store_true", help="C5: replay each map's batch from a CUDA graph (measured: no gain, the sweep is not launch-bound)")
     ap.add_argument("--map-threads", type=int, default=4, help="C5 e2e: host threads driving the map handles")
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (default: per workload)")

@@ -74,6 +74,7 @@ _SIGS = {
     "ctp_build_prm": [_P, _P, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
     "ctp_build_prm_dev": [_P, _P, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P, _P],
     "ctp_csr_from_directed": [_P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _I64, _P],
+    "ctp_edge_check_knn_dev": [_P, _P, _I64, _I64, _I, _P, _D, _D, _P, _P],
     "ctp_csr_from_directed_dev": [_P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _I64, _P, _P],
     "ctp_sample_multiple": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
     "ctp_sssp": [_P, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _P, _P],
@@ -526,6 +527,14 @@ class DeviceMap:
 
     def knn_dev(self, nodes, q, n, k, idx, d2=None, stream=None):
         _check(lib().ctp_knn_dev(self._h, _ptr(nodes), q, n, k, _ptr(idx), _ptr(d2), _stream_ptr(stream)))
+
+    def csr_from_directed_dev(self, nodes, q, n, k, nbr, directed_free, row_ptr, col, w, cap, nnz_off, stream=None):
+        _check(lib().ctp_csr_from_directed_dev(self._h, _ptr(nodes), q, n, k, _ptr(nbr), _ptr(directed_free), _ptr(row_ptr),
+                                               _ptr(col), _ptr(w), cap, _ptr(nnz_off), _stream_ptr(stream)))
+
+    def edge_check_knn_dev(self, nodes, q, n, k, nbr, clr, cdc, directed_free, stream=None):
+        _check(lib().ctp_edge_check_knn_dev(self._h, _ptr(nodes), q, n, k, _ptr(nbr), clr, cdc, _ptr(directed_free),
+                                            _stream_ptr(stream)))
 
     def build_prm_dev(self, nodes, q, n, k, clr, cdc, row_ptr, col, w, cap, nnz_off, nbr=None, directed_free=None,
                       stream=None):

@@ -1261,6 +1261,27 @@ extern "C" int ctp_build_prm(ctp_map *m, const double *nodes, int64_t q, int64_t
 
 // CSR from a given k-NN table and its directed verdicts (the merge step when the n*k checks were
 // sharded over several GPUs): same symmetric-union rule as ctp_build_prm
+// the middle stage of the PRM build on its own: the q*n*k directed checks of a k-NN table (stride k, -1 = no
+// neighbour) against THIS map.  The neighbour and the adjacency stages do not look at the map, so a sweep over many
+// maps can run them once for all queries and only this stage (and the rejection) map by map.
+extern "C" int ctp_edge_check_knn_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, const int32_t *nbr,
+                                      double clr, double cdc, uint8_t *directed_free, void *stream) {
+  REQUIRE(m && q >= 1 && n >= 2 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument (k must be in [1,16])");
+  REQUIRE(nodes && nbr && directed_free, "null buffer");
+  REQUIRE(cdc > 0, "collision_distance_check must be > 0");
+  REQUIRE(q * n * k < ((int64_t)1 << 31), "q*n*k must fit in int32");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t edges = q * n * k;
+  EdgeSrc S{nodes, nullptr, nullptr, nbr, n, k, 1, k, nullptr};
+  S.small = 1;
+  S.dk = ctp_div_make((uint32_t)k);
+  S.dn = ctp_div_make((uint32_t)n);
+  EdgeOut O{directed_free, nullptr, nullptr, nullptr, m->d_lookups};
+  StageSpan span(m, CTP_STAGE_EDGES, st);
+  return launch_edges(m, m->prm_group, S, edges, clr, cdc, 0, O, st);
+}
+
 extern "C" int ctp_csr_from_directed_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, const int32_t *nbr,
                                          const uint8_t *directed_free, int32_t *row_ptr, int32_t *col, double *w,
                                          int64_t cap, int64_t *nnz_off, void *stream) {

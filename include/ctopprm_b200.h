@@ -209,6 +209,11 @@ int ctp_build_prm_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, i
                       double clr, double cdc, int32_t *nbr, uint8_t *directed_free,
                       int32_t *row_ptr, int32_t *col, double *w, int64_t cap, int64_t *nnz_off,
                       void *stream);
+/* the middle stage alone: the q*n*k directed checks (:355-373) of a given k-NN table nbr (q x n x k, -1 = no
+ * neighbour) against this map -> directed_free (q x n x k).  ctp_knn_dev and ctp_csr_from_directed_dev do not look
+ * at the map: a sweep over many maps runs them once for all queries and only the rejection and this stage per map. */
+int ctp_edge_check_knn_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, int k, const int32_t *nbr,
+                           double clr, double cdc, uint8_t *directed_free, void *stream);
 /* the merge step when the n*k directed checks were sharded (several GPUs each checking a range of
  * source rows with ctp_edge_check_indexed): CSR from a given k-NN table nbr (q x n x k, -1 = no
  * neighbour) and its verdicts directed_free (q x n x k), same symmetric-union rule (:374-385). */

@@ -1041,3 +1041,36 @@ def test_large_segment_batch_through_the_chunked_host_path(c1):
     # pinned outputs, verdicts only
     fr2 = m.edge_check(a, b, CLR, CDC, group=1, pinned=True)[0]
     assert np.array_equal(fr2, free)
+
+
+def test_prm_build_composed_from_its_stages(c1):
+    """ctp_knn_dev -> ctp_edge_check_knn_dev -> ctp_csr_from_directed_dev (the stages a multi-map sweep runs
+    separately) give exactly what ctp_build_prm_dev gives in one call"""
+    import torch
+    m, om, c, e = c1
+    q, n, k = 3, 800, 13
+    s, g, cand = _queries(c, e, q, n, 88)
+    nodes_h = np.stack([om.sample_reject(s[i], g[i], cand[i], CLR, n)[0] for i in range(q)])
+    dev = torch.device("cuda")
+    nodes = torch.from_numpy(nodes_h).to(dev)
+    cap = 2 * q * n * k
+
+    def outs():
+        return (torch.zeros((q, n + 1), dtype=torch.int32, device=dev), torch.zeros(cap, dtype=torch.int32, device=dev),
+                torch.zeros(cap, dtype=torch.float64, device=dev), torch.zeros(q + 1, dtype=torch.int64, device=dev))
+    rp0, col0, w0, off0 = outs()
+    nbr0 = torch.zeros((q, n, k), dtype=torch.int32, device=dev)
+    fr0 = torch.zeros((q, n, k), dtype=torch.uint8, device=dev)
+    m.build_prm_dev(nodes, q, n, k, CLR, CDC, rp0, col0, w0, cap, off0, nbr=nbr0, directed_free=fr0)
+    rp1, col1, w1, off1 = outs()
+    nbr1 = torch.zeros((q, n, k), dtype=torch.int32, device=dev)
+    fr1 = torch.zeros((q, n, k), dtype=torch.uint8, device=dev)
+    m.knn_dev(nodes, q, n, k, nbr1)
+    for i in range(q):  # "one map per query": the middle stage query by query
+        m.edge_check_knn_dev(nodes[i], 1, n, k, nbr1[i], CLR, CDC, fr1[i])
+    m.csr_from_directed_dev(nodes, q, n, k, nbr1, fr1, rp1, col1, w1, cap, off1)
+    torch.cuda.synchronize()
+    assert torch.equal(nbr0, nbr1) and torch.equal(fr0, fr1)
+    assert torch.equal(rp0, rp1) and torch.equal(off0, off1)
+    nnz = int(off0[q])
+    assert torch.equal(col0[:nnz], col1[:nnz]) and torch.equal(w0[:nnz], w1[:nnz])
