@@ -406,7 +406,9 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
 #ifndef CTP_KNN_DIRECT_THREADS
 #define CTP_KNN_DIRECT_THREADS 256  // measured: 64 -> 2.92, 128 -> 2.80, 256 -> 2.73, 512 -> 2.82 ms per C2 step
 #endif
+#ifndef CTP_KNN_DIRECT_KEEP
 #define CTP_KNN_DIRECT_KEEP 48
+#endif
 #define CTP_KNN_SMALL_LIST 8192
 #define CTP_KNN_DIRECT_SMEM (CTP_KNN_DIRECT_KEEP * CTP_KNN_DIRECT_THREADS * 4)
 
