@@ -215,6 +215,30 @@ static void map_fill_params(ctp_map *m, const double c[3], const double e[3]) {
   d.mey = c[1] - 1.0 * max_e / 2.0;
   d.mez = c[2] - 1.0 * max_e / 2.0;
   d.n = m->n;
+  // Is getClearence's position test implied by the index tests of the interpolation?  Every step of the index map
+  // q = ((p - c) * s1 + 1) * s2 is monotone in p, so it is enough to look at the two positions next to the box: the
+  // first one above it must already give floor(q) >= N-1 (rejected as "ceil >= N"), the first one below it q < 1
+  // (floor <= 0: negative is rejected, 0 makes the kernel do the comparisons).  Same operations, one rounding each,
+  // as ctp_w2i on the device.
+  {
+    const double cc[3] = {c[0], c[1], c[2]};
+    const double lo[3] = {d.lox, d.loy, d.loz}, hi[3] = {d.hix, d.hiy, d.hiz};
+    bool ok = d.s1 > 0 && d.s2 > 0;
+    for (int a = 0; a < 3 && ok; a++) {
+      volatile double t = nextafter(hi[a], INFINITY) - cc[a];
+      t = t * d.s1;
+      t = t + 1.0;
+      t = t * d.s2;
+      const double q_hi = t;
+      t = nextafter(lo[a], -INFINITY) - cc[a];
+      t = t * d.s1;
+      t = t + 1.0;
+      t = t * d.s2;
+      const double q_lo = t;
+      ok = (floor(q_hi) >= N - 1.0) && (q_lo < 1.0);
+    }
+    d.box_implied = ok ? 1 : 0;
+  }
   d.nb = (m->n + 3) / 4;
   d.plain = m->d_plain;
   d.cell8 = m->d_cell8;

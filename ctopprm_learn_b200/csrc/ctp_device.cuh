@@ -23,6 +23,7 @@ struct MapDev {
   double dp;                           // max_extents_ / (N - 1)  (src/esdf_map.cpp:124)
   double mex, mey, mez;                // centroid - max_extents_/2 (src/esdf_map.cpp:125)
   int n;
+  int box_implied;                     // 1: outside the box => floor(q) >= N-1 or <= 0 on that axis (checked on the host)
   int nb;                              // bricks per axis
   int tex_cmask, tex_cshift;           // x-slab mosaic of the gather texture: tile (x & cmask, x >> cshift)
   const float *plain;
@@ -114,16 +115,26 @@ template <> struct Corners<CTP_L_BRICK> {
 //   ceil(q)  >= N          <=>  q > N-1
 //   x1 == x0 (q integral)   =>  xd = 0/0 = NaN    => result NaN
 //   otherwise x1 - x0 == 1  =>  xd = (q - x0)/1 = q - floor(q), exact
-template <int L>
-__device__ __forceinline__ double esdf_interp(const MapDev &M, double qx, double qy, double qz) {
+// BOX = true: the caller has not applied getClearence's position test (src/esdf_map.cpp:141-146); it is applied
+// here, but only where the index tests below do not already imply it (see MapDev::box_implied).
+template <int L, bool BOX = false>
+__device__ __forceinline__ double esdf_interp(const MapDev &M, double qx, double qy, double qz, double px = 0.0,
+                                              double py = 0.0, double pz = 0.0) {
   const int x0 = __double2int_rd(qx), y0 = __double2int_rd(qy), z0 = __double2int_rd(qz);
   const double xd = qx - (double)x0, yd = qy - (double)y0, zd = qz - (double)z0;
   // q in [0, N-1] and not integral  <=>  floor(q) in [0, N-2] and q - floor(q) > 0; a NaN q gives
   // a NaN fraction and fails the '>' (the conversion saturates for out-of-range q, which the
   // unsigned range test rejects)
   const unsigned nm2 = (unsigned)(M.n - 2);
-  const bool ok = ((unsigned)x0 <= nm2) & ((unsigned)y0 <= nm2) & ((unsigned)z0 <= nm2) & (xd > 0.0) & (yd > 0.0) &
-                  (zd > 0.0);
+  bool ok = ((unsigned)x0 <= nm2) & ((unsigned)y0 <= nm2) & ((unsigned)z0 <= nm2) & (xd > 0.0) & (yd > 0.0) &
+            (zd > 0.0);
+  if (BOX) {
+    // a position above the box maps to floor(q) >= N-1 and one below it to floor(q) <= 0 (verified on the host for
+    // this map, then true for every position because each step of the index map is monotone), so the six
+    // comparisons are only needed when an index is 0
+    if (ok && (((x0 == 0) | (y0 == 0) | (z0 == 0)) || !M.box_implied))
+      ok = (px >= M.lox) & (px <= M.hix) & (py >= M.loy) & (py <= M.hiy) & (pz >= M.loz) & (pz <= M.hiz);
+  }
   if (!ok) return ctp_nan();
   float v[8];
   Corners<L>::load(M, x0, y0, z0, v);
@@ -147,11 +158,8 @@ __device__ __forceinline__ double ctp_w2i(double p, double c, double s1, double 
 // tests (q >= 0 => round(q) >= 0; q <= N-1 => round(q) < N), so it is not evaluated.
 template <int L>
 __device__ __forceinline__ double esdf_clearance(const MapDev &M, double px, double py, double pz) {
-  const bool inside = (px >= M.lox) & (px <= M.hix) & (py >= M.loy) & (py <= M.hiy) &
-                      (pz >= M.loz) & (pz <= M.hiz);
-  if (!inside) return ctp_nan();
-  return esdf_interp<L>(M, ctp_w2i(px, M.cx, M.s1, M.s2), ctp_w2i(py, M.cy, M.s1, M.s2),
-                        ctp_w2i(pz, M.cz, M.s1, M.s2));
+  return esdf_interp<L, true>(M, ctp_w2i(px, M.cx, M.s1, M.s2), ctp_w2i(py, M.cy, M.s1, M.s2),
+                              ctp_w2i(pz, M.cz, M.s1, M.s2), px, py, pz);
 }
 
 // BaseMap::isInCollision (src/base_map.cpp:7-12): !isfinite(c) || c < clearance

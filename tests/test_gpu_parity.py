@@ -1074,3 +1074,54 @@ def test_prm_build_composed_from_its_stages(c1):
     assert torch.equal(rp0, rp1) and torch.equal(off0, off1)
     nnz = int(off0[q])
     assert torch.equal(col0[:nnz], col1[:nnz]) and torch.equal(w0[:nnz], w1[:nnz])
+
+
+@pytest.mark.parametrize("shift", [0.0, 3.7, 1.0e6, -4.0e9])
+def test_clearance_at_the_box_faces(orc, shift):
+    """positions on, just inside and just outside every face of the map box (and at its corners), where
+    getClearence's position test and the index tests of the interpolation meet; cubic and non-cubic extents,
+    centroids far from the origin (coarse rounding of p - c)"""
+    nvox = 40
+    vox, c, e = synth.random_columns_esdf(nvox, 4.0, 6, 9)
+    vox = (np.abs(vox) + 0.5).astype(np.float32)
+    for ee in (e, e * np.array([1.0, 0.75, 0.5])):
+        cc = c + shift
+        m = capi.DeviceMap(vox, cc, ee, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX)
+        om = orc.OracleMap(vox, cc, ee)
+        try:
+            lo, hi = cc - ee / 2, cc + ee / 2
+            pts = []
+            rng = np.random.default_rng(int(abs(shift)) % 1000 + 1)
+            base = cc + (rng.random((40, 3)) - 0.5) * ee * 0.9
+            for ax in range(3):
+                for face in (lo[ax], hi[ax]):
+                    vals = [face]
+                    for _ in range(6):
+                        vals.append(np.nextafter(vals[-1], np.inf))
+                    v2 = face
+                    for _ in range(6):
+                        v2 = np.nextafter(v2, -np.inf)
+                        vals.append(v2)
+                    vals += [face + 1e-9, face - 1e-9, face + ee[ax] / nvox * 0.5, face - ee[ax] / nvox * 0.5,
+                             face + ee[ax] / nvox, face - ee[ax] / nvox]
+                    for v in vals:
+                        for b in base[:6]:
+                            p = b.copy()
+                            p[ax] = v
+                            pts.append(p)
+            for sx in (lo[0], hi[0]):
+                for sy in (lo[1], hi[1]):
+                    for sz in (lo[2], hi[2]):
+                        pts.append(np.array([sx, sy, sz]))
+            pts = np.array(pts)
+            want = om.clearance(pts)
+            for layout in (capi.LAYOUT_PLAIN, capi.LAYOUT_TEX):
+                m.set_layout(layout)
+                assert np.array_equal(m.clearance(pts), want, equal_nan=True)
+            a = pts[:-8]
+            b = np.roll(a, 7, axis=0)
+            f0 = om.edge_nodes(a, b, 0.1, 0.05, nthreads=4)
+            f1 = m.edge_check(a, b, 0.1, 0.05)
+            assert np.array_equal(f1[0], f0[0]) and np.array_equal(f1[2], f0[2])
+        finally:
+            m.close()
