@@ -47,9 +47,10 @@ def env_int(name, default):
         return default
 
 
-def make_queries(c, e, q_total, n, cand_per_node, lo, hi, out=None):
-    """C4 query set (seed 4); rank slice [lo, hi).  Candidate streams: seed 400000 + query id."""
-    s, g = synth.random_queries(c, e, q_total, 4)
+def make_queries(c, e, q_total, n, cand_per_node, lo, hi, out=None, cfg=None):
+    """C4 query set (seed 4): start / goal ~U in free space of the map `cfg`; rank slice [lo, hi).
+    Candidate streams: seed 400000 + query id."""
+    s, g = synth.random_queries(c, e, q_total, 4, cfg=cfg)
     s, g = s[lo:hi], g[lo:hi]
     m = cand_per_node * n
     cand = out if out is not None else np.empty((hi - lo, m, 3))
@@ -142,6 +143,74 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
+EPSILON_BAND = 1e-9  # north_star: verdicts may differ only where |clearance - min_clearance| < epsilon at the deciding sample
+
+
+def detailed_parity(dmap, om, nodes_d, n, pq, clr, cdc, dev, torch):
+    """Array-by-array comparison of the first pq roadmaps with the CPU restatement (oracle/), counted on the device:
+    k-NN lists, per-directed-edge verdicts, first-hit march indices, CSR columns and FP64 weights.  A verdict mismatch
+    is 'explained' when the clearance of some march sample of that edge lies within EPSILON_BAND of the threshold."""
+    k = K_NN
+    cap = 2 * pq * n * k
+    nbr_d = torch.zeros((pq, n, k), dtype=torch.int32, device=dev)
+    fr_d = torch.zeros((pq, n, k), dtype=torch.uint8, device=dev)
+    rp_d = torch.zeros((pq, n + 1), dtype=torch.int32, device=dev)
+    col_d = torch.zeros(cap, dtype=torch.int32, device=dev)
+    w_d = torch.zeros(cap, dtype=torch.float64, device=dev)
+    off_d = torch.zeros(pq + 1, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream()
+    dmap.build_prm_dev(nodes_d[:pq], pq, n, k, clr, cdc, rp_d, col_d, w_d, cap, off_d, nbr=nbr_d, directed_free=fr_d, stream=st)
+    rows = torch.arange(pq * n, dtype=torch.int32, device=dev).repeat_interleave(k)
+    base = (torch.arange(pq, dtype=torch.int32, device=dev) * n).repeat_interleave(n * k)
+    nb = nbr_d.reshape(-1)
+    to = torch.where(nb >= 0, nb + base, nb)
+    free2 = torch.zeros(pq * n * k, dtype=torch.uint8, device=dev)
+    hidx_d = torch.zeros(pq * n * k, dtype=torch.int32, device=dev)
+    dmap.edge_check_indexed_dev(nodes_d[:pq], pq * n, rows, to, clr, cdc, free2, hit_idx=hidx_d, stream=st)
+    torch.cuda.synchronize()
+    nodes_h = nodes_d[:pq].cpu().numpy()
+    want = [om.build_prm(nodes_h[i], clr, cdc, k=k, nthreads=cpu_cores()) for i in range(pq)]
+    frm_h = np.repeat(np.arange(n, dtype=np.int32), k)
+    hidx_h = np.stack([om.edge_index(nodes_h[i], frm_h, want[i]["nbr"].reshape(-1), clr, cdc, nthreads=cpu_cores())[1]
+                       for i in range(pq)])
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    nbr_w = T(np.stack([w_["nbr"] for w_ in want]))
+    fr_w = T(np.stack([w_["directed_free"] for w_ in want]).astype(np.uint8))
+    knn_mis = int((nbr_w != nbr_d).sum().item())
+    bad = (fr_w != fr_d)
+    directed_mis = int(bad.sum().item())
+    first_hit_mis = int((T(hidx_h).reshape(-1) != hidx_d).sum().item())
+    rp_w = T(np.stack([w_["row_ptr"] for w_ in want]))
+    rowptr_mis = int((rp_w != rp_d).sum().item())
+    col_mis = w_mis = 0
+    off_h = off_d.cpu().numpy()
+    for i in range(pq):
+        a, b = int(off_h[i]), int(off_h[i + 1])
+        if b - a != len(want[i]["col"]):
+            col_mis += abs(b - a - len(want[i]["col"]))
+            continue
+        col_mis += int((T(want[i]["col"]) != col_d[a:b]).sum().item())
+        w_mis += int((T(want[i]["w"]) != w_d[a:b]).sum().item())
+    in_band = 0
+    if directed_mis:
+        idx = torch.nonzero(bad.reshape(-1)).reshape(-1).cpu().numpy()
+        nbr_h = nbr_d.cpu().numpy().reshape(pq, n, k)
+        for e in idx:
+            qi, r, sl = int(e // (n * k)), int((e // k) % n), int(e % k)
+            a_, b_ = nodes_h[qi][r], nodes_h[qi][nbr_h[qi, r, sl]]
+            npts = np.ceil(np.sqrt(((b_ - a_) ** 2).sum()) / cdc + 1.0)
+            t = np.arange(1, int(npts)) / npts
+            cl = om.clearance(a_ + (b_ - a_) * t[:, None])
+            in_band += int(np.nanmin(np.abs(cl - clr)) < EPSILON_BAND) if len(cl) else 0
+    return {"queries_compared_array_by_array": int(pq), "directed_edges_compared": int(pq * n * k),
+            "knn_index_mismatch": knn_mis, "directed_mismatch": directed_mis, "epsilon": EPSILON_BAND,
+            "epsilon_band": in_band, "directed_mismatch_outside_epsilon_band": directed_mis - in_band,
+            "first_hit_mismatch": first_hit_mis, "row_ptr_mismatch": rowptr_mis, "csr_col_mismatch": col_mis,
+            "csr_weight_mismatch": w_mis,
+            "against": "oracle/ctp_oracle.c restatement (exact float32 k-NN in place of FLANN's approximate search), "
+                       "compared on the device"}
+
+
 class CpuArm:
     """The reference's CPU implementation of the path: oracle/_ref (the reference's own
     src/esdf_map.cpp + src/base_map.cpp) when it was built, else the oracle port."""
@@ -187,7 +256,7 @@ def run_reference(args, rank, world):
     q_total = (args.queries or qdef) * world
     # bounded sample: one query per core per step (at least 8), the first queries of the same set
     q_s = args.cpu_queries or max(8, min(4 * cores, 512))
-    s, g, cand = make_queries(c, e, q_total, n, cpn, 0, min(q_s, q_total))
+    s, g, cand = make_queries(c, e, q_total, n, cpn, 0, min(q_s, q_total), cfg=mapcfg)
     q_s = len(s)
     for _ in range(args.warmup):
         arm.run(s[:max(1, q_s // 8)], g[:max(1, q_s // 8)], cand[:max(1, q_s // 8)], n, clr, cdc, cores)
@@ -283,6 +352,37 @@ def run_paths_leg(dmap, nodes_d, row_ptr_d, col_d, w_d, nnz_off_d, nq, n, clr, c
             "api": "ctp_shorten_path / ctp_deformable (host buffers, wall clock)"}
 
 
+def run_legs(args):
+    """The other BASELINE configs as legs of the default line (N = 1): each one is this script run as a child process
+    on the same GPU with its own workload flag; the child's JSON line is condensed here."""
+    import subprocess as sp
+    legs = {}
+    todo = {
+        "C3": ["--workload", "C3", "--steps", "20", "--no-paths", "--no-planner", "--no-sustained", "--no-e2e-full"],
+        "MU_C2": ["--workload", "MU", "--mu-map", "C2", "--steps", "10"],
+        "MU_C3": ["--workload", "MU", "--mu-map", "C3", "--steps", "10"],
+        "C5": ["--workload", "C5", "--steps", "10"],
+    }
+    keep = ("value", "unit", "ms_per_step", "steps", "roofline", "parity", "cpu_baseline", "e2e", "stage_ms_per_step",
+            "free_edge_fraction", "lookups_per_s", "shortest_path", "cluster_stage", "gpu_launches")
+    for name, flags in todo.items():
+        t0 = time.perf_counter()
+        try:
+            r = sp.run([sys.executable, os.path.abspath(__file__), "--gpus", "1", "--warmup", "3", "--no-legs"] + flags,
+                       stdout=sp.PIPE, stderr=sp.PIPE, timeout=900, env=dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK=os.environ.get("LOCAL_RANK", "0")))
+            out = r.stdout.decode().strip().splitlines()
+            d = json.loads(out[-1]) if out else {}
+            leg = {k_: d[k_] for k_ in keep if k_ in d}
+            leg["workload"] = d.get("config", {}).get("workload")
+            if r.returncode != 0 or not d:
+                leg["error"] = r.stderr.decode()[-400:]
+        except Exception as ex:  # a leg must never take the headline down with it
+            leg = {"error": repr(ex)[:400]}
+        leg["wall_s"] = time.perf_counter() - t0
+        legs[name] = leg
+    return legs
+
+
 def run_multimap(args, rank, world):
     """--workload C5 (BASELINE configs[4]): a sweep over procedurally generated maps, one handle and one batch of
     queries per map.  64 maps per GPU per step (seeds 100 + 64*rank ...), random columns 256^3 as C2, generated
@@ -311,7 +411,7 @@ def run_multimap(args, rank, world):
         dm.set_layout(capi.LAYOUT_TEX)
         dm.reserve(qpm, n, m_c, K_NN)
         maps.append(dm)
-        s, g = synth.random_queries(c, e, qpm, seed)
+        s, g = synth.random_queries(c, e, qpm, seed, cfg=((cx, cy, r), None))
         s_l.append(s)
         g_l.append(g)
         cand_l.append(np.stack([synth.ellipsoid_candidates(s[i], g[i], m_c, seed * 1000 + i) for i in range(qpm)]))
@@ -703,6 +803,10 @@ def main():
     ap.add_argument("--cpu-queries", type=int, default=0, help="size of the CPU baseline sample (queries)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-full", action="store_true", help="skip the full-format companion of the e2e leg")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained-clock leg")
+    ap.add_argument("--no-legs", action="store_true", help="skip the C3 / MU / C5 legs of the default line")
+    ap.add_argument("--parity-queries", type=int, default=16, help="queries compared array by array with the oracle")
     ap.add_argument("--no-single", action="store_true", help="skip the single-query latency leg")
     ap.add_argument("--no-paths", action="store_true", help="skip the shortening / mutual-visibility leg")
     ap.add_argument("--no-sssp", action="store_true", help="skip the shortest-path leg")
@@ -774,7 +878,7 @@ def main():
     # this rank's shard of the query set, staged in page-locked host memory
     m_c = cpn * n
     cand_h = capi.pinned_empty((q, m_c, 3), np.float64)
-    s_h, g_h, _ = make_queries(c, e, q * world, n, cpn, rank * q, (rank + 1) * q, out=cand_h)
+    s_h, g_h, _ = make_queries(c, e, q * world, n, cpn, rank * q, (rank + 1) * q, out=cand_h, cfg=mapcfg)
 
     stream = torch.cuda.current_stream()
     cand_d = torch.from_numpy(cand_h).to(dev)
@@ -834,6 +938,31 @@ def main():
     value = checks_per_step * world * args.steps / (ms_max * 1e-3)
     nnz_total = int(nnz_off_d[q].item())
     free_frac = None
+
+    # ---- sustained clocks: the same step repeated for >= 2.5 s (the K timed steps above last a fraction of a second
+    # at boost clocks); reported next to the headline, not instead of it ----
+    sustained = None
+    if not args.no_sustained:
+        reps = int(min(5000, max(args.steps, 2500.0 / max(ms_max / args.steps, 1e-3))))
+        clocks2 = ClockSampler(local)
+        if rank == 0:
+            clocks2.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        s0.record(stream)
+        for _ in range(reps):
+            step()
+        s1.record(stream)
+        sync_all()
+        clk2 = clocks2.stop() if rank == 0 else None
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms_s = float(ts.item())
+        sustained = {"value": checks_per_step * world * reps / (ms_s * 1e-3), "unit": UNIT, "steps": reps,
+                     "seconds": ms_s * 1e-3, "ms_per_step": ms_s / reps, "clocks": clk2}
+        dmap.read_lookups(stream)
+        dmap.read_launches()
 
     # ---- single-query latency (ms per query, PRM-build part), same device path, q = 1 ----
     def step1():
@@ -942,33 +1071,66 @@ def main():
             print(f"bench.py: paths leg skipped: {ex}", file=sys.stderr)
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers, copies timed) ----
+    # The roadmaps come back in the compact form (CTP_CSR_UPPER | CTP_CSR_NO_WEIGHTS: every undirected edge once, the
+    # weights ||to - from|| left to the host-side mirror include/ctopprm/csr_expand.hpp, which reproduces them bit for
+    # bit); the same call with the full symmetric weighted CSR is timed next to it, and so is the mirror itself.
     e2e = None
+    e2e_full = None
     if not args.no_e2e:
-        out = dict(nodes=capi.pinned_empty((q, n, 3), np.float64), n_filled=capi.pinned_empty((q,), np.int32),
-                   row_ptr=capi.pinned_empty((q, n + 1), np.int32), col=capi.pinned_empty((cap,), np.int32),
-                   w=capi.pinned_empty((cap,), np.float64), nnz_off=capi.pinned_empty((q + 1,), np.int64))
         k2 = args.e2e_steps or max(2, min(args.steps, 5))
-        for _ in range(2):
-            dmap.sample_multiple(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, out=out)
-        sync_all()
-        dmap.read_io()
-        t0 = time.perf_counter()
-        for _ in range(k2):
-            dmap.sample_multiple(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, out=out)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        io_h2d, io_d2h = dmap.read_io()
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        nnz_e = int(out["nnz_off"][q])
-        # bytes actually copied (the library counts them): the candidate streams go up head-first, tails on demand
-        h2d, d2h = int(io_h2d // k2), int(io_d2h // k2)
-        e2e = {"value": checks_per_step * world * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / k2, "steps": k2,
-               "api": "ctp_sample_multiple (host candidate streams -> host CSR), wall clock, max over ranks"}
-        assert nnz_e == nnz_total, "host-API CSR differs from the device-API CSR"
+
+        def time_e2e(flags, out, reps):
+            for _ in range(2):
+                dmap.sample_multiple(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, out=out, csr_flags=flags)
+            sync_all()
+            dmap.read_io()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                dmap.sample_multiple(s_h, g_h, cand_h, n, clr, cdc, k=K_NN, out=out, csr_flags=flags)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            io_h2d, io_d2h = dmap.read_io()
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            # bytes actually copied (the library counts them): the candidate streams go up head-first, tails on demand
+            return {"value": checks_per_step * world * reps / dt, "unit": UNIT, "h2d_bytes_per_step": int(io_h2d // reps),
+                    "d2h_bytes_per_step": int(io_d2h // reps), "ms_per_step": 1e3 * dt / reps, "steps": reps}
+
+        compact = capi.CSR_UPPER | capi.CSR_NO_WEIGHTS
+        out_c = dict(nodes=capi.pinned_empty((q, n, 3), np.float64), n_filled=capi.pinned_empty((q,), np.int32),
+                     row_ptr=capi.pinned_empty((q, n + 1), np.int32), col=capi.pinned_empty((cap // 2,), np.int32),
+                     nnz_off=capi.pinned_empty((q + 1,), np.int64))
+        e2e = time_e2e(compact, out_c, k2)
+        e2e["api"] = ("ctp_sample_multiple_ex(CTP_CSR_UPPER | CTP_CSR_NO_WEIGHTS): host candidate streams -> host nodes + compact "
+                      "adjacency (each undirected edge once; weights recomputable from the nodes), wall clock, max over ranks")
+        assert 2 * int(out_c["nnz_off"][q]) == nnz_total, "compact host-API adjacency differs from the device-API CSR"
+        if rank == 0 and world == 1:
+            # the host-side mirror back to the full symmetric weighted CSR (not part of the timed call: a consumer that
+            # walks the upper lists or rebuilds visibility_node_ids does not need it)
+            from ctopprm_learn_b200 import hostlib
+            thr = cpu_cores()
+            full_h = dict(row_ptr=np.empty((q, n + 1), dtype=np.int32), col=np.empty(nnz_total, dtype=np.int32),
+                          w=np.empty(nnz_total), nnz_off=np.empty(q + 1, dtype=np.int64))
+            hostlib.csr_expand_upper(out_c["nodes"], out_c["row_ptr"], out_c["col"], out_c["nnz_off"], threads=thr, out=full_h)
+            t0 = time.perf_counter()
+            hostlib.csr_expand_upper(out_c["nodes"], out_c["row_ptr"], out_c["col"], out_c["nnz_off"], threads=thr, out=full_h)
+            e2e["host_mirror_ms"] = 1e3 * (time.perf_counter() - t0)
+            e2e["host_mirror_threads"] = thr
+            same = (np.array_equal(full_h["row_ptr"], row_ptr_d.cpu().numpy())
+                    and np.array_equal(full_h["col"], col_d[:nnz_total].cpu().numpy())
+                    and np.array_equal(full_h["w"], w_d[:nnz_total].cpu().numpy()))
+            e2e["host_mirror_equals_device_csr"] = bool(same)
+            del full_h
+        if not args.no_e2e_full:
+            out_f = dict(nodes=out_c["nodes"], n_filled=out_c["n_filled"], row_ptr=out_c["row_ptr"],
+                         col=capi.pinned_empty((cap,), np.int32), w=capi.pinned_empty((cap,), np.float64),
+                         nnz_off=out_c["nnz_off"])
+            e2e_full = time_e2e(0, out_f, max(2, k2 // 2))
+            e2e_full["api"] = "ctp_sample_multiple: the full symmetric CSR with FP64 weights comes back (round-1 format)"
+            assert int(out_f["nnz_off"][q]) == nnz_total, "host-API CSR differs from the device-API CSR"
+            del out_f
 
     # ---- end to end per query: host candidates -> host start->goal paths (PRM build + shortest path) ----
     e2e_query = None
@@ -1064,6 +1226,9 @@ def main():
         parity = {"queries_checked": int(q_s), "nnz_mismatch": int((gpu_nnz != oc["nnz"]).sum()),
                   "n_filled_mismatch": int((n_filled_d[:q_s].cpu().numpy() != oc["n_filled"]).sum())}
         free_frac = float(oc["n_free"].sum() / (q_s * n * K_NN))
+        if args.parity_queries > 0:
+            pq = max(1, min(args.parity_queries, q, 2 if n > 50000 else q))
+            parity.update(detailed_parity(dmap, arm.om, nodes_d, n, pq, clr, cdc, dev, torch))
         arm.close()
 
     if rank == 0:
@@ -1077,33 +1242,41 @@ def main():
         launches_edge = max(1, stage_calls["edges"])
         alg_bytes = lookups * 32.0
         achieved = alg_bytes / (edge_ms * 1e-3) / 1e9 if edge_ms > 0 else 0.0
-        traffic = None
+        traffic = lts_bytes = None
+        grid_in_hbm = vox.nbytes > (100 << 20)  # beyond the 126 MB L2 the gathers are DRAM traffic
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-            traffic = tr.get(f"{args.workload}:{dmap.layout_name()}", {}).get("dram_bytes_per_launch")
+            ent = tr.get(f"{args.workload}:{dmap.layout_name()}", {})
+            traffic = ent.get("dram_bytes_per_launch")
+            lts_bytes = ent.get("lts_bytes_per_launch")
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args.workload, n, q, cpn, world),
-                           layout=dmap.layout_name() + (" (edge march) + cell8 (rejection)" if extra else ""),
-                           lanes_per_edge=dmap.prm_group()),
+            "config": workload_config(args.workload, n, q, cpn, world),
+            "impl_config": {"layout": dmap.layout_name() + (" (edge march) + cell8 (rejection)" if extra else ""),
+                            "lanes_per_edge": dmap.prm_group()},
             "ms_per_query": {"batched": ms_max / args.steps / q, "single_query_latency": single_ms,
                              "single_query_latency_cuda_graph": single_graph_ms, "class_surface": planner_leg},
             "paths": paths_leg, "shortest_path": sssp_leg, "e2e_query": e2e_query,
             "lookups_per_s": lookups / (ms_max * 1e-3),
             "stage_ms_per_step": {k_: v / args.steps for k_, v in stage_ms.items()},
-            "roofline": {"bound": "hbm", "kernel": "k_edge_flat" if dmap.prm_group() == 1 else "k_edge_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
+            "roofline": {"bound": "hbm" if grid_in_hbm else "l2", "limiter": "dram gathers" if grid_in_hbm else "issue / fp64 pipe (grid L2-resident)",
+                         "kernel": "k_edge_flat" if dmap.prm_group() == 1 else "k_edge_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "l2_bytes_per_launch": lts_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": alg_bytes / launches_edge,
                          "lookups_per_launch": lookups / launches_edge, "ms_per_launch": edge_ms / launches_edge,
                          "share_of_step": edge_ms / ms},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": cpu,
-            "csr_nnz_per_step": nnz_total, "free_edge_fraction": free_frac, "parity": parity,
+            "e2e": e2e, "e2e_full_csr": e2e_full, "sustained": sustained, "gpu_launches": int(launches), "clocks": clk,
+            "cpu_baseline": cpu, "csr_nnz_per_step": nnz_total, "free_edge_fraction": free_frac, "parity": parity,
+            "reference_note": "the CPU arm's neighbour stage is the oracle's exact float32 k-NN (FLANN is absent from the "
+                              "reference tree); its collision code is the reference's own src/esdf_map.cpp + src/base_map.cpp",
         }
+        if world == 1 and args.workload == "C2" and not args.no_legs:
+            line["legs"] = run_legs(args)
         emit_line(line)
     dmap.close()
     if world > 1:

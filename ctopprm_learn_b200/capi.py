@@ -12,6 +12,7 @@ LAYOUT_PLAIN, LAYOUT_CELL8, LAYOUT_TEX, LAYOUT_BRICK = 1, 2, 4, 8
 LAYOUT_NAMES = {1: "plain", 2: "cell8", 4: "tex", 8: "brick"}
 DEFAULT_LAYOUT = LAYOUT_TEX  # the layout bench.py uses unless told otherwise (fastest measured; n <= 1024)
 EDGE_NODES, EDGE_GUARDS = 0, 1
+CSR_UPPER, CSR_NO_WEIGHTS = 1, 2
 TUNE_KNN_PER_CELL, TUNE_KNN_TILE, TUNE_PIPE_CHUNK, TUNE_EDGE_ORDER, TUNE_SSSP_FRONTIER, TUNE_PIPE_HEAD, TUNE_SSSP_CLUSTER = 0, 1, 2, 3, 4, 5, 6
 ERR_NEED_CANDIDATES = -4
 
@@ -73,10 +74,13 @@ _SIGS = {
     "ctp_knn_dev": [_P, _P, _I64, _I64, _I, _P, _P, _P],
     "ctp_build_prm": [_P, _P, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
     "ctp_build_prm_dev": [_P, _P, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P, _P],
+    "ctp_build_prm_ex_dev": [_P, _P, _I64, _I64, _I, _D, _D, _I, _P, _P, _P, _P, _P, _I64, _P, _P],
     "ctp_csr_from_directed": [_P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _I64, _P],
     "ctp_edge_check_knn_dev": [_P, _P, _I64, _I64, _I, _P, _D, _D, _P, _P],
     "ctp_csr_from_directed_dev": [_P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _I64, _P, _P],
     "ctp_sample_multiple": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
+    "ctp_sample_multiple_ex": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, _I, _P, _P, _P, _P, _P, _I64, _P],
+    "ctp_sample_ellipsoid_draws": [_P, _P, _P, _I64, _I64, _D, _I, C.c_uint64, _P, _P],
     "ctp_sssp": [_P, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "ctp_sssp_dev": [_P, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
     "ctp_query_paths": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, C.c_int32, _P, _P, _P, _P, _P],
@@ -365,6 +369,17 @@ class DeviceMap:
         _check(lib().ctp_sample_ellipsoid(self._h, _ptr(start), _ptr(goal), q, m, ratio, int(planar), seed, _ptr(cand)))
         return cand
 
+    def sample_ellipsoid_draws(self, start, goal, m, ratio, planar, seed):
+        """candidates plus the (u, g0, g1, g2) draws each one was made from (q x m x 4)"""
+        start = _np(start, np.float64).reshape(-1, 3)
+        goal = _np(goal, np.float64).reshape(-1, 3)
+        q = len(start)
+        cand = np.empty((q, m, 3))
+        draws = np.empty((q, m, 4))
+        _check(lib().ctp_sample_ellipsoid_draws(self._h, _ptr(start), _ptr(goal), q, m, ratio, int(planar), seed, _ptr(cand),
+                                                _ptr(draws)))
+        return cand, draws
+
     def knn(self, nodes, k=13):
         nodes = _np(nodes, np.float64)
         if nodes.ndim == 2:
@@ -374,6 +389,29 @@ class DeviceMap:
         d2 = np.empty((q, n, k), dtype=np.float32)
         _check(lib().ctp_knn(self._h, _ptr(nodes), q, n, k, _ptr(idx), _ptr(d2)))
         return idx, d2
+
+    def build_prm_ex(self, nodes, clr, cdc, k=13, csr_flags=0):
+        """compact adjacency (CSR_UPPER / CSR_NO_WEIGHTS) through the device entry point, torch staging"""
+        import torch
+        nodes = _np(nodes, np.float64)
+        if nodes.ndim == 2:
+            nodes = nodes[None]
+        q, n, _ = nodes.shape
+        dev = torch.device("cuda", self.device)
+        cap = 2 * q * n * k
+        nd = torch.from_numpy(nodes).to(dev)
+        rp = torch.zeros((q, n + 1), dtype=torch.int32, device=dev)
+        col = torch.zeros(cap, dtype=torch.int32, device=dev)
+        w = None if csr_flags & CSR_NO_WEIGHTS else torch.zeros(cap, dtype=torch.float64, device=dev)
+        off = torch.zeros(q + 1, dtype=torch.int64, device=dev)
+        st = torch.cuda.current_stream(dev)
+        _check(lib().ctp_build_prm_ex_dev(self._h, _ptr(nd), q, n, k, clr, cdc, csr_flags, None, None, _ptr(rp), _ptr(col),
+                                          _ptr(w), cap, _ptr(off), _stream_ptr(st)))
+        torch.cuda.synchronize(dev)
+        off = off.cpu().numpy()
+        nnz = int(off[q])
+        return dict(row_ptr=rp.cpu().numpy(), col=col[:nnz].cpu().numpy(), w=None if w is None else w[:nnz].cpu().numpy(),
+                    nnz_off=off)
 
     def build_prm(self, nodes, clr, cdc, k=13):
         nodes = _np(nodes, np.float64)
@@ -430,8 +468,9 @@ class DeviceMap:
         _check(lib().ctp_sssp_dev(self._h, q, n, _ptr(row_ptr), _ptr(col), _ptr(w), _ptr(nnz_off), _ptr(src), ns,
                                   _ptr(dist), _ptr(pred), _ptr(label), _stream_ptr(stream)))
 
-    def sample_multiple(self, start, goal, cand, n, clr, cdc, k=13, out=None):
-        """TopologicalPRMClustering::sampleMultiple from host candidates to host CSR."""
+    def sample_multiple(self, start, goal, cand, n, clr, cdc, k=13, out=None, csr_flags=0):
+        """TopologicalPRMClustering::sampleMultiple from host candidates to host CSR
+        (csr_flags: CSR_UPPER / CSR_NO_WEIGHTS select the compact forms of the adjacency)."""
         start = _np(start, np.float64).reshape(-1, 3)
         goal = _np(goal, np.float64).reshape(-1, 3)
         q = len(start)
@@ -442,9 +481,10 @@ class DeviceMap:
             out = dict(nodes=np.empty((q, n, 3)), n_filled=np.empty(q, dtype=np.int32),
                        row_ptr=np.empty((q, n + 1), dtype=np.int32), col=np.empty(cap, dtype=np.int32),
                        w=np.empty(cap), nnz_off=np.empty(q + 1, dtype=np.int64))
-        _check(lib().ctp_sample_multiple(self._h, _ptr(start), _ptr(goal), _ptr(cand), q, m, n, k, clr, cdc,
-                                         _ptr(out["nodes"]), _ptr(out["n_filled"]), _ptr(out["row_ptr"]),
-                                         _ptr(out["col"]), _ptr(out["w"]), cap, _ptr(out["nnz_off"])))
+        cap = min(cap, out["col"].size)
+        _check(lib().ctp_sample_multiple_ex(self._h, _ptr(start), _ptr(goal), _ptr(cand), q, m, n, k, clr, cdc, csr_flags,
+                                            _ptr(out["nodes"]), _ptr(out["n_filled"]), _ptr(out["row_ptr"]),
+                                            _ptr(out["col"]), _ptr(out.get("w")), cap, _ptr(out["nnz_off"])))
         return out
 
     def query_paths(self, start, goal, cand, n, clr, cdc, k=13, path_cap=512, out=None):
@@ -517,6 +557,10 @@ class DeviceMap:
         _check(lib().ctp_edge_check_dev(self._h, _ptr(a), _ptr(b), a.numel() // 3, clr, cdc, mode, group, _ptr(free),
                                         _ptr(hit), _ptr(hit_idx), _ptr(lookups), _stream_ptr(stream)))
 
+    def edge_check_indexed_dev(self, nodes, n_nodes, frm, to, clr, cdc, free, group=0, hit_idx=None, lookups=None, stream=None):
+        _check(lib().ctp_edge_check_indexed_dev(self._h, _ptr(nodes), n_nodes, _ptr(frm), _ptr(to), frm.numel(), clr, cdc,
+                                                group, _ptr(free), _ptr(hit_idx), _ptr(lookups), _stream_ptr(stream)))
+
     def sample_reject_dev(self, start, goal, cand, q, m, clr, n, nodes, n_filled, n_used, accept=None, stream=None):
         _check(lib().ctp_sample_reject_dev(self._h, _ptr(start), _ptr(goal), _ptr(cand), q, m, clr, n, _ptr(nodes),
                                            _ptr(n_filled), _ptr(n_used), _ptr(accept), _stream_ptr(stream)))
@@ -537,6 +581,6 @@ class DeviceMap:
                                             _stream_ptr(stream)))
 
     def build_prm_dev(self, nodes, q, n, k, clr, cdc, row_ptr, col, w, cap, nnz_off, nbr=None, directed_free=None,
-                      stream=None):
-        _check(lib().ctp_build_prm_dev(self._h, _ptr(nodes), q, n, k, clr, cdc, _ptr(nbr), _ptr(directed_free),
-                                       _ptr(row_ptr), _ptr(col), _ptr(w), cap, _ptr(nnz_off), _stream_ptr(stream)))
+                      stream=None, csr_flags=0):
+        _check(lib().ctp_build_prm_ex_dev(self._h, _ptr(nodes), q, n, k, clr, cdc, csr_flags, _ptr(nbr), _ptr(directed_free),
+                                          _ptr(row_ptr), _ptr(col), _ptr(w), cap, _ptr(nnz_off), _stream_ptr(stream)))

@@ -90,6 +90,7 @@ struct ctp_map {
   int sssp_smem_optin = -1;   // opt-in shared memory per CTA of this device, -1 until the graph kernels were configured
   unsigned knn_smem_set = 0;  // bit K: the dynamic shared-memory limit of the k-NN kernels <K> has been raised
   int64_t pipe_nu_seen = 0;  // largest n_used (candidates consumed by a query) seen by the running pipeline call
+  int occ_cache[32] = {0};    // resident CTAs per SM of the edge kernels, per (layout, lanes per edge): see occ_slot
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;    // pool, two per recorded span
   std::vector<int> prof_stage;         // stage id of span i (events 2i, 2i+1)
@@ -705,10 +706,16 @@ extern "C" int ctp_gradient(ctp_map *m, const double *xyz, int64_t cnt, double *
 }
 
 // ----------------------------------- segment checks ----------------------------------------
+// slot of (layout, lanes per edge) in ctp_map::occ_cache: layouts 1, 2, 4, 8 x groups 1, 4, 8, 16, 32
+static inline int occ_slot(int layout, int group) {
+  const int li = layout == CTP_L_PLAIN ? 0 : layout == CTP_L_CELL8 ? 1 : layout == CTP_L_TEX ? 2 : 3;
+  const int gi = group == 1 ? 0 : group == 4 ? 1 : group == 8 ? 2 : group == 16 ? 3 : 4;
+  return li * 5 + gi;
+}
 template <int L, int G>
 static int launch_edges_LG(ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr, double cdc, int guards,
                            const EdgeOut &O, cudaStream_t st) {
-  static int occ = 0;  // resident CTAs per SM for this instantiation
+  int &occ = m->occ_cache[occ_slot(L, G)];  // resident CTAs per SM for this instantiation, on this handle's device
   if (occ == 0) {
     int o = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_edge_march<L, G>, 256, 0));
@@ -728,7 +735,7 @@ static int launch_edges_LG(ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr
 template <int L>
 static int launch_edges_flat(ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr, double cdc, int guards,
                              const EdgeOut &O, cudaStream_t st) {
-  static int occ = 0;
+  int &occ = m->occ_cache[occ_slot(L, 1)];
   if (occ == 0) {
     int o = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_edge_flat<L>, 32 * CTP_FLAT_WARPS, 0));
@@ -923,10 +930,9 @@ static size_t ws_bytes_knn(int64_t q, int64_t n) {
   return align_up((size_t)q * sizeof(KnnGrid)) + 2 * align_up((size_t)q * n * 16) + 3 * align_up((size_t)q * n * 4) + align_up((size_t)q * n) +
          align_up((size_t)q * mc * 4) + align_up((size_t)q * (mc + 1) * 4) + 512;
 }
+static size_t ws_bytes_csr(int64_t q, int64_t n);
 static size_t ws_bytes_prm(int64_t q, int64_t n, int k) {
-  return ws_bytes_knn(q, n) + align_up((size_t)q * n * csr_ns(k) * 4) + 2 * align_up((size_t)q * n * k) +
-         align_up((size_t)q * n * k * 8) +
-         align_up((size_t)q * n * 4) + align_up((size_t)q * 8);
+  return ws_bytes_knn(q, n) + align_up((size_t)q * n * csr_ns(k) * 4) + align_up((size_t)q * n * k) + ws_bytes_csr(q, n);
 }
 
 extern "C" int ctp_reserve(ctp_map *m, int64_t q, int64_t n, int64_t cand, int k) {
@@ -965,7 +971,7 @@ static int sample_reject_launch(ctp_map *m, const double *start, const double *g
   m->launches++;
   CK(cudaGetLastError());
   // n_used defaults to "whole stream consumed"; the scatter pass overwrites it when n-2 were found
-  k_fill_i32<<<grid_for(q, 256, 1024), 256, 0, st>>>(n_used, q, (int32_t)cnt);
+  k_fill_i32<<<grid_for(q, 256, 1024), 256, 0, st>>>(n_used, q, n == 2 ? 0 : (int32_t)cnt);  // n == 2: the loop of :309 never runs
   m->launches++;
   k_reject_scatter<<<grid, CTP_REJ_BLOCK, 0, st>>>(cand, start, goal, d_acc, d_bc, nblk, cnt, stride, n, nodes, n_used);
   m->launches++;
@@ -1042,6 +1048,29 @@ extern "C" int ctp_sample_ellipsoid(ctp_map *m, const double *start, const doubl
   CK(cudaMemcpyAsync(d_g, goal, q * 24, cudaMemcpyHostToDevice, 0));
   CKR(ctp_sample_ellipsoid_dev(m, d_s, d_g, q, cnt, ratio, planar, seed, d_c, 0));
   CK(cudaMemcpyAsync(cand, d_c, q * cnt * 24, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return CTP_OK;
+}
+
+// the same candidates together with the draws they were made from (draws: q x cnt x 4 = u, g0, g1, g2), so a test can
+// push the very same draws through the CPU restatement of random_ellipsoid_point
+extern "C" int ctp_sample_ellipsoid_draws(ctp_map *m, const double *start, const double *goal, int64_t q, int64_t cnt,
+                                          double ratio, int planar, uint64_t seed, double *cand, double *draws) {
+  REQUIRE(m && q >= 1 && cnt >= 0 && ratio > 1.0, "bad argument (ratio must be > 1)");
+  if (cnt == 0) return CTP_OK;
+  REQUIRE(start && goal && cand && draws, "null buffer");
+  CK(cudaSetDevice(m->device));
+  CKR(arena_reserve(m->io, 2 * align_up(q * 24) + align_up(q * cnt * 24) + align_up(q * cnt * 32)));
+  IoScope sc(m);
+  double *d_s = arena_take<double>(m->io, q * 3), *d_g = arena_take<double>(m->io, q * 3);
+  double *d_c = arena_take<double>(m->io, q * cnt * 3), *d_d = arena_take<double>(m->io, q * cnt * 4);
+  CK(cudaMemcpyAsync(d_s, start, q * 24, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d_g, goal, q * 24, cudaMemcpyHostToDevice, 0));
+  k_sample_ellipsoid<<<grid_for(q * cnt, 256, m->sm_count * 16), 256>>>(d_s, d_g, q, cnt, ratio, planar, seed, d_c, d_d);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(cand, d_c, q * cnt * 24, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(draws, d_d, q * cnt * 32, cudaMemcpyDeviceToHost, 0));
   CK(cudaStreamSynchronize(0));
   return CTP_OK;
 }
@@ -1155,45 +1184,89 @@ extern "C" int ctp_knn(ctp_map *m, const double *nodes, int64_t q, int64_t n, in
 
 // ------------------------------------- PRM build -------------------------------------------
 // symmetric union of the free directed edges -> CSR (:374-385); rec holds the neighbour ids
+struct CsrScratch {
+  int32_t *own;     // entries a row contributes to itself
+  int32_t *xcnt;    // entries other rows push into it
+  int64_t *nnz;
+  uint16_t *rec16;  // null when the ids do not fit 16 bits
+  void *xtra;       // rows x CTP_CSR_XCAP parked ids (16-bit with rec16, else 32-bit)
+  int32_t *big, *big_cnt;
+  int32_t *big_tmp; // one line of n + 32 ids per CTA of k_csr_emit_big
+  int big_ctas;
+};
+static size_t ws_bytes_csr(int64_t q, int64_t n) {
+  const size_t rows = (size_t)q * n;
+  return 3 * align_up(rows * 4) + align_up((size_t)q * 8) + align_up(rows * 32) + align_up(rows * CTP_CSR_XCAP * 4) +
+         align_up((size_t)256 * (size_t)(n + 32) * 4) + 1024;
+}
+static CsrScratch csr_scratch_take(ctp_map *m, int64_t q, int64_t n, int k) {
+  Arena &a = m->ws;
+  const size_t rows = (size_t)q * n;
+  CsrScratch s;
+  s.own = arena_take<int32_t>(a, rows);
+  s.xcnt = arena_take<int32_t>(a, rows);
+  s.nnz = arena_take<int64_t>(a, q);
+  const bool small = n <= 65535 && k <= 14;
+  s.rec16 = small ? arena_take<uint16_t>(a, rows * 16) : nullptr;
+  s.xtra = small ? (void *)arena_take<uint16_t>(a, rows * CTP_CSR_XCAP) : (void *)arena_take<int32_t>(a, rows * CTP_CSR_XCAP);
+  s.big = arena_take<int32_t>(a, rows);
+  s.big_cnt = arena_take<int32_t>(a, 1);
+  s.big_ctas = std::max(1, std::min(m->sm_count, 256));
+  s.big_tmp = arena_take<int32_t>(a, (size_t)s.big_ctas * (size_t)(n + 32));
+  return s;
+}
+
+// csr_flags: CTP_CSR_UPPER = only entries with col > row; CTP_CSR_NO_WEIGHTS = w is not written (may be null)
 static int csr_emit(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *d_rec, const uint8_t *d_free,
-                    uint8_t *d_flag, int32_t *d_deg, int64_t *d_nnz, int32_t *d_coltmp, int32_t *row_ptr, int32_t *col,
-                    double *w, int64_t cap, int64_t *nnz_off, cudaStream_t st) {
-  // 32-byte rows of 16-bit ids for the reverse-edge test when they fit.  They borrow the unsorted-column
-  // scratch: k_csr_degree is their only reader and k_csr_fill, the first writer of that scratch, runs after it.
-  uint16_t *d_rec16 = (n <= 65535 && k <= 14) ? reinterpret_cast<uint16_t *>(d_coltmp) : nullptr;
+                    const CsrScratch &sc, int csr_flags, int32_t *row_ptr, int32_t *col, double *w, int64_t cap,
+                    int64_t *nnz_off, cudaStream_t st) {
   const int64_t rows = q * n, edges = rows * k;
   const int ns = csr_ns(k);
+  const int upper = (csr_flags & CTP_CSR_UPPER) ? 1 : 0;
+  if (csr_flags & CTP_CSR_NO_WEIGHTS) w = nullptr;
   StageSpan span(m, CTP_STAGE_CSR, st);
-  const int eb = (int)((edges + 255) / 256), rb = (int)((rows + 255) / 256);
-  k_csr_rowmask<<<rb, 256, 0, st>>>(d_free, k, ns, rows, d_rec, d_deg, d_rec16);
-  m->launches++;
+  const int rb = (int)((rows + 255) / 256);
+  CK(cudaMemsetAsync(sc.big_cnt, 0, 4, st));
+  CK(cudaMemsetAsync(sc.xcnt, 0, (size_t)rows * 4, st));
   CsrSplit sp;
   sp.small = edges < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
   sp.dk = ctp_div_make((uint32_t)k);
   sp.dn = ctp_div_make(sp.small ? (uint32_t)n : 1u);
-  if (ns == 16) k_csr_degree<16><<<eb, 256, 0, st>>>(d_rec, d_rec16, d_free, n, k, edges, sp, d_flag, d_deg);
-  else k_csr_degree<32><<<eb, 256, 0, st>>>(d_rec, nullptr, d_free, n, k, edges, sp, d_flag, d_deg);
+  k_csr_rowmask<<<rb, 256, 0, st>>>(d_free, n, k, ns, rows, sp, upper, d_rec, sc.own, sc.rec16);
   m->launches++;
-  k_csr_rowptr<<<(unsigned)q, 1024, 0, st>>>(d_deg, n, row_ptr, d_nnz);
+  if (sc.rec16)
+    k_csr_count<16, uint16_t, true><<<rb, 256, 0, st>>>(d_rec, sc.rec16, n, k, rows, sp, upper, sc.xcnt, (uint16_t *)sc.xtra, sc.big, sc.big_cnt);
+  else if (ns == 16)
+    k_csr_count<16, int32_t, false><<<rb, 256, 0, st>>>(d_rec, nullptr, n, k, rows, sp, upper, sc.xcnt, (int32_t *)sc.xtra, sc.big, sc.big_cnt);
+  else
+    k_csr_count<32, int32_t, false><<<rb, 256, 0, st>>>(d_rec, nullptr, n, k, rows, sp, upper, sc.xcnt, (int32_t *)sc.xtra, sc.big, sc.big_cnt);
   m->launches++;
-  k_csr_query_offsets<<<1, 1024, 0, st>>>(d_nnz, q, nnz_off);
+  k_csr_rowptr<<<(unsigned)q, 1024, 0, st>>>(sc.own, sc.xcnt, n, row_ptr, sc.nnz);
   m->launches++;
-  // unsorted rows go to scratch (at most 2 entries per directed edge), the finish pass ranks them into col
+  k_csr_query_offsets<<<1, 1024, 0, st>>>(sc.nnz, q, nnz_off);
+  m->launches++;
   const int64_t tcap = std::min<int64_t>(cap, 2 * edges);
-  if (ns == 16) k_csr_fill<16><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, sp, row_ptr, nnz_off, tcap, d_deg, d_coltmp);
-  else k_csr_fill<32><<<eb, 256, 0, st>>>(d_rec, d_flag, n, k, edges, sp, row_ptr, nnz_off, tcap, d_deg, d_coltmp);
+  const int eb = (int)((rows + CTP_CSR_EMIT_ROWS - 1) / CTP_CSR_EMIT_ROWS);
+  if (sc.rec16)
+    k_csr_emit<16, uint16_t><<<eb, CTP_CSR_EMIT_ROWS, 0, st>>>(nodes, d_rec, sc.rec16, (const uint16_t *)sc.xtra, n, k, rows, sp, upper, row_ptr, nnz_off, tcap, col, w);
+  else if (ns == 16)
+    k_csr_emit<16, int32_t><<<eb, CTP_CSR_EMIT_ROWS, 0, st>>>(nodes, d_rec, nullptr, (const int32_t *)sc.xtra, n, k, rows, sp, upper, row_ptr, nnz_off, tcap, col, w);
+  else
+    k_csr_emit<32, int32_t><<<eb, CTP_CSR_EMIT_ROWS, 0, st>>>(nodes, d_rec, nullptr, (const int32_t *)sc.xtra, n, k, rows, sp, upper, row_ptr, nnz_off, tcap, col, w);
   m->launches++;
-  k_csr_finish_flat<<<(int)((rows + 255) / 256), 256, 0, st>>>(nodes, n, rows, sp, row_ptr, nnz_off, tcap, d_coltmp, col, w);
+  if (ns == 16) k_csr_emit_big<16><<<sc.big_ctas, 256, 0, st>>>(nodes, d_rec, n, k, sp, upper, sc.big, sc.big_cnt, row_ptr, nnz_off, tcap, sc.big_tmp, col, w);
+  else k_csr_emit_big<32><<<sc.big_ctas, 256, 0, st>>>(nodes, d_rec, n, k, sp, upper, sc.big, sc.big_cnt, row_ptr, nnz_off, tcap, sc.big_tmp, col, w);
   m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
 }
 
-extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, double clr,
-                                 double cdc, int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr, int32_t *col,
-                                 double *w, int64_t cap, int64_t *nnz_off, void *stream) {
+extern "C" int ctp_build_prm_ex_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, double clr,
+                                    double cdc, int csr_flags, int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr,
+                                    int32_t *col, double *w, int64_t cap, int64_t *nnz_off, void *stream) {
   REQUIRE(m && q >= 1 && n >= 2 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument (k must be in [1,16])");
-  REQUIRE(nodes && row_ptr && col && w && nnz_off && cap >= 0, "null buffer");
+  REQUIRE((csr_flags & ~(CTP_CSR_UPPER | CTP_CSR_NO_WEIGHTS)) == 0, "unknown csr_flags bits");
+  REQUIRE(nodes && row_ptr && col && (w || (csr_flags & CTP_CSR_NO_WEIGHTS)) && nnz_off && cap >= 0, "null buffer");
   REQUIRE(cdc > 0, "collision_distance_check must be > 0");
   REQUIRE(q * n * k < ((int64_t)1 << 31), "q*n*k must fit in int32");
   CK(cudaSetDevice(m->device));
@@ -1204,10 +1277,7 @@ extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int
   const int ns = csr_ns(k);
   int32_t *d_rec = arena_take<int32_t>(m->ws, rows * ns);  // per node: k neighbour ids + free-edge mask
   uint8_t *d_free = directed_free ? directed_free : arena_take<uint8_t>(m->ws, edges);
-  uint8_t *d_flag = arena_take<uint8_t>(m->ws, edges);
-  int32_t *d_deg = arena_take<int32_t>(m->ws, rows);
-  int64_t *d_nnz = arena_take<int64_t>(m->ws, q);
-  int32_t *d_coltmp = arena_take<int32_t>(m->ws, 2 * edges);
+  const CsrScratch csc = csr_scratch_take(m, q, n, k);
   const float4 *d_sorted_keep = nullptr;
   int rc;
   {
@@ -1231,13 +1301,19 @@ extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int
     StageSpan span(m, CTP_STAGE_EDGES, st);
     CKR(launch_edges(m, m->prm_group, S, edges, clr, cdc, 0, O, st));
   }
-  CKR(csr_emit(m, nodes, q, n, k, d_rec, d_free, d_flag, d_deg, d_nnz, d_coltmp, row_ptr, col, w, cap, nnz_off, st));
+  CKR(csr_emit(m, nodes, q, n, k, d_rec, d_free, csc, csr_flags, row_ptr, col, w, cap, nnz_off, st));
   if (nbr) {
     k_rec_to_nbr<<<(int)((edges + 255) / 256), 256, 0, st>>>(d_rec, ns, k, edges, nbr);
     m->launches++;
   }
   CK(cudaGetLastError());
   return CTP_OK;
+}
+
+extern "C" int ctp_build_prm_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, double clr,
+                                 double cdc, int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr, int32_t *col,
+                                 double *w, int64_t cap, int64_t *nnz_off, void *stream) {
+  return ctp_build_prm_ex_dev(m, nodes, q, n, k, clr, cdc, 0, nbr, directed_free, row_ptr, col, w, cap, nnz_off, stream);
 }
 
 static int build_prm_host_tail(ctp_map *m, int64_t q, int64_t n, int k, int32_t *nbr, uint8_t *directed_free,
@@ -1319,14 +1395,11 @@ extern "C" int ctp_csr_from_directed_dev(ctp_map *m, const double *nodes, int64_
   const int64_t rows = q * n, edges = rows * k;
   const int ns = csr_ns(k);
   int32_t *d_rec = arena_take<int32_t>(m->ws, rows * ns);
-  uint8_t *d_flag = arena_take<uint8_t>(m->ws, edges);
-  int32_t *d_deg = arena_take<int32_t>(m->ws, rows);
-  int64_t *d_nnz = arena_take<int64_t>(m->ws, q);
-  int32_t *d_coltmp = arena_take<int32_t>(m->ws, 2 * edges);
+  const CsrScratch csc = csr_scratch_take(m, q, n, k);
   m->ws.used = keep;
   k_nbr_to_rec<<<(int)((edges + 255) / 256), 256, 0, st>>>(nbr, ns, k, edges, d_rec);
   m->launches++;
-  return csr_emit(m, nodes, q, n, k, d_rec, directed_free, d_flag, d_deg, d_nnz, d_coltmp, row_ptr, col, w, cap, nnz_off, st);
+  return csr_emit(m, nodes, q, n, k, d_rec, directed_free, csc, 0, row_ptr, col, w, cap, nnz_off, st);
 }
 
 extern "C" int ctp_csr_from_directed(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, const int32_t *nbr,
@@ -1336,7 +1409,7 @@ extern "C" int ctp_csr_from_directed(ctp_map *m, const double *nodes, int64_t q,
   REQUIRE(nodes && nbr && directed_free && row_ptr && col && w && nnz_off, "null buffer");
   CK(cudaSetDevice(m->device));
   const int64_t edges = q * n * k, dcap = 2 * edges;
-  for (int64_t i = 0; i < edges; i++) REQUIRE(nbr[i] < n, "neighbour index out of range");
+  for (int64_t i = 0; i < edges; i++) REQUIRE(nbr[i] >= -1 && nbr[i] < n, "neighbour index out of range (-1 = no neighbour)");
   CKR(arena_reserve(m->io, align_up(q * n * 24) + align_up(edges * 4) + align_up(edges) + align_up(q * (n + 1) * 4) +
                                align_up(dcap * 4) + align_up(dcap * 8) + align_up((q + 1) * 8)));
   IoScope sc(m);
@@ -1623,8 +1696,17 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
                                    int64_t q, int64_t cnt, int64_t n, int k, double clr, double cdc, double *nodes,
                                    int32_t *n_filled, int32_t *row_ptr, int32_t *col, double *w, int64_t cap,
                                    int64_t *nnz_off) {
+  return ctp_sample_multiple_ex(m, start, goal, cand, q, cnt, n, k, clr, cdc, 0, nodes, n_filled, row_ptr, col, w, cap, nnz_off);
+}
+
+extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const double *goal, const double *cand,
+                                      int64_t q, int64_t cnt, int64_t n, int k, double clr, double cdc, int csr_flags,
+                                      double *nodes, int32_t *n_filled, int32_t *row_ptr, int32_t *col, double *w,
+                                      int64_t cap, int64_t *nnz_off) {
   REQUIRE(m && q >= 1 && n >= 2 && cnt >= 0 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument");
-  REQUIRE(start && goal && cand && nodes && n_filled && row_ptr && col && w && nnz_off, "null buffer");
+  REQUIRE((csr_flags & ~(CTP_CSR_UPPER | CTP_CSR_NO_WEIGHTS)) == 0, "unknown csr_flags bits");
+  const bool want_w = !(csr_flags & CTP_CSR_NO_WEIGHTS);
+  REQUIRE(start && goal && cand && nodes && n_filled && row_ptr && col && (w || !want_w) && nnz_off, "null buffer");
   REQUIRE(cdc > 0, "collision_distance_check must be > 0");
   CK(cudaSetDevice(m->device));
   CKR(pipe_init(m));
@@ -1640,9 +1722,9 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
   const int64_t n_chunks = (int64_t)cs.size() - 1;
   const int nbuf = n_chunks > 1 ? 2 : 1;
   m->pipe_nu_seen = 0;  // the up-front share of the streams adapts within this call only
-  const int64_t ecap = 2 * qc * n * k;  // CSR entries a chunk can produce
+  const int64_t ecap = ((csr_flags & CTP_CSR_UPPER) ? 1 : 2) * qc * n * k;  // CSR entries a chunk can produce
   size_t per = 2 * align_up(qc * 24) + align_up(qc * cnt * 24) + align_up(qc * n * 24) + 2 * align_up(qc * 4) +
-               align_up(qc * (n + 1) * 4) + align_up(ecap * 4) + align_up(ecap * 8) + align_up((qc + 1) * 8);
+               align_up(qc * (n + 1) * 4) + align_up(ecap * 4) + (want_w ? align_up(ecap * 8) : 0) + align_up((qc + 1) * 8);
   CKR(arena_reserve(m->io, nbuf * per + 4096));
   CKR(ctp_reserve(m, qc, n, cnt, k));
   CKR(pipe_host_staging(m, qc));
@@ -1658,7 +1740,7 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
     F[i].d_nu = arena_take<int32_t>(m->io, qc);
     B[i].d_rp = arena_take<int32_t>(m->io, qc * (n + 1));
     B[i].d_col = arena_take<int32_t>(m->io, ecap);
-    B[i].d_w = arena_take<double>(m->io, ecap);
+    B[i].d_w = want_w ? arena_take<double>(m->io, ecap) : nullptr;
     B[i].d_off = arena_take<int64_t>(m->io, qc + 1);
   }
   cudaStream_t s_comp = m->pipe_st[1], s_out = m->pipe_st[2], s_small = m->pipe_st[3];
@@ -1678,8 +1760,8 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
         rc_deferred = fail(CTP_ERR_CAPACITY, "CSR needs more than %lld entries", (long long)cap);
     } else if (nnz) {
       CK(cudaMemcpyAsync(col + base, B[bi].d_col, nnz * 4, cudaMemcpyDeviceToHost, s_out));
-      CK(cudaMemcpyAsync(w + base, B[bi].d_w, nnz * 8, cudaMemcpyDeviceToHost, s_out));
-      m->io_d2h += (unsigned long long)nnz * 12;
+      if (want_w) CK(cudaMemcpyAsync(w + base, B[bi].d_w, nnz * 8, cudaMemcpyDeviceToHost, s_out));
+      m->io_d2h += (unsigned long long)nnz * (want_w ? 12 : 4);
     }
     CK(cudaEventRecord(m->ev_out[bi], s_out));
     base += nnz;
@@ -1691,8 +1773,8 @@ extern "C" int ctp_sample_multiple(ctp_map *m, const double *start, const double
     const int64_t q0 = cs[c], qn = cs[c + 1] - q0;
     CKR(pipe_stage_b_refill(m, F[bi], bi, cand, q0, qn, cnt, n, clr, m->h_nf + (size_t)bi * qc,
                             m->h_nf + (size_t)(2 + bi) * (qc + 1)));
-    CKR(ctp_build_prm_dev(m, F[bi].d_n, qn, n, k, clr, cdc, nullptr, nullptr, B[bi].d_rp, B[bi].d_col, B[bi].d_w, ecap,
-                          B[bi].d_off, s_comp));
+    CKR(ctp_build_prm_ex_dev(m, F[bi].d_n, qn, n, k, clr, cdc, csr_flags, nullptr, nullptr, B[bi].d_rp, B[bi].d_col,
+                             B[bi].d_w, ecap, B[bi].d_off, s_comp));
     CK(cudaEventRecord(m->ev_comp[bi], s_comp));
     if (c >= 1) CKR(finish(c - 1));
     CK(cudaStreamWaitEvent(s_small, m->ev_comp[bi], 0));

@@ -28,7 +28,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
 // reference; the draws come from Philox keyed by `seed`, counter = (candidate, query, block).
 __global__ void __launch_bounds__(256)
 k_sample_ellipsoid(const double *__restrict__ start, const double *__restrict__ goal, int64_t q, int64_t m,
-                   double ratio, int planar, uint64_t seed, double *__restrict__ cand) {
+                   double ratio, int planar, uint64_t seed, double *__restrict__ cand, double *__restrict__ draws = nullptr) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < q * m; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t qi = t / m, ci = t - qi * m;
     const double sx = start[3 * qi], sy = start[3 * qi + 1], sz = start[3 * qi + 2];
@@ -69,6 +69,12 @@ k_sample_ellipsoid(const double *__restrict__ start, const double *__restrict__ 
     o[0] = ((a1[0] * b0 + a2[0] * b1) + a3[0] * b2) + (sx + gx) / 2.0;
     o[1] = ((a1[1] * b0 + a2[1] * b1) + a3[1] * b2) + (sy + gy) / 2.0;
     o[2] = planar ? sz : ((a1[2] * b0 + a2[2] * b1) + a3[2] * b2) + (sz + gz) / 2.0;
+    if (draws) {  // the uniform and the three normal draws of this point (src/common.cpp:295-303)
+      draws[4 * t] = u;
+      draws[4 * t + 1] = g0;
+      draws[4 * t + 2] = g1;
+      draws[4 * t + 3] = g2;
+    }
   }
 }
 

@@ -726,22 +726,31 @@ __device__ __forceinline__ int64_t csr_row_query(int64_t row, int64_t n, const C
   return sp.small ? (int64_t)ctp_div_u31((uint32_t)row, sp.dn) : row / n;
 }
 
-// free bytes of a row -> mask in the record; out-degree seeds deg[].  When every node id fits 16 bits
+// free bytes of a row -> mask in the record; own[] = entries the row contributes to itself.  A slot without a
+// neighbour (id < 0) never counts as free, whatever the caller's verdict byte says.  upper != 0: only entries with
+// col > row are emitted (each undirected edge once), so own[] counts only those.  When every node id fits 16 bits
 // (n <= 65535, k <= 14) the row is also written as a 32-byte record of 16-bit ids (slot 15 = mask, absent
 // neighbours = 0xffff), which halves the gather of the reverse-edge test.
-__global__ void __launch_bounds__(256) k_csr_rowmask(const uint8_t *__restrict__ fr, int k, int ns, int64_t total_rows,
-                                                     int32_t *__restrict__ rec, int32_t *__restrict__ deg,
-                                                     uint16_t *__restrict__ rec16) {
+__global__ void __launch_bounds__(256) k_csr_rowmask(const uint8_t *__restrict__ fr, int64_t n, int k, int ns,
+                                                     int64_t total_rows, CsrSplit sp, int upper, int32_t *__restrict__ rec,
+                                                     int32_t *__restrict__ own, uint16_t *__restrict__ rec16) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (row >= total_rows) return;
-  unsigned mask = 0;
-  for (int s = 0; s < k; s++) mask |= (fr[row * k + s] ? 1u : 0u) << s;
+  const int i = (int)(row - csr_row_query(row, n, sp) * n);
+  unsigned mask = 0, gt = 0;
+  int ids[CTP_KNN_MAXK];
+#pragma unroll
+  for (int s = 0; s < CTP_KNN_MAXK; s++) {
+    ids[s] = s < k ? rec[row * ns + s] : -1;
+    if (s < k && fr[row * k + s] && ids[s] >= 0) mask |= 1u << s;
+    if (ids[s] > i) gt |= 1u << s;
+  }
   rec[row * ns + ns - 1] = (int)mask;
-  deg[row] = __popc(mask);
+  own[row] = __popc(upper ? (mask & gt) : mask);
   if (rec16) {
     unsigned short v[16];
 #pragma unroll
-    for (int s = 0; s < 15; s++) v[s] = s < k ? (unsigned short)rec[row * ns + s] : (unsigned short)0xffff;  // -1 -> 0xffff
+    for (int s = 0; s < 15; s++) v[s] = (unsigned short)ids[s];  // -1 -> 0xffff
     v[15] = (unsigned short)mask;
     uint4 lo, hi;
     lo.x = v[0] | (v[1] << 16); lo.y = v[2] | (v[3] << 16); lo.z = v[4] | (v[5] << 16); lo.w = v[6] | (v[7] << 16);
@@ -752,14 +761,15 @@ __global__ void __launch_bounds__(256) k_csr_rowmask(const uint8_t *__restrict__
   }
 }
 
-// does the 32-byte record of row `row` list `target` as a free neighbour?
-__device__ __forceinline__ bool csr_lists_free16(const uint16_t *__restrict__ rec16, int64_t row, int k, int target) {
-  // the whole 32-byte record in one 256-bit load (sm_100 LDG.256): one request per edge instead of two
-  unsigned w[8];
+// the 32-byte record of a row in one 256-bit load (sm_100 LDG.256)
+__device__ __forceinline__ void csr_load_rec16(const uint16_t *__restrict__ rec16, int64_t row, unsigned w[8]) {
   asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
       : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
       : "l"(rec16 + row * 16));
-  const unsigned mask = w[7] >> 16;
+}
+// does a 16-bit record list `target` as a free neighbour?  mask_out = the record's free mask
+__device__ __forceinline__ bool csr_lists_free16(const unsigned w[8], int k, int target, unsigned &mask_out) {
+  const unsigned mask = (w[7] >> 16) & ((1u << k) - 1u);
   const unsigned t = (unsigned)target & 0xffffu;
   unsigned hit = 0;
 #pragma unroll
@@ -767,11 +777,13 @@ __device__ __forceinline__ bool csr_lists_free16(const uint16_t *__restrict__ re
     hit |= ((w[i] & 0xffffu) == t ? 1u : 0u) << (2 * i);
     hit |= ((w[i] >> 16) == t ? 1u : 0u) << (2 * i + 1);
   }
-  return (hit & mask & ((1u << k) - 1u)) != 0;
+  mask_out = mask;
+  return (hit & mask) != 0;
 }
 
 template <int NS>
-__device__ __forceinline__ bool csr_lists_free(const int32_t *__restrict__ rec, int64_t row, int k, int target) {
+__device__ __forceinline__ bool csr_lists_free(const int32_t *__restrict__ rec, int64_t row, int k, int target,
+                                               unsigned &mask_out) {
   const int4 *r4 = reinterpret_cast<const int4 *>(rec + row * NS);
   int v[NS];
 #pragma unroll
@@ -779,48 +791,102 @@ __device__ __forceinline__ bool csr_lists_free(const int32_t *__restrict__ rec, 
     const int4 q = __ldg(r4 + t);
     v[4 * t] = q.x; v[4 * t + 1] = q.y; v[4 * t + 2] = q.z; v[4 * t + 3] = q.w;
   }
-  const unsigned mask = (unsigned)v[NS - 1];
+  const unsigned mask = (unsigned)v[NS - 1] & ((1u << k) - 1u);
   unsigned hit = 0;
 #pragma unroll
   for (int s = 0; s < NS - 1; s++) hit |= (v[s] == target ? 1u : 0u) << s;
-  if (NS == 32) hit |= 0;  // k <= 16 < 31 slots
-  return (hit & mask & ((1u << k) - 1u)) != 0;
+  mask_out = mask;
+  return (hit & mask) != 0;
 }
 
-// per directed edge: flag 0 = blocked, 1 = free and the reverse edge is listed free as well,
-// 2 = free and the reverse is not (row j gets the extra entry i)
-template <int NS>
-__global__ void __launch_bounds__(256) k_csr_degree(const int32_t *__restrict__ rec, const uint16_t *__restrict__ rec16,
-                                                    const uint8_t *__restrict__ fr, int64_t n, int k, int64_t total_edges,
-                                                    CsrSplit sp, uint8_t *__restrict__ flag, int32_t *__restrict__ deg) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= total_edges) return;
-  if (!fr[e]) {
-    flag[e] = 0;
-    return;
+// Extra entries.  A free directed edge i -> j always puts j into row i (an "own" entry, known from row i's mask);
+// it also puts i into row j unless row j lists i as a free neighbour itself.  Those extra entries are pushed here:
+// one thread per row i walks its free slots, gathers the record of each neighbour j (one 32-byte load) and, where
+// j does not list i, bumps xcnt[j] and parks i in row j's staging line (CTP_CSR_XCAP ids per row; the value the
+// atomic returns is the slot).  A row whose line overflows is put on the `big` list and finished by k_csr_emit_big
+// (its count stays exact).  upper != 0: row j only holds ids above j, so only slots with j < i push anything.
+#define CTP_CSR_XCAP 16
+
+template <int NS, typename XT, bool R16>
+__global__ void __launch_bounds__(256) k_csr_count(const int32_t *__restrict__ rec, const uint16_t *__restrict__ rec16,
+                                                   int64_t n, int k, int64_t total_rows, CsrSplit sp, int upper,
+                                                   int32_t *__restrict__ xcnt, XT *__restrict__ xtra,
+                                                   int32_t *__restrict__ big_list, int32_t *__restrict__ big_cnt) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= total_rows) return;
+  const int64_t q = csr_row_query(row, n, sp);
+  const int64_t qbase = q * n;
+  const int i = (int)(row - qbase);
+  int ids[CTP_KNN_MAXK];
+  unsigned mask;
+  if (R16) {
+    unsigned w[8];
+    csr_load_rec16(rec16, row, w);
+#pragma unroll
+    for (int s = 0; s < 15; s++) ids[s] = (int)((s & 1) ? (w[s >> 1] >> 16) : (w[s >> 1] & 0xffffu));
+    ids[15] = 0;
+    mask = (w[7] >> 16) & ((1u << k) - 1u);
+  } else {
+    const int4 *r4 = reinterpret_cast<const int4 *>(rec + row * NS);
+    int v[NS];
+#pragma unroll
+    for (int t = 0; t < NS / 4; t++) {
+      const int4 qq = __ldg(r4 + t);
+      v[4 * t] = qq.x; v[4 * t + 1] = qq.y; v[4 * t + 2] = qq.z; v[4 * t + 3] = qq.w;
+    }
+#pragma unroll
+    for (int s = 0; s < CTP_KNN_MAXK; s++) ids[s] = v[s];
+    mask = (unsigned)v[NS - 1] & ((1u << k) - 1u);
   }
-  int64_t row, qbase;
-  int slot, i;
-  csr_edge_split(e, n, k, sp, row, slot, qbase, i);
-  const int j = rec[row * NS + slot];
-  const bool rev = rec16 ? csr_lists_free16(rec16, qbase + j, k, i) : csr_lists_free<NS>(rec, qbase + j, k, i);
-  flag[e] = rev ? 1 : 2;
-  if (!rev) atomicAdd(deg + qbase + j, 1);
+  if (upper) {
+#pragma unroll
+    for (int s = 0; s < CTP_KNN_MAXK; s++)
+      if (ids[s] >= i) mask &= ~(1u << s);
+  }
+  // four neighbour records in flight at a time
+#pragma unroll
+  for (int s0 = 0; s0 < CTP_KNN_MAXK; s0 += 4) {
+    if (!((mask >> s0) & 15u)) continue;
+    bool rev[4];
+    unsigned mj[4];
+    (void)mj;
+    if (R16) {
+      unsigned w[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if ((mask >> (s0 + u)) & 1u) csr_load_rec16(rec16, qbase + ids[s0 + u], w[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if ((mask >> (s0 + u)) & 1u) rev[u] = csr_lists_free16(w[u], k, i, mj[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if ((mask >> (s0 + u)) & 1u) rev[u] = csr_lists_free<NS>(rec, qbase + ids[s0 + u], k, i, mj[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (!((mask >> (s0 + u)) & 1u) || rev[u]) continue;
+      const int j = ids[s0 + u];
+      const int pos = atomicAdd(xcnt + qbase + j, 1);
+      if (pos < CTP_CSR_XCAP) xtra[(qbase + j) * CTP_CSR_XCAP + pos] = (XT)i;
+      else if (pos == CTP_CSR_XCAP) big_list[atomicAdd(big_cnt, 1)] = (int32_t)(qbase + j);
+    }
+  }
 }
 
 // one CTA per query: row_ptr (relative) = exclusive scan of degrees; nnz per query
-__global__ void __launch_bounds__(1024) k_csr_rowptr(int32_t *__restrict__ deg, int64_t n,
-                                                     int32_t *__restrict__ row_ptr, int64_t *__restrict__ nnz) {
+__global__ void __launch_bounds__(1024) k_csr_rowptr(const int32_t *__restrict__ own, const int32_t *__restrict__ xcnt,
+                                                     int64_t n, int32_t *__restrict__ row_ptr, int64_t *__restrict__ nnz) {
   __shared__ int wsum[32];
   __shared__ int carry;
   const int64_t q = blockIdx.x;
-  int32_t *dq = deg + q * n;
+  const int32_t *dq = own + q * n, *xq = xcnt + q * n;
   int32_t *rp = row_ptr + q * (n + 1);
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (int64_t base = 0; base < n; base += 1024) {
     const int64_t i = base + threadIdx.x;
-    const int v = i < n ? dq[i] : 0;
+    const int v = i < n ? dq[i] + xq[i] : 0;
     int s = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -841,10 +907,7 @@ __global__ void __launch_bounds__(1024) k_csr_rowptr(int32_t *__restrict__ deg, 
     __syncthreads();
     const int woff = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
     const int c = carry;
-    if (i < n) {
-      rp[i] = c + woff + s - v;
-      dq[i] = 0;  // becomes the fill cursor
-    }
+    if (i < n) rp[i] = c + woff + s - v;
     __syncthreads();
     if (threadIdx.x == 1023) carry = c + woff + s;
     __syncthreads();
@@ -893,95 +956,211 @@ __global__ void __launch_bounds__(1024) k_csr_query_offsets(const int64_t *__res
   if (threadIdx.x == 0) nnz_off[q] = carry;
 }
 
-// own free neighbours go to the head of the row in slot order (rank from the mask, no atomics);
-// the extra entries contributed by other rows follow, placed with a per-row cursor
-template <int NS>
-__global__ void __launch_bounds__(256) k_csr_fill(const int32_t *__restrict__ rec, const uint8_t *__restrict__ flag,
-                                                  int64_t n, int k, int64_t total_edges, CsrSplit sp,
-                                                  const int32_t *__restrict__ row_ptr,
-                                                  const int64_t *__restrict__ nnz_off, int64_t cap,
-                                                  int32_t *__restrict__ cursor, int32_t *__restrict__ col) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= total_edges) return;
-  const int fl = flag[e];
-  if (!fl) return;
-  int64_t row, qbase;
-  int slot, i;
-  csr_edge_split(e, n, k, sp, row, slot, qbase, i);
-  const int64_t q = csr_row_query(row, n, sp);
-  const int j = rec[row * NS + slot];
-  const int32_t *rp = row_ptr + q * (n + 1);
-  const int64_t base = nnz_off[q];
-  {
-    const unsigned mask = (unsigned)rec[row * NS + NS - 1];
-    const int64_t pos = base + rp[i] + __popc(mask & ((1u << slot) - 1u));
-    if (pos < cap) col[pos] = j;
-  }
-  if (fl == 2) {
-    const unsigned mj = (unsigned)rec[(qbase + j) * NS + NS - 1];
-    const int64_t pos = base + rp[j] + __popc(mj) + atomicAdd(cursor + qbase + j, 1);
-    if (pos < cap) col[pos] = i;
+// ascending sorting network over N registers (N a power of two), fully unrolled
+template <int N> __device__ __forceinline__ void csr_reg_sort(unsigned (&v)[N]) {
+#pragma unroll
+  for (int kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        const int l = i ^ jj;
+        if (l > i) {
+          const unsigned a = v[i], b = v[l];
+          const unsigned lo = min(a, b), hi = max(a, b);
+          const bool up = (i & kk) == 0;
+          v[i] = up ? lo : hi;
+          v[l] = up ? hi : lo;
+        }
+      }
+    }
   }
 }
 
-// one thread per CSR ENTRY (a warp takes 32 consecutive rows and walks their entries in flat order):
-// the entry's final position is its rank among the row's column ids (they are distinct), so the
-// ascending order needs no per-thread sort and every load/store is coalesced; the FP64 weight
-// ||to - from|| (:369-371) is computed on the way out.  col_in -> col / w (out of place).
-__global__ void __launch_bounds__(256) k_csr_finish_flat(const double *__restrict__ nodes, int64_t n, int64_t total_rows,
-                                                         CsrSplit sp, const int32_t *__restrict__ row_ptr,
-                                                         const int64_t *__restrict__ nnz_off, int64_t cap,
-                                                         const int32_t *__restrict__ col_in, int32_t *__restrict__ col,
-                                                         double *__restrict__ w) {
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
-  if (r0 >= total_rows) return;
-  // lane l: global start/end of row r0 + l (rows of one warp may straddle two queries)
-  const int64_t row = r0 + lane;
-  int64_t rb = 0, re = 0;
+// Emit: a CTA takes CTP_CSR_EMIT_ROWS consecutive rows.  Phase 1, one thread per row: the row's own free ids and
+// its parked extra ids go through a 32-wide sorting network in registers (absent slots = 0xffffffff sort to the
+// tail) and the row's ascending ids land in shared memory, back to back in row order.  Phase 2, one thread per
+// ENTRY: the FP64 weight ||to - from|| (:369-371) from the staged own coordinates and one gathered neighbour, then
+// col / w go out in final order -- every global load and store of the kernel is coalesced except that one gather.
+#define CTP_CSR_EMIT_ROWS 128
+
+template <int NS, typename XT>
+__global__ void __launch_bounds__(CTP_CSR_EMIT_ROWS)
+k_csr_emit(const double *__restrict__ nodes, const int32_t *__restrict__ rec, const uint16_t *__restrict__ rec16,
+           const XT *__restrict__ xtra, int64_t n, int k, int64_t total_rows, CsrSplit sp, int upper,
+           const int32_t *__restrict__ row_ptr, const int64_t *__restrict__ nnz_off, int64_t cap,
+           int32_t *__restrict__ col, double *__restrict__ w) {
+  __shared__ unsigned s_col[CTP_CSR_EMIT_ROWS * 32];
+  __shared__ uint8_t s_own[CTP_CSR_EMIT_ROWS * 32];
+  __shared__ double s_node[CTP_CSR_EMIT_ROWS][3];
+  __shared__ long long s_gbeg[CTP_CSR_EMIT_ROWS];  // global position of the row's first entry
+  __shared__ int s_loff[CTP_CSR_EMIT_ROWS + 1];    // position of the row's first entry in s_col
+  __shared__ long long s_qbase[CTP_CSR_EMIT_ROWS];
+  __shared__ int s_wsum[CTP_CSR_EMIT_ROWS / 32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int64_t row = (int64_t)blockIdx.x * CTP_CSR_EMIT_ROWS + t;
+  unsigned v[32];
+  int cnt = 0;
   if (row < total_rows) {
-    const int64_t q = csr_row_query(row, n, sp), i = row - q * n;
+    const int64_t q = csr_row_query(row, n, sp);
+    const int64_t qbase = q * n;
+    const int i = (int)(row - qbase);
     const int32_t *rp = row_ptr + q * (n + 1);
-    rb = nnz_off[q] + rp[i];
-    re = nnz_off[q] + rp[i + 1];
-  }
-  const int len = (int)(re - rb);
-  int incl = len;
+    const int rb = rp[i], deg_i = rp[i + 1] - rb;
+    s_gbeg[t] = nnz_off[q] + rb;
+    s_qbase[t] = qbase;
+    s_node[t][0] = nodes[3 * row];
+    s_node[t][1] = nodes[3 * row + 1];
+    s_node[t][2] = nodes[3 * row + 2];
+    unsigned mask;
+    if (rec16) {
+      unsigned ww[8];
+      csr_load_rec16(rec16, row, ww);
+      mask = (ww[7] >> 16) & ((1u << k) - 1u);
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(full, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const int total = __shfl_sync(full, incl, 31);
-  for (int e0 = 0; e0 < total; e0 += 32) {
-    const int e = e0 + lane;
-    // owner lane = number of rows whose inclusive prefix is <= e
-    int lo = 0;
+      for (int s = 0; s < 16; s++) {
+        const unsigned id = (s & 1) ? (ww[s >> 1] >> 16) : (ww[s >> 1] & 0xffffu);
+        if (upper && (int)id <= i) mask &= ~(1u << s);
+        v[s] = ((mask >> s) & 1u) ? id : 0xffffffffu;
+      }
+    } else {
+      const int4 *r4 = reinterpret_cast<const int4 *>(rec + row * NS);
+      int rr[NS];
 #pragma unroll
-    for (int step = 16; step > 0; step >>= 1) {
-      const int probe = __shfl_sync(full, incl, lo + step - 1);
-      if (probe <= e) lo += step;
-    }
-    const int owner = min(lo, 31);
-    const int64_t obeg = __shfl_sync(full, rb, owner);
-    const int olen = __shfl_sync(full, len, owner);
-    const int oexcl = __shfl_sync(full, incl, owner) - olen;
-    if (e < total) {
-      if (obeg + olen <= cap) {
-        const int32_t c = col_in[obeg + (e - oexcl)];
-        int rank = 0;
-#pragma unroll 4
-        for (int x = 0; x < olen; x++) rank += (__ldg(col_in + obeg + x) < c) ? 1 : 0;
-        const int64_t orow = r0 + owner;
-        const int64_t oq = csr_row_query(orow, n, sp);
-        const double *me = nodes + 3 * orow;
-        const double *o = nodes + 3 * (oq * n + c);
-        const double dx = o[0] - me[0], dy = o[1] - me[1], dz = o[2] - me[2];
-        col[obeg + rank] = c;
-        w[obeg + rank] = sqrt((dx * dx + dy * dy) + dz * dz);
+      for (int u = 0; u < NS / 4; u++) {
+        const int4 qq = __ldg(r4 + u);
+        rr[4 * u] = qq.x; rr[4 * u + 1] = qq.y; rr[4 * u + 2] = qq.z; rr[4 * u + 3] = qq.w;
+      }
+      mask = (unsigned)rr[NS - 1] & ((1u << k) - 1u);
+#pragma unroll
+      for (int s = 0; s < 16; s++) {
+        if (upper && rr[s] <= i) mask &= ~(1u << s);
+        v[s] = ((mask >> s) & 1u) ? (unsigned)rr[s] : 0xffffffffu;
       }
     }
+    const int nx = deg_i - __popc(mask);
+    if (nx <= CTP_CSR_XCAP) {  // else: a `big` row, written by k_csr_emit_big
+      cnt = deg_i;
+      const XT *xr = xtra + row * CTP_CSR_XCAP;
+      if (sizeof(XT) == 2) {
+        const uint4 *x4 = reinterpret_cast<const uint4 *>(xr);
+        const uint4 a = nx > 0 ? x4[0] : make_uint4(0, 0, 0, 0), b = nx > 8 ? x4[1] : make_uint4(0, 0, 0, 0);
+        const unsigned ww[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+          const unsigned id = (s & 1) ? (ww[s >> 1] >> 16) : (ww[s >> 1] & 0xffffu);
+          v[16 + s] = s < nx ? id : 0xffffffffu;
+        }
+      } else {
+        const uint4 *x4 = reinterpret_cast<const uint4 *>(xr);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint4 a = nx > 4 * u ? x4[u] : make_uint4(0, 0, 0, 0);
+          v[16 + 4 * u] = 4 * u < nx ? a.x : 0xffffffffu;
+          v[16 + 4 * u + 1] = 4 * u + 1 < nx ? a.y : 0xffffffffu;
+          v[16 + 4 * u + 2] = 4 * u + 2 < nx ? a.z : 0xffffffffu;
+          v[16 + 4 * u + 3] = 4 * u + 3 < nx ? a.w : 0xffffffffu;
+        }
+      }
+      csr_reg_sort<32>(v);
+    }
+  }
+  // exclusive scan of cnt over the CTA
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) s_wsum[wid] = incl;
+  __syncthreads();
+  int woff = 0;
+#pragma unroll
+  for (int u = 0; u < CTP_CSR_EMIT_ROWS / 32; u++) woff += u < wid ? s_wsum[u] : 0;
+  const int loff = woff + incl - cnt;
+  s_loff[t] = loff;
+  if (t == CTP_CSR_EMIT_ROWS - 1) s_loff[CTP_CSR_EMIT_ROWS] = loff + cnt;
+#pragma unroll
+  for (int s = 0; s < 32; s++)
+    if (s < cnt) {
+      s_col[loff + s] = v[s];
+      s_own[loff + s] = (uint8_t)t;
+    }
+  __syncthreads();
+  const int total = s_loff[CTP_CSR_EMIT_ROWS];
+  for (int x = t; x < total; x += CTP_CSR_EMIT_ROWS) {
+    const int ow = s_own[x];
+    const unsigned c = s_col[x];
+    const int64_t pos = s_gbeg[ow] + (x - s_loff[ow]);
+    const double *o = nodes + 3 * (s_qbase[ow] + (int64_t)c);
+    const double dx = o[0] - s_node[ow][0], dy = o[1] - s_node[ow][1], dz = o[2] - s_node[ow][2];
+    if (pos < cap) {
+      col[pos] = (int32_t)c;
+      if (w) w[pos] = sqrt((dx * dx + dy * dy) + dz * dz);
+    }
+  }
+}
+
+// Rows with more than CTP_CSR_XCAP extra entries (a node many others list without being listed back: never seen
+// on sampled roadmaps, but legal).  One CTA per listed row j: own free ids, then every i of the query whose record
+// lists j free while j's does not list i, collected straight into the row's col range; ranked into order through
+// a per-CTA scratch line (tmp: gridDim.x lines of n + 32 ids); weights last.
+template <int NS>
+__global__ void __launch_bounds__(256) k_csr_emit_big(const double *__restrict__ nodes, const int32_t *__restrict__ rec,
+                                                      int64_t n, int k, CsrSplit sp, int upper, const int32_t *__restrict__ big_list,
+                                                      const int32_t *__restrict__ big_cnt, const int32_t *__restrict__ row_ptr,
+                                                      const int64_t *__restrict__ nnz_off, int64_t cap,
+                                                      int32_t *__restrict__ tmp_all, int32_t *__restrict__ col,
+                                                      double *__restrict__ w) {
+  __shared__ int s_fill;
+  const int nbig = *big_cnt;
+  int32_t *tmp = tmp_all + (size_t)blockIdx.x * (size_t)(n + 32);
+  for (int b = blockIdx.x; b < nbig; b += gridDim.x) {
+    const int64_t row = big_list[b];
+    const int64_t q = csr_row_query(row, n, sp), qbase = q * n;
+    const int j = (int)(row - qbase);
+    const int32_t *rp = row_ptr + q * (n + 1);
+    const int64_t gb = nnz_off[q] + rp[j];
+    const int deg_j = rp[j + 1] - rp[j];
+    if (gb + deg_j > cap) continue;  // uniform over the CTA
+    const unsigned kmask = (1u << k) - 1u;
+    const unsigned mj = (unsigned)rec[row * NS + NS - 1] & kmask;
+    if (threadIdx.x == 0) {
+      int c = 0;
+      for (int s = 0; s < k; s++)
+        if (((mj >> s) & 1u) && (!upper || rec[row * NS + s] > j)) col[gb + c++] = rec[row * NS + s];
+      s_fill = c;
+    }
+    __syncthreads();
+    for (int64_t i = (upper ? j + 1 : 0) + threadIdx.x; i < n; i += blockDim.x) {
+      const int32_t *ri = rec + (qbase + i) * NS;
+      const unsigned mi = (unsigned)ri[NS - 1] & kmask;
+      bool lists = false;
+      for (int s = 0; s < k; s++) lists |= ((mi >> s) & 1u) && ri[s] == j;
+      if (!lists) continue;
+      bool back = false;
+      for (int s = 0; s < k; s++) back |= ((mj >> s) & 1u) && rec[row * NS + s] == (int)i;
+      if (!back) col[gb + atomicAdd(&s_fill, 1)] = (int32_t)i;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < deg_j; x += blockDim.x) {
+      const int32_t c = col[gb + x];
+      int rank = 0;
+      for (int y = 0; y < deg_j; y++) rank += col[gb + y] < c ? 1 : 0;
+      tmp[rank] = c;
+    }
+    __syncthreads();
+    const double *me = nodes + 3 * row;
+    for (int x = threadIdx.x; x < deg_j; x += blockDim.x) {
+      const int32_t c = tmp[x];
+      col[gb + x] = c;
+      if (w) {
+        const double *o = nodes + 3 * (qbase + c);
+        const double dx = o[0] - me[0], dy = o[1] - me[1], dz = o[2] - me[2];
+        w[gb + x] = sqrt((dx * dx + dy * dy) + dz * dz);
+      }
+    }
+    __syncthreads();
   }
 }
 

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <memory>
 
+#include "ctopprm/csr_expand.hpp"
 #include "ctopprm/esdf_map.hpp"
 #include "ctopprm/topological_prm_clustering.hpp"
 
@@ -32,6 +33,11 @@ struct PlannerBox { std::unique_ptr<Planner> pl; };
 }  // namespace
 
 extern "C" {
+// compact (upper, unweighted) adjacency of q roadmaps -> full symmetric weighted CSR, on `threads` host threads
+void ctph_csr_expand_upper(const double *nodes, long long q, long long n, const int *rp_up, const int *col_up,
+                           const long long *off_up, int *row_ptr, int *col, double *w, long long *nnz_off, int threads) {
+  ctopprm::csr_expand_upper(nodes, q, n, rp_up, col_up, (const int64_t *)off_up, row_ptr, col, w, (int64_t *)nnz_off, threads);
+}
 void *ctph_map_load(const char *filename, int device, int layouts) {
   try {
     ESDFMap::setDevice(device);

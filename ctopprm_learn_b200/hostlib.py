@@ -256,3 +256,21 @@ def remove_too_long(lengths):
     keep = np.empty(len(lengths), dtype=np.int32)
     n = lib().ctph_remove_too_long(_p(lengths), len(lengths), _p(keep))
     return keep[:n].copy()
+
+
+def csr_expand_upper(nodes, row_ptr_up, col_up, off_up, threads=1, want_w=True, out=None):
+    """host-side mirror (include/ctopprm/csr_expand.hpp): compact adjacency -> full symmetric weighted CSR.
+    nodes q x n x 3, row_ptr_up q x (n+1), col_up packed, off_up q+1.  out: dict(row_ptr, col, w, nnz_off) to reuse."""
+    nodes = _f(nodes)
+    q, n = nodes.shape[0], nodes.shape[1]
+    rp = np.ascontiguousarray(row_ptr_up, dtype=np.int32)
+    cu = np.ascontiguousarray(col_up, dtype=np.int32)
+    ou = np.ascontiguousarray(off_up, dtype=np.int64)
+    nnz = 2 * int(ou[q])
+    if out is None:
+        out = dict(row_ptr=np.empty((q, n + 1), dtype=np.int32), col=np.empty(nnz, dtype=np.int32),
+                   w=np.empty(nnz) if want_w else None, nnz_off=np.empty(q + 1, dtype=np.int64))
+    w = out.get("w")
+    lib().ctph_csr_expand_upper(_p(nodes), C.c_longlong(q), C.c_longlong(n), _p(rp), _p(cu), _p(ou), _p(out["row_ptr"]),
+                                _p(out["col"]), _p(w) if w is not None else None, _p(out["nnz_off"]), C.c_int(threads))
+    return out

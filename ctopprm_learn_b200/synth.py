@@ -158,8 +158,55 @@ def default_query(centroid, extents):
     return s, g
 
 
-def random_queries(centroid, extents, q: int, seed: int, min_sep_frac: float = 1 / 3):
-    """C4: start-goal pairs ~U inside the box (1 m inset) with ||g-s|| >= E*min_sep_frac."""
+def config_obstacles(cfg: str):
+    """the analytic obstacles of a configured map: (centroid, trunks (cx, cy, r), canopies (x, y, z, r) or None) --
+    the same draws, in the same order, as random_columns_esdf / forest_esdf make"""
+    kind, extent, n, n_obs, seed, _ = CONFIGS[cfg]
+    rng = np.random.default_rng(seed)
+    c = centroid_for(extent)
+    cx = c[0] + (rng.random(n_obs) - 0.5) * extent
+    cy = c[1] + (rng.random(n_obs) - 0.5) * extent
+    if kind == "columns":
+        r = 0.15 + rng.random(n_obs) * 0.45
+        return c, (cx, cy, r), None
+    r = 0.1 + rng.random(n_obs) * 0.4
+    n_canopy = n_obs // 2
+    k = rng.integers(0, n_obs, n_canopy)
+    sz = c[2] + (rng.random(n_canopy) - 0.5) * extent * 0.6
+    sr = 0.5 + rng.random(n_canopy) * 1.0
+    return c, (cx, cy, r), (cx[k], cy[k], sz, sr)
+
+
+def analytic_clearance(cfg, pts):
+    """distance from pts (m x 3) to the nearest analytic obstacle of a configured map (not the gridded field: used
+    only to draw start / goal positions in free space).  cfg: a CONFIGS key, or the
+    obstacles themselves as ((cx, cy, r), canopies or None)."""
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+    if isinstance(cfg, str):
+        _, (cx, cy, r), canopy = config_obstacles(cfg)
+    else:
+        (cx, cy, r), canopy = cfg
+    out = np.full(len(pts), np.inf)
+    for lo in range(0, len(pts), 4096):
+        p = pts[lo:lo + 4096]
+        d = np.hypot(p[:, None, 0] - cx[None], p[:, None, 1] - cy[None]) - r[None]
+        best = d.min(axis=1)
+        if canopy is not None:
+            sx, sy, sz, sr = canopy
+            ds = np.sqrt((p[:, None, 0] - sx[None]) ** 2 + (p[:, None, 1] - sy[None]) ** 2 + (p[:, None, 2] - sz[None]) ** 2) - sr[None]
+            best = np.minimum(best, ds.min(axis=1))
+        out[lo:lo + 4096] = best
+    return out
+
+
+# start / goal of the C4 query set keep this much distance to the analytic obstacles (min_clearance + 2 voxels of
+# slack for the gridded field): "start-goal pairs ~U in free space" (SURVEY.md section 8d)
+QUERY_CLEARANCE = MIN_CLEARANCE + 0.1
+
+
+def random_queries(centroid, extents, q: int, seed: int, min_sep_frac: float = 1 / 3, cfg=None):
+    """C4: start-goal pairs ~U inside the box (1 m inset) with ||g-s|| >= E*min_sep_frac; with cfg (a CONFIGS key)
+    both ends are also required to lie in free space of that map (analytic obstacles, QUERY_CLEARANCE)."""
     rng = np.random.default_rng(seed)
     c = np.asarray(centroid, dtype=np.float64)
     e = np.asarray(extents, dtype=np.float64)
@@ -167,11 +214,17 @@ def random_queries(centroid, extents, q: int, seed: int, min_sep_frac: float = 1
     out_g = np.empty((q, 3))
     k = 0
     while k < q:
-        s = c + (rng.random(3) - 0.5) * (e - 2.0)
-        g = c + (rng.random(3) - 0.5) * (e - 2.0)
-        if np.linalg.norm(g - s) >= e.max() * min_sep_frac:
-            out_s[k], out_g[k] = s, g
-            k += 1
+        # pairs are drawn in blocks so that the free-space test is vectorised; the draw order does not depend on q
+        blk = 256
+        s = c + (rng.random((blk, 3)) - 0.5) * (e - 2.0)
+        g = c + (rng.random((blk, 3)) - 0.5) * (e - 2.0)
+        ok = np.linalg.norm(g - s, axis=1) >= e.max() * min_sep_frac
+        if cfg is not None:
+            ok &= (analytic_clearance(cfg, s) >= QUERY_CLEARANCE) & (analytic_clearance(cfg, g) >= QUERY_CLEARANCE)
+        for i in np.nonzero(ok)[0]:
+            if k < q:
+                out_s[k], out_g[k] = s[i], g[i]
+                k += 1
     return out_s, out_g
 
 

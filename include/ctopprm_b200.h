@@ -187,6 +187,11 @@ int ctp_sample_ellipsoid_dev(ctp_map *map, const double *start, const double *go
 int ctp_sample_ellipsoid(ctp_map *map, const double *start, const double *goal, int64_t q,
                          int64_t m, double ratio, int planar, uint64_t seed, double *cand);
 
+/* the same candidates plus the draws behind them: draws q x m x 4 = (u, g0, g1, g2), the uniform and the three
+ * normal variates random_ellipsoid_point consumes per point (src/common.cpp:295-303) */
+int ctp_sample_ellipsoid_draws(ctp_map *map, const double *start, const double *goal, int64_t q, int64_t m,
+                               double ratio, int planar, uint64_t seed, double *cand, double *draws);
+
 /* ---- neighbour stage of sampleMultiple (:329-339): exact float32 k-NN.
  * nodes: q x n x 3 doubles, narrowed to float as :300-326.  idx: q x n x k (self excluded,
  * ascending (distance, index)), d2 (optional): q x n x k float32 squared distances. */
@@ -209,6 +214,16 @@ int ctp_build_prm_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, i
                       double clr, double cdc, int32_t *nbr, uint8_t *directed_free,
                       int32_t *row_ptr, int32_t *col, double *w, int64_t cap, int64_t *nnz_off,
                       void *stream);
+/* Compact forms of the adjacency (the symmetric CSR stores every undirected edge twice, and w(i,j) = w(j,i) =
+ * ||to - from|| can be recomputed from the node coordinates bit for bit): csr_flags is an OR of
+ *   CTP_CSR_UPPER       only entries with col > row (each undirected edge once; row_ptr / nnz_off describe those)
+ *   CTP_CSR_NO_WEIGHTS  w is neither computed nor written (w may be NULL)
+ * include/ctopprm/csr_expand.hpp mirrors a compact roadmap into the full symmetric, weighted CSR on the host. */
+#define CTP_CSR_UPPER 1
+#define CTP_CSR_NO_WEIGHTS 2
+int ctp_build_prm_ex_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, int k, double clr,
+                         double cdc, int csr_flags, int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr,
+                         int32_t *col, double *w, int64_t cap, int64_t *nnz_off, void *stream);
 /* the middle stage alone: the q*n*k directed checks (:355-373) of a given k-NN table nbr (q x n x k, -1 = no
  * neighbour) against this map -> directed_free (q x n x k).  ctp_knn_dev and ctp_csr_from_directed_dev do not look
  * at the map: a sweep over many maps runs them once for all queries and only the rejection and this stage per map. */
@@ -234,6 +249,12 @@ int ctp_sample_multiple(ctp_map *map, const double *start, const double *goal,
                         const double *cand, int64_t q, int64_t m, int64_t n, int k, double clr,
                         double cdc, double *nodes, int32_t *n_filled, int32_t *row_ptr,
                         int32_t *col, double *w, int64_t cap, int64_t *nnz_off);
+
+/* same with a compact adjacency (csr_flags as ctp_build_prm_ex_dev): two thirds to four fifths fewer bytes come back */
+int ctp_sample_multiple_ex(ctp_map *map, const double *start, const double *goal, const double *cand, int64_t q,
+                           int64_t m, int64_t n, int k, double clr, double cdc, int csr_flags, double *nodes,
+                           int32_t *n_filled, int32_t *row_ptr, int32_t *col, double *w, int64_t cap,
+                           int64_t *nnz_off);
 
 /* ---- graph search over the CSR roadmaps (first "next" item): shortest paths from
  * a set of sources, one independent problem per query.  Replaces Dijkstra::findPath as called by

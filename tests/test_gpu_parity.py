@@ -1125,3 +1125,184 @@ def test_clearance_at_the_box_faces(orc, shift):
             assert np.array_equal(f1[0], f0[0]) and np.array_equal(f1[2], f0[2])
         finally:
             m.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: fused adjacency stage (count -> scan -> emit), compact forms, draw-for-draw sampling
+
+def _union_csr(nodes, nbr, fr):
+    """symmetric union of the free directed edges by definition (include/topological_prm_clustering.hpp:374-385)"""
+    n, k = nbr.shape
+    adj = [set() for _ in range(n)]
+    for i in range(n):
+        for s in range(k):
+            j = int(nbr[i, s])
+            if fr[i, s] and j >= 0:
+                adj[i].add(j)
+                adj[j].add(i)
+    rp = np.zeros(n + 1, dtype=np.int32)
+    col, w = [], []
+    for i in range(n):
+        js = sorted(adj[i])
+        rp[i + 1] = rp[i] + len(js)
+        col += js
+        for j in js:
+            d = nodes[j] - nodes[i]
+            w.append(np.sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]))
+    return rp, np.array(col, dtype=np.int32), np.array(w)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_build_prm_and_merge_small_k(c1, k):
+    """k = 1..3: the 16-bit neighbour records used to borrow a scratch buffer that was too small for them"""
+    m, om, c, e = c1
+    m.set_layout(capi.LAYOUT_PLAIN)
+    q, n = 2, 700
+    s, g, cand = _queries(c, e, q, n, 60 + k)
+    nodes = m.sample_reject(s, g, cand, CLR, n)[0]
+    got = m.build_prm(nodes, CLR, CDC, k=k)
+    merged = m.csr_from_directed(nodes, got["nbr"], got["directed_free"])
+    for i in range(q):
+        want = om.build_prm(nodes[i], CLR, CDC, k=k, nthreads=4)
+        assert np.array_equal(got["nbr"][i], want["nbr"])
+        assert np.array_equal(got["directed_free"][i], want["directed_free"])
+        _csr_equal(got, i, want)
+        _csr_equal(merged, i, want)
+
+
+def test_adjacency_rows_with_many_incoming_edges(c1):
+    """a node that hundreds of others list without being listed back overflows the per-row staging line of the
+    adjacency stage and takes the k_csr_emit_big path; another one sits exactly at the line's capacity"""
+    m, om, c, e = c1
+    rng = np.random.default_rng(5)
+    n, k = 900, 4
+    nodes = c + (rng.random((2, n, 3)) - 0.5) * e * 0.9
+    nbr = np.empty((2, n, k), dtype=np.int32)
+    for qi in range(2):
+        for i in range(n):
+            others = rng.choice(np.delete(np.arange(n), i), k, replace=False)
+            nbr[qi, i] = others
+        nbr[qi, 3:400, 0] = 0          # node 0: ~400 incoming edges
+        nbr[qi, 0] = [1, 2, 3, 4]
+        nbr[qi, 500:516, 1] = 7        # node 7: 16 extra incoming edges (= the line's capacity)
+        nbr[qi, 520:537, 2] = 9        # node 9: 17 (one past it)
+        for i in range(n):              # no duplicates within a row, no self loops
+            row = nbr[qi, i]
+            for s_ in range(k):
+                while row[s_] == i or (row[:s_] == row[s_]).any():
+                    row[s_] = (row[s_] + 11) % n
+    fr = (rng.random((2, n, k)) < 0.85).astype(np.uint8)
+    fr[:, 3:400, 0] = 1
+    got = m.csr_from_directed(nodes, nbr, fr)
+    for qi in range(2):
+        rp, col, w = _union_csr(nodes[qi], nbr[qi], fr[qi])
+        a, b = int(got["nnz_off"][qi]), int(got["nnz_off"][qi + 1])
+        assert np.array_equal(got["row_ptr"][qi], rp)
+        assert np.array_equal(got["col"][a:b], col)
+        assert np.array_equal(got["w"][a:b], w)
+    assert got["row_ptr"][0][1] - got["row_ptr"][0][0] > 300
+
+
+def test_missing_neighbour_marked_free_is_ignored(c1):
+    m, om, c, e = c1
+    rng = np.random.default_rng(6)
+    n, k = 300, 5
+    nodes = c + (rng.random((1, n, 3)) - 0.5) * e * 0.9
+    nbr = np.stack([rng.permutation(np.delete(np.arange(n), i))[:k] for i in range(n)]).astype(np.int32)[None]
+    nbr[0, ::7, 3:] = -1               # short rows
+    fr = np.ones((1, n, k), dtype=np.uint8)  # ... whose missing slots are (wrongly) marked free
+    got = m.csr_from_directed(nodes, nbr, fr)
+    rp, col, w = _union_csr(nodes[0], nbr[0], fr[0])
+    assert np.array_equal(got["row_ptr"][0], rp) and np.array_equal(got["col"], col) and np.array_equal(got["w"], w)
+    with pytest.raises(capi.CtpError):
+        bad = nbr.copy()
+        bad[0, 0, 0] = -2
+        m.csr_from_directed(nodes, bad, fr)
+
+
+@pytest.mark.parametrize("n,k", [(900, 13), (70000, 13), (500, 16)])
+def test_compact_adjacency_forms(c1, n, k):
+    """CTP_CSR_UPPER / CTP_CSR_NO_WEIGHTS: each undirected edge once; mirrored on the host it is the full CSR again
+    (16-bit records at n = 900, 32-bit records at n = 70000, 128-byte records at k = 16)"""
+    from ctopprm_learn_b200 import hostlib
+    m, om, c, e = c1
+    m.set_layout(capi.LAYOUT_PLAIN)
+    q = 2
+    s, g = synth.random_queries(c, e, q, 71)
+    cand = np.stack([synth.ellipsoid_candidates(s[i], g[i], 4 * n, 710 + i) for i in range(q)])
+    nodes = m.sample_reject(s, g, cand, CLR, n)[0]
+    full = m.build_prm_ex(nodes, CLR, CDC, k=k, csr_flags=0)
+    ref = m.build_prm(nodes, CLR, CDC, k=k)
+    for key in ("row_ptr", "col", "w", "nnz_off"):
+        assert np.array_equal(full[key], ref[key])
+    for flags in (capi.CSR_UPPER, capi.CSR_UPPER | capi.CSR_NO_WEIGHTS, capi.CSR_NO_WEIGHTS):
+        got = m.build_prm_ex(nodes, CLR, CDC, k=k, csr_flags=flags)
+        if not flags & capi.CSR_UPPER:
+            assert np.array_equal(got["row_ptr"], full["row_ptr"]) and np.array_equal(got["col"], full["col"])
+            assert got["w"] is None
+            continue
+        assert int(got["nnz_off"][q]) * 2 == int(full["nnz_off"][q])
+        for i in range(q):
+            rp, a0 = full["row_ptr"][i], int(full["nnz_off"][i])
+            rows = np.repeat(np.arange(n), np.diff(rp))
+            colf = full["col"][a0:a0 + rp[n]]
+            keep = colf > rows
+            b0 = int(got["nnz_off"][i])
+            assert np.array_equal(got["col"][b0:b0 + got["row_ptr"][i][n]], colf[keep])
+            assert np.array_equal(np.diff(got["row_ptr"][i]), np.bincount(rows[keep], minlength=n))
+            if got["w"] is not None:
+                assert np.array_equal(got["w"][b0:b0 + got["row_ptr"][i][n]], full["w"][a0:a0 + rp[n]][keep])
+        back = hostlib.csr_expand_upper(nodes, got["row_ptr"], got["col"], got["nnz_off"], threads=2)
+        for key in ("row_ptr", "col", "w", "nnz_off"):
+            assert np.array_equal(back[key], full[key]), key
+
+
+def test_sample_multiple_compact_output(c1):
+    m, om, c, e = c1
+    q, n = 5, 800
+    s, g, cand = _queries(c, e, q, n, 44)
+    full = m.sample_multiple(s, g, cand, n, CLR, CDC)
+    m.set_tunable(capi.TUNE_PIPE_CHUNK, 2)
+    try:
+        cap = q * n * 13
+        out = dict(nodes=np.empty((q, n, 3)), n_filled=np.empty(q, dtype=np.int32), row_ptr=np.empty((q, n + 1), dtype=np.int32),
+                   col=np.empty(cap, dtype=np.int32), nnz_off=np.empty(q + 1, dtype=np.int64))
+        got = m.sample_multiple(s, g, cand, n, CLR, CDC, out=out, csr_flags=capi.CSR_UPPER | capi.CSR_NO_WEIGHTS)
+    finally:
+        m.set_tunable(capi.TUNE_PIPE_CHUNK, 0)
+    from ctopprm_learn_b200 import hostlib
+    back = hostlib.csr_expand_upper(got["nodes"], got["row_ptr"], got["col"], got["nnz_off"])
+    nnz = int(full["nnz_off"][q])
+    assert np.array_equal(got["nodes"], full["nodes"]) and np.array_equal(back["row_ptr"], full["row_ptr"])
+    assert np.array_equal(back["col"], full["col"][:nnz]) and np.array_equal(back["w"], full["w"][:nnz])
+
+
+def test_ellipsoid_points_draw_for_draw(c1, orc):
+    """a12: the device transform of (u, g) draws against the CPU restatement of random_ellipsoid_point
+    (src/common.cpp:256-312) fed with the very same draws.  The only operations that are not correctly rounded on
+    both sides are cbrt / pow(u, 1/3): tolerance 4 ulp of the largest coordinate scale, stated here."""
+    m, om, c, e = c1
+    s, g = synth.random_queries(c, e, 4, 21)
+    for planar in (False, True):
+        cand, draws = m.sample_ellipsoid_draws(s, g, 3000, 1.2, planar, 99)
+        assert np.array_equal(cand, m.sample_ellipsoid(s, g, 3000, 1.2, planar, 99))
+        assert ((draws[..., 0] > 0) & (draws[..., 0] < 1)).all()
+        for i in range(4):
+            two_major = np.sqrt(((g[i] - s[i]) ** 2).sum()) * 1.2
+            want = np.stack([orc.ellipsoid_point(s[i], g[i], two_major, float(d[0]), d[1:4]) for d in draws[i]])
+            if planar:
+                want[:, 2] = s[i][2]
+            scale = np.abs(want).max()
+            assert np.abs(cand[i] - want).max() <= 4 * np.spacing(scale)
+            assert (cand[i] == want).mean() > 0.5  # most coordinates agree to the last bit
+        # the normal draws really are standard normal, the uniform really uniform
+        assert abs(draws[..., 1:].mean()) < 0.02 and abs(draws[..., 1:].std() - 1) < 0.02
+        assert abs(draws[..., 0].mean() - 0.5) < 0.02
+
+
+def test_two_node_query_consumes_no_candidates(c1):
+    m, om, c, e = c1
+    s, g, cand = _queries(c, e, 2, 50, 12)
+    nodes, n_filled, n_used, _ = m.sample_reject(s, g, cand, CLR, 2)
+    assert (n_filled == 2).all() and (n_used == 0).all()  # the loop of :309 never runs
+    assert np.array_equal(nodes[:, 0], s) and np.array_equal(nodes[:, 1], g)
