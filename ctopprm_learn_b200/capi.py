@@ -83,6 +83,11 @@ _SIGS = {
     "ctp_sample_ellipsoid_draws": [_P, _P, _P, _I64, _I64, _D, _I, C.c_uint64, _P, _P],
     "ctp_sssp": [_P, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "ctp_sssp_dev": [_P, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
+    "ctp_cluster_flood_dev": [_P, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P],
+    "ctp_roadmap_create": [_P, _I64, _I64, _P, _P, _P, _P, _I, _P],
+    "ctp_roadmap_destroy": [_P],
+    "ctp_roadmap_info": [_P, _P],
+    "ctp_cluster_flood": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "ctp_query_paths": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, C.c_int32, _P, _P, _P, _P, _P],
     "ctp_sample_path": [_P, _P, _P, _P, _P, _I64, _P, _P, _P],
     "ctp_deformable": [_P, _P, _P, _P, _I64, _P, _P, _P, _I64, _D, _D, _P],
@@ -468,6 +473,10 @@ class DeviceMap:
         _check(lib().ctp_sssp_dev(self._h, q, n, _ptr(row_ptr), _ptr(col), _ptr(w), _ptr(nnz_off), _ptr(src), ns,
                                   _ptr(dist), _ptr(pred), _ptr(label), _stream_ptr(stream)))
 
+    def roadmap(self, row_ptr, col, w, nnz_off, max_seeds=16):
+        """q CSR roadmaps resident on the device for the floods of the cluster stage"""
+        return Roadmap(self, row_ptr, col, w, nnz_off, max_seeds)
+
     def sample_multiple(self, start, goal, cand, n, clr, cdc, k=13, out=None, csr_flags=0):
         """TopologicalPRMClustering::sampleMultiple from host candidates to host CSR
         (csr_flags: CSR_UPPER / CSR_NO_WEIGHTS select the compact forms of the adjacency)."""
@@ -584,3 +593,55 @@ class DeviceMap:
                       stream=None, csr_flags=0):
         _check(lib().ctp_build_prm_ex_dev(self._h, _ptr(nodes), q, n, k, clr, cdc, csr_flags, _ptr(nbr), _ptr(directed_free),
                                           _ptr(row_ptr), _ptr(col), _ptr(w), cap, _ptr(nnz_off), _stream_ptr(stream)))
+
+
+class Roadmap:
+    """ctp_roadmap: q roadmaps on the device plus the state of their cluster floods (dist / prev / label)."""
+
+    def __init__(self, dmap, row_ptr, col, w, nnz_off, max_seeds=16):
+        row_ptr = _np(row_ptr, np.int32)
+        if row_ptr.ndim == 1:
+            row_ptr = row_ptr[None]
+        self.q, self.n = row_ptr.shape[0], row_ptr.shape[1] - 1
+        self.max_seeds = int(max_seeds)
+        self._map = dmap  # keeps the map handle alive
+        col, w, nnz_off = _np(col, np.int32), _np(w, np.float64), _np(nnz_off, np.int64)
+        h = C.c_void_p()
+        _check(lib().ctp_roadmap_create(dmap._h, self.q, self.n, _ptr(row_ptr), _ptr(col), _ptr(w), _ptr(nnz_off),
+                                        self.max_seeds, C.byref(h)))
+        self._h = h
+        info = np.zeros(4, dtype=np.int64)
+        _check(lib().ctp_roadmap_info(self._h, _ptr(info)))
+        self.rec_cap = int(info[3])
+
+    def flood(self, seeds, mode=0):
+        """one flood (mode 0: all seeds, mode 1: the newest seed on top of the previous state); seeds is a list of
+        per-query seed lists.  -> dist, prev, label (q x n), records [(m_i x 2 nodes, m_i dist, m_i labels)], n_updates (q)"""
+        sd = np.full((self.q, self.max_seeds), -1, dtype=np.int32)
+        ns = np.zeros(self.q, dtype=np.int32)
+        for i, lst in enumerate(seeds):
+            ns[i] = len(lst)
+            sd[i, :len(lst)] = lst
+        dist = np.empty((self.q, self.n))
+        prev = np.empty((self.q, self.n), dtype=np.int32)
+        label = np.empty((self.q, self.n), dtype=np.int32)
+        rn = np.empty((self.q, self.rec_cap, 2), dtype=np.int32)
+        rd = np.empty((self.q, self.rec_cap))
+        rl = np.empty((self.q, self.rec_cap), dtype=np.int32)
+        rc = np.zeros(self.q, dtype=np.int32)
+        upd = np.zeros(self.q, dtype=np.uint64)
+        _check(lib().ctp_cluster_flood(self._h, _ptr(sd), _ptr(ns), mode, _ptr(dist), _ptr(prev), _ptr(label), _ptr(rn),
+                                       _ptr(rl), _ptr(rd), _ptr(rc), _ptr(upd)))
+        recs = [(rn[i, :rc[i]].copy(), rd[i, :rc[i]].copy(), rl[i, :rc[i]].copy()) for i in range(self.q)]
+        return dist, prev, label, recs, upd
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ctp_roadmap_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

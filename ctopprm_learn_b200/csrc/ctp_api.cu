@@ -18,6 +18,7 @@
 #include "ctp_edt.cuh"
 #include "ctp_paths.cuh"
 #include "ctp_prm.cuh"
+#include "ctp_cluster.cuh"
 
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -1430,9 +1431,18 @@ extern "C" int ctp_csr_from_directed(ctp_map *m, const double *nodes, int64_t q,
 }
 
 // ----------------------------- shortest paths over the CSR roadmaps ---------------------------
+static int sssp_launch(ctp_map *m, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col, const double *w,
+                       const int64_t *nnz_off, const int32_t *src, int ns, double *dist, int32_t *pred, int32_t *label,
+                       const double *dist_init, void *stream);
 extern "C" int ctp_sssp_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col, const double *w,
                             const int64_t *nnz_off, const int32_t *src, int ns, double *dist, int32_t *pred,
                             int32_t *label, void *stream) {
+  return sssp_launch(m, q, n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label, nullptr, stream);
+}
+// dist_init (optional, q x n): upper bounds the search starts from instead of +inf
+static int sssp_launch(ctp_map *m, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col, const double *w,
+                       const int64_t *nnz_off, const int32_t *src, int ns, double *dist, int32_t *pred, int32_t *label,
+                       const double *dist_init, void *stream) {
   REQUIRE(m && q >= 1 && n >= 1 && ns >= 1 && ns <= CTP_SSSP_THREADS, "bad argument (1 <= sources per query <= 1024)");
   REQUIRE(row_ptr && col && w && nnz_off && src && dist && pred, "null buffer");
   REQUIRE(n < ((int64_t)1 << 31), "n must fit in int32");
@@ -1480,9 +1490,9 @@ extern "C" int ctp_sssp_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row
     cfg.numAttrs = 1;
     cudaError_t e = CL == CTP_SSSP_CL_BIG
                         ? cudaLaunchKernelEx(&cfg, k_sssp_cluster<CTP_SSSP_CL_BIG>, n, slice, cap_e, row_ptr, col, w, nnz_off, src,
-                                             ns, dist, pred)
+                                             ns, dist, pred, dist_init)
                         : cudaLaunchKernelEx(&cfg, k_sssp_cluster<CTP_SSSP_CL>, n, slice, cap_e, row_ptr, col, w, nnz_off, src, ns,
-                                             dist, pred);
+                                             dist, pred, dist_init);
     if (e != cudaSuccess) cudaGetLastError();  // forget it: the caller falls back
     return e == cudaSuccess;
   };
@@ -1504,10 +1514,10 @@ extern "C" int ctp_sssp_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row
       m->sssp_cluster = 0;  // the launch itself failed: use the one-CTA kernels from now on
   }
   if (m->sssp_frontier && fits_one) {
-    k_sssp_frontier<<<(unsigned)q, CTP_SSSP_THREADS, smem_f, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label);
+    k_sssp_frontier<<<(unsigned)q, CTP_SSSP_THREADS, smem_f, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label, dist_init);
   } else if (smem <= (size_t)smem_optin) {
     k_sssp<true><<<(unsigned)q, CTP_SSSP_THREADS, smem, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label,
-                                                              nullptr, nullptr);
+                                                              nullptr, nullptr, dist_init);
   } else {  // distances do not fit in shared memory: same algorithm on a global (L2-resident) array
     const size_t keep = m->ws.used;
     CKR(arena_reserve(m->ws, keep + align_up((size_t)q * n * 8) + align_up((size_t)q * n) + 1024));
@@ -1515,7 +1525,7 @@ extern "C" int ctp_sssp_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row
     uint8_t *g_chg = arena_take<uint8_t>(m->ws, (size_t)q * n);
     m->ws.used = keep;
     k_sssp<false><<<(unsigned)q, CTP_SSSP_THREADS, 0, st>>>(n, row_ptr, col, w, nnz_off, src, ns, dist, pred, label, g_dist,
-                                                            g_chg);
+                                                            g_chg, dist_init);
   }
   m->launches++;
   CK(cudaGetLastError());
@@ -1553,6 +1563,214 @@ extern "C" int ctp_sssp(ctp_map *m, int64_t q, int64_t n, const int32_t *row_ptr
   CK(cudaMemcpyAsync(pred, d_pred, q * n * 4, cudaMemcpyDeviceToHost, 0));
   if (label) CK(cudaMemcpyAsync(label, d_label, q * n * 4, cudaMemcpyDeviceToHost, 0));
   CK(cudaStreamSynchronize(0));
+  return CTP_OK;
+}
+
+// ----------------------------- the floods of the cluster stage --------------------------------
+// One flood for q roadmaps: shortest-path launch (all seeds, or the newest seed on top of the distances of the
+// previous floods), then predecessors / labels / update counts and the inter-cluster connection records that the
+// sequential loop of the reference would have produced (ctp_cluster.cuh).
+extern "C" int ctp_cluster_flood_dev(ctp_map *m, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col,
+                                     const double *w, const int64_t *nnz_off, const int32_t *seeds, int max_seeds,
+                                     const int32_t *n_seeds, int mode, double *dist, int32_t *prev, int32_t *label,
+                                     int64_t rec_cap, int32_t *rec_nodes, int32_t *rec_label, double *rec_dist,
+                                     int32_t *rec_count, uint64_t *n_updates, void *stream) {
+  REQUIRE(m && q >= 1 && n >= 1 && max_seeds >= 1 && max_seeds <= CTP_SSSP_THREADS, "bad argument (1 <= max_seeds <= 1024)");
+  REQUIRE(mode == 0 || mode == 1, "mode must be 0 (flood from all seeds) or 1 (re-flood from the newest seed)");
+  REQUIRE(row_ptr && col && w && nnz_off && seeds && n_seeds && dist && prev && label && rec_count && n_updates, "null buffer");
+  REQUIRE(rec_cap >= 0 && rec_cap < ((int64_t)1 << 31) && (rec_cap == 0 || (rec_nodes && rec_label && rec_dist)), "bad record capacity");
+  REQUIRE(n < ((int64_t)1 << 31), "n must fit in int32");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = q * n;
+  const size_t keep = m->ws.used;
+  // (the shortest-path launch may take total * 9 bytes more for its global-array variant: reserved here, so that the
+  // arena cannot move under the buffers taken below)
+  CKR(arena_reserve(m->ws, keep + 2 * align_up(total * 8) + 3 * align_up(total * 4) + align_up(q * max_seeds * 4) + 8192));
+  double *d_new = arena_take<double>(m->ws, total);
+  int32_t *d_pred = arena_take<int32_t>(m->ws, total);
+  int32_t *d_lnew = arena_take<int32_t>(m->ws, total);
+  int32_t *d_src = arena_take<int32_t>(m->ws, q * max_seeds);
+  const int tb = 256;
+  const unsigned gb = (unsigned)((total + tb - 1) / tb);
+  CK(cudaMemsetAsync(rec_count, 0, q * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(n_updates, 0, q * sizeof(uint64_t), st));
+  k_cluster_sources<<<(unsigned)((q * max_seeds + tb - 1) / tb), tb, 0, st>>>(q, seeds, max_seeds, n_seeds, mode, d_src);
+  m->launches++;
+  int rc = sssp_launch(m, q, n, row_ptr, col, w, nnz_off, d_src, max_seeds, d_new, d_pred, nullptr, mode == 1 ? dist : nullptr, st);
+  if (rc != CTP_OK) {
+    m->ws.used = keep;
+    return rc;
+  }
+  if (mode == 1) CK(cudaMemcpyAsync(d_lnew, label, total * 4, cudaMemcpyDeviceToDevice, st));
+  int32_t *lab_w = mode == 1 ? d_lnew : label;
+  k_cluster_prev<<<gb, tb, 0, st>>>(q, n, row_ptr, col, w, nnz_off, seeds, max_seeds, n_seeds, mode, dist, d_new, prev, lab_w,
+                                    (unsigned long long *)n_updates);
+  if (mode == 0) k_cluster_label<<<gb, tb, 0, st>>>(q, n, n_seeds, prev, d_new, label);
+  k_cluster_records<<<gb, tb, 0, st>>>(q, n, row_ptr, col, w, nnz_off, seeds, max_seeds, n_seeds, mode, dist, label, d_new, lab_w,
+                                       prev, (int)rec_cap, rec_nodes, rec_label, rec_dist, rec_count);
+  k_cluster_commit<<<gb, tb, 0, st>>>(total, n, n_seeds, d_new, mode == 1 ? d_lnew : nullptr, dist, label);
+  m->launches += mode == 0 ? 4 : 3;
+  m->ws.used = keep;
+  CK(cudaGetLastError());
+  return CTP_OK;
+}
+
+// q roadmaps resident on the device together with the state of their floods (distance to the nearest seed, predecessor,
+// cluster label): what clusterGraph keeps in its HeapNodes between wavefrontFill and the addCentroid calls
+struct ctp_roadmap {
+  ctp_map *m = nullptr;
+  int64_t q = 0, n = 0, nnz = 0, rec_cap = 0;
+  int max_seeds = 0;
+  int32_t *d_rp = nullptr, *d_col = nullptr, *d_prev = nullptr, *d_label = nullptr, *d_seeds = nullptr, *d_ns = nullptr;
+  int32_t *d_rec_nodes = nullptr, *d_rec_label = nullptr, *d_rec_count = nullptr;
+  double *d_w = nullptr, *d_dist = nullptr, *d_rec_dist = nullptr;
+  int64_t *d_off = nullptr;
+  uint64_t *d_upd = nullptr;
+  std::vector<int64_t> h_off;
+};
+
+extern "C" int ctp_roadmap_destroy(ctp_roadmap *r) {
+  if (!r) return CTP_OK;
+  if (r->m) cudaSetDevice(r->m->device);
+  void *ptrs[] = {r->d_rp, r->d_col, r->d_prev, r->d_label, r->d_seeds, r->d_ns, r->d_rec_nodes, r->d_rec_label, r->d_rec_count,
+                  r->d_w,  r->d_dist, r->d_rec_dist, r->d_off, r->d_upd};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  delete r;
+  return CTP_OK;
+}
+
+extern "C" int ctp_roadmap_create(ctp_map *m, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col,
+                                  const double *w, const int64_t *nnz_off, int max_seeds, ctp_roadmap **out) {
+  REQUIRE(m && out && q >= 1 && n >= 1 && max_seeds >= 1 && max_seeds <= CTP_SSSP_THREADS, "bad argument (1 <= max_seeds <= 1024)");
+  REQUIRE(row_ptr && col && w && nnz_off, "null buffer");
+  REQUIRE(n < ((int64_t)1 << 31), "n must fit in int32");
+  const int64_t nnz = nnz_off[q];
+  REQUIRE(nnz >= 0 && nnz_off[0] == 0, "nnz_off must start at 0");
+  int64_t widest = 0;
+  for (int64_t i = 0; i < q; i++) {
+    REQUIRE(nnz_off[i + 1] >= nnz_off[i], "nnz_off must not decrease");
+    REQUIRE(row_ptr[i * (n + 1)] == 0 && row_ptr[i * (n + 1) + n] == nnz_off[i + 1] - nnz_off[i], "row_ptr does not match nnz_off");
+    widest = std::max(widest, nnz_off[i + 1] - nnz_off[i]);
+  }
+  for (int64_t i = 0; i < nnz; i++) REQUIRE(col[i] >= 0 && col[i] < n, "column index out of range");
+  CK(cudaSetDevice(m->device));
+  ctp_roadmap *r = new (std::nothrow) ctp_roadmap();
+  if (!r) return fail(CTP_ERR_NOMEM, "out of host memory");
+  r->m = m;
+  r->q = q;
+  r->n = n;
+  r->nnz = nnz;
+  r->max_seeds = max_seeds;
+  r->rec_cap = std::max<int64_t>(widest, 1);  // a record per directed edge at most
+  r->h_off.assign(nnz_off, nnz_off + q + 1);
+  auto alloc = [&](auto **p, size_t bytes) { return cudaMalloc((void **)p, bytes ? bytes : 1); };
+  cudaError_t e = cudaSuccess;
+  auto take = [&](auto **p, size_t bytes) {
+    if (e == cudaSuccess) e = alloc(p, bytes);
+  };
+  take(&r->d_rp, q * (n + 1) * 4);
+  take(&r->d_col, nnz * 4 + 4);
+  take(&r->d_w, nnz * 8 + 8);
+  take(&r->d_off, (q + 1) * 8);
+  take(&r->d_dist, q * n * 8);
+  take(&r->d_prev, q * n * 4);
+  take(&r->d_label, q * n * 4);
+  take(&r->d_seeds, q * max_seeds * 4);
+  take(&r->d_ns, q * 4);
+  take(&r->d_rec_nodes, q * r->rec_cap * 8);
+  take(&r->d_rec_label, q * r->rec_cap * 4);
+  take(&r->d_rec_dist, q * r->rec_cap * 8);
+  take(&r->d_rec_count, q * 4);
+  take(&r->d_upd, q * 8);
+  if (e != cudaSuccess) {
+    ctp_roadmap_destroy(r);
+    return fail(e == cudaErrorMemoryAllocation ? CTP_ERR_NOMEM : CTP_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  int rc = CTP_OK;
+  auto up = [&](void *d, const void *h, size_t bytes) {
+    if (rc == CTP_OK && bytes && cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, 0) != cudaSuccess)
+      rc = fail(CTP_ERR_CUDA, "host -> device copy of the roadmap failed");
+  };
+  up(r->d_rp, row_ptr, q * (n + 1) * 4);
+  up(r->d_col, col, nnz * 4);
+  up(r->d_w, w, nnz * 8);
+  up(r->d_off, nnz_off, (q + 1) * 8);
+  if (rc == CTP_OK && cudaStreamSynchronize(0) != cudaSuccess) rc = fail(CTP_ERR_CUDA, "roadmap upload failed");
+  if (rc != CTP_OK) {
+    ctp_roadmap_destroy(r);
+    return rc;
+  }
+  *out = r;
+  return CTP_OK;
+}
+
+// Host form: seeds in, the whole state and the records out.  The records of each query come back in the order the
+// sequential loop appends them: ascending (distance of the expanding node, its id), neighbours ascending.
+extern "C" int ctp_cluster_flood(ctp_roadmap *r, const int32_t *seeds, const int32_t *n_seeds, int mode, double *dist,
+                                 int32_t *prev, int32_t *label, int32_t *rec_nodes, int32_t *rec_label, double *rec_dist,
+                                 int32_t *rec_count, uint64_t *n_updates) {
+  REQUIRE(r && seeds && n_seeds && dist && prev && label && rec_nodes && rec_label && rec_dist && rec_count && n_updates,
+          "null argument");
+  ctp_map *m = r->m;
+  const int64_t q = r->q, n = r->n;
+  for (int64_t i = 0; i < q; i++) {
+    REQUIRE(n_seeds[i] >= 0 && n_seeds[i] <= r->max_seeds, "n_seeds out of range");
+    for (int s = 0; s < n_seeds[i]; s++)
+      REQUIRE(seeds[i * r->max_seeds + s] >= 0 && seeds[i * r->max_seeds + s] < n, "seed id out of range");
+  }
+  CK(cudaSetDevice(m->device));
+  CK(cudaMemcpyAsync(r->d_seeds, seeds, q * r->max_seeds * 4, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(r->d_ns, n_seeds, q * 4, cudaMemcpyHostToDevice, 0));
+  m->ws.used = 0;
+  CKR(ctp_cluster_flood_dev(m, q, n, r->d_rp, r->d_col, r->d_w, r->d_off, r->d_seeds, r->max_seeds, r->d_ns, mode, r->d_dist,
+                            r->d_prev, r->d_label, r->rec_cap, r->d_rec_nodes, r->d_rec_label, r->d_rec_dist, r->d_rec_count, r->d_upd, 0));
+  CK(cudaMemcpyAsync(dist, r->d_dist, q * n * 8, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(prev, r->d_prev, q * n * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(label, r->d_label, q * n * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(rec_count, r->d_rec_count, q * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(n_updates, r->d_upd, q * 8, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  std::vector<int32_t> tmp_nodes, tmp_label, order;
+  std::vector<double> tmp_dist;
+  for (int64_t i = 0; i < q; i++) {
+    const int64_t c = rec_count[i];
+    if (c > r->rec_cap) return fail(CTP_ERR_CAPACITY, "more connection records than directed edges (internal error)");
+    if (c == 0) continue;
+    tmp_nodes.resize(2 * c);
+    tmp_dist.resize(c);
+    tmp_label.resize(c);
+    CK(cudaMemcpyAsync(tmp_label.data(), r->d_rec_label + i * r->rec_cap, c * 4, cudaMemcpyDeviceToHost, 0));
+    CK(cudaMemcpyAsync(tmp_nodes.data(), r->d_rec_nodes + 2 * i * r->rec_cap, c * 8, cudaMemcpyDeviceToHost, 0));
+    CK(cudaMemcpyAsync(tmp_dist.data(), r->d_rec_dist + i * r->rec_cap, c * 8, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    order.resize(c);
+    for (int64_t t = 0; t < c; t++) order[t] = (int32_t)t;
+    const double *dq = dist + i * n;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      const int ea = tmp_nodes[2 * a], eb = tmp_nodes[2 * b];
+      if (ea != eb) return dq[ea] < dq[eb] || (dq[ea] == dq[eb] && ea < eb);
+      return tmp_nodes[2 * a + 1] < tmp_nodes[2 * b + 1];
+    });
+    int32_t *on = rec_nodes + 2 * i * r->rec_cap;
+    double *od = rec_dist + i * r->rec_cap;
+    int32_t *ol = rec_label + i * r->rec_cap;
+    for (int64_t t = 0; t < c; t++) {
+      ol[t] = tmp_label[order[t]];
+      on[2 * t] = tmp_nodes[2 * order[t]];
+      on[2 * t + 1] = tmp_nodes[2 * order[t] + 1];
+      od[t] = tmp_dist[order[t]];
+    }
+  }
+  return CTP_OK;
+}
+extern "C" int ctp_roadmap_info(const ctp_roadmap *r, int64_t info[4]) {
+  REQUIRE(r && info, "null argument");
+  info[0] = r->q;
+  info[1] = r->n;
+  info[2] = r->nnz;
+  info[3] = r->rec_cap;
   return CTP_OK;
 }
 

@@ -96,7 +96,8 @@ __device__ __forceinline__ int sssp_block_scan_excl(int v, int *s_warp, int &tot
 __global__ void __launch_bounds__(CTP_SSSP_THREADS)
 k_sssp_frontier(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                 const double *__restrict__ w, const int64_t *__restrict__ nnz_off, const int32_t *__restrict__ src, int ns,
-                double *__restrict__ dist_out, int32_t *__restrict__ pred_out, int32_t *__restrict__ label_out) {
+                double *__restrict__ dist_out, int32_t *__restrict__ pred_out, int32_t *__restrict__ label_out,
+                const double *__restrict__ dist_init) {
   extern __shared__ unsigned long long s_mem[];
   __shared__ int s_warp[32];
   __shared__ int s_off[CTP_SSSP_TILE + 1];
@@ -110,7 +111,10 @@ k_sssp_frontier(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *_
   unsigned long long *dist = s_mem;
   unsigned *bits = reinterpret_cast<unsigned *>(s_mem + nn);
   uint16_t *queue = reinterpret_cast<uint16_t *>(bits + words);
-  for (int u = threadIdx.x; u < nn; u += blockDim.x) dist[u] = CTP_SSSP_INF;
+  // dist_init (optional): upper bounds the search starts from instead of +inf (the re-flood of addCentroid,
+  // include/topological_prm_clustering.hpp:1315-1331, only ever lowers the distances of the previous flood)
+  for (int u = threadIdx.x; u < nn; u += blockDim.x)
+    dist[u] = dist_init ? (unsigned long long)__double_as_longlong(dist_init[q * n + u]) : CTP_SSSP_INF;
   for (int t = threadIdx.x; t < words; t += blockDim.x) bits[t] = 0;
   __syncthreads();
   if (threadIdx.x < ns) {
@@ -239,7 +243,7 @@ template <int CL>
 __global__ void __launch_bounds__(CTP_SSSP_CL_THREADS)
 k_sssp_cluster(int64_t n, int slice, int cap_e, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                const double *__restrict__ w, const int64_t *__restrict__ nnz_off, const int32_t *__restrict__ src, int ns,
-               double *__restrict__ dist_out, int32_t *__restrict__ pred_out) {
+               double *__restrict__ dist_out, int32_t *__restrict__ pred_out, const double *__restrict__ dist_init) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ unsigned long long s_mem[];
@@ -263,7 +267,8 @@ k_sssp_cluster(int64_t n, int slice, int cap_e, const int32_t *__restrict__ row_
   unsigned *bits1 = bits0 + words;
   int32_t *s_rp = reinterpret_cast<int32_t *>(bits1 + words);
   int32_t *s_col = s_rp + slice + 1;
-  for (int u = threadIdx.x; u < slice; u += blockDim.x) dist[u] = CTP_SSSP_INF;
+  for (int u = threadIdx.x; u < slice; u += blockDim.x)
+    dist[u] = (dist_init && u < mine) ? (unsigned long long)__double_as_longlong(dist_init[q * n + lo + u]) : CTP_SSSP_INF;
   for (int t = threadIdx.x; t < 2 * words; t += blockDim.x) bits0[t] = 0;
   if (threadIdx.x < 3) s_work[threadIdx.x] = 0;
   // stage the rows this CTA owns
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(CTP_SSSP_THREADS)
 k_sssp(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const double *__restrict__ w,
        const int64_t *__restrict__ nnz_off, const int32_t *__restrict__ src, int ns, double *__restrict__ dist_out,
        int32_t *__restrict__ pred_out, int32_t *__restrict__ label_out, unsigned long long *__restrict__ g_dist,
-       uint8_t *__restrict__ g_chg) {
+       uint8_t *__restrict__ g_chg, const double *__restrict__ dist_init) {
   extern __shared__ unsigned long long s_mem[];
   const int64_t q = blockIdx.x;
   const int32_t *rp = row_ptr + q * (n + 1);
@@ -369,7 +374,7 @@ k_sssp(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict
   unsigned long long *dist = SMEM ? s_mem : g_dist + q * n;
   uint8_t *chg = SMEM ? reinterpret_cast<uint8_t *>(s_mem + n) : g_chg + q * n;
   for (int u = threadIdx.x; u < n; u += blockDim.x) {
-    dist[u] = CTP_SSSP_INF;
+    dist[u] = dist_init ? (unsigned long long)__double_as_longlong(dist_init[q * n + u]) : CTP_SSSP_INF;
     chg[u] = 0;
   }
   __syncthreads();

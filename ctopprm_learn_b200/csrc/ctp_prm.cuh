@@ -1088,15 +1088,35 @@ k_csr_emit(const double *__restrict__ nodes, const int32_t *__restrict__ rec, co
     }
   __syncthreads();
   const int total = s_loff[CTP_CSR_EMIT_ROWS];
-  for (int x = t; x < total; x += CTP_CSR_EMIT_ROWS) {
-    const int ow = s_own[x];
-    const unsigned c = s_col[x];
-    const int64_t pos = s_gbeg[ow] + (x - s_loff[ow]);
-    const double *o = nodes + 3 * (s_qbase[ow] + (int64_t)c);
-    const double dx = o[0] - s_node[ow][0], dy = o[1] - s_node[ow][1], dz = o[2] - s_node[ow][2];
-    if (pos < cap) {
-      col[pos] = (int32_t)c;
-      if (w) w[pos] = sqrt((dx * dx + dy * dy) + dz * dz);
+  // four entries per thread and step: their neighbour gathers (the only scattered loads of the kernel) are issued
+  // together, the FP64 norms follow
+  for (int x0 = t; x0 < total; x0 += 4 * CTP_CSR_EMIT_ROWS) {
+    int ow[4];
+    unsigned c[4];
+    double ox[4], oy[4], oz[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int x = x0 + u * CTP_CSR_EMIT_ROWS;
+      const bool in = x < total;
+      ow[u] = in ? s_own[x] : 0;
+      c[u] = in ? s_col[x] : 0u;
+      const double *o = nodes + 3 * (s_qbase[ow[u]] + (int64_t)c[u]);
+      ox[u] = in ? o[0] : 0.0;
+      oy[u] = in ? o[1] : 0.0;
+      oz[u] = in ? o[2] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int x = x0 + u * CTP_CSR_EMIT_ROWS;
+      if (x >= total) continue;
+      const int64_t pos = s_gbeg[ow[u]] + (x - s_loff[ow[u]]);
+      if (pos < cap) {
+        col[pos] = (int32_t)c[u];
+        if (w) {
+          const double dx = ox[u] - s_node[ow[u]][0], dy = oy[u] - s_node[ow[u]][1], dz = oz[u] - s_node[ow[u]][2];
+          w[pos] = sqrt((dx * dx + dy * dy) + dz * dz);
+        }
+      }
     }
   }
 }

@@ -242,16 +242,58 @@ int ctph_remove_too_long(const double *lens, int P, int32_t *keep) {
   for (size_t i = 0; i < out.size(); i++) keep[i] = out[i].from_id;
   return (int)out.size();
 }
-// whole entry point; returns number of paths for the single start-goal pair, lengths in `lengths`
+// clusterGraph on a planner whose roadmap exists: stitched cluster paths (points back to back, offsets, DFS lengths), the
+// final seeds and labels, stats = {seeds, floods, refloods, capped_refloods, homotopy_checks}.  Returns the number of
+// paths, -1 when a capacity is too small.
+int ctph_planner_cluster_graph(void *p, double max_path_length, const int32_t *seed_candidates, int n_cand, int cap_paths,
+                               int cap_pts, double *out_pts, int32_t *out_off, double *out_len, int32_t *seeds_out,
+                               int32_t *nseeds_out, int32_t *labels_out, int32_t *stats_out) {
+  PL(p)->setMaxPathLength(max_path_length);
+  PL(p)->setSeedCandidates(std::vector<int>(seed_candidates, seed_candidates + n_cand));
+  std::vector<Path> r = PL(p)->clusterGraph();
+  int tot = 0;
+  out_off[0] = 0;
+  for (size_t i = 0; i < r.size(); i++) {
+    if ((int)i >= cap_paths || tot + (int)r[i].plan.size() > cap_pts) return -1;
+    for (auto *nd : r[i].plan) put(nd->data, out_pts + 3 * (size_t)tot++);
+    out_off[i + 1] = tot;
+    out_len[i] = r[i].length;
+  }
+  const auto &sd = PL(p)->clusterSeeds();
+  for (size_t i = 0; i < sd.size(); i++) seeds_out[i] = sd[i];
+  *nseeds_out = (int32_t)sd.size();
+  const auto &lb = PL(p)->clusterLabels();
+  for (size_t i = 0; i < lb.size(); i++) labels_out[i] = lb[i];
+  const auto &st = PL(p)->clusterStats();
+  const int32_t sv[5] = {st.seeds, st.floods, st.refloods, st.capped_refloods, st.homotopy_checks};
+  memcpy(stats_out, sv, sizeof sv);
+  return (int)r.size();
+}
+// whole entry point for the single start-goal pair; cand (optional, m x 3): the candidate stream of sampleMultiple.
+// Paths come back sorted by length: points back to back (out_pts, cap_pts points), offsets (cap_paths + 1), lengths.
+// Returns the number of paths (-1: capacity).
 int ctph_find_geometrical_paths(void *map, const char *yaml_text, const double *start, const double *goal,
-                                const char *output_folder, double *lengths, int cap) {
+                                const char *output_folder, const double *cand, int64_t m, int cap_paths, int cap_pts,
+                                double *out_pts, int32_t *out_off, double *lengths) {
   YAML::Node cfg = YAML::Load(std::string(yaml_text));
   std::vector<V3> gates = {V(start), V(goal)};
+  Planner::gate_candidate_streams.clear();
+  if (cand && m > 0) {
+    std::vector<V3> c((size_t)m);
+    memcpy(c[0].data(), cand, (size_t)m * 24);
+    Planner::gate_candidate_streams.push_back(c);
+  }
   auto r = Planner::find_geometrical_paths(cfg, MAP(map), gates, output_folder);
+  Planner::gate_candidate_streams.clear();
   if (r.empty()) return 0;
-  int c = 0;
-  for (auto &p : r[0])
-    if (c < cap) lengths[c++] = p.length;
+  int tot = 0;
+  out_off[0] = 0;
+  for (size_t i = 0; i < r[0].size(); i++) {
+    if ((int)i >= cap_paths || tot + (int)r[0][i].plan.size() > cap_pts) return -1;
+    for (auto *nd : r[0][i].plan) put(nd->data, out_pts + 3 * (size_t)tot++);
+    out_off[i + 1] = tot;
+    lengths[i] = r[0][i].length;
+  }
   return (int)r[0].size();
 }
 }

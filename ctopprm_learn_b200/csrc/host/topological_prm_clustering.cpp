@@ -18,9 +18,10 @@ template <> double Planner::min_clearance_ = 0;
 template <> double Planner::cutoof_distance_ratio_to_shortest_ = 0;
 template <> double Planner::min_allowed = 0;
 template <> uint64_t Planner::sampling_seed = 1;
+template <> std::vector<std::vector<V3>> Planner::gate_candidate_streams = {};
 template <>
 std::function<std::vector<Path>(Planner &, const Path &)> Planner::cluster_stage =
-    [](Planner &, const Path &shortest) { return std::vector<Path>{shortest}; };
+    [](Planner &prm, const Path &) { return prm.clusterGraph(); };
 
 namespace {
 [[noreturn]] void die(const char *what) {
@@ -114,14 +115,22 @@ template <> void Planner::sampleMultiple(const int num_samples) {
     nodes_[i] = new Node(V3(nodes[3 * (size_t)i], nodes[3 * (size_t)i + 1], nodes[3 * (size_t)i + 2]));
     nodes_[i]->id = i;
   }
-  for (int i = 0; i < n; i++) {
-    auto &adj = nodes_[i]->visibility_node_ids;
-    adj.reserve((size_t)(row_ptr[i + 1] - row_ptr[i]));  // one bucket array per node, no rehash
-    for (int32_t e = row_ptr[i]; e < row_ptr[i + 1]; e++) adj[nodes_[col[e]]] = w[e];
-  }
   csr_row_ptr_ = row_ptr;
   csr_col_.assign(col.begin(), col.begin() + nnz_off[1]);
   csr_w_.assign(w.begin(), w.begin() + nnz_off[1]);
+  adjacency_ready_ = false;  // visibility_node_ids are filled on first use (nodes(), saveRoadmapDense)
+}
+
+// CSR -> visibility_node_ids of every node (the pointer graph of the reference, :374-385)
+template <> void Planner::materializeAdjacency() {
+  if (adjacency_ready_) return;
+  adjacency_ready_ = true;
+  const int n = (int)nodes_.size();
+  for (int i = 0; i < n; i++) {
+    auto &adj = nodes_[i]->visibility_node_ids;
+    adj.reserve(adj.size() + (size_t)(csr_row_ptr_[i + 1] - csr_row_ptr_[i]));  // one bucket array per node, no rehash
+    for (int32_t e = csr_row_ptr_[i]; e < csr_row_ptr_[i + 1]; e++) adj[nodes_[csr_col_[e]]] = csr_w_[e];
+  }
 }
 
 // findShortestPath (:2172) = dijkstra.findPath(0, {1}, nodes_): on the device over the CSR the PRM build
@@ -340,6 +349,7 @@ std::vector<uint8_t> Planner::isNewHomotopyClassBatch(const std::vector<Path> &m
 template <> bool Planner::isNewSeedAccepted(Node *candidate, const std::vector<Node *> &seeds) {
   // sequential form (:1861-1882): stop at the first seed that is a roadmap neighbour or visible; here all
   // segment checks go out in one batch and the same decision is read off the verdicts
+  materializeAdjacency();
   std::vector<V3> a, b;
   for (Node *sd : seeds) {
     if (sd->visibility_node_ids.count(candidate) > 0) return false;
@@ -359,6 +369,7 @@ template <> bool Planner::isNewSeedAccepted(Node *candidate, const std::vector<N
 // ---- CSV writers: node rows "x,y,z", edge rows "x0,y0,z0,x1,y1,z1" (:2066-2150; consumer
 // columns_2(...).py:20-33 tells them apart by column count).  Default ostream precision.
 template <> void Planner::saveRoadmapDense(std::string filename) {
+  materializeAdjacency();
   std::ofstream f(filename);
   if (!f.is_open()) return;
   for (auto *n : nodes_) f << n->data(0) << "," << n->data(1) << "," << n->data(2) << std::endl;
@@ -411,6 +422,7 @@ std::vector<std::vector<Path>> Planner::find_geometrical_paths(const YAML::Node 
   for (size_t i = 0; i + 1 < gates.size(); i++) {
     Planner prm(planner_config, map, output_folder, gates[i], gates[i + 1]);
     prm.setBorders(map->getMinPos(), map->getMaxPos());
+    if (i < gate_candidate_streams.size() && !gate_candidate_streams[i].empty()) prm.setCandidateStream(gate_candidate_streams[i]);
     auto t0 = now();
     prm.sampleMultiple(num_samples_between_gate);
     auto t1 = now();
@@ -421,7 +433,7 @@ std::vector<std::vector<Path>> Planner::find_geometrical_paths(const YAML::Node 
     if (shortest.empty() || shortest[0].plan.empty()) return paths_between_gates;  // :2569-2572
     prm.max_path_length_ = shortest[0].length * prm.max_path_length_ratio_;
     std::vector<Path> found = cluster_stage(prm, shortest[0]);
-    prm.saveRoadmapDense(output_folder + "roadmap_all" + std::to_string(i) + ".csv");
+    if (!output_folder.empty()) prm.saveRoadmapFromCSR(output_folder + "roadmap_all" + std::to_string(i) + ".csv");
     INFO_GREEN("algorithm time clustering " << ms(t0, now()) << " ms");
     auto both_ways = [](std::vector<Path> in) {  // shorten_path(false) then shorten_path(true) (:2612-2625)
       return shorten_paths(shorten_paths(in, false), true);

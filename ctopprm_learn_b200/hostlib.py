@@ -157,11 +157,22 @@ class HostMap:
                                                 count, _p(out))
         return out
 
-    def find_geometrical_paths(self, yaml_text, start, goal, out_dir, cap=64):
+    def find_geometrical_paths(self, yaml_text, start, goal, out_dir, cap=64, cand=None, cap_pts=1 << 16, want_paths=False):
+        """TopologicalPRMClustering::find_geometrical_paths for one start-goal pair (out_dir "" = no CSV files);
+        cand = the candidate stream of sampleMultiple (else drawn on the device).  -> lengths[, paths]"""
         s, g = _f(start), _f(goal)
         lens = np.empty(cap)
-        n = lib().ctph_find_geometrical_paths(self.h, yaml_text.encode(), _p(s), _p(g), out_dir.encode(), _p(lens), cap)
-        return lens[:min(n, cap)]
+        pts = np.empty((cap_pts, 3))
+        off = np.zeros(cap + 1, dtype=np.int32)
+        c = None if cand is None else _f(cand).reshape(-1, 3)
+        n = lib().ctph_find_geometrical_paths(self.h, yaml_text.encode(), _p(s), _p(g), out_dir.encode(),
+                                              None if c is None else _p(c), C.c_int64(0 if c is None else len(c)), cap,
+                                              cap_pts, _p(pts), _p(off), _p(lens))
+        if n < 0:
+            raise RuntimeError("find_geometrical_paths: output capacity too small")
+        if want_paths:
+            return lens[:n].copy(), [pts[off[i]:off[i + 1]].copy() for i in range(n)]
+        return lens[:n].copy()
 
 
 class HostPlanner:
@@ -208,6 +219,24 @@ class HostPlanner:
         cluster = np.empty(self.n, dtype=np.int32)
         lib().ctph_planner_flood(self.h, _p(seeds), len(seeds), _p(dist), _p(pred), _p(cluster))
         return dist, pred, cluster
+
+    def cluster_graph(self, max_path_length, seed_candidates=(), cap_paths=4096, cap_pts=1 << 20):
+        """clusterGraph (:1832-1952) -> (paths, DFS lengths, seeds, labels, stats)"""
+        sc = np.ascontiguousarray(seed_candidates, dtype=np.int32)
+        pts = np.empty((cap_pts, 3))
+        off = np.zeros(cap_paths + 1, dtype=np.int32)
+        lens = np.empty(cap_paths)
+        seeds = np.full(1024, -1, dtype=np.int32)
+        ns = C.c_int32(0)
+        labels = np.empty(self.n, dtype=np.int32)
+        stats = np.zeros(5, dtype=np.int32)
+        k = lib().ctph_planner_cluster_graph(self.h, C.c_double(max_path_length), _p(sc), len(sc), cap_paths, cap_pts, _p(pts),
+                                             _p(off), _p(lens), _p(seeds), C.byref(ns), _p(labels), _p(stats))
+        if k < 0:
+            raise RuntimeError("cluster_graph: output capacity too small")
+        names = ("seeds", "floods", "refloods", "capped_refloods", "homotopy_checks")
+        return ([pts[off[i]:off[i + 1]].copy() for i in range(k)], lens[:k].copy(), seeds[:ns.value].copy(), labels,
+                dict(zip(names, (int(v) for v in stats))))
 
     def seed_accepted(self, candidate_id, seed_ids):
         seed_ids = np.ascontiguousarray(seed_ids, dtype=np.int32)

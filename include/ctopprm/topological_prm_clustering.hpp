@@ -2,11 +2,11 @@
 // TopologicalPRMClustering<T> (include/topological_prm_clustering.hpp) behind the same method
 // names: sampleMultiple (:288-401), findShortestPath (:2172), shorten_path (:2313-2479),
 // removeTooLongPaths (:2193-2222), removeEquivalentPaths (:2237-2298), the roadmap CSV writers
-// (:2066-2150) and the static entry point find_geometrical_paths (:2489-2684).  The cluster stage
-// between Dijkstra and shortening (clusterGraph, wavefrontFill, addCentroid, cluster DFS -- host
-// glue) is not re-implemented here: find_geometrical_paths calls the hook
-// `cluster_stage` where the reference calls clusterGraph() (:2591); by default the hook returns the
-// shortest path only.  INTEGRATION.md shows how the reference's own clusterGraph plugs in.
+// (:2066-2150), clusterGraph (:1832-1952: wavefrontFill, addCentroid, isNewHomotopyClass, findMinClustertours,
+// the depth-first search over clusters and the stitching -- floods, shortening and mutual-visibility tests on
+// the device, see csrc/host/cluster_graph.cpp) and the static entry point find_geometrical_paths (:2489-2684).
+// find_geometrical_paths calls the hook `cluster_stage` where the reference calls clusterGraph() (:2591); by
+// default the hook is clusterGraph().
 #pragma once
 #include <functional>
 #include <memory>
@@ -42,6 +42,24 @@ template <class T> class TopologicalPRMClustering {
   static std::vector<path_with_length<T>> removeTooLongPaths(std::vector<path_with_length<T>> paths);
   static std::vector<path_with_length<T>> removeEquivalentPaths(std::vector<path_with_length<T>> paths);
   std::vector<path_with_length<T>> findShortestPath();
+  // clusterGraph (:1832-1952): seeds -> wavefrontFill (floods on the device roadmap, centroids added while a max
+  // connection is a new homotopy class) -> min tours -> depth-first search over clusters -> stitched paths
+  std::vector<path_with_length<T>> clusterGraph();
+  struct ClusterStats {
+    int seeds = 0;            // clusters at the end
+    int floods = 0;           // wavefrontFill floods (1)
+    int refloods = 0;         // addCentroid calls
+    int capped_refloods = 0;  // re-floods in which the reference's cnt < max_nodes cap (:1319) would have fired
+    int homotopy_checks = 0;  // isNewHomotopyClass evaluations (batched; includes speculative ones)
+  };
+  const ClusterStats &clusterStats() const { return cluster_stats_; }
+  const std::vector<int> &clusterSeeds() const { return cluster_seeds_; }
+  const std::vector<int> &clusterLabels() const { return cluster_labels_; }
+  // node ids tried, in this order, as extra initial seeds when num_clusters > 2 (the reference draws them with
+  // randIntMinMax, :1847); when unset they come from a generator seeded with sampling_seed
+  void setSeedCandidates(const std::vector<int> &ids) { seed_candidates_ = ids; }
+  // length bound of the search over clusters (find_geometrical_paths sets it to shortest * max_path_length_ratio, :2588)
+  void setMaxPathLength(double len) { max_path_length_ = len; }
   // the decision at the end of isNewHomotopyClass (:1702-1726) for a batch of (min, max) connection path
   // pairs: shorten min backward then forward, max forward then backward, then isDeformablePath at
   // ceil(longer / cdc) + 1 connectors.  All pairs share four shorten launches and one deformability launch.
@@ -65,11 +83,23 @@ template <class T> class TopologicalPRMClustering {
   void setEllipseRatioMajorAxis(const double r) { ellipse_ratio_major_axis_focal_length_ = r; }
 
   // ---- additions of the accelerated build ----
-  const std::vector<HeapNode<T> *> &nodes() const { return nodes_; }
+  // the roadmap as HeapNodes; their visibility_node_ids maps are filled from the CSR on first use (the planner's own
+  // stages work on the CSR and never need them)
+  const std::vector<HeapNode<T> *> &nodes() {
+    materializeAdjacency();
+    return nodes_;
+  }
+  void materializeAdjacency();
+  // the CSR roadmap as the device handed it back
+  const std::vector<int32_t> &csrRowPtr() const { return csr_row_ptr_; }
+  const std::vector<int32_t> &csrCol() const { return csr_col_; }
+  const std::vector<double> &csrWeights() const { return csr_w_; }
   // candidate stream for the next sampleMultiple (draw order of fillRandomStateInEllipse); when unset
   // the candidates are generated on the device from `sampling_seed`
   void setCandidateStream(const std::vector<Vector<3>> &cand) { candidate_stream_ = cand; }
   static uint64_t sampling_seed;
+  // find_geometrical_paths: candidate stream of gate pair i (optional; pairs without one draw on the device)
+  static std::vector<std::vector<Vector<3>>> gate_candidate_streams;
   // where the reference runs clusterGraph(); receives the planner after Dijkstra and returns the
   // candidate paths to shorten and filter
   static std::function<std::vector<path_with_length<T>>(TopologicalPRMClustering<T> &, const path_with_length<T> &)>
@@ -82,6 +112,9 @@ template <class T> class TopologicalPRMClustering {
   // CSR of the roadmap as sampleMultiple received it from the device (input of the device graph search)
   std::vector<int32_t> csr_row_ptr_, csr_col_;
   std::vector<double> csr_w_;
+  bool adjacency_ready_ = true;
+  std::vector<int> seed_candidates_, cluster_seeds_, cluster_labels_;
+  ClusterStats cluster_stats_;
   int num_clusters_, max_clusters_, min_clusters_;
   double min_ratio_;
   double max_path_length_ratio_;

@@ -273,6 +273,45 @@ int ctp_sssp_dev(ctp_map *map, int64_t q, int64_t n, const int32_t *row_ptr, con
                  const double *w, const int64_t *nnz_off, const int32_t *src, int ns, double *dist,
                  int32_t *pred, int32_t *label, void *stream);
 
+/* ---- the floods of the cluster stage (wavefrontFill + addCentroid on the GPU CSR).
+ * One call = one flood for q roadmaps at once.
+ *   mode 0: wavefrontFill's multi-source Dijkstra from seeds[0 .. n_seeds) with its inter-cluster connection
+ *           records (include/topological_prm_clustering.hpp:826-962);
+ *   mode 1: addCentroid's re-flood from the newest seed seeds[n_seeds-1] on top of the dist / prev / label state of
+ *           the floods before it (:1276-1374) -- only the nodes the new cluster claims change.
+ * seeds: q x max_seeds node ids, n_seeds[q] (0 = this query takes no part: nothing of it is touched).
+ * dist / prev / label: q x n, written (mode 0) or updated (mode 1); dist = +inf, prev = label = -1 for nodes no seed
+ * reaches.  prev[v] = the node whose relaxation first produced dist[v] in the sequential loop's pop order,
+ * ascending (distance, node id).  Records: every (expanding node ex, neighbour nb) the sequential loop would have
+ * appended to all_cluster_connections / new_connections, with its distance dist_then(nb) + dist(ex) + w where
+ * dist_then is nb's possibly still tentative distance at that moment; rec_nodes q x rec_cap x 2 (ex, nb), rec_label
+ * q x rec_cap (the cluster nb belonged to at that moment -- it may change later in the same flood), rec_dist
+ * q x rec_cap, rec_count[q] (records beyond rec_cap are counted, not written).  The _dev form leaves them in no
+ * particular order; ctp_cluster_flood sorts each query's records into the sequential loop's append order.
+ * n_updates[q]: successful relaxations (the reference's cnt - 1, which caps addCentroid at n, :1319: a mode-1 flood
+ * whose count reaches n - 1 is not reproduced -- callers test for it).
+ * The neighbour order (ascending id) and the pop order among equal distances (ascending id) are this library's rule:
+ * the reference iterates an unordered_map keyed by pointers, so it has no reproducible order of its own. */
+int ctp_cluster_flood_dev(ctp_map *map, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col,
+                          const double *w, const int64_t *nnz_off, const int32_t *seeds, int max_seeds,
+                          const int32_t *n_seeds, int mode, double *dist, int32_t *prev, int32_t *label,
+                          int64_t rec_cap, int32_t *rec_nodes, int32_t *rec_label, double *rec_dist,
+                          int32_t *rec_count, uint64_t *n_updates, void *stream);
+
+/* q roadmaps kept on the device together with the state of their floods -- what clusterGraph (:1832-1952) keeps in
+ * its HeapNodes (distance_from_start, previous_point, cluster_id) between wavefrontFill and the addCentroid calls.
+ * CSR as ctp_build_prm returns it.  info = { q, n, nnz, record capacity per query (= its widest nnz) }. */
+typedef struct ctp_roadmap ctp_roadmap;
+int ctp_roadmap_create(ctp_map *map, int64_t q, int64_t n, const int32_t *row_ptr, const int32_t *col,
+                       const double *w, const int64_t *nnz_off, int max_seeds, ctp_roadmap **out);
+int ctp_roadmap_destroy(ctp_roadmap *r);
+int ctp_roadmap_info(const ctp_roadmap *r, int64_t info[4]);
+/* host form of ctp_cluster_flood_dev on a resident roadmap: seeds (q x max_seeds) and n_seeds in; the state after the
+ * flood and the sorted records out (rec_nodes q x cap x 2, rec_label / rec_dist q x cap with cap from ctp_roadmap_info) */
+int ctp_cluster_flood(ctp_roadmap *r, const int32_t *seeds, const int32_t *n_seeds, int mode, double *dist,
+                      int32_t *prev, int32_t *label, int32_t *rec_nodes, int32_t *rec_label, double *rec_dist,
+                      int32_t *rec_count, uint64_t *n_updates);
+
 /* The planner's first two phases in one call (find_geometrical_paths :2558-2572: sampleMultiple, then
  * findShortestPath), for q independent queries: host candidate streams in, host start->goal paths
  * out; the roadmaps stay on the device.  path_ids: q x path_cap node ids in the query's own node

@@ -155,6 +155,24 @@ int orc_remove_equivalent(const orc_map *m, const double *pts, const int32_t *of
 void orc_sssp(int n, const int32_t *row_ptr, const int32_t *col, const double *w, const int32_t *src,
               int ns, double *dist, int32_t *pred, int32_t *label);
 
+/* ---- cluster stage (ctp_oracle_cluster.c; include/topological_prm_clustering.hpp:589-1952) ---- */
+/* one flood: mode 0 = wavefrontFill's multi-source flood (:826-962), mode 1 = addCentroid's re-flood from
+ * seeds[nseeds-1] (:1276-1374) on top of the dist / prev / cluster arrays passed in.  Records (expanding node,
+ * neighbour, distance) in the reference's append order; returns their number. */
+int orc_cluster_flood(int n, const int32_t *rp, const int32_t *col, const double *w, const int32_t *seeds, int nseeds,
+                      int mode, double *dist, int32_t *prev, int32_t *cluster, int cap, int32_t *rec_nodes,
+                      int32_t *rec_label, double *rec_dist, int64_t *n_updates);
+/* clusterGraph (:1832-1952): stitched cluster paths (points back to back, offsets, DFS lengths), final seeds and
+ * labels.  Returns the number of paths, -1 capacity, -2 where the reference would exit(1). */
+int orc_cluster_graph(const orc_map *m, int n, const double *xyz, const int32_t *rp, const int32_t *col, const double *w,
+                      double clr, double cdc, int num_clusters, int max_clusters, int min_clusters, double max_path_length,
+                      const int32_t *seed_candidates, int n_cand, int cap_paths, int cap_pts, double *out_pts,
+                      int32_t *out_off, double *out_len, int32_t *seeds_out, int32_t *nseeds_out, int32_t *cluster_out);
+/* re-floods of the last orc_cluster_graph call in which the node-count cap of addCentroid (:1319) fired */
+int orc_cluster_capped_refloods(void);
+/* removeTooLongPaths (:2193-2222) */
+void orc_remove_too_long(const double *lengths, int P, double min_allowed, double cutoff_ratio, uint8_t *keep);
+
 /* exact signed squared Euclidean distance transform of an n^3 occupancy grid (.npy order), by definition
  * (separable brute-force minimisation, O(n^4)): the checker for ctp_map_create_occupancy.  The map pipeline's
  * own distance field comes from mesh_to_sdf (map.py:49-73, not in this image): parity unpinned at that

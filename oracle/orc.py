@@ -237,6 +237,109 @@ def sssp(row_ptr, col, w, src, want_label=False):
     return (dist, pred, label) if want_label else (dist, pred)
 
 
+def cluster_flood(row_ptr, col, w, seeds, mode=0, dist=None, prev=None, cluster=None, cap=None):
+    """orc_cluster_flood: one flood of the cluster stage -> dist, prev, cluster, records (nodes m x 2, dist m), updates"""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    w = _f64(w)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+    n = len(row_ptr) - 1
+    dist = np.empty(n) if dist is None else _f64(dist).copy()
+    prev = np.empty(n, dtype=np.int32) if prev is None else np.ascontiguousarray(prev, dtype=np.int32).copy()
+    cluster = np.empty(n, dtype=np.int32) if cluster is None else np.ascontiguousarray(cluster, dtype=np.int32).copy()
+    cap = len(col) if cap is None else cap
+    rn = np.empty((cap, 2), dtype=np.int32)
+    rd = np.empty(cap)
+    rl = np.empty(cap, dtype=np.int32)
+    upd = C.c_int64(0)
+    m = _L().orc_cluster_flood(C.c_int(n), _p(row_ptr), _p(col), _p(w), _p(seeds), C.c_int(len(seeds)), C.c_int(mode), _p(dist),
+                               _p(prev), _p(cluster), C.c_int(cap), _p(rn), _p(rl), _p(rd), C.byref(upd))
+    return dist, prev, cluster, rn[:min(m, cap)].copy(), rd[:min(m, cap)].copy(), upd.value, rl[:min(m, cap)].copy()
+
+
+def cluster_graph(om, nodes, row_ptr, col, w, clr, cdc, max_path_length, num_clusters=2, max_clusters=10, min_clusters=2,
+                  seed_candidates=(), cap_paths=4096, cap_pts=1 << 20):
+    """orc_cluster_graph: clusterGraph (:1832-1952) -> (paths [k x 3 arrays], DFS lengths, seeds, labels)"""
+    nodes = _f64(nodes).reshape(-1, 3)
+    n = len(nodes)
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    w = _f64(w)
+    sc = np.ascontiguousarray(seed_candidates, dtype=np.int32)
+    pts = np.empty((cap_pts, 3))
+    off = np.zeros(cap_paths + 1, dtype=np.int32)
+    lens = np.empty(cap_paths)
+    seeds = np.full(max(2, max_clusters), -1, dtype=np.int32)
+    ns = C.c_int32(0)
+    labels = np.empty(n, dtype=np.int32)
+    rc = _L().orc_cluster_graph(C.byref(om.m), C.c_int(n), _p(nodes), _p(row_ptr), _p(col), _p(w), C.c_double(clr), C.c_double(cdc),
+                                C.c_int(num_clusters), C.c_int(max_clusters), C.c_int(min_clusters), C.c_double(max_path_length),
+                                _p(sc), C.c_int(len(sc)), C.c_int(cap_paths), C.c_int(cap_pts), _p(pts), _p(off), _p(lens),
+                                _p(seeds), C.byref(ns), _p(labels))
+    if rc < 0:
+        raise RuntimeError(f"orc_cluster_graph failed: {rc}")
+    return [pts[off[i]:off[i + 1]].copy() for i in range(rc)], lens[:rc].copy(), seeds[:ns.value].copy(), labels
+
+
+def cluster_capped_refloods():
+    """re-floods of the last cluster_graph call in which addCentroid's node-count cap (:1319) fired"""
+    return int(_L().orc_cluster_capped_refloods())
+
+
+def find_geometrical_paths(om, start, goal, cand, n, clr, cdc, num_clusters=2, max_clusters=10, min_clusters=2,
+                           max_path_length_ratio=1.5, cutoff_ratio=1.3, min_allowed=0.0, seed_candidates=(), nthreads=1):
+    """find_geometrical_paths (include/topological_prm_clustering.hpp:2489-2684) for one start-goal pair, composed from
+    the restated stages: sampleMultiple -> Dijkstra -> clusterGraph -> shorten both ways -> removeTooLongPaths ->
+    removeEquivalentPaths -> shorten both ways -> removeEquivalentPaths -> sort by length.
+    -> dict(paths, lengths, cluster_paths, cluster_lengths, seeds, labels, shortest, capped_refloods)"""
+    nodes, filled, _, _ = om.sample_reject(start, goal, cand, clr, n)
+    if filled < n:
+        raise RuntimeError("candidate stream too short")
+    g = om.build_prm(nodes, clr, cdc, nthreads=nthreads)
+    dist, _ = sssp(g["row_ptr"], g["col"], g["w"], [0])
+    out = dict(paths=[], lengths=np.zeros(0), cluster_paths=[], cluster_lengths=np.zeros(0), seeds=np.zeros(0, np.int32),
+               labels=None, shortest=float(dist[1]), capped_refloods=0, nodes=nodes, graph=g)
+    if not np.isfinite(dist[1]):
+        return out
+    found, flen, seeds, labels = cluster_graph(om, nodes, g["row_ptr"], g["col"], g["w"], clr, cdc, dist[1] * max_path_length_ratio,
+                                               num_clusters, max_clusters, min_clusters, seed_candidates)
+    out.update(cluster_paths=found, cluster_lengths=flen, seeds=seeds, labels=labels, capped_refloods=cluster_capped_refloods())
+
+    def both_ways(paths, lens):
+        res, rl = [], []
+        for p, l in zip(paths, lens):
+            for fwd in (False, True):  # shorten_path(path, false) then shorten_path(path) (:2612-2625)
+                q, _, ql, status, _ = om.shorten_path(p, l, fwd, clr, cdc, cap=len(p) + 4096)
+                if status < 0:
+                    raise RuntimeError(f"shorten_path status {status}: the reference would exit")
+                if status == 0:
+                    p, l = q, ql
+            res.append(p)
+            rl.append(l)
+        return res, rl
+
+    paths, lens = both_ways(found, list(flen))
+    keep = remove_too_long(lens, min_allowed, cutoff_ratio)
+    paths = [p for p, k in zip(paths, keep) if k]
+    lens = [l for l, k in zip(lens, keep) if k]
+    for _ in range(2):
+        if len(paths) > 1:
+            ids = om.remove_equivalent(paths, lens, clr, cdc)
+            paths, lens = [paths[i] for i in ids], [lens[i] for i in ids]
+        if _ == 0:
+            paths, lens = both_ways(paths, lens)
+    order = sorted(range(len(paths)), key=lambda i: lens[i])  # std::sort by length (:2656)
+    out.update(paths=[paths[i] for i in order], lengths=np.array([lens[i] for i in order]))
+    return out
+
+
+def remove_too_long(lengths, min_allowed, cutoff_ratio):
+    lengths = _f64(lengths)
+    keep = np.empty(len(lengths), dtype=np.uint8)
+    _L().orc_remove_too_long(_p(lengths), C.c_int(len(lengths)), C.c_double(min_allowed), C.c_double(cutoff_ratio), _p(keep))
+    return keep.astype(bool)
+
+
 def edt_signed(occ, pitch):
     """orc_edt_signed: exact signed EDT of an occupancy grid by definition -> (f32 field, signed int32 d2)"""
     occ = np.ascontiguousarray(np.asarray(occ) != 0, dtype=np.uint8)
