@@ -358,13 +358,13 @@ def run_legs(args):
     import subprocess as sp
     legs = {}
     todo = {
-        "C3": ["--workload", "C3", "--steps", "20", "--no-paths", "--no-planner", "--no-sustained", "--no-e2e-full"],
+        "C3": ["--workload", "C3", "--steps", "20", "--no-paths", "--no-sustained", "--no-e2e-full"],
         "MU_C2": ["--workload", "MU", "--mu-map", "C2", "--steps", "10"],
         "MU_C3": ["--workload", "MU", "--mu-map", "C3", "--steps", "10"],
         "C5": ["--workload", "C5", "--steps", "10"],
     }
     keep = ("value", "unit", "ms_per_step", "steps", "roofline", "parity", "cpu_baseline", "e2e", "stage_ms_per_step",
-            "free_edge_fraction", "lookups_per_s", "shortest_path", "cluster_stage", "gpu_launches")
+            "free_edge_fraction", "lookups_per_s", "shortest_path", "ms_per_query", "gpu_launches")
     for name, flags in todo.items():
         t0 = time.perf_counter()
         try:
@@ -1162,41 +1162,71 @@ def main():
 
     # ---- one query through the reference's class surface (C++ host layer over the C ABI): rank 0, N = 1 ----
     planner_leg = None
-    if rank == 0 and world == 1 and not args.no_planner and n <= 20000:
-        import tempfile
+    full_query = None
+    if rank == 0 and world == 1 and not args.no_planner:
         from ctopprm_learn_b200 import hostlib
-        fn = tempfile.mktemp(suffix=".npy")
-        try:
-            synth.write_map(fn, vox, c, e)
+        t0 = time.perf_counter()
+        hm = hostlib.HostMap.from_memory(vox, c, e, device=local)
+        t_load = time.perf_counter() - t0
+        qi = 0  # the first query whose goal is reachable, when the query-paths leg has told us
+        if e2e_query is not None and (qout["path_n"] > 0).any():
+            qi = int(np.argmax(qout["path_n"] > 0))
+        ya = hostlib.DEFAULT_YAML.format(map="(memory)", clr=clr, cdc=cdc, planar="false", n=n, s=list(s_h[qi]), g=list(g_h[qi]))
+        t_sm, t_sp, found = [], [], 0
+        for rep in range(4):
+            pl = hostlib.HostPlanner(hm, ya, s_h[qi], g_h[qi])
+            pl.set_candidates(cand_h[qi])
             t0 = time.perf_counter()
-            hm = hostlib.HostMap(fn, device=local)
-            t_load = time.perf_counter() - t0
-            qi = 0  # the first query whose goal is reachable, when the query-paths leg has told us
-            if e2e_query is not None and (qout["path_n"] > 0).any():
-                qi = int(np.argmax(qout["path_n"] > 0))
-            ya = hostlib.DEFAULT_YAML.format(map=fn, clr=clr, cdc=cdc, planar="false", n=n, s=list(s_h[qi]), g=list(g_h[qi]))
-            t_sm, t_sp, found = [], [], 0
-            for rep in range(4):
-                pl = hostlib.HostPlanner(hm, ya, s_h[qi], g_h[qi])
-                pl.set_candidates(cand_h[qi])
-                t0 = time.perf_counter()
-                pl.sample_multiple(n)      # device PRM build + HeapNode graph re-materialised on the host
-                t1 = time.perf_counter()
-                ids, length = pl.shortest()  # findShortestPath: ctp_sssp over the same roadmap
-                t2 = time.perf_counter()
-                pl.close()
-                if rep:
-                    t_sm.append(t1 - t0)
-                    t_sp.append(t2 - t1)
-                    found = int(len(ids) > 0)
-            hm.close()
-            planner_leg = {"map_load_ms": 1e3 * t_load, "sample_multiple_ms": 1e3 * float(np.median(t_sm)),
-                           "find_shortest_path_ms": 1e3 * float(np.median(t_sp)), "query": qi, "path_found": found,
-                           "api": "ESDFMap::load + TopologicalPRMClustering::sampleMultiple / findShortestPath "
-                                  "(include/ctopprm/*.hpp over the C ABI; pointer graph rebuilt on the host), wall clock"}
-        finally:
-            if os.path.exists(fn):
-                os.unlink(fn)
+            pl.sample_multiple(n)      # device PRM build; the CSR comes back, the pointer graph is filled only on demand
+            t1 = time.perf_counter()
+            ids, length = pl.shortest()  # findShortestPath: ctp_sssp over the same roadmap
+            t2 = time.perf_counter()
+            pl.close()
+            if rep:
+                t_sm.append(t1 - t0)
+                t_sp.append(t2 - t1)
+                found = int(len(ids) > 0)
+        planner_leg = {"map_load_ms": 1e3 * t_load, "sample_multiple_ms": 1e3 * float(np.median(t_sm)),
+                       "find_shortest_path_ms": 1e3 * float(np.median(t_sp)), "query": qi, "path_found": found,
+                       "api": "ESDFMap::loadFromMemory + TopologicalPRMClustering::sampleMultiple / findShortestPath "
+                              "(include/ctopprm/*.hpp over the C ABI), wall clock"}
+        # the whole CTopPRM query -- PRM build, shortest path, cluster stage (floods, homotopy checks, min tours, search
+        # over clusters), shortening, pruning -- through find_geometrical_paths, on the map's face-to-face query
+        # (C1-C3 start / goal on opposite faces) and beside the CPU restatement of the same stages
+        fs, fg = synth.default_query(c, e, cfg=WORKLOADS[args.workload][0])
+        fcand = synth.ellipsoid_candidates(fs, fg, cpn * n, 4242)
+        fya = hostlib.DEFAULT_YAML.format(map="(memory)", clr=clr, cdc=cdc, planar="false", n=n, s=list(fs), g=list(fg))
+        t_full, lens_g, paths_g = [], None, None
+        for rep in range(4):
+            t0 = time.perf_counter()
+            lens_g, paths_g = hm.find_geometrical_paths(fya, fs, fg, "", cand=fcand, want_paths=True, cap_pts=1 << 20, cap=4096)
+            if rep:
+                t_full.append(time.perf_counter() - t0)
+        full_query = {"ms_per_query": 1e3 * float(np.median(t_full)), "distinct_paths": int(len(lens_g)),
+                      "path_lengths": [float(x) for x in lens_g[:8]], "nodes": n,
+                      "api": "TopologicalPRMClustering::find_geometrical_paths (sampleMultiple -> findShortestPath -> "
+                             "clusterGraph -> shorten -> removeTooLong / removeEquivalent -> shorten -> removeEquivalent), "
+                             "host candidates in, host paths out, wall clock, median of 3"}
+        if not args.no_cpu:
+            from oracle import orc as _orc
+            _orc.build()
+            om_f = _orc.OracleMap(vox, c, e)
+            cores = cpu_cores()
+            t0 = time.perf_counter()
+            ow = _orc.find_geometrical_paths(om_f, fs, fg, fcand, n, clr, cdc, nthreads=1)
+            t_cpu1 = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            _orc.find_geometrical_paths(om_f, fs, fg, fcand, n, clr, cdc, nthreads=cores)
+            t_cpuN = time.perf_counter() - t0
+            same = bool(len(ow["lengths"]) == len(lens_g) and np.array_equal(ow["lengths"], lens_g) and
+                        all(np.array_equal(a_, b_) for a_, b_ in zip(ow["paths"], paths_g)))
+            full_query["cpu_restatement"] = {"ms_per_query_1_thread": 1e3 * t_cpu1, "ms_per_query_all_cores": 1e3 * t_cpuN,
+                                             "cores": cores, "kind": "port", "distinct_paths": int(len(ow["lengths"])),
+                                             "cluster_seeds": int(len(ow["seeds"])), "capped_refloods": int(ow["capped_refloods"]),
+                                             "note": "oracle restatement of the same stages; only the roadmap's directed checks "
+                                                     "use more than one thread (the reference is single-threaded throughout)"}
+            full_query["paths_identical_to_cpu"] = same
+        hm.close()
 
     # ---- CPU baseline (rank 0, N = 1): bounded sample of the same queries, all host cores ----
     cpu = None
@@ -1259,7 +1289,8 @@ def main():
             "impl_config": {"layout": dmap.layout_name() + (" (edge march) + cell8 (rejection)" if extra else ""),
                             "lanes_per_edge": dmap.prm_group()},
             "ms_per_query": {"batched": ms_max / args.steps / q, "single_query_latency": single_ms,
-                             "single_query_latency_cuda_graph": single_graph_ms, "class_surface": planner_leg},
+                             "single_query_latency_cuda_graph": single_graph_ms, "class_surface": planner_leg,
+                             "full_query": full_query},
             "paths": paths_leg, "shortest_path": sssp_leg, "e2e_query": e2e_query,
             "lookups_per_s": lookups / (ms_max * 1e-3),
             "stage_ms_per_step": {k_: v / args.steps for k_, v in stage_ms.items()},

@@ -50,6 +50,13 @@ void *ctph_map_load(const char *filename, int device, int layouts) {
     return nullptr;
   }
 }
+void *ctph_map_from_memory(const float *vox, int n, const double *c, const double *e, int device, int layouts) {
+  ESDFMap::setDevice(device);
+  if (layouts) ESDFMap::setLayouts(layouts);
+  auto *b = new MapBox{std::make_shared<ESDFMap>()};
+  b->map->loadFromMemory(vox, n, V(c), V(e));
+  return b;
+}
 void *ctph_map_from_occupancy(const unsigned char *occ, int n, const double *c, const double *e, int device, int layouts) {
   ESDFMap::setDevice(device);
   if (layouts) ESDFMap::setLayouts(layouts);

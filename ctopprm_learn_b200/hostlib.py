@@ -46,6 +46,7 @@ def lib():
         L = C.CDLL(lib_path())
         L.ctph_map_load.restype = C.c_void_p
         L.ctph_map_from_occupancy.restype = C.c_void_p
+        L.ctph_map_from_memory.restype = C.c_void_p
         L.ctph_planner_new.restype = C.c_void_p
         L.ctph_get_clearence.restype = C.c_double
         L.ctph_planner_graph.restype = C.c_int64
@@ -82,6 +83,15 @@ class HostMap:
         c, e = _f(centroid), _f(extents)
         self = cls.__new__(cls)
         self.h = C.c_void_p(lib().ctph_map_from_occupancy(_p(occ), occ.shape[0], _p(c), _p(e), device, layouts))
+        return self
+
+    @classmethod
+    def from_memory(cls, vox, centroid, extents, device=0, layouts=0):
+        """ESDFMap::loadFromMemory: the voxel grid as the .npy record holds it (x*n*n + y*n + z)"""
+        vox = np.ascontiguousarray(vox, dtype=np.float32)
+        c, e = _f(centroid), _f(extents)
+        self = cls.__new__(cls)
+        self.h = C.c_void_p(lib().ctph_map_from_memory(_p(vox), vox.shape[0], _p(c), _p(e), device, layouts))
         return self
 
     def save(self, filename):

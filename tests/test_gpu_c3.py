@@ -1,0 +1,77 @@
+"""BASELINE configs[2] at full size: the forest ESDF of 1024^3 voxels (4 GiB, beyond the L2), 100 000-node roadmap.
+The paths that only this size exercises -- the 32 x 32 mosaic of the gather texture, the 32 GiB CELL8 records the
+rejection stage reads, 64-bit voxel offsets, the cell-ordered edge walk, single-CTA per-query kernels on 10^5 nodes --
+against the oracle: nodes, candidates consumed, k-NN lists, directed verdicts, CSR with FP64 weights of one query,
+2^20 random segments through ctp_edge_check in every layout built, and the cluster stage on the 100 000-node roadmap.
+Set CTP_SKIP_C3=1 to leave this module out (map synthesis + oracle take about a minute of host time)."""
+import os
+
+import numpy as np
+import pytest
+
+from ctopprm_learn_b200 import capi, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("CTP_SKIP_C3") == "1", reason="CTP_SKIP_C3=1")]
+
+CLR, CDC = synth.MIN_CLEARANCE, synth.COLLISION_DISTANCE_CHECK
+NT = max(1, min(32, os.cpu_count() or 1))
+
+
+@pytest.fixture(scope="module")
+def c3(orc):
+    vox, c, e = synth.make_config_map("C3")
+    assert vox.shape == (1024, 1024, 1024)
+    m = capi.DeviceMap(vox, c, e, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX | capi.LAYOUT_CELL8)
+    m.set_layout(capi.LAYOUT_TEX)
+    yield m, orc.OracleMap(vox, c, e), c, e
+    m.close()
+
+
+def test_c3_roadmap_vs_oracle(c3, orc):
+    m, om, c, e = c3
+    n, k = 100000, 13
+    s, g = synth.default_query(c, e, cfg="C3")
+    cand = synth.ellipsoid_candidates(s, g, 6 * n, 303)
+    nodes, n_filled, n_used, accept = m.sample_reject(s[None], g[None], cand[None], CLR, n)
+    n0, filled0, used0, acc0 = om.sample_reject(s, g, cand, CLR, n)
+    assert n_filled[0] == filled0 == n and n_used[0] == used0
+    assert np.array_equal(accept[0, :used0], acc0[:used0])
+    assert np.array_equal(nodes[0], n0)
+    got = m.build_prm(nodes, CLR, CDC)
+    want = om.build_prm(n0, CLR, CDC, nthreads=NT)
+    assert np.array_equal(got["nbr"][0], want["nbr"])                      # k-NN lists
+    assert np.array_equal(got["directed_free"][0], want["directed_free"])  # 1.3 M directed verdicts
+    assert np.array_equal(got["row_ptr"][0], want["row_ptr"])
+    assert np.array_equal(got["col"], want["col"]) and np.array_equal(got["w"], want["w"])
+    # the one-call form from the candidate stream (chunk pipeline, CELL8 rejection) gives the same roadmap
+    out = m.sample_multiple(s[None], g[None], cand[None], n, CLR, CDC)
+    assert np.array_equal(out["nodes"][0], n0) and np.array_equal(out["row_ptr"][0], want["row_ptr"])
+    nnz = int(out["nnz_off"][1])
+    assert np.array_equal(out["col"][:nnz], want["col"]) and np.array_equal(out["w"][:nnz], want["w"])
+    # shortest path and the flood of the cluster stage on the 100 000-node roadmap
+    dist = m.sssp(got["row_ptr"], got["col"], got["w"], got["nnz_off"], np.zeros(1, np.int32))[0]
+    d0, _ = orc.sssp(want["row_ptr"], want["col"], want["w"], [0])
+    assert np.array_equal(dist[0], d0)
+    rm = m.roadmap(got["row_ptr"], got["col"], got["w"], got["nnz_off"], max_seeds=4)
+    fd, fp, fl, recs, upd = rm.flood([[0, 1]], mode=0)
+    o = orc.cluster_flood(want["row_ptr"], want["col"], want["w"], [0, 1], mode=0)
+    assert np.array_equal(fd[0], np.where(o[0] == np.finfo(np.float64).max, np.inf, o[0]))
+    assert np.array_equal(fp[0], o[1]) and np.array_equal(fl[0], o[2])
+    assert np.array_equal(recs[0][0], o[3]) and np.array_equal(recs[0][1], o[4]) and np.array_equal(recs[0][2], o[6])
+    rm.close()
+
+
+@pytest.mark.parametrize("layout", [capi.LAYOUT_TEX, capi.LAYOUT_CELL8, capi.LAYOUT_PLAIN])
+def test_c3_random_segments_vs_oracle(c3, layout):
+    m, om, c, e = c3
+    m.set_layout(layout)
+    try:
+        a, b = synth.random_edges(c, e, 1 << 20, 31)
+        free, hit, hit_idx, lookups = m.edge_check(a, b, CLR, CDC)
+        f0, h0, hi0, l0, _ = om.edge_nodes(a, b, CLR, CDC, nthreads=NT)
+        assert np.array_equal(free, f0) and np.array_equal(hit_idx, hi0) and np.array_equal(lookups, l0)
+        assert np.array_equal(hit, h0, equal_nan=True)
+        p = c + (np.random.default_rng(5).random((1 << 20, 3)) - 0.5) * (e + 0.2)
+        assert np.array_equal(m.clearance(p), om.clearance(p, nthreads=NT), equal_nan=True)
+    finally:
+        m.set_layout(capi.LAYOUT_TEX)
