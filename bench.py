@@ -778,6 +778,104 @@ def run_microbench(args, rank, world):
         dist.destroy_process_group()
 
 
+def run_shard_query(args, rank, world):
+    """--shard-query (second regime): ONE query of the workload's size split over all GPUs --
+    candidate blocks -> accept counts -> NCCL all-gather of the accepted node sets -> each GPU's slice of the neighbour
+    search and of the directed checks -> MAX all-reduce of the tables -> CSR on every GPU (ctopprm_learn_b200/sharded.py,
+    device tensors end to end).  Strong scaling: the work is fixed, the GPUs share it.  A step = one whole query;
+    per-phase times come from a second, instrumented set of steps (a device synchronisation after every phase)."""
+    import torch
+    import torch.distributed as dist
+    from ctopprm_learn_b200 import capi, sharded
+
+    local = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev, **({} if "RANK" in os.environ else
+                                                      {"rank": 0, "world_size": 1, "init_method": "tcp://127.0.0.1:29655"}))
+    mapcfg, n_def, _, cpn = WORKLOADS[args.workload]
+    n = args.nodes or n_def
+    clr, cdc = synth.MIN_CLEARANCE, synth.COLLISION_DISTANCE_CHECK
+    vox, c, e = synth.make_config_map(mapcfg)
+    layout = capi.DEFAULT_LAYOUT if vox.shape[0] <= 1024 else capi.LAYOUT_PLAIN
+    extra = capi.LAYOUT_CELL8 if vox.nbytes > (100 << 20) and not args.no_cell8 else 0
+    dmap = capi.DeviceMap(vox, c, e, device=local, layouts=layout | capi.LAYOUT_PLAIN | extra)
+    dmap.set_layout(layout)
+    be = sharded.DeviceBackend(dmap)
+    s, g = synth.default_query(c, e, cfg=mapcfg)
+    cand = synth.ellipsoid_candidates(s, g, cpn * n, 4242)
+    lo, hi = sharded.shard_range(len(cand), rank, world)
+    block = torch.from_numpy(cand[lo:hi]).to(dev)  # this rank's block of the shared sample file, resident in HBM
+
+    def step(tm=None):
+        return sharded.sample_multiple_sharded(be, s, g, block, n, clr, cdc, k=K_NN, local_device=local, timings=tm, to_host=False)
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dmap.read_launches()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = dmap.read_launches()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    tm = {}
+    for _ in range(args.steps):
+        step(tm)
+    phases = torch.tensor([tm[k_] for k_ in ("reject", "allgather_nodes", "knn_and_edges", "allreduce_tables", "csr")],
+                          dtype=torch.float64, device=dev)
+    dist.all_reduce(phases, op=dist.ReduceOp.MAX)
+    phases = (phases / args.steps * 1e3).tolist()
+    # identical on every rank, and identical to the one-call build on one GPU
+    nnz = int(out["nnz_off"][1])
+    sig = torch.stack([out["col"][:nnz].to(torch.int64).sum(), out["row_ptr"].to(torch.int64).sum(),
+                       out["directed_free"].to(torch.int64).sum(), torch.tensor(nnz, device=dev)])
+    sigs = torch.empty(world * 4, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sigs, sig)
+    same_on_all = bool((sigs.view(world, 4) == sigs.view(world, 4)[0]).all())
+    equal_one_gpu = None
+    if rank == 0:
+        cap = 2 * n * K_NN
+        rp = torch.zeros((1, n + 1), dtype=torch.int32, device=dev)
+        col = torch.zeros(cap, dtype=torch.int32, device=dev)
+        w = torch.zeros(cap, dtype=torch.float64, device=dev)
+        off = torch.zeros(2, dtype=torch.int64, device=dev)
+        dmap.build_prm_dev(out["nodes"].reshape(1, n, 3).contiguous(), 1, n, K_NN, clr, cdc, rp, col, w, cap, off,
+                           stream=torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        equal_one_gpu = bool(int(off[1]) == nnz and torch.equal(rp[0], out["row_ptr"]) and torch.equal(col[:nnz], out["col"][:nnz])
+                             and torch.equal(w[:nnz], out["w"][:nnz]))
+        ms_q = ms_max / args.steps
+        line = {"metric": METRIC, "value": n * K_NN / (ms_q * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_q, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{args.workload} --shard-query: ONE {n}-node query on the {mapcfg} map ({vox.shape[0]}^3 voxels) "
+                                       f"split over {world} GPU(s): candidate blocks, all-gather of node sets, row slices of k-NN + "
+                                       f"{n * K_NN} directed checks, MAX all-reduce of the tables, CSR replicated",
+                           "nodes_per_query": n, "k": K_NN, "candidates": len(cand), "parallelism": f"one query over {world} GPU(s), NCCL"},
+                "ms_per_query": ms_q,
+                "phase_ms_max_over_ranks": dict(zip(("reject", "allgather_nodes", "knn_and_edges", "allreduce_tables", "csr"), phases)),
+                "phase_note": "instrumented steps (device synchronised after every phase); allgather_nodes includes the host read "
+                              "of the accept counts, allreduce_tables moves n*k*5 bytes",
+                "identical_on_all_ranks": same_on_all, "identical_to_one_gpu_build": equal_one_gpu,
+                "gpu_launches": int(launches), "clocks": clk}
+        emit_line(line)
+    dmap.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -793,6 +891,8 @@ def main():
     ap.add_argument("--map-graphs", action="store_true", help="C5: replay each map's batch from a CUDA graph (measured: no gain, the sweep is not launch-bound)")
     ap.add_argument("--map-threads", type=int, default=4, help="C5 e2e: host threads driving the map handles")
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (default: per workload)")
+    ap.add_argument("--shard-query", action="store_true", help="one query of the workload's size split over all GPUs (strong scaling)")
+    ap.add_argument("--nodes", type=int, default=0, help="--shard-query: nodes of the query (default: the workload's)")
     ap.add_argument("--layout", default="auto", choices=["auto", "plain", "cell8", "tex", "brick"])
     ap.add_argument("--group", type=int, default=0, help="lanes per edge in the march kernel (0 = library default)")
     ap.add_argument("--knn-per-cell", type=float, default=0.0)
@@ -821,6 +921,11 @@ def main():
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.workload == "MU" and args.impl != "reference":
         run_microbench(args, rank, world)
+        return
+    if args.shard_query and args.impl != "reference":
+        if args.workload not in WORKLOADS:
+            raise SystemExit("bench.py: --shard-query needs --workload C1, C2 or C3")
+        run_shard_query(args, rank, world)
         return
     if args.workload == "MU":
         args.workload = "C2"  # no separate CPU arm for the microbench: its own cpu_baseline leg carries the comparison

@@ -77,6 +77,7 @@ _SIGS = {
     "ctp_build_prm_ex_dev": [_P, _P, _I64, _I64, _I, _D, _D, _I, _P, _P, _P, _P, _P, _I64, _P, _P],
     "ctp_csr_from_directed": [_P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _I64, _P],
     "ctp_edge_check_knn_dev": [_P, _P, _I64, _I64, _I, _P, _D, _D, _P, _P],
+    "ctp_prm_rows_dev": [_P, _P, _I64, _I, _D, _D, _I64, _I64, _P, _P, _P, _P],
     "ctp_csr_from_directed_dev": [_P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _I64, _P, _P],
     "ctp_sample_multiple": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, _P, _P, _P, _P, _P, _I64, _P],
     "ctp_sample_multiple_ex": [_P, _P, _P, _P, _I64, _I64, _I64, _I, _D, _D, _I, _P, _P, _P, _P, _P, _I64, _P],
@@ -584,6 +585,13 @@ class DeviceMap:
     def csr_from_directed_dev(self, nodes, q, n, k, nbr, directed_free, row_ptr, col, w, cap, nnz_off, stream=None):
         _check(lib().ctp_csr_from_directed_dev(self._h, _ptr(nodes), q, n, k, _ptr(nbr), _ptr(directed_free), _ptr(row_ptr),
                                                _ptr(col), _ptr(w), cap, _ptr(nnz_off), _stream_ptr(stream)))
+
+    def prm_rows_dev(self, nodes, n, k, clr, cdc, first, last, nbr, directed_free, stream=None):
+        """neighbour search + directed checks for the slice [first, last) of the cell order -> rows done"""
+        done = C.c_int64(0)
+        _check(lib().ctp_prm_rows_dev(self._h, _ptr(nodes), n, k, clr, cdc, first, last, _ptr(nbr), _ptr(directed_free),
+                                      C.byref(done), _stream_ptr(stream)))
+        return done.value
 
     def edge_check_knn_dev(self, nodes, q, n, k, nbr, clr, cdc, directed_free, stream=None):
         _check(lib().ctp_edge_check_knn_dev(self._h, _ptr(nodes), q, n, k, _ptr(nbr), clr, cdc, _ptr(directed_free),

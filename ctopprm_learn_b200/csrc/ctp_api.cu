@@ -1077,8 +1077,10 @@ extern "C" int ctp_sample_ellipsoid_draws(ctp_map *m, const double *start, const
 }
 
 // --------------------------------------- k-NN ----------------------------------------------
+// slice (optional, q == 1): {first, last} positions of the cell-sorted order on entry, moved to cell boundaries on
+// return (one 16-byte read back); only the rows of the points at those positions are searched and written
 static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, int32_t *idx, int idx_stride,
-                      float *d2, cudaStream_t st, const float4 **sorted_out = nullptr) {
+                      float *d2, cudaStream_t st, const float4 **sorted_out = nullptr, int64_t *slice = nullptr) {
   const int mc = knn_max_cells(n);
   const int64_t total = q * n;
   KnnGrid *d_grid = arena_take<KnnGrid>(m->ws, q);
@@ -1102,6 +1104,17 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
   k_knn_scatter<<<blocks, 256, 0, st>>>(d_pts, n, total, mc, d_cell_of, d_start, d_cnt, d_sorted);
   m->launches++;
   CK(cudaGetLastError());
+  int64_t first = 0, last = total;
+  if (slice) {
+    int64_t *d_bounds = reinterpret_cast<int64_t *>(d_fb);  // free until the search kernels run
+    k_knn_slice_bounds<<<1, 32, 0, st>>>(d_grid, d_start, slice[0], slice[1], d_bounds);
+    m->launches++;
+    CK(cudaMemcpyAsync(slice, d_bounds, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    first = slice[0];
+    last = slice[1];
+    if (last <= first) return CTP_OK;
+  }
   if (m->knn_tile && n > 4 * k) {
     CK(cudaMemsetAsync(d_fbn, 0, 8, st));
     const int lblocks = m->sm_count * 8;
@@ -1113,10 +1126,10 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
                               CTP_KNN_DIRECT_SMEM));                                                              \
       m->knn_smem_set |= 1u << K;                                                                                 \
     }                                                                                                             \
-    k_knn_direct<K><<<(int)((total + CTP_KNN_DIRECT_THREADS - 1) / CTP_KNN_DIRECT_THREADS),                       \
-                      CTP_KNN_DIRECT_THREADS, CTP_KNN_DIRECT_SMEM, st>>>(d_sorted, n, total, d_grid, mc, d_start,  \
+    k_knn_direct<K><<<(int)((last - first + CTP_KNN_DIRECT_THREADS - 1) / CTP_KNN_DIRECT_THREADS),                \
+                      CTP_KNN_DIRECT_THREADS, CTP_KNN_DIRECT_SMEM, st>>>(d_sorted, n, last, d_grid, mc, d_start,   \
                                                                          idx, idx_stride, d2, d_fb2, d_fbk,       \
-                                                                         d_fbn + 1);                              \
+                                                                         d_fbn + 1, first);                       \
     k_knn_direct_list<K><<<lblocks, CTP_KNN_DIRECT_THREADS, CTP_KNN_DIRECT_SMEM, st>>>(                           \
         d_sorted, n, d_fb2, d_fbk, d_fbn + 1, 1, d_grid, mc, d_start, idx, idx_stride, d2, d_fb, d_fbn);          \
     k_knn_ring_warp<K><<<lblocks, 32 * CTP_KNN_RW_WARPS, 0, st>>>(d_sorted, n, d_fb, d_fbn, d_grid, mc, d_start,  \
@@ -1136,10 +1149,10 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
               (long long)total, fb[1], 100.0 * fb[1] / (double)total, fb[0], 100.0 * fb[0] / (double)total);
     }
   } else {
-    const int sblocks = (int)((total + 127) / 128);
-#define KNN_CASE(K)                                                                                            \
-  case K:                                                                                                      \
-    k_knn_search<K><<<sblocks, 128, 0, st>>>(d_sorted, n, total, d_grid, mc, d_start, idx, idx_stride, d2);   \
+    const int sblocks = (int)((last - first + 127) / 128);
+#define KNN_CASE(K)                                                                                                \
+  case K:                                                                                                          \
+    k_knn_search<K><<<sblocks, 128, 0, st>>>(d_sorted, n, last, d_grid, mc, d_start, idx, idx_stride, d2, first); \
     m->launches++;                                                                                             \
     break;
     switch (k) {
@@ -1381,6 +1394,46 @@ extern "C" int ctp_edge_check_knn_dev(ctp_map *m, const double *nodes, int64_t q
   EdgeOut O{directed_free, nullptr, nullptr, nullptr, m->d_lookups};
   StageSpan span(m, CTP_STAGE_EDGES, st);
   return launch_edges(m, m->prm_group, S, edges, clr, cdc, 0, O, st);
+}
+
+// One GPU's share of a single large query split over several: the neighbour search and the
+// directed checks for the nodes at positions [first, last) of the k-NN grid's cell order (moved to cell boundaries, so
+// that the GPUs agree on who owns which node; a compact part of space, so different GPUs march through different parts
+// of the map).  Rows of other nodes come back as nbr = 0x80808080 (below every valid entry, -1 included) and
+// directed_free = 0: an element-wise maximum over the GPUs (one all-reduce each) assembles the full tables.
+extern "C" int ctp_prm_rows_dev(ctp_map *m, const double *nodes, int64_t n, int k, double clr, double cdc, int64_t first,
+                                int64_t last, int32_t *nbr, uint8_t *directed_free, int64_t *rows_done, void *stream) {
+  REQUIRE(m && n >= 2 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument (k must be in [1,16])");
+  REQUIRE(nodes && nbr && directed_free, "null buffer");
+  REQUIRE(first >= 0 && first <= last && last <= n, "slice must satisfy 0 <= first <= last <= n");
+  REQUIRE(cdc > 0, "collision_distance_check must be > 0");
+  REQUIRE(n * k < ((int64_t)1 << 31), "n*k must fit in int32");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t keep = m->ws.used;
+  CKR(arena_reserve(m->ws, keep + ws_bytes_prm(1, n, k) + 8192));
+  const int64_t edges = n * k;
+  CK(cudaMemsetAsync(nbr, 0x80, edges * 4, st));
+  CK(cudaMemsetAsync(directed_free, 0, edges, st));
+  const float4 *d_sorted = nullptr;
+  int64_t slice[2] = {first, last};
+  int rc;
+  {
+    StageSpan span(m, CTP_STAGE_KNN, st);
+    rc = knn_launch(m, nodes, 1, n, k, nbr, k, nullptr, st, &d_sorted, slice);
+  }
+  m->ws.used = keep;
+  CKR(rc);
+  if (rows_done) *rows_done = slice[1] - slice[0];
+  if (slice[1] <= slice[0]) return CTP_OK;
+  // work item r*k + slot = row order[r].w of the slice (the flat kernel walks the slice in cell order)
+  EdgeSrc S{nodes, nullptr, nullptr, nbr, n, k, 1, k, d_sorted + slice[0]};
+  S.small = 1;
+  S.dk = ctp_div_make((uint32_t)k);
+  S.dn = ctp_div_make((uint32_t)n);
+  EdgeOut O{directed_free, nullptr, nullptr, nullptr, m->d_lookups};
+  StageSpan span(m, CTP_STAGE_EDGES, st);
+  return launch_edges(m, 1, S, (slice[1] - slice[0]) * k, clr, cdc, 0, O, st);
 }
 
 extern "C" int ctp_csr_from_directed_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, const int32_t *nbr,

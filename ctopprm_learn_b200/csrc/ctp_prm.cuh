@@ -298,6 +298,24 @@ __global__ void __launch_bounds__(256) k_knn_scatter(const float4 *__restrict__ 
   sorted[q * n + pos] = pts[t];
 }
 
+// A slice [first, last) of the cell-sorted positions of query 0, moved to cell boundaries: out = {A, B} with
+// A / B = the smallest cell start >= first / last.  The order of the points INSIDE a cell depends on the scatter's
+// atomics, the cell starts do not: every GPU that built the grid from the same nodes gets the same A and B, so
+// slices [shard(r), shard(r + 1)) of different GPUs hold disjoint sets of points that cover the sample.
+__global__ void k_knn_slice_bounds(const KnnGrid *__restrict__ grids, const int32_t *__restrict__ cell_start, int64_t first,
+                                   int64_t last, int64_t *__restrict__ out) {
+  if (threadIdx.x > 1 || blockIdx.x) return;
+  const int ncell = grids[0].ncell;
+  const int64_t want = threadIdx.x ? last : first;
+  int lo = 0, hi = ncell;  // cell_start[0 .. ncell] is non-decreasing, cell_start[ncell] = n
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cell_start[mid] >= want) hi = mid;
+    else lo = mid + 1;
+  }
+  out[threadIdx.x] = cell_start[lo];
+}
+
 // k best (d2, index) pairs of a thread, ascending; one 64-bit key per pair (the bit pattern of a
 // non-negative float orders like the number, so key order == (distance, index) order)
 template <int K> struct TopK {
@@ -390,8 +408,8 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
                                                     const KnnGrid *__restrict__ grids, int cell_stride,
                                                     const int32_t *__restrict__ cell_start,
                                                     int32_t *__restrict__ idx, int idx_stride,
-                                                    float *__restrict__ d2out) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+                                                    float *__restrict__ d2out, int64_t first) {
+  const int64_t t = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= total) return;
   knn_ring_search<K>(t, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out);
 }
@@ -503,10 +521,11 @@ __global__ void __launch_bounds__(CTP_KNN_DIRECT_THREADS)
 k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const KnnGrid *__restrict__ grids,
              int cell_stride, const int32_t *__restrict__ cell_start, int32_t *__restrict__ idx, int idx_stride,
              float *__restrict__ d2out, int32_t *__restrict__ fb_list, uint8_t *__restrict__ fb_kept,
-             int32_t *__restrict__ fb_count) {
+             int32_t *__restrict__ fb_count, int64_t first) {
   extern __shared__ int32_t s_keep_raw[];  // CTP_KNN_DIRECT_SMEM bytes, passed at launch
   int32_t(*s_keep)[CTP_KNN_DIRECT_THREADS] = reinterpret_cast<int32_t(*)[CTP_KNN_DIRECT_THREADS]>(s_keep_raw);
-  const int64_t t = blockIdx.x * (int64_t)CTP_KNN_DIRECT_THREADS + threadIdx.x;
+  // positions [first, total) of the sorted array (first > 0: one GPU's slice of a query split over several)
+  const int64_t t = first + blockIdx.x * (int64_t)CTP_KNN_DIRECT_THREADS + threadIdx.x;
   if (t >= total) return;
   knn_direct_point<K>(t, threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out, 0, 0, 0,
                       fb_list, fb_kept, fb_count);

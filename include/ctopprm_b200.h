@@ -256,6 +256,17 @@ int ctp_sample_multiple_ex(ctp_map *map, const double *start, const double *goal
                            int32_t *n_filled, int32_t *row_ptr, int32_t *col, double *w, int64_t cap,
                            int64_t *nnz_off);
 
+/* One GPU's share of ONE large query split over several GPUs (the callers' side is
+ * ctopprm_learn_b200/sharded.py: candidate blocks -> accept counts -> all-gather of the accepted nodes -> this call on
+ * every GPU -> element-wise maximum of nbr and directed_free over the GPUs -> ctp_csr_from_directed_dev).
+ * Neighbour search and directed checks (:329-397) for the nodes at positions [first, last) of the k-NN grid's cell
+ * order, the bounds moved up to cell boundaries (all GPUs build the same grid from the same nodes and so agree on the
+ * owner of every node).  nbr (n x k) / directed_free (n x k) rows of the slice are written; all other rows are set to
+ * 0x80808080 / 0.  rows_done (host, optional): nodes in the slice after alignment.  Synchronises the stream once
+ * (16-byte read back of the aligned bounds). */
+int ctp_prm_rows_dev(ctp_map *map, const double *nodes, int64_t n, int k, double clr, double cdc, int64_t first,
+                     int64_t last, int32_t *nbr, uint8_t *directed_free, int64_t *rows_done, void *stream);
+
 /* ---- graph search over the CSR roadmaps (first "next" item): shortest paths from
  * a set of sources, one independent problem per query.  Replaces Dijkstra::findPath as called by
  * findShortestPath (include/topological_prm_clustering.hpp:2172, include/dijkstra.hpp:83-176) with

@@ -408,25 +408,109 @@ def test_csr_from_directed(c1):
 
 
 def test_sharded_single_query_device_backend(c1):
-    """sharded.sample_multiple_sharded with the product backend (one rank; 2-rank logic: tests/test_sharded_gloo.py)"""
+    """sharded.sample_multiple_sharded with the product backend, device tensors end to end over NCCL (one rank here;
+    two ranks: test_sharded_single_query_two_gpus; the host logic at world sizes 2 and 3: tests/test_sharded_gloo.py)"""
     import torch.distributed as dist
     from ctopprm_learn_b200 import sharded
     m, om, c, e = c1
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29617")
-    dist.init_process_group("gloo", rank=0, world_size=1)
+    dist.init_process_group("nccl", rank=0, world_size=1)
     try:
         n = 900
         s, g = synth.default_query(c, e)
         cand = synth.ellipsoid_candidates(s, g, 5 * n, 13)
-        out = sharded.sample_multiple_sharded(sharded.DeviceBackend(m), s, g, cand, n, CLR, CDC)
+        tm = {}
+        out = sharded.sample_multiple_sharded(sharded.DeviceBackend(m), s, g, cand, n, CLR, CDC, timings=tm)
     finally:
         dist.destroy_process_group()
+    assert set(tm) == {"reject", "allgather_nodes", "knn_and_edges", "allreduce_tables", "csr"}
     want_nodes = om.sample_reject(s, g, cand, CLR, n)[0]
     want = om.build_prm(want_nodes, CLR, CDC, nthreads=8)
     assert np.array_equal(out["nodes"], want_nodes) and np.array_equal(out["directed_free"], want["directed_free"])
+    assert np.array_equal(out["nbr"], want["nbr"])
     assert np.array_equal(out["row_ptr"], want["row_ptr"]) and np.array_equal(out["col"], want["col"])
     assert np.array_equal(out["w"], want["w"])
+
+
+@pytest.mark.parametrize("n,parts", [(900, 3), (20000, 8), (30, 4)])
+def test_prm_row_slices_cover_the_roadmap(c1, n, parts):
+    """ctp_prm_rows_dev: the slices that `parts` GPUs would take, run one after the other on this GPU -- disjoint, they
+    cover every node, and their element-wise maximum is the neighbour table and the verdicts of the one-GPU build"""
+    import torch
+    from ctopprm_learn_b200 import sharded
+    m, om, c, e = c1
+    s, g = synth.default_query(c, e)
+    cand = synth.ellipsoid_candidates(s, g, 6 * n, 19)
+    nodes = m.sample_reject(s[None], g[None], cand[None], CLR, n)[0]
+    full = m.build_prm(nodes, CLR, CDC)
+    dev = torch.device("cuda", m.device)
+    nodes_t = torch.from_numpy(nodes[0]).to(dev)
+    k = 13
+    nbr = torch.full((n, k), int(sharded.NBR_UNOWNED), dtype=torch.int32, device=dev)
+    free = torch.zeros((n, k), dtype=torch.uint8, device=dev)
+    owned = torch.zeros(n, dtype=torch.int32, device=dev)
+    total = 0
+    for r in range(parts):
+        lo, hi = sharded.shard_range(n, r, parts)
+        nb = torch.empty((n, k), dtype=torch.int32, device=dev)
+        fr = torch.empty((n, k), dtype=torch.uint8, device=dev)
+        total += m.prm_rows_dev(nodes_t, n, k, CLR, CDC, lo, hi, nb, fr, stream=torch.cuda.current_stream(dev))
+        torch.cuda.synchronize(dev)
+        mine = nb[:, 0] != int(sharded.NBR_UNOWNED)
+        assert (fr[~mine] == 0).all()
+        owned += mine.to(torch.int32)
+        nbr = torch.maximum(nbr, nb)
+        free = torch.maximum(free, fr)
+    assert total == n and (owned == 1).all()  # every node is owned by exactly one slice
+    assert np.array_equal(nbr.cpu().numpy(), full["nbr"][0])
+    assert np.array_equal(free.cpu().numpy().astype(bool), full["directed_free"][0])
+
+
+def _two_gpu_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    from ctopprm_learn_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        vox, c, e = synth.make_config_map("C1")
+        m = capi.DeviceMap(vox, c, e, device=rank, layouts=capi.LAYOUT_PLAIN | capi.LAYOUT_TEX)
+        n = 5000
+        s, g = synth.default_query(c, e)
+        cand = synth.ellipsoid_candidates(s, g, 5 * n, 23)
+        out = sharded.sample_multiple_sharded(sharded.DeviceBackend(m), s, g, cand, n, CLR, CDC, local_device=rank)
+        np.savez(os.path.join(tmp, f"out{rank}.npz"), **out)
+        m.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_single_query_two_gpus(c1, tmp_path):
+    """one query split over two GPUs (NCCL all-gather of the node sets, MAX all-reduce of the tables) = one-GPU build"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_two_gpu_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    m, om, c, e = c1
+    n = 5000
+    s, g = synth.default_query(c, e)
+    cand = synth.ellipsoid_candidates(s, g, 5 * n, 23)
+    want_nodes = om.sample_reject(s, g, cand, CLR, n)[0]
+    want = om.build_prm(want_nodes, CLR, CDC, nthreads=8)
+    for r in range(2):
+        out = np.load(tmp_path / f"out{r}.npz")
+        assert np.array_equal(out["nodes"], want_nodes) and np.array_equal(out["nbr"], want["nbr"])
+        assert np.array_equal(out["directed_free"], want["directed_free"])
+        assert np.array_equal(out["row_ptr"], want["row_ptr"]) and np.array_equal(out["col"], want["col"])
+        assert np.array_equal(out["w"], want["w"])
 
 
 @pytest.mark.parametrize("group", [1, 8])

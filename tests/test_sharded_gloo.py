@@ -1,12 +1,14 @@
 """world_size-2 (and 3) gloo runs of the sharding logic on CPU.  There is no device here, so the test
 injects the ORACLE as the compute backend; what is under test is the host logic of
 ctopprm_learn_b200/sharded.py: block assignment, order-preserving merge of accepted nodes, row-range
-edge checks, verdict gather -- the result must equal the unsharded build."""
+slices of the neighbour search and of the edge checks, the element-wise MAX merge of the tables -- over the same
+collectives the GPUs use (all_gather_into_tensor, all_reduce MAX); the result must equal the unsharded build."""
 import os
 import socket
 
 import numpy as np
 import pytest
+import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -26,43 +28,56 @@ def test_shard_range_covers_everything():
 
 
 class OracleBackend:
-    """test-only stand-in for sharded.DeviceBackend"""
+    """test-only stand-in for sharded.DeviceBackend: the same tensor interface, computed by the oracle on the CPU"""
 
     def __init__(self, vox, c, e):
         from oracle import orc
         self.orc = orc
         self.om = orc.OracleMap(vox, c, e)
 
-    def accepted(self, start, goal, cand, clr, cap):
-        nodes, filled, _, _ = self.om.sample_reject(start, goal, cand, clr, cap + 2)
-        return nodes[2:filled]
+    def to_device(self, a, dtype):
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype)
 
-    def knn(self, nodes, k):
-        return self.orc.knn_grid(nodes, k)[0]
+    def sync(self):
+        pass
 
-    def edge_rows(self, nodes, nbr, lo, hi, clr, cdc):
-        k = nbr.shape[1]
-        frm = np.repeat(np.arange(lo, hi, dtype=np.int32), k)
-        to = np.ascontiguousarray(nbr[lo:hi].reshape(-1))
-        free, _, _ = self.om.edge_index(nodes, frm, np.maximum(to, 0), clr, cdc)
-        free = free & (to >= 0)
-        return free.reshape(hi - lo, k).astype(np.uint8)
+    def accept_block(self, start_t, goal_t, cand_t, clr, cap):
+        out = torch.zeros((cap, 3), dtype=torch.float64)
+        if cand_t.shape[0] == 0 or cap == 0:
+            return out, torch.zeros(1, dtype=torch.int64)
+        nodes, filled, _, _ = self.om.sample_reject(start_t.numpy()[0], goal_t.numpy()[0], cand_t.numpy(), clr, cap + 2)
+        out[:filled - 2] = torch.from_numpy(nodes[2:filled])
+        return out, torch.tensor([filled - 2], dtype=torch.int64)
 
-    def csr(self, nodes, nbr, directed_free):
+    def prm_rows(self, nodes_t, k, clr, cdc, first, last):
+        nodes = nodes_t.numpy()
+        n = len(nodes)
+        nbr = np.full((n, k), sharded.NBR_UNOWNED, dtype=np.int32)
+        free = np.zeros((n, k), dtype=np.uint8)
+        if last > first:
+            nbr[first:last] = self.orc.knn_grid(nodes, k)[0][first:last]
+            frm = np.repeat(np.arange(first, last, dtype=np.int32), k)
+            to = np.ascontiguousarray(nbr[first:last].reshape(-1))
+            f, _, _ = self.om.edge_index(nodes, frm, np.maximum(to, 0), clr, cdc)
+            free[first:last] = (f & (to >= 0)).reshape(last - first, k)
+        return torch.from_numpy(nbr), torch.from_numpy(free)
+
+    def csr(self, nodes_t, nbr_t, free_t):
         import ctypes as C
-        n, k = nbr.shape
+        n, k = nbr_t.shape
         row_ptr = np.empty(n + 1, dtype=np.int32)
         col = np.empty(2 * n * k, dtype=np.int32)
         w = np.empty(2 * n * k)
         L = self.orc._L()
         L.orc_csr_from_directed.restype = C.c_int64
-        nn = np.ascontiguousarray(nodes)
-        nb = np.ascontiguousarray(nbr, dtype=np.int32)
-        fr = np.ascontiguousarray(directed_free, dtype=np.uint8)
+        nn = np.ascontiguousarray(nodes_t.numpy())
+        nb = np.ascontiguousarray(nbr_t.numpy(), dtype=np.int32)
+        fr = np.ascontiguousarray(free_t.numpy(), dtype=np.uint8)
         nnz = L.orc_csr_from_directed(nn.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(k), nb.ctypes.data_as(C.c_void_p),
                                       fr.ctypes.data_as(C.c_void_p), row_ptr.ctypes.data_as(C.c_void_p),
                                       col.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p))
-        return row_ptr, col[:nnz], w[:nnz]
+        return (torch.from_numpy(row_ptr), torch.from_numpy(col), torch.from_numpy(w),
+                torch.tensor([0, nnz], dtype=torch.int64))
 
 
 def _worker(rank, world, port, n, tmp):
