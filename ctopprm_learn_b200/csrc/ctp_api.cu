@@ -91,6 +91,8 @@ struct ctp_map {
   int sssp_smem_optin = -1;   // opt-in shared memory per CTA of this device, -1 until the graph kernels were configured
   unsigned knn_smem_set = 0;  // bit K: the dynamic shared-memory limit of the k-NN kernels <K> has been raised
   int64_t pipe_nu_seen = 0;  // largest n_used (candidates consumed by a query) seen by the running pipeline call
+  int64_t csr_pair_cap = 0;   // overflow pairs of the adjacency stage (0 = one per node)
+  int perq_cluster = -1;      // per-query setup / scan kernels on clusters of 8 CTAs: -1 automatic, 0 never, 1 always
   int occ_cache[32] = {0};    // resident CTAs per SM of the edge kernels, per (layout, lanes per edge): see occ_slot
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;    // pool, two per recorded span
@@ -498,6 +500,13 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
       return CTP_OK;
     case CTP_TUNE_KNN_TILE:
       m->knn_tile = value != 0.0;
+      return CTP_OK;
+    case CTP_TUNE_CSR_PAIR_CAP:
+      REQUIRE(value >= 0 && value <= 1e9, "pair capacity must be >= 0");
+      m->csr_pair_cap = (int64_t)value;
+      return CTP_OK;
+    case CTP_TUNE_PERQ_CLUSTER:
+      m->perq_cluster = value < 0 ? -1 : (value != 0.0);
       return CTP_OK;
     case CTP_TUNE_PIPE_HEAD:
       REQUIRE(value >= 0 && value <= 1e6, "head factor must be >= 0");
@@ -1076,6 +1085,30 @@ extern "C" int ctp_sample_ellipsoid_draws(ctp_map *m, const double *start, const
   return CTP_OK;
 }
 
+// Per-query kernels that one CTA per query would leave on a handful of SMs (few queries of very many points) run on a
+// thread-block cluster of 8 CTAs per query instead (ctp_prm.cuh: k_knn_setup, k_knn_scan, k_csr_rowptr).
+#define CTP_PERQ_CL 8
+static inline bool perq_clustered(const ctp_map *m, int64_t q, int64_t len) {
+  if (m->perq_cluster >= 0) return m->perq_cluster != 0 && q * CTP_PERQ_CL < ((int64_t)1 << 30);
+  return q * CTP_PERQ_CL <= 2 * (int64_t)m->sm_count && len >= 16384;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_perq_cluster(void (*kern)(KArgs...), int64_t q, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(q * CTP_PERQ_CL));
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CTP_PERQ_CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // --------------------------------------- k-NN ----------------------------------------------
 // slice (optional, q == 1): {first, last} positions of the cell-sorted order on entry, moved to cell boundaries on
 // return (one 16-byte read back); only the rows of the points at those positions are searched and written
@@ -1093,13 +1126,16 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
   int32_t *d_fbn = arena_take<int32_t>(m->ws, 2);  // [0] ring-search list, [1] direct-search list
   uint8_t *d_fbk = arena_take<uint8_t>(m->ws, total);
   CK(cudaMemsetAsync(d_cnt, 0, (size_t)q * mc * 4, st));
-  k_knn_setup<<<(unsigned)q, 1024, 0, st>>>(nodes, n, mc, m->knn_per_cell, d_grid, d_pts);
+  const bool clustered = perq_clustered(m, q, n);
+  if (clustered) CK(launch_perq_cluster(k_knn_setup<CTP_PERQ_CL>, q, st, nodes, n, mc, m->knn_per_cell, d_grid, d_pts));
+  else k_knn_setup<1><<<(unsigned)q, 1024, 0, st>>>(nodes, n, mc, m->knn_per_cell, d_grid, d_pts);
   m->launches++;
   CK(cudaGetLastError());
   const int blocks = (int)((total + 255) / 256);
   k_knn_count<<<blocks, 256, 0, st>>>(d_pts, n, total, d_grid, mc, d_cell_of, d_cnt);
   m->launches++;
-  k_knn_scan<<<(unsigned)q, 1024, 0, st>>>(d_grid, mc, d_cnt, d_start);
+  if (clustered) CK(launch_perq_cluster(k_knn_scan<CTP_PERQ_CL>, q, st, d_grid, mc, d_cnt, d_start));
+  else k_knn_scan<1><<<(unsigned)q, 1024, 0, st>>>(d_grid, mc, d_cnt, d_start);
   m->launches++;
   k_knn_scatter<<<blocks, 256, 0, st>>>(d_pts, n, total, mc, d_cell_of, d_start, d_cnt, d_sorted);
   m->launches++;
@@ -1205,13 +1241,15 @@ struct CsrScratch {
   uint16_t *rec16;  // null when the ids do not fit 16 bits
   void *xtra;       // rows x CTP_CSR_XCAP parked ids (16-bit with rec16, else 32-bit)
   int32_t *big, *big_cnt;
+  int2 *big_pairs;  // (row, id) of the extra entries that did not fit a row's staging line
+  int pair_cap;
   int32_t *big_tmp; // one line of n + 32 ids per CTA of k_csr_emit_big
   int big_ctas;
 };
 static size_t ws_bytes_csr(int64_t q, int64_t n) {
   const size_t rows = (size_t)q * n;
   return 3 * align_up(rows * 4) + align_up((size_t)q * 8) + align_up(rows * 32) + align_up(rows * CTP_CSR_XCAP * 4) +
-         align_up((size_t)256 * (size_t)(n + 32) * 4) + 1024;
+         align_up(rows * 8) + align_up((size_t)256 * (size_t)(n + 32) * 4) + 2048;
 }
 static CsrScratch csr_scratch_take(ctp_map *m, int64_t q, int64_t n, int k) {
   Arena &a = m->ws;
@@ -1224,7 +1262,10 @@ static CsrScratch csr_scratch_take(ctp_map *m, int64_t q, int64_t n, int k) {
   s.rec16 = small ? arena_take<uint16_t>(a, rows * 16) : nullptr;
   s.xtra = small ? (void *)arena_take<uint16_t>(a, rows * CTP_CSR_XCAP) : (void *)arena_take<int32_t>(a, rows * CTP_CSR_XCAP);
   s.big = arena_take<int32_t>(a, rows);
-  s.big_cnt = arena_take<int32_t>(a, 1);
+  s.big_cnt = arena_take<int32_t>(a, 2);  // [0] rows on the big list, [1] overflow pairs
+  s.pair_cap = (int)std::min<size_t>(rows, (size_t)1 << 26);
+  if (m->csr_pair_cap > 0) s.pair_cap = (int)std::min<int64_t>(s.pair_cap, m->csr_pair_cap);
+  s.big_pairs = arena_take<int2>(a, (size_t)s.pair_cap);
   s.big_ctas = std::max(1, std::min(m->sm_count, 256));
   s.big_tmp = arena_take<int32_t>(a, (size_t)s.big_ctas * (size_t)(n + 32));
   return s;
@@ -1240,7 +1281,7 @@ static int csr_emit(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k
   if (csr_flags & CTP_CSR_NO_WEIGHTS) w = nullptr;
   StageSpan span(m, CTP_STAGE_CSR, st);
   const int rb = (int)((rows + 255) / 256);
-  CK(cudaMemsetAsync(sc.big_cnt, 0, 4, st));
+  CK(cudaMemsetAsync(sc.big_cnt, 0, 8, st));
   CK(cudaMemsetAsync(sc.xcnt, 0, (size_t)rows * 4, st));
   CsrSplit sp;
   sp.small = edges < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
@@ -1249,13 +1290,14 @@ static int csr_emit(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k
   k_csr_rowmask<<<rb, 256, 0, st>>>(d_free, n, k, ns, rows, sp, upper, d_rec, sc.own, sc.rec16);
   m->launches++;
   if (sc.rec16)
-    k_csr_count<16, uint16_t, true><<<rb, 256, 0, st>>>(d_rec, sc.rec16, n, k, rows, sp, upper, sc.xcnt, (uint16_t *)sc.xtra, sc.big, sc.big_cnt);
+    k_csr_count<16, uint16_t, true><<<rb, 256, 0, st>>>(d_rec, sc.rec16, n, k, rows, sp, upper, sc.xcnt, (uint16_t *)sc.xtra, sc.big, sc.big_cnt, sc.big_pairs, sc.pair_cap);
   else if (ns == 16)
-    k_csr_count<16, int32_t, false><<<rb, 256, 0, st>>>(d_rec, nullptr, n, k, rows, sp, upper, sc.xcnt, (int32_t *)sc.xtra, sc.big, sc.big_cnt);
+    k_csr_count<16, int32_t, false><<<rb, 256, 0, st>>>(d_rec, nullptr, n, k, rows, sp, upper, sc.xcnt, (int32_t *)sc.xtra, sc.big, sc.big_cnt, sc.big_pairs, sc.pair_cap);
   else
-    k_csr_count<32, int32_t, false><<<rb, 256, 0, st>>>(d_rec, nullptr, n, k, rows, sp, upper, sc.xcnt, (int32_t *)sc.xtra, sc.big, sc.big_cnt);
+    k_csr_count<32, int32_t, false><<<rb, 256, 0, st>>>(d_rec, nullptr, n, k, rows, sp, upper, sc.xcnt, (int32_t *)sc.xtra, sc.big, sc.big_cnt, sc.big_pairs, sc.pair_cap);
   m->launches++;
-  k_csr_rowptr<<<(unsigned)q, 1024, 0, st>>>(sc.own, sc.xcnt, n, row_ptr, sc.nnz);
+  if (perq_clustered(m, q, n)) CK(launch_perq_cluster(k_csr_rowptr<CTP_PERQ_CL>, q, st, sc.own, sc.xcnt, n, row_ptr, sc.nnz));
+  else k_csr_rowptr<1><<<(unsigned)q, 1024, 0, st>>>(sc.own, sc.xcnt, n, row_ptr, sc.nnz);
   m->launches++;
   k_csr_query_offsets<<<1, 1024, 0, st>>>(sc.nnz, q, nnz_off);
   m->launches++;
@@ -1268,8 +1310,12 @@ static int csr_emit(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k
   else
     k_csr_emit<32, int32_t><<<eb, CTP_CSR_EMIT_ROWS, 0, st>>>(nodes, d_rec, nullptr, (const int32_t *)sc.xtra, n, k, rows, sp, upper, row_ptr, nnz_off, tcap, col, w);
   m->launches++;
-  if (ns == 16) k_csr_emit_big<16><<<sc.big_ctas, 256, 0, st>>>(nodes, d_rec, n, k, sp, upper, sc.big, sc.big_cnt, row_ptr, nnz_off, tcap, sc.big_tmp, col, w);
-  else k_csr_emit_big<32><<<sc.big_ctas, 256, 0, st>>>(nodes, d_rec, n, k, sp, upper, sc.big, sc.big_cnt, row_ptr, nnz_off, tcap, sc.big_tmp, col, w);
+  if (sc.rec16)
+    k_csr_emit_big<16, uint16_t><<<sc.big_ctas, 256, 0, st>>>(nodes, d_rec, n, k, sp, upper, sc.big, sc.big_cnt, (const uint16_t *)sc.xtra, sc.big_pairs, sc.pair_cap, row_ptr, nnz_off, tcap, sc.big_tmp, col, w);
+  else if (ns == 16)
+    k_csr_emit_big<16, int32_t><<<sc.big_ctas, 256, 0, st>>>(nodes, d_rec, n, k, sp, upper, sc.big, sc.big_cnt, (const int32_t *)sc.xtra, sc.big_pairs, sc.pair_cap, row_ptr, nnz_off, tcap, sc.big_tmp, col, w);
+  else
+    k_csr_emit_big<32, int32_t><<<sc.big_ctas, 256, 0, st>>>(nodes, d_rec, n, k, sp, upper, sc.big, sc.big_cnt, (const int32_t *)sc.xtra, sc.big_pairs, sc.pair_cap, row_ptr, nnz_off, tcap, sc.big_tmp, col, w);
   m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;

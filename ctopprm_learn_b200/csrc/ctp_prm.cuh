@@ -3,6 +3,7 @@
 // exact float32 k-NN on a uniform grid, symmetric CSR emit.  All kernels are batched over
 // q independent queries (blockIdx.y or a flat q*n index).
 #pragma once
+#include <cooperative_groups.h>
 #include "ctp_device.cuh"
 
 // =========================== rejection sampling (:299-327) ================================
@@ -134,13 +135,20 @@ __device__ __forceinline__ int knn_cell_1d(float x, float lo, float inv_h, int d
 // points actually fill (an ellipsoid clipped by the map and by obstacles fills a third of its
 // box or less), then a cell size h such that a ball of radius h is expected to hold `in_ball`
 // points -- the quantity the tile search's completeness test depends on.
+// CL > 1: one thread-block cluster of CL CTAs per query (few queries of many points would otherwise leave this kernel
+// on a handful of SMs): each CTA takes a strided share of the points, boxes and occupancy bitmaps meet through
+// distributed shared memory.
+template <int CL>
 __global__ void __launch_bounds__(1024) k_knn_setup(const double *__restrict__ nodes, int64_t n,
                                                     int max_cells, double in_ball,
                                                     KnnGrid *__restrict__ grids, float4 *__restrict__ pts) {
-  const int64_t q = blockIdx.x;
+  namespace cg = cooperative_groups;
+  const int64_t q = blockIdx.x / CL;
+  const int rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
+  const int64_t first = (int64_t)rank * blockDim.x + threadIdx.x, stride = (int64_t)CL * blockDim.x;
   const double *nq = nodes + 3 * q * n;
   float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int64_t i = first; i < n; i += stride) {
     const float x = (float)nq[3 * i], y = (float)nq[3 * i + 1], z = (float)nq[3 * i + 2];
     pts[q * n + i] = make_float4(x, y, z, __int_as_float((int)i));
     lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x);
@@ -148,6 +156,7 @@ __global__ void __launch_bounds__(1024) k_knn_setup(const double *__restrict__ n
     lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
   }
   __shared__ float s_lo[3][32], s_hi[3][32];
+  __shared__ float s_box[6];  // this CTA's box, read by the other CTAs of the cluster
   __shared__ float s_blo[3], s_binv[3];
   __shared__ int s_bg[3];
   __shared__ unsigned s_occ[128];  // up to 16^3 coarse cells
@@ -163,9 +172,19 @@ __global__ void __launch_bounds__(1024) k_knn_setup(const double *__restrict__ n
   if (threadIdx.x < 128) s_occ[threadIdx.x] = 0;
   __syncthreads();
   const int nw = (blockDim.x + 31) / 32;
+  for (int a = 0; a < 3; a++)
+    for (int w = 0; w < nw; w++) { lo[a] = fminf(lo[a], s_lo[a][w]); hi[a] = fmaxf(hi[a], s_hi[a][w]); }
+  if (CL > 1) {
+    if (threadIdx.x == 0)
+      for (int a = 0; a < 3; a++) { s_box[a] = lo[a]; s_box[3 + a] = hi[a]; }
+    cg::this_cluster().sync();
+    for (int r = 0; r < CL; r++) {
+      const float *ob = cg::this_cluster().map_shared_rank(s_box, r);
+      for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], ob[a]); hi[a] = fmaxf(hi[a], ob[3 + a]); }
+    }
+  }
   double e[3], emax = 0;
   for (int a = 0; a < 3; a++) {
-    for (int w = 0; w < nw; w++) { lo[a] = fminf(lo[a], s_lo[a][w]); hi[a] = fmaxf(hi[a], s_hi[a][w]); }
     e[a] = (double)hi[a] - (double)lo[a];
     if (!(e[a] >= 0)) e[a] = 0;  // NaN coordinates
     emax = fmax(emax, e[a]);
@@ -181,7 +200,7 @@ __global__ void __launch_bounds__(1024) k_knn_setup(const double *__restrict__ n
     }
   }
   __syncthreads();
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int64_t i = first; i < n; i += stride) {
     const float4 p = pts[q * n + i];
     const int cx = min(max((int)((p.x - s_blo[0]) * s_binv[0]), 0), s_bg[0] - 1);
     const int cy = min(max((int)((p.y - s_blo[1]) * s_binv[1]), 0), s_bg[1] - 1);
@@ -190,9 +209,15 @@ __global__ void __launch_bounds__(1024) k_knn_setup(const double *__restrict__ n
     atomicOr(&s_occ[c >> 5], 1u << (c & 31));
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (CL > 1) cg::this_cluster().sync();
+  if (threadIdx.x == 0 && rank == 0) {
     int occ = 0;
-    for (int w = 0; w < 128; w++) occ += __popc(s_occ[w]);
+    for (int w = 0; w < 128; w++) {
+      unsigned bits = s_occ[w];
+      if (CL > 1)
+        for (int r = 1; r < CL; r++) bits |= cg::this_cluster().map_shared_rank(s_occ, r)[w];
+      occ += __popc(bits);
+    }
     if (occ < 1) occ = 1;
     // D-dimensional measure of the occupied coarse cells and the radius whose D-ball holds in_ball points
     int D = 0;
@@ -225,6 +250,7 @@ __global__ void __launch_bounds__(1024) k_knn_setup(const double *__restrict__ n
     g.ncell = d[0] * d[1] * d[2];
     grids[q] = g;
   }
+  if (CL > 1) cg::this_cluster().sync();  // rank 0 reads the other CTAs' bitmaps: nobody leaves before it is done
 }
 
 __global__ void __launch_bounds__(256) k_knn_count(const float4 *__restrict__ pts, int64_t n, int64_t total,
@@ -241,49 +267,85 @@ __global__ void __launch_bounds__(256) k_knn_count(const float4 *__restrict__ pt
   atomicAdd(cell_cnt + q * cell_stride + c, 1);
 }
 
-// one CTA per query: exclusive scan of cell counts -> cell_start (ncell+1 entries)
-__global__ void __launch_bounds__(1024) k_knn_scan(const KnnGrid *__restrict__ grids, int cell_stride,
-                                                   int32_t *__restrict__ cell_cnt, int32_t *__restrict__ cell_start) {
+// exclusive scan of a 1024-wide tile: returns this thread's inclusive prefix; wsum[31] holds the tile total afterwards
+__device__ __forceinline__ int cta_scan_1024(int v, int *wsum) {
+  int s = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) >= o) s += t;
+  }
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = wsum[threadIdx.x];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (threadIdx.x >= o) w += t;
+    }
+    wsum[threadIdx.x] = w;
+  }
+  __syncthreads();
+  return s + ((threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0);
+}
+
+// Exclusive scan of `len` values of one query by one CTA (CL == 1) or by a cluster of CL CTAs: each CTA scans a
+// contiguous chunk, the chunk totals meet through distributed shared memory and a second sweep adds the offset.
+// value(i) reads element i, store(i, prefix) writes it.  Returns the grand total (valid in every thread).
+template <int CL, typename Value, typename Store, typename Add>
+__device__ __forceinline__ long long cluster_excl_scan(int rank, int64_t len, Value value, Store store, Add add_offset) {
+  namespace cg = cooperative_groups;
   __shared__ int wsum[32];
   __shared__ int carry;
-  const int64_t q = blockIdx.x;
+  __shared__ int s_total;
+  const int64_t chunk = CL > 1 ? ((len + CL - 1) / CL + 1023) / 1024 * 1024 : len;
+  const int64_t lo = CL > 1 ? (rank * chunk < len ? rank * chunk : len) : 0;
+  const int64_t hi = CL > 1 ? (lo + chunk < len ? lo + chunk : len) : len;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = lo; base < hi; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const int v = i < hi ? value(i) : 0;
+    const int incl = cta_scan_1024(v, wsum);
+    const int c = carry;
+    if (i < hi) store(i, c + incl - v);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + incl;
+    __syncthreads();
+  }
+  if (CL == 1) return carry;
+  if (threadIdx.x == 0) s_total = carry;
+  cg::this_cluster().sync();
+  int off = 0, total = 0;
+  for (int r = 0; r < CL; r++) {
+    const int t = *cg::this_cluster().map_shared_rank(&s_total, r);
+    off += r < rank ? t : 0;
+    total += t;
+  }
+  cg::this_cluster().sync();  // every CTA has read the totals before anyone may exit
+  if (off)
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 1024) add_offset(i, off);
+  return total;
+}
+
+// per query: exclusive scan of cell counts -> cell_start (ncell+1 entries); CL CTAs (a cluster) per query
+template <int CL>
+__global__ void __launch_bounds__(1024) k_knn_scan(const KnnGrid *__restrict__ grids, int cell_stride,
+                                                   int32_t *__restrict__ cell_cnt, int32_t *__restrict__ cell_start) {
+  const int64_t q = blockIdx.x / CL;
+  const int rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
   const int ncell = grids[q].ncell;
   int32_t *cnt = cell_cnt + q * cell_stride;
   int32_t *st = cell_start + q * (cell_stride + 1);
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < ncell; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = i < ncell ? cnt[i] : 0;
-    int s = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, s, o);
-      if ((threadIdx.x & 31) >= o) s += t;
-    }
-    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int w = wsum[threadIdx.x];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, o);
-        if (threadIdx.x >= o) w += t;
-      }
-      wsum[threadIdx.x] = w;
-    }
-    __syncthreads();
-    const int woff = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
-    const int c = carry;
-    if (i < ncell) {
-      st[i] = c + woff + s - v;
-      cnt[i] = 0;  // becomes the scatter cursor
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = c + woff + s;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) st[ncell] = carry;
+  const long long total = cluster_excl_scan<CL>(
+      rank, ncell, [&](int64_t i) { return cnt[i]; },
+      [&](int64_t i, int pre) {
+        st[i] = pre;
+        cnt[i] = 0;  // becomes the scatter cursor
+      },
+      [&](int64_t i, int off) { st[i] += off; });
+  if (threadIdx.x == 0 && rank == 0) st[ncell] = (int32_t)total;
 }
 
 __global__ void __launch_bounds__(256) k_knn_scatter(const float4 *__restrict__ pts, int64_t n, int64_t total,
@@ -830,7 +892,8 @@ template <int NS, typename XT, bool R16>
 __global__ void __launch_bounds__(256) k_csr_count(const int32_t *__restrict__ rec, const uint16_t *__restrict__ rec16,
                                                    int64_t n, int k, int64_t total_rows, CsrSplit sp, int upper,
                                                    int32_t *__restrict__ xcnt, XT *__restrict__ xtra,
-                                                   int32_t *__restrict__ big_list, int32_t *__restrict__ big_cnt) {
+                                                   int32_t *__restrict__ big_list, int32_t *__restrict__ big_cnt,
+                                                   int2 *__restrict__ big_pairs, int pair_cap) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (row >= total_rows) return;
   const int64_t q = csr_row_query(row, n, sp);
@@ -887,53 +950,31 @@ __global__ void __launch_bounds__(256) k_csr_count(const int32_t *__restrict__ r
       if (!((mask >> (s0 + u)) & 1u) || rev[u]) continue;
       const int j = ids[s0 + u];
       const int pos = atomicAdd(xcnt + qbase + j, 1);
-      if (pos < CTP_CSR_XCAP) xtra[(qbase + j) * CTP_CSR_XCAP + pos] = (XT)i;
-      else if (pos == CTP_CSR_XCAP) big_list[atomicAdd(big_cnt, 1)] = (int32_t)(qbase + j);
+      if (pos < CTP_CSR_XCAP) {
+        xtra[(qbase + j) * CTP_CSR_XCAP + pos] = (XT)i;
+      } else {  // the line is full: row j goes on the `big` list once, the id into the overflow pairs
+        if (pos == CTP_CSR_XCAP) big_list[atomicAdd(big_cnt, 1)] = (int32_t)(qbase + j);
+        const int p = atomicAdd(big_cnt + 1, 1);
+        if (p < pair_cap) big_pairs[p] = make_int2((int)(qbase + j), i);
+      }
     }
   }
 }
 
-// one CTA per query: row_ptr (relative) = exclusive scan of degrees; nnz per query
+// per query: row_ptr (relative) = exclusive scan of degrees; nnz per query; CL CTAs (a cluster) per query
+template <int CL>
 __global__ void __launch_bounds__(1024) k_csr_rowptr(const int32_t *__restrict__ own, const int32_t *__restrict__ xcnt,
                                                      int64_t n, int32_t *__restrict__ row_ptr, int64_t *__restrict__ nnz) {
-  __shared__ int wsum[32];
-  __shared__ int carry;
-  const int64_t q = blockIdx.x;
+  const int64_t q = blockIdx.x / CL;
+  const int rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
   const int32_t *dq = own + q * n, *xq = xcnt + q * n;
   int32_t *rp = row_ptr + q * (n + 1);
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int64_t base = 0; base < n; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const int v = i < n ? dq[i] + xq[i] : 0;
-    int s = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, s, o);
-      if ((threadIdx.x & 31) >= o) s += t;
-    }
-    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int w = wsum[threadIdx.x];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, o);
-        if (threadIdx.x >= o) w += t;
-      }
-      wsum[threadIdx.x] = w;
-    }
-    __syncthreads();
-    const int woff = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
-    const int c = carry;
-    if (i < n) rp[i] = c + woff + s - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = c + woff + s;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    rp[n] = carry;
-    nnz[q] = carry;
+  const long long total = cluster_excl_scan<CL>(
+      rank, n, [&](int64_t i) { return dq[i] + xq[i]; }, [&](int64_t i, int pre) { rp[i] = pre; },
+      [&](int64_t i, int off) { rp[i] += off; });
+  if (threadIdx.x == 0 && rank == 0) {
+    rp[n] = (int32_t)total;
+    nnz[q] = total;
   }
 }
 
@@ -1141,13 +1182,17 @@ k_csr_emit(const double *__restrict__ nodes, const int32_t *__restrict__ rec, co
 }
 
 // Rows with more than CTP_CSR_XCAP extra entries (a node many others list without being listed back: never seen
-// on sampled roadmaps, but legal).  One CTA per listed row j: own free ids, then every i of the query whose record
-// lists j free while j's does not list i, collected straight into the row's col range; ranked into order through
-// a per-CTA scratch line (tmp: gridDim.x lines of n + 32 ids); weights last.
-template <int NS>
+// on roadmaps of 10^4 nodes, a few per query at 10^6).  One CTA per listed row j: own free ids, the ids parked in
+// its staging line, then those that overflowed it (the pair list k_csr_count appended to; should that list itself
+// have overflowed: every i of the query whose record lists j free while j's does not list i), collected straight into
+// the row's col range; ranked into order through a per-CTA scratch line (tmp: gridDim.x lines of n + 32 ids);
+// weights last.
+template <int NS, typename XT>
 __global__ void __launch_bounds__(256) k_csr_emit_big(const double *__restrict__ nodes, const int32_t *__restrict__ rec,
                                                       int64_t n, int k, CsrSplit sp, int upper, const int32_t *__restrict__ big_list,
-                                                      const int32_t *__restrict__ big_cnt, const int32_t *__restrict__ row_ptr,
+                                                      const int32_t *__restrict__ big_cnt, const XT *__restrict__ xtra,
+                                                      const int2 *__restrict__ big_pairs, int pair_cap,
+                                                      const int32_t *__restrict__ row_ptr,
                                                       const int64_t *__restrict__ nnz_off, int64_t cap,
                                                       int32_t *__restrict__ tmp_all, int32_t *__restrict__ col,
                                                       double *__restrict__ w) {
@@ -1171,6 +1216,15 @@ __global__ void __launch_bounds__(256) k_csr_emit_big(const double *__restrict__
       s_fill = c;
     }
     __syncthreads();
+    const int npair = big_cnt[1];
+    if (npair <= pair_cap) {
+      for (int x = threadIdx.x; x < CTP_CSR_XCAP; x += blockDim.x)
+        col[gb + atomicAdd(&s_fill, 1)] = (int32_t)xtra[row * CTP_CSR_XCAP + x];
+      for (int p = threadIdx.x; p < npair; p += blockDim.x) {
+        const int2 pr = big_pairs[p];
+        if (pr.x == (int)row) col[gb + atomicAdd(&s_fill, 1)] = pr.y;
+      }
+    } else
     for (int64_t i = (upper ? j + 1 : 0) + threadIdx.x; i < n; i += blockDim.x) {
       const int32_t *ri = rec + (qbase + i) * NS;
       const unsigned mi = (unsigned)ri[NS - 1] & kmask;

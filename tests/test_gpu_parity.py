@@ -1277,14 +1277,38 @@ def test_adjacency_rows_with_many_incoming_edges(c1):
                     row[s_] = (row[s_] + 11) % n
     fr = (rng.random((2, n, k)) < 0.85).astype(np.uint8)
     fr[:, 3:400, 0] = 1
-    got = m.csr_from_directed(nodes, nbr, fr)
-    for qi in range(2):
-        rp, col, w = _union_csr(nodes[qi], nbr[qi], fr[qi])
-        a, b = int(got["nnz_off"][qi]), int(got["nnz_off"][qi + 1])
-        assert np.array_equal(got["row_ptr"][qi], rp)
-        assert np.array_equal(got["col"][a:b], col)
-        assert np.array_equal(got["w"][a:b], w)
-    assert got["row_ptr"][0][1] - got["row_ptr"][0][0] > 300
+    for pair_cap in (0, 8):  # ids past a row's staging line: from the overflow list, or (list too small) by a full scan
+        m.set_tunable(capi.TUNE_CSR_PAIR_CAP, pair_cap)
+        try:
+            got = m.csr_from_directed(nodes, nbr, fr)
+        finally:
+            m.set_tunable(capi.TUNE_CSR_PAIR_CAP, 0)
+        for qi in range(2):
+            rp, col, w = _union_csr(nodes[qi], nbr[qi], fr[qi])
+            a, b = int(got["nnz_off"][qi]), int(got["nnz_off"][qi + 1])
+            assert np.array_equal(got["row_ptr"][qi], rp)
+            assert np.array_equal(got["col"][a:b], col)
+            assert np.array_equal(got["w"][a:b], w)
+        assert got["row_ptr"][0][1] - got["row_ptr"][0][0] > 300
+
+
+@pytest.mark.parametrize("n", [700, 20000])
+def test_per_query_kernels_on_clusters(c1, n):
+    """grid setup, cell scan and row-offset scan of a query on a cluster of 8 CTAs (automatic for few large queries,
+    forced here at both sizes) give the roadmap of the one-CTA kernels"""
+    m, om, c, e = c1
+    s, g, cand = _queries(c, e, 2, n, 71)
+    nodes = m.sample_reject(s, g, cand, CLR, n)[0]
+    outs = []
+    for mode in (0, 1):
+        m.set_tunable(capi.TUNE_PERQ_CLUSTER, mode)
+        try:
+            outs.append(m.build_prm(nodes, CLR, CDC))
+        finally:
+            m.set_tunable(capi.TUNE_PERQ_CLUSTER, -1)
+    for key in ("nbr", "directed_free", "row_ptr", "col", "w", "nnz_off"):
+        assert np.array_equal(outs[0][key], outs[1][key]), key
+    _csr_equal(outs[1], 0, om.build_prm(nodes[0], CLR, CDC, nthreads=8))
 
 
 def test_missing_neighbour_marked_free_is_ignored(c1):
