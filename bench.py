@@ -660,8 +660,11 @@ def run_microbench(args, rank, world):
     layouts = {"auto": capi.DEFAULT_LAYOUT, "plain": capi.LAYOUT_PLAIN, "cell8": capi.LAYOUT_CELL8, "tex": capi.LAYOUT_TEX,
                "brick": capi.LAYOUT_BRICK}
     layout = layouts[args.layout]
-    dmap = capi.DeviceMap(vox, c, e, device=local, layouts=layout | capi.LAYOUT_PLAIN)
+    extra = capi.LAYOUT_CELL8 if args.layout == "auto" and vox.nbytes > (100 << 20) and not args.no_cell8 else 0
+    dmap = capi.DeviceMap(vox, c, e, device=local, layouts=layout | capi.LAYOUT_PLAIN | extra)
     dmap.set_layout(layout)
+    if args.seg_bin != -1:
+        dmap.set_tunable(capi.TUNE_SEG_BIN, args.seg_bin)
     m_e = args.mu_edges
     a_h, b_h = synth.random_edges(c, e, m_e, 1000 + rank)
     a_d, b_d = torch.from_numpy(a_h).to(dev), torch.from_numpy(b_h).to(dev)
@@ -763,7 +766,9 @@ def run_microbench(args, rank, world):
                 "data": "synthetic",
                 "config": {"workload": f"MU: gather-kernel microbench, {m_e} random directed segments per GPU per step (length "
                                        f"U[0.2, 1.5] m) on the {args.mu_map} map ({vox.shape[0]}^3 voxels), one ctp_edge_check_dev "
-                                       "call per step", "segments_per_step_per_gpu": m_e, "layout": dmap.layout_name(),
+                                       "call per step", "segments_per_step_per_gpu": m_e,
+                           "layout": dmap.layout_name() + (" set; the library reads the CELL8 records for large unordered batches on grids beyond the L2" if extra and args.seg_bin == -1 else ""),
+                           "seg_bin": args.seg_bin,
                            "min_clearance": clr, "collision_distance_check": cdc,
                            "l2": f"endpoints ({m_e * 48 >> 20} MiB per step) exceed the 126 MB L2; the grid is re-read by design"},
                 "lookups_per_s": lookups / (ms_max * 1e-3), "lookups_per_segment": lookups / args.steps / m_e,
@@ -891,6 +896,7 @@ def main():
     ap.add_argument("--map-graphs", action="store_true", help="C5: replay each map's batch from a CUDA graph (measured: no gain, the sweep is not launch-bound)")
     ap.add_argument("--map-threads", type=int, default=4, help="C5 e2e: host threads driving the map handles")
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (default: per workload)")
+    ap.add_argument("--seg-bin", type=int, default=-1, help="MU: bin the segments by voxel block first (1), never (0), library default (-1)")
     ap.add_argument("--shard-query", action="store_true", help="one query of the workload's size split over all GPUs (strong scaling)")
     ap.add_argument("--nodes", type=int, default=0, help="--shard-query: nodes of the query (default: the workload's)")
     ap.add_argument("--layout", default="auto", choices=["auto", "plain", "cell8", "tex", "brick"])

@@ -91,6 +91,7 @@ struct ctp_map {
   int sssp_smem_optin = -1;   // opt-in shared memory per CTA of this device, -1 until the graph kernels were configured
   unsigned knn_smem_set = 0;  // bit K: the dynamic shared-memory limit of the k-NN kernels <K> has been raised
   int64_t pipe_nu_seen = 0;  // largest n_used (candidates consumed by a query) seen by the running pipeline call
+  int seg_bin = -1;           // ctp_edge_check: bin large batches by voxel block first: -1 automatic, 0 never, 1 always
   int64_t csr_pair_cap = 0;   // overflow pairs of the adjacency stage (0 = one per node)
   int perq_cluster = -1;      // per-query setup / scan kernels on clusters of 8 CTAs: -1 automatic, 0 never, 1 always
   int occ_cache[32] = {0};    // resident CTAs per SM of the edge kernels, per (layout, lanes per edge): see occ_slot
@@ -501,6 +502,9 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
     case CTP_TUNE_KNN_TILE:
       m->knn_tile = value != 0.0;
       return CTP_OK;
+    case CTP_TUNE_SEG_BIN:
+      m->seg_bin = value < 0 ? -1 : (value != 0.0);
+      return CTP_OK;
     case CTP_TUNE_CSR_PAIR_CAP:
       REQUIRE(value >= 0 && value <= 1e9, "pair capacity must be >= 0");
       m->csr_pair_cap = (int64_t)value;
@@ -614,6 +618,30 @@ extern "C" int ctp_host_free(void *ptr) {
     case CTP_L_TEX:   { constexpr int L = CTP_L_TEX;   __VA_ARGS__; } break;   \
     default:          { constexpr int L = CTP_L_BRICK; __VA_ARGS__; } break;   \
   }
+
+// Per-query kernels that one CTA per query would leave on a handful of SMs (few queries of very many points) run on a
+// thread-block cluster of 8 CTAs per query instead (ctp_prm.cuh: k_knn_setup, k_knn_scan, k_csr_rowptr).
+#define CTP_PERQ_CL 8
+static inline bool perq_clustered(const ctp_map *m, int64_t q, int64_t len) {
+  if (m->perq_cluster >= 0) return m->perq_cluster != 0 && q * CTP_PERQ_CL < ((int64_t)1 << 30);
+  return q * CTP_PERQ_CL <= 2 * (int64_t)m->sm_count && len >= 16384;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_perq_cluster(void (*kern)(KArgs...), int64_t q, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(q * CTP_PERQ_CL));
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CTP_PERQ_CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 static inline int grid_for(int64_t items, int block, int cap_blocks) {
   int64_t g = (items + block - 1) / block;
@@ -798,7 +826,43 @@ extern "C" int ctp_edge_check_dev(ctp_map *m, const double *a, const double *b, 
   CK(cudaSetDevice(m->device));
   EdgeSrc S{a, b, nullptr, nullptr, 0, 0, 0, 0, nullptr};
   EdgeOut O{free_out, hit, hit_idx, lookups, m->d_lookups};
-  return launch_edges(m, group ? group : 16, S, cnt, clr, cdc, mode == CTP_EDGE_GUARDS, O, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  // A large unordered batch on a grid beyond the L2 reads the one-sector CELL8 records where they exist (isolated
+  // lookups pay for every sector a layout touches: 2^24 random segments on the 1024^3 grid 5.8 ms on the gather texture,
+  // 4.6 ms on CELL8).  Binning the segments by the voxel block of their midpoint first (CTP_TUNE_SEG_BIN) is available
+  // but off by default: measured on the same batch it does not pay (5.6 ms texture, 5.6 ms CELL8, 4.3 ms BRICK) -- the
+  // kernel is bound by per-segment setup and wasted speculative samples, not by DRAM or TLB misses, and the
+  // indirection un-coalesces the endpoint loads and the verdict stores.
+  const bool big_grid = (size_t)m->n * m->n * m->n * 4 > ((size_t)100 << 20);
+  const bool bin = m->seg_bin > 0;
+  const int active_keep = m->active;
+  const size_t keep = m->ws.used;
+  if (bin && cnt < ((int64_t)1 << 31)) {
+    const unsigned nb = (unsigned)((m->n + (1 << CTP_BIN_SHIFT) - 1) >> CTP_BIN_SHIFT);
+    int bits = 0;
+    while ((1u << bits) < nb) bits++;
+    if (bits <= 8) {
+      const int64_t nkeys = (int64_t)1 << (3 * bits);
+      CKR(arena_reserve(m->ws, keep + 2 * align_up(cnt * 4) + 2 * align_up((nkeys + 1) * 4) + 4096));
+      unsigned *d_key = arena_take<unsigned>(m->ws, cnt);
+      int32_t *d_perm = arena_take<int32_t>(m->ws, cnt);
+      int32_t *d_cnt = arena_take<int32_t>(m->ws, nkeys + 1), *d_start = arena_take<int32_t>(m->ws, nkeys + 1);
+      m->ws.used = keep;  // dead once the kernels below have run (stream order)
+      CK(cudaMemsetAsync(d_cnt, 0, (size_t)nkeys * 4, st));
+      const int blocks = (int)((cnt + 255) / 256);
+      k_seg_bin_count<<<blocks, 256, 0, st>>>(m->dev, a, b, cnt, nb, d_key, d_cnt);
+      if (nkeys >= 16384) CK(launch_perq_cluster(k_excl_scan_i32<CTP_PERQ_CL>, 1, st, d_cnt, nkeys, d_start));
+      else k_excl_scan_i32<1><<<1, 1024, 0, st>>>(d_cnt, nkeys, d_start);
+      k_seg_bin_scatter<<<blocks, 256, 0, st>>>(d_key, cnt, d_start, d_cnt, d_perm);
+      m->launches += 3;
+      CK(cudaGetLastError());
+      S.perm = d_perm;
+    }
+  }
+  if (m->seg_bin < 0 && big_grid && cnt >= 65536 && m->reject_layout_auto && (m->layouts & CTP_L_CELL8)) m->active = CTP_L_CELL8;
+  const int rc = launch_edges(m, group ? group : 16, S, cnt, clr, cdc, mode == CTP_EDGE_GUARDS, O, st);
+  m->active = active_keep;
+  return rc;
 }
 
 extern "C" int ctp_edge_check_indexed_dev(ctp_map *m, const double *nodes, int64_t n_nodes, const int32_t *from,
@@ -1083,30 +1147,6 @@ extern "C" int ctp_sample_ellipsoid_draws(ctp_map *m, const double *start, const
   CK(cudaMemcpyAsync(draws, d_d, q * cnt * 32, cudaMemcpyDeviceToHost, 0));
   CK(cudaStreamSynchronize(0));
   return CTP_OK;
-}
-
-// Per-query kernels that one CTA per query would leave on a handful of SMs (few queries of very many points) run on a
-// thread-block cluster of 8 CTAs per query instead (ctp_prm.cuh: k_knn_setup, k_knn_scan, k_csr_rowptr).
-#define CTP_PERQ_CL 8
-static inline bool perq_clustered(const ctp_map *m, int64_t q, int64_t len) {
-  if (m->perq_cluster >= 0) return m->perq_cluster != 0 && q * CTP_PERQ_CL < ((int64_t)1 << 30);
-  return q * CTP_PERQ_CL <= 2 * (int64_t)m->sm_count && len >= 16384;
-}
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_perq_cluster(void (*kern)(KArgs...), int64_t q, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(q * CTP_PERQ_CL));
-  cfg.blockDim = dim3(1024);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CTP_PERQ_CL;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // --------------------------------------- k-NN ----------------------------------------------

@@ -274,10 +274,14 @@ struct EdgeSrc {
                         // through neighbouring voxels; outputs stay indexed by the original edge number
   CtpDiv dk, dn;        // from == NULL: division by k and by n (valid when small != 0)
   int small;            // every edge index of the launch is below 2^31
+  const int32_t *perm;  // pairs mode, optional: work item i takes segment perm[i] (segments binned by the voxel
+                        // block of their midpoint, so that neighbouring work items read neighbouring voxels);
+                        // outputs stay indexed by the segment number
 };
 
 // work item -> edge number (identity unless S.order is set)
 __device__ __forceinline__ int64_t ctp_edge_of_item(const EdgeSrc &S, int64_t item) {
+  if (S.perm) return S.perm[item];
   if (!S.order) return item;
   int64_t r, qbase;
   if (S.small) {
@@ -379,7 +383,8 @@ __global__ void __launch_bounds__(256) k_edge_march(MapDev M, EdgeSrc S, int64_t
   const int gshift = lane - sub;
   const unsigned gmask = (G == 32) ? full : ((1u << G) - 1u);
   const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
-  int64_t e = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G - n_groups;
+  int64_t item = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G - n_groups;
+  int64_t e = 0;  // the segment the group is marching (= item unless the launch is permuted)
 
   bool active = false;
   double ax = 0, ay = 0, az = 0, vx = 0, vy = 0, vz = 0, npts = 1.0;
@@ -389,8 +394,9 @@ __global__ void __launch_bounds__(256) k_edge_march(MapDev M, EdgeSrc S, int64_t
   for (;;) {
     if (!active) {
       for (;;) {
-        e += n_groups;
-        if (e >= m) break;
+        item += n_groups;
+        if (item >= m) break;
+        e = S.perm ? (int64_t)S.perm[item] : item;
         const int state = ctp_arm_edge(S, e, guards, cdc, ax, ay, az, vx, vy, vz, npts, n_last);
         if (state != 0) {
           if (sub == 0) {
@@ -603,6 +609,50 @@ __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, Edg
     for (int o = 16; o > 0; o >>= 1) my_lookups += __shfl_xor_sync(full, my_lookups, o);
     if (lane == 0 && my_lookups) atomicAdd(O.total_lookups, my_lookups);
   }
+}
+
+// ---- binning of generic segments ---------------------------------------------------------------
+// Segments handed to ctp_edge_check come in no particular order; on a grid beyond the L2 (and the TLB reach) every
+// lookup of every segment is then a DRAM access to a cold page.  Key = Morton code of the 16^3-voxel block that holds
+// the segment's midpoint: after a counting sort on it the segments a warp (and its neighbours on the SM, and the SMs
+// next to it) work on lie in one corner of the map.  Outputs are written by segment number, so the order of the
+// segments inside a bin (decided by atomics) does not show.
+#define CTP_BIN_SHIFT 4
+__device__ __forceinline__ unsigned ctp_morton3(unsigned x, unsigned y, unsigned z) {
+  unsigned key = 0;
+#pragma unroll
+  for (int b = 0; b < 8; b++) key |= ((x >> b) & 1u) << (3 * b) | ((y >> b) & 1u) << (3 * b + 1) | ((z >> b) & 1u) << (3 * b + 2);
+  return key;
+}
+__device__ __forceinline__ unsigned ctp_segment_bin(const MapDev &M, const double *a, const double *b, unsigned nbins_axis) {
+  unsigned c[3];
+  const double cen[3] = {M.cx, M.cy, M.cz};
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    const double mid = 0.5 * (a[ax] + b[ax]);
+    const double qd = ((mid - cen[ax]) * M.s1 + 1.0) * M.s2;  // the index transform of getClearence, any rounding will do
+    int v = qd > 0.0 ? (qd < M.nd ? (int)qd : M.n - 1) : 0;   // NaN -> 0
+    v >>= CTP_BIN_SHIFT;
+    c[ax] = (unsigned)(v < (int)nbins_axis ? v : (int)nbins_axis - 1);
+  }
+  return ctp_morton3(c[0], c[1], c[2]);
+}
+__global__ void __launch_bounds__(256) k_seg_bin_count(MapDev M, const double *__restrict__ a, const double *__restrict__ b,
+                                                       int64_t cnt, unsigned nbins_axis, unsigned *__restrict__ key_of,
+                                                       int32_t *__restrict__ bin_cnt) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  const unsigned key = ctp_segment_bin(M, a + 3 * i, b + 3 * i, nbins_axis);
+  key_of[i] = key;
+  atomicAdd(bin_cnt + key, 1);
+}
+__global__ void __launch_bounds__(256) k_seg_bin_scatter(const unsigned *__restrict__ key_of, int64_t cnt,
+                                                         const int32_t *__restrict__ bin_start, int32_t *__restrict__ cursor,
+                                                         int32_t *__restrict__ perm) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  const unsigned key = key_of[i];
+  perm[bin_start[key] + atomicAdd(cursor + key, 1)] = (int32_t)i;
 }
 
 // ---- layout builders ----------------------------------------------------------------------

@@ -329,6 +329,21 @@ __device__ __forceinline__ long long cluster_excl_scan(int rank, int64_t len, Va
   return total;
 }
 
+// exclusive scan of len counters (one problem): out[i] = sum of in[0..i), out[len] = total; the counters are zeroed
+// (they become scatter cursors).  One CTA, or a cluster of CL.
+template <int CL>
+__global__ void __launch_bounds__(1024) k_excl_scan_i32(int32_t *__restrict__ in, int64_t len, int32_t *__restrict__ out) {
+  const int rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
+  const long long total = cluster_excl_scan<CL>(
+      rank, len, [&](int64_t i) { return in[i]; },
+      [&](int64_t i, int pre) {
+        out[i] = pre;
+        in[i] = 0;
+      },
+      [&](int64_t i, int off) { out[i] += off; });
+  if (threadIdx.x == 0 && rank == 0) out[len] = (int32_t)total;
+}
+
 // per query: exclusive scan of cell counts -> cell_start (ncell+1 entries); CL CTAs (a cluster) per query
 template <int CL>
 __global__ void __launch_bounds__(1024) k_knn_scan(const KnnGrid *__restrict__ grids, int cell_stride,
@@ -386,8 +401,31 @@ template <int K> struct TopK {
 #pragma unroll
     for (int s = 0; s < K; s++) key[s] = 0x7f8000007fffffffull;  // (+inf, INT_MAX)
   }
+  // ascending order of the K slots by Batcher's odd-even merge network for 16 inputs, with the exchanges that would
+  // touch the absent inputs K..15 (+inf: they never move) left out at compile time
+  __device__ __forceinline__ void sort() {
+#pragma unroll
+    for (int p = 1; p < 16; p <<= 1) {
+#pragma unroll
+      for (int kk = p; kk >= 1; kk >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 16; a++) {  // exchange (a, a + kk) of the merge step, if the network has it
+          const int b = a + kk, r = a - kk % p;
+          if (r >= 0 && (r % (2 * kk)) < kk && b <= 15 && a / (2 * p) == b / (2 * p) && b < K) {
+            const bool sw = key[b < K ? b : 0] < key[a < K ? a : 0];
+            const unsigned long long lo = sw ? key[b < K ? b : 0] : key[a < K ? a : 0];
+            const unsigned long long hi = sw ? key[a < K ? a : 0] : key[b < K ? b : 0];
+            key[a < K ? a : 0] = lo;
+            key[b < K ? b : 0] = hi;
+          }
+        }
+      }
+    }
+  }
   __device__ __forceinline__ void push(float dd, int j) {
-    const unsigned long long k = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)j;
+    push_key(((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)j);
+  }
+  __device__ __forceinline__ void push_key(const unsigned long long k) {
     if (k < key[K - 1]) {
       key[K - 1] = k;
 #pragma unroll
@@ -550,13 +588,25 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s
   }
   TopK<K> best;
   if (done) {
-    best.init();
-    for (int u = 0; u < kept; u++) {
-      const int pos = s_keep[u][tid];
-      if (pos == selfpos) continue;
+    // kept > K survivors (the point itself among them, with the key of an absent entry).  The first K go straight into
+    // the K slots and through a sorting network (a third of the instructions of K insertions, and their gathers are
+    // all in flight together); the others, four gathers at a time, are inserted only if they beat the current k-th.
+    auto key_of = [&](int pos) {
       const float4 o = __ldg(sq + pos);
       const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
-      best.push((ddx * ddx + ddy * ddy) + ddz * ddz, __float_as_int(o.w));
+      const unsigned long long kk =
+          ((unsigned long long)__float_as_uint((ddx * ddx + ddy * ddy) + ddz * ddz) << 32) | (unsigned)__float_as_int(o.w);
+      return pos == selfpos ? 0x7f8000007fffffffull : kk;
+    };
+#pragma unroll
+    for (int u = 0; u < K; u++) best.key[u] = key_of(s_keep[u][tid]);
+    best.sort();
+    for (int u0 = K; u0 < kept; u0 += 4) {
+      unsigned long long kq[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) kq[i] = u0 + i < kept ? key_of(s_keep[min(u0 + i, CTP_KNN_DIRECT_KEEP - 1)][tid]) : 0x7f8000007fffffffull;
+#pragma unroll
+      for (int i = 0; i < 4; i++) best.push_key(kq[i]);
     }
     // a candidate the fused filter dropped has d2 >= thr2 * (1 - 2^-22): with the k-th survivor below
     // thr2 * (1 - 1e-5) none of them can belong to the k nearest

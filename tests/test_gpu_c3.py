@@ -62,16 +62,28 @@ def test_c3_roadmap_vs_oracle(c3, orc):
 
 
 @pytest.mark.parametrize("layout", [capi.LAYOUT_TEX, capi.LAYOUT_CELL8, capi.LAYOUT_PLAIN])
-def test_c3_random_segments_vs_oracle(c3, layout):
+@pytest.mark.parametrize("binning", [0, 1, -1])
+def test_c3_random_segments_vs_oracle(c3, layout, binning):
+    """2^20 unordered segments: marched as they come (0), binned by voxel block first with the layout as set (1), and
+    the library's own choice (-1: as they come, on the CELL8 records) -- verdicts, first hits, lookup counts equal the
+    oracle's"""
     m, om, c, e = c3
+    if binning == -1 and layout != capi.LAYOUT_TEX:
+        pytest.skip("the automatic mode picks its own layout")
     m.set_layout(layout)
+    m.set_tunable(capi.TUNE_SEG_BIN, binning)
     try:
         a, b = synth.random_edges(c, e, 1 << 20, 31)
-        free, hit, hit_idx, lookups = m.edge_check(a, b, CLR, CDC)
-        f0, h0, hi0, l0, _ = om.edge_nodes(a, b, CLR, CDC, nthreads=NT)
-        assert np.array_equal(free, f0) and np.array_equal(hit_idx, hi0) and np.array_equal(lookups, l0)
-        assert np.array_equal(hit, h0, equal_nan=True)
+        a[:7] = np.nan               # degenerate segments take part in the binning as well
+        b[7:9] = a[7:9]
+        a[9] = c + 10 * e            # far outside the map
+        for group in (0, 1):
+            free, hit, hit_idx, lookups = m.edge_check(a, b, CLR, CDC, group=group)
+            f0, h0, hi0, l0, _ = om.edge_nodes(a, b, CLR, CDC, nthreads=NT)
+            assert np.array_equal(free, f0) and np.array_equal(hit_idx, hi0) and np.array_equal(lookups, l0)
+            assert np.array_equal(hit, h0, equal_nan=True)
         p = c + (np.random.default_rng(5).random((1 << 20, 3)) - 0.5) * (e + 0.2)
         assert np.array_equal(m.clearance(p), om.clearance(p, nthreads=NT), equal_nan=True)
     finally:
         m.set_layout(capi.LAYOUT_TEX)
+        m.set_tunable(capi.TUNE_SEG_BIN, -1)

@@ -1414,3 +1414,23 @@ def test_two_node_query_consumes_no_candidates(c1):
     nodes, n_filled, n_used, _ = m.sample_reject(s, g, cand, CLR, 2)
     assert (n_filled == 2).all() and (n_used == 0).all()  # the loop of :309 never runs
     assert np.array_equal(nodes[:, 0], s) and np.array_equal(nodes[:, 1], g)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_segments_binned_by_voxel_block(c1, layout):
+    """ctp_edge_check with the binning pre-pass forced on a small map: same outputs as without, for both kernels"""
+    m, om, c, e = c1
+    m.set_layout(layout)
+    a, b = synth.random_edges(c, e, 150000, 9, lo=0.0, hi=3.0)
+    a[3] = np.nan
+    b[5] = c - 7 * e
+    f0, h0, hi0, l0, _ = om.edge_nodes(a, b, CLR, CDC, nthreads=8)
+    try:
+        for binning in (1, 0):
+            m.set_tunable(capi.TUNE_SEG_BIN, binning)
+            for group in (1, 8):
+                free, hit, hit_idx, lookups = m.edge_check(a, b, CLR, CDC, group=group)
+                assert np.array_equal(free, f0) and np.array_equal(hit_idx, hi0) and np.array_equal(lookups, l0)
+                assert np.array_equal(hit, h0, equal_nan=True)
+    finally:
+        m.set_tunable(capi.TUNE_SEG_BIN, -1)
