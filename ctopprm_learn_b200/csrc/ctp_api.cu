@@ -744,11 +744,11 @@ extern "C" int ctp_gradient(ctp_map *m, const double *xyz, int64_t cnt, double *
 }
 
 // ----------------------------------- segment checks ----------------------------------------
-// slot of (layout, lanes per edge) in ctp_map::occ_cache: layouts 1, 2, 4, 8 x groups 1, 4, 8, 16, 32
+// slot of (layout, lanes per edge) in ctp_map::occ_cache: layouts 1, 2, 4, 8 x groups 1, 4, 8, 16, 32 (+ one)
 static inline int occ_slot(int layout, int group) {
   const int li = layout == CTP_L_PLAIN ? 0 : layout == CTP_L_CELL8 ? 1 : layout == CTP_L_TEX ? 2 : 3;
-  const int gi = group == 1 ? 0 : group == 4 ? 1 : group == 8 ? 2 : group == 16 ? 3 : 4;
-  return li * 5 + gi;
+  const int gi = group == 1 ? 0 : group == 4 ? 1 : group == 8 ? 2 : group == 16 ? 3 : group == 2 ? 5 : 4;  // 2 = flat kernel, growing rounds
+  return li * 6 + gi;
 }
 template <int L, int G>
 static int launch_edges_LG(ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr, double cdc, int guards,
@@ -773,10 +773,12 @@ static int launch_edges_LG(ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr
 template <int L>
 static int launch_edges_flat(ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr, double cdc, int guards,
                              const EdgeOut &O, cudaStream_t st) {
-  int &occ = m->occ_cache[occ_slot(L, 1)];
+  const bool grow = !S.indexed;  // arbitrary segments: short first rounds; k-NN edges: one round of 16
+  int &occ = m->occ_cache[occ_slot(L, grow ? 2 : 1)];
   if (occ == 0) {
     int o = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_edge_flat<L>, 32 * CTP_FLAT_WARPS, 0));
+    if (grow) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_edge_flat<L, true>, 32 * CTP_FLAT_WARPS, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_edge_flat<L, false>, 32 * CTP_FLAT_WARPS, 0));
     occ = o > 0 ? o : 1;
   }
   const int64_t per_block = CTP_FLAT_EPW * CTP_FLAT_WARPS;
@@ -784,7 +786,8 @@ static int launch_edges_flat(ctp_map *m, const EdgeSrc &S, int64_t cnt, double c
   const int64_t cap = (int64_t)m->sm_count * occ;  // persistent: one resident wave
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_edge_flat<L><<<(int)blocks, 32 * CTP_FLAT_WARPS, 0, st>>>(m->dev, S, cnt, clr, cdc, guards, O);
+  if (grow) k_edge_flat<L, true><<<(int)blocks, 32 * CTP_FLAT_WARPS, 0, st>>>(m->dev, S, cnt, clr, cdc, guards, O);
+  else k_edge_flat<L, false><<<(int)blocks, 32 * CTP_FLAT_WARPS, 0, st>>>(m->dev, S, cnt, clr, cdc, guards, O);
   m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;

@@ -479,12 +479,18 @@ __device__ __forceinline__ double ctp_div_small(double a, double b, double rb) {
 }
 
 #define CTP_FLAT_R 16
+#ifndef CTP_FLAT_R0
+#define CTP_FLAT_R0 2  // first round of the growing schedule (2^24 random segments, C3 / C2 map: 2 -> 2.94 / 2.11 ms, 4 -> 3.18 / 2.16, 8 -> 3.72 / 2.30, one round of 16 -> 4.60 / 2.52)
+#endif
 #define CTP_FLAT_WARPS 8
 
 // (64 edges per warp, two per lane: the sample loop then runs ~11 full steps instead of ~5.4 with a
 // partly empty last one)
 #define CTP_FLAT_EPW 64
-template <int L>
+// GROW: the rounds of an edge take CTP_FLAT_R0 = 2, 4, 8, then CTP_FLAT_R samples.  The PRM's k-NN edges (a handful of samples, nearly
+// all free) want everything in one round; arbitrary segments collide early and often, and every sample of a round
+// past the first hit is a wasted lookup.
+template <int L, bool GROW>
 __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, EdgeSrc S, int64_t m, double clr,
                                                                    double cdc, int guards, EdgeOut O) {
   __shared__ double s_par[CTP_FLAT_WARPS][8][CTP_FLAT_EPW];
@@ -535,13 +541,15 @@ __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, Edg
         }
       }
     }
+    int round_cap = GROW ? CTP_FLAT_R0 : CTP_FLAT_R;
     for (;;) {
       int c[2], incl[2];
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        c[h] = alive[h] ? min(CTP_FLAT_R, n_last[h] - base[h] + 1) : 0;
+        c[h] = alive[h] ? min(GROW ? round_cap : CTP_FLAT_R, n_last[h] - base[h] + 1) : 0;
         incl[h] = c[h];
       }
+      if (GROW) round_cap = min(2 * round_cap, CTP_FLAT_R);
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t0 = __shfl_up_sync(full, incl[0], o), t1 = __shfl_up_sync(full, incl[1], o);

@@ -1,4 +1,5 @@
-for A in "--seg-bin 0 --layout tex" "--seg-bin 1 --layout tex" "--seg-bin 0 --layout cell8" "--seg-bin 1 --layout cell8" "--seg-bin 1 --layout brick" "" ; do python bench.py --workload MU --mu-map C3 --steps 10 --no-cpu --no-e2e $A 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('MU C3', '$A', round(d['value']/1e9,3), 'G seg/s', round(d['ms_per_step'],3), 'ms', round(d['roofline']['frac'],3), d['lookups_per_segment'])"; done
-python bench.py --workload MU --mu-map C2 --steps 10 --no-cpu --no-e2e --seg-bin 1 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('MU C2 bin', round(d['value']/1e9,3), 'G seg/s', round(d['ms_per_step'],3), 'ms', round(d['roofline']['frac'],3))"
+cp ctopprm_learn_b200/lib/libctopprm_b200.so /tmp/keep.so
+for R in 2 8; do cp tools/_variants/lib_r$R.so ctopprm_learn_b200/lib/libctopprm_b200.so
+for A in "--mu-map C3" "--mu-map C2"; do python bench.py --workload MU --steps 10 --no-cpu --no-e2e $A 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('MU R0=$R', '$A', round(d['value']/1e9,3), 'G seg/s', round(d['ms_per_step'],3), 'ms', round(d['roofline']['frac'],3))"; done; done
+cp /tmp/keep.so ctopprm_learn_b200/lib/libctopprm_b200.so
