@@ -896,6 +896,7 @@ def main():
     ap.add_argument("--map-graphs", action="store_true", help="C5: replay each map's batch from a CUDA graph (measured: no gain, the sweep is not launch-bound)")
     ap.add_argument("--map-threads", type=int, default=4, help="C5 e2e: host threads driving the map handles")
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (default: per workload)")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind each rank to its GPU's NUMA node")
     ap.add_argument("--seg-bin", type=int, default=-1, help="MU: bin the segments by voxel block first (1), never (0), library default (-1)")
     ap.add_argument("--shard-query", action="store_true", help="one query of the workload's size split over all GPUs (strong scaling)")
     ap.add_argument("--nodes", type=int, default=0, help="--shard-query: nodes of the query (default: the workload's)")
@@ -956,6 +957,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # one process per GPU: host staging buffers and the threads that fill them stay on the GPU's own NUMA node
+    numa = capi.bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa else None
 
     mapcfg, n, qdef, cpn = WORKLOADS[args.workload]
     q = args.queries or qdef
@@ -1313,7 +1316,8 @@ def main():
             lens_g, paths_g = hm.find_geometrical_paths(fya, fs, fg, "", cand=fcand, want_paths=True, cap_pts=1 << 20, cap=4096)
             if rep:
                 t_full.append(time.perf_counter() - t0)
-        full_query = {"ms_per_query": 1e3 * float(np.median(t_full)), "distinct_paths": int(len(lens_g)),
+        full_query = {"ms_per_query": 1e3 * float(np.median(t_full)), "phase_ms_last_call": hostlib.last_phase_times(),
+                      "distinct_paths": int(len(lens_g)),
                       "path_lengths": [float(x) for x in lens_g[:8]], "nodes": n,
                       "api": "TopologicalPRMClustering::find_geometrical_paths (sampleMultiple -> findShortestPath -> "
                              "clusterGraph -> shorten -> removeTooLong / removeEquivalent -> shorten -> removeEquivalent), "
@@ -1412,7 +1416,7 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes / launches_edge,
                          "lookups_per_launch": lookups / launches_edge, "ms_per_launch": edge_ms / launches_edge,
                          "share_of_step": edge_ms / ms},
-            "e2e": e2e, "e2e_full_csr": e2e_full, "sustained": sustained, "gpu_launches": int(launches), "clocks": clk,
+            "e2e": e2e, "e2e_full_csr": e2e_full, "numa_binding_rank0": numa, "sustained": sustained, "gpu_launches": int(launches), "clocks": clk,
             "cpu_baseline": cpu, "csr_nnz_per_step": nnz_total, "free_edge_fraction": free_frac, "parity": parity,
             "reference_note": "the CPU arm's neighbour stage is the oracle's exact float32 k-NN (FLANN is absent from the "
                               "reference tree); its collision code is the reference's own src/esdf_map.cpp + src/base_map.cpp",

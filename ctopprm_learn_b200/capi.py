@@ -117,6 +117,33 @@ def lib():
     return _lib
 
 
+def bind_to_gpu_numa_node(device=0):
+    """Pin this process (and the page-locked buffers it allocates afterwards) to the CPUs of the NUMA node the GPU hangs
+    off: with one process per GPU every rank then stages its host <-> device copies through its own node's memory instead of
+    all ranks sharing one.  Returns {"node", "cpus"} or None when the topology cannot be read (nothing is changed then)."""
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        base = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if node < 0 or not cpus or cpus == allowed:
+            return {"node": node, "cpus": len(allowed), "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus), "bound": True}
+    except Exception:
+        return None
+
+
 def pinned_empty(shape, dtype):
     """numpy array over page-locked host memory (ctp_host_alloc); freed with the array."""
     dtype = np.dtype(dtype)

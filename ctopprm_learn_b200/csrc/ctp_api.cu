@@ -91,6 +91,8 @@ struct ctp_map {
   int sssp_smem_optin = -1;   // opt-in shared memory per CTA of this device, -1 until the graph kernels were configured
   unsigned knn_smem_set = 0;  // bit K: the dynamic shared-memory limit of the k-NN kernels <K> has been raised
   int64_t pipe_nu_seen = 0;  // largest n_used (candidates consumed by a query) seen by the running pipeline call
+  void *rm_block = nullptr;   // device block of the last destroyed ctp_roadmap, kept for the next one (cudaMalloc / cudaFree
+  size_t rm_block_cap = 0;    // cost milliseconds each on a context that maps tens of GiB)
   int seg_bin = -1;           // ctp_edge_check: bin large batches by voxel block first: -1 automatic, 0 never, 1 always
   int64_t csr_pair_cap = 0;   // overflow pairs of the adjacency stage (0 = one per node)
   int perq_cluster = -1;      // per-query setup / scan kernels on clusters of 8 CTAs: -1 automatic, 0 never, 1 always
@@ -458,6 +460,7 @@ extern "C" int ctp_map_destroy(ctp_map *m) {
   cudaFree(m->d_lookups);
   cudaFree(m->ws.base);
   cudaFree(m->io.base);
+  if (m->rm_block) cudaFree(m->rm_block);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   if (m->pipe_ready) {
     for (int i = 0; i < 4; i++) cudaStreamDestroy(m->pipe_st[i]);
@@ -1769,16 +1772,25 @@ struct ctp_roadmap {
   double *d_w = nullptr, *d_dist = nullptr, *d_rec_dist = nullptr;
   int64_t *d_off = nullptr;
   uint64_t *d_upd = nullptr;
+  void *block = nullptr;  // all of the above live in this one allocation
+  size_t block_cap = 0;
   std::vector<int64_t> h_off;
 };
 
 extern "C" int ctp_roadmap_destroy(ctp_roadmap *r) {
   if (!r) return CTP_OK;
-  if (r->m) cudaSetDevice(r->m->device);
-  void *ptrs[] = {r->d_rp, r->d_col, r->d_prev, r->d_label, r->d_seeds, r->d_ns, r->d_rec_nodes, r->d_rec_label, r->d_rec_count,
-                  r->d_w,  r->d_dist, r->d_rec_dist, r->d_off, r->d_upd};
-  for (void *p : ptrs)
-    if (p) cudaFree(p);
+  ctp_map *m = r->m;
+  if (m) cudaSetDevice(m->device);
+  if (r->block) {
+    cudaDeviceSynchronize();  // nothing may still be reading the block when its next owner starts writing
+    if (m && r->block_cap > m->rm_block_cap) {  // keep the larger of the two blocks for the next roadmap of this map
+      if (m->rm_block) cudaFree(m->rm_block);
+      m->rm_block = r->block;
+      m->rm_block_cap = r->block_cap;
+    } else {
+      cudaFree(r->block);
+    }
+  }
   delete r;
   return CTP_OK;
 }
@@ -1807,29 +1819,46 @@ extern "C" int ctp_roadmap_create(ctp_map *m, int64_t q, int64_t n, const int32_
   r->max_seeds = max_seeds;
   r->rec_cap = std::max<int64_t>(widest, 1);  // a record per directed edge at most
   r->h_off.assign(nnz_off, nnz_off + q + 1);
-  auto alloc = [&](auto **p, size_t bytes) { return cudaMalloc((void **)p, bytes ? bytes : 1); };
-  cudaError_t e = cudaSuccess;
-  auto take = [&](auto **p, size_t bytes) {
-    if (e == cudaSuccess) e = alloc(p, bytes);
+  // one block for everything (taken over from the last destroyed roadmap of this map when it is large enough)
+  size_t need = 0;
+  auto sz = [&](size_t bytes) {
+    const size_t at = need;
+    need += align_up(bytes ? bytes : 1);
+    return at;
   };
-  take(&r->d_rp, q * (n + 1) * 4);
-  take(&r->d_col, nnz * 4 + 4);
-  take(&r->d_w, nnz * 8 + 8);
-  take(&r->d_off, (q + 1) * 8);
-  take(&r->d_dist, q * n * 8);
-  take(&r->d_prev, q * n * 4);
-  take(&r->d_label, q * n * 4);
-  take(&r->d_seeds, q * max_seeds * 4);
-  take(&r->d_ns, q * 4);
-  take(&r->d_rec_nodes, q * r->rec_cap * 8);
-  take(&r->d_rec_label, q * r->rec_cap * 4);
-  take(&r->d_rec_dist, q * r->rec_cap * 8);
-  take(&r->d_rec_count, q * 4);
-  take(&r->d_upd, q * 8);
-  if (e != cudaSuccess) {
-    ctp_roadmap_destroy(r);
-    return fail(e == cudaErrorMemoryAllocation ? CTP_ERR_NOMEM : CTP_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  const size_t o_rp = sz(q * (n + 1) * 4), o_col = sz(nnz * 4 + 4), o_w = sz(nnz * 8 + 8), o_off = sz((q + 1) * 8);
+  const size_t o_dist = sz(q * n * 8), o_prev = sz(q * n * 4), o_label = sz(q * n * 4), o_seeds = sz(q * max_seeds * 4);
+  const size_t o_ns = sz(q * 4), o_rn = sz(q * r->rec_cap * 8), o_rl = sz(q * r->rec_cap * 4), o_rd = sz(q * r->rec_cap * 8);
+  const size_t o_rc = sz(q * 4), o_upd = sz(q * 8);
+  if (m->rm_block && m->rm_block_cap >= need) {
+    r->block = m->rm_block;
+    r->block_cap = m->rm_block_cap;
+    m->rm_block = nullptr;
+    m->rm_block_cap = 0;
+  } else {
+    const cudaError_t e = cudaMalloc(&r->block, need);
+    if (e != cudaSuccess) {
+      r->block = nullptr;
+      ctp_roadmap_destroy(r);
+      return fail(e == cudaErrorMemoryAllocation ? CTP_ERR_NOMEM : CTP_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    r->block_cap = need;
   }
+  char *bp = (char *)r->block;
+  r->d_rp = (int32_t *)(bp + o_rp);
+  r->d_col = (int32_t *)(bp + o_col);
+  r->d_w = (double *)(bp + o_w);
+  r->d_off = (int64_t *)(bp + o_off);
+  r->d_dist = (double *)(bp + o_dist);
+  r->d_prev = (int32_t *)(bp + o_prev);
+  r->d_label = (int32_t *)(bp + o_label);
+  r->d_seeds = (int32_t *)(bp + o_seeds);
+  r->d_ns = (int32_t *)(bp + o_ns);
+  r->d_rec_nodes = (int32_t *)(bp + o_rn);
+  r->d_rec_label = (int32_t *)(bp + o_rl);
+  r->d_rec_dist = (double *)(bp + o_rd);
+  r->d_rec_count = (int32_t *)(bp + o_rc);
+  r->d_upd = (uint64_t *)(bp + o_upd);
   int rc = CTP_OK;
   auto up = [&](void *d, const void *h, size_t bytes) {
     if (rc == CTP_OK && bytes && cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, 0) != cudaSuccess)

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <chrono>
+#include <memory>
 #include <random>
 
 #include "ctopprm/topological_prm_clustering.hpp"
@@ -145,8 +146,9 @@ struct Stage {
   std::vector<Conn> mn, mx;              // C x C, used for i < j
   std::vector<std::vector<Link>> all;    // all_cluster_connections
   std::vector<Poly> min_paths;           // min_cluster_paths_
-  std::vector<int32_t> rec_nodes, rec_label;
-  std::vector<double> rec_dist;
+  // record buffers of a flood, one record per directed edge at most (left uninitialised: tens of megabytes)
+  std::unique_ptr<int32_t[]> rec_nodes, rec_label;
+  std::unique_ptr<double[]> rec_dist;
   int64_t rec_cap = 0;
   Planner::ClusterStats stats;
 
@@ -160,8 +162,8 @@ struct Stage {
     const int32_t ns = (int32_t)seeds.size();
     int32_t count = 0;
     uint64_t upd = 0;
-    if (ctp_cluster_flood(rm, sd.data(), &ns, mode, dist.data(), prev.data(), cl.data(), rec_nodes.data(), rec_label.data(),
-                          rec_dist.data(), &count, &upd) != CTP_OK)
+    if (ctp_cluster_flood(rm, sd.data(), &ns, mode, dist.data(), prev.data(), cl.data(), rec_nodes.get(), rec_label.get(),
+                          rec_dist.get(), &count, &upd) != CTP_OK)
       dieCluster("ctp_cluster_flood");
     if (mode == 0) stats.floods++;
     else {
@@ -380,9 +382,7 @@ template <> std::vector<Path> Planner::clusterGraph() {
   st.C = std::max(2, max_clusters_);
   st.clr = min_clearance_;
   st.cdc = collision_distance_check_;
-  std::vector<double> xyz((size_t)n * 3);
-  for (int i = 0; i < n; i++) std::copy(nodes_[i]->data.data(), nodes_[i]->data.data() + 3, xyz.begin() + 3 * (size_t)i);
-  st.xyz = xyz.data();
+  st.xyz = node_xyz_.data();
   st.rp = csr_row_ptr_.data();
   st.col = csr_col_.data();
   const int64_t nnz_off[2] = {0, (int64_t)csr_col_.size()};
@@ -394,9 +394,9 @@ template <> std::vector<Path> Planner::clusterGraph() {
   st.dist.resize((size_t)n);
   st.prev.resize((size_t)n);
   st.cl.resize((size_t)n);
-  st.rec_nodes.resize((size_t)st.rec_cap * 2);
-  st.rec_label.resize((size_t)st.rec_cap);
-  st.rec_dist.resize((size_t)st.rec_cap);
+  st.rec_nodes.reset(new int32_t[(size_t)st.rec_cap * 2]);
+  st.rec_label.reset(new int32_t[(size_t)st.rec_cap]);
+  st.rec_dist.reset(new double[(size_t)st.rec_cap]);
   st.mn.resize((size_t)st.C * st.C);
   st.mx.resize((size_t)st.C * st.C);
   st.all.resize((size_t)st.C * st.C);
@@ -428,8 +428,8 @@ template <> std::vector<Path> Planner::clusterGraph() {
         }
     std::vector<V3> a, b;
     for (size_t s = 0; s < upto; s++) {
-      a.push_back(nodes_[st.seeds[s]]->data);
-      b.push_back(nodes_[r]->data);
+      a.push_back(V3(st.xyz[3 * (size_t)st.seeds[s]], st.xyz[3 * (size_t)st.seeds[s] + 1], st.xyz[3 * (size_t)st.seeds[s] + 2]));
+      b.push_back(V3(st.xyz[3 * (size_t)r], st.xyz[3 * (size_t)r + 1], st.xyz[3 * (size_t)r + 2]));
     }
     const std::vector<uint8_t> free = a.empty() ? std::vector<uint8_t>() : map_->isSimplePathFreeBetweenNodesBatch(a, b, st.clr, st.cdc);
     bool visible = false;
@@ -446,9 +446,13 @@ template <> std::vector<Path> Planner::clusterGraph() {
 
   auto t0 = now();
   st.wavefrontFill(min_clusters_);
+  cluster_phase_times_ = PhaseTimes();
+  cluster_phase_times_.wavefront = sec(t0, now()) * 1e3;
   INFO_GREEN("computation time wavefront " << sec(t0, now()));
+  auto t01 = now();
   st.findMinClusterTours();
   auto t1 = now();
+  cluster_phase_times_.min_tours = sec(t01, t1) * 1e3;
   const int S = (int)st.seeds.size();
   ClusterDfs dfs{st, S, st.cl[1], max_path_length_, std::vector<uint8_t>((size_t)S * S, 0), {}, {}};
   for (int i = 0; i < S; i++)  // createClusterNodes (:589-606)
@@ -497,7 +501,8 @@ template <> std::vector<Path> Planner::clusterGraph() {
   cluster_stats_ = st.stats;
   cluster_seeds_.assign(st.seeds.begin(), st.seeds.end());
   cluster_labels_.assign(st.cl.begin(), st.cl.end());
-  for (int i = 0; i < n; i++) nodes_[i]->cluster_id = st.cl[i];
+  for (int i = 0; i < n; i++)
+    if (nodes_[i]) nodes_[i]->cluster_id = st.cl[i];  // the others take it from cluster_labels_ when they are created
   ctp_roadmap_destroy(st.rm);
   return distinct;
 }

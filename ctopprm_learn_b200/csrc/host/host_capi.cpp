@@ -288,7 +288,7 @@ int ctph_find_geometrical_paths(void *map, const char *yaml_text, const double *
   if (cand && m > 0) {
     std::vector<V3> c((size_t)m);
     memcpy(c[0].data(), cand, (size_t)m * 24);
-    Planner::gate_candidate_streams.push_back(c);
+    Planner::gate_candidate_streams.push_back(std::move(c));
   }
   auto r = Planner::find_geometrical_paths(cfg, MAP(map), gates, output_folder);
   Planner::gate_candidate_streams.clear();
@@ -303,6 +303,16 @@ int ctph_find_geometrical_paths(void *map, const char *yaml_text, const double *
   }
   return (int)r[0].size();
 }
+}
+
+// phases of the last find_geometrical_paths call: {prm, dijkstra, wavefront, min_tours, dfs_and_stitch, shorten_and_filter,
+// total} in ms, then {cluster_paths, seeds, refloods, homotopy_checks, capped_refloods}
+extern "C" void ctph_last_phase_times(double *ms7, int32_t *counts5) {
+  const auto &p = Planner::last_phase_times;
+  const double t[7] = {p.prm, p.dijkstra, p.wavefront, p.min_tours, p.dfs_and_stitch, p.shorten_and_filter, p.total};
+  const int32_t c[5] = {p.cluster_paths, p.seeds, p.refloods, p.homotopy_checks, p.capped_refloods};
+  memcpy(ms7, t, sizeof t);
+  memcpy(counts5, c, sizeof c);
 }
 
 // YAML subset reader, testable without a device: value of "a" or "a.b" as text; returns 0 if undefined

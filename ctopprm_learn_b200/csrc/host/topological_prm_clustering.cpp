@@ -19,6 +19,7 @@ template <> double Planner::cutoof_distance_ratio_to_shortest_ = 0;
 template <> double Planner::min_allowed = 0;
 template <> uint64_t Planner::sampling_seed = 1;
 template <> std::vector<std::vector<V3>> Planner::gate_candidate_streams = {};
+template <> Planner::PhaseTimes Planner::last_phase_times = {};
 template <>
 std::function<std::vector<Path>(Planner &, const Path &)> Planner::cluster_stage =
     [](Planner &prm, const Path &) { return prm.clusterGraph(); };
@@ -88,16 +89,17 @@ template <> void Planner::sampleMultiple(const int num_samples) {
   std::vector<int32_t> row_ptr((size_t)n + 1), col((size_t)2 * n * k);
   int32_t n_filled = 0;
   int64_t nnz_off[2] = {0, 0};
-  std::vector<V3> cand = candidate_stream_;
-  const bool generated = cand.empty();
-  int64_t m = generated ? 4 * (int64_t)n : (int64_t)cand.size();
+  std::vector<V3> drawn;
+  const bool generated = candidate_stream_.empty();
+  int64_t m = generated ? 4 * (int64_t)n : (int64_t)candidate_stream_.size();
   for (int attempt = 0;; attempt++) {
     if (generated) {
-      cand.resize((size_t)m);
+      drawn.resize((size_t)m);
       if (ctp_sample_ellipsoid(h, start_->data.data(), end_->data.data(), 1, m, ellipse_ratio_major_axis_focal_length_,
-                               planar_ ? 1 : 0, sampling_seed, cand[0].data()) != CTP_OK)
+                               planar_ ? 1 : 0, sampling_seed, drawn[0].data()) != CTP_OK)
         die("ctp_sample_ellipsoid");
     }
+    const std::vector<V3> &cand = generated ? drawn : candidate_stream_;
     const int rc = ctp_sample_multiple(h, start_->data.data(), end_->data.data(), cand[0].data(), 1, m, n, k, min_clearance_,
                                        collision_distance_check_, nodes.data(), &n_filled, row_ptr.data(), col.data(),
                                        w.data(), (int64_t)col.size(), nnz_off);
@@ -111,18 +113,43 @@ template <> void Planner::sampleMultiple(const int num_samples) {
   nodes_.assign((size_t)n, nullptr);
   nodes_[0] = start_;
   nodes_[1] = end_;
-  for (int i = 2; i < n; i++) {
-    nodes_[i] = new Node(V3(nodes[3 * (size_t)i], nodes[3 * (size_t)i + 1], nodes[3 * (size_t)i + 2]));
-    nodes_[i]->id = i;
-  }
-  csr_row_ptr_ = row_ptr;
+  node_xyz_.swap(nodes);
+  sp_dist_.clear();
+  sp_pred_.clear();
+  cluster_labels_.clear();
+  csr_row_ptr_.swap(row_ptr);
   csr_col_.assign(col.begin(), col.begin() + nnz_off[1]);
   csr_w_.assign(w.begin(), w.begin() + nnz_off[1]);
-  adjacency_ready_ = false;  // visibility_node_ids are filled on first use (nodes(), saveRoadmapDense)
+  adjacency_ready_ = false;  // HeapNodes and their visibility_node_ids are created on first use (nodes(), nodeAt())
+}
+
+template <> Node *Planner::nodeAt(int i) {
+  Node *&nd = nodes_[(size_t)i];
+  if (!nd) {
+    nd = new Node(V3(node_xyz_[3 * (size_t)i], node_xyz_[3 * (size_t)i + 1], node_xyz_[3 * (size_t)i + 2]));
+    nd->id = i;
+  }
+  return nd;
+}
+
+// every HeapNode of the roadmap, with the fields the stages that ran so far would have left in them
+template <> void Planner::materializeNodes() {
+  const int n = (int)nodes_.size();
+  for (int i = 0; i < n; i++) nodeAt(i);
+  if ((int)sp_dist_.size() == n) {
+    for (int i = 0; i < n; i++) {
+      nodes_[i]->distance_from_start = std::isfinite(sp_dist_[i]) ? sp_dist_[i] : DBL_MAX;
+      nodes_[i]->previous_point = sp_pred_[i] >= 0 ? nodes_[sp_pred_[i]] : nullptr;
+    }
+    nodes_[0]->previous_point = nodes_[0];
+  }
+  if ((int)cluster_labels_.size() == n)
+    for (int i = 0; i < n; i++) nodes_[i]->cluster_id = cluster_labels_[i];
 }
 
 // CSR -> visibility_node_ids of every node (the pointer graph of the reference, :374-385)
 template <> void Planner::materializeAdjacency() {
+  materializeNodes();
   if (adjacency_ready_) return;
   adjacency_ready_ = true;
   const int n = (int)nodes_.size();
@@ -138,30 +165,40 @@ template <> void Planner::materializeAdjacency() {
 // reference's Dijkstra leaves them for the nodes it settles.
 template <> std::vector<Path> Planner::findShortestPath() {
   const int n = (int)nodes_.size();
-  if (n < 2 || (int)csr_row_ptr_.size() != n + 1) return dijkstra.findPath(0, {1}, nodes_);
+  if (n < 2 || (int)csr_row_ptr_.size() != n + 1) {
+    materializeAdjacency();
+    return dijkstra.findPath(0, {1}, nodes_);
+  }
   ctp_map *h = handleOf(map_, "findShortestPath");
-  std::vector<double> dist((size_t)n);
-  std::vector<int32_t> pred((size_t)n);
+  sp_dist_.resize((size_t)n);
+  sp_pred_.resize((size_t)n);
   const int64_t nnz_off[2] = {0, (int64_t)csr_col_.size()};
   const int32_t src = 0;
-  if (ctp_sssp(h, 1, n, csr_row_ptr_.data(), csr_col_.data(), csr_w_.data(), nnz_off, &src, 1, dist.data(), pred.data(),
+  if (ctp_sssp(h, 1, n, csr_row_ptr_.data(), csr_col_.data(), csr_w_.data(), nnz_off, &src, 1, sp_dist_.data(), sp_pred_.data(),
                nullptr) != CTP_OK)
     die("ctp_sssp");
-  for (int i = 0; i < n; i++) {
-    nodes_[i]->distance_from_start = std::isfinite(dist[i]) ? dist[i] : DBL_MAX;
-    nodes_[i]->previous_point = pred[i] >= 0 ? nodes_[pred[i]] : nullptr;
-  }
+  // the HeapNodes that exist already get their fields now, the others when they are created (materializeNodes)
+  for (int i = 0; i < n; i++)
+    if (nodes_[i]) {
+      nodes_[i]->distance_from_start = std::isfinite(sp_dist_[i]) ? sp_dist_[i] : DBL_MAX;
+      nodes_[i]->previous_point = sp_pred_[i] >= 0 ? nodeAt(sp_pred_[i]) : nullptr;
+    }
   nodes_[0]->previous_point = nodes_[0];
   Path p;
   p.from_id = 0;
   p.to_id = 1;
-  if (!std::isfinite(dist[1])) {  // no path: length "infinite", empty plan (include/dijkstra.hpp:165-171)
+  if (!std::isfinite(sp_dist_[1])) {  // no path: length "infinite", empty plan (include/dijkstra.hpp:165-171)
     p.length = DBL_MAX;
     return {p};
   }
-  p.length = dist[1];
+  p.length = sp_dist_[1];
   std::vector<Node *> rev;
-  for (Node *c = nodes_[1]; c != nodes_[0]; c = c->previous_point) rev.push_back(c);
+  for (int c = 1; c != 0; c = sp_pred_[c]) {
+    Node *nd = nodeAt(c);
+    nd->distance_from_start = sp_dist_[c];
+    nd->previous_point = nodeAt(sp_pred_[c]);
+    rev.push_back(nd);
+  }
   rev.push_back(nodes_[0]);
   p.plan.assign(rev.rbegin(), rev.rend());
   return {p};
@@ -181,7 +218,9 @@ void Planner::floodFromSeeds(const std::vector<int> &seed_ids, std::vector<doubl
     die("ctp_sssp");
   pred.assign(p32.begin(), p32.end());
   cluster.assign(l32.begin(), l32.end());
-  for (int i = 0; i < n; i++) nodes_[i]->cluster_id = cluster[i];
+  cluster_labels_ = cluster;
+  for (int i = 0; i < n; i++)
+    if (nodes_[i]) nodes_[i]->cluster_id = cluster[i];
 }
 
 template <> std::vector<V3> Planner::samplePath(std::vector<Node *> path, const double length_tot, const double num_samples) {
@@ -369,7 +408,7 @@ template <> bool Planner::isNewSeedAccepted(Node *candidate, const std::vector<N
 // ---- CSV writers: node rows "x,y,z", edge rows "x0,y0,z0,x1,y1,z1" (:2066-2150; consumer
 // columns_2(...).py:20-33 tells them apart by column count).  Default ostream precision.
 template <> void Planner::saveRoadmapDense(std::string filename) {
-  materializeAdjacency();
+  materializeAdjacency();  // (creates every HeapNode first)
   std::ofstream f(filename);
   if (!f.is_open()) return;
   for (auto *n : nodes_) f << n->data(0) << "," << n->data(1) << "," << n->data(2) << std::endl;
@@ -422,7 +461,8 @@ std::vector<std::vector<Path>> Planner::find_geometrical_paths(const YAML::Node 
   for (size_t i = 0; i + 1 < gates.size(); i++) {
     Planner prm(planner_config, map, output_folder, gates[i], gates[i + 1]);
     prm.setBorders(map->getMinPos(), map->getMaxPos());
-    if (i < gate_candidate_streams.size() && !gate_candidate_streams[i].empty()) prm.setCandidateStream(gate_candidate_streams[i]);
+    if (i < gate_candidate_streams.size() && !gate_candidate_streams[i].empty())
+      prm.setCandidateStream(std::move(gate_candidate_streams[i]));  // consumed: one stream serves one call
     auto t0 = now();
     prm.sampleMultiple(num_samples_between_gate);
     auto t1 = now();
@@ -432,9 +472,14 @@ std::vector<std::vector<Path>> Planner::find_geometrical_paths(const YAML::Node 
     INFO_GREEN("djikstra time clustering " << ms(t1, t2) << " ms");
     if (shortest.empty() || shortest[0].plan.empty()) return paths_between_gates;  // :2569-2572
     prm.max_path_length_ = shortest[0].length * prm.max_path_length_ratio_;
+    last_phase_times = PhaseTimes();
+    last_phase_times.prm = ms(t0, t1);
+    last_phase_times.dijkstra = ms(t1, t2);
     std::vector<Path> found = cluster_stage(prm, shortest[0]);
+    auto t3 = now();
     if (!output_folder.empty()) prm.saveRoadmapFromCSR(output_folder + "roadmap_all" + std::to_string(i) + ".csv");
     INFO_GREEN("algorithm time clustering " << ms(t0, now()) << " ms");
+    auto t4 = now();
     auto both_ways = [](std::vector<Path> in) {  // shorten_path(false) then shorten_path(true) (:2612-2625)
       return shorten_paths(shorten_paths(in, false), true);
     };
@@ -444,6 +489,20 @@ std::vector<std::vector<Path>> Planner::find_geometrical_paths(const YAML::Node 
     shortened = both_ways(shortened);
     shortened = removeEquivalentPaths(shortened);
     std::sort(shortened.begin(), shortened.end(), [](const Path &a, const Path &b) { return a.length < b.length; });
+    {
+      PhaseTimes &pt = last_phase_times;
+      const PhaseTimes in_cluster = prm.cluster_phase_times_;
+      pt.wavefront = in_cluster.wavefront;
+      pt.min_tours = in_cluster.min_tours;
+      pt.dfs_and_stitch = ms(t2, t3) - in_cluster.wavefront - in_cluster.min_tours;
+      pt.shorten_and_filter = ms(t4, now());
+      pt.total = ms(t0, t3) + pt.shorten_and_filter;
+      pt.cluster_paths = (int)found.size();
+      pt.seeds = prm.cluster_stats_.seeds;
+      pt.refloods = prm.cluster_stats_.refloods;
+      pt.homotopy_checks = prm.cluster_stats_.homotopy_checks;
+      pt.capped_refloods = prm.cluster_stats_.capped_refloods;
+    }
     paths_between_gates[i] = shortened;
   }
   return paths_between_gates;

@@ -259,6 +259,17 @@ class HostPlanner:
         return ids[:min(cnt, cap)].copy(), length.value
 
 
+def last_phase_times():
+    """phases of the last find_geometrical_paths call (ms) and the cluster stage's counters"""
+    t = np.zeros(7)
+    c = np.zeros(5, dtype=np.int32)
+    lib().ctph_last_phase_times(_p(t), _p(c))
+    names = ("prm", "dijkstra", "wavefront", "min_tours", "dfs_and_stitch", "shorten_and_filter", "total")
+    out = {k: float(v) for k, v in zip(names, t)}
+    out.update({k: int(v) for k, v in zip(("cluster_paths", "seeds", "refloods", "homotopy_checks", "capped_refloods"), c)})
+    return out
+
+
 def shorten_path(pts, length, forward, cap=512):
     pts = _f(pts).reshape(-1, 3)
     out = np.empty((cap, 3))

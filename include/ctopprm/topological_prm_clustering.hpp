@@ -31,9 +31,7 @@ template <class T> class TopologicalPRMClustering {
   // n node rows "x,y,z", then one 6-column edge row per CSR entry
   static void saveRoadmapCSR(std::string filename, const double *nodes, int n, const int32_t *row_ptr, const int32_t *col);
   void saveRoadmapFromCSR(std::string filename) {
-    std::vector<double> xyz;
-    for (auto *nd : nodes_) xyz.insert(xyz.end(), nd->data.data(), nd->data.data() + 3);
-    saveRoadmapCSR(filename, xyz.data(), (int)nodes_.size(), csr_row_ptr_.data(), csr_col_.data());
+    saveRoadmapCSR(filename, node_xyz_.data(), (int)nodes_.size(), csr_row_ptr_.data(), csr_col_.data());
   }
   static void savePathSamples(std::string filename, std::vector<T> path);
   static path_with_length<T> shorten_path(path_with_length<T> path, bool forward = true);
@@ -53,6 +51,13 @@ template <class T> class TopologicalPRMClustering {
     int homotopy_checks = 0;  // isNewHomotopyClass evaluations (batched; includes speculative ones)
   };
   const ClusterStats &clusterStats() const { return cluster_stats_; }
+  // wall-clock milliseconds of the phases of the last find_geometrical_paths call (last gate pair): the reference prints
+  // the same spans as "prm time clustering", "djikstra time clustering", "computation time wavefront", ... (:2561-2605)
+  struct PhaseTimes {
+    double prm = 0, dijkstra = 0, wavefront = 0, min_tours = 0, dfs_and_stitch = 0, shorten_and_filter = 0, total = 0;
+    int cluster_paths = 0, seeds = 0, refloods = 0, homotopy_checks = 0, capped_refloods = 0;
+  };
+  static PhaseTimes last_phase_times;
   const std::vector<int> &clusterSeeds() const { return cluster_seeds_; }
   const std::vector<int> &clusterLabels() const { return cluster_labels_; }
   // node ids tried, in this order, as extra initial seeds when num_clusters > 2 (the reference draws them with
@@ -90,6 +95,11 @@ template <class T> class TopologicalPRMClustering {
     return nodes_;
   }
   void materializeAdjacency();
+  // the HeapNode of roadmap node i, created on first use (coordinates, id, and what findShortestPath / the floods
+  // left for it); the planner's own stages work on the coordinate table and the CSR
+  HeapNode<T> *nodeAt(int i);
+  void materializeNodes();
+  const std::vector<double> &nodeCoordinates() const { return node_xyz_; }  // n x 3
   // the CSR roadmap as the device handed it back
   const std::vector<int32_t> &csrRowPtr() const { return csr_row_ptr_; }
   const std::vector<int32_t> &csrCol() const { return csr_col_; }
@@ -97,6 +107,7 @@ template <class T> class TopologicalPRMClustering {
   // candidate stream for the next sampleMultiple (draw order of fillRandomStateInEllipse); when unset
   // the candidates are generated on the device from `sampling_seed`
   void setCandidateStream(const std::vector<Vector<3>> &cand) { candidate_stream_ = cand; }
+  void setCandidateStream(std::vector<Vector<3>> &&cand) { candidate_stream_ = std::move(cand); }
   static uint64_t sampling_seed;
   // find_geometrical_paths: candidate stream of gate pair i (optional; pairs without one draw on the device)
   static std::vector<std::vector<Vector<3>>> gate_candidate_streams;
@@ -107,7 +118,10 @@ template <class T> class TopologicalPRMClustering {
   static constexpr int num_nn = 14;  // reference :291 (13 neighbours + self)
 
  private:
-  std::vector<HeapNode<T> *> nodes_;
+  std::vector<HeapNode<T> *> nodes_;     // entries 0 (start) and 1 (end) always exist, the others on demand
+  std::vector<double> node_xyz_;         // n x 3, as the device returned them
+  std::vector<double> sp_dist_;          // findShortestPath: distance from the start / predecessor of every node
+  std::vector<int32_t> sp_pred_;
   std::vector<Vector<3>> candidate_stream_;
   // CSR of the roadmap as sampleMultiple received it from the device (input of the device graph search)
   std::vector<int32_t> csr_row_ptr_, csr_col_;
@@ -115,6 +129,7 @@ template <class T> class TopologicalPRMClustering {
   bool adjacency_ready_ = true;
   std::vector<int> seed_candidates_, cluster_seeds_, cluster_labels_;
   ClusterStats cluster_stats_;
+  PhaseTimes cluster_phase_times_;
   int num_clusters_, max_clusters_, min_clusters_;
   double min_ratio_;
   double max_path_length_ratio_;
