@@ -93,6 +93,7 @@ struct ctp_map {
   int64_t pipe_nu_seen = 0;  // largest n_used (candidates consumed by a query) seen by the running pipeline call
   void *rm_block = nullptr;   // device block of the last destroyed ctp_roadmap, kept for the next one (cudaMalloc / cudaFree
   size_t rm_block_cap = 0;    // cost milliseconds each on a context that maps tens of GiB)
+  double knn_radius = 0;      // > 0: neighbours farther than this are dropped from the k-NN table (radius-neighbour mode)
   int seg_bin = -1;           // ctp_edge_check: bin large batches by voxel block first: -1 automatic, 0 never, 1 always
   int64_t csr_pair_cap = 0;   // overflow pairs of the adjacency stage (0 = one per node)
   int perq_cluster = -1;      // per-query setup / scan kernels on clusters of 8 CTAs: -1 automatic, 0 never, 1 always
@@ -504,6 +505,10 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
       return CTP_OK;
     case CTP_TUNE_KNN_TILE:
       m->knn_tile = value != 0.0;
+      return CTP_OK;
+    case CTP_TUNE_KNN_RADIUS:
+      REQUIRE(value >= 0, "radius must be >= 0 (0 = off)");
+      m->knn_radius = value;
       return CTP_OK;
     case CTP_TUNE_SEG_BIN:
       m->seg_bin = value < 0 ? -1 : (value != 0.0);
@@ -1242,6 +1247,11 @@ static int knn_launch(ctp_map *m, const double *nodes, int64_t q, int64_t n, int
       KNN_CASE(9) KNN_CASE(10) KNN_CASE(11) KNN_CASE(12) KNN_CASE(13) KNN_CASE(14) KNN_CASE(15) KNN_CASE(16)
     }
 #undef KNN_CASE
+  }
+  if (m->knn_radius > 0) {
+    const float r2 = (float)(m->knn_radius * m->knn_radius);
+    k_knn_radius_mask<<<(unsigned)((total * k + 255) / 256), 256, 0, st>>>(nodes, n, total, k, r2, idx, idx_stride, d2);
+    m->launches++;
   }
   CK(cudaGetLastError());
   return CTP_OK;

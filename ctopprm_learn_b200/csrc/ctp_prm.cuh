@@ -666,6 +666,29 @@ k_knn_direct_list(const float4 *__restrict__ sorted, int64_t n, const int32_t *_
                         pass_lo, 2, list_kept ? list_kept[i] : 0, fb_list, nullptr, fb_count);
 }
 
+// Radius-neighbour candidates (north_star's wording; the reference itself takes the k nearest, :329-339): with a radius
+// set, a neighbour farther than it is dropped from the table (slot = -1, the "no neighbour" value every later stage
+// knows), so a node's candidates are its nearest ones WITHIN the radius, at most k.  The distance is the float32 one
+// the search itself ranks by ((dx*dx + dy*dy) + dz*dz on the coordinates narrowed to float).
+__global__ void __launch_bounds__(256) k_knn_radius_mask(const double *__restrict__ nodes, int64_t n, int64_t total_rows, int k,
+                                                         float r2, int32_t *__restrict__ idx, int idx_stride,
+                                                         float *__restrict__ d2out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= total_rows * k) return;
+  const int64_t row = e / k;
+  const int s = (int)(e - row * k);
+  const int j = idx[row * idx_stride + s];
+  if (j < 0) return;
+  const int64_t qbase = (row / n) * n;
+  const double *a = nodes + 3 * row, *b = nodes + 3 * (qbase + j);
+  const float dx = (float)a[0] - (float)b[0], dy = (float)a[1] - (float)b[1], dz = (float)a[2] - (float)b[2];
+  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  if (d2 > r2) {
+    idx[row * idx_stride + s] = -1;
+    if (d2out) d2out[row * k + s] = __int_as_float(0x7f800000);
+  }
+}
+
 // ---- warp-level selection helpers: (d2, index) keys, bitonic networks over the lanes ------------
 __device__ __forceinline__ unsigned long long knn_min64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 __device__ __forceinline__ unsigned long long knn_max64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }

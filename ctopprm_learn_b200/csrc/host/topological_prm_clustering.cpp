@@ -67,6 +67,8 @@ Planner::TopologicalPRMClustering(const YAML::Node &planner_config, std::shared_
   min_clearance_ = loadParam<double>(planner_config, "min_clearance");
   collision_distance_check_ = loadParam<double>(planner_config, "collision_distance_check");
   ellipse_ratio_major_axis_focal_length_ = loadParam<double>(planner_config, "ellipse_ratio_major_axis_focal_length");
+  // addition of the accelerated build (not a reference key): candidates limited to a radius around each node
+  if (planner_config["neighbour_radius"].IsDefined()) neighbour_radius_ = planner_config["neighbour_radius"].as<double>();
   if (collision_distance_check_ == 0) {
     ERROR("you need to specify collision_distance_check for sampling-based motion planning");
     exit(1);
@@ -89,6 +91,7 @@ template <> void Planner::sampleMultiple(const int num_samples) {
   std::vector<int32_t> row_ptr((size_t)n + 1), col((size_t)2 * n * k);
   int32_t n_filled = 0;
   int64_t nnz_off[2] = {0, 0};
+  if (ctp_set_tunable(h, CTP_TUNE_KNN_RADIUS, neighbour_radius_ > 0 ? neighbour_radius_ : 0.0) != CTP_OK) die("ctp_set_tunable");
   std::vector<V3> drawn;
   const bool generated = candidate_stream_.empty();
   int64_t m = generated ? 4 * (int64_t)n : (int64_t)candidate_stream_.size();

@@ -141,6 +141,7 @@ template <class T> class TopologicalPRMClustering {
   static double cutoof_distance_ratio_to_shortest_;
   static double min_allowed;
   double ellipse_ratio_major_axis_focal_length_;
+  double neighbour_radius_ = 0;  // optional YAML key neighbour_radius (m): radius-neighbour candidates, 0 = plain k nearest
   HeapNode<T> *start_;
   HeapNode<T> *end_;
   bool planar_;

@@ -104,6 +104,7 @@ int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int r
 #define CTP_TUNE_PIPE_HEAD 5     /* chunk pipelines: upload value*n (+256) candidates per query first, the tails only if a query
                                    of the chunk is still short (default 2.3; 0 = always upload whole streams) */
 #define CTP_TUNE_SSSP_CLUSTER 6  /* ctp_sssp: one query per cluster of 8 or 16 CTAs, distances (and, with 16, the rows) in distributed shared memory: 1 whenever possible, 0 never, -1 automatic (default: few queries in flight, or a query too large for one CTA) */
+#define CTP_TUNE_KNN_RADIUS 10   /* radius-neighbour candidates: value > 0 (metres) drops every neighbour farther than it from the k-NN table (slot = -1), so a node connects to its nearest nodes within the radius, at most k; 0 (default) = the reference's plain k nearest (:329-339) */
 #define CTP_TUNE_SEG_BIN 9       /* ctp_edge_check: bin the segments of a batch by the 16^3-voxel block of their midpoint before marching them (measured: no gain, the kernel is not bound by memory on such batches): 1 always, 0 never and the layout as set, -1 (default) never, but batches of >= 65536 segments on a grid > 100 MB read the CELL8 records when they were materialised */
 #define CTP_TUNE_CSR_PAIR_CAP 7  /* adjacency stage: capacity of the overflow list of rows with more than 16 incoming-only edges (0 = automatic: one pair per node; tests set it small to reach the full-scan fallback) */
 #define CTP_TUNE_PERQ_CLUSTER 8  /* per-query setup / scan kernels on a cluster of 8 CTAs per query: 1 always, 0 never, -1 automatic (default: few queries of >= 16384 points) */

@@ -359,6 +359,21 @@ def knn_grid(nodes, k=13, nthreads=1):
     return idx, d2
 
 
+def csr_from_directed(nodes, nbr, directed_free):
+    """orc_csr_from_directed: symmetric union of the free directed edges -> row_ptr, col, w"""
+    nodes = _f64(nodes).reshape(-1, 3)
+    nbr = np.ascontiguousarray(nbr, dtype=np.int32)
+    n, k = nbr.shape
+    fr = np.ascontiguousarray(directed_free, dtype=np.uint8)
+    row_ptr = np.empty(n + 1, dtype=np.int32)
+    col = np.empty(2 * n * k, dtype=np.int32)
+    w = np.empty(2 * n * k)
+    L = _L()
+    L.orc_csr_from_directed.restype = C.c_int64
+    nnz = L.orc_csr_from_directed(_p(nodes), C.c_int(n), C.c_int(k), _p(nbr), _p(fr), _p(row_ptr), _p(col), _p(w))
+    return row_ptr, col[:nnz].copy(), w[:nnz].copy()
+
+
 def knn(nodes, k=13, nthreads=1):
     nodes = _f64(nodes).reshape(-1, 3)
     n = len(nodes)

@@ -1434,3 +1434,35 @@ def test_segments_binned_by_voxel_block(c1, layout):
                 assert np.array_equal(hit, h0, equal_nan=True)
     finally:
         m.set_tunable(capi.TUNE_SEG_BIN, -1)
+
+
+@pytest.mark.parametrize("radius", [0.45, 0.8, 5.0])
+def test_radius_neighbour_mode(c1, orc, radius):
+    """CTP_TUNE_KNN_RADIUS: candidates = the nearest nodes within the radius, at most k (the reference itself takes the
+    k nearest; north_star words it as radius neighbours).  Against the oracle's k-NN with the same cut applied."""
+    m, om, c, e = c1
+    n, k = 2500, 13
+    s, g, cand = _queries(c, e, 2, n, 57)
+    nodes = m.sample_reject(s, g, cand, CLR, n)[0]
+    m.set_tunable(capi.TUNE_KNN_RADIUS, radius)
+    try:
+        got = m.build_prm(nodes, CLR, CDC)
+        idx_only, d2_only = m.knn(nodes, k)
+    finally:
+        m.set_tunable(capi.TUNE_KNN_RADIUS, 0)
+    r2 = np.float32(radius * radius)
+    dropped = 0
+    for qi in range(2):
+        idx, d2 = orc.knn_grid(nodes[qi], k, nthreads=8)
+        far = d2 > r2
+        dropped += int(far.sum())
+        idx = np.where(far, -1, idx).astype(np.int32)
+        assert np.array_equal(got["nbr"][qi], idx) and np.array_equal(idx_only[qi], idx)
+        assert np.array_equal(d2_only[qi], np.where(far, np.float32(np.inf), d2))
+        frm = np.repeat(np.arange(n, dtype=np.int32), k)
+        free = om.edge_index(nodes[qi], frm, np.maximum(idx.reshape(-1), 0), CLR, CDC, nthreads=8)[0] & (idx.reshape(-1) >= 0)
+        assert np.array_equal(got["directed_free"][qi].reshape(-1), free)
+        rp, col, w = orc.csr_from_directed(nodes[qi], idx, free.reshape(n, k))
+        a, b = int(got["nnz_off"][qi]), int(got["nnz_off"][qi + 1])
+        assert np.array_equal(got["row_ptr"][qi], rp) and np.array_equal(got["col"][a:b], col) and np.array_equal(got["w"][a:b], w)
+    assert (dropped > 0) == (radius < 5.0)
