@@ -1213,14 +1213,20 @@ k_csr_emit(const double *__restrict__ nodes, const int32_t *__restrict__ rec, co
   const int loff = woff + incl - cnt;
   s_loff[t] = loff;
   if (t == CTP_CSR_EMIT_ROWS - 1) s_loff[CTP_CSR_EMIT_ROWS] = loff + cnt;
+  // ids below 2^25 leave room for the owning row (7 bits) in the same word: one shared load per entry instead of two
+  const bool pack = n < ((int64_t)1 << 25);
 #pragma unroll
   for (int s = 0; s < 32; s++)
     if (s < cnt) {
-      s_col[loff + s] = v[s];
-      s_own[loff + s] = (uint8_t)t;
+      s_col[loff + s] = pack ? (v[s] | ((unsigned)t << 25)) : v[s];
+      if (!pack) s_own[loff + s] = (uint8_t)t;
     }
-  __syncthreads();
+  // The usual CTA: all rows of one query, none of them a `big` row -- then the CTA's entries are one contiguous run of
+  // col / w that starts at the first row's position, and the per-row tables are not needed to place an entry.
+  const bool row_ok = row >= total_rows || (s_qbase[t] == s_qbase[0] && s_gbeg[t] == s_gbeg[0] + loff);
+  const bool flat = __syncthreads_and(row_ok) != 0;  // (also the barrier between the phases)
   const int total = s_loff[CTP_CSR_EMIT_ROWS];
+  const long long g0 = s_gbeg[0], q0 = s_qbase[0];
   // four entries per thread and step: their neighbour gathers (the only scattered loads of the kernel) are issued
   // together, the FP64 norms follow
   for (int x0 = t; x0 < total; x0 += 4 * CTP_CSR_EMIT_ROWS) {
@@ -1231,9 +1237,10 @@ k_csr_emit(const double *__restrict__ nodes, const int32_t *__restrict__ rec, co
     for (int u = 0; u < 4; u++) {
       const int x = x0 + u * CTP_CSR_EMIT_ROWS;
       const bool in = x < total;
-      ow[u] = in ? s_own[x] : 0;
-      c[u] = in ? s_col[x] : 0u;
-      const double *o = nodes + 3 * (s_qbase[ow[u]] + (int64_t)c[u]);
+      const unsigned word = in ? s_col[x] : 0u;
+      ow[u] = pack ? (int)(word >> 25) : (in ? s_own[x] : 0);
+      c[u] = pack ? (word & 0x1ffffffu) : word;
+      const double *o = nodes + 3 * ((flat ? q0 : s_qbase[ow[u]]) + (int64_t)c[u]);
       ox[u] = in ? o[0] : 0.0;
       oy[u] = in ? o[1] : 0.0;
       oz[u] = in ? o[2] : 0.0;
@@ -1242,7 +1249,7 @@ k_csr_emit(const double *__restrict__ nodes, const int32_t *__restrict__ rec, co
     for (int u = 0; u < 4; u++) {
       const int x = x0 + u * CTP_CSR_EMIT_ROWS;
       if (x >= total) continue;
-      const int64_t pos = s_gbeg[ow[u]] + (x - s_loff[ow[u]]);
+      const int64_t pos = flat ? g0 + x : s_gbeg[ow[u]] + (x - s_loff[ow[u]]);
       if (pos < cap) {
         col[pos] = (int32_t)c[u];
         if (w) {
