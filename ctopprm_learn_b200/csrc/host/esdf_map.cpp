@@ -13,6 +13,7 @@ struct NpyRecord {
   std::vector<size_t> shape;
   size_t word_size = 0;
   char kind = 'f';
+  char order = '<';  // '<' little-endian, '|' not applicable, '>' big-endian, '=' native
   std::vector<char> bytes;
   size_t count() const {
     size_t c = 1;
@@ -39,6 +40,7 @@ NpyRecord readNpy(FILE *fp) {
   if (p != std::string::npos && h.compare(p + 16, 4, "True") == 0) throw std::runtime_error("npy: fortran order unsupported");
   p = h.find("descr");
   p = h.find('\'', p + 6);
+  r.order = h[p + 1];
   r.kind = h[p + 2];
   r.word_size = strtoull(h.c_str() + p + 3, nullptr, 10);
   p = h.find('(', h.find("shape"));
@@ -73,6 +75,13 @@ void ESDFMap::load(std::string filename) {
   readNpy(fp);  // voxel_resolution: read and discarded (src/esdf_map.cpp:25)
   if (vox.shape.size() != 3 || cen.count() != 3 || ext.count() != 3 || cen.word_size != 8 || ext.word_size != 8)
     throw std::runtime_error("ESDFMap::load: unexpected record shapes in " + filename);
+  // the reference reads shape[0] for all three axes and reinterprets the bytes as native floats; a record that is
+  // not a cube of little-endian floats would be read out of bounds / as garbage, so it is refused here
+  if (vox.shape[0] != vox.shape[1] || vox.shape[0] != vox.shape[2])
+    throw std::runtime_error("ESDFMap::load: voxel record is not a cube in " + filename);
+  for (const NpyRecord *r : {&vox, &cen, &ext})
+    if (r->kind != 'f' || r->order == '>')
+      throw std::runtime_error("ESDFMap::load: records must be little-endian floating point in " + filename);
   const double *c = reinterpret_cast<const double *>(cen.bytes.data());
   const double *e = reinterpret_cast<const double *>(ext.bytes.data());
   centroid = Vector<3>(c[0], c[1], c[2]);
