@@ -665,6 +665,8 @@ def run_microbench(args, rank, world):
     dmap.set_layout(layout)
     if args.seg_bin != -1:
         dmap.set_tunable(capi.TUNE_SEG_BIN, args.seg_bin)
+    if args.edge_filter >= 0:
+        dmap.set_tunable(capi.TUNE_EDGE_FILTER, args.edge_filter)
     m_e = args.mu_edges
     a_h, b_h = synth.random_edges(c, e, m_e, 1000 + rank)
     a_d, b_d = torch.from_numpy(a_h).to(dev), torch.from_numpy(b_h).to(dev)
@@ -905,6 +907,7 @@ def main():
     ap.add_argument("--knn-per-cell", type=float, default=0.0)
     ap.add_argument("--knn-ring", action="store_true", help="ring-search k-NN only (no tile kernel)")
     ap.add_argument("--knn-mode", type=int, default=-1, help="0 per-thread ring search, 1 direct search (default)")
+    ap.add_argument("--edge-filter", type=int, default=-1, help="flat edge kernel: 1 float32 verdict filter in front of the FP64 code (default), 0 FP64 only")
     ap.add_argument("--edge-order", type=int, default=-1, help="1 cell-sorted row order in the edge kernel (default), 0 node order")
     ap.add_argument("--pipe-chunk", type=int, default=0, help="queries per chunk of the e2e copy/compute pipeline")
     ap.add_argument("--cpu-queries", type=int, default=0, help="size of the CPU baseline sample (queries)")
@@ -980,6 +983,8 @@ def main():
         dmap.set_tunable(capi.TUNE_KNN_PER_CELL, args.knn_per_cell)
     if args.edge_order >= 0:
         dmap.set_tunable(capi.TUNE_EDGE_ORDER, args.edge_order)
+    if args.edge_filter >= 0:
+        dmap.set_tunable(capi.TUNE_EDGE_FILTER, args.edge_filter)
     if args.pipe_chunk:
         dmap.set_tunable(capi.TUNE_PIPE_CHUNK, args.pipe_chunk)
     if args.pipe_head:

@@ -14,7 +14,7 @@ DEFAULT_LAYOUT = LAYOUT_TEX  # the layout bench.py uses unless told otherwise (f
 EDGE_NODES, EDGE_GUARDS = 0, 1
 CSR_UPPER, CSR_NO_WEIGHTS = 1, 2
 TUNE_KNN_PER_CELL, TUNE_KNN_TILE, TUNE_PIPE_CHUNK, TUNE_EDGE_ORDER, TUNE_SSSP_FRONTIER, TUNE_PIPE_HEAD, TUNE_SSSP_CLUSTER = 0, 1, 2, 3, 4, 5, 6
-TUNE_CSR_PAIR_CAP, TUNE_PERQ_CLUSTER, TUNE_SEG_BIN, TUNE_KNN_RADIUS = 7, 8, 9, 10
+TUNE_CSR_PAIR_CAP, TUNE_PERQ_CLUSTER, TUNE_SEG_BIN, TUNE_KNN_RADIUS, TUNE_EDGE_FILTER = 7, 8, 9, 10, 11
 ERR_NEED_CANDIDATES = -4
 
 _lib = None

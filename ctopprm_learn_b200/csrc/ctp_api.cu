@@ -98,6 +98,9 @@ struct ctp_map {
   int64_t csr_pair_cap = 0;   // overflow pairs of the adjacency stage (0 = one per node)
   int perq_cluster = -1;      // per-query setup / scan kernels on clusters of 8 CTAs: -1 automatic, 0 never, 1 always
   int occ_cache[32] = {0};    // resident CTAs per SM of the edge kernels, per (layout, lanes per edge): see occ_slot
+  int edge_filter = 1;        // flat edge kernel: float32 verdict filter in front of the exact FP64 code (CTP_TUNE_EDGE_FILTER)
+  float stat_gmax = 0.f, stat_vmax = 0.f;  // grid statistics behind the filter's error bound (k_map_stats)
+  bool stat_finite = false;
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;    // pool, two per recorded span
   std::vector<int> prof_stage;         // stage id of span i (events 2i, 2i+1)
@@ -203,6 +206,22 @@ static int map_build_layouts(ctp_map *m) {
     td.normalizedCoords = 0;
     CK(cudaCreateTextureObject(&m->tex, &rd, &td, nullptr));
   }
+  {
+    // largest adjacent-voxel difference, largest |voxel|, finiteness: the error bound of the float32 verdict filter
+    unsigned *d_st = nullptr, h_st[3] = {0, 0, 1};
+    CK(cudaMalloc(&d_st, 3 * sizeof(unsigned)));
+    cudaError_t e1 = cudaMemsetAsync(d_st, 0, 3 * sizeof(unsigned), 0);
+    if (e1 == cudaSuccess) {
+      k_map_stats<<<m->sm_count * 8, 256>>>(m->d_plain, n, d_st);
+      m->launches++;
+      e1 = cudaMemcpy(h_st, d_st, sizeof h_st, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_st);
+    CK(e1);
+    memcpy(&m->stat_gmax, &h_st[0], 4);
+    memcpy(&m->stat_vmax, &h_st[1], 4);
+    m->stat_finite = h_st[2] == 0;
+  }
   CK(cudaDeviceSynchronize());
   return CTP_OK;
 }
@@ -246,6 +265,26 @@ static void map_fill_params(ctp_map *m, const double c[3], const double e[3]) {
       ok = (floor(q_hi) >= N - 1.0) && (q_lo < 1.0);
     }
     d.box_implied = ok ? 1 : 0;
+  }
+  {
+    // float32 verdict filter (ctp_device.cuh, EdgeFilt): eta bounds the FP64 rounding of the reference's own index
+    // coordinate against the affine form qa + t * qv (sample position: 2u * |p|, index transform: 4u * |q|, the same
+    // for qa, 2u relative on qv; |p| <= |c| + E * 2^15 / N and |q| <= 2^15 on every edge the filter accepts, in voxels
+    // via the factor N / E); eps is the clearance bound for delta_cap, with a safety factor of 1.5.
+    const double u = 1.1102230246251565e-16;
+    const double cmax = fmax(fmax(fabs(c[0]), fabs(c[1])), fabs(c[2]));
+    const double vox_per_m = fabs(d.s1 * d.s2);
+    const double pmax = cmax + max_e * 32768.0 / N;
+    const double eta = 8.0 * u * pmax * vox_per_m + 16.0 * u * (32768.0 + CTP_FILT_QV_MAX);
+    const double delta_cap = ((4.5 * CTP_FILT_QV_MAX + 3.0) * 5.9604644775390625e-08 + eta) * 1.0001 + 1.2e-7;
+    const double G = (double)m->stat_gmax, V = (double)m->stat_vmax;
+    const double eps = 1.5 * (3.0 * G * (delta_cap + 5.9604644775390625e-08) + 8.0 * 5.9604644775390625e-08 * (G + V)) + 1e-300;
+    d.filt_eta = eta;
+    d.filt_g = m->stat_gmax;
+    d.filt_eps = eps;
+    // worth it only while the undecided band stays narrow (a grid of garbage would send every sample to the exact code);
+    // maps whose position test is not implied by the index tests (non-cubic extents) keep the exact kernel
+    d.filt_ok = (m->stat_finite && d.box_implied && eta < 1e-6 && eps == eps && eps < 1e-3 && d.s1 > 0 && d.s2 > 0 && m->n >= 4) ? 1 : 0;
   }
   d.nb = (m->n + 3) / 4;
   d.plain = m->d_plain;
@@ -533,6 +572,9 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
     case CTP_TUNE_EDGE_ORDER:
       m->edge_order = value < 0 ? -1 : (value != 0.0);
       return CTP_OK;
+    case CTP_TUNE_EDGE_FILTER:
+      m->edge_filter = value != 0.0;
+      return CTP_OK;
     case CTP_TUNE_PIPE_CHUNK:
       REQUIRE(value >= 0 && value <= 65535, "queries per chunk must be in [0, 65535]");
       m->pipe_chunk = (int64_t)value;
@@ -819,6 +861,59 @@ static int launch_edges(ctp_map *m, int group, const EdgeSrc &S, int64_t cnt, do
   return CTP_OK;
 }
 
+// Scratch of the whole-edge filter: the node table (cell + fraction of every node's index coordinate), the list of
+// undecided edges and its counter
+struct EdgeScratch {
+  float4 *qt = nullptr;
+  int32_t *list = nullptr;
+  int32_t *count = nullptr;
+};
+static size_t ws_bytes_edge_filter(int64_t rows, int64_t edges) {
+  return align_up((size_t)rows * 16) + align_up((size_t)edges * 4) + 256;
+}
+static EdgeScratch edge_scratch_take(ctp_map *m, int64_t rows, int64_t edges) {
+  EdgeScratch s;
+  s.qt = arena_take<float4>(m->ws, rows);
+  s.list = arena_take<int32_t>(m->ws, edges);
+  s.count = arena_take<int32_t>(m->ws, 64);
+  return s;
+}
+// may the roadmap edges of this launch go through k_edge_mid first?
+static bool edge_filter_applies(const ctp_map *m, const EdgeSrc &S, int64_t cnt, double clr, double cdc, int group) {
+  return m->edge_filter && group == 1 && m->dev.filt_ok && m->n <= 1024 && S.indexed && !S.from && S.small && !S.perm &&
+         cnt > 0 && cnt < ((int64_t)1 << 31) && clr == clr && fabs(clr) < 1e30 && cdc > 0 && cdc < 1e30;
+}
+
+// The n*k directed checks of a roadmap: the whole-edge float32 filter decides what it can with certainty from one
+// lookup per edge (k_edge_mid), the exact flat kernel marches the rest from the list.  `rows` = nodes the table covers
+// (all queries of the launch).
+template <int L>
+static int launch_edges_prm_L(ctp_map *m, EdgeSrc S, int64_t rows, int64_t cnt, double clr, double cdc, const EdgeOut &O,
+                              const EdgeScratch &es, cudaStream_t st) {
+  k_node_qtable<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(m->dev, S.a, rows, es.qt);
+  CK(cudaMemsetAsync(es.count, 0, sizeof(int32_t), st));
+  MidPar P;
+  const double vox = 1.0 / (m->dev.s1 * m->dev.s2);
+  P.hc = (float)(vox / cdc);
+  P.f_need = (float)nextafter((double)(float)(clr + 2.0 * m->dev.filt_eps), INFINITY);
+  if ((double)P.f_need < clr + 2.0 * m->dev.filt_eps) P.f_need = nextafterf(P.f_need, INFINITY);
+  P.lip_g = nextafterf((float)((double)m->dev.filt_g * 1.001), INFINITY);
+  P.eta = nextafterf((float)m->dev.filt_eta, INFINITY);
+  k_edge_mid<L><<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(m->dev, S, cnt, P, es.qt, O, es.list, es.count);
+  m->launches += 2;
+  CK(cudaGetLastError());
+  S.perm = es.list;
+  S.m_dev = es.count;
+  S.order = nullptr;
+  return launch_edges_flat<L>(m, S, cnt, clr, cdc, 0, O, st);
+}
+static int launch_edges_prm(ctp_map *m, int group, const EdgeSrc &S, int64_t rows, int64_t cnt, double clr, double cdc,
+                            const EdgeOut &O, const EdgeScratch &es, cudaStream_t st) {
+  if (!es.qt || !edge_filter_applies(m, S, cnt, clr, cdc, group)) return launch_edges(m, group, S, cnt, clr, cdc, 0, O, st);
+  DISPATCH_L(m, return launch_edges_prm_L<L>(m, S, rows, cnt, clr, cdc, O, es, st));
+  return CTP_OK;
+}
+
 static int check_edge_args(ctp_map *m, int64_t cnt, double cdc, int group) {
   REQUIRE(m && cnt >= 0, "bad argument");
   REQUIRE(cdc > 0, "collision_distance_check must be > 0 (topological_prm_clustering.hpp:270-275)");
@@ -1017,7 +1112,8 @@ static size_t ws_bytes_knn(int64_t q, int64_t n) {
 }
 static size_t ws_bytes_csr(int64_t q, int64_t n);
 static size_t ws_bytes_prm(int64_t q, int64_t n, int k) {
-  return ws_bytes_knn(q, n) + align_up((size_t)q * n * csr_ns(k) * 4) + align_up((size_t)q * n * k) + ws_bytes_csr(q, n);
+  return ws_bytes_knn(q, n) + align_up((size_t)q * n * csr_ns(k) * 4) + align_up((size_t)q * n * k) + ws_bytes_csr(q, n) +
+         ws_bytes_edge_filter(q * n, q * n * k);
 }
 
 extern "C" int ctp_reserve(ctp_map *m, int64_t q, int64_t n, int64_t cand, int k) {
@@ -1394,6 +1490,7 @@ extern "C" int ctp_build_prm_ex_dev(ctp_map *m, const double *nodes, int64_t q, 
   int32_t *d_rec = arena_take<int32_t>(m->ws, rows * ns);  // per node: k neighbour ids + free-edge mask
   uint8_t *d_free = directed_free ? directed_free : arena_take<uint8_t>(m->ws, edges);
   const CsrScratch csc = csr_scratch_take(m, q, n, k);
+  const EdgeScratch esc = edge_scratch_take(m, rows, edges);
   const float4 *d_sorted_keep = nullptr;
   int rc;
   {
@@ -1415,7 +1512,7 @@ extern "C" int ctp_build_prm_ex_dev(ctp_map *m, const double *nodes, int64_t q, 
   EdgeOut O{d_free, nullptr, nullptr, nullptr, m->d_lookups};
   {
     StageSpan span(m, CTP_STAGE_EDGES, st);
-    CKR(launch_edges(m, m->prm_group, S, edges, clr, cdc, 0, O, st));
+    CKR(launch_edges_prm(m, m->prm_group, S, rows, edges, clr, cdc, O, esc, st));
   }
   CKR(csr_emit(m, nodes, q, n, k, d_rec, d_free, csc, csr_flags, row_ptr, col, w, cap, nnz_off, st));
   if (nbr) {
@@ -1494,8 +1591,12 @@ extern "C" int ctp_edge_check_knn_dev(ctp_map *m, const double *nodes, int64_t q
   S.dk = ctp_div_make((uint32_t)k);
   S.dn = ctp_div_make((uint32_t)n);
   EdgeOut O{directed_free, nullptr, nullptr, nullptr, m->d_lookups};
+  const size_t keep = m->ws.used;
+  CKR(arena_reserve(m->ws, keep + ws_bytes_edge_filter(q * n, edges) + 1024));
+  const EdgeScratch esc = edge_scratch_take(m, q * n, edges);
+  m->ws.used = keep;  // dead once the kernels below have run (stream order)
   StageSpan span(m, CTP_STAGE_EDGES, st);
-  return launch_edges(m, m->prm_group, S, edges, clr, cdc, 0, O, st);
+  return launch_edges_prm(m, m->prm_group, S, q * n, edges, clr, cdc, O, esc, st);
 }
 
 // One GPU's share of a single large query split over several: the neighbour search and the
@@ -1515,6 +1616,7 @@ extern "C" int ctp_prm_rows_dev(ctp_map *m, const double *nodes, int64_t n, int 
   const size_t keep = m->ws.used;
   CKR(arena_reserve(m->ws, keep + ws_bytes_prm(1, n, k) + 8192));
   const int64_t edges = n * k;
+  const EdgeScratch esc = edge_scratch_take(m, n, edges);
   CK(cudaMemsetAsync(nbr, 0x80, edges * 4, st));
   CK(cudaMemsetAsync(directed_free, 0, edges, st));
   const float4 *d_sorted = nullptr;
@@ -1535,7 +1637,7 @@ extern "C" int ctp_prm_rows_dev(ctp_map *m, const double *nodes, int64_t n, int 
   S.dn = ctp_div_make((uint32_t)n);
   EdgeOut O{directed_free, nullptr, nullptr, nullptr, m->d_lookups};
   StageSpan span(m, CTP_STAGE_EDGES, st);
-  return launch_edges(m, 1, S, (slice[1] - slice[0]) * k, clr, cdc, 0, O, st);
+  return launch_edges_prm(m, 1, S, n, (slice[1] - slice[0]) * k, clr, cdc, O, esc, st);
 }
 
 extern "C" int ctp_csr_from_directed_dev(ctp_map *m, const double *nodes, int64_t q, int64_t n, int k, const int32_t *nbr,

@@ -26,6 +26,10 @@ struct MapDev {
   int box_implied;                     // 1: outside the box => floor(q) >= N-1 or <= 0 on that axis (checked on the host)
   int nb;                              // bricks per axis
   int tex_cmask, tex_cshift;           // x-slab mosaic of the gather texture: tile (x & cmask, x >> cshift)
+  int filt_ok;                         // 1: the float32 verdict filter of the flat edge kernel may be used on this map
+  double filt_eps;                     // |float32 clearance - reference clearance| bound of the filter (see EdgeFilter)
+  double filt_eta;                     // FP64 slack of the index coordinate (voxels) added to every edge's delta
+  float filt_g;                        // largest |difference of adjacent voxels| (k_map_stats)
   const float *plain;
   const float *cell8;
   const float *brick;
@@ -274,9 +278,10 @@ struct EdgeSrc {
                         // through neighbouring voxels; outputs stay indexed by the original edge number
   CtpDiv dk, dn;        // from == NULL: division by k and by n (valid when small != 0)
   int small;            // every edge index of the launch is below 2^31
-  const int32_t *perm;  // pairs mode, optional: work item i takes segment perm[i] (segments binned by the voxel
-                        // block of their midpoint, so that neighbouring work items read neighbouring voxels);
-                        // outputs stay indexed by the segment number
+  const int32_t *perm;  // optional: work item i takes edge / segment perm[i] (segments binned by the voxel block of
+                        // their midpoint; roadmap edges the whole-edge filter left undecided); outputs stay indexed
+                        // by the edge number
+  const int32_t *m_dev; // optional: the number of work items is read from here (a list filled by an earlier kernel)
 };
 
 // work item -> edge number (identity unless S.order is set)
@@ -304,11 +309,10 @@ struct EdgeOut {
   unsigned long long *total_lookups;  // device counter, one atomic per warp
 };
 
-// endpoints + sample count of edge e (src/base_map.cpp:52-63).
-// returns 0 = march needed, 1 = free without lookups, 2 = not free without lookups (missing / absurd)
-__device__ __forceinline__ int ctp_arm_edge(const EdgeSrc &S, int64_t e, int guards, double cdc, double &ax,
-                                            double &ay, double &az, double &vx, double &vy, double &vz,
-                                            double &npts, int &n_last) {
+// endpoints of edge e as (start, vector), in march order (src/base_map.cpp:52-56, :82,90); false = no such edge
+// (missing neighbour)
+__device__ __forceinline__ bool ctp_edge_ends(const EdgeSrc &S, int64_t e, int guards, double &ax, double &ay, double &az,
+                                              double &vx, double &vy, double &vz) {
   const double *pa, *pb;
   bool missing = false;
   if (S.indexed) {
@@ -355,6 +359,13 @@ __device__ __forceinline__ int ctp_arm_edge(const EdgeSrc &S, int64_t e, int gua
   ax = x0;
   ay = y0;
   az = z0;
+  return !missing;
+}
+
+// sample count of an edge vector (src/base_map.cpp:57-63).
+// returns 0 = march needed, 1 = free without lookups, 2 = not free without lookups (absurd length)
+__device__ __forceinline__ int ctp_edge_count(double vx, double vy, double vz, int guards, double cdc, double &npts,
+                                              int &n_last) {
   const double d = sqrt((vx * vx + vy * vy) + vz * vz);
   npts = ceil((d / cdc) + 1.0);
   n_last = 0;
@@ -362,10 +373,24 @@ __device__ __forceinline__ int ctp_arm_edge(const EdgeSrc &S, int64_t e, int gua
   // NaN npts: `index < NaN` is false, the reference loop body never runs => free.
   const bool trivially_free = (!guards && d < cdc) || !(npts == npts) || npts < 2.0;
   const bool absurd = npts > 2147483647.0;  // reference would spin on int overflow
-  if (missing || absurd) return 2;
+  if (absurd) return 2;
   if (trivially_free) return 1;
   n_last = (int)npts - 1;  // indices 1 .. npts-1 (src/base_map.cpp:64)
   return 0;
+}
+
+// endpoints + sample count of edge e (src/base_map.cpp:52-63).
+// returns 0 = march needed, 1 = free without lookups, 2 = not free without lookups (missing / absurd)
+__device__ __forceinline__ int ctp_arm_edge(const EdgeSrc &S, int64_t e, int guards, double cdc, double &ax,
+                                            double &ay, double &az, double &vx, double &vy, double &vz,
+                                            double &npts, int &n_last) {
+  const bool present = ctp_edge_ends(S, e, guards, ax, ay, az, vx, vy, vz);
+  const int st = ctp_edge_count(vx, vy, vz, guards, cdc, npts, n_last);
+  if (!present) {
+    n_last = 0;
+    return 2;
+  }
+  return st;
 }
 
 // One group of G lanes marches one segment, G consecutive samples per step, in the
@@ -478,6 +503,161 @@ __device__ __forceinline__ double ctp_div_small(double a, double b, double rb) {
   return __fma_rn(__fma_rn(-q0, b, a), rb, q0);
 }
 
+// ---- float32 whole-edge filter for roadmap edges ----------------------------------------------------
+// Nearly all k-NN edges of a roadmap are free, and most of them run through space whose clearance is far above the
+// threshold.  k_edge_mid decides those from ONE lookup: the trilinear interpolant f is continuous and, inside a cell,
+// |df/dq_axis| <= G (G = the largest difference of adjacent voxels of the grid, k_map_stats), so along the march
+// |f(q_j) - f(q_i)| <= G * |q_j - q_i|_1 = G * |qv|_1 * |j - i| / n  (q in voxel units, qv = the edge vector).  When the
+// clearance of the MIDDLE sample exceeds the threshold by more than that bound for the farthest sample, every sample of
+// the edge is free -- provided none of them sits exactly on a lattice plane (the reference's 0/0 -> NaN -> collision
+// quirk on integral index coordinates) and all lie in cells 1 .. N-2 (no range / position test can fire).  Everything
+// is evaluated in float32 with RIGOROUS bounds on the difference to the reference's FP64 values; an edge that cannot be
+// decided with certainty goes, by its number, onto a list that the exact kernel (k_edge_flat) then marches.  Verdicts,
+// and the reference-order lookup counts, are therefore bit-identical to the all-FP64 path (tests/test_gpu_filter.py
+// runs both against the oracle on inputs built to sit on those bounds).  The same idea as floating-point filters for
+// exact geometric predicates.
+//
+// Per node (k_node_qtable, FP64 once per node instead of once per edge): qa = w2i(a), cell Ia = floor(qa) (10 bits per
+// axis) and fraction fa = float(qa - Ia) (|error| <= 2^-25).  Per edge: qv = float(Ib - Ia) + (fb - fa), off the true
+// qb - qa by at most 2^-24 * (|qv| + 2) per axis.
+//  * sample count: x = |qv| * (voxel / cdc) + 1 in float32 is within tol = 2^-24 * (6 x + 2 (voxel/cdc) (Qv + 2)) of
+//    d / cdc + 1; npts = ceil(x) and the d < cdc shortcut are taken only when x is farther than tol from an integer.
+//  * index coordinate of sample i relative to Ia: r = fma(qv, fl(i * rcp(n)), fa) with
+//    |r - (q_ref(i) - Ia)| <= 2^-24 * (4.01 |qv| + 3.5) + eta < delta, eta = the FP64 roundings of the reference's own
+//    transform against the affine form (host-computed from centroid, extent, N: MapDev::filt_eta).
+//  * lattice planes: every |r - rint(r)| > delta  =>  no index coordinate of the sample is integral, its cell is certain.
+//  * clearance at the middle sample: |f32 - f_ref| <= 3 G delta + 3 * 2^-24 (G + Vmax) < filt_eps (computed for
+//    delta_cap = delta at CTP_FILT_QV_MAX voxels per axis -- longer edges are left to the exact kernel -- times 1.5).
+#define CTP_FILT_QV_MAX 256.0f
+#define CTP_QT_INVALID 0x80000000u
+
+// cell and fraction of every node's index coordinate; .w = x | y << 10 | z << 20, or CTP_QT_INVALID when a coordinate
+// is NaN or outside [0, 1024)
+__global__ void __launch_bounds__(256) k_node_qtable(MapDev M, const double *__restrict__ nodes, int64_t total,
+                                                     float4 *__restrict__ qt) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double q0 = ctp_w2i(nodes[3 * i], M.cx, M.s1, M.s2), q1 = ctp_w2i(nodes[3 * i + 1], M.cy, M.s1, M.s2),
+               q2 = ctp_w2i(nodes[3 * i + 2], M.cz, M.s1, M.s2);
+  const bool ok = (q0 >= 0.0) & (q0 < 1024.0) & (q1 >= 0.0) & (q1 < 1024.0) & (q2 >= 0.0) & (q2 < 1024.0);
+  const double f0 = floor(q0), f1 = floor(q1), f2 = floor(q2);
+  const unsigned pack = ok ? ((unsigned)(int)f0 | ((unsigned)(int)f1 << 10) | ((unsigned)(int)f2 << 20)) : CTP_QT_INVALID;
+  qt[i] = make_float4((float)(q0 - f0), (float)(q1 - f1), (float)(q2 - f2), __uint_as_float(pack));
+}
+
+template <int L>
+__device__ __forceinline__ float ctp_filter_value(const MapDev &M, float xd, float yd, float zd, int x0, int y0, int z0) {
+  float v[8];
+  Corners<L>::load(M, x0, y0, z0, v);
+  const float c00 = __fmaf_rn(xd, __fsub_rn(v[4], v[0]), v[0]);
+  const float c01 = __fmaf_rn(xd, __fsub_rn(v[5], v[1]), v[1]);
+  const float c10 = __fmaf_rn(xd, __fsub_rn(v[6], v[2]), v[2]);
+  const float c11 = __fmaf_rn(xd, __fsub_rn(v[7], v[3]), v[3]);
+  const float c0 = __fmaf_rn(yd, __fsub_rn(c10, c00), c00);
+  const float c1 = __fmaf_rn(yd, __fsub_rn(c11, c01), c01);
+  return __fmaf_rn(zd, __fsub_rn(c1, c0), c0);
+}
+
+struct MidPar {
+  float hc;      // voxel size / collision_distance_check, rounded to nearest
+  float f_need;  // min_clearance + 2 * filt_eps, rounded up
+  float lip_g;   // G * 1.001, rounded up
+  float eta;     // filt_eta, rounded up
+};
+
+// Roadmap edges (batched PRM mode of EdgeSrc: from == NULL, neighbour table `to`): work item -> edge as in
+// ctp_edge_of_item.  Decided edges get their verdict (free) here; the numbers of all others are appended to `list`.
+template <int L>
+__global__ void __launch_bounds__(256) k_edge_mid(MapDev M, EdgeSrc S, int64_t m, MidPar P, const float4 *__restrict__ qt,
+                                                  EdgeOut O, int32_t *__restrict__ list, int32_t *__restrict__ list_cnt) {
+  const unsigned full = 0xffffffffu;
+  const int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool valid = item < m;
+  bool decided = false;
+  int n_last = 0;
+  int64_t e = 0;
+  if (valid) {
+    const uint32_t r32 = ctp_div_u31((uint32_t)item, S.dk);
+    const int slot = (int)((uint32_t)item - r32 * (uint32_t)S.k);
+    const int64_t qbase = (int64_t)(ctp_div_u31(r32, S.dn) * (uint32_t)S.n);
+    const int64_t row = S.order ? qbase + __float_as_int(S.order[r32].w) : (int64_t)r32;
+    e = row * S.k + slot;
+    const int32_t t = S.to[row * S.to_stride + slot];
+    if (t >= 0) {
+      const float4 A = qt[row], B = qt[qbase + t];
+      const unsigned pa = __float_as_uint(A.w), pb = __float_as_uint(B.w);
+      const int ax = pa & 1023, ay = (pa >> 10) & 1023, az = (pa >> 20) & 1023;
+      const int bx = pb & 1023, by = (pb >> 10) & 1023, bz = (pb >> 20) & 1023;
+      // both ends in cells 1 .. N-2 (exact cells): so is every sample between them
+      const int lo = min(min(min(ax, ay), az), min(min(bx, by), bz)), hi = max(max(max(ax, ay), az), max(max(bx, by), bz));
+      bool sure = (((pa | pb) & CTP_QT_INVALID) == 0) & (lo >= 1) & (hi <= M.n - 2);
+      const float vx = __fadd_rn((float)(bx - ax), __fsub_rn(B.x, A.x)), vy = __fadd_rn((float)(by - ay), __fsub_rn(B.y, A.y)),
+                  vz = __fadd_rn((float)(bz - az), __fsub_rn(B.z, A.z));
+      const float Qv = fmaxf(fmaxf(fabsf(vx), fabsf(vy)), fabsf(vz));
+      const float l1 = __fadd_ru(__fadd_ru(fabsf(vx), fabsf(vy)), fabsf(vz));
+      const float d2 = __fmaf_rn(vz, vz, __fmaf_rn(vy, vy, __fmul_rn(vx, vx)));
+      const float x = __fmaf_rn(sqrtf(d2), P.hc, 1.0f);
+      const float tol = __fmul_rn(5.9604645e-8f, __fmaf_rn(6.0f, x, __fmul_rn(__fmul_rn(2.0f, P.hc), __fadd_rn(Qv, 2.0f))));
+      const float up = ceilf(x);
+      sure = sure & (Qv <= CTP_FILT_QV_MAX) & (x >= 1.0f) & (x < 1000.0f);
+      sure = sure & (__fsub_rn(up, x) > tol) & (__fsub_rn(x, __fsub_rn(up, 1.0f)) > tol);  // ceil, and d < cdc at x = 2, certain
+      if (sure) {
+        if (x < 2.0f) {
+          decided = true;  // d < cdc: free without lookups (src/base_map.cpp:57-59)
+        } else {
+          n_last = (int)up - 1;
+          const float inv_n = __frcp_rn(up);
+          const float delta = __fadd_ru(__fmul_ru(__fmaf_rn(4.5f, Qv, 5.0f), 5.9610e-8f), __fadd_ru(P.eta, 1.2e-7f));
+          const int mid = (n_last + 1) >> 1;
+          const float tm = __fmul_rn((float)mid, inv_n);
+          const float rx = __fmaf_rn(vx, tm, A.x), ry = __fmaf_rn(vy, tm, A.y), rz = __fmaf_rn(vz, tm, A.z);
+          const float flx = floorf(rx), fly = floorf(ry), flz = floorf(rz);
+          const float xd = __fsub_rn(rx, flx), yd = __fsub_rn(ry, fly), zd = __fsub_rn(rz, flz);
+          const float mx = fminf(xd, __fsub_rn(1.f, xd)), my = fminf(yd, __fsub_rn(1.f, yd)), mz = fminf(zd, __fsub_rn(1.f, zd));
+          if (fminf(fminf(mx, my), mz) > delta) {
+            const float f = ctp_filter_value<L>(M, xd, yd, zd, ax + (int)flx, ay + (int)fly, az + (int)flz);
+            const int far = max(mid - 1, n_last - mid);
+            const float drop = __fmul_ru(__fmul_ru(__fmul_ru(P.lip_g, l1), (float)far), __fmul_ru(inv_n, 1.000001f));
+            bool all_free = __fsub_rd(f, drop) >= P.f_need;
+            if (all_free) {
+              for (int idx = 1; idx <= n_last; idx++) {  // arithmetic only: no sample within delta of a lattice plane
+                const float ti = __fmul_rn((float)idx, inv_n);
+                const float sx = __fmaf_rn(vx, ti, A.x), sy = __fmaf_rn(vy, ti, A.y), sz = __fmaf_rn(vz, ti, A.z);
+                const float dx = fabsf(__fsub_rn(sx, rintf(sx))), dy = fabsf(__fsub_rn(sy, rintf(sy))),
+                            dz = fabsf(__fsub_rn(sz, rintf(sz)));
+                all_free = all_free & (fminf(fminf(dx, dy), dz) > delta);
+              }
+              decided = all_free;
+            }
+          }
+        }
+      }
+    }
+    if (decided) {
+      O.free_out[e] = 1;
+      if (O.hit) { O.hit[3 * e] = ctp_nan(); O.hit[3 * e + 1] = ctp_nan(); O.hit[3 * e + 2] = ctp_nan(); }
+      if (O.hit_idx) O.hit_idx[e] = -1;
+      if (O.lookups) O.lookups[e] = n_last;
+    }
+  }
+  // undecided edges -> list (one atomic per warp)
+  const bool push = valid && !decided;
+  const unsigned pm = __ballot_sync(full, push);
+  const int lane = threadIdx.x & 31;
+  if (pm) {
+    int base = 0;
+    if (lane == __ffs(pm) - 1) base = atomicAdd(list_cnt, __popc(pm));
+    base = __shfl_sync(full, base, __ffs(pm) - 1);
+    if (push) list[base + __popc(pm & ((1u << lane) - 1u))] = (int32_t)e;
+  }
+  if (O.total_lookups) {
+    unsigned lk = decided ? (unsigned)n_last : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lk += __shfl_xor_sync(full, lk, o);
+    if (lane == 0 && lk) atomicAdd(O.total_lookups, (unsigned long long)lk);
+  }
+}
+
 #define CTP_FLAT_R 16
 #ifndef CTP_FLAT_R0
 #define CTP_FLAT_R0 2  // first round of the growing schedule (2^24 random segments, C3 / C2 map: 2 -> 2.94 / 2.11 ms, 4 -> 3.18 / 2.16, 8 -> 3.72 / 2.30, one round of 16 -> 4.60 / 2.52)
@@ -504,6 +684,7 @@ __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, Edg
   int2 *ob = s_ob[w];
   uint8_t *slot = s_slot[w];
   const int64_t n_warps = (int64_t)gridDim.x * CTP_FLAT_WARPS;
+  if (S.m_dev) m = *S.m_dev;  // a list filled by an earlier kernel on the same stream
   const int64_t n_chunks = (m + CTP_FLAT_EPW - 1) / CTP_FLAT_EPW;
   unsigned long long my_lookups = 0;
 
@@ -616,6 +797,35 @@ __global__ void __launch_bounds__(32 * CTP_FLAT_WARPS) k_edge_flat(MapDev M, Edg
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my_lookups += __shfl_xor_sync(full, my_lookups, o);
     if (lane == 0 && my_lookups) atomicAdd(O.total_lookups, my_lookups);
+  }
+}
+
+// ---- statistics of the grid the filter's error bound needs ------------------------------------------------------
+// out[0] = largest |difference of voxels adjacent along an axis| (float bits), out[1] = largest |voxel| (float bits),
+// out[2] = number of non-finite voxels (saturating flag)
+__global__ void __launch_bounds__(256) k_map_stats(const float *__restrict__ plain, int n, unsigned *__restrict__ out) {
+  const size_t nn = (size_t)n * n, total = nn * n;
+  float g = 0.f, vm = 0.f;
+  bool bad = false;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int z = (int)(o % n), y = (int)((o / n) % n), x = (int)(o / nn);
+    const float v = plain[o];
+    bad |= !(fabsf(v) <= 3.4028234e38f);
+    vm = fmaxf(vm, fabsf(v));
+    if (z + 1 < n) g = fmaxf(g, fabsf(plain[o + 1] - v));
+    if (y + 1 < n) g = fmaxf(g, fabsf(plain[o + n] - v));
+    if (x + 1 < n) g = fmaxf(g, fabsf(plain[o + nn] - v));
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, s));
+    vm = fmaxf(vm, __shfl_xor_sync(0xffffffffu, vm, s));
+  }
+  const bool any_bad = __any_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, __float_as_uint(g));
+    atomicMax(out + 1, __float_as_uint(vm));
+    if (any_bad) atomicMax(out + 2, 1u);
   }
 }
 
