@@ -1030,6 +1030,7 @@ def main():
 
     # ---- timed region: device-resident inputs, CUDA events on the launching stream ----
     dmap.read_lookups(stream)
+    dmap.read_filter_counter(stream)
     dmap.read_launches()
     dmap.profile(True)
     dmap.profile_read()
@@ -1048,6 +1049,7 @@ def main():
     stage_ms, stage_calls = dmap.profile_read()
     dmap.profile(False)
     lookups = dmap.read_lookups(stream)
+    filt_decided, filt_seen, filt_lookups = dmap.read_filter_counter(stream)
     launches = dmap.read_launches()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -1420,7 +1422,11 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": alg_bytes / launches_edge,
                          "lookups_per_launch": lookups / launches_edge, "ms_per_launch": edge_ms / launches_edge,
-                         "share_of_step": edge_ms / ms},
+                         "share_of_step": edge_ms / ms,
+                         "whole_edge_filter": {"edges_shown": filt_seen / max(launches_edge, 1), "edges_decided_fraction": filt_decided / max(filt_seen, 1),
+                                               "lookups_performed_per_launch": (filt_seen + lookups - filt_lookups) / max(launches_edge, 1),
+                                               "note": "achieved / algorithmic bytes count the reference-order lookups (what the CPU performs); the "
+                                                       "float32 whole-edge filter decides most free roadmap edges from one lookup, with identical verdicts"}},
             "e2e": e2e, "e2e_full_csr": e2e_full, "numa_binding_rank0": numa, "sustained": sustained, "gpu_launches": int(launches), "clocks": clk,
             "cpu_baseline": cpu, "csr_nnz_per_step": nnz_total, "free_edge_fraction": free_frac, "parity": parity,
             "reference_note": "the CPU arm's neighbour stage is the oracle's exact float32 k-NN (FLANN is absent from the "

@@ -51,6 +51,7 @@ _SIGS = {
     "ctp_set_tunable": [_P, _I, _D],
     "ctp_reserve": [_P, _I64, _I64, _I64, _I],
     "ctp_lookup_counter_read": [_P, _P, _P, _I],
+    "ctp_filter_counter_read": [_P, _P, _P, _I],
     "ctp_launch_counter_read": [_P, _P, _I],
     "ctp_io_counter_read": [_P, _P, _P, _I],
     "ctp_profile": [_P, _I],
@@ -307,6 +308,13 @@ class DeviceMap:
         v = C.c_uint64(0)
         _check(lib().ctp_lookup_counter_read(self._h, _stream_ptr(stream), C.byref(v), int(reset)))
         return v.value
+
+    def read_filter_counter(self, stream=None, reset=True):
+        """(edges decided by the whole-edge filter, edges it was shown, reference-order lookups of the decided ones)
+        since the last reset"""
+        v = (C.c_uint64 * 3)(0, 0, 0)
+        _check(lib().ctp_filter_counter_read(self._h, _stream_ptr(stream), v, int(reset)))
+        return int(v[0]), int(v[1]), int(v[2])
 
     def read_launches(self, reset=True):
         v = C.c_uint64(0)

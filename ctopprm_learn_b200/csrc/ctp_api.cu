@@ -98,7 +98,10 @@ struct ctp_map {
   int64_t csr_pair_cap = 0;   // overflow pairs of the adjacency stage (0 = one per node)
   int perq_cluster = -1;      // per-query setup / scan kernels on clusters of 8 CTAs: -1 automatic, 0 never, 1 always
   int occ_cache[32] = {0};    // resident CTAs per SM of the edge kernels, per (layout, lanes per edge): see occ_slot
-  int edge_filter = 1;        // flat edge kernel: float32 verdict filter in front of the exact FP64 code (CTP_TUNE_EDGE_FILTER)
+  int edge_filter = 1;        // roadmap edges: float32 whole-edge filter in front of the exact kernel: 0 never, 1 where it pays
+                              // (calibrated on the first launch), 2 always (CTP_TUNE_EDGE_FILTER)
+  double filter_cal_clr = -1e300, filter_cal_cdc = -1e300;  // (threshold, spacing) the calibration below was taken for
+  bool filter_pays = true;
   float stat_gmax = 0.f, stat_vmax = 0.f;  // grid statistics behind the filter's error bound (k_map_stats)
   bool stat_finite = false;
   bool prof = false;
@@ -342,8 +345,8 @@ static int map_create_common(const void *vox, bool is_f64, int n, const double c
       cudaFree(tmp);
       CK(e2);
     }
-    CK(cudaMalloc(&m->d_lookups, sizeof(unsigned long long)));
-    CK(cudaMemset(m->d_lookups, 0, sizeof(unsigned long long)));
+    CK(cudaMalloc(&m->d_lookups, 4 * sizeof(unsigned long long)));  // [0] lookups, [1] / [2] edges decided / seen by the whole-edge filter
+    CK(cudaMemset(m->d_lookups, 0, 4 * sizeof(unsigned long long)));
     CKR(map_build_layouts(m));
     return CTP_OK;
   };
@@ -391,8 +394,8 @@ static int map_create_generated(int n, const double c[3], const double e[3], int
     CK(cudaMalloc(&m->d_plain, cnt * sizeof(float)));
     m->map_bytes += cnt * sizeof(float);
     CKR(fill(m));
-    CK(cudaMalloc(&m->d_lookups, sizeof(unsigned long long)));
-    CK(cudaMemset(m->d_lookups, 0, sizeof(unsigned long long)));
+    CK(cudaMalloc(&m->d_lookups, 4 * sizeof(unsigned long long)));  // [0] lookups, [1] / [2] edges decided / seen by the whole-edge filter
+    CK(cudaMemset(m->d_lookups, 0, 4 * sizeof(unsigned long long)));
     CKR(map_build_layouts(m));
     return CTP_OK;
   };
@@ -573,7 +576,7 @@ extern "C" int ctp_set_tunable(ctp_map *m, int key, double value) {
       m->edge_order = value < 0 ? -1 : (value != 0.0);
       return CTP_OK;
     case CTP_TUNE_EDGE_FILTER:
-      m->edge_filter = value != 0.0;
+      m->edge_filter = value == 2.0 ? 2 : (value != 0.0);
       return CTP_OK;
     case CTP_TUNE_PIPE_CHUNK:
       REQUIRE(value >= 0 && value <= 65535, "queries per chunk must be in [0, 65535]");
@@ -606,6 +609,22 @@ extern "C" int ctp_lookup_counter_read(ctp_map *m, void *stream, uint64_t *looku
   if (reset) CK(cudaMemsetAsync(m->d_lookups, 0, sizeof v, st));
   CK(cudaStreamSynchronize(st));
   *lookups = v;
+  return CTP_OK;
+}
+
+// edges the whole-edge float32 filter decided / was shown, and the reference-order lookups of the decided ones, since
+// the last reset (counted by k_edge_mid)
+extern "C" int ctp_filter_counter_read(ctp_map *m, void *stream, uint64_t out[3], int reset) {
+  REQUIRE(m && out, "null");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long v[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(v, m->d_lookups + 1, sizeof v, cudaMemcpyDeviceToHost, st));
+  if (reset) CK(cudaMemsetAsync(m->d_lookups + 1, 0, sizeof v, st));
+  CK(cudaStreamSynchronize(st));
+  out[0] = v[0];
+  out[1] = v[1];
+  out[2] = v[2];
   return CTP_OK;
 }
 
@@ -865,8 +884,8 @@ static int launch_edges(ctp_map *m, int group, const EdgeSrc &S, int64_t cnt, do
 // undecided edges and its counter
 struct EdgeScratch {
   float4 *qt = nullptr;
-  int32_t *list = nullptr;
-  int32_t *count = nullptr;
+  int32_t *list = nullptr;   // edges the middle probe left undecided
+  int32_t *count = nullptr;  // its length
 };
 static size_t ws_bytes_edge_filter(int64_t rows, int64_t edges) {
   return align_up((size_t)rows * 16) + align_up((size_t)edges * 4) + 256;
@@ -891,17 +910,37 @@ template <int L>
 static int launch_edges_prm_L(ctp_map *m, EdgeSrc S, int64_t rows, int64_t cnt, double clr, double cdc, const EdgeOut &O,
                               const EdgeScratch &es, cudaStream_t st) {
   k_node_qtable<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(m->dev, S.a, rows, es.qt);
-  CK(cudaMemsetAsync(es.count, 0, sizeof(int32_t), st));
+  CK(cudaMemsetAsync(es.count, 0, 64 * sizeof(int32_t), st));
   MidPar P;
   const double vox = 1.0 / (m->dev.s1 * m->dev.s2);
   P.hc = (float)(vox / cdc);
-  P.f_need = (float)nextafter((double)(float)(clr + 2.0 * m->dev.filt_eps), INFINITY);
+  P.f_need = (float)(clr + 2.0 * m->dev.filt_eps);
   if ((double)P.f_need < clr + 2.0 * m->dev.filt_eps) P.f_need = nextafterf(P.f_need, INFINITY);
   P.lip_g = nextafterf((float)((double)m->dev.filt_g * 1.001), INFINITY);
   P.eta = nextafterf((float)m->dev.filt_eta, INFINITY);
-  k_edge_mid<L><<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(m->dev, S, cnt, P, es.qt, O, es.list, es.count);
+  const int64_t per_cta = CTP_MID_THREADS * CTP_MID_IPT;
+  const unsigned ctas = (unsigned)((cnt + per_cta - 1) / per_cta);
+  // middle probe for every edge; the exact kernel for the edges it leaves on the list.  (Measured and dropped: further
+  // probes stepping along the undecided edges -- they decide 99 % of the C2 edges from a fifth of the lookups, but the
+  // dependent, divergent probes cost as much as marching those edges exactly.)
+  k_edge_mid<L><<<ctas, CTP_MID_THREADS, 0, st>>>(m->dev, S, (uint32_t)cnt, P, es.qt, O, es.list, es.count, m->d_lookups);
   m->launches += 2;
   CK(cudaGetLastError());
+  // the first filtered launch for this (threshold, spacing) on this map: see what the middle probe decides; where it
+  // is little (edges long against the clearance around them, or a grid with jumps) the filter costs more than it saves
+  // and the following launches go straight to the exact kernel.  One synchronisation, once; verdicts do not depend on it.
+  if (m->filter_cal_clr != clr || m->filter_cal_cdc != cdc) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone && cnt >= 4096) {
+      int32_t left = 0;
+      CK(cudaMemcpyAsync(&left, es.count, sizeof left, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      m->filter_cal_clr = clr;
+      m->filter_cal_cdc = cdc;
+      m->filter_pays = (double)left <= 0.65 * (double)cnt;
+    }
+  }
   S.perm = es.list;
   S.m_dev = es.count;
   S.order = nullptr;
@@ -909,7 +948,9 @@ static int launch_edges_prm_L(ctp_map *m, EdgeSrc S, int64_t rows, int64_t cnt, 
 }
 static int launch_edges_prm(ctp_map *m, int group, const EdgeSrc &S, int64_t rows, int64_t cnt, double clr, double cdc,
                             const EdgeOut &O, const EdgeScratch &es, cudaStream_t st) {
-  if (!es.qt || !edge_filter_applies(m, S, cnt, clr, cdc, group)) return launch_edges(m, group, S, cnt, clr, cdc, 0, O, st);
+  const bool calibrated = m->filter_cal_clr == clr && m->filter_cal_cdc == cdc;
+  if (!es.qt || !edge_filter_applies(m, S, cnt, clr, cdc, group) || (calibrated && !m->filter_pays && m->edge_filter != 2))
+    return launch_edges(m, group, S, cnt, clr, cdc, 0, O, st);
   DISPATCH_L(m, return launch_edges_prm_L<L>(m, S, rows, cnt, clr, cdc, O, es, st));
   return CTP_OK;
 }

@@ -565,96 +565,190 @@ struct MidPar {
   float eta;     // filt_eta, rounded up
 };
 
-// Roadmap edges (batched PRM mode of EdgeSrc: from == NULL, neighbour table `to`): work item -> edge as in
-// ctp_edge_of_item.  Decided edges get their verdict (free) here; the numbers of all others are appended to `list`.
+// Roadmap edges (batched PRM mode of EdgeSrc: from == NULL, neighbour table `to`; fewer than 2^31 edges): work item ->
+// edge as in ctp_edge_of_item.  Decided edges get their verdict (free) here; the numbers of all others are appended
+// to `list`.  A thread takes CTP_MID_IPT items a block apart and runs them phase by phase, so that the dependent
+// loads of the items (row order -> neighbour id -> node table -> grid) are in flight together.
+//  * lattice planes, all samples: index coordinates in 32-bit fixed point, R_i = FA + i * S mod 1 with
+//    S = fl(qv * rcp(n)) truncated to 2^-32: |R_i - frac(q_ref(i))| <= 2^-24 (3.01 |qv| + 2.5) + i * 2^-32 + eta < delta
+//    for i < 1000; a sample is off every lattice plane when (R + D) mod 1 >= 2 D on all three axes, D = delta.
+// stats[1] += decided edges, stats[2] += edges seen, stats[3] += reference-order lookups of the decided edges (which
+// O.total_lookups receives as well).
+#define CTP_MID_THREADS 256
+#ifndef CTP_MID_IPT
+#define CTP_MID_IPT 2
+#endif
+#ifndef CTP_MID_MINB
+#define CTP_MID_MINB 5  // 48 registers: measured 1.74 ms per C2 step against 1.81 at 4 CTAs per SM (56 registers)
+#endif
 template <int L>
-__global__ void __launch_bounds__(256) k_edge_mid(MapDev M, EdgeSrc S, int64_t m, MidPar P, const float4 *__restrict__ qt,
-                                                  EdgeOut O, int32_t *__restrict__ list, int32_t *__restrict__ list_cnt) {
+__global__ void __launch_bounds__(CTP_MID_THREADS, CTP_MID_MINB) k_edge_mid(MapDev M, EdgeSrc S, uint32_t m, MidPar P,
+                                                              const float4 *__restrict__ qt, EdgeOut O,
+                                                              int32_t *__restrict__ list, int32_t *__restrict__ list_cnt,
+                                                              unsigned long long *__restrict__ stats) {
+  __shared__ int s_push[CTP_MID_IPT][CTP_MID_THREADS / 32];
+  __shared__ int s_base;
+  __shared__ unsigned s_lk, s_dec;
   const unsigned full = 0xffffffffu;
-  const int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const bool valid = item < m;
-  bool decided = false;
-  int n_last = 0;
-  int64_t e = 0;
-  if (valid) {
-    const uint32_t r32 = ctp_div_u31((uint32_t)item, S.dk);
-    const int slot = (int)((uint32_t)item - r32 * (uint32_t)S.k);
-    const int64_t qbase = (int64_t)(ctp_div_u31(r32, S.dn) * (uint32_t)S.n);
-    const int64_t row = S.order ? qbase + __float_as_int(S.order[r32].w) : (int64_t)r32;
-    e = row * S.k + slot;
-    const int32_t t = S.to[row * S.to_stride + slot];
-    if (t >= 0) {
-      const float4 A = qt[row], B = qt[qbase + t];
-      const unsigned pa = __float_as_uint(A.w), pb = __float_as_uint(B.w);
-      const int ax = pa & 1023, ay = (pa >> 10) & 1023, az = (pa >> 20) & 1023;
-      const int bx = pb & 1023, by = (pb >> 10) & 1023, bz = (pb >> 20) & 1023;
-      // both ends in cells 1 .. N-2 (exact cells): so is every sample between them
-      const int lo = min(min(min(ax, ay), az), min(min(bx, by), bz)), hi = max(max(max(ax, ay), az), max(max(bx, by), bz));
-      bool sure = (((pa | pb) & CTP_QT_INVALID) == 0) & (lo >= 1) & (hi <= M.n - 2);
-      const float vx = __fadd_rn((float)(bx - ax), __fsub_rn(B.x, A.x)), vy = __fadd_rn((float)(by - ay), __fsub_rn(B.y, A.y)),
-                  vz = __fadd_rn((float)(bz - az), __fsub_rn(B.z, A.z));
-      const float Qv = fmaxf(fmaxf(fabsf(vx), fabsf(vy)), fabsf(vz));
-      const float l1 = __fadd_ru(__fadd_ru(fabsf(vx), fabsf(vy)), fabsf(vz));
-      const float d2 = __fmaf_rn(vz, vz, __fmaf_rn(vy, vy, __fmul_rn(vx, vx)));
-      const float x = __fmaf_rn(sqrtf(d2), P.hc, 1.0f);
-      const float tol = __fmul_rn(5.9604645e-8f, __fmaf_rn(6.0f, x, __fmul_rn(__fmul_rn(2.0f, P.hc), __fadd_rn(Qv, 2.0f))));
-      const float up = ceilf(x);
-      sure = sure & (Qv <= CTP_FILT_QV_MAX) & (x >= 1.0f) & (x < 1000.0f);
-      sure = sure & (__fsub_rn(up, x) > tol) & (__fsub_rn(x, __fsub_rn(up, 1.0f)) > tol);  // ceil, and d < cdc at x = 2, certain
-      if (sure) {
-        if (x < 2.0f) {
-          decided = true;  // d < cdc: free without lookups (src/base_map.cpp:57-59)
-        } else {
-          n_last = (int)up - 1;
-          const float inv_n = __frcp_rn(up);
-          const float delta = __fadd_ru(__fmul_ru(__fmaf_rn(4.5f, Qv, 5.0f), 5.9610e-8f), __fadd_ru(P.eta, 1.2e-7f));
-          const int mid = (n_last + 1) >> 1;
-          const float tm = __fmul_rn((float)mid, inv_n);
-          const float rx = __fmaf_rn(vx, tm, A.x), ry = __fmaf_rn(vy, tm, A.y), rz = __fmaf_rn(vz, tm, A.z);
-          const float flx = floorf(rx), fly = floorf(ry), flz = floorf(rz);
-          const float xd = __fsub_rn(rx, flx), yd = __fsub_rn(ry, fly), zd = __fsub_rn(rz, flz);
-          const float mx = fminf(xd, __fsub_rn(1.f, xd)), my = fminf(yd, __fsub_rn(1.f, yd)), mz = fminf(zd, __fsub_rn(1.f, zd));
-          if (fminf(fminf(mx, my), mz) > delta) {
-            const float f = ctp_filter_value<L>(M, xd, yd, zd, ax + (int)flx, ay + (int)fly, az + (int)flz);
-            const int far = max(mid - 1, n_last - mid);
-            const float drop = __fmul_ru(__fmul_ru(__fmul_ru(P.lip_g, l1), (float)far), __fmul_ru(inv_n, 1.000001f));
-            bool all_free = __fsub_rd(f, drop) >= P.f_need;
-            if (all_free) {
-              for (int idx = 1; idx <= n_last; idx++) {  // arithmetic only: no sample within delta of a lattice plane
-                const float ti = __fmul_rn((float)idx, inv_n);
-                const float sx = __fmaf_rn(vx, ti, A.x), sy = __fmaf_rn(vy, ti, A.y), sz = __fmaf_rn(vz, ti, A.z);
-                const float dx = fabsf(__fsub_rn(sx, rintf(sx))), dy = fabsf(__fsub_rn(sy, rintf(sy))),
-                            dz = fabsf(__fsub_rn(sz, rintf(sz)));
-                all_free = all_free & (fminf(fminf(dx, dy), dz) > delta);
-              }
-              decided = all_free;
-            }
-          }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t tile0 = blockIdx.x * (uint32_t)(CTP_MID_THREADS * CTP_MID_IPT);
+  if (tile0 >= m) return;  // (uniform per CTA)
+  if (threadIdx.x == 0) { s_lk = 0; s_dec = 0; }
+  uint32_t e[CTP_MID_IPT], row[CTP_MID_IPT], nb[CTP_MID_IPT];
+  bool valid[CTP_MID_IPT], sure[CTP_MID_IPT];
+  // phase 1: work item -> (row, slot), neighbour id
+#pragma unroll
+  for (int h = 0; h < CTP_MID_IPT; h++) {
+    const uint32_t item = tile0 + (uint32_t)h * CTP_MID_THREADS + threadIdx.x;
+    valid[h] = item < m;
+    const uint32_t it = valid[h] ? item : 0u;
+    const uint32_t r32 = ctp_div_u31(it, S.dk);
+    const uint32_t slot = it - r32 * (uint32_t)S.k;
+    const uint32_t qbase = ctp_div_u31(r32, S.dn) * (uint32_t)S.n;
+    row[h] = S.order ? qbase + (uint32_t)__float_as_int(S.order[r32].w) : r32;
+    e[h] = row[h] * (uint32_t)S.k + slot;
+    const int32_t t = S.to[(size_t)row[h] * S.to_stride + slot];
+    sure[h] = valid[h] & (t >= 0);
+    nb[h] = sure[h] ? qbase + (uint32_t)t : row[h];
+  }
+  // phase 2: node table
+  float4 A[CTP_MID_IPT], B[CTP_MID_IPT];
+#pragma unroll
+  for (int h = 0; h < CTP_MID_IPT; h++) {
+    A[h] = qt[row[h]];
+    B[h] = qt[nb[h]];
+  }
+  // phase 3: edge vector, sample count, the middle sample's cell and fractions
+  float vx[CTP_MID_IPT], vy[CTP_MID_IPT], vz[CTP_MID_IPT], inv_n[CTP_MID_IPT], delta[CTP_MID_IPT];
+  float xd[CTP_MID_IPT], yd[CTP_MID_IPT], zd[CTP_MID_IPT], step[CTP_MID_IPT];
+  int cx[CTP_MID_IPT], cy[CTP_MID_IPT], cz[CTP_MID_IPT], n_last[CTP_MID_IPT];
+  bool trivial[CTP_MID_IPT];
+#pragma unroll
+  for (int h = 0; h < CTP_MID_IPT; h++) {
+    const unsigned pa = __float_as_uint(A[h].w), pb = __float_as_uint(B[h].w);
+    const int ax = pa & 1023, ay = (pa >> 10) & 1023, az = (pa >> 20) & 1023;
+    const int bx = pb & 1023, by = (pb >> 10) & 1023, bz = (pb >> 20) & 1023;
+    // both ends in cells 1 .. N-2 (exact cells): so is every sample between them
+    const int lo = min(min(min(ax, ay), az), min(min(bx, by), bz)), hi = max(max(max(ax, ay), az), max(max(bx, by), bz));
+    bool ok = sure[h] & (((pa | pb) & CTP_QT_INVALID) == 0) & (lo >= 1) & (hi <= M.n - 2);
+    vx[h] = __fadd_rn((float)(bx - ax), __fsub_rn(B[h].x, A[h].x));
+    vy[h] = __fadd_rn((float)(by - ay), __fsub_rn(B[h].y, A[h].y));
+    vz[h] = __fadd_rn((float)(bz - az), __fsub_rn(B[h].z, A[h].z));
+    const float Qv = fmaxf(fmaxf(fabsf(vx[h]), fabsf(vy[h])), fabsf(vz[h]));
+    const float l1 = __fadd_ru(__fadd_ru(fabsf(vx[h]), fabsf(vy[h])), fabsf(vz[h]));
+    const float d2 = __fmaf_rn(vz[h], vz[h], __fmaf_rn(vy[h], vy[h], __fmul_rn(vx[h], vx[h])));
+    const float x = __fmaf_rn(sqrtf(d2), P.hc, 1.0f);
+    const float tol = __fmul_rn(5.9604645e-8f, __fmaf_rn(6.0f, x, __fmul_rn(__fmul_rn(2.0f, P.hc), __fadd_rn(Qv, 2.0f))));
+    const float up = ceilf(x);
+    ok = ok & (Qv <= CTP_FILT_QV_MAX) & (x >= 1.0f) & (x < 1000.0f);
+    ok = ok & (__fsub_rn(up, x) > tol) & (__fsub_rn(x, __fsub_rn(up, 1.0f)) > tol);  // ceil, and d < cdc at x = 2, certain
+    trivial[h] = ok & (x < 2.0f);  // d < cdc: free without lookups (src/base_map.cpp:57-59)
+    n_last[h] = (ok && !trivial[h]) ? (int)up - 1 : 0;
+    inv_n[h] = __frcp_rn(fmaxf(up, 1.0f));
+    delta[h] = __fadd_ru(__fmul_ru(__fmaf_rn(4.5f, Qv, 5.0f), 5.9610e-8f), __fadd_ru(P.eta, 3.0e-7f));
+    const int mid = (n_last[h] + 1) >> 1;
+    const float tm = __fmul_rn((float)mid, inv_n[h]);
+    const float rx = __fmaf_rn(vx[h], tm, A[h].x), ry = __fmaf_rn(vy[h], tm, A[h].y), rz = __fmaf_rn(vz[h], tm, A[h].z);
+    const float flx = floorf(rx), fly = floorf(ry), flz = floorf(rz);
+    xd[h] = __fsub_rn(rx, flx); yd[h] = __fsub_rn(ry, fly); zd[h] = __fsub_rn(rz, flz);
+    const float mx = fminf(xd[h], __fsub_rn(1.f, xd[h])), my = fminf(yd[h], __fsub_rn(1.f, yd[h])),
+                mz = fminf(zd[h], __fsub_rn(1.f, zd[h]));
+    ok = ok & (fminf(fminf(mx, my), mz) > delta[h]);
+    // an undecidable item still fetches (its loads are in flight with the others'): keep its cell inside the grid
+    const int hi_cell = M.n - 2;
+    cx[h] = ok ? ax + (int)flx : 1; cy[h] = ok ? ay + (int)fly : 1; cz[h] = ok ? az + (int)flz : 1;
+    cx[h] = min(max(cx[h], 0), hi_cell); cy[h] = min(max(cy[h], 0), hi_cell); cz[h] = min(max(cz[h], 0), hi_cell);
+    // bound on the clearance lost per sample step: G * |qv|_1 / n, every rounding upward
+    step[h] = fmaxf(__fmul_ru(__fmul_ru(P.lip_g, l1), __fmul_ru(inv_n[h], 1.000001f)), 1e-30f);
+    sure[h] = ok;
+  }
+  // phase 4: the lookups
+  float f[CTP_MID_IPT];
+#pragma unroll
+  for (int h = 0; h < CTP_MID_IPT; h++) f[h] = ctp_filter_value<L>(M, xd[h], yd[h], zd[h], cx[h], cy[h], cz[h]);
+  // phase 5: verdicts; no sample of a free edge may sit on a lattice plane
+  bool decided[CTP_MID_IPT];
+  unsigned lk = 0, dec = 0;
+#pragma unroll
+  for (int h = 0; h < CTP_MID_IPT; h++) {
+    // the middle probe proves the samples mid - s .. mid + s free, s = floor((f - f_need) / step)
+    bool all_free = false;
+    if (sure[h] & !trivial[h]) {
+      const float a0 = __fsub_rd(f[h], P.f_need);
+      const int mid = (n_last[h] + 1) >> 1;
+      const int far = max(mid - 1, n_last[h] - mid);
+      all_free = a0 >= __fmul_ru(step[h], (float)far);
+    }
+    if (all_free) {
+      const float sc = 4294967296.0f;
+      const unsigned D = __float2uint_ru(__fmul_ru(delta[h], sc)), W = 2u * D + 1u;
+      const unsigned Sx = (unsigned)__float2ll_rz(__fmul_rn(__fmul_rn(vx[h], inv_n[h]), sc)),
+                     Sy = (unsigned)__float2ll_rz(__fmul_rn(__fmul_rn(vy[h], inv_n[h]), sc)),
+                     Sz = (unsigned)__float2ll_rz(__fmul_rn(__fmul_rn(vz[h], inv_n[h]), sc));
+      unsigned Rx = (unsigned)__float2ll_rz(__fmul_rn(A[h].x, sc)) + D, Ry = (unsigned)__float2ll_rz(__fmul_rn(A[h].y, sc)) + D,
+               Rz = (unsigned)__float2ll_rz(__fmul_rn(A[h].z, sc)) + D;
+      // four samples per trip; the trips run past n_last (up to three positions beyond the far end): testing more
+      // positions than needed can only leave an edge to the exact kernel
+      bool near = false;
+      for (int idx = 1; idx <= n_last[h]; idx += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          Rx += Sx; Ry += Sy; Rz += Sz;
+          near |= (Rx < W) | (Ry < W) | (Rz < W);
         }
       }
+      all_free = !near;
     }
-    if (decided) {
-      O.free_out[e] = 1;
-      if (O.hit) { O.hit[3 * e] = ctp_nan(); O.hit[3 * e + 1] = ctp_nan(); O.hit[3 * e + 2] = ctp_nan(); }
-      if (O.hit_idx) O.hit_idx[e] = -1;
-      if (O.lookups) O.lookups[e] = n_last;
+    decided[h] = (sure[h] & trivial[h]) | all_free;
+    if (decided[h]) {
+      O.free_out[e[h]] = 1;
+      if (O.hit) { O.hit[3 * (size_t)e[h]] = ctp_nan(); O.hit[3 * (size_t)e[h] + 1] = ctp_nan(); O.hit[3 * (size_t)e[h] + 2] = ctp_nan(); }
+      if (O.hit_idx) O.hit_idx[e[h]] = -1;
+      if (O.lookups) O.lookups[e[h]] = n_last[h];
+      lk += (unsigned)n_last[h];
+      dec++;
     }
   }
-  // undecided edges -> list (one atomic per warp)
-  const bool push = valid && !decided;
-  const unsigned pm = __ballot_sync(full, push);
-  const int lane = threadIdx.x & 31;
-  if (pm) {
-    int base = 0;
-    if (lane == __ffs(pm) - 1) base = atomicAdd(list_cnt, __popc(pm));
-    base = __shfl_sync(full, base, __ffs(pm) - 1);
-    if (push) list[base + __popc(pm & ((1u << lane) - 1u))] = (int32_t)e;
-  }
-  if (O.total_lookups) {
-    unsigned lk = decided ? (unsigned)n_last : 0u;
+  // undecided edges -> list: one atomic per CTA; counters likewise
+  unsigned pm[CTP_MID_IPT];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lk += __shfl_xor_sync(full, lk, o);
-    if (lane == 0 && lk) atomicAdd(O.total_lookups, (unsigned long long)lk);
+  for (int h = 0; h < CTP_MID_IPT; h++) {
+    pm[h] = __ballot_sync(full, valid[h] && !decided[h]);
+    if (lane == 0) s_push[h][wid] = __popc(pm[h]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lk += __shfl_xor_sync(full, lk, o);
+    dec += __shfl_xor_sync(full, dec, o);
+  }
+  __syncthreads();
+  if (lane == 0) {
+    if (lk) atomicAdd(&s_lk, lk);
+    if (dec) atomicAdd(&s_dec, dec);
+  }
+  if (threadIdx.x == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int h = 0; h < CTP_MID_IPT; h++)
+      for (int w2 = 0; w2 < CTP_MID_THREADS / 32; w2++) {
+        const int c = s_push[h][w2];
+        s_push[h][w2] = tot;
+        tot += c;
+      }
+    s_base = tot ? atomicAdd(list_cnt, tot) : 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < CTP_MID_IPT; h++)
+    if (valid[h] && !decided[h]) list[s_base + s_push[h][wid] + __popc(pm[h] & ((1u << lane) - 1u))] = (int32_t)e[h];
+  if (threadIdx.x == 0) {
+    if (O.total_lookups && s_lk) atomicAdd(O.total_lookups, (unsigned long long)s_lk);
+    if (stats) {
+      if (s_lk) atomicAdd(stats + 3, (unsigned long long)s_lk);
+      if (s_dec) atomicAdd(stats + 1, (unsigned long long)s_dec);
+      const uint32_t seen = min(m - min(tile0, m), (uint32_t)(CTP_MID_THREADS * CTP_MID_IPT));
+      atomicAdd(stats + 2, (unsigned long long)seen);
+    }
   }
 }
 

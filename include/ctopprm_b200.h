@@ -95,6 +95,11 @@ int ctp_reserve(ctp_map *map, int64_t q, int64_t n, int64_t m, int k);
 /* sum of ESDF lookups executed in reference order by edge-marching kernels since the last
  * reset (device counter; reading it synchronises the stream). */
 int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int reset);
+/* out[0] = roadmap edges the whole-edge float32 filter decided with certainty (free, one lookup each), out[1] = roadmap
+   edges it was shown, out[2] = the reference-order lookups (samples) of the decided edges, since the last reset; the other
+   edges were marched by the exact FP64 kernel.  Same verdicts either way (base_map.cpp:49-74); a diagnostic for the
+   bench line (lookups actually performed = out[1] + total lookups - out[2]). */
+int ctp_filter_counter_read(ctp_map *map, void *stream, uint64_t out[3], int reset);
 
 /* implementation knobs (defaults are the tuned ones; exposed for benchmarking) */
 #define CTP_TUNE_KNN_PER_CELL 0 /* k-NN grid: expected points inside a ball of one cell size (default 22) */
@@ -108,7 +113,7 @@ int ctp_lookup_counter_read(ctp_map *map, void *stream, uint64_t *lookups, int r
 #define CTP_TUNE_SEG_BIN 9       /* ctp_edge_check: bin the segments of a batch by the 16^3-voxel block of their midpoint before marching them (measured: no gain, the kernel is not bound by memory on such batches): 1 always, 0 never and the layout as set, -1 (default) never, but batches of >= 65536 segments on a grid > 100 MB read the CELL8 records when they were materialised */
 #define CTP_TUNE_CSR_PAIR_CAP 7  /* adjacency stage: capacity of the overflow list of rows with more than 16 incoming-only edges (0 = automatic: one pair per node; tests set it small to reach the full-scan fallback) */
 #define CTP_TUNE_PERQ_CLUSTER 8  /* per-query setup / scan kernels on a cluster of 8 CTAs per query: 1 always, 0 never, -1 automatic (default: few queries of >= 16384 points) */
-#define CTP_TUNE_EDGE_FILTER 11 /* flat edge kernel: 1 (default) = float32 verdict filter with a rigorous error bound in front of the exact FP64 evaluation (only undecided samples take the FP64 code; verdicts identical), 0 = every sample in FP64 */
+#define CTP_TUNE_EDGE_FILTER 11 /* roadmap edges (ctp_build_prm*, ctp_edge_check_knn_dev, ctp_prm_rows_dev): float32 whole-edge filter with rigorous error bounds in front of the exact FP64 kernel (a few lookups and a Lipschitz bound decide most free edges; the undecided ones are marched in FP64; verdicts identical): 1 (default) = where it pays (the first launch per threshold measures what the filter decides, one stream synchronisation), 2 = always, 0 = never */
 #define CTP_TUNE_PIPE_CHUNK 2   /* queries per chunk of the ctp_sample_multiple copy/compute pipeline (0 = automatic) */
 int ctp_set_tunable(ctp_map *map, int key, double value);
 /* number of kernels this handle has enqueued since the last reset (host-side counter) */

@@ -30,7 +30,7 @@ def _check(m, om, a, b, clr, cdc, layouts=LAYOUTS, mode=capi.EDGE_NODES):
     nbr = torch.from_numpy(np.concatenate([np.arange(cnt, 2 * cnt), np.arange(0, cnt)]).astype(np.int32)).to(dev)
     for layout in layouts:
         m.set_layout(layout)
-        for filt in (1, 0):
+        for filt in (2, 0):  # 2 = always (1 would drop the filter where its calibration says it does not pay)
             m.set_tunable(capi.TUNE_EDGE_FILTER, filt)
             m.read_lookups()
             free = torch.full((2 * cnt,), 7, dtype=torch.uint8, device=dev)
@@ -178,7 +178,7 @@ def test_filter_in_the_prm_build(orc, c1_map):
         cand = synth.ellipsoid_candidates(s, g, 30000, 21)
         nodes = om.sample_reject(s, g, cand, CLR, 5000)[0]
         want = om.build_prm(nodes, CLR, CDC, nthreads=8)
-        for filt in (1, 0):
+        for filt in (2, 0):  # 2 = always (1 would drop the filter where its calibration says it does not pay)
             m.set_tunable(capi.TUNE_EDGE_FILTER, filt)
             out = m.build_prm(nodes[None], CLR, CDC, k=13)
             nnz = int(out["nnz_off"][1])
