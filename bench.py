@@ -1416,8 +1416,8 @@ def main():
             "paths": paths_leg, "shortest_path": sssp_leg, "e2e_query": e2e_query,
             "lookups_per_s": lookups / (ms_max * 1e-3),
             "stage_ms_per_step": {k_: v / args.steps for k_, v in stage_ms.items()},
-            "roofline": {"bound": "hbm" if grid_in_hbm else "l2", "limiter": "dram gathers" if grid_in_hbm else "issue / fp64 pipe (grid L2-resident)",
-                         "kernel": "k_edge_flat" if dmap.prm_group() == 1 else "k_edge_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm" if grid_in_hbm else "l2", "limiter": "dram gathers" if grid_in_hbm else ("issue (grid L2-resident; float32 whole-edge filter + FP64 march of the rest)" if filt_seen else "issue / fp64 pipe (grid L2-resident)"),
+                         "kernel": ("k_edge_mid + k_edge_flat" if filt_seen else "k_edge_flat") if dmap.prm_group() == 1 else "k_edge_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "l2_bytes_per_launch": lts_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": alg_bytes / launches_edge,
