@@ -2252,8 +2252,10 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
   REQUIRE(cdc > 0, "collision_distance_check must be > 0");
   CK(cudaSetDevice(m->device));
   CKR(pipe_init(m));
-  // chunk size: about 8M directed edges per chunk, at least 1 query, at most 65535 (grid.y limits)
-  int64_t qc = m->pipe_chunk > 0 ? m->pipe_chunk : pipe_auto_chunk(q, n, k, 8 << 20);
+  // chunk size: about 16M directed edges per chunk, at least 1 query, at most 65535 (grid.y limits).  (C2, 512 queries:
+  // chunks of 16 / 32 / 64 / 128 queries give 3.4 / 4.6 / 5.6 / 6.0 G checks/s end to end -- every chunk costs the host
+  // a synchronisation on its accept counts and the device a drained compute stream.)
+  int64_t qc = m->pipe_chunk > 0 ? m->pipe_chunk : pipe_auto_chunk(q, n, k, 16 << 20);
   qc = std::min<int64_t>(std::min<int64_t>(qc, q), 65535);
   REQUIRE(qc * n * k < ((int64_t)1 << 31), "n*k too large for one chunk");
   // chunk boundaries: a short first chunk gets the device->host stream going early, the rest are qc long
