@@ -2125,6 +2125,18 @@ static int pipe_init(ctp_map *m) {
 }
 
 // pinned host staging of the per-chunk offsets and accept counts (two buffers of qc entries each)
+// small results the host waits for (accept counts, CSR offsets) are WRITTEN into mapped page-locked memory by a kernel on
+// the compute stream: a cudaMemcpyAsync of a few hundred bytes would queue behind the tens of megabytes of the previous
+// chunk's outputs on the device->host copy engine (measured: 0.6 ms per chunk with the compute stream drained)
+template <typename T>
+__global__ void k_to_host(const T *__restrict__ src, T *__restrict__ dst, int64_t cnt) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < cnt) dst[i] = src[i];
+}
+template <typename T> static void to_host(const T *src, T *dst_mapped, int64_t cnt, cudaStream_t st) {
+  if (cnt > 0) k_to_host<T><<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(src, dst_mapped, cnt);
+}
+
 static int pipe_host_staging(ctp_map *m, int64_t qc) {
   if (m->h_off_cap >= 2 * (qc + 1)) return CTP_OK;
   if (m->h_off) cudaFreeHost(m->h_off);
@@ -2132,8 +2144,9 @@ static int pipe_host_staging(ctp_map *m, int64_t qc) {
   m->h_off = nullptr;
   m->h_nf = nullptr;
   m->h_off_cap = 0;
-  CK(cudaHostAlloc((void **)&m->h_off, 2 * (qc + 1) * sizeof(int64_t), cudaHostAllocDefault));
-  CK(cudaHostAlloc((void **)&m->h_nf, 4 * (qc + 1) * sizeof(int32_t), cudaHostAllocDefault));  // accept counts, then n_used
+  CK(cudaHostAlloc((void **)&m->h_off, 2 * (qc + 1) * sizeof(int64_t), cudaHostAllocMapped));
+  // accept counts after the rejection (2 buffers), n_used (2), accept counts after the build (2)
+  CK(cudaHostAlloc((void **)&m->h_nf, 6 * (qc + 1) * sizeof(int32_t), cudaHostAllocMapped));
   m->h_off_cap = 2 * (qc + 1);
   return CTP_OK;
 }
@@ -2174,7 +2187,7 @@ static int64_t pipe_auto_chunk(int64_t q, int64_t n, int k, int64_t edges) {
 static int pipe_stage_a(ctp_map *m, PipeFront &b, int bi, const double *start, const double *goal, const double *cand,
                         int64_t q0, int64_t qn, int64_t cnt, int64_t n, double clr, bool wait_reuse, int32_t *h_nf,
                         int32_t *h_nu) {
-  cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1], s_small = m->pipe_st[3];
+  cudaStream_t s_in = m->pipe_st[0], s_comp = m->pipe_st[1];
   const int64_t head = pipe_head(m, n, cnt);
   b.head = head;
   if (wait_reuse) CK(cudaStreamWaitEvent(s_in, m->ev_comp[bi], 0));  // the staging buffer's last reader
@@ -2190,11 +2203,11 @@ static int pipe_stage_a(ctp_map *m, PipeFront &b, int bi, const double *start, c
   m->ws.used = 0;
   CK(cudaMemsetAsync(b.d_n, 0, qn * n * 24, s_comp));  // rows of a query that runs out of candidates stay defined
   CKR(sample_reject_launch(m, b.d_s, b.d_g, b.d_c, qn, head, cnt, clr, n, b.d_n, b.d_nf, b.d_nu, nullptr, s_comp));
-  CK(cudaEventRecord(m->ev_rejd[bi], s_comp));
-  CK(cudaStreamWaitEvent(s_small, m->ev_rejd[bi], 0));
-  CK(cudaMemcpyAsync(h_nf, b.d_nf, qn * 4, cudaMemcpyDeviceToHost, s_small));
-  CK(cudaMemcpyAsync(h_nu, b.d_nu, qn * 4, cudaMemcpyDeviceToHost, s_small));
-  CK(cudaEventRecord(m->ev_rej[bi], s_small));
+  to_host(b.d_nf, h_nf, qn, s_comp);
+  to_host(b.d_nu, h_nu, qn, s_comp);
+  m->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(m->ev_rej[bi], s_comp));
   return CTP_OK;
 }
 
@@ -2291,12 +2304,25 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
   int64_t base = 0;     // CSR entries emitted by the chunks finished so far
   int rc_deferred = CTP_OK;
   nnz_off[0] = 0;
+  // CTP_PIPE_TRACE=1: a timeline of the call on stderr (device time stamps of every chunk's phases)
+  struct TraceMark { const char *what; int64_t chunk; cudaEvent_t ev; };
+  std::vector<TraceMark> trace;
+  const bool tracing = getenv("CTP_PIPE_TRACE") != nullptr;
+  auto mark = [&](const char *what, int64_t c, cudaStream_t s) {
+    if (!tracing) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    trace.push_back({what, c, e});
+  };
+  mark("call start", -1, m->pipe_st[0]);
   // last part of a chunk: once its offsets are on the host, copy exactly nnz col/w entries out
   auto finish = [&](int64_t c) -> int {
     const int bi = (int)(c % nbuf);
     const int64_t q0 = cs[c], qn = cs[c + 1] - q0;
     CK(cudaEventSynchronize(m->ev_small[bi]));
     const int64_t *ho = m->h_off + (size_t)bi * (qc + 1);
+    memcpy(n_filled + q0, m->h_nf + (size_t)(4 + bi) * (qc + 1), (size_t)qn * 4);
     const int64_t nnz = ho[qn];
     for (int64_t i = 1; i <= qn; i++) nnz_off[q0 + i] = base + ho[i];
     if (base + nnz > cap) {
@@ -2307,6 +2333,7 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
       if (want_w) CK(cudaMemcpyAsync(w + base, B[bi].d_w, nnz * 8, cudaMemcpyDeviceToHost, s_out));
       m->io_d2h += (unsigned long long)nnz * (want_w ? 12 : 4);
     }
+    mark("d2h end", c, s_out);
     CK(cudaEventRecord(m->ev_out[bi], s_out));
     base += nnz;
     return CTP_OK;
@@ -2317,15 +2344,19 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
     const int64_t q0 = cs[c], qn = cs[c + 1] - q0;
     CKR(pipe_stage_b_refill(m, F[bi], bi, cand, q0, qn, cnt, n, clr, m->h_nf + (size_t)bi * qc,
                             m->h_nf + (size_t)(2 + bi) * (qc + 1)));
+    mark("build start", c, s_comp);
     CKR(ctp_build_prm_ex_dev(m, F[bi].d_n, qn, n, k, clr, cdc, csr_flags, nullptr, nullptr, B[bi].d_rp, B[bi].d_col,
                              B[bi].d_w, ecap, B[bi].d_off, s_comp));
+    mark("build end", c, s_comp);
+    to_host(B[bi].d_off, m->h_off + (size_t)bi * (qc + 1), qn + 1, s_comp);
+    to_host(F[bi].d_nf, m->h_nf + (size_t)(4 + bi) * (qc + 1), qn, s_comp);
+    m->launches += 2;
+    CK(cudaGetLastError());
     CK(cudaEventRecord(m->ev_comp[bi], s_comp));
+    CK(cudaEventRecord(m->ev_small[bi], s_comp));
     if (c >= 1) CKR(finish(c - 1));
-    CK(cudaStreamWaitEvent(s_small, m->ev_comp[bi], 0));
-    CK(cudaMemcpyAsync(m->h_off + (size_t)bi * (qc + 1), B[bi].d_off, (qn + 1) * 8, cudaMemcpyDeviceToHost, s_small));
-    CK(cudaMemcpyAsync(n_filled + q0, F[bi].d_nf, qn * 4, cudaMemcpyDeviceToHost, s_small));
-    CK(cudaEventRecord(m->ev_small[bi], s_small));
     CK(cudaStreamWaitEvent(s_out, m->ev_comp[bi], 0));
+    mark("d2h start", c, s_out);
     CK(cudaMemcpyAsync(nodes + 3 * q0 * n, F[bi].d_n, qn * n * 24, cudaMemcpyDeviceToHost, s_out));
     CK(cudaMemcpyAsync(row_ptr + q0 * (n + 1), B[bi].d_rp, qn * (n + 1) * 4, cudaMemcpyDeviceToHost, s_out));
     m->io_d2h += (unsigned long long)qn * (n * 24 + (n + 1) * 4 + 4) + (unsigned long long)(qn + 1) * 8;
@@ -2337,14 +2368,25 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
     if (c < n_chunks) {
       const int bi = (int)(c % nbuf);
       const int64_t q0 = cs[c], qn = cs[c + 1] - q0;
+      mark("h2d start", c, m->pipe_st[0]);
       CKR(pipe_stage_a(m, F[bi], bi, start, goal, cand, q0, qn, cnt, n, clr, c >= nbuf, m->h_nf + (size_t)bi * qc,
                        m->h_nf + (size_t)(2 + bi) * (qc + 1)));
+      mark("h2d end", c, m->pipe_st[0]);
+      mark("reject end", c, s_comp);
     }
   }
   CKR(finish(n_chunks - 1));
   CK(cudaStreamSynchronize(s_out));
   CK(cudaStreamSynchronize(s_small));
   CK(cudaStreamSynchronize(s_comp));
+  if (tracing) {
+    for (const TraceMark &tm : trace) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, trace[0].ev, tm.ev);
+      fprintf(stderr, "[ctp pipe] %8.3f ms  chunk %2lld  %s\n", ms, (long long)tm.chunk, tm.what);
+    }
+    for (const TraceMark &tm : trace) cudaEventDestroy(tm.ev);
+  }
   if (rc_deferred != CTP_OK) return rc_deferred;
   for (int64_t i = 0; i < q; i++)
     if (n_filled[i] < n)
