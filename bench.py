@@ -1219,13 +1219,19 @@ def main():
             return {"value": checks_per_step * world * reps / dt, "unit": UNIT, "h2d_bytes_per_step": int(io_h2d // reps),
                     "d2h_bytes_per_step": int(io_d2h // reps), "ms_per_step": 1e3 * dt / reps, "steps": reps}
 
-        compact = capi.CSR_UPPER | capi.CSR_NO_WEIGHTS
-        out_c = dict(nodes=capi.pinned_empty((q, n, 3), np.float64), n_filled=capi.pinned_empty((q,), np.int32),
-                     row_ptr=capi.pinned_empty((q, n + 1), np.int32), col=capi.pinned_empty((cap // 2,), np.int32),
+        # compact wire form: each undirected edge once, no weights, 16-bit columns where the ids fit, nodes as positions
+        # in the candidate streams the host already holds
+        c16 = n <= 65536
+        compact = capi.CSR_UPPER | capi.CSR_NO_WEIGHTS | capi.NODES_AS_INDEX | (capi.CSR_COL16 if c16 else 0)
+        out_c = dict(nodes=capi.pinned_empty((q, n), np.int32), n_filled=capi.pinned_empty((q,), np.int32),
+                     row_ptr=capi.pinned_empty((q, n + 1), np.int32),
+                     col=capi.pinned_empty((cap // 2,), np.uint16 if c16 else np.int32),
                      nnz_off=capi.pinned_empty((q + 1,), np.int64))
         e2e = time_e2e(compact, out_c, k2)
-        e2e["api"] = ("ctp_sample_multiple_ex(CTP_CSR_UPPER | CTP_CSR_NO_WEIGHTS): host candidate streams -> host nodes + compact "
-                      "adjacency (each undirected edge once; weights recomputable from the nodes), wall clock, max over ranks")
+        e2e["api"] = ("ctp_sample_multiple_ex(CTP_CSR_UPPER | CTP_CSR_NO_WEIGHTS | CTP_NODES_AS_INDEX" + (" | CTP_CSR_COL16" if c16 else "") +
+                      "): host candidate streams -> host roadmap in the compact wire form (accepted nodes as positions in their "
+                      "candidate streams, each undirected edge once" + (", 16-bit columns" if c16 else "") + "; weights recomputable "
+                      "from the nodes), wall clock, max over ranks")
         assert 2 * int(out_c["nnz_off"][q]) == nnz_total, "compact host-API adjacency differs from the device-API CSR"
         if rank == 0 and world == 1:
             # the host-side mirror back to the full symmetric weighted CSR (not part of the timed call: a consumer that
@@ -1234,9 +1240,13 @@ def main():
             thr = cpu_cores()
             full_h = dict(row_ptr=np.empty((q, n + 1), dtype=np.int32), col=np.empty(nnz_total, dtype=np.int32),
                           w=np.empty(nnz_total), nnz_off=np.empty(q + 1, dtype=np.int64))
-            hostlib.csr_expand_upper(out_c["nodes"], out_c["row_ptr"], out_c["col"], out_c["nnz_off"], threads=thr, out=full_h)
             t0 = time.perf_counter()
-            hostlib.csr_expand_upper(out_c["nodes"], out_c["row_ptr"], out_c["col"], out_c["nnz_off"], threads=thr, out=full_h)
+            nodes_h = capi.nodes_from_index(out_c["nodes"], cand_h, s_h, g_h)
+            col_h = out_c["col"][:nnz_total // 2].astype(np.int32)
+            e2e["host_unpack_ms"] = 1e3 * (time.perf_counter() - t0)  # numpy, one thread (include/ctopprm/csr_expand.hpp has the C++ form)
+            hostlib.csr_expand_upper(nodes_h, out_c["row_ptr"], col_h, out_c["nnz_off"], threads=thr, out=full_h)
+            t0 = time.perf_counter()
+            hostlib.csr_expand_upper(nodes_h, out_c["row_ptr"], col_h, out_c["nnz_off"], threads=thr, out=full_h)
             e2e["host_mirror_ms"] = 1e3 * (time.perf_counter() - t0)
             e2e["host_mirror_threads"] = thr
             same = (np.array_equal(full_h["row_ptr"], row_ptr_d.cpu().numpy())
@@ -1245,7 +1255,7 @@ def main():
             e2e["host_mirror_equals_device_csr"] = bool(same)
             del full_h
         if not args.no_e2e_full:
-            out_f = dict(nodes=out_c["nodes"], n_filled=out_c["n_filled"], row_ptr=out_c["row_ptr"],
+            out_f = dict(nodes=capi.pinned_empty((q, n, 3), np.float64), n_filled=out_c["n_filled"], row_ptr=out_c["row_ptr"],
                          col=capi.pinned_empty((cap,), np.int32), w=capi.pinned_empty((cap,), np.float64),
                          nnz_off=out_c["nnz_off"])
             e2e_full = time_e2e(0, out_f, max(2, k2 // 2))

@@ -12,7 +12,7 @@ LAYOUT_PLAIN, LAYOUT_CELL8, LAYOUT_TEX, LAYOUT_BRICK = 1, 2, 4, 8
 LAYOUT_NAMES = {1: "plain", 2: "cell8", 4: "tex", 8: "brick"}
 DEFAULT_LAYOUT = LAYOUT_TEX  # the layout bench.py uses unless told otherwise (fastest measured; n <= 1024)
 EDGE_NODES, EDGE_GUARDS = 0, 1
-CSR_UPPER, CSR_NO_WEIGHTS = 1, 2
+CSR_UPPER, CSR_NO_WEIGHTS, CSR_COL16, NODES_AS_INDEX = 1, 2, 4, 8
 TUNE_KNN_PER_CELL, TUNE_KNN_TILE, TUNE_PIPE_CHUNK, TUNE_EDGE_ORDER, TUNE_SSSP_FRONTIER, TUNE_PIPE_HEAD, TUNE_SSSP_CLUSTER = 0, 1, 2, 3, 4, 5, 6
 TUNE_CSR_PAIR_CAP, TUNE_PERQ_CLUSTER, TUNE_SEG_BIN, TUNE_KNN_RADIUS, TUNE_EDGE_FILTER = 7, 8, 9, 10, 11
 ERR_NEED_CANDIDATES = -4
@@ -156,6 +156,22 @@ def pinned_empty(shape, dtype):
     import weakref
     weakref.finalize(buf, lambda addr=p.value: lib().ctp_host_free(C.c_void_p(addr)))
     return arr
+
+
+def nodes_from_index(node_src, cand, start, goal):
+    """coordinates of the nodes a NODES_AS_INDEX call reported by position in the candidate streams
+    (include/ctopprm/csr_expand.hpp: nodes_from_index)"""
+    node_src = np.asarray(node_src)
+    q, n = node_src.shape
+    cand = np.asarray(cand, dtype=np.float64).reshape(q, -1, 3)
+    nodes = np.zeros((q, n, 3))
+    for i in range(q):
+        s = node_src[i]
+        ok = s >= 0
+        nodes[i, ok] = cand[i, s[ok]]
+        nodes[i, s == -2] = np.asarray(start, dtype=np.float64).reshape(-1, 3)[i]
+        nodes[i, s == -3] = np.asarray(goal, dtype=np.float64).reshape(-1, 3)[i]
+    return nodes
 
 
 def exported_symbols():
@@ -516,7 +532,9 @@ class DeviceMap:
 
     def sample_multiple(self, start, goal, cand, n, clr, cdc, k=13, out=None, csr_flags=0):
         """TopologicalPRMClustering::sampleMultiple from host candidates to host CSR
-        (csr_flags: CSR_UPPER / CSR_NO_WEIGHTS select the compact forms of the adjacency)."""
+        (csr_flags: CSR_UPPER / CSR_NO_WEIGHTS select the compact forms of the adjacency; CSR_COL16: out["col"] is a
+        uint16 array; NODES_AS_INDEX: out["nodes"] is an int32 (q, n) array of candidate positions, see
+        nodes_from_index)."""
         start = _np(start, np.float64).reshape(-1, 3)
         goal = _np(goal, np.float64).reshape(-1, 3)
         q = len(start)
@@ -524,9 +542,12 @@ class DeviceMap:
         m = cand.shape[1]
         cap = 2 * q * n * k
         if out is None:
-            out = dict(nodes=np.empty((q, n, 3)), n_filled=np.empty(q, dtype=np.int32),
-                       row_ptr=np.empty((q, n + 1), dtype=np.int32), col=np.empty(cap, dtype=np.int32),
-                       w=np.empty(cap), nnz_off=np.empty(q + 1, dtype=np.int64))
+            out = dict(nodes=np.empty((q, n), dtype=np.int32) if csr_flags & NODES_AS_INDEX else np.empty((q, n, 3)),
+                       n_filled=np.empty(q, dtype=np.int32), row_ptr=np.empty((q, n + 1), dtype=np.int32),
+                       col=np.empty(cap, dtype=np.uint16 if csr_flags & CSR_COL16 else np.int32),
+                       w=None if csr_flags & CSR_NO_WEIGHTS else np.empty(cap), nnz_off=np.empty(q + 1, dtype=np.int64))
+        assert out["col"].dtype == (np.uint16 if csr_flags & CSR_COL16 else np.int32)
+        assert out["nodes"].dtype == (np.int32 if csr_flags & NODES_AS_INDEX else np.float64)
         cap = min(cap, out["col"].size)
         _check(lib().ctp_sample_multiple_ex(self._h, _ptr(start), _ptr(goal), _ptr(cand), q, m, n, k, clr, cdc, csr_flags,
                                             _ptr(out["nodes"]), _ptr(out["n_filled"]), _ptr(out["row_ptr"]),

@@ -1168,7 +1168,7 @@ extern "C" int ctp_reserve(ctp_map *m, int64_t q, int64_t n, int64_t cand, int k
 // rejection over the first cnt candidates of each stream; streams are `stride` candidates apart
 static int sample_reject_launch(ctp_map *m, const double *start, const double *goal, const double *cand, int64_t q,
                                 int64_t cnt, int64_t stride, double clr, int64_t n, double *nodes, int32_t *n_filled,
-                                int32_t *n_used, uint8_t *accept, cudaStream_t st) {
+                                int32_t *n_used, uint8_t *accept, cudaStream_t st, int32_t *src_idx = nullptr) {
   const int nblk = (int)std::max<int64_t>(1, (cnt + CTP_REJ_BLOCK - 1) / CTP_REJ_BLOCK);
   const size_t keep = m->ws.used;
   CKR(arena_reserve(m->ws, keep + ws_bytes_reject(q, cnt) + 512));
@@ -1195,7 +1195,7 @@ static int sample_reject_launch(ctp_map *m, const double *start, const double *g
   // n_used defaults to "whole stream consumed"; the scatter pass overwrites it when n-2 were found
   k_fill_i32<<<grid_for(q, 256, 1024), 256, 0, st>>>(n_used, q, n == 2 ? 0 : (int32_t)cnt);  // n == 2: the loop of :309 never runs
   m->launches++;
-  k_reject_scatter<<<grid, CTP_REJ_BLOCK, 0, st>>>(cand, start, goal, d_acc, d_bc, nblk, cnt, stride, n, nodes, n_used);
+  k_reject_scatter<<<grid, CTP_REJ_BLOCK, 0, st>>>(cand, start, goal, d_acc, d_bc, nblk, cnt, stride, n, nodes, n_used, src_idx);
   m->launches++;
   CK(cudaGetLastError());
   return CTP_OK;
@@ -2128,6 +2128,15 @@ static int pipe_init(ctp_map *m) {
 // small results the host waits for (accept counts, CSR offsets) are WRITTEN into mapped page-locked memory by a kernel on
 // the compute stream: a cudaMemcpyAsync of a few hundred bytes would queue behind the tens of megabytes of the previous
 // chunk's outputs on the device->host copy engine (measured: 0.6 ms per chunk with the compute stream drained)
+// int32 column ids -> uint16 (CTP_CSR_COL16), four per thread
+__global__ void __launch_bounds__(256) k_narrow_u16(const int32_t *__restrict__ in, int64_t cnt, uint16_t *__restrict__ out) {
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < cnt; i += (int64_t)gridDim.x * blockDim.x * 4) {
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i + u < cnt) out[i + u] = (uint16_t)in[i + u];
+  }
+}
+
 template <typename T>
 __global__ void k_to_host(const T *__restrict__ src, T *__restrict__ dst, int64_t cnt) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -2160,6 +2169,7 @@ static int pipe_host_staging(ctp_map *m, int64_t qc) {
 struct PipeFront {
   double *d_s, *d_g, *d_c, *d_n;
   int32_t *d_nf, *d_nu;
+  int32_t *d_src = nullptr;  // optional: candidate index of every accepted node (CTP_NODES_AS_INDEX)
   int64_t head = 0;  // candidates per query uploaded up front for the chunk now in this buffer
 };
 
@@ -2202,7 +2212,8 @@ static int pipe_stage_a(ctp_map *m, PipeFront &b, int bi, const double *start, c
   if (wait_reuse) CK(cudaStreamWaitEvent(s_comp, m->ev_out[bi], 0));  // outputs of the buffer's previous chunk have left
   m->ws.used = 0;
   CK(cudaMemsetAsync(b.d_n, 0, qn * n * 24, s_comp));  // rows of a query that runs out of candidates stay defined
-  CKR(sample_reject_launch(m, b.d_s, b.d_g, b.d_c, qn, head, cnt, clr, n, b.d_n, b.d_nf, b.d_nu, nullptr, s_comp));
+  if (b.d_src) CK(cudaMemsetAsync(b.d_src, 0xff, qn * n * 4, s_comp));  // -1 = no node
+  CKR(sample_reject_launch(m, b.d_s, b.d_g, b.d_c, qn, head, cnt, clr, n, b.d_n, b.d_nf, b.d_nu, nullptr, s_comp, b.d_src));
   to_host(b.d_nf, h_nf, qn, s_comp);
   to_host(b.d_nu, h_nu, qn, s_comp);
   m->launches += 2;
@@ -2243,7 +2254,8 @@ static int pipe_stage_b_refill(ctp_map *m, const PipeFront &b, int bi, const dou
   CK(cudaStreamWaitEvent(s_comp, m->ev_in[bi], 0));
   m->ws.used = 0;
   CK(cudaMemsetAsync(b.d_n, 0, qn * n * 24, s_comp));
-  CKR(sample_reject_launch(m, b.d_s, b.d_g, b.d_c, qn, cnt, cnt, clr, n, b.d_n, b.d_nf, b.d_nu, nullptr, s_comp));
+  if (b.d_src) CK(cudaMemsetAsync(b.d_src, 0xff, qn * n * 4, s_comp));
+  CKR(sample_reject_launch(m, b.d_s, b.d_g, b.d_c, qn, cnt, cnt, clr, n, b.d_n, b.d_nf, b.d_nu, nullptr, s_comp, b.d_src));
   return CTP_OK;
 }
 
@@ -2259,8 +2271,11 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
                                       double *nodes, int32_t *n_filled, int32_t *row_ptr, int32_t *col, double *w,
                                       int64_t cap, int64_t *nnz_off) {
   REQUIRE(m && q >= 1 && n >= 2 && cnt >= 0 && k >= 1 && k <= CTP_KNN_MAXK, "bad argument");
-  REQUIRE((csr_flags & ~(CTP_CSR_UPPER | CTP_CSR_NO_WEIGHTS)) == 0, "unknown csr_flags bits");
+  REQUIRE((csr_flags & ~(CTP_CSR_UPPER | CTP_CSR_NO_WEIGHTS | CTP_CSR_COL16 | CTP_NODES_AS_INDEX)) == 0, "unknown csr_flags bits");
   const bool want_w = !(csr_flags & CTP_CSR_NO_WEIGHTS);
+  const bool col16 = (csr_flags & CTP_CSR_COL16) != 0, node_idx = (csr_flags & CTP_NODES_AS_INDEX) != 0;
+  REQUIRE(!col16 || n <= 65536, "CTP_CSR_COL16 needs n <= 65536");
+  const int build_flags = csr_flags & (CTP_CSR_UPPER | CTP_CSR_NO_WEIGHTS);
   REQUIRE(start && goal && cand && nodes && n_filled && row_ptr && col && (w || !want_w) && nnz_off, "null buffer");
   REQUIRE(cdc > 0, "collision_distance_check must be > 0");
   CK(cudaSetDevice(m->device));
@@ -2281,13 +2296,14 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
   m->pipe_nu_seen = 0;  // the up-front share of the streams adapts within this call only
   const int64_t ecap = ((csr_flags & CTP_CSR_UPPER) ? 1 : 2) * qc * n * k;  // CSR entries a chunk can produce
   size_t per = 2 * align_up(qc * 24) + align_up(qc * cnt * 24) + align_up(qc * n * 24) + 2 * align_up(qc * 4) +
-               align_up(qc * (n + 1) * 4) + align_up(ecap * 4) + (want_w ? align_up(ecap * 8) : 0) + align_up((qc + 1) * 8);
+               align_up(qc * (n + 1) * 4) + align_up(ecap * 4) + (want_w ? align_up(ecap * 8) : 0) + align_up((qc + 1) * 8) +
+               (node_idx ? align_up(qc * n * 4) : 0) + (col16 ? align_up(ecap * 2) : 0);
   CKR(arena_reserve(m->io, nbuf * per + 4096));
   CKR(ctp_reserve(m, qc, n, cnt, k));
   CKR(pipe_host_staging(m, qc));
   IoScope sc(m);
   PipeFront F[2];
-  struct { int32_t *d_rp, *d_col; double *d_w; int64_t *d_off; } B[2];
+  struct { int32_t *d_rp, *d_col; double *d_w; int64_t *d_off; uint16_t *d_col16; } B[2];
   for (int i = 0; i < nbuf; i++) {
     F[i].d_s = arena_take<double>(m->io, qc * 3);
     F[i].d_g = arena_take<double>(m->io, qc * 3);
@@ -2295,10 +2311,12 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
     F[i].d_n = arena_take<double>(m->io, qc * n * 3);
     F[i].d_nf = arena_take<int32_t>(m->io, qc);
     F[i].d_nu = arena_take<int32_t>(m->io, qc);
+    F[i].d_src = node_idx ? arena_take<int32_t>(m->io, qc * n) : nullptr;
     B[i].d_rp = arena_take<int32_t>(m->io, qc * (n + 1));
     B[i].d_col = arena_take<int32_t>(m->io, ecap);
     B[i].d_w = want_w ? arena_take<double>(m->io, ecap) : nullptr;
     B[i].d_off = arena_take<int64_t>(m->io, qc + 1);
+    B[i].d_col16 = col16 ? arena_take<uint16_t>(m->io, ecap) : nullptr;
   }
   cudaStream_t s_comp = m->pipe_st[1], s_out = m->pipe_st[2], s_small = m->pipe_st[3];
   int64_t base = 0;     // CSR entries emitted by the chunks finished so far
@@ -2329,9 +2347,10 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
       if (rc_deferred == CTP_OK)
         rc_deferred = fail(CTP_ERR_CAPACITY, "CSR needs more than %lld entries", (long long)cap);
     } else if (nnz) {
-      CK(cudaMemcpyAsync(col + base, B[bi].d_col, nnz * 4, cudaMemcpyDeviceToHost, s_out));
+      if (col16) CK(cudaMemcpyAsync((uint16_t *)col + base, B[bi].d_col16, nnz * 2, cudaMemcpyDeviceToHost, s_out));
+      else CK(cudaMemcpyAsync(col + base, B[bi].d_col, nnz * 4, cudaMemcpyDeviceToHost, s_out));
       if (want_w) CK(cudaMemcpyAsync(w + base, B[bi].d_w, nnz * 8, cudaMemcpyDeviceToHost, s_out));
-      m->io_d2h += (unsigned long long)nnz * (want_w ? 12 : 4);
+      m->io_d2h += (unsigned long long)nnz * ((want_w ? 8 : 0) + (col16 ? 2 : 4));
     }
     mark("d2h end", c, s_out);
     CK(cudaEventRecord(m->ev_out[bi], s_out));
@@ -2345,8 +2364,13 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
     CKR(pipe_stage_b_refill(m, F[bi], bi, cand, q0, qn, cnt, n, clr, m->h_nf + (size_t)bi * qc,
                             m->h_nf + (size_t)(2 + bi) * (qc + 1)));
     mark("build start", c, s_comp);
-    CKR(ctp_build_prm_ex_dev(m, F[bi].d_n, qn, n, k, clr, cdc, csr_flags, nullptr, nullptr, B[bi].d_rp, B[bi].d_col,
+    CKR(ctp_build_prm_ex_dev(m, F[bi].d_n, qn, n, k, clr, cdc, build_flags, nullptr, nullptr, B[bi].d_rp, B[bi].d_col,
                              B[bi].d_w, ecap, B[bi].d_off, s_comp));
+    if (col16) {  // the chunk's whole column buffer (its nnz is not known on the host yet; what lies beyond is never copied)
+      const int64_t ce = ((csr_flags & CTP_CSR_UPPER) ? 1 : 2) * qn * n * k;
+      k_narrow_u16<<<(unsigned)std::min<int64_t>((ce + 1023) / 1024, 65535 * 4), 256, 0, s_comp>>>(B[bi].d_col, ce, B[bi].d_col16);
+      m->launches++;
+    }
     mark("build end", c, s_comp);
     to_host(B[bi].d_off, m->h_off + (size_t)bi * (qc + 1), qn + 1, s_comp);
     to_host(F[bi].d_nf, m->h_nf + (size_t)(4 + bi) * (qc + 1), qn, s_comp);
@@ -2357,9 +2381,10 @@ extern "C" int ctp_sample_multiple_ex(ctp_map *m, const double *start, const dou
     if (c >= 1) CKR(finish(c - 1));
     CK(cudaStreamWaitEvent(s_out, m->ev_comp[bi], 0));
     mark("d2h start", c, s_out);
-    CK(cudaMemcpyAsync(nodes + 3 * q0 * n, F[bi].d_n, qn * n * 24, cudaMemcpyDeviceToHost, s_out));
+    if (node_idx) CK(cudaMemcpyAsync((int32_t *)nodes + q0 * n, F[bi].d_src, qn * n * 4, cudaMemcpyDeviceToHost, s_out));
+    else CK(cudaMemcpyAsync(nodes + 3 * q0 * n, F[bi].d_n, qn * n * 24, cudaMemcpyDeviceToHost, s_out));
     CK(cudaMemcpyAsync(row_ptr + q0 * (n + 1), B[bi].d_rp, qn * (n + 1) * 4, cudaMemcpyDeviceToHost, s_out));
-    m->io_d2h += (unsigned long long)qn * (n * 24 + (n + 1) * 4 + 4) + (unsigned long long)(qn + 1) * 8;
+    m->io_d2h += (unsigned long long)qn * (n * (node_idx ? 4 : 24) + (n + 1) * 4 + 4) + (unsigned long long)(qn + 1) * 8;
     return CTP_OK;
   };
   for (int64_t c = 0; c <= n_chunks; c++) {

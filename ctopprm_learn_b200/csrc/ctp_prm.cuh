@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(CTP_REJ_BLOCK)
 k_reject_scatter(const double *__restrict__ cand, const double *__restrict__ start,
                  const double *__restrict__ goal, const uint8_t *__restrict__ accept,
                  const int32_t *__restrict__ block_off, int nblk, int64_t m, int64_t stride, int64_t n,
-                 double *__restrict__ nodes, int32_t *__restrict__ n_used) {
+                 double *__restrict__ nodes, int32_t *__restrict__ n_used, int32_t *__restrict__ src_idx) {
   const int64_t q = blockIdx.y;
   const int64_t i = blockIdx.x * (int64_t)CTP_REJ_BLOCK + threadIdx.x;
   const bool ok = i < m && accept[q * m + i];
@@ -104,12 +104,14 @@ k_reject_scatter(const double *__restrict__ cand, const double *__restrict__ sta
     o[0] = p[0];
     o[1] = p[1];
     o[2] = p[2];
+    if (src_idx) src_idx[q * n + 2 + rank] = (int32_t)i;  // which candidate of the stream this node is
     if (rank == n - 3) n_used[q] = (int32_t)(i + 1);  // the do/while stops right here
   }
   if (blockIdx.x == 0 && threadIdx.x < 3) {
     nq[threadIdx.x] = start[3 * q + threadIdx.x];
     nq[3 + threadIdx.x] = goal[3 * q + threadIdx.x];
   }
+  if (src_idx && blockIdx.x == 0 && threadIdx.x < 2) src_idx[q * n + threadIdx.x] = -2 - (int)threadIdx.x;  // start, goal
 }
 
 // =========================== exact float32 k-NN (:329-339) ================================

@@ -65,4 +65,23 @@ inline void csr_expand_upper(const double *nodes, int64_t q, int64_t n, const in
   for (auto &th : pool) th.join();
 }
 
+// The wire formats CTP_NODES_AS_INDEX / CTP_CSR_COL16 of ctp_sample_multiple_ex back into what csr_expand_upper takes:
+// node coordinates gathered from the candidate streams the host already holds (cand q x m x 3; -2 = start, -3 = goal,
+// -1 = row not filled -> zeros, as the coordinate form leaves them), 16-bit column ids widened.
+inline void nodes_from_index(const int32_t *node_src, int64_t q, int64_t n, const double *cand, int64_t m,
+                             const double *start, const double *goal, double *nodes) {
+  for (int64_t i = 0; i < q; i++)
+    for (int64_t r = 0; r < n; r++) {
+      const int32_t s = node_src[i * n + r];
+      const double *p = s >= 0 ? cand + 3 * (i * m + s) : (s == -2 ? start + 3 * i : (s == -3 ? goal + 3 * i : nullptr));
+      double *o = nodes + 3 * (i * n + r);
+      o[0] = p ? p[0] : 0.0;
+      o[1] = p ? p[1] : 0.0;
+      o[2] = p ? p[2] : 0.0;
+    }
+}
+inline void widen_col16(const uint16_t *col16, int64_t nnz, int32_t *col) {
+  for (int64_t e = 0; e < nnz; e++) col[e] = (int32_t)col16[e];
+}
+
 }  // namespace ctopprm

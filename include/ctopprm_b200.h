@@ -231,6 +231,13 @@ int ctp_build_prm_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, i
  * include/ctopprm/csr_expand.hpp mirrors a compact roadmap into the full symmetric, weighted CSR on the host. */
 #define CTP_CSR_UPPER 1
 #define CTP_CSR_NO_WEIGHTS 2
+/* wire formats of the host-pointer call ctp_sample_multiple_ex only (fewer bytes over the host link; with 8 GPUs on one
+ * host the link, not the GPUs, bounds the end-to-end rate):
+ *   CTP_CSR_COL16       n <= 65536: `col` receives uint16_t entries (the buffer is read as uint16_t *, cap counts entries)
+ *   CTP_NODES_AS_INDEX  `nodes` receives, as int32_t q x n, the position of every accepted node in its query's candidate
+ *                       stream (-2 = start, -3 = goal, -1 = row not filled) instead of coordinates the host already has */
+#define CTP_CSR_COL16 4
+#define CTP_NODES_AS_INDEX 8
 int ctp_build_prm_ex_dev(ctp_map *map, const double *nodes, int64_t q, int64_t n, int k, double clr,
                          double cdc, int csr_flags, int32_t *nbr, uint8_t *directed_free, int32_t *row_ptr,
                          int32_t *col, double *w, int64_t cap, int64_t *nnz_off, void *stream);

@@ -1466,3 +1466,29 @@ def test_radius_neighbour_mode(c1, orc, radius):
         a, b = int(got["nnz_off"][qi]), int(got["nnz_off"][qi + 1])
         assert np.array_equal(got["row_ptr"][qi], rp) and np.array_equal(got["col"][a:b], col) and np.array_equal(got["w"][a:b], w)
     assert (dropped > 0) == (radius < 5.0)
+
+
+@pytest.mark.parametrize("chunk", [0, 3])
+def test_sample_multiple_wire_formats(c1, chunk):
+    """CTP_CSR_COL16 / CTP_NODES_AS_INDEX: 16-bit columns and candidate positions instead of coordinates carry the same
+    roadmap as the plain call"""
+    m, om, c, e = c1
+    m.set_layout(capi.LAYOUT_TEX)
+    q, n = 7, 900
+    rng = np.random.default_rng(31)
+    s = c + (rng.random((q, 3)) - 0.5) * e * 0.5
+    g = c + (rng.random((q, 3)) - 0.5) * e * 0.5
+    cand = np.stack([synth.ellipsoid_candidates(s[i], g[i], 6 * n, 500 + i) for i in range(q)])
+    m.set_tunable(capi.TUNE_PIPE_CHUNK, chunk)
+    try:
+        ref = m.sample_multiple(s, g, cand, n, CLR, CDC, csr_flags=capi.CSR_UPPER | capi.CSR_NO_WEIGHTS)
+        flags = capi.CSR_UPPER | capi.CSR_NO_WEIGHTS | capi.CSR_COL16 | capi.NODES_AS_INDEX
+        out = m.sample_multiple(s, g, cand, n, CLR, CDC, csr_flags=flags)
+    finally:
+        m.set_tunable(capi.TUNE_PIPE_CHUNK, 0)
+    nnz = int(ref["nnz_off"][q])
+    assert np.array_equal(out["nnz_off"], ref["nnz_off"]) and np.array_equal(out["row_ptr"], ref["row_ptr"])
+    assert np.array_equal(out["n_filled"], ref["n_filled"])
+    assert out["col"].dtype == np.uint16 and np.array_equal(out["col"][:nnz].astype(np.int32), ref["col"][:nnz])
+    assert np.array_equal(capi.nodes_from_index(out["nodes"], cand, s, g), ref["nodes"])
+    assert np.array_equal(out["nodes"][:, 0], np.full(q, -2)) and np.array_equal(out["nodes"][:, 1], np.full(q, -3))
