@@ -95,6 +95,7 @@ _SIGS = {
     "ctp_sample_path": [_P, _P, _P, _P, _P, _I64, _P, _P, _P],
     "ctp_deformable": [_P, _P, _P, _P, _I64, _P, _P, _P, _I64, _D, _D, _P],
     "ctp_shorten_path": [_P, _P, _P, _P, _I64, _I, _D, _D, C.c_int32, _P, _P, _P, _P, _P],
+    "ctp_shorten_path_ex": [_P, _P, _P, _P, _I64, _I, _P, _D, _D, C.c_int32, _P, _P, _P, _P, _P],
 }
 
 

@@ -217,11 +217,12 @@ k_deformable(MapDev M, const double *__restrict__ pts, const int32_t *__restrict
 template <int L>
 __global__ void __launch_bounds__(CTP_PATH_BLOCK)
 k_shorten(MapDev M, const double *__restrict__ pts, const int32_t *__restrict__ off,
-          const double *__restrict__ length, int forward, double clr, double cdc, int32_t cap,
-          const int64_t *__restrict__ scratch_off, double *__restrict__ scratch, double *__restrict__ out,
-          int32_t *__restrict__ origin, int32_t *__restrict__ out_n, double *__restrict__ out_len,
-          int32_t *__restrict__ status) {
+          const double *__restrict__ length, int forward_all, const uint8_t *__restrict__ forward_each, double clr,
+          double cdc, int32_t cap, const int64_t *__restrict__ scratch_off, double *__restrict__ scratch,
+          double *__restrict__ out, int32_t *__restrict__ origin, int32_t *__restrict__ out_n,
+          double *__restrict__ out_len, int32_t *__restrict__ status) {
   const int pi = blockIdx.x;
+  const int forward = forward_each ? (int)forward_each[pi] : forward_all;  // per polyline, or one direction for the batch
   const int npts = off[pi + 1] - off[pi];
   const double *P = pts + 3 * (size_t)off[pi];
   const double len = length[pi];

@@ -89,6 +89,13 @@ extern "C" int ctp_deformable(ctp_map *m, const double *pts, const int32_t *off,
 extern "C" int ctp_shorten_path(ctp_map *m, const double *pts, const int32_t *off, const double *length,
                                 int64_t count, int forward, double clr, double cdc, int32_t cap, double *out,
                                 int32_t *origin, int32_t *out_n, double *out_len, int32_t *status) {
+  return ctp_shorten_path_ex(m, pts, off, length, count, forward, nullptr, clr, cdc, cap, out, origin, out_n, out_len, status);
+}
+
+extern "C" int ctp_shorten_path_ex(ctp_map *m, const double *pts, const int32_t *off, const double *length,
+                                   int64_t count, int forward, const uint8_t *forward_each, double clr, double cdc,
+                                   int32_t cap, double *out, int32_t *origin, int32_t *out_n, double *out_len,
+                                   int32_t *status) {
   REQUIRE(m && count >= 0 && cap >= 2, "bad argument");
   if (count == 0) return CTP_OK;
   REQUIRE(pts && off && length && out && origin && out_n && out_len && status, "null buffer");
@@ -105,7 +112,7 @@ extern "C" int ctp_shorten_path(ctp_map *m, const double *pts, const int32_t *of
   const int64_t total = off[count];
   CKR(arena_reserve(m->io, align_up(total * 24) + align_up((count + 1) * 4) + 2 * align_up(count * 8) +
                                align_up((count + 1) * 8) + align_up(soff[count] * 24) + align_up(count * cap * 24) +
-                               align_up(count * cap * 4) + 2 * align_up(count * 4)));
+                               align_up(count * cap * 4) + 2 * align_up(count * 4) + align_up(count)));
   IoScope sc(m);
   double *d_p = arena_take<double>(m->io, total * 3);
   int32_t *d_off = arena_take<int32_t>(m->io, count + 1);
@@ -116,13 +123,15 @@ extern "C" int ctp_shorten_path(ctp_map *m, const double *pts, const int32_t *of
   int32_t *d_or = arena_take<int32_t>(m->io, count * cap);
   int32_t *d_on = arena_take<int32_t>(m->io, count), *d_st = arena_take<int32_t>(m->io, count);
   double *d_ol = arena_take<double>(m->io, count);
+  uint8_t *d_fw = forward_each ? arena_take<uint8_t>(m->io, count) : nullptr;
   CK(cudaMemcpyAsync(d_p, pts, total * 24, cudaMemcpyHostToDevice, 0));
   CK(cudaMemcpyAsync(d_off, off, (count + 1) * 4, cudaMemcpyHostToDevice, 0));
   CK(cudaMemcpyAsync(d_len, length, count * 8, cudaMemcpyHostToDevice, 0));
   CK(cudaMemcpyAsync(d_so, soff.data(), (count + 1) * 8, cudaMemcpyHostToDevice, 0));
+  if (d_fw) CK(cudaMemcpyAsync(d_fw, forward_each, count, cudaMemcpyHostToDevice, 0));
   CK(cudaMemsetAsync(d_or, 0xff, count * cap * 4, 0));
   CK(cudaMemsetAsync(d_out, 0, count * cap * 24, 0));
-  DISPATCH_L(m, k_shorten<L><<<(unsigned)count, CTP_PATH_BLOCK>>>(m->dev, d_p, d_off, d_len, forward, clr, cdc, cap,
+  DISPATCH_L(m, k_shorten<L><<<(unsigned)count, CTP_PATH_BLOCK>>>(m->dev, d_p, d_off, d_len, forward, d_fw, clr, cdc, cap,
                                                                    d_so, d_scr, d_out, d_or, d_on, d_ol, d_st));
   m->launches++;
   CK(cudaGetLastError());

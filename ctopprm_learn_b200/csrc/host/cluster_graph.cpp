@@ -19,6 +19,8 @@
 // that would have hit it are counted in ClusterStats::capped_refloods.
 #include <algorithm>
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 #include <chrono>
 #include <memory>
 #include <random>
@@ -60,7 +62,8 @@ double polyLength(const std::vector<double> &p) {  // calc_path_length (include/
 }
 
 // shorten_path (:2313-2479) for a batch of polylines held by value; "no point added" keeps the original (:2423-2427)
-std::vector<Poly> shortenBatch(ctp_map *h, const std::vector<Poly> &in, bool forward, double clr, double cdc) {
+std::vector<Poly> shortenBatch(ctp_map *h, const std::vector<Poly> &in, bool forward, double clr, double cdc,
+                               const std::vector<uint8_t> *forward_each = nullptr) {
   const int64_t count = (int64_t)in.size();
   if (count == 0) return {};
   std::vector<double> pts, len;
@@ -76,8 +79,9 @@ std::vector<Poly> shortenBatch(ctp_map *h, const std::vector<Poly> &in, bool for
   for (;;) {
     std::vector<double> out((size_t)count * cap * 3), out_len((size_t)count);
     std::vector<int32_t> origin((size_t)count * cap), out_n((size_t)count), status((size_t)count);
-    if (ctp_shorten_path(h, pts.data(), off.data(), len.data(), count, forward ? 1 : 0, clr, cdc, cap, out.data(), origin.data(),
-                         out_n.data(), out_len.data(), status.data()) != CTP_OK)
+    if (ctp_shorten_path_ex(h, pts.data(), off.data(), len.data(), count, forward ? 1 : 0,
+                            forward_each ? forward_each->data() : nullptr, clr, cdc, cap, out.data(), origin.data(),
+                            out_n.data(), out_len.data(), status.data()) != CTP_OK)
       dieCluster("ctp_shorten_path");
     bool grow = false;
     for (int64_t i = 0; i < count; i++) grow |= status[i] == CTP_ERR_CAPACITY;
@@ -162,9 +166,14 @@ struct Stage {
     const int32_t ns = (int32_t)seeds.size();
     int32_t count = 0;
     uint64_t upd = 0;
+    const auto t0 = std::chrono::high_resolution_clock::now();
     if (ctp_cluster_flood(rm, sd.data(), &ns, mode, dist.data(), prev.data(), cl.data(), rec_nodes.get(), rec_label.get(),
                           rec_dist.get(), &count, &upd) != CTP_OK)
       dieCluster("ctp_cluster_flood");
+    if (getenv("CTOPPRM_TRACE"))
+      fprintf(stderr, "[ctopprm] flood mode %d: %.3f ms, %d records, %llu updates\n", mode,
+              std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count(), count,
+              (unsigned long long)upd);
     if (mode == 0) stats.floods++;
     else {
       stats.refloods++;
@@ -245,12 +254,34 @@ struct Stage {
   // isNewHomotopyClass (:1664-1726) for a list of cluster pairs in one batch: -> verdicts and the shortened min paths
   void homotopyBatch(const std::vector<std::pair<int, int>> &pairs, std::vector<uint8_t> &is_new, std::vector<Poly> &short_min) {
     std::vector<Poly> a, b;
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    struct Tr {
+      std::chrono::high_resolution_clock::time_point t0;
+      size_t pairs;
+      ~Tr() {
+        if (getenv("CTOPPRM_TRACE"))
+          fprintf(stderr, "[ctopprm] homotopy batch of %zu pairs: %.3f ms\n", pairs,
+                  std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count());
+      }
+    } tr{t0, pairs.size()};
     for (auto &pr : pairs) {
       a.push_back(connectionPath(MN(pr.first, pr.second).node1, MN(pr.first, pr.second).node2));
       b.push_back(connectionPath(MX(pr.first, pr.second).node1, MX(pr.first, pr.second).node2));
     }
-    a = shortenBatch(h, shortenBatch(h, a, false, clr, cdc), true, clr, cdc);   // :1702-1703
-    b = shortenBatch(h, shortenBatch(h, b, true, clr, cdc), false, clr, cdc);   // :1706-1707
+    // the min path backward then forward (:1702-1703), the max path forward then backward (:1706-1707): the two chains
+    // are independent, so each pass is ONE launch over both sets with a direction per polyline
+    {
+      const size_t P = a.size();
+      std::vector<Poly> both(a);
+      both.insert(both.end(), b.begin(), b.end());
+      std::vector<uint8_t> dir(2 * P);
+      for (size_t i = 0; i < P; i++) dir[i] = 0, dir[P + i] = 1;
+      both = shortenBatch(h, both, false, clr, cdc, &dir);
+      for (size_t i = 0; i < P; i++) dir[i] = 1, dir[P + i] = 0;
+      both = shortenBatch(h, both, false, clr, cdc, &dir);
+      a.assign(both.begin(), both.begin() + (long)P);
+      b.assign(both.begin() + (long)P, both.end());
+    }
     is_new = deformableBatch(h, a, b, clr, cdc);
     short_min = a;
     stats.homotopy_checks += (int)pairs.size();

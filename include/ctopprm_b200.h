@@ -374,6 +374,11 @@ int ctp_shorten_path(ctp_map *map, const double *pts, const int32_t *off, const 
                      int64_t count, int forward, double clr, double cdc, int32_t cap,
                      double *out, int32_t *origin, int32_t *out_n, double *out_len,
                      int32_t *status);
+/* the same with a direction per polyline (forward_each[i] != 0 = forward; NULL = `forward` for all): isNewHomotopyClass
+ * (:1702-1707) shortens one path backward-then-forward and the other forward-then-backward -- both go in one launch */
+int ctp_shorten_path_ex(ctp_map *map, const double *pts, const int32_t *off, const double *length,
+                        int64_t count, int forward, const uint8_t *forward_each, double clr, double cdc, int32_t cap,
+                        double *out, int32_t *origin, int32_t *out_n, double *out_len, int32_t *status);
 
 #ifdef __cplusplus
 }
