@@ -98,6 +98,8 @@ struct ctp_map {
   int64_t csr_pair_cap = 0;   // overflow pairs of the adjacency stage (0 = one per node)
   int perq_cluster = -1;      // per-query setup / scan kernels on clusters of 8 CTAs: -1 automatic, 0 never, 1 always
   int occ_cache[32] = {0};    // resident CTAs per SM of the edge kernels, per (layout, lanes per edge): see occ_slot
+  char *h_stage = nullptr;    // page-locked staging of the small host-pointer calls (StagedIn / StagedOut)
+  size_t h_stage_cap = 0;
   int edge_filter = 1;        // roadmap edges: float32 whole-edge filter in front of the exact kernel: 0 never, 1 where it pays
                               // (calibrated on the first launch), 2 always (CTP_TUNE_EDGE_FILTER)
   double filter_cal_clr = -1e300, filter_cal_cdc = -1e300;  // (threshold, spacing) the calibration below was taken for
@@ -501,6 +503,7 @@ extern "C" int ctp_map_destroy(ctp_map *m) {
   cudaFree(m->d_cell8);
   cudaFree(m->d_brick);
   cudaFree(m->d_lookups);
+  if (m->h_stage) cudaFreeHost(m->h_stage);
   cudaFree(m->ws.base);
   cudaFree(m->io.base);
   if (m->rm_block) cudaFree(m->rm_block);
@@ -759,6 +762,61 @@ extern "C" int ctp_gradient_dev(ctp_map *m, const double *xyz, int64_t cnt, doub
 }
 
 // host-pointer wrappers: stage through the io arena
+// The small host-pointer calls (polylines: tens of kilobytes in a handful of arrays) used to issue one cudaMemcpyAsync
+// per array from / to pageable memory -- ten staged copies of ~10 us each around a kernel of ~100 us.  StagedIn packs the
+// input arrays into one page-locked block laid out like the device arena and uploads it with ONE copy; StagedOut brings
+// the (contiguous) output takes back with ONE copy and hands the pieces out.
+static int stage_reserve(ctp_map *m, size_t bytes) {
+  if (bytes <= m->h_stage_cap) return CTP_OK;
+  if (m->h_stage) {
+    CK(cudaDeviceSynchronize());
+    cudaFreeHost(m->h_stage);
+  }
+  m->h_stage = nullptr;
+  m->h_stage_cap = 0;
+  const size_t want = bytes + bytes / 2 + (1 << 16);
+  CK(cudaHostAlloc((void **)&m->h_stage, want, cudaHostAllocDefault));
+  m->h_stage_cap = want;
+  return CTP_OK;
+}
+struct StagedIn {
+  ctp_map *m;
+  char *dev0 = nullptr;
+  size_t host_off;  // where this block starts in the staging buffer
+  size_t used = 0;
+  StagedIn(ctp_map *mm, size_t at) : m(mm), host_off(at) {}
+  template <typename T> T *put(const T *src, size_t count) {
+    T *d = arena_take<T>(m->io, count);
+    if (!dev0) dev0 = (char *)d;
+    const size_t off = (size_t)((char *)d - dev0);
+    memcpy(m->h_stage + host_off + off, src, count * sizeof(T));
+    used = off + align_up(count * sizeof(T));
+    return d;
+  }
+  cudaError_t upload(cudaStream_t st) const {
+    return used ? cudaMemcpyAsync(dev0, m->h_stage + host_off, used, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  }
+};
+struct StagedOut {
+  ctp_map *m;
+  char *dev0 = nullptr;
+  size_t host_off;
+  size_t used = 0;
+  StagedOut(ctp_map *mm, size_t at) : m(mm), host_off(at) {}
+  template <typename T> T *take(size_t count) {
+    T *d = arena_take<T>(m->io, count);
+    if (!dev0) dev0 = (char *)d;
+    used = (size_t)((char *)d - dev0) + align_up(count * sizeof(T));
+    return d;
+  }
+  cudaError_t download(cudaStream_t st) const {
+    return used ? cudaMemcpyAsync(m->h_stage + host_off, dev0, used, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+  }
+  template <typename T> void get(const T *d, T *dst, size_t count) const {
+    memcpy(dst, m->h_stage + host_off + (size_t)((const char *)d - dev0), count * sizeof(T));
+  }
+};
+
 struct IoScope {
   ctp_map *m;
   explicit IoScope(ctp_map *mm) : m(mm) { m->io.used = 0; }

@@ -58,31 +58,29 @@ extern "C" int ctp_deformable(ctp_map *m, const double *pts, const int32_t *off,
   }
   CK(cudaSetDevice(m->device));
   const int64_t total = off[count];
-  CKR(arena_reserve(m->io, align_up(total * 24) + align_up((count + 1) * 4) + align_up(count * 8) +
-                               2 * align_up(pairs * 4) + align_up(pairs * 8) + align_up((pairs + 1) * 8) +
-                               align_up(soff[pairs] * 24) + align_up(pairs)));
+  const size_t in_bytes = align_up(total * 24) + align_up((count + 1) * 4) + align_up(count * 8) + 2 * align_up(pairs * 4) +
+                          align_up(pairs * 8) + align_up((pairs + 1) * 8);
+  CKR(arena_reserve(m->io, in_bytes + align_up(soff[pairs] * 24) + align_up(pairs)));
+  CKR(stage_reserve(m, in_bytes + align_up(pairs)));
   IoScope sc(m);
-  double *d_p = arena_take<double>(m->io, total * 3);
-  int32_t *d_off = arena_take<int32_t>(m->io, count + 1);
-  double *d_len = arena_take<double>(m->io, count);
-  int32_t *d_ia = arena_take<int32_t>(m->io, pairs), *d_ib = arena_take<int32_t>(m->io, pairs);
-  double *d_nc = arena_take<double>(m->io, pairs);
-  int64_t *d_so = arena_take<int64_t>(m->io, pairs + 1);
+  StagedIn in(m, 0);
+  double *d_p = in.put(pts, total * 3);
+  int32_t *d_off = in.put(off, count + 1);
+  double *d_len = in.put(length, count);
+  int32_t *d_ia = in.put(ia, pairs), *d_ib = in.put(ib, pairs);
+  double *d_nc = in.put(num_check, pairs);
+  int64_t *d_so = in.put(soff.data(), pairs + 1);
   double *d_scr = arena_take<double>(m->io, soff[pairs] * 3);
-  uint8_t *d_out = arena_take<uint8_t>(m->io, pairs);
-  CK(cudaMemcpyAsync(d_p, pts, total * 24, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_off, off, (count + 1) * 4, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_len, length, count * 8, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_ia, ia, pairs * 4, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_ib, ib, pairs * 4, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_nc, num_check, pairs * 8, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_so, soff.data(), (pairs + 1) * 8, cudaMemcpyHostToDevice, 0));
+  StagedOut res(m, in_bytes);
+  uint8_t *d_out = res.take<uint8_t>(pairs);
+  CK(in.upload(0));
   DISPATCH_L(m, k_deformable<L><<<(unsigned)pairs, CTP_PATH_BLOCK>>>(m->dev, d_p, d_off, d_len, d_ia, d_ib, d_nc, d_so,
                                                                       d_scr, clr, cdc, d_out));
   m->launches++;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(out, d_out, pairs, cudaMemcpyDeviceToHost, 0));
+  CK(res.download(0));
   CK(cudaStreamSynchronize(0));
+  res.get(d_out, out, pairs);
   return CTP_OK;
 }
 
@@ -110,36 +108,37 @@ extern "C" int ctp_shorten_path_ex(ctp_map *m, const double *pts, const int32_t 
   }
   CK(cudaSetDevice(m->device));
   const int64_t total = off[count];
-  CKR(arena_reserve(m->io, align_up(total * 24) + align_up((count + 1) * 4) + 2 * align_up(count * 8) +
-                               align_up((count + 1) * 8) + align_up(soff[count] * 24) + align_up(count * cap * 24) +
-                               align_up(count * cap * 4) + 2 * align_up(count * 4) + align_up(count)));
+  const size_t in_bytes = align_up(total * 24) + align_up((count + 1) * 4) + align_up(count * 8) + align_up((count + 1) * 8) +
+                          align_up(count);
+  const size_t out_bytes = align_up(count * cap * 24) + align_up(count * cap * 4) + 2 * align_up(count * 4) + align_up(count * 8);
+  CKR(arena_reserve(m->io, in_bytes + align_up(soff[count] * 24) + out_bytes));
+  CKR(stage_reserve(m, in_bytes + out_bytes));
   IoScope sc(m);
-  double *d_p = arena_take<double>(m->io, total * 3);
-  int32_t *d_off = arena_take<int32_t>(m->io, count + 1);
-  double *d_len = arena_take<double>(m->io, count);
-  int64_t *d_so = arena_take<int64_t>(m->io, count + 1);
+  StagedIn in(m, 0);
+  double *d_p = in.put(pts, total * 3);
+  int32_t *d_off = in.put(off, count + 1);
+  double *d_len = in.put(length, count);
+  int64_t *d_so = in.put(soff.data(), count + 1);
+  uint8_t *d_fw = forward_each ? in.put(forward_each, count) : nullptr;
   double *d_scr = arena_take<double>(m->io, soff[count] * 3);
-  double *d_out = arena_take<double>(m->io, count * cap * 3);
-  int32_t *d_or = arena_take<int32_t>(m->io, count * cap);
-  int32_t *d_on = arena_take<int32_t>(m->io, count), *d_st = arena_take<int32_t>(m->io, count);
-  double *d_ol = arena_take<double>(m->io, count);
-  uint8_t *d_fw = forward_each ? arena_take<uint8_t>(m->io, count) : nullptr;
-  CK(cudaMemcpyAsync(d_p, pts, total * 24, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_off, off, (count + 1) * 4, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_len, length, count * 8, cudaMemcpyHostToDevice, 0));
-  CK(cudaMemcpyAsync(d_so, soff.data(), (count + 1) * 8, cudaMemcpyHostToDevice, 0));
-  if (d_fw) CK(cudaMemcpyAsync(d_fw, forward_each, count, cudaMemcpyHostToDevice, 0));
+  StagedOut res(m, in_bytes);
+  double *d_out = res.take<double>(count * cap * 3);
+  int32_t *d_or = res.take<int32_t>(count * cap);
+  int32_t *d_on = res.take<int32_t>(count), *d_st = res.take<int32_t>(count);
+  double *d_ol = res.take<double>(count);
+  CK(in.upload(0));
   CK(cudaMemsetAsync(d_or, 0xff, count * cap * 4, 0));
   CK(cudaMemsetAsync(d_out, 0, count * cap * 24, 0));
   DISPATCH_L(m, k_shorten<L><<<(unsigned)count, CTP_PATH_BLOCK>>>(m->dev, d_p, d_off, d_len, forward, d_fw, clr, cdc, cap,
                                                                    d_so, d_scr, d_out, d_or, d_on, d_ol, d_st));
   m->launches++;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(out, d_out, count * cap * 24, cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(origin, d_or, count * cap * 4, cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(out_n, d_on, count * 4, cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(out_len, d_ol, count * 8, cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(status, d_st, count * 4, cudaMemcpyDeviceToHost, 0));
+  CK(res.download(0));
   CK(cudaStreamSynchronize(0));
+  res.get(d_out, out, count * cap * 3);
+  res.get(d_or, origin, count * cap);
+  res.get(d_on, out_n, count);
+  res.get(d_ol, out_len, count);
+  res.get(d_st, status, count);
   return CTP_OK;
 }

@@ -1,4 +1,6 @@
 // topological_prm_clustering.cpp -- TopologicalPRMClustering<Vector<3>> on the C ABI.
+#include <cstring>
+
 #include "ctopprm/topological_prm_clustering.hpp"
 
 #include <algorithm>
@@ -83,12 +85,40 @@ template <> void Planner::setBorders(V3 min_position, V3 max_position) {
 
 // PRM construction (:288-401): candidates -> rejection -> k-NN(13) -> directed checks -> symmetric
 // adjacency, one ctp_sample_multiple call; the CSR is re-materialised into visibility_node_ids.
+namespace {
+// Page-locked buffers for the one call that moves megabytes per query (candidates in, roadmap out): through pageable
+// std::vectors the copies are staged by the driver at a few GB/s and took most of sampleMultiple's 0.9 ms.
+struct PlannerStaging {
+  void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[5] = {0, 0, 0, 0, 0};
+  void *get(int i, size_t bytes) {
+    if (bytes > cap[i]) {
+      if (p[i]) ctp_host_free(p[i]);
+      p[i] = nullptr;
+      cap[i] = 0;
+      const size_t want = bytes + bytes / 4 + 4096;
+      if (ctp_host_alloc(&p[i], want) != CTP_OK) die("ctp_host_alloc");
+      cap[i] = want;
+    }
+    return p[i];
+  }
+  ~PlannerStaging() {
+    for (void *q : p)
+      if (q) ctp_host_free(q);
+  }
+};
+}  // namespace
+
 template <> void Planner::sampleMultiple(const int num_samples) {
   ctp_map *h = handleOf(map_, "sampleMultiple");
   const int n = num_samples, k = num_nn - 1;
   if (n < 2) return;
-  std::vector<double> nodes((size_t)n * 3), w((size_t)2 * n * k);
-  std::vector<int32_t> row_ptr((size_t)n + 1), col((size_t)2 * n * k);
+  // one set per host thread, kept for the life of the thread: planners come and go per query, and page-locking a few
+  // megabytes costs milliseconds
+  static thread_local PlannerStaging stg;
+  const size_t ecap = (size_t)2 * n * k;
+  double *nodes = (double *)stg.get(0, (size_t)n * 24), *w = (double *)stg.get(1, ecap * 8);
+  int32_t *row_ptr = (int32_t *)stg.get(2, ((size_t)n + 1) * 4), *col = (int32_t *)stg.get(3, ecap * 4);
   int32_t n_filled = 0;
   int64_t nnz_off[2] = {0, 0};
   if (ctp_set_tunable(h, CTP_TUNE_KNN_RADIUS, neighbour_radius_ > 0 ? neighbour_radius_ : 0.0) != CTP_OK) die("ctp_set_tunable");
@@ -103,9 +133,10 @@ template <> void Planner::sampleMultiple(const int num_samples) {
         die("ctp_sample_ellipsoid");
     }
     const std::vector<V3> &cand = generated ? drawn : candidate_stream_;
-    const int rc = ctp_sample_multiple(h, start_->data.data(), end_->data.data(), cand[0].data(), 1, m, n, k, min_clearance_,
-                                       collision_distance_check_, nodes.data(), &n_filled, row_ptr.data(), col.data(),
-                                       w.data(), (int64_t)col.size(), nnz_off);
+    double *cand_pin = (double *)stg.get(4, (size_t)m * 24);
+    memcpy(cand_pin, cand[0].data(), (size_t)m * 24);
+    const int rc = ctp_sample_multiple(h, start_->data.data(), end_->data.data(), cand_pin, 1, m, n, k, min_clearance_,
+                                       collision_distance_check_, nodes, &n_filled, row_ptr, col, w, (int64_t)ecap, nnz_off);
     if (rc == CTP_OK) break;
     if (rc == CTP_ERR_NEED_CANDIDATES && generated && attempt < 6) {
       m *= 4;  // the reference's do/while would simply keep drawing (:314-317)
@@ -116,13 +147,13 @@ template <> void Planner::sampleMultiple(const int num_samples) {
   nodes_.assign((size_t)n, nullptr);
   nodes_[0] = start_;
   nodes_[1] = end_;
-  node_xyz_.swap(nodes);
+  node_xyz_.assign(nodes, nodes + (size_t)n * 3);
   sp_dist_.clear();
   sp_pred_.clear();
   cluster_labels_.clear();
-  csr_row_ptr_.swap(row_ptr);
-  csr_col_.assign(col.begin(), col.begin() + nnz_off[1]);
-  csr_w_.assign(w.begin(), w.begin() + nnz_off[1]);
+  csr_row_ptr_.assign(row_ptr, row_ptr + n + 1);
+  csr_col_.assign(col, col + nnz_off[1]);
+  csr_w_.assign(w, w + nnz_off[1]);
   adjacency_ready_ = false;  // HeapNodes and their visibility_node_ids are created on first use (nodes(), nodeAt())
 }
 
