@@ -2108,24 +2108,33 @@ extern "C" int ctp_cluster_flood(ctp_roadmap *r, const int32_t *seeds, const int
   m->ws.used = 0;
   CKR(ctp_cluster_flood_dev(m, q, n, r->d_rp, r->d_col, r->d_w, r->d_off, r->d_seeds, r->max_seeds, r->d_ns, mode, r->d_dist,
                             r->d_prev, r->d_label, r->rec_cap, r->d_rec_nodes, r->d_rec_label, r->d_rec_dist, r->d_rec_count, r->d_upd, 0));
-  CK(cudaMemcpyAsync(dist, r->d_dist, q * n * 8, cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(prev, r->d_prev, q * n * 4, cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(label, r->d_label, q * n * 4, cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(rec_count, r->d_rec_count, q * 4, cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(n_updates, r->d_upd, q * 8, cudaMemcpyDeviceToHost, 0));
+  // results through the page-locked staging block: asynchronous copies at link speed, one synchronisation
+  const size_t o_dist = 0, o_prev = o_dist + align_up(q * n * 8), o_label = o_prev + align_up(q * n * 4),
+               o_cnt = o_label + align_up(q * n * 4), o_upd = o_cnt + align_up(q * 4), o_end = o_upd + align_up(q * 8);
+  CKR(stage_reserve(m, o_end + (size_t)r->rec_cap * 20 + 1024));
+  char *hs = m->h_stage;
+  CK(cudaMemcpyAsync(hs + o_dist, r->d_dist, q * n * 8, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(hs + o_prev, r->d_prev, q * n * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(hs + o_label, r->d_label, q * n * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(hs + o_cnt, r->d_rec_count, q * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(hs + o_upd, r->d_upd, q * 8, cudaMemcpyDeviceToHost, 0));
   CK(cudaStreamSynchronize(0));
-  std::vector<int32_t> tmp_nodes, tmp_label, order;
-  std::vector<double> tmp_dist;
+  memcpy(dist, hs + o_dist, q * n * 8);
+  memcpy(prev, hs + o_prev, q * n * 4);
+  memcpy(label, hs + o_label, q * n * 4);
+  memcpy(rec_count, hs + o_cnt, q * 4);
+  memcpy(n_updates, hs + o_upd, q * 8);
+  std::vector<int32_t> order;
   for (int64_t i = 0; i < q; i++) {
     const int64_t c = rec_count[i];
     if (c > r->rec_cap) return fail(CTP_ERR_CAPACITY, "more connection records than directed edges (internal error)");
     if (c == 0) continue;
-    tmp_nodes.resize(2 * c);
-    tmp_dist.resize(c);
-    tmp_label.resize(c);
-    CK(cudaMemcpyAsync(tmp_label.data(), r->d_rec_label + i * r->rec_cap, c * 4, cudaMemcpyDeviceToHost, 0));
-    CK(cudaMemcpyAsync(tmp_nodes.data(), r->d_rec_nodes + 2 * i * r->rec_cap, c * 8, cudaMemcpyDeviceToHost, 0));
-    CK(cudaMemcpyAsync(tmp_dist.data(), r->d_rec_dist + i * r->rec_cap, c * 8, cudaMemcpyDeviceToHost, 0));
+    int32_t *tmp_label = (int32_t *)(hs + o_end);
+    int32_t *tmp_nodes = (int32_t *)(hs + o_end + align_up(c * 4));
+    double *tmp_dist = (double *)(hs + o_end + align_up(c * 4) + align_up(c * 8));
+    CK(cudaMemcpyAsync(tmp_label, r->d_rec_label + i * r->rec_cap, c * 4, cudaMemcpyDeviceToHost, 0));
+    CK(cudaMemcpyAsync(tmp_nodes, r->d_rec_nodes + 2 * i * r->rec_cap, c * 8, cudaMemcpyDeviceToHost, 0));
+    CK(cudaMemcpyAsync(tmp_dist, r->d_rec_dist + i * r->rec_cap, c * 8, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));
     order.resize(c);
     for (int64_t t = 0; t < c; t++) order[t] = (int32_t)t;
