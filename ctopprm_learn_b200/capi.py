@@ -602,6 +602,7 @@ class DeviceMap:
         return out
 
     def shorten_path(self, paths, lengths, forward, clr, cdc, cap=None):
+        """forward: one flag for the batch, or a sequence with one flag per polyline (ctp_shorten_path_ex)"""
         pts, off = self._pack_polylines(paths)
         lengths = _np(lengths, np.float64)
         cnt = len(paths)
@@ -612,8 +613,14 @@ class DeviceMap:
         out_n = np.empty(cnt, dtype=np.int32)
         out_len = np.empty(cnt)
         st = np.empty(cnt, dtype=np.int32)
-        _check(lib().ctp_shorten_path(self._h, _ptr(pts), _ptr(off), _ptr(lengths), cnt, int(forward), clr, cdc, cap,
-                                      _ptr(out), _ptr(origin), _ptr(out_n), _ptr(out_len), _ptr(st)))
+        if np.ndim(forward) == 0:
+            _check(lib().ctp_shorten_path(self._h, _ptr(pts), _ptr(off), _ptr(lengths), cnt, int(forward), clr, cdc, cap,
+                                          _ptr(out), _ptr(origin), _ptr(out_n), _ptr(out_len), _ptr(st)))
+        else:
+            each = _np(np.asarray(forward).astype(np.uint8), np.uint8)
+            assert len(each) == cnt
+            _check(lib().ctp_shorten_path_ex(self._h, _ptr(pts), _ptr(off), _ptr(lengths), cnt, 0, _ptr(each), clr, cdc, cap,
+                                             _ptr(out), _ptr(origin), _ptr(out_n), _ptr(out_len), _ptr(st)))
         return [out[i, :out_n[i]] for i in range(cnt)], [origin[i, :out_n[i]] for i in range(cnt)], out_len, st
 
     # -- device-pointer API (torch CUDA tensors) -----------------------------------------

@@ -764,6 +764,10 @@ def test_argument_errors_do_not_launch(c1):
         m.set_layout(64)
     with pytest.raises(capi.CtpError):
         m.edge_check_indexed(np.zeros((4, 3)), [0, 5], [1, 2], CLR, CDC)  # index out of range
+    with pytest.raises(capi.CtpError):  # 16-bit columns cannot name 70000 nodes
+        m.sample_multiple(s[None], g[None], np.zeros((1, 10, 3)), 70000, CLR, CDC, csr_flags=capi.CSR_UPPER | capi.CSR_COL16,
+                          out=dict(nodes=np.empty((1, 70000, 3)), n_filled=np.empty(1, np.int32), row_ptr=np.empty((1, 70001), np.int32),
+                                   col=np.empty(16, np.uint16), w=np.empty(16), nnz_off=np.empty(2, np.int64)))
     # the handle is still usable afterwards
     assert np.isfinite(m.clearance(s[None])[0]) or True
 
@@ -1492,3 +1496,43 @@ def test_sample_multiple_wire_formats(c1, chunk):
     assert out["col"].dtype == np.uint16 and np.array_equal(out["col"][:nnz].astype(np.int32), ref["col"][:nnz])
     assert np.array_equal(capi.nodes_from_index(out["nodes"], cand, s, g), ref["nodes"])
     assert np.array_equal(out["nodes"][:, 0], np.full(q, -2)) and np.array_equal(out["nodes"][:, 1], np.full(q, -3))
+
+
+def test_shorten_direction_per_polyline(c1, roadmap_paths):
+    """ctp_shorten_path_ex: a direction per polyline gives what the two one-direction calls give"""
+    m, om, c, e = c1
+    paths, lengths = roadmap_paths
+    fwd = m.shorten_path(paths, lengths, True, CLR, CDC)
+    bwd = m.shorten_path(paths, lengths, False, CLR, CDC)
+    each = [(i % 3) != 0 for i in range(len(paths))]
+    mix = m.shorten_path(paths, lengths, each, CLR, CDC)
+    for i, f in enumerate(each):
+        ref = fwd if f else bwd
+        assert np.array_equal(mix[0][i], ref[0][i]) and np.array_equal(mix[1][i], ref[1][i])
+        assert mix[2][i] == ref[2][i] and mix[3][i] == ref[3][i]
+
+
+def test_filter_counters(c1):
+    """ctp_filter_counter_read: edges shown / decided by the whole-edge filter, lookups of the decided ones"""
+    m, om, c, e = c1
+    m.set_layout(capi.LAYOUT_TEX)
+    s, g = synth.default_query(c, e)
+    nodes = om.sample_reject(s, g, synth.ellipsoid_candidates(s, g, 12000, 3), CLR, 2000)[0]
+    m.set_tunable(capi.TUNE_EDGE_FILTER, 2)
+    try:
+        m.read_filter_counter()
+        m.read_lookups()
+        out = m.build_prm(nodes[None], CLR, CDC)
+        decided, seen, lk = m.read_filter_counter()
+        total = m.read_lookups()
+    finally:
+        m.set_tunable(capi.TUNE_EDGE_FILTER, 1)
+    assert seen == 2000 * 13 and 0 < decided <= seen and 0 < lk <= total
+    want = om.build_prm(nodes, CLR, CDC, nthreads=4)
+    assert np.array_equal(out["directed_free"][0], want["directed_free"].astype(bool))
+    m.set_tunable(capi.TUNE_EDGE_FILTER, 0)
+    try:
+        m.build_prm(nodes[None], CLR, CDC)
+        assert m.read_filter_counter()[1] == 0 and m.read_lookups() == total
+    finally:
+        m.set_tunable(capi.TUNE_EDGE_FILTER, 1)
