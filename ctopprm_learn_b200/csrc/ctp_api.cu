@@ -2223,6 +2223,13 @@ static int pipe_host_staging(ctp_map *m, int64_t qc) {
   CK(cudaHostAlloc((void **)&m->h_off, 2 * (qc + 1) * sizeof(int64_t), cudaHostAllocMapped));
   // accept counts after the rejection (2 buffers), n_used (2), accept counts after the build (2)
   CK(cudaHostAlloc((void **)&m->h_nf, 6 * (qc + 1) * sizeof(int32_t), cudaHostAllocMapped));
+  {  // the kernels write through the host pointers: that needs unified addressing (every 64-bit CUDA platform has it)
+    void *d0 = nullptr, *d1 = nullptr;
+    CK(cudaHostGetDevicePointer(&d0, m->h_off, 0));
+    CK(cudaHostGetDevicePointer(&d1, m->h_nf, 0));
+    if (d0 != (void *)m->h_off || d1 != (void *)m->h_nf)
+      return fail(CTP_ERR_CUDA, "mapped page-locked memory is not addressable by its host pointer on this device");
+  }
   m->h_off_cap = 2 * (qc + 1);
   return CTP_OK;
 }
