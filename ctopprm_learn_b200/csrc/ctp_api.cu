@@ -1960,11 +1960,22 @@ extern "C" int ctp_cluster_flood_dev(ctp_map *m, int64_t q, int64_t n, const int
   }
   if (mode == 1) CK(cudaMemcpyAsync(d_lnew, label, total * 4, cudaMemcpyDeviceToDevice, st));
   int32_t *lab_w = mode == 1 ? d_lnew : label;
-  k_cluster_prev<<<gb, tb, 0, st>>>(q, n, row_ptr, col, w, nnz_off, seeds, max_seeds, n_seeds, mode, dist, d_new, prev, lab_w,
-                                    (unsigned long long *)n_updates);
+  // a warp per node while that still is a modest launch (one query, a few queries), a thread per node for big batches
+  const bool wide = total <= ((int64_t)1 << 20);
+  const unsigned gw = (unsigned)((total * 32 + tb - 1) / tb);
+  if (wide)
+    k_cluster_prev<32><<<gw, tb, 0, st>>>(q, n, row_ptr, col, w, nnz_off, seeds, max_seeds, n_seeds, mode, dist, d_new, prev, lab_w,
+                                          (unsigned long long *)n_updates);
+  else
+    k_cluster_prev<1><<<gb, tb, 0, st>>>(q, n, row_ptr, col, w, nnz_off, seeds, max_seeds, n_seeds, mode, dist, d_new, prev, lab_w,
+                                         (unsigned long long *)n_updates);
   if (mode == 0) k_cluster_label<<<gb, tb, 0, st>>>(q, n, n_seeds, prev, d_new, label);
-  k_cluster_records<<<gb, tb, 0, st>>>(q, n, row_ptr, col, w, nnz_off, seeds, max_seeds, n_seeds, mode, dist, label, d_new, lab_w,
-                                       prev, (int)rec_cap, rec_nodes, rec_label, rec_dist, rec_count);
+  if (wide)
+    k_cluster_records<32><<<gw, tb, 0, st>>>(q, n, row_ptr, col, w, nnz_off, seeds, max_seeds, n_seeds, mode, dist, label, d_new, lab_w,
+                                             prev, (int)rec_cap, rec_nodes, rec_label, rec_dist, rec_count);
+  else
+    k_cluster_records<1><<<gb, tb, 0, st>>>(q, n, row_ptr, col, w, nnz_off, seeds, max_seeds, n_seeds, mode, dist, label, d_new, lab_w,
+                                            prev, (int)rec_cap, rec_nodes, rec_label, rec_dist, rec_count);
   k_cluster_commit<<<gb, tb, 0, st>>>(total, n, n_seeds, d_new, mode == 1 ? d_lnew : nullptr, dist, label);
   m->launches += mode == 0 ? 4 : 3;
   m->ws.used = keep;

@@ -27,13 +27,19 @@ __device__ __forceinline__ bool cl_before(double da, int a, double db, int b) { 
 // ---- predecessors, labels of the improved nodes, update counts -----------------------------------------------
 // mode 0 (full flood): dist_old is ignored (every reached node counts as improved), seeds get label = their index.
 // mode 1 (one more seed, cluster id c = n_seeds - 1): only nodes with dist_new < dist_old are touched.
+// LPN lanes per node (1 or 32): the floods of ONE query leave a thread-per-node launch on 40 CTAs, each thread walking
+// its ~15 x 15 dependent loads alone; with a warp per node the lanes share the node's edges and meet in a shuffle
+// reduction (one flood of a 10 000-node roadmap: see DESIGN section 5).
+template <int LPN>
 __global__ void __launch_bounds__(256)
 k_cluster_prev(int64_t q, int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                const double *__restrict__ w, const int64_t *__restrict__ nnz_off, const int32_t *__restrict__ seeds,
                int max_seeds, const int32_t *__restrict__ n_seeds, int mode, const double *__restrict__ dist_old,
                const double *__restrict__ dist_new, int32_t *__restrict__ prev, int32_t *__restrict__ label,
                unsigned long long *__restrict__ n_updates) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t t = tid / LPN;  // the node; all LPN lanes of it take the same branches below
+  const int sub = (int)(tid - t * LPN);
   if (t >= q * n) return;
   const int64_t qi = t / n;
   const int v = (int)(t - qi * n);
@@ -73,7 +79,7 @@ k_cluster_prev(int64_t q, int64_t n, const int32_t *__restrict__ row_ptr, const 
   int best = -1;
   double bd = 0;
   int succ = 0;
-  for (int e = eb; e < ee; e++) {
+  for (int e = eb + sub; e < ee; e += LPN) {
     const int u = cq[e];
     const double du = dn[u];
     if (!(du < inf)) continue;
@@ -96,6 +102,19 @@ k_cluster_prev(int64_t q, int64_t n, const int32_t *__restrict__ row_ptr, const 
       }
       succ += low ? 1 : 0;
     }
+  }
+  if (LPN > 1) {  // (a node's lanes are one whole warp: 256 threads per CTA, LPN = 32)
+#pragma unroll
+    for (int o = LPN / 2; o > 0; o >>= 1) {
+      const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+      succ += __shfl_xor_sync(0xffffffffu, succ, o);
+      if (ob >= 0 && (best < 0 || cl_before(od, ob, bd, best))) {
+        best = ob;
+        bd = od;
+      }
+    }
+    if (sub) return;
   }
   prev[t] = best;
   if (mode == 1) label[t] = ns - 1;
@@ -124,6 +143,8 @@ k_cluster_label(int64_t q, int64_t n, const int32_t *__restrict__ n_seeds, const
 // relaxations, :859-872 / :1315-1331) and, if that state belongs to another cluster, a record
 // (ex, nb, cluster_state(nb), dist_state(nb) + dist[ex] + w) -- :930-938 / :1352-1360.
 // mode 0: label = labels of this flood.  mode 1: dist_old / label_old = the arrays before this flood, c = new cluster.
+// LPN lanes per expanded node, as k_cluster_prev.
+template <int LPN>
 __global__ void __launch_bounds__(256)
 k_cluster_records(int64_t q, int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                   const double *__restrict__ w, const int64_t *__restrict__ nnz_off, const int32_t *__restrict__ seeds,
@@ -132,7 +153,9 @@ k_cluster_records(int64_t q, int64_t n, const int32_t *__restrict__ row_ptr, con
                   const int32_t *__restrict__ label_new, const int32_t *__restrict__ prev_new, int rec_cap,
                   int32_t *__restrict__ rec_nodes, int32_t *__restrict__ rec_label, double *__restrict__ rec_dist,
                   int32_t *__restrict__ rec_count) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t t = tid / LPN;
+  const int sub = (int)(tid - t * LPN);
   if (t >= q * n) return;
   const int64_t qi = t / n;
   const int ex = (int)(t - qi * n);
@@ -149,7 +172,7 @@ k_cluster_records(int64_t q, int64_t n, const int32_t *__restrict__ row_ptr, con
   const double *wq = w + nnz_off[qi];
   const int32_t *ln = label_new + qi * n;
   const int lex = ln[ex];
-  for (int e = rp[ex]; e < rp[ex + 1]; e++) {
+  for (int e = rp[ex] + sub; e < rp[ex + 1]; e += LPN) {
     const int nb = cq[e];
     const double dnb = dn[nb];
     double sd_ = 0;

@@ -169,7 +169,13 @@ __device__ __forceinline__ bool warp_edge_nodes(const MapDev &M, double ax, doub
 // ---------------- BaseMap::isDeformablePath (src/base_map.cpp:160-192) ----------------------
 // One CTA per pair: two threads resample the two polylines, then the warps share the K
 // straight connectors between equal-parameter samples; first blocked connector ends the pair.
-#define CTP_PATH_BLOCK 256
+#ifndef CTP_PATH_BLOCK
+#define CTP_PATH_BLOCK 1024  // largest CTA of the polyline kernels (shared arrays are sized for it); the launch picks
+                             // ctp_path_threads(): a handful of polylines / pairs (the cluster stage of one query) is bound
+                             // by the latency of the sequential steps and takes 32 warps per CTA -- 32 speculative anchor
+                             // tests / connectors in flight per step instead of 8 -- while a large batch fills the SMs
+                             // with 8-warp CTAs (2016 pairs: 0.51 ms, against 0.89 ms with 32-warp CTAs)
+#endif
 template <int L>
 __global__ void __launch_bounds__(CTP_PATH_BLOCK)
 k_deformable(MapDev M, const double *__restrict__ pts, const int32_t *__restrict__ off,
@@ -197,7 +203,7 @@ k_deformable(MapDev M, const double *__restrict__ pts, const int32_t *__restrict
     if (threadIdx.x == 0) out[pair] = 0xFB;  // (uint8_t)CTP_ERR_SAMPLE_PATH
     return;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = CTP_PATH_BLOCK / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (int)(blockDim.x >> 5);
   for (int i = warp; i < K; i += nwarp) {
     if (*(volatile int *)&s_blocked) break;
     double hit[3];
@@ -231,7 +237,7 @@ k_shorten(MapDev M, const double *__restrict__ pts, const int32_t *__restrict__ 
   double *sampled = scratch + 3 * scratch_off[pi];
   const double num_samples = ceil(len / cdc) + 1;  // :2326
   const int S = num_samples > 0 ? (int)num_samples : 0;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = CTP_PATH_BLOCK / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (int)(blockDim.x >> 5);
 
   __shared__ int s_rc, s_nout, s_i0, s_state;  // s_state: 0 run, 1 "no point added", <0 error
   __shared__ double s_anchor[3], s_slen;

@@ -1,6 +1,9 @@
 // ctp_paths_api.inl -- host-pointer entry points for the polyline operations
 // (included at the end of ctp_api.cu).
 
+// threads per CTA of k_shorten / k_deformable for a batch of `items` polylines / pairs
+static int ctp_path_threads(const ctp_map *m, int64_t items) { return items <= 2 * (int64_t)m->sm_count ? CTP_PATH_BLOCK : 256; }
+
 static int check_polylines(const int32_t *off, int64_t count) {
   REQUIRE(off[0] == 0, "offsets must start at 0");
   for (int64_t i = 0; i < count; i++) REQUIRE(off[i + 1] - off[i] >= 2, "every polyline needs at least 2 points");
@@ -74,7 +77,7 @@ extern "C" int ctp_deformable(ctp_map *m, const double *pts, const int32_t *off,
   StagedOut res(m, in_bytes);
   uint8_t *d_out = res.take<uint8_t>(pairs);
   CK(in.upload(0));
-  DISPATCH_L(m, k_deformable<L><<<(unsigned)pairs, CTP_PATH_BLOCK>>>(m->dev, d_p, d_off, d_len, d_ia, d_ib, d_nc, d_so,
+  DISPATCH_L(m, k_deformable<L><<<(unsigned)pairs, ctp_path_threads(m, pairs)>>>(m->dev, d_p, d_off, d_len, d_ia, d_ib, d_nc, d_so,
                                                                       d_scr, clr, cdc, d_out));
   m->launches++;
   CK(cudaGetLastError());
@@ -129,7 +132,7 @@ extern "C" int ctp_shorten_path_ex(ctp_map *m, const double *pts, const int32_t 
   CK(in.upload(0));
   CK(cudaMemsetAsync(d_or, 0xff, count * cap * 4, 0));
   CK(cudaMemsetAsync(d_out, 0, count * cap * 24, 0));
-  DISPATCH_L(m, k_shorten<L><<<(unsigned)count, CTP_PATH_BLOCK>>>(m->dev, d_p, d_off, d_len, forward, d_fw, clr, cdc, cap,
+  DISPATCH_L(m, k_shorten<L><<<(unsigned)count, ctp_path_threads(m, count)>>>(m->dev, d_p, d_off, d_len, forward, d_fw, clr, cdc, cap,
                                                                    d_so, d_scr, d_out, d_or, d_on, d_ol, d_st));
   m->launches++;
   CK(cudaGetLastError());
