@@ -574,7 +574,9 @@ struct MidPar {
 //    for i < 1000; a sample is off every lattice plane when (R + D) mod 1 >= 2 D on all three axes, D = delta.
 // stats[1] += decided edges, stats[2] += edges seen, stats[3] += reference-order lookups of the decided edges (which
 // O.total_lookups receives as well).
+#ifndef CTP_MID_THREADS
 #define CTP_MID_THREADS 256
+#endif
 #ifndef CTP_MID_IPT
 #define CTP_MID_IPT 2
 #endif

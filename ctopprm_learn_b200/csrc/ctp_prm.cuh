@@ -1117,7 +1117,9 @@ template <int N> __device__ __forceinline__ void csr_reg_sort(unsigned (&v)[N]) 
 // tail) and the row's ascending ids land in shared memory, back to back in row order.  Phase 2, one thread per
 // ENTRY: the FP64 weight ||to - from|| (:369-371) from the staged own coordinates and one gathered neighbour, then
 // col / w go out in final order -- every global load and store of the kernel is coalesced except that one gather.
+#ifndef CTP_CSR_EMIT_ROWS
 #define CTP_CSR_EMIT_ROWS 128
+#endif
 
 template <int NS, typename XT>
 __global__ void __launch_bounds__(CTP_CSR_EMIT_ROWS)
