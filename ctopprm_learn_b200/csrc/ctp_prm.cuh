@@ -555,6 +555,7 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s
   const int cy = knn_cell_1d(me.y, g.loy, g.inv_h, g.dy);
   const int cz = knn_cell_1d(me.z, g.loz, g.inv_h, g.dz);
   const float lb = (float)(g.h * 0.999);  // rounding here only shifts which points take the wider search
+  const float gx = (me.x - g.lox) * g.inv_h, gy = (me.y - g.loy) * g.inv_h, gz = (me.z - g.loz) * g.inv_h;
   const int selfpos = (int)(t - q * n);
   int kept = 0, kept_prev = kept_in;  // kept counts the point itself as well (d2 = 0 always passes the filter)
   bool done = false;
@@ -566,10 +567,22 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s
     thr2 = wide * wide;
     kept = 0;
     const int xa = max(cx - R, 0), xb = min(cx + R, g.dx - 1);
+    // Pruning by the ball itself: a cell row (z, y) whose nearest face is farther than `wide` holds no survivor, and in
+    // the other rows only the cells the ball's chord reaches.  In cell units, with the point's own float grid coordinate
+    // (the expression the binning floors; a point binned into cell c has a coordinate in [c, c + 1), the last cell of an
+    // axis also what lies beyond it) and 10^-3 cells of margin for the float roundings of the binning and the distances.
+    const float wc = wide * g.inv_h * 1.0001f + 1e-3f, wc2 = wc * wc;
     for (int z = max(cz - R, 0); z <= min(cz + R, g.dz - 1); z++) {
+      const float az = fmaxf((z == cz ? 0.f : (z > cz ? (float)z - gz : gz - (float)(z + 1))) - 1e-3f, 0.f);
       for (int y = max(cy - R, 0); y <= min(cy + R, g.dy - 1); y++) {
+        const float ay = fmaxf((y == cy ? 0.f : (y > cy ? (float)y - gy : gy - (float)(y + 1))) - 1e-3f, 0.f);
+        const float rem = wc2 - (az * az + ay * ay);
+        if (!(rem > 0.f)) continue;
+        const float xr = sqrtf(rem);
+        const int xa2 = max(xa, min((int)floorf(gx - xr), g.dx - 1)), xb2 = min(xb, max((int)floorf(gx + xr), 0));
+        if (xa2 > xb2) continue;
         const int row = (z * g.dy + y) * g.dx;
-        const int pb = st[row + xa], pe = st[row + xb + 1];
+        const int pb = st[row + xa2], pe = st[row + xb2 + 1];
         for (int c = pb; c < pe; c++) {
           const float4 o = sq[c];
           const float ddx = me.x - o.x, ddy = me.y - o.y, ddz = me.z - o.z;
