@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
 // 2k in a ball of radius lb * cbrt(2k / kept)), at most (pass + 1) cells.  k_knn_direct runs pass 0
 // for every point and lists the sparse ones with their survivor count; k_knn_direct_list runs the
 // wider passes for the listed points only, so dense points never wait for sparse lanes.
-template <int K>
+template <int K, bool PRUNE>
 __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s_keep)[CTP_KNN_DIRECT_THREADS],
                                                  const float4 *__restrict__ sorted, int64_t n,
                                                  const KnnGrid *__restrict__ grids, int cell_stride,
@@ -567,20 +567,26 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s
     thr2 = wide * wide;
     kept = 0;
     const int xa = max(cx - R, 0), xb = min(cx + R, g.dx - 1);
-    // Pruning by the ball itself: a cell row (z, y) whose nearest face is farther than `wide` holds no survivor, and in
-    // the other rows only the cells the ball's chord reaches.  In cell units, with the point's own float grid coordinate
+    // Pruning by the ball itself (PRUNE: the wider passes over 125 or 343 cells -- on the 27 cells of pass 0 the extra
+    // arithmetic per row and the less uniform runs cost more than the cells saved: 1.72 against 1.67 ms on C2): a cell
+    // row (z, y) whose nearest face is farther than `wide` holds no survivor, and in the other rows only the cells the
+    // ball's chord reaches.  In cell units, with the point's own float grid coordinate
     // (the expression the binning floors; a point binned into cell c has a coordinate in [c, c + 1), the last cell of an
     // axis also what lies beyond it) and 10^-3 cells of margin for the float roundings of the binning and the distances.
     const float wc = wide * g.inv_h * 1.0001f + 1e-3f, wc2 = wc * wc;
     for (int z = max(cz - R, 0); z <= min(cz + R, g.dz - 1); z++) {
       const float az = fmaxf((z == cz ? 0.f : (z > cz ? (float)z - gz : gz - (float)(z + 1))) - 1e-3f, 0.f);
       for (int y = max(cy - R, 0); y <= min(cy + R, g.dy - 1); y++) {
-        const float ay = fmaxf((y == cy ? 0.f : (y > cy ? (float)y - gy : gy - (float)(y + 1))) - 1e-3f, 0.f);
-        const float rem = wc2 - (az * az + ay * ay);
-        if (!(rem > 0.f)) continue;
-        const float xr = sqrtf(rem);
-        const int xa2 = max(xa, min((int)floorf(gx - xr), g.dx - 1)), xb2 = min(xb, max((int)floorf(gx + xr), 0));
-        if (xa2 > xb2) continue;
+        int xa2 = xa, xb2 = xb;
+        if (PRUNE) {
+          const float ay = fmaxf((y == cy ? 0.f : (y > cy ? (float)y - gy : gy - (float)(y + 1))) - 1e-3f, 0.f);
+          const float rem = wc2 - (az * az + ay * ay);
+          if (!(rem > 0.f)) continue;
+          const float xr = sqrtf(rem);
+          xa2 = max(xa, min((int)floorf(gx - xr), g.dx - 1));
+          xb2 = min(xb, max((int)floorf(gx + xr), 0));
+          if (xa2 > xb2) continue;
+        }
         const int row = (z * g.dy + y) * g.dx;
         const int pb = st[row + xa2], pe = st[row + xb2 + 1];
         for (int c = pb; c < pe; c++) {
@@ -654,7 +660,7 @@ k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const 
   // positions [first, total) of the sorted array (first > 0: one GPU's slice of a query split over several)
   const int64_t t = first + blockIdx.x * (int64_t)CTP_KNN_DIRECT_THREADS + threadIdx.x;
   if (t >= total) return;
-  knn_direct_point<K>(t, threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out, 0, 0, 0,
+  knn_direct_point<K, false>(t, threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out, 0, 0, 0,
                       fb_list, fb_kept, fb_count);
 }
 
@@ -677,7 +683,7 @@ k_knn_direct_list(const float4 *__restrict__ sorted, int64_t n, const int32_t *_
     return;
   }
   for (int i = blockIdx.x * CTP_KNN_DIRECT_THREADS + threadIdx.x; i < cnt; i += gridDim.x * CTP_KNN_DIRECT_THREADS)
-    knn_direct_point<K>(list[i], threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out,
+    knn_direct_point<K, true>(list[i], threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out,
                         pass_lo, 2, list_kept ? list_kept[i] : 0, fb_list, nullptr, fb_count);
 }
 
