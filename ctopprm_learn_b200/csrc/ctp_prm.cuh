@@ -537,7 +537,10 @@ __global__ void __launch_bounds__(128) k_knn_search(const float4 *__restrict__ s
 // 2k in a ball of radius lb * cbrt(2k / kept)), at most (pass + 1) cells.  k_knn_direct runs pass 0
 // for every point and lists the sparse ones with their survivor count; k_knn_direct_list runs the
 // wider passes for the listed points only, so dense points never wait for sparse lanes.
-template <int K, bool PRUNE>
+#ifndef CTP_KNN_PRUNE0
+#define CTP_KNN_PRUNE0 0  // pruning in pass 0: 0 none (2.31 ms per C2 step), 1 rows and x-ranges (2.37), 2 corner rows only (2.34)
+#endif
+template <int K, int PRUNE>
 __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s_keep)[CTP_KNN_DIRECT_THREADS],
                                                  const float4 *__restrict__ sorted, int64_t n,
                                                  const KnnGrid *__restrict__ grids, int cell_stride,
@@ -578,7 +581,13 @@ __device__ __forceinline__ void knn_direct_point(int64_t t, int tid, int32_t (*s
       const float az = fmaxf((z == cz ? 0.f : (z > cz ? (float)z - gz : gz - (float)(z + 1))) - 1e-3f, 0.f);
       for (int y = max(cy - R, 0); y <= min(cy + R, g.dy - 1); y++) {
         int xa2 = xa, xb2 = xb;
-        if (PRUNE) {
+        if (PRUNE == 2) {  // pass 0: only the four corner rows are tested, whole rows
+          if (z != cz && y != cy) {
+            const float ay = fmaxf((y > cy ? (float)y - gy : gy - (float)(y + 1)) - 1e-3f, 0.f);
+            if (!(az * az + ay * ay < wc2)) continue;
+          }
+        }
+        if (PRUNE == 1) {
           const float ay = fmaxf((y == cy ? 0.f : (y > cy ? (float)y - gy : gy - (float)(y + 1))) - 1e-3f, 0.f);
           const float rem = wc2 - (az * az + ay * ay);
           if (!(rem > 0.f)) continue;
@@ -660,7 +669,7 @@ k_knn_direct(const float4 *__restrict__ sorted, int64_t n, int64_t total, const 
   // positions [first, total) of the sorted array (first > 0: one GPU's slice of a query split over several)
   const int64_t t = first + blockIdx.x * (int64_t)CTP_KNN_DIRECT_THREADS + threadIdx.x;
   if (t >= total) return;
-  knn_direct_point<K, false>(t, threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out, 0, 0, 0,
+  knn_direct_point<K, CTP_KNN_PRUNE0>(t, threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out, 0, 0, 0,
                       fb_list, fb_kept, fb_count);
 }
 
@@ -683,7 +692,7 @@ k_knn_direct_list(const float4 *__restrict__ sorted, int64_t n, const int32_t *_
     return;
   }
   for (int i = blockIdx.x * CTP_KNN_DIRECT_THREADS + threadIdx.x; i < cnt; i += gridDim.x * CTP_KNN_DIRECT_THREADS)
-    knn_direct_point<K, true>(list[i], threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out,
+    knn_direct_point<K, 1>(list[i], threadIdx.x, s_keep, sorted, n, grids, cell_stride, cell_start, idx, idx_stride, d2out,
                         pass_lo, 2, list_kept ? list_kept[i] : 0, fb_list, nullptr, fb_count);
 }
 
